@@ -1,0 +1,238 @@
+/*
+ * grlcuda.h — C ABI of libgrlcuda.so, the B200-native batched Generals.io turn engine.
+ *
+ * Drop-in boundary for the reference's turn-processing hot path.  The reference
+ * (mitchelldurbincs/GeneralsReinforcementLearning, Go) has no FFI of its own; the
+ * seam this ABI replaces is the public surface of `game.Engine`:
+ *
+ *   grl_create / grl_reset_*   <- NewEngine            internal/game/engine.go:62-71,
+ *                                                      engine_initializer.go:34-87,218-225
+ *   grl_step / grl_step_fused  <- Engine.Step          internal/game/engine.go:75
+ *                                 (TurnProcessor.ProcessTurn, turn_processor.go:29-77)
+ *   grl_mask                   <- Engine.GetLegalActionMask   engine.go:271-280
+ *                                 Serializer.GenerateActionMask experience/serializer.go:112-176
+ *   grl_visibility             <- Engine.ComputePlayerVisibility visibility.go:153,
+ *                                 visibility_optimized.go:166-195
+ *   grl_observe                <- Serializer.StateToTensor    experience/serializer.go:37-109
+ *                                 CalculateRewardWithConfig   experience/rewards.go:45-85
+ *                                 Engine.IsGameOver/GetWinner engine.go:198,248
+ *   grl_get_state/grl_set_state<- Engine.GameState()/GameState.Clone  engine.go:197, state.go:37-70
+ *
+ * One grl_env = B independent games ("envs") resident on ONE CUDA device as
+ * struct-of-arrays slabs, stepped in lockstep on one stream.  The handle is not
+ * internally locked (the reference serialises each game under one mutex,
+ * internal/grpc/gameserver/game_manager.go:25).  Every data pointer is
+ * caller-allocated and never retained past the call; pointers may be host or
+ * device memory (detected with cudaPointerGetAttributes; host buffers are staged
+ * through library scratch and copied on the env's stream, and the call returns
+ * after the copy completes).  Calls with device buffers are asynchronous on the
+ * env's stream; use grl_sync().
+ *
+ * The same ABI, prefixed grlo_, is exported by the CPU oracle (oracle/) — test
+ * infrastructure only.
+ */
+#ifndef GRLCUDA_H
+#define GRLCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRL_ABI_VERSION 1
+
+#define GRL_MAX_DIM 32      /* width, height <= 32: one 32-bit word spans a board row */
+#define GRL_MAX_PLAYERS 8   /* reference bitfield allows 32 (core/board.go:11); configs need <= 4 */
+#define GRL_MAX_ACTIONS 12  /* action slots per env per step: Go's sort.Slice is an insertion
+                               sort (stable) only for n <= 12 (processor/action_processor.go:39) */
+#define GRL_OBS_CHANNELS 9  /* experience/serializer.go:9-20 */
+
+/* ---- call status ------------------------------------------------------- */
+enum {
+  GRL_OK = 0,
+  GRL_ERR_INVALID_ARG = -1,
+  GRL_ERR_CUDA = -2,
+  GRL_ERR_NOMEM = -3,
+  GRL_ERR_MAPGEN = -4, /* mapgen could not place a general (mapgen/generator.go:252) */
+  GRL_ERR_UNSUPPORTED = -5
+};
+
+/* ---- per-env step error plane (numbers = proto/common/v1/common.proto:39-55,
+ *      sentinels internal/game/core/errors.go:8-17) ------------------------ */
+enum {
+  GRL_STEP_OK = 0,
+  GRL_STEP_INVALID_COORDINATES = 1,
+  GRL_STEP_NOT_ADJACENT = 2,
+  GRL_STEP_NOT_OWNED = 3,
+  GRL_STEP_INSUFFICIENT_ARMY = 4,
+  GRL_STEP_GAME_OVER = 5,
+  GRL_STEP_MOVE_TO_SELF = 7,
+  GRL_STEP_TARGET_IS_MOUNTAIN = 8,
+  GRL_STEP_ARMY_OVERFLOW = 100 /* not a reference error: a tile army left the uint16 plane's
+                                  range; the value was saturated (never wraps silently) */
+};
+
+/* ---- tile types (internal/game/core/board.go:20-26) --------------------- */
+enum { GRL_TILE_NORMAL = 0, GRL_TILE_GENERAL = 1, GRL_TILE_CITY = 2, GRL_TILE_MOUNTAIN = 3 };
+#define GRL_NEUTRAL (-1)
+
+/* ---- one move (core/action.go:23-35).  8 bytes, [B][max_actions] per step.
+ * present == 0 is an empty slot (the reference passes a shorter slice).
+ * Slots of one env are applied in the order a stable sort by player_id gives. */
+typedef struct grl_action {
+  int8_t player_id;
+  int8_t from_x, from_y;
+  int8_t to_x, to_y;
+  uint8_t move_all; /* 1: leave one behind; 0: move half, floor, min 1 (core/movement.go:40-49) */
+  uint8_t present;
+  uint8_t reserved;
+} grl_action;
+
+/* ---- reward weights (experience/rewards.go:9-37) ------------------------ */
+typedef struct grl_reward_config {
+  float win_game, lose_game;
+  float capture_city, lose_city;
+  float capture_general, lose_general;
+  float territory_gained, territory_lost; /* territory_lost / army_lost are carried but, as in */
+  float army_gained, army_lost;           /* the reference, never read by the reward sum       */
+  float army_advantage;
+} grl_reward_config;
+
+typedef struct grl_config {
+  int32_t num_envs;           /* B games on this device */
+  int32_t width, height;      /* 1..GRL_MAX_DIM */
+  int32_t num_players;        /* 1..GRL_MAX_PLAYERS */
+  int32_t device;             /* CUDA ordinal */
+  int32_t max_actions;        /* action slots per env per step, 1..GRL_MAX_ACTIONS */
+  int32_t fog_of_war;         /* engine_initializer.go:118 hard-wires 1 */
+  int32_t env_id_base;        /* global id of env 0 (shard offset); keys the synthetic policy */
+  /* internal/config/config.go:198-209 */
+  int32_t city_ratio;             /* 20 */
+  int32_t city_start_army;        /* 40 */
+  int32_t min_general_spacing;    /* 5 */
+  int32_t production_general;     /* 1 */
+  int32_t production_city;        /* 1 */
+  int32_t production_normal;      /* 1 */
+  int32_t normal_growth_interval; /* 25 */
+  int32_t host_threads;       /* host mapgen / oracle stepping threads; 0 = all cores */
+  grl_reward_config reward;
+} grl_config;
+
+typedef struct grl_env grl_env;
+
+/* ---- mask read-out variants -------------------------------- */
+enum {
+  GRL_MASK_ENGINE_URDL = 0,     /* rules/legal_moves.go:19-73: bytes [B][P][N*4], list-based, army>1 */
+  GRL_MASK_SERIALIZER_UDLR = 1, /* experience/serializer.go:112-176: bytes [B][P][N*4], ownership scan */
+  GRL_MASK_ENGINE_URDL_BITS = 2,/* packed: uint32 [B][P][ceil(4N/32)], bit i of the flat []bool */
+  GRL_MASK_ENGINE_HALF_BITS = 3 /* packed tile x 4 dirs x {full,half}: uint32 [B][P][2][ceil(4N/32)];
+                                   a half move is legal iff the full move is (core/action.go:56-105) */
+};
+
+/* ---- fused step outputs; any NULL member is skipped --------------------- */
+typedef struct grl_step_outputs {
+  float *obs;            /* [B][P][9][H][W]  StateToTensor of the post-step state        */
+  uint32_t *mask_bits;   /* [B][P][ceil(4N/32)] GRL_MASK_ENGINE_URDL_BITS                */
+  float *reward;         /* [B][P]  CalculateReward(prev, curr, p)                        */
+  uint8_t *done;         /* [B]     Engine.IsGameOver()                                   */
+  int8_t *winner;        /* [B]     Engine.GetWinner()                                    */
+  uint8_t *step_error;   /* [B]     GRL_STEP_* of this step                               */
+  int32_t *action_index; /* [B][P]  Serializer.ActionToIndex of the player's submitted move
+                                    (UDLR order, serializer.go:179-198); -1 when the player
+                                    submitted none or the turn aborted (no experience)    */
+} grl_step_outputs;
+
+/* ---- full state planes for parity / replay / checkpoint (host memory).
+ * Arrays are [count][...]; NULL members are skipped. ----------------------- */
+typedef struct grl_state_planes {
+  int32_t *owner;        /* [count][N]  -1 neutral                                   */
+  int32_t *army;         /* [count][N]                                               */
+  int32_t *type;         /* [count][N]  GRL_TILE_*                                   */
+  uint32_t *visible;     /* [count][N]  Tile.VisibleBitfield (bit p)                 */
+  uint8_t *owned;        /* [count][P][N] membership in Player.OwnedTiles (cached!)  */
+  uint8_t *changed;      /* [count][N]  GameState.ChangedTiles                       */
+  uint8_t *vis_changed;  /* [count][N]  GameState.VisibilityChangedTiles             */
+  int32_t *turn;         /* [count]                                                  */
+  int32_t *game_over;    /* [count]     Engine.gameOver                              */
+  int32_t *winner;       /* [count]                                                  */
+  int32_t *alive;        /* [count][P]                                               */
+  int32_t *army_count;   /* [count][P]  Player.ArmyCount (over the cached list)      */
+  int32_t *general_idx;  /* [count][P]  Player.GeneralIdx (highest general-type tile in the
+                                        list; the reference's tie-break is Go map order) */
+  int32_t *step_error;   /* [count]                                                  */
+} grl_state_planes;
+
+/* flags for grl_step / grl_step_fused */
+enum {
+  GRL_STEP_FLAG_NONE = 0,
+  GRL_STEP_FLAG_RANDOM_POLICY = 1 /* ignore `actions`; every alive player plays one move drawn
+                                     uniformly from its engine mask with the counter-based
+                                     generator keyed (policy_seed, global env id, turn, player) */
+};
+
+int grl_abi_version(void);
+const char *grl_status_string(int status);
+const char *grl_last_error(void); /* thread-local detail of the last failing call */
+
+/* Fill *cfg with the reference defaults (config.go:198-209, rewards.go:23-37). */
+int grl_default_config(grl_config *cfg);
+
+int grl_create(const grl_config *cfg, grl_env **out);
+int grl_destroy(grl_env *env);
+int grl_sync(grl_env *env);
+int grl_get_config(const grl_env *env, grl_config *out);
+
+/* Reset `n` envs (env_ids NULL = all B in order) from seeds: map i is what
+ * mapgen.NewGenerator(DefaultMapConfig(W,H,P), rand.New(rand.NewSource(seeds[i]))).GenerateMap()
+ * yields (mapgen/generator.go:25-253), generated on the host and uploaded once; then the
+ * turn-0 full stats + full fog + game-over check of engine_initializer.go:218-225. */
+int grl_reset_seeded(grl_env *env, const int32_t *env_ids, int32_t n, const int64_t *seeds);
+
+/* Reset from caller-built boards (the reference's tests build boards by hand):
+ * owner/army/type are host int32 [n][N]; visible bits start at 0. */
+int grl_reset_boards(grl_env *env, const int32_t *env_ids, int32_t n, const int32_t *owner,
+                     const int32_t *army, const int32_t *type);
+
+/* Host-only: generate one map exactly as the reference does (no device work). */
+int grl_mapgen(const grl_config *cfg, int64_t seed, int32_t *owner, int32_t *army, int32_t *type);
+
+/* One ProcessTurn for every env.  actions: [B][max_actions] (host or device), may be NULL
+ * (every slot empty).  Stepping a finished env mutates nothing and records
+ * GRL_STEP_GAME_OVER (turn_processor.go:95-113). */
+int grl_step(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t policy_seed);
+
+/* ProcessTurn + all read-outs in one pass over the state (the hot path). */
+int grl_step_fused(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t policy_seed,
+                   const grl_step_outputs *out);
+
+/* Read-outs of the current state (no step).  reward is the one computed by the last step
+ * (0 after reset). */
+int grl_observe(grl_env *env, const grl_step_outputs *out);
+int grl_mask(grl_env *env, int variant, void *out);
+/* visible/fog: bytes [B][P][N] (PlayerVisibility.VisibleTiles / FogTiles). */
+int grl_visibility(grl_env *env, uint8_t *visible, uint8_t *fog);
+
+/* Draw the synthetic policy's actions for the current state into `actions`
+ * ([B][max_actions], slot p = player p's move, empty when it has none). */
+int grl_sample_actions(grl_env *env, uint64_t policy_seed, grl_action *actions);
+
+int grl_get_state(grl_env *env, int32_t first_env, int32_t count, const grl_state_planes *out);
+int grl_set_state(grl_env *env, int32_t first_env, int32_t count, const grl_state_planes *in);
+
+/* 64-bit digest per env of the full game state (tiles, lists, sets, header); identical
+ * function in the oracle, used for parity at sizes too large to copy back. out: [B]. */
+int grl_state_hash(grl_env *env, uint64_t *out);
+/* Digest of a float/word buffer laid out [rows][row_words] (device or host pointer),
+ * one uint64 per row; used to compare observation planes at scale. */
+int grl_buffer_hash(grl_env *env, const void *buf, size_t row_words, int32_t rows, uint64_t *out);
+
+/* Episode statistics since create: [0] env-steps executed (not idle), [1] error-turn steps,
+ * [2] games finished, [3] steps attempted on finished envs. */
+int grl_stats(grl_env *env, uint64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRLCUDA_H */
