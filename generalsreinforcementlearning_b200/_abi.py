@@ -152,6 +152,7 @@ ABI_FUNCTIONS = {
     "state_hash": (C.c_int, [C.c_void_p, C.c_void_p]),
     "buffer_hash": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]),
     "stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "launch_count": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 

@@ -1,0 +1,1241 @@
+// grl_kernels.cu — sm_100a kernels of the batched Generals.io turn engine.
+//
+// One warp owns one game.  Every boolean plane of a game (ownership per player, the
+// reference's cached OwnedTiles lists, visibility per player, the changed / visibility-
+// changed tile sets, terrain) is an N-bit LINEAR bitmask, N = W*H <= 1024, held as one
+// 32-bit word per lane.  Stencils (3x3 fog dilation, the 5x5 "affected players" probe,
+// the four move directions) are funnel shifts across neighbouring lanes' words; set sizes
+// are popc + REDUX.  Only the armies are a per-tile plane (uint16, staged in shared memory).
+//
+// Reference semantics (file:line into /root/reference):
+//   turn order          internal/game/turn_processor.go:29-77,124-135
+//   actions             internal/game/processor/action_processor.go:36-99,
+//                       internal/game/core/action.go:56-105, core/movement.go:23-118
+//   eliminations        internal/game/engine.go:80-152
+//   production          internal/game/production_manager.go:26-101
+//   cached lists/stats  internal/game/stats.go:8-144
+//   fog of war          internal/game/visibility_optimized.go:16-163
+//   win check           internal/game/rules/win_conditions.go:21-57
+//   legal mask          internal/game/rules/legal_moves.go:19-73
+//   observation         internal/experience/serializer.go:37-109
+//   reward              internal/experience/rewards.go:45-175
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/grlcuda.h"
+#include "grl_launch.h"
+#include "grl_layout.h"
+
+#define FULL 0xffffffffu
+#define GRL_WARPS_PER_CTA 8
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ uint64_t policy_draw(uint64_t seed, uint64_t env, uint64_t turn, uint64_t player) {
+  uint64_t x = mix64(seed ^ (env * 0xD6E8FEB86659FD93ULL));
+  return mix64(x ^ (turn * 0xA0761D6478BD642FULL) ^ (player << 56));
+}
+
+__device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// float32(army) / 1000.0f, correctly rounded (== IEEE division; verified for every army value):
+// q = RN(x*r), rem = RN(x - q*1000) exact by FMA, q' = RN(q + rem*r)   with r = RN(1/1000).
+__device__ __forceinline__ float army_frac(uint32_t army) {
+  const float r = 1.0f / 1000.0f;
+  float x = (float)army;
+  float q = __fmul_rn(x, r);
+  float rem = __fmaf_rn(-q, 1000.0f, x);
+  float v = __fmaf_rn(rem, r, q);
+  return army >= 1000u ? 1.0f : v;  // serializer.go:84-88 clip
+}
+
+// Per-lane geometry words and linear-bitmask stencils.
+struct Geo {
+  uint32_t valid, nc0, ncl;  // tiles that exist / x != 0 / x != W-1, word `lane`
+  int W;
+  int lane;
+};
+
+__device__ __forceinline__ uint32_t word_prev(uint32_t v, int lane) {
+  uint32_t p = __shfl_up_sync(FULL, v, 1);
+  return lane == 0 ? 0u : p;
+}
+__device__ __forceinline__ uint32_t word_next(uint32_t v, int lane) {
+  uint32_t n = __shfl_down_sync(FULL, v, 1);
+  return lane == 31 ? 0u : n;
+}
+// bit t of result = bit (t-k) of v
+__device__ __forceinline__ uint32_t shl_bits(uint32_t v, int k, int lane) {
+  return __funnelshift_lc(word_prev(v, lane), v, k);
+}
+// bit t of result = bit (t+k) of v
+__device__ __forceinline__ uint32_t shr_bits(uint32_t v, int k, int lane) {
+  return __funnelshift_rc(v, word_next(v, lane), k);
+}
+// in-bounds 3x3 neighbourhood union (visibility_optimized.go:9-13,118-128)
+__device__ __forceinline__ uint32_t dilate3(uint32_t v, const Geo &g) {
+  uint32_t h = v | (shl_bits(v, 1, g.lane) & g.nc0) | (shr_bits(v, 1, g.lane) & g.ncl);
+  uint32_t r = h | shl_bits(h, g.W, g.lane) | shr_bits(h, g.W, g.lane);
+  return r & g.valid;
+}
+
+// bits 0..7 of b spread to bit positions 0,4,8,...,28
+__device__ __forceinline__ uint32_t spread8(uint32_t b) {
+  uint32_t x = b & 0xffu;
+  x = (x | (x << 12)) & 0x000F000Fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x;
+}
+
+// Views into one game's slab staged in shared memory.
+struct SlabView {
+  uint32_t *hdr, *own, *list, *vis, *chg, *vch;
+  uint16_t *army;
+  const uint32_t *M, *C, *G;
+};
+
+__device__ __forceinline__ SlabView make_view(uint32_t *s, const uint32_t *st, const GrlLayout &L) {
+  SlabView v;
+  v.hdr = s;
+  v.own = s + L.off_own;
+  v.list = s + L.off_list;
+  v.vis = s + L.off_vis;
+  v.chg = s + L.off_changed;
+  v.vch = s + L.off_vchg;
+  v.army = reinterpret_cast<uint16_t *>(s + L.off_army);
+  v.M = st;
+  v.C = st + L.NW;
+  v.G = st + 2 * L.NW;
+  return v;
+}
+
+// sum of army over the tiles of a linear bitmask (word `lane` in x); slow path helper
+__device__ __forceinline__ int sum_army_over(uint32_t x, const uint16_t *army, int NW, int N, int lane) {
+  int acc = 0;
+  for (int i = 0; i < NW; i++) {
+    uint32_t xw = __shfl_sync(FULL, x, i);
+    int t = 32 * i + lane;
+    int a = (t < N) ? (int)army[t] : 0;
+    acc += ((xw >> lane) & 1u) ? a : 0;
+  }
+  return __reduce_add_sync(FULL, acc);
+}
+
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) for the state slabs -------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// cached-list statistics (internal/game/stats.go:8-144) on register words.
+// armyCount[p] = trueArmy[p] - (armies on tiles p owns that are missing from its list).
+// ---------------------------------------------------------------------------------------
+template <int PT>
+__device__ __forceinline__ void stats_update(const GrlKParams &prm, SlabView &S, const uint32_t (&own)[PT],
+                                             uint32_t (&lst)[PT], uint32_t chg, uint32_t G, uint32_t &alive, int lane,
+                                             bool force_full) {
+  int c = __reduce_add_sync(FULL, __popc(chg));
+  if (c == 0 && !force_full) return;  // stats.go:11-15 (turn > 0 inside a step)
+  bool full = force_full || c > prm.N / 5;  // stats.go:20-25
+#pragma unroll
+  for (int p = 0; p < PT; p++) {
+    if (p < prm.P) {
+      lst[p] = full ? own[p] : (own[p] & (lst[p] | chg));
+      uint32_t orphan = own[p] & ~lst[p];
+      int true_army = (int)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY];
+      int corr = 0;
+      if (__any_sync(FULL, orphan != 0u)) corr = sum_army_over(orphan, S.army, prm.NW, prm.N, lane);
+      uint32_t gen = lst[p] & G;
+      int gi = gen ? (32 * lane + 31 - __clz(gen)) : -1;
+      gi = __reduce_max_sync(FULL, gi);
+      if (lane == 0) {
+        S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ARMY_COUNT] = (uint32_t)(true_army - corr);
+        S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_GENERAL_IDX] = (uint32_t)gi;
+      }
+      alive = gi >= 0 ? (alive | (1u << p)) : (alive & ~(1u << p));
+    }
+  }
+  __syncwarp();
+}
+
+// engine legal-move direction masks for one player (rules/legal_moves.go:19-73):
+// a tile in the cached list, still owned, army > 1, target in bounds and not a mountain.
+struct DirMasks {
+  uint32_t up, right, down, left;
+};
+__device__ __forceinline__ DirMasks dir_targets(uint32_t M, const Geo &g) {
+  uint32_t free_ = g.valid & ~M;
+  DirMasks d;
+  d.up = shl_bits(free_, g.W, g.lane);            // tile t-W exists and is not a mountain
+  d.down = shr_bits(free_, g.W, g.lane);          // tile t+W
+  d.left = shl_bits(free_, 1, g.lane) & g.nc0;    // tile t-1, x != 0
+  d.right = shr_bits(free_, 1, g.lane) & g.ncl;   // tile t+1, x != W-1
+  return d;
+}
+
+// army > 1 per tile as a linear bitmask (word `lane`)
+__device__ __forceinline__ uint32_t army_gt1_mask(const uint16_t *army, int NW, int N, int lane) {
+  uint32_t mine = 0;
+  for (int i = 0; i < NW; i++) {
+    int t = 32 * i + lane;
+    bool gt = (t < N) && army[t] > 1;
+    uint32_t w = __ballot_sync(FULL, gt);
+    if (lane == i) mine = w;
+  }
+  return mine;
+}
+
+struct PackedAction {  // grl_action as one 64-bit word (little endian field order)
+  uint32_t lo, hi;
+  __device__ __forceinline__ int player() const { return (int)(int8_t)(lo & 0xff); }
+  __device__ __forceinline__ int fx() const { return (int)(int8_t)((lo >> 8) & 0xff); }
+  __device__ __forceinline__ int fy() const { return (int)(int8_t)((lo >> 16) & 0xff); }
+  __device__ __forceinline__ int tx() const { return (int)(int8_t)((lo >> 24) & 0xff); }
+  __device__ __forceinline__ int ty() const { return (int)(int8_t)(hi & 0xff); }
+  __device__ __forceinline__ bool move_all() const { return ((hi >> 8) & 0xff) != 0; }
+  __device__ __forceinline__ bool present() const { return ((hi >> 16) & 0xff) != 0; }
+};
+
+__device__ __forceinline__ PackedAction pack_action(int player, int fx, int fy, int tx, int ty, bool move_all) {
+  PackedAction a;
+  a.lo = (uint32_t)(player & 0xff) | ((uint32_t)(fx & 0xff) << 8) | ((uint32_t)(fy & 0xff) << 16) |
+         ((uint32_t)(tx & 0xff) << 24);
+  a.hi = (uint32_t)(ty & 0xff) | ((move_all ? 1u : 0u) << 8) | (1u << 16);
+  return a;
+}
+
+// Synthetic policy: player p draws uniformly from the set bits of its engine mask
+// in flat-index order (tile-major, dirs U,R,D,L).  Warp-uniform result.
+__device__ __forceinline__ PackedAction sample_policy_action(const GrlKParams &prm, const DirMasks &dm, uint32_t src,
+                                                             int p, uint64_t env_global, uint32_t turn, const Geo &g) {
+  PackedAction none;
+  none.lo = none.hi = 0;
+  uint32_t U = src & dm.up, R = src & dm.right, D = src & dm.down, Lm = src & dm.left;
+  int cnt = __popc(U) + __popc(R) + __popc(D) + __popc(Lm);
+  int total = __reduce_add_sync(FULL, cnt);
+  if (total == 0) return none;
+  uint64_t r = policy_draw(prm.policy_seed, env_global, (uint64_t)turn, (uint64_t)p);
+  int k = (int)((uint32_t)r % (uint32_t)total);
+  int incl = cnt;  // inclusive prefix sum over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(FULL, incl, o);
+    if (g.lane >= o) incl += v;
+  }
+  int excl = incl - cnt;
+  bool mine = (k >= excl) && (k < incl);
+  int kk = k - excl;
+  // smallest bit b with count(bits <= b) > kk, by binary search on the prefix count
+  int b = 0;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    int cand = b + step;                      // test whether count(bits < cand) <= kk
+    uint32_t m = (1u << cand) - 1u;           // cand in 1..31
+    int c = __popc(U & m) + __popc(R & m) + __popc(D & m) + __popc(Lm & m);
+    if (c <= kk) b = cand;
+  }
+  uint32_t below = (1u << b) - 1u;
+  int rem = kk - (__popc(U & below) + __popc(R & below) + __popc(D & below) + __popc(Lm & below));
+  uint32_t nib = ((U >> b) & 1u) | (((R >> b) & 1u) << 1) | (((D >> b) & 1u) << 2) | (((Lm >> b) & 1u) << 3);
+  int dir = 0;
+#pragma unroll
+  for (int d = 0; d < 4; d++) {
+    if ((nib >> d) & 1u) {
+      if (rem == 0) dir = d;
+      rem--;
+    }
+  }
+  int packed = mine ? ((32 * g.lane + b) * 4 + dir) : 0;
+  uint32_t who = __ballot_sync(FULL, mine);
+  packed = __shfl_sync(FULL, packed, __ffs(who) - 1);
+  int tile = packed >> 2;
+  dir = packed & 3;
+  int fx = tile % prm.W, fy = tile / prm.W;
+  int tx = fx + (dir == 1) - (dir == 3);
+  int ty = fy + (dir == 2) - (dir == 0);
+  return pack_action(p, fx, fy, tx, ty, ((r >> 32) & 1ULL) != 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// The fused turn kernel.  DO_STEP: ProcessTurn.  DO_OUT: observation / mask / reward / done.
+// ---------------------------------------------------------------------------------------
+template <int PT, bool DO_STEP, bool DO_OUT>
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
+    grl_turn_kernel(const __grid_constant__ GrlKParams prm) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ __align__(8) uint64_t s_bar[GRL_WARPS_PER_CTA];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GrlLayout &L = prm.L;
+  const int P = prm.P, NW = prm.NW, N = prm.N, W = prm.W;
+  const int act_words = 2 * GRL_MAX_ACTIONS;
+  const int per_warp = L.slab_words + L.static_words + act_words;
+  uint32_t *s = smem + warp * per_warp;
+  uint32_t *st = s + L.slab_words;
+  uint32_t *s_act = st + L.static_words;
+  SlabView S = make_view(s, st, L);
+
+  Geo g;
+  g.lane = lane;
+  g.W = W;
+  g.valid = prm.geom[lane];
+  g.nc0 = prm.geom[32 + lane];
+  g.ncl = prm.geom[64 + lane];
+  const bool act_lane = lane < NW;
+
+  if (prm.use_tma && lane == 0) {
+    mbar_init(&s_bar[warp], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t tma_phase = 0;
+
+  for (int game = blockIdx.x * GRL_WARPS_PER_CTA + warp; game < prm.B; game += gridDim.x * GRL_WARPS_PER_CTA) {
+    uint32_t *gslab = prm.state + (size_t)game * L.slab_words;
+    const uint32_t *gstat = prm.statics + (size_t)game * L.static_words;
+
+    // ---- stage the slab in shared memory ---------------------------------------------
+    if (prm.use_tma) {
+      fence_proxy_async_smem();  // generic-proxy accesses of the previous game precede the bulk write
+      __syncwarp();
+      if (lane == 0) {
+        mbar_expect_tx(&s_bar[warp], (uint32_t)(L.slab_words + L.static_words) * 4u);
+        tma_load(s, gslab, (uint32_t)L.slab_words * 4u, &s_bar[warp]);
+        tma_load(st, gstat, (uint32_t)L.static_words * 4u, &s_bar[warp]);
+      }
+      mbar_wait(&s_bar[warp], tma_phase);
+      tma_phase ^= 1u;
+    } else {
+      const uint4 *src = reinterpret_cast<const uint4 *>(gslab);
+      uint4 *dst = reinterpret_cast<uint4 *>(s);
+      for (int k = lane; k < L.slab_words / 4; k += 32) dst[k] = src[k];
+      const uint4 *src2 = reinterpret_cast<const uint4 *>(gstat);
+      uint4 *dst2 = reinterpret_cast<uint4 *>(st);
+      for (int k = lane; k < L.static_words / 4; k += 32) dst2[k] = __ldg(src2 + k);
+      __syncwarp();
+    }
+
+    // ---- mask words into registers -----------------------------------------------------
+    uint32_t own[PT], lst[PT], vis[PT], own_prev[PT];
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      bool on = act_lane && p < P;
+      own[p] = on ? S.own[p * NW + lane] : 0u;
+      lst[p] = on ? S.list[p * NW + lane] : 0u;
+      vis[p] = on ? S.vis[p * NW + lane] : 0u;
+      own_prev[p] = own[p];
+    }
+    uint32_t chg = act_lane ? S.chg[lane] : 0u;
+    uint32_t vch = act_lane ? S.vch[lane] : 0u;
+    const uint32_t M = act_lane ? S.M[lane] : 0u;
+    const uint32_t C = act_lane ? S.C[lane] : 0u;
+    const uint32_t G = act_lane ? S.G[lane] : 0u;
+
+    uint32_t turn = S.hdr[GRL_HDR_TURN];
+    uint32_t flags = S.hdr[GRL_HDR_FLAGS];
+    uint32_t alive = flags & 0xffu;
+    bool over = (flags & GRL_FLAG_OVER) != 0;
+    uint32_t err = 0;
+    bool stepped = false;
+    int prev_true_army[PT];
+#pragma unroll
+    for (int p = 0; p < PT; p++)
+      prev_true_army[p] = p < P ? (int)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY] : 0;
+
+    if (DO_STEP) {
+      if (over) {
+        // turn_processor.go:95-113: ErrGameOver, nothing mutated
+        err = GRL_STEP_GAME_OVER;
+        if (lane == 0) {
+          S.hdr[GRL_HDR_REJECTED] += 1;
+          for (int p = 0; p < P; p++) {
+            S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_REWARD] = 0u;
+            S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ACTION_INDEX] = 0xffffffffu;
+          }
+        }
+      } else {
+        stepped = true;
+        const uint32_t turn_before = turn;
+        turn += 1;  // turn_processor.go:125
+
+        // ---- the synthetic policy reads the PRE-turn state (all players at once) ----------
+        const bool use_policy = (prm.flags & GRL_STEP_FLAG_RANDOM_POLICY) != 0;
+        if (lane < GRL_MAX_ACTIONS) {
+          s_act[2 * lane] = 0u;
+          s_act[2 * lane + 1] = 0u;
+        }
+        __syncwarp();
+        if (use_policy) {
+          uint32_t gt1 = army_gt1_mask(S.army, NW, N, lane);
+          DirMasks dm = dir_targets(M, g);
+#pragma unroll
+          for (int p = 0; p < PT; p++) {
+            if (p < P && p < prm.A) {
+              uint32_t src = ((alive >> p) & 1u) ? (lst[p] & own[p] & gt1) : 0u;
+              PackedAction a = sample_policy_action(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn_before, g);
+              if (lane == 0) {
+                s_act[2 * p] = a.lo;
+                s_act[2 * p + 1] = a.hi;
+              }
+            }
+          }
+        } else if (prm.actions != nullptr) {
+          if (lane < prm.A) {
+            const uint2 *ga = reinterpret_cast<const uint2 *>(prm.actions) + (size_t)game * prm.A;
+            uint2 a = ga[lane];
+            s_act[2 * lane] = a.x;
+            s_act[2 * lane + 1] = a.y;
+          }
+        }
+
+        // ---- fog of war, from LAST turn's vchg and the CURRENT lists (Q1) -----------------
+        if (prm.fog) {
+          int nv = __reduce_add_sync(FULL, __popc(vch));
+          if (nv > N / 10) {  // visibility_optimized.go:22-25 -> full :33-53
+#pragma unroll
+            for (int p = 0; p < PT; p++)
+              if (p < P) vis[p] = ((alive >> p) & 1u) ? dilate3(lst[p], g) : 0u;
+          } else if (nv > 0) {  // incremental :56-97
+            uint32_t d3 = dilate3(vch, g);
+            uint32_t d5 = dilate3(d3, g);
+#pragma unroll
+            for (int p = 0; p < PT; p++) {
+              if (p < P) {
+                bool affected = __any_sync(FULL, (own[p] & d5) != 0u);  // owners read NOW (:100-115)
+                vis[p] &= ~d3;                                          // all players' bits cleared (:131-149)
+                if (affected && ((alive >> p) & 1u)) vis[p] |= dilate3(lst[p], g);
+              }
+            }
+          }
+        }
+        // turn_processor.go:129-134
+        chg = 0u;
+        vch = 0u;
+        if (act_lane) {
+          S.chg[lane] = 0u;
+          S.vch[lane] = 0u;
+        }
+        __syncwarp();
+
+        // ---- actions: serial by definition, one lane, on the shared-memory slab -----------
+        uint32_t ord_lo = 0, ord_hi = 0;  // up to 8 orders, one byte each: eliminated | capturer<<4
+        int n_orders = 0;
+        if (lane == 0) {
+          uint32_t processed = 0;
+          uint32_t overflow = 0;
+          const uint32_t alive_start = alive;  // action_processor.go:56-60 reads Alive as of now
+          int aidx[PT];
+#pragma unroll
+          for (int p = 0; p < PT; p++) aidx[p] = -1;
+          // stable sort by player id == for each id ascending, slots in submission order
+          for (int p = 0; p < P; p++) {
+            for (int sl = 0; sl < prm.A; sl++) {
+              PackedAction a;
+              a.lo = s_act[2 * sl];
+              a.hi = s_act[2 * sl + 1];
+              if (!a.present() || a.player() != p) continue;
+              const int fx = a.fx(), fy = a.fy(), tx = a.tx(), ty = a.ty();
+              {  // collectExperiences: Serializer.ActionToIndex, last submission wins
+                int ddx = tx - fx, ddy = ty - fy, dir = 0;
+                if (ddy == -1 && ddx == 0) dir = 0;
+                else if (ddy == 1 && ddx == 0) dir = 1;
+                else if (ddy == 0 && ddx == -1) dir = 2;
+                else if (ddy == 0 && ddx == 1) dir = 3;
+                int ai = (fy * W + fx) * 4 + dir;
+#pragma unroll
+                for (int q = 0; q < PT; q++)
+                  if (q == p) aidx[q] = ai;
+              }
+              if (!((alive_start >> p) & 1u)) continue;
+              // core/action.go:56-105 Validate
+              uint32_t e = 0;
+              if ((unsigned)fx >= (unsigned)W || (unsigned)fy >= (unsigned)prm.H) e = GRL_STEP_INVALID_COORDINATES;
+              else if ((unsigned)tx >= (unsigned)W || (unsigned)ty >= (unsigned)prm.H) e = GRL_STEP_INVALID_COORDINATES;
+              else if (fx == tx && fy == ty) e = GRL_STEP_MOVE_TO_SELF;
+              else {
+                int ddx = fx - tx, ddy = fy - ty;
+                bool adj = (ddx == 0 && (ddy == 1 || ddy == -1)) || (ddy == 0 && (ddx == 1 || ddx == -1));
+                if (!adj) e = GRL_STEP_NOT_ADJACENT;
+              }
+              int fi = 0, ti = 0;
+              uint32_t a_from = 0;
+              if (!e) {
+                fi = fy * W + fx;
+                ti = ty * W + tx;
+                if (!((S.own[p * NW + (fi >> 5)] >> (fi & 31)) & 1u)) e = GRL_STEP_NOT_OWNED;
+                else {
+                  a_from = S.army[fi];
+                  if (a_from <= 1u) e = GRL_STEP_INSUFFICIENT_ARMY;
+                  else if ((S.M[ti >> 5] >> (ti & 31)) & 1u) e = GRL_STEP_TARGET_IS_MOUNTAIN;
+                }
+              }
+              if (e) {
+                if (!err) err = e;  // first error remembered, processing continues (:66-77)
+                continue;
+              }
+              // core/movement.go:23-89 ApplyMoveAction
+              uint32_t moved = a.move_all() ? a_from - 1u : (a_from / 2u == 0u ? 1u : a_from / 2u);
+              S.army[fi] = (uint16_t)(a_from - moved);
+              S.chg[fi >> 5] |= 1u << (fi & 31);
+              const int tw = ti >> 5;
+              const uint32_t tb = 1u << (ti & 31);
+              S.chg[tw] |= tb;
+              uint32_t a_to = S.army[ti];
+              uint32_t *ta = &S.hdr[GRL_HDR_PLAYER0 + GRL_PL_TRUE_ARMY];
+              ta[GRL_HDR_PER_PLAYER * p] -= moved;
+              if (S.own[p * NW + tw] & tb) {
+                uint32_t sum = a_to + moved;
+                if (sum > 65535u) {
+                  sum = 65535u;
+                  overflow = 1;
+                }
+                S.army[ti] = (uint16_t)sum;
+                ta[GRL_HDR_PER_PLAYER * p] += sum - a_to;
+              } else {
+                int q = -1;
+                for (int r = 0; r < P; r++)
+                  if (S.own[r * NW + tw] & tb) q = r;
+                if (moved > a_to) {  // ties defend (movement.go:69)
+                  if (q >= 0) {
+                    S.own[q * NW + tw] &= ~tb;
+                    ta[GRL_HDR_PER_PLAYER * q] -= a_to;
+                  }
+                  S.own[p * NW + tw] |= tb;
+                  S.army[ti] = (uint16_t)(moved - a_to);
+                  ta[GRL_HDR_PER_PLAYER * p] += moved - a_to;
+                  S.vch[tw] |= tb;  // action_processor.go:78-87
+                  // core.ProcessCaptures movement.go:100-118: first capture of a player's general wins
+                  if ((S.G[tw] & tb) && q >= 0 && !((processed >> q) & 1u) && n_orders < 8) {
+                    uint32_t o = (uint32_t)q | ((uint32_t)p << 4);
+                    if (n_orders < 4) ord_lo |= o << (8 * n_orders);
+                    else ord_hi |= o << (8 * (n_orders - 4));
+                    n_orders++;
+                    processed |= 1u << q;
+                  }
+                } else {
+                  S.army[ti] = (uint16_t)(a_to - moved);
+                  if (q >= 0) ta[GRL_HDR_PER_PLAYER * q] -= moved;
+                }
+              }
+            }
+          }
+          for (int p = 0; p < P; p++)
+#pragma unroll
+            for (int q = 0; q < PT; q++)
+              if (q == p) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ACTION_INDEX] = (uint32_t)aidx[q];
+          if (overflow) S.hdr[GRL_HDR_OVERFLOW] = 1u;
+        }
+        __syncwarp();
+        err = __shfl_sync(FULL, err, 0);
+        n_orders = __shfl_sync(FULL, n_orders, 0);
+        ord_lo = __shfl_sync(FULL, ord_lo, 0);
+        ord_hi = __shfl_sync(FULL, ord_hi, 0);
+#pragma unroll
+        for (int p = 0; p < PT; p++)
+          if (p < P && act_lane) own[p] = S.own[p * NW + lane];
+        if (act_lane) {
+          chg = S.chg[lane];
+          vch = S.vch[lane];
+        }
+
+        // ---- eliminations + tile turnover over the CACHED list (engine.go:118-152) --------
+        if (n_orders > 0) {
+          for (int o = 0; o < n_orders; o++) {
+            uint32_t ob = (o < 4 ? (ord_lo >> (8 * o)) : (ord_hi >> (8 * (o - 4)))) & 0xffu;
+            int el = (int)(ob & 0xfu), nw = (int)(ob >> 4);
+            uint32_t X = 0;
+#pragma unroll
+            for (int q = 0; q < PT; q++)
+              if (q == el) X = lst[q] & own[q];
+#pragma unroll
+            for (int q = 0; q < PT; q++) {
+              if (q == el) own[q] &= ~X;
+              if (q == nw) own[q] |= X;
+            }
+            chg |= X;
+            vch |= X;
+            int moved_army = 0;
+            if (__any_sync(FULL, X != 0u)) moved_army = sum_army_over(X, S.army, NW, N, lane);
+            if (lane == 0) {
+              S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * el + GRL_PL_TRUE_ARMY] -= (uint32_t)moved_army;
+              S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * nw + GRL_PL_TRUE_ARMY] += (uint32_t)moved_army;
+              S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * el + GRL_PL_GENERAL_IDX] = 0xffffffffu;
+            }
+            alive &= ~(1u << el);
+          }
+          __syncwarp();
+          stats_update<PT>(prm, S, own, lst, chg, G, alive, lane, false);  // engine.go:107
+        }
+
+        if (err == 0) {
+          // ---- production over the cached lists (production_manager.go:26-101) ------------
+          uint32_t AL = 0;
+#pragma unroll
+          for (int p = 0; p < PT; p++)
+            if (p < P && ((alive >> p) & 1u)) AL |= lst[p];
+          const bool grow = (turn % (uint32_t)prm.grow_interval) == 0u;
+          uint32_t PG = prm.pg > 0 ? (AL & G) : 0u;
+          uint32_t PC = prm.pc > 0 ? (AL & C) : 0u;
+          uint32_t PN = (grow && prm.pn > 0) ? (AL & ~(G | C | M)) : 0u;
+          uint32_t produced = PG | PC | PN;
+          chg |= produced;
+          if (__any_sync(FULL, produced != 0u)) {
+            uint32_t overflow = 0;
+            if (grow) {  // dense: most owned tiles grow
+              for (int i = 0; i < NW; i++) {
+                uint32_t wg = __shfl_sync(FULL, PG, i), wc = __shfl_sync(FULL, PC, i), wn = __shfl_sync(FULL, PN, i);
+                int t = 32 * i + lane;
+                uint32_t add = (((wg >> lane) & 1u) ? (uint32_t)prm.pg : 0u) + (((wc >> lane) & 1u) ? (uint32_t)prm.pc : 0u) +
+                               (((wn >> lane) & 1u) ? (uint32_t)prm.pn : 0u);
+                if (add) {
+                  uint32_t a = (uint32_t)S.army[t] + add;
+                  if (a > 65535u) {
+                    a = 65535u;
+                    overflow = 1;
+                  }
+                  S.army[t] = (uint16_t)a;
+                }
+              }
+            } else {  // sparse: generals and cities only
+              uint32_t w = produced;
+              while (w) {
+                int b = __ffs(w) - 1;
+                w &= w - 1u;
+                int t = 32 * lane + b;
+                uint32_t add = ((PG >> b) & 1u) ? (uint32_t)prm.pg : (uint32_t)prm.pc;
+                uint32_t a = (uint32_t)S.army[t] + add;
+                if (a > 65535u) {
+                  a = 65535u;
+                  overflow = 1;
+                }
+                S.army[t] = (uint16_t)a;
+              }
+            }
+            if (__any_sync(FULL, overflow != 0u) && lane == 0) S.hdr[GRL_HDR_OVERFLOW] = 1u;
+#pragma unroll
+            for (int p = 0; p < PT; p++) {
+              if (p < P) {
+                int d = prm.pg * __popc(PG & own[p]) + prm.pc * __popc(PC & own[p]) + prm.pn * __popc(PN & own[p]);
+                d = __reduce_add_sync(FULL, d);
+                if (lane == 0) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY] += (uint32_t)d;
+              }
+            }
+            __syncwarp();
+          }
+          // ---- end of turn: stats, game over (turn_processor.go:170-179) --------------------
+          stats_update<PT>(prm, S, own, lst, chg, G, alive, lane, false);
+          int n_alive = __popc(alive & ((1u << P) - 1u));
+          bool now_over = P > 1 ? (n_alive <= 1) : (n_alive == 0);  // win_conditions.go:38-44
+          if (now_over && !over && lane == 0) S.hdr[GRL_HDR_FINISHED] += 1;
+          over = now_over;
+        }
+        if (lane == 0) {
+          S.hdr[GRL_HDR_STEPS] += 1;
+          if (err) S.hdr[GRL_HDR_ERRORS] += 1;
+        }
+      }
+    }
+    const uint32_t turn_err = err;  // the reference's validation error (or game over)
+    if (DO_STEP && stepped && err == 0 && S.hdr[GRL_HDR_OVERFLOW]) err = GRL_STEP_ARMY_OVERFLOW;
+
+    // ---- reward: CalculateRewardWithConfig(prev, curr, p) (rewards.go:45-85) -------------
+    if (DO_STEP && stepped) {
+      int n_alive = __popc(alive & ((1u << P) - 1u));
+      int sole = n_alive == 1 ? (__ffs(alive & ((1u << P) - 1u)) - 1) : -1;
+      int total_army = 0;
+#pragma unroll
+      for (int p = 0; p < PT; p++)
+        if (p < P) total_army += (int)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY];
+      uint32_t any_prev = 0;
+#pragma unroll
+      for (int p = 0; p < PT; p++) any_prev |= own_prev[p];
+#pragma unroll
+      for (int p = 0; p < PT; p++) {
+        if (p < P) {
+          int d_tiles = __reduce_add_sync(FULL, __popc(own[p]) - __popc(own_prev[p]));
+          uint32_t gained = own[p] & ~own_prev[p], lost = own_prev[p] & ~own[p];
+          int cc = 0, gg = 0;
+          if (__any_sync(FULL, ((gained | lost) & (C | G)) != 0u)) {
+            cc = __reduce_add_sync(FULL, __popc(gained & C) | (__popc(lost & C) << 16));
+            gg = __reduce_add_sync(FULL, __popc(gained & G & any_prev) | (__popc(lost & G) << 16));
+          }
+          int cur_army = (int)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY];
+          float r = 0.0f;
+          bool terminal = false;
+          if (n_alive <= 1) {  // state.go:73-100 on the current state
+            if (sole == p) {
+              r = prm.rw[0];
+              terminal = true;
+            } else if (sole != -1) {
+              r = prm.rw[1];
+              terminal = true;
+            }
+          }
+          if (!terminal) {  // one rounding per Go statement, no FMA contraction (Q12)
+            r = __fadd_rn(r, __fmul_rn((float)d_tiles, prm.rw[6]));
+            r = __fadd_rn(r, __fmul_rn((float)(cur_army - prev_true_army[p]), prm.rw[8]));
+            r = __fadd_rn(r, __fmul_rn((float)(cc & 0xffff), prm.rw[2]));
+            r = __fadd_rn(r, __fmul_rn((float)(cc >> 16), prm.rw[3]));
+            r = __fadd_rn(r, __fmul_rn((float)(gg & 0xffff), prm.rw[4]));
+            r = __fadd_rn(r, __fmul_rn((float)(gg >> 16), prm.rw[5]));
+            float adv = 0.0f;
+            if (total_army != 0) adv = __fdiv_rn((float)(cur_army - (total_army - cur_army)), (float)total_army);
+            r = __fadd_rn(r, __fmul_rn(adv, prm.rw[10]));
+          }
+          if (lane == 0) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_REWARD] = __float_as_uint(r);
+        }
+      }
+      if (turn_err != 0 && lane == 0)  // aborted turn: no experience is emitted (engine.go:111-113)
+        for (int p = 0; p < P; p++) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ACTION_INDEX] = 0xffffffffu;
+    }
+
+    // ---- write the state back ---------------------------------------------------------------
+    if (DO_STEP) {
+      if (stepped) {
+        if (act_lane) {
+#pragma unroll
+          for (int p = 0; p < PT; p++) {
+            if (p < P) {
+              S.own[p * NW + lane] = own[p];
+              S.list[p * NW + lane] = lst[p];
+              S.vis[p * NW + lane] = vis[p];
+            }
+          }
+          S.chg[lane] = chg;
+          S.vch[lane] = vch;
+        }
+        if (lane == 0) S.hdr[GRL_HDR_TURN] = turn;
+      }
+      if (lane == 0)
+        S.hdr[GRL_HDR_FLAGS] = (alive & 0xffu) | (over ? GRL_FLAG_OVER : 0u) | (err << GRL_FLAG_ERR_SHIFT);
+      __syncwarp();
+      if (prm.use_tma) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tma_store(gslab, s, (uint32_t)L.slab_words * 4u);
+      } else {
+        const uint4 *src = reinterpret_cast<const uint4 *>(s);
+        uint4 *dst = reinterpret_cast<uint4 *>(gslab);
+        for (int k = lane; k < L.slab_words / 4; k += 32) dst[k] = src[k];
+      }
+    } else {
+      err = (flags >> GRL_FLAG_ERR_SHIFT) & 0xffu;
+    }
+
+    // ---- read-outs ---------------------------------------------------------------------------
+    if (DO_OUT) {
+      const uint32_t pmask = (1u << P) - 1u;
+      if (lane == 0) {
+        if (prm.done) prm.done[game] = over ? 1 : 0;
+        if (prm.winner) {  // engine.go:248-263
+          int n_alive = __popc(alive & pmask);
+          prm.winner[game] = (int8_t)((over && n_alive == 1) ? (__ffs(alive & pmask) - 1) : -1);
+        }
+        if (prm.step_error) prm.step_error[game] = (uint8_t)err;
+      }
+      if (lane < P) {
+        if (prm.reward)
+          prm.reward[(size_t)game * P + lane] =
+              __uint_as_float(S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_REWARD]);
+        if (prm.action_index)
+          prm.action_index[(size_t)game * P + lane] =
+              (int32_t)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ACTION_INDEX];
+      }
+
+      // engine legal-action mask, packed in the reference's flat index order (t*4 + dir, U,R,D,L)
+      if (prm.mask_bits) {
+        uint32_t gt1 = army_gt1_mask(S.army, NW, N, lane);
+        DirMasks dm = dir_targets(M, g);
+        const int words = (4 * N + 31) / 32;
+#pragma unroll
+        for (int p = 0; p < PT; p++) {
+          if (p < P) {
+            uint32_t src = ((alive >> p) & 1u) ? (lst[p] & own[p] & gt1) : 0u;
+            uint32_t U = src & dm.up, R = src & dm.right, D = src & dm.down, Lm = src & dm.left;
+            uint32_t *dst = prm.mask_bits + ((size_t)game * P + p) * words;
+            for (int k0 = 0; k0 < words; k0 += 32) {
+              int k = k0 + lane;  // output word k covers tiles 8k..8k+7 = byte k&3 of mask word k>>2
+              int srcl = (k >> 2) & 31, sh = (k & 3) * 8;
+              uint32_t bu = __shfl_sync(FULL, U, srcl) >> sh, br = __shfl_sync(FULL, R, srcl) >> sh;
+              uint32_t bd = __shfl_sync(FULL, D, srcl) >> sh, bl = __shfl_sync(FULL, Lm, srcl) >> sh;
+              uint32_t w = spread8(bu) | (spread8(br) << 1) | (spread8(bd) << 2) | (spread8(bl) << 3);
+              if (k < words) dst[k] = w;
+            }
+          }
+        }
+      }
+
+      // observation planes: Serializer.StateToTensor (serializer.go:37-109)
+      if (prm.obs) {
+        uint32_t any_own = 0;
+#pragma unroll
+        for (int p = 0; p < PT; p++) any_own |= own[p];
+        const uint32_t CG = C | G;
+#pragma unroll
+        for (int p = 0; p < PT; p++) {
+          if (p < P) {
+            const uint32_t V = prm.fog ? vis[p] : g.valid;
+            const uint32_t w7 = V, w8 = ~V & g.valid, w6 = V & M, nm = V & ~M;
+            const uint32_t w5 = nm & CG, w2 = nm & own[p], w3 = nm & any_own & ~own[p], w4 = nm & ~any_own;
+            float *base = prm.obs + ((size_t)game * P + p) * GRL_OBS_CHANNELS * N;
+            if ((N & 3) == 0) {
+              // 128-bit path: a lane writes 4 consecutive tiles of each channel plane
+              for (int q0 = 0; q0 * 4 < N; q0 += 32) {
+                const int q = q0 + lane;
+                const int t0 = 4 * q;
+                const int srcl = (t0 >> 5) & 31, sh = t0 & 31;
+                const uint32_t n7 = (__shfl_sync(FULL, w7, srcl) >> sh) & 0xfu, n8 = (__shfl_sync(FULL, w8, srcl) >> sh) & 0xfu;
+                const uint32_t n6 = (__shfl_sync(FULL, w6, srcl) >> sh) & 0xfu, n5 = (__shfl_sync(FULL, w5, srcl) >> sh) & 0xfu;
+                const uint32_t n2 = (__shfl_sync(FULL, w2, srcl) >> sh) & 0xfu, n3 = (__shfl_sync(FULL, w3, srcl) >> sh) & 0xfu;
+                const uint32_t n4 = (__shfl_sync(FULL, w4, srcl) >> sh) & 0xfu;
+                if (t0 < N) {
+                  const uint2 aw = *reinterpret_cast<const uint2 *>(S.army + t0);
+                  const float f0 = army_frac(aw.x & 0xffffu), f1 = army_frac(aw.x >> 16);
+                  const float f2 = army_frac(aw.y & 0xffffu), f3 = army_frac(aw.y >> 16);
+                  float4 *o = reinterpret_cast<float4 *>(base + t0);
+                  const int cs = N / 4;  // channel stride in float4
+#define NIBF(n) make_float4(((n)&1u) ? 1.f : 0.f, ((n)&2u) ? 1.f : 0.f, ((n)&4u) ? 1.f : 0.f, ((n)&8u) ? 1.f : 0.f)
+#define NIBA(n) make_float4(((n)&1u) ? f0 : 0.f, ((n)&2u) ? f1 : 0.f, ((n)&4u) ? f2 : 0.f, ((n)&8u) ? f3 : 0.f)
+                  __stcs(o + 0 * cs, NIBA(n2));
+                  __stcs(o + 1 * cs, NIBA(n3));
+                  __stcs(o + 2 * cs, NIBF(n2));
+                  __stcs(o + 3 * cs, NIBF(n3));
+                  __stcs(o + 4 * cs, NIBF(n4));
+                  __stcs(o + 5 * cs, NIBF(n5));
+                  __stcs(o + 6 * cs, NIBF(n6));
+                  __stcs(o + 7 * cs, NIBF(n7));
+                  __stcs(o + 8 * cs, NIBF(n8));
+#undef NIBF
+#undef NIBA
+                }
+              }
+            } else {
+              // generic path (N % 4 != 0, e.g. 15x15): one tile per lane, coalesced 32-bit stores
+              for (int i = 0; i < NW; i++) {
+                const int t = 32 * i + lane;
+                const uint32_t b7 = (__shfl_sync(FULL, w7, i) >> lane) & 1u, b8 = (__shfl_sync(FULL, w8, i) >> lane) & 1u;
+                const uint32_t b6 = (__shfl_sync(FULL, w6, i) >> lane) & 1u, b5 = (__shfl_sync(FULL, w5, i) >> lane) & 1u;
+                const uint32_t b2 = (__shfl_sync(FULL, w2, i) >> lane) & 1u, b3 = (__shfl_sync(FULL, w3, i) >> lane) & 1u;
+                const uint32_t b4 = (__shfl_sync(FULL, w4, i) >> lane) & 1u;
+                if (t < N) {
+                  const float f = army_frac((uint32_t)S.army[t]);
+                  float *o = base + t;
+                  __stcs(o + 0 * N, b2 ? f : 0.f);
+                  __stcs(o + 1 * N, b3 ? f : 0.f);
+                  __stcs(o + 2 * N, b2 ? 1.f : 0.f);
+                  __stcs(o + 3 * N, b3 ? 1.f : 0.f);
+                  __stcs(o + 4 * N, b4 ? 1.f : 0.f);
+                  __stcs(o + 5 * N, b5 ? 1.f : 0.f);
+                  __stcs(o + 6 * N, b6 ? 1.f : 0.f);
+                  __stcs(o + 7 * N, b7 ? 1.f : 0.f);
+                  __stcs(o + 8 * N, b8 ? 1.f : 0.f);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+
+    if (DO_STEP && prm.use_tma) {
+      if (lane == 0) tma_store_commit_wait();  // the slab buffer is reused by the next game
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Reset: freshly uploaded slabs carry ownership, armies and terrain; this kernel performs
+// the turn-0 set-up of engine_initializer.go:113-143,218-225 (players alive, full stats,
+// full fog, game-over check), preserving the env's lifetime counters.
+// ---------------------------------------------------------------------------------------
+template <int PT>
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
+    grl_reset_kernel(const __grid_constant__ GrlKParams prm, const uint32_t *__restrict__ src_state,
+                     const uint32_t *__restrict__ src_static, const int32_t *__restrict__ env_ids, int n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GrlLayout &L = prm.L;
+  const int P = prm.P, NW = prm.NW, N = prm.N;
+  Geo g;
+  g.lane = lane;
+  g.W = prm.W;
+  g.valid = prm.geom[lane];
+  g.nc0 = prm.geom[32 + lane];
+  g.ncl = prm.geom[64 + lane];
+  for (int i = blockIdx.x * GRL_WARPS_PER_CTA + warp; i < n; i += gridDim.x * GRL_WARPS_PER_CTA) {
+    const int game = env_ids ? env_ids[i] : i;
+    if (game < 0 || game >= prm.B) continue;
+    const uint32_t *ss = src_state + (size_t)i * L.slab_words;
+    const uint32_t *sst = src_static + (size_t)i * L.static_words;
+    uint32_t *ds = prm.state + (size_t)game * L.slab_words;
+    uint32_t *dst = const_cast<uint32_t *>(prm.statics) + (size_t)game * L.static_words;
+    for (int k = lane; k < L.static_words; k += 32) dst[k] = sst[k];
+    for (int k = L.off_army + lane; k < L.slab_words; k += 32) ds[k] = ss[k];
+    const bool act = lane < NW;
+    const uint32_t G = act ? sst[2 * NW + lane] : 0u;
+    const uint16_t *army = reinterpret_cast<const uint16_t *>(ss + L.off_army);
+    uint32_t alive = 0;
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      if (p < P) {
+        uint32_t own = act ? ss[L.off_own + p * NW + lane] : 0u;
+        int total = sum_army_over(own, army, NW, N, lane);
+        uint32_t gen = own & G;
+        int gi = gen ? (32 * lane + 31 - __clz(gen)) : -1;
+        gi = __reduce_max_sync(FULL, gi);
+        if (gi >= 0) alive |= 1u << p;
+        uint32_t v = (gi >= 0 && prm.fog) ? dilate3(own, g) : 0u;  // players start Alive; stats then sets Alive = has general
+        if (act) {
+          ds[L.off_own + p * NW + lane] = own;
+          ds[L.off_list + p * NW + lane] = own;
+          ds[L.off_vis + p * NW + lane] = v;
+        }
+        if (lane == 0) {
+          uint32_t *h = ds + GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p;
+          h[GRL_PL_ARMY_COUNT] = (uint32_t)total;
+          h[GRL_PL_GENERAL_IDX] = (uint32_t)gi;
+          h[GRL_PL_TRUE_ARMY] = (uint32_t)total;
+          h[GRL_PL_REWARD] = 0u;
+          h[GRL_PL_ACTION_INDEX] = 0xffffffffu;
+        }
+      }
+    }
+    if (act) {
+      ds[L.off_changed + lane] = 0u;
+      ds[L.off_vchg + lane] = 0u;
+    }
+    if (lane == 0) {
+      int n_alive = __popc(alive);
+      bool over = P > 1 ? (n_alive <= 1) : (n_alive == 0);
+      ds[GRL_HDR_TURN] = 0u;
+      ds[GRL_HDR_FLAGS] = alive | (over ? GRL_FLAG_OVER : 0u);
+      ds[GRL_HDR_OVERFLOW] = 0u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Read-out kernels that are not on the hot path (one thread per tile / per word).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool bit_of(const uint32_t *w, int t) { return (w[t >> 5] >> (t & 31)) & 1u; }
+
+// variant 0: engine mask bytes (U,R,D,L; list-based; army > 1)   rules/legal_moves.go:19-73
+// variant 1: serializer mask bytes (U,D,L,R; ownership scan; army >= 2)  serializer.go:112-176
+__global__ void grl_mask_bytes_kernel(const GrlKParams prm, int variant, uint8_t *__restrict__ out) {
+  const GrlLayout &L = prm.L;
+  const size_t total = (size_t)prm.B * prm.P * prm.N;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int t = (int)(idx % prm.N);
+    const int p = (int)((idx / prm.N) % prm.P);
+    const int game = (int)(idx / ((size_t)prm.N * prm.P));
+    const uint32_t *s = prm.state + (size_t)game * L.slab_words;
+    const uint32_t *M = prm.statics + (size_t)game * L.static_words;
+    const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+    const int x = t % prm.W, y = t / prm.W;
+    bool src = bit_of(s + L.off_own + p * prm.NW, t) && army[t] > 1;
+    if (variant == 0) src = src && bit_of(s + L.off_list + p * prm.NW, t) && ((s[GRL_HDR_FLAGS] >> p) & 1u);
+    const bool up = src && y > 0 && !bit_of(M, t - prm.W);
+    const bool down = src && y < prm.H - 1 && !bit_of(M, t + prm.W);
+    const bool left = src && x > 0 && !bit_of(M, t - 1);
+    const bool right = src && x < prm.W - 1 && !bit_of(M, t + 1);
+    uchar4 v = variant == 0 ? make_uchar4(up, right, down, left) : make_uchar4(up, down, left, right);
+    reinterpret_cast<uchar4 *>(out)[idx] = v;
+  }
+}
+
+// PlayerVisibility (visibility_optimized.go:166-195): visible = bit p; fog = !visible && type != normal
+__global__ void grl_visibility_kernel(const GrlKParams prm, uint8_t *__restrict__ visible, uint8_t *__restrict__ fog) {
+  const GrlLayout &L = prm.L;
+  const size_t total = (size_t)prm.B * prm.P * prm.N;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int t = (int)(idx % prm.N);
+    const int p = (int)((idx / prm.N) % prm.P);
+    const int game = (int)(idx / ((size_t)prm.N * prm.P));
+    const uint32_t *s = prm.state + (size_t)game * L.slab_words;
+    const uint32_t *stt = prm.statics + (size_t)game * L.static_words;
+    bool v, f = false;
+    if (!prm.fog) {
+      v = true;
+    } else {
+      v = bit_of(s + L.off_vis + p * prm.NW, t);
+      bool special = bit_of(stt, t) || bit_of(stt + prm.NW, t) || bit_of(stt + 2 * prm.NW, t);
+      f = !v && special;
+    }
+    if (visible) visible[idx] = v;
+    if (fog) fog[idx] = f;
+  }
+}
+
+// packed engine mask with the half-move replica: [B][P][rep][words]
+__global__ void grl_mask_replicate_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t rows, int words,
+                                          int rep) {
+  const size_t total = rows * (size_t)words * rep;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t row = idx / ((size_t)words * rep);
+    int k = (int)(idx % words);
+    out[idx] = in[row * words + k];
+  }
+}
+
+// 64-bit digest of the full game state; identical definition in oracle/grl_oracle.c
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32) grl_state_hash_kernel(const GrlKParams prm, uint64_t *__restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GrlLayout &L = prm.L;
+  for (int game = blockIdx.x * GRL_WARPS_PER_CTA + warp; game < prm.B; game += gridDim.x * GRL_WARPS_PER_CTA) {
+    const uint32_t *s = prm.state + (size_t)game * L.slab_words;
+    const uint32_t *stt = prm.statics + (size_t)game * L.static_words;
+    const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+    uint64_t h = 0;
+    for (int t = lane; t < prm.N; t += 32) {
+      int owner = -1;
+      uint64_t lists = 0, vis = 0;
+      for (int p = 0; p < prm.P; p++) {
+        if (bit_of(s + L.off_own + p * prm.NW, t)) owner = p;
+        if (bit_of(s + L.off_list + p * prm.NW, t)) lists |= 1ULL << p;
+        if (bit_of(s + L.off_vis + p * prm.NW, t)) vis |= 1ULL << p;
+      }
+      uint64_t type = bit_of(stt, t) ? 3 : (bit_of(stt + prm.NW, t) ? 2 : (bit_of(stt + 2 * prm.NW, t) ? 1 : 0));
+      uint64_t pack = (uint64_t)(owner + 1) | (type << 4) | ((uint64_t)bit_of(s + L.off_changed, t) << 6) |
+                      ((uint64_t)bit_of(s + L.off_vchg, t) << 7) | (vis << 8) | (lists << 16) | ((uint64_t)army[t] << 24);
+      h += mix64(pack ^ ((uint64_t)(t + 1) * 0xD6E8FEB86659FD93ULL));
+    }
+    h = warp_sum64(h);
+    if (lane == 0) {
+      uint32_t flags = s[GRL_HDR_FLAGS];
+      h += mix64(0x1000000000ULL + (uint64_t)s[GRL_HDR_TURN]);
+      h += mix64(0x2000000000ULL + (uint64_t)((flags >> 8) & 1u) + ((uint64_t)(flags & 0xffu) << 8));
+      for (int p = 0; p < prm.P; p++)
+        h += mix64(0x3000000000ULL + ((uint64_t)p << 40) +
+                   (uint64_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ARMY_COUNT]);
+      out[game] = h;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
+    grl_buffer_hash_kernel(const uint32_t *__restrict__ buf, size_t row_words, int rows, uint64_t *__restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * GRL_WARPS_PER_CTA + warp; r < rows; r += gridDim.x * GRL_WARPS_PER_CTA) {
+    const uint32_t *w = buf + (size_t)r * row_words;
+    uint64_t h = 0;
+    for (size_t i = lane; i < row_words; i += 32) h += mix64((uint64_t)w[i] ^ ((uint64_t)(i + 1) * 0xD6E8FEB86659FD93ULL));
+    h = warp_sum64(h);
+    if (lane == 0) out[r] = h;
+  }
+}
+
+// synthetic policy as a stand-alone kernel: fills grl_action[B][A]
+template <int PT>
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32) grl_sample_kernel(const __grid_constant__ GrlKParams prm, uint2 *__restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GrlLayout &L = prm.L;
+  const int P = prm.P, NW = prm.NW, N = prm.N;
+  Geo g;
+  g.lane = lane;
+  g.W = prm.W;
+  g.valid = prm.geom[lane];
+  g.nc0 = prm.geom[32 + lane];
+  g.ncl = prm.geom[64 + lane];
+  for (int game = blockIdx.x * GRL_WARPS_PER_CTA + warp; game < prm.B; game += gridDim.x * GRL_WARPS_PER_CTA) {
+    const uint32_t *s = prm.state + (size_t)game * L.slab_words;
+    const uint32_t *stt = prm.statics + (size_t)game * L.static_words;
+    const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+    const bool act = lane < NW;
+    const uint32_t M = act ? stt[lane] : 0u;
+    const uint32_t flags = s[GRL_HDR_FLAGS];
+    const uint32_t turn = s[GRL_HDR_TURN];
+    uint32_t gt1 = army_gt1_mask(army, NW, N, lane);
+    DirMasks dm = dir_targets(M, g);
+    if (lane < prm.A) out[(size_t)game * prm.A + lane] = make_uint2(0u, 0u);
+    __syncwarp();
+    if (flags & GRL_FLAG_OVER) continue;
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      if (p < P && p < prm.A) {
+        uint32_t own = act ? s[L.off_own + p * NW + lane] : 0u;
+        uint32_t lst = act ? s[L.off_list + p * NW + lane] : 0u;
+        uint32_t src = ((flags >> p) & 1u) ? (lst & own & gt1) : 0u;
+        PackedAction a = sample_policy_action(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn, g);
+        if (lane == 0) out[(size_t)game * prm.A + p] = make_uint2(a.lo, a.hi);
+      }
+    }
+  }
+}
+
+// lifetime counters: sum header words 2..5 over all envs
+__global__ void grl_stats_kernel(const GrlKParams prm, unsigned long long *__restrict__ out) {
+  unsigned long long acc[4] = {0, 0, 0, 0};
+  for (int game = blockIdx.x * blockDim.x + threadIdx.x; game < prm.B; game += gridDim.x * blockDim.x) {
+    const uint32_t *s = prm.state + (size_t)game * prm.L.slab_words;
+    for (int k = 0; k < 4; k++) acc[k] += s[GRL_HDR_STEPS + k];
+  }
+  for (int k = 0; k < 4; k++) {
+    unsigned long long v = warp_sum64(acc[k]);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + k, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers (called from grl_abi.cu)
+// ---------------------------------------------------------------------------------------
+static inline int grid_for(int items_per_cta_warps, int n) {
+  int ctas = (n + items_per_cta_warps - 1) / items_per_cta_warps;
+  return ctas < 1 ? 1 : ctas;
+}
+
+size_t grl_turn_smem_bytes(const GrlLayout &L) {
+  return (size_t)GRL_WARPS_PER_CTA * (size_t)(L.slab_words + L.static_words + 2 * GRL_MAX_ACTIONS) * 4u;
+}
+
+template <int PT, bool S, bool O>
+static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream) {
+  size_t smem = grl_turn_smem_bytes(prm.L);
+  auto kern = grl_turn_kernel<PT, S, O>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<grid_for(GRL_WARPS_PER_CTA, prm.B), GRL_WARPS_PER_CTA * 32, smem, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+template <int PT>
+static cudaError_t launch_turn_p(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream) {
+  if (do_step && do_out) return launch_turn_t<PT, true, true>(prm, stream);
+  if (do_step) return launch_turn_t<PT, true, false>(prm, stream);
+  return launch_turn_t<PT, false, true>(prm, stream);
+}
+
+static int player_template(int P) { return P <= 2 ? 2 : (P <= 4 ? 4 : 8); }
+
+cudaError_t grl_launch_turn(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream) {
+  switch (player_template(prm.P)) {
+    case 2: return launch_turn_p<2>(prm, do_step, do_out, stream);
+    case 4: return launch_turn_p<4>(prm, do_step, do_out, stream);
+    default: return launch_turn_p<8>(prm, do_step, do_out, stream);
+  }
+}
+
+cudaError_t grl_launch_reset(const GrlKParams &prm, const uint32_t *src_state, const uint32_t *src_static,
+                             const int32_t *env_ids, int n, cudaStream_t stream) {
+  int grid = grid_for(GRL_WARPS_PER_CTA, n);
+  switch (player_template(prm.P)) {
+    case 2: grl_reset_kernel<2><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, src_state, src_static, env_ids, n); break;
+    case 4: grl_reset_kernel<4><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, src_state, src_static, env_ids, n); break;
+    default: grl_reset_kernel<8><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, src_state, src_static, env_ids, n); break;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_sample(const GrlKParams &prm, void *out, cudaStream_t stream) {
+  int grid = grid_for(GRL_WARPS_PER_CTA, prm.B);
+  switch (player_template(prm.P)) {
+    case 2: grl_sample_kernel<2><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, (uint2 *)out); break;
+    case 4: grl_sample_kernel<4><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, (uint2 *)out); break;
+    default: grl_sample_kernel<8><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, (uint2 *)out); break;
+  }
+  return cudaGetLastError();
+}
+
+static int flat_grid(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  if (g > 148 * 16) g = 148 * 16;
+  return g < 1 ? 1 : (int)g;
+}
+
+cudaError_t grl_launch_mask_bytes(const GrlKParams &prm, int variant, uint8_t *out, cudaStream_t stream) {
+  size_t total = (size_t)prm.B * prm.P * prm.N;
+  grl_mask_bytes_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(prm, variant, out);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_visibility(const GrlKParams &prm, uint8_t *visible, uint8_t *fog, cudaStream_t stream) {
+  size_t total = (size_t)prm.B * prm.P * prm.N;
+  grl_visibility_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(prm, visible, fog);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_mask_replicate(const uint32_t *in, uint32_t *out, size_t rows, int words, int rep, cudaStream_t stream) {
+  grl_mask_replicate_kernel<<<flat_grid(rows * words * rep, 256), 256, 0, stream>>>(in, out, rows, words, rep);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_state_hash(const GrlKParams &prm, uint64_t *out, cudaStream_t stream) {
+  grl_state_hash_kernel<<<grid_for(GRL_WARPS_PER_CTA, prm.B), GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, out);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_buffer_hash(const uint32_t *buf, size_t row_words, int rows, uint64_t *out, cudaStream_t stream) {
+  grl_buffer_hash_kernel<<<grid_for(GRL_WARPS_PER_CTA, rows), GRL_WARPS_PER_CTA * 32, 0, stream>>>(buf, row_words, rows, out);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_stats(const GrlKParams &prm, unsigned long long *out, cudaStream_t stream) {
+  grl_stats_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm, out);
+  return cudaGetLastError();
+}
+
+// envs that were created but never reset reject steps like a finished game
+__global__ void grl_mark_over_kernel(const GrlKParams prm) {
+  for (int game = blockIdx.x * blockDim.x + threadIdx.x; game < prm.B; game += gridDim.x * blockDim.x) {
+    uint32_t *s = prm.state + (size_t)game * prm.L.slab_words;
+    s[GRL_HDR_FLAGS] = GRL_FLAG_OVER;
+    for (int p = 0; p < prm.P; p++) {
+      s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_GENERAL_IDX] = 0xffffffffu;
+      s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ACTION_INDEX] = 0xffffffffu;
+    }
+  }
+}
+
+cudaError_t grl_launch_mark_over(const GrlKParams &prm, cudaStream_t stream) {
+  grl_mark_over_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm);
+  return cudaGetLastError();
+}

@@ -1,0 +1,19 @@
+// grl_launch.h — kernel launchers defined in grl_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include "grl_layout.h"
+
+size_t grl_turn_smem_bytes(const GrlLayout &L);
+cudaError_t grl_launch_turn(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream);
+cudaError_t grl_launch_reset(const GrlKParams &prm, const uint32_t *src_state, const uint32_t *src_static,
+                             const int32_t *env_ids, int n, cudaStream_t stream);
+cudaError_t grl_launch_sample(const GrlKParams &prm, void *out, cudaStream_t stream);
+cudaError_t grl_launch_mask_bytes(const GrlKParams &prm, int variant, uint8_t *out, cudaStream_t stream);
+cudaError_t grl_launch_visibility(const GrlKParams &prm, uint8_t *visible, uint8_t *fog, cudaStream_t stream);
+cudaError_t grl_launch_mask_replicate(const uint32_t *in, uint32_t *out, size_t rows, int words, int rep,
+                                      cudaStream_t stream);
+cudaError_t grl_launch_state_hash(const GrlKParams &prm, uint64_t *out, cudaStream_t stream);
+cudaError_t grl_launch_buffer_hash(const uint32_t *buf, size_t row_words, int rows, uint64_t *out, cudaStream_t stream);
+cudaError_t grl_launch_stats(const GrlKParams &prm, unsigned long long *out, cudaStream_t stream);
+cudaError_t grl_launch_mark_over(const GrlKParams &prm, cudaStream_t stream);

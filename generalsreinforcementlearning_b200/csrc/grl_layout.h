@@ -1,0 +1,90 @@
+// grl_layout.h — device-resident state layout shared by the host ABI code and the kernels.
+//
+// One game ("env") is one contiguous, 16-byte aligned SLAB of 32-bit words in HBM, so a
+// warp (or one TMA bulk copy) moves it with fully coalesced 128-bit transactions:
+//
+//   header   8 + 5*P words (rounded up to 4)
+//     [0] turn            [1] flags: bits0-7 alive, bit8 gameOver, bits16-23 last step_error
+//     [2] steps executed  [3] error turns  [4] games finished  [5] steps rejected (game over)
+//     [6] sticky army-overflow flag        [7] reserved
+//     per player p at 8+5p: armyCount, generalIdx, trueArmy (sum over true ownership),
+//                           reward bits (fp32 of the last step), actionIndex of the last step
+//   own [P][NW]   ownership as one N-bit linear bitmask per player (tile t = bit t&31 of word t>>5)
+//   list[P][NW]   the reference's cached Player.OwnedTiles, as a set
+//   vis [P][NW]   Tile.VisibleBitfield transposed: bit p of tile t = bit t of vis[p]
+//   changed[NW], vchg[NW]   GameState.ChangedTiles / VisibilityChangedTiles
+//   army u16[NA]  (NA = N rounded up to 8)
+//
+// Terrain never changes within an episode (core/movement.go:38), so it lives in a separate
+// read-only STATIC slab: mountain[NW], city[NW], general[NW] (rounded up to 4 words).
+//
+// NW = ceil(N/32) <= 32 because W,H <= 32: lane j of a warp owns word j of every mask.
+#pragma once
+#include <stdint.h>
+
+#define GRL_HDR_TURN 0
+#define GRL_HDR_FLAGS 1
+#define GRL_HDR_STEPS 2
+#define GRL_HDR_ERRORS 3
+#define GRL_HDR_FINISHED 4
+#define GRL_HDR_REJECTED 5
+#define GRL_HDR_OVERFLOW 6
+#define GRL_HDR_PLAYER0 8
+#define GRL_HDR_PER_PLAYER 5
+#define GRL_PL_ARMY_COUNT 0
+#define GRL_PL_GENERAL_IDX 1
+#define GRL_PL_TRUE_ARMY 2
+#define GRL_PL_REWARD 3
+#define GRL_PL_ACTION_INDEX 4
+
+#define GRL_FLAG_OVER (1u << 8)
+#define GRL_FLAG_ERR_SHIFT 16
+
+struct GrlLayout {
+  int N, P, NW, NA;
+  int hdr_words;
+  int off_own, off_list, off_vis, off_changed, off_vchg, off_army;
+  int slab_words;    // multiple of 4
+  int static_words;  // multiple of 4: [M][C][G]
+};
+
+static inline GrlLayout grl_make_layout(int W, int H, int P) {
+  GrlLayout L;
+  L.N = W * H;
+  L.P = P;
+  L.NW = (L.N + 31) / 32;
+  L.NA = (L.N + 7) & ~7;
+  L.hdr_words = (GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * P + 3) & ~3;
+  L.off_own = L.hdr_words;
+  L.off_list = L.off_own + P * L.NW;
+  L.off_vis = L.off_list + P * L.NW;
+  L.off_changed = L.off_vis + P * L.NW;
+  L.off_vchg = L.off_changed + L.NW;
+  L.off_army = (L.off_vchg + L.NW + 3) & ~3;
+  L.slab_words = (L.off_army + L.NA / 2 + 3) & ~3;
+  L.static_words = (3 * L.NW + 3) & ~3;
+  return L;
+}
+
+// Kernel parameter block (passed by value, __grid_constant__).
+struct GrlKParams {
+  uint32_t *state;          // [B][slab_words]
+  const uint32_t *statics;  // [B][static_words]
+  const uint32_t *geom;     // [3][32]: valid tiles, x != 0, x != W-1 (linear bitmasks)
+  const void *actions;      // grl_action [B][A] or nullptr
+  float *obs;
+  uint32_t *mask_bits;
+  float *reward;
+  uint8_t *done;
+  int8_t *winner;
+  uint8_t *step_error;
+  int32_t *action_index;
+  unsigned long long policy_seed;
+  uint32_t flags;
+  int B, W, H, N, P, NW, A;
+  GrlLayout L;
+  int fog, pg, pc, pn, grow_interval;
+  int env_id_base;
+  int use_tma;
+  float rw[11];
+};

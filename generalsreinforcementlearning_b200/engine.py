@@ -224,6 +224,11 @@ class BatchedEngine:
         self.lib.check(self.lib.stats(self._h, _ptr(out)), "stats")
         return out
 
+    def launch_count(self) -> int:
+        out = np.zeros(1, np.uint64)
+        self.lib.check(self.lib.launch_count(self._h, _ptr(out)), "launch_count")
+        return int(out[0])
+
     def is_game_over(self) -> np.ndarray:
         return self.get_state()["game_over"].astype(bool)
 

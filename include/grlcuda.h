@@ -232,6 +232,9 @@ int grl_buffer_hash(grl_env *env, const void *buf, size_t row_words, int32_t row
  * [2] games finished, [3] steps attempted on finished envs. */
 int grl_stats(grl_env *env, uint64_t out[4]);
 
+/* Number of CUDA kernels this env has launched since create (diagnostic; the oracle reports 0). */
+int grl_launch_count(grl_env *env, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1518,3 +1518,9 @@ int grlo_test_place_generals(int W, int H, int players, int spacing, int64_t see
   free(T);
   return st;
 }
+
+int grlo_launch_count(grlo_env *e, uint64_t *out) {
+  if (!e || !out) return GRL_ERR_INVALID_ARG;
+  *out = 0; /* no GPU work happens in the oracle */
+  return GRL_OK;
+}

@@ -1,0 +1,95 @@
+"""CPU-side checks of the product library: it loads, exports exactly what include/grlcuda.h
+declares, and its host-only entry points (config, map generation) agree with the oracle.
+No CUDA compute is attempted here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from generalsreinforcementlearning_b200 import _abi, build as grl_build
+from generalsreinforcementlearning_b200._abi import BoundLibrary, Config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "grlcuda.h")
+
+
+def header_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(grl_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def product_lib():
+    path = grl_build.build()
+    return BoundLibrary(path, "grl_")
+
+
+def test_header_and_binding_agree():
+    declared = header_functions()
+    bound = sorted("grl_" + n for n in _abi.ABI_FUNCTIONS)
+    assert declared == bound
+
+
+def test_product_exports_every_declared_symbol(product_lib):
+    for name in header_functions():
+        assert hasattr(product_lib.cdll, name), name
+    assert product_lib.abi_version() == 1
+
+
+def test_oracle_exports_the_same_abi(oracle_lib):
+    for name in header_functions():
+        assert hasattr(oracle_lib.cdll, "grlo_" + name[len("grl_"):]), name
+
+
+def test_struct_sizes_match_header():
+    # grl_action is 8 bytes; grl_config is 16 int32 + 11 floats
+    assert _abi.ACTION_DTYPE.itemsize == 8
+    assert C.sizeof(Config) == 16 * 4 + 11 * 4
+    assert C.sizeof(_abi.StepOutputs) == 7 * 8
+    assert C.sizeof(_abi.StatePlanes) == 14 * 8
+
+
+def test_default_config_matches_reference_and_oracle(product_lib, oracle_lib):
+    a, b = Config(), Config()
+    assert product_lib.default_config(C.byref(a)) == 0
+    assert oracle_lib.default_config(C.byref(b)) == 0
+    assert bytes(a) == bytes(b)
+    # internal/config/config.go:198-209, experience/rewards.go:23-37
+    assert (a.city_ratio, a.city_start_army, a.min_general_spacing) == (20, 40, 5)
+    assert (a.production_general, a.production_city, a.production_normal, a.normal_growth_interval) == (1, 1, 1, 25)
+    assert a.fog_of_war == 1
+    assert abs(a.reward.army_advantage - 0.05) < 1e-9 and a.reward.win_game == 1.0
+
+
+def test_bad_config_is_rejected_without_touching_cuda(product_lib):
+    cfg = Config()
+    product_lib.default_config(C.byref(cfg))
+    cfg.width = 33
+    h = C.c_void_p()
+    assert product_lib.create(C.byref(cfg), C.byref(h)) == -1
+    assert b"width" in product_lib.last_error()
+
+
+@pytest.mark.parametrize("W,H,P", [(5, 5, 2), (10, 10, 2), (15, 15, 2), (20, 20, 2), (20, 20, 4), (25, 25, 4),
+                                    (32, 32, 8), (8, 8, 2), (7, 13, 3)])
+def test_product_mapgen_matches_oracle(product_lib, oracle_lib, W, H, P):
+    """Host map generation in the product (grl_mapgen.cpp) and in the oracle are written
+    separately; both must give the reference's seeded maps."""
+    cfg = Config()
+    product_lib.default_config(C.byref(cfg))
+    cfg.width, cfg.height, cfg.num_players = W, H, P
+    N = W * H
+    seeds = [12345, 12346, 0, -7, 1, 42, 2**31 - 1, 2**31, 987654321987] + list(range(100, 140))
+    for seed in seeds:
+        outs = []
+        for lib in (product_lib, oracle_lib):
+            o, a, t = (np.zeros(N, np.int32) for _ in range(3))
+            st = lib.mapgen(C.byref(cfg), seed, o.ctypes.data, a.ctypes.data, t.ctypes.data)
+            outs.append((st, o, a, t))
+        assert outs[0][0] == outs[1][0], seed
+        if outs[0][0] == 0:
+            for x, y in zip(outs[0][1:], outs[1][1:]):
+                assert np.array_equal(x, y), seed

@@ -1,0 +1,85 @@
+"""BASELINE-size runs: parity through digests (too large to copy every plane back) and
+size-independent properties of the turn engine."""
+import numpy as np
+import pytest
+
+from generalsreinforcementlearning_b200 import _abi
+from helpers import new_engine
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("W,H,P,B,T", [(10, 10, 2, 65536, 40), (15, 15, 2, 32768, 30), (20, 20, 2, 16384, 60),
+                                        (20, 20, 4, 8192, 40)])
+def test_digest_parity_at_scale(cuda_lib, oracle_lib, W, H, P, B, T):
+    """Every env's full-state digest and its reward/done/mask planes match the oracle while
+    both play the same counter-based random policy (BASELINE configs 2-4)."""
+    import torch
+
+    gc = new_engine(cuda_lib, W, H, P, B, host_threads=0)
+    oc = new_engine(oracle_lib, W, H, P, B, host_threads=0)
+    seeds = np.arange(B, dtype=np.int64) + 12345
+    gc.reset_seeded(seeds)
+    oc.reset_seeded(seeds)
+    assert np.array_equal(gc.state_hash(), oc.state_hash())
+    dev = torch.device("cuda:0")
+    obs = torch.empty((B, P, 9, H, W), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, P, gc.mask_words), dtype=torch.int32, device=dev)
+    reward = torch.empty((B, P), dtype=torch.float32, device=dev)
+    done = torch.empty(B, dtype=torch.uint8, device=dev)
+    oo = oc.alloc_outputs_host()
+    oo_small = {k: oo[k] for k in ("mask_bits", "reward", "done")}
+    for t in range(T):
+        gc.step_fused(None, gc.outputs(obs=obs, mask_bits=mask, reward=reward, done=done),
+                      _abi.STEP_FLAG_RANDOM_POLICY, 2024)
+        with_obs = t % 10 == 9 or t == T - 1
+        oc.step_fused(None, oc.outputs(**(oo if with_obs else oo_small)), _abi.STEP_FLAG_RANDOM_POLICY, 2024)
+        assert np.array_equal(gc.state_hash(), oc.state_hash()), f"turn {t}"
+        assert np.array_equal(reward.cpu().numpy().view(np.uint32), oo["reward"].view(np.uint32)), f"turn {t}"
+        assert np.array_equal(done.cpu().numpy(), oo["done"]), f"turn {t}"
+        assert np.array_equal(mask.cpu().numpy().view(np.uint32), oo["mask_bits"]), f"turn {t}"
+        if with_obs:  # observation planes through row digests computed on the device
+            rows, words = B * P, 9 * W * H
+            assert np.array_equal(gc.buffer_hash(obs, words, rows), oc.buffer_hash(oo["obs"], words, rows)), f"turn {t}"
+    assert np.array_equal(gc.stats(), oc.stats())
+
+
+def test_properties_at_headline_size(cuda_lib):
+    """20x20 2p, 65,536 games: invariants that need no oracle."""
+    import torch
+
+    W, H, P, B = 20, 20, 2, 65536
+    e = new_engine(cuda_lib, W, H, P, B, host_threads=0)
+    seeds = np.arange(B, dtype=np.int64) % 4096 + 1  # 16 replicas of 4,096 distinct maps
+    e.reset_seeded(seeds)
+    dev = torch.device("cuda:0")
+    obs = torch.empty((B, P, 9, H, W), dtype=torch.float32, device=dev)
+    reward = torch.empty((B, P), dtype=torch.float32, device=dev)
+    acts = torch.empty((B, e.A, 8), dtype=torch.uint8, device=dev)
+    for t in range(50):
+        # replicas must receive identical moves: draw for the first 4,096 envs and tile them
+        e.sample_actions(7, acts)
+        tiled = acts[:4096].repeat(16, 1, 1).contiguous()
+        e.step_fused(tiled, e.outputs(obs=obs, reward=reward))
+    e.sync()
+    h = e.state_hash().reshape(16, 4096)
+    assert (h == h[0]).all(), "identical seeds + identical moves must give identical games"
+    o = obs.view(16, 4096, P, 9, H * W)
+    assert torch.equal(o[0], o[5]) and torch.equal(o[0], o[15])
+    # channel algebra of StateToTensor: visible + fog == 1; own/enemy/neutral/mountain partition the visible tiles
+    assert torch.equal(obs[:, :, 7] + obs[:, :, 8], torch.ones_like(obs[:, :, 7]))
+    part = obs[:, :, 2] + obs[:, :, 3] + obs[:, :, 4] + obs[:, :, 6]
+    assert torch.equal(part, obs[:, :, 7])
+    assert float(obs.min()) >= 0.0 and float(obs.max()) <= 1.0
+    st = e.get_state(0, 256)
+    # armies are conserved up to production: every tile army is non-negative and mountains stay empty/neutral
+    assert (st["army"] >= 0).all()
+    assert (st["owner"][st["type"] == 3] == -1).all() and (st["army"][st["type"] == 3] == 0).all()
+    assert (st["turn"] == 50).all()
+    # a step on finished games is idempotent
+    s2 = {k: v.copy() for k, v in st.items()}
+    s2["game_over"][:] = 1
+    e.set_state(s2, 0)
+    before = e.state_hash()[:256].copy()
+    e.step(None)
+    assert np.array_equal(e.state_hash()[:256], before)
