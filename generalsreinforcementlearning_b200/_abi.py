@@ -137,6 +137,7 @@ ABI_FUNCTIONS = {
     "create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "destroy": (C.c_int, [C.c_void_p]),
     "sync": (C.c_int, [C.c_void_p]),
+    "set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "get_config": (C.c_int, [C.c_void_p, C.POINTER(Config)]),
     "reset_seeded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "reset_boards": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

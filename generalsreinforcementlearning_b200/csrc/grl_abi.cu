@@ -50,7 +50,8 @@ struct grl_env {
   grl_config cfg;
   GrlLayout L;
   int N;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream work is issued on
+  cudaStream_t own_stream = nullptr;  // created by grl_create
   uint32_t *d_state = nullptr;
   uint32_t *d_static = nullptr;
   uint32_t *d_geom = nullptr;
@@ -482,8 +483,9 @@ int grl_create(const grl_config *cfg, grl_env **out) {
     grl_destroy(env);
     return code;
   };
-  if (cudaStreamCreateWithFlags(&env->stream, cudaStreamNonBlocking) != cudaSuccess)
+  if (cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(GRL_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(cudaGetLastError())));
+  env->stream = env->own_stream;
   const size_t sbytes = (size_t)cfg->num_envs * env->L.slab_words * 4;
   const size_t tbytes = (size_t)cfg->num_envs * env->L.static_words * 4;
   if (cudaMalloc((void **)&env->d_state, sbytes) != cudaSuccess || cudaMalloc((void **)&env->d_static, tbytes) != cudaSuccess ||
@@ -512,7 +514,7 @@ int grl_destroy(grl_env *env) {
   if (env->d_state) cudaFree(env->d_state);
   if (env->d_static) cudaFree(env->d_static);
   if (env->d_geom) cudaFree(env->d_geom);
-  if (env->stream) cudaStreamDestroy(env->stream);
+  if (env->own_stream) cudaStreamDestroy(env->own_stream);
   delete env;
   return GRL_OK;
 }
@@ -521,6 +523,14 @@ int grl_sync(grl_env *env) {
   if (!env) return fail(GRL_ERR_INVALID_ARG, "null env");
   CUDA_TRY(cudaSetDevice(env->cfg.device));
   CUDA_TRY(cudaStreamSynchronize(env->stream));
+  return GRL_OK;
+}
+
+int grl_set_stream(grl_env *env, void *cuda_stream) {
+  if (!env) return fail(GRL_ERR_INVALID_ARG, "null env");
+  CUDA_TRY(cudaSetDevice(env->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(env->stream));  // work already issued stays ordered
+  env->stream = static_cast<cudaStream_t>(cuda_stream);  // NULL is CUDA's default stream
   return GRL_OK;
 }
 

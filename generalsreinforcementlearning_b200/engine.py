@@ -90,6 +90,10 @@ class BatchedEngine:
     def sync(self) -> None:
         self.lib.check(self.lib.sync(self._h), "sync")
 
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        """Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self.lib.check(self.lib.set_stream(self._h, cuda_stream), "set_stream")
+
     # -- reset ---------------------------------------------------------------
     def reset_seeded(self, seeds: Sequence[int], env_ids: Optional[Sequence[int]] = None) -> None:
         seeds = np.ascontiguousarray(seeds, dtype=np.int64)

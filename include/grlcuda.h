@@ -182,6 +182,9 @@ int grl_default_config(grl_config *cfg);
 int grl_create(const grl_config *cfg, grl_env **out);
 int grl_destroy(grl_env *env);
 int grl_sync(grl_env *env);
+/* Run this env's work on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL is
+ * CUDA's default stream).  Lets a trainer order the step against its own kernels. */
+int grl_set_stream(grl_env *env, void *cuda_stream);
 int grl_get_config(const grl_env *env, grl_config *out);
 
 /* Reset `n` envs (env_ids NULL = all B in order) from seeds: map i is what

@@ -355,8 +355,11 @@ static void stats_full(game_t *g) {
 }
 
 /* stats.go:66-144 performIncrementalStatsUpdate.  Go iterates the
- * tempTileOwnership map in runtime-random order; ascending order is used here,
- * which fixes list ORDER and the GeneralIdx tie-break only. */
+ * tempTileOwnership map in runtime-random order; ascending order is used here, which
+ * fixes list ORDER only.  GeneralIdx is "the last general-type tile seen", which for a
+ * player holding two or more general-type tiles depends on that random order in Go
+ * (parity unpinned): the canonical choice here is the HIGHEST index, which
+ * is also what the full rebuild's ascending scan yields. */
 static void stats_incremental(game_t *g) {
   for (int p = 0; p < g->P; p++) {
     player_t *pl = &g->pl[p];
@@ -368,7 +371,7 @@ static void stats_incremental(game_t *g) {
       if (g->T[idx].owner == p) {
         pl->army_count += g->T[idx].army;
         pl->owned[n_new++] = idx; /* newOwnedTiles reuses the backing array */
-        if (g->T[idx].type == GRL_TILE_GENERAL) pl->general_idx = idx;
+        if (g->T[idx].type == GRL_TILE_GENERAL && idx > pl->general_idx) pl->general_idx = idx;
       }
     }
     for (int idx = 0; idx < g->N; idx++) {
@@ -382,7 +385,7 @@ static void stats_incremental(game_t *g) {
       if (!found) {
         pl->army_count += g->T[idx].army;
         pl->owned[n_new++] = idx;
-        if (g->T[idx].type == GRL_TILE_GENERAL) pl->general_idx = idx;
+        if (g->T[idx].type == GRL_TILE_GENERAL && idx > pl->general_idx) pl->general_idx = idx;
       }
     }
     pl->n_owned = n_new;
@@ -1010,6 +1013,10 @@ int grlo_create(const grl_config *c, grlo_env **out) {
     g->prev_army = (int *)calloc((size_t)e->N, sizeof(int));
     for (int p = 0; p < g->P; p++) g->pl[p].owned = (int *)calloc((size_t)e->N, sizeof(int));
     for (int i = 0; i < e->N; i++) g->T[i].owner = GRL_NEUTRAL;
+    for (int p = 0; p < g->P; p++) {
+      g->pl[p].general_idx = -1;
+      g->action_index[p] = -1;
+    }
     g->game_over = 1; /* not reset yet: stepping is rejected */
   }
   *out = e;
@@ -1026,6 +1033,12 @@ int grlo_destroy(grlo_env *e) {
 
 int grlo_sync(grlo_env *e) {
   (void)e;
+  return GRL_OK;
+}
+
+int grlo_set_stream(grlo_env *e, void *stream) {
+  (void)e;
+  (void)stream;
   return GRL_OK;
 }
 
@@ -1322,15 +1335,7 @@ int grlo_get_state(grlo_env *e, int32_t first, int32_t count, const grl_state_pl
     for (int p = 0; p < P; p++) {
       if (o->alive) o->alive[(size_t)c * P + p] = g->pl[p].alive;
       if (o->army_count) o->army_count[(size_t)c * P + p] = g->pl[p].army_count;
-      if (o->general_idx) {
-        /* canonical tie-break: highest general-type tile in the list (header note) */
-        int gi = -1;
-        for (int k = 0; k < g->pl[p].n_owned; k++) {
-          int idx = g->pl[p].owned[k];
-          if (g->T[idx].type == GRL_TILE_GENERAL && g->T[idx].owner == p && idx > gi) gi = idx;
-        }
-        o->general_idx[(size_t)c * P + p] = g->pl[p].general_idx == -1 ? -1 : gi;
-      }
+      if (o->general_idx) o->general_idx[(size_t)c * P + p] = g->pl[p].general_idx;
     }
   }
   return GRL_OK;

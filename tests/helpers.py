@@ -84,22 +84,14 @@ def one_action(engine, player, fx, fy, tx, ty, move_all=True, env=0, slot=0, act
 
 
 def compare_states(a, b, ctx=""):
-    """Bit-exact comparison of two get_state() dicts.  general_idx is compared only where
-    it is pinned (a player holding exactly one general-type tile in its list)."""
+    """Bit-exact comparison of two get_state() dicts (general_idx uses the canonical
+    highest-index tie-break in both implementations)."""
     for k in a:
-        if k == "general_idx":
-            continue
         if not np.array_equal(a[k], b[k]):
             bad = np.argwhere(np.asarray(a[k]) != np.asarray(b[k]))
             raise AssertionError(f"{ctx}: state plane {k!r} differs at {bad[:8].tolist()} "
                                  f"({len(bad)} cells): {np.asarray(a[k])[tuple(bad[0])]} vs "
                                  f"{np.asarray(b[k])[tuple(bad[0])]}")
-    gen = (a["type"] == GENERAL)[:, None, :] & (a["owned"] != 0) & (a["owner"][:, None, :] ==
-                                                                   np.arange(a["owned"].shape[1])[None, :, None])
-    pinned = gen.sum(-1) <= 1
-    ga, gb = a["general_idx"], b["general_idx"]
-    if not np.array_equal(ga[pinned], gb[pinned]):
-        raise AssertionError(f"{ctx}: general_idx differs: {ga} vs {gb}")
 
 
 def ctypes_fn(lib, name, restype, argtypes):

@@ -89,7 +89,7 @@ def rollout_compare(cuda_lib, oracle_lib, W, H, P, B, T, seed, err_rate=0.0, pol
 
 
 @pytest.mark.parametrize("W,H,P", [(10, 10, 2), (15, 15, 2), (20, 20, 2), (20, 20, 4), (5, 5, 2), (7, 13, 3),
-                                    (12, 9, 1), (32, 32, 8), (6, 6, 5)])
+                                    (12, 9, 1), (32, 32, 8), (14, 11, 5)])
 def test_seeded_rollout_parity(cuda_lib, oracle_lib, W, H, P):
     gc, _ = rollout_compare(cuda_lib, oracle_lib, W, H, P, B=48, T=120, seed=W * 100 + P)
     assert gc.stats()[0] > 0
