@@ -182,10 +182,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 template <int PT>
 __device__ __forceinline__ void stats_update(const GrlKParams &prm, SlabView &S, const uint32_t (&own)[PT],
                                              uint32_t (&lst)[PT], uint32_t chg, uint32_t G, uint32_t &alive, int lane,
-                                             bool force_full) {
+                                             int N, int NW) {
   int c = __reduce_add_sync(FULL, __popc(chg));
-  if (c == 0 && !force_full) return;  // stats.go:11-15 (turn > 0 inside a step)
-  bool full = force_full || c > prm.N / 5;  // stats.go:20-25
+  if (c == 0) return;               // stats.go:11-15 (turn > 0 inside a step)
+  const bool full = c > N / 5;      // stats.go:20-25
 #pragma unroll
   for (int p = 0; p < PT; p++) {
     if (p < prm.P) {
@@ -193,7 +193,7 @@ __device__ __forceinline__ void stats_update(const GrlKParams &prm, SlabView &S,
       uint32_t orphan = own[p] & ~lst[p];
       int true_army = (int)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY];
       int corr = 0;
-      if (__any_sync(FULL, orphan != 0u)) corr = sum_army_over(orphan, S.army, prm.NW, prm.N, lane);
+      if (__any_sync(FULL, orphan != 0u)) corr = sum_army_over(orphan, S.army, NW, N, lane);
       uint32_t gen = lst[p] & G;
       int gi = gen ? (32 * lane + 31 - __clz(gen)) : -1;
       gi = __reduce_max_sync(FULL, gi);
@@ -307,21 +307,65 @@ __device__ __forceinline__ PackedAction sample_policy_action(const GrlKParams &p
 
 // ---------------------------------------------------------------------------------------
 // The fused turn kernel.  DO_STEP: ProcessTurn.  DO_OUT: observation / mask / reward / done.
+// TW/TH > 0 bake the board geometry in (the BASELINE sizes): loop trip counts, channel strides
+// and x/y arithmetic become immediates.  TW == 0 reads the geometry from the parameter block.
 // ---------------------------------------------------------------------------------------
-template <int PT, bool DO_STEP, bool DO_OUT>
-__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
+
+// One decoded move, staged in shared memory as two words.  The checks that depend only on the
+// action itself (core/action.go:58-79) run on one lane per slot, in parallel; the checks that
+// depend on the board (ownership, army, mountain) run in the serial phase.
+//   word0: fi[0:10) ti[10:20) player[20:23) moveAll[23] staticErr[24:28) present[28]
+//   word1: Serializer.ActionToIndex (serializer.go:179-198)
+__device__ __forceinline__ uint2 decode_action(uint2 raw, int W, int H, int P) {
+  PackedAction a;
+  a.lo = raw.x;
+  a.hi = raw.y;
+  const int pid = a.player();
+  if (!a.present() || pid < 0 || pid >= P) return make_uint2(0u, 0xffffffffu);  // action_processor.go:56-60
+  const int fx = a.fx(), fy = a.fy(), tx = a.tx(), ty = a.ty();
+  const int ddx = tx - fx, ddy = ty - fy;
+  int dir = 0;
+  if (ddy == -1 && ddx == 0) dir = 0;
+  else if (ddy == 1 && ddx == 0) dir = 1;
+  else if (ddy == 0 && ddx == -1) dir = 2;
+  else if (ddy == 0 && ddx == 1) dir = 3;
+  const int aidx = (fy * W + fx) * 4 + dir;
+  uint32_t e = 0;
+  if ((unsigned)fx >= (unsigned)W || (unsigned)fy >= (unsigned)H) e = GRL_STEP_INVALID_COORDINATES;
+  else if ((unsigned)tx >= (unsigned)W || (unsigned)ty >= (unsigned)H) e = GRL_STEP_INVALID_COORDINATES;
+  else if (ddx == 0 && ddy == 0) e = GRL_STEP_MOVE_TO_SELF;
+  else if (!((ddx == 0 && (ddy == 1 || ddy == -1)) || (ddy == 0 && (ddx == 1 || ddx == -1)))) e = GRL_STEP_NOT_ADJACENT;
+  const uint32_t fi = e == GRL_STEP_INVALID_COORDINATES ? 0u : (uint32_t)(fy * W + fx);
+  const uint32_t ti = e == GRL_STEP_INVALID_COORDINATES ? 0u : (uint32_t)(ty * W + tx);
+  uint32_t w = fi | (ti << 10) | ((uint32_t)pid << 20) | ((a.move_all() ? 1u : 0u) << 23) | (e << 24) | (1u << 28);
+  return make_uint2(w, (uint32_t)aidx);
+}
+
+template <int PT>
+struct TurnOccupancy {  // CTAs of 256 threads per SM the register budget is tuned for
+  static constexpr int kMinBlocks = PT <= 2 ? 4 : (PT <= 4 ? 3 : 2);
+};
+
+template <int PT, int TW, int TH, bool DO_STEP, bool DO_OUT>
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMinBlocks)
     grl_turn_kernel(const __grid_constant__ GrlKParams prm) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t s_bar[GRL_WARPS_PER_CTA];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GrlLayout &L = prm.L;
-  const int P = prm.P, NW = prm.NW, N = prm.N, W = prm.W;
+  const int P = prm.P;
+  const int W = TW ? TW : prm.W;
+  const int H = TW ? TH : prm.H;
+  const int N = TW ? TW * TH : prm.N;
+  const int NW = TW ? (TW * TH + 31) / 32 : prm.NW;
   const int act_words = 2 * GRL_MAX_ACTIONS;
   const int per_warp = L.slab_words + L.static_words + act_words;
   uint32_t *s = smem + warp * per_warp;
   uint32_t *st = s + L.slab_words;
   uint32_t *s_act = st + L.static_words;
   SlabView S = make_view(s, st, L);
+  S.C = st + NW;
+  S.G = st + 2 * NW;
 
   Geo g;
   g.lane = lane;
@@ -330,6 +374,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
   g.nc0 = prm.geom[32 + lane];
   g.ncl = prm.geom[64 + lane];
   const bool act_lane = lane < NW;
+  const uint32_t pmask = (1u << P) - 1u;
 
   if (prm.use_tma && lane == 0) {
     mbar_init(&s_bar[warp], 1);
@@ -351,6 +396,19 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
         tma_load(s, gslab, (uint32_t)L.slab_words * 4u, &s_bar[warp]);
         tma_load(st, gstat, (uint32_t)L.static_words * 4u, &s_bar[warp]);
       }
+    }
+    // the action slots do not depend on the slab: decode them while the bulk copy is in flight
+    const bool use_policy = DO_STEP && (prm.flags & GRL_STEP_FLAG_RANDOM_POLICY) != 0;
+    if (DO_STEP) {
+      if (lane < GRL_MAX_ACTIONS) {
+        uint2 d = make_uint2(0u, 0xffffffffu);
+        if (!use_policy && prm.actions != nullptr && lane < prm.A)
+          d = decode_action(__ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)game * prm.A + lane), W, H, P);
+        s_act[2 * lane] = d.x;
+        s_act[2 * lane + 1] = d.y;
+      }
+    }
+    if (prm.use_tma) {
       mbar_wait(&s_bar[warp], tma_phase);
       tma_phase ^= 1u;
     } else {
@@ -360,8 +418,8 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
       const uint4 *src2 = reinterpret_cast<const uint4 *>(gstat);
       uint4 *dst2 = reinterpret_cast<uint4 *>(st);
       for (int k = lane; k < L.static_words / 4; k += 32) dst2[k] = __ldg(src2 + k);
-      __syncwarp();
     }
+    __syncwarp();
 
     // ---- mask words into registers -----------------------------------------------------
     uint32_t own[PT], lst[PT], vis[PT], own_prev[PT];
@@ -407,12 +465,6 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
         turn += 1;  // turn_processor.go:125
 
         // ---- the synthetic policy reads the PRE-turn state (all players at once) ----------
-        const bool use_policy = (prm.flags & GRL_STEP_FLAG_RANDOM_POLICY) != 0;
-        if (lane < GRL_MAX_ACTIONS) {
-          s_act[2 * lane] = 0u;
-          s_act[2 * lane + 1] = 0u;
-        }
-        __syncwarp();
         if (use_policy) {
           uint32_t gt1 = army_gt1_mask(S.army, NW, N, lane);
           DirMasks dm = dir_targets(M, g);
@@ -421,18 +473,12 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
             if (p < P && p < prm.A) {
               uint32_t src = ((alive >> p) & 1u) ? (lst[p] & own[p] & gt1) : 0u;
               PackedAction a = sample_policy_action(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn_before, g);
-              if (lane == 0) {
-                s_act[2 * p] = a.lo;
-                s_act[2 * p + 1] = a.hi;
+              if (lane == 0 && a.present()) {
+                uint2 d = decode_action(make_uint2(a.lo, a.hi), W, H, P);
+                s_act[2 * p] = d.x;
+                s_act[2 * p + 1] = d.y;
               }
             }
-          }
-        } else if (prm.actions != nullptr) {
-          if (lane < prm.A) {
-            const uint2 *ga = reinterpret_cast<const uint2 *>(prm.actions) + (size_t)game * prm.A;
-            uint2 a = ga[lane];
-            s_act[2 * lane] = a.x;
-            s_act[2 * lane + 1] = a.y;
           }
         }
 
@@ -463,6 +509,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
           S.chg[lane] = 0u;
           S.vch[lane] = 0u;
         }
+        if (lane < P) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ACTION_INDEX] = 0xffffffffu;
         __syncwarp();
 
         // ---- actions: serial by definition, one lane, on the shared-memory slab -----------
@@ -472,44 +519,19 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
           uint32_t processed = 0;
           uint32_t overflow = 0;
           const uint32_t alive_start = alive;  // action_processor.go:56-60 reads Alive as of now
-          int aidx[PT];
-#pragma unroll
-          for (int p = 0; p < PT; p++) aidx[p] = -1;
+          uint32_t *ta = &S.hdr[GRL_HDR_PLAYER0 + GRL_PL_TRUE_ARMY];
           // stable sort by player id == for each id ascending, slots in submission order
           for (int p = 0; p < P; p++) {
             for (int sl = 0; sl < prm.A; sl++) {
-              PackedAction a;
-              a.lo = s_act[2 * sl];
-              a.hi = s_act[2 * sl + 1];
-              if (!a.present() || a.player() != p) continue;
-              const int fx = a.fx(), fy = a.fy(), tx = a.tx(), ty = a.ty();
-              {  // collectExperiences: Serializer.ActionToIndex, last submission wins
-                int ddx = tx - fx, ddy = ty - fy, dir = 0;
-                if (ddy == -1 && ddx == 0) dir = 0;
-                else if (ddy == 1 && ddx == 0) dir = 1;
-                else if (ddy == 0 && ddx == -1) dir = 2;
-                else if (ddy == 0 && ddx == 1) dir = 3;
-                int ai = (fy * W + fx) * 4 + dir;
-#pragma unroll
-                for (int q = 0; q < PT; q++)
-                  if (q == p) aidx[q] = ai;
-              }
+              const uint32_t w = s_act[2 * sl];
+              if (!(w >> 28) || (int)((w >> 20) & 7u) != p) continue;
+              // collectExperiences keys the action map by player: the last submission wins
+              S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ACTION_INDEX] = s_act[2 * sl + 1];
               if (!((alive_start >> p) & 1u)) continue;
-              // core/action.go:56-105 Validate
-              uint32_t e = 0;
-              if ((unsigned)fx >= (unsigned)W || (unsigned)fy >= (unsigned)prm.H) e = GRL_STEP_INVALID_COORDINATES;
-              else if ((unsigned)tx >= (unsigned)W || (unsigned)ty >= (unsigned)prm.H) e = GRL_STEP_INVALID_COORDINATES;
-              else if (fx == tx && fy == ty) e = GRL_STEP_MOVE_TO_SELF;
-              else {
-                int ddx = fx - tx, ddy = fy - ty;
-                bool adj = (ddx == 0 && (ddy == 1 || ddy == -1)) || (ddy == 0 && (ddx == 1 || ddx == -1));
-                if (!adj) e = GRL_STEP_NOT_ADJACENT;
-              }
-              int fi = 0, ti = 0;
+              uint32_t e = (w >> 24) & 0xfu;
+              const int fi = (int)(w & 1023u), ti = (int)((w >> 10) & 1023u);
               uint32_t a_from = 0;
-              if (!e) {
-                fi = fy * W + fx;
-                ti = ty * W + tx;
+              if (!e) {  // board-dependent half of core/action.go:56-105 Validate
                 if (!((S.own[p * NW + (fi >> 5)] >> (fi & 31)) & 1u)) e = GRL_STEP_NOT_OWNED;
                 else {
                   a_from = S.army[fi];
@@ -522,14 +544,14 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
                 continue;
               }
               // core/movement.go:23-89 ApplyMoveAction
-              uint32_t moved = a.move_all() ? a_from - 1u : (a_from / 2u == 0u ? 1u : a_from / 2u);
+              const bool move_all = (w >> 23) & 1u;
+              uint32_t moved = move_all ? a_from - 1u : (a_from / 2u == 0u ? 1u : a_from / 2u);
               S.army[fi] = (uint16_t)(a_from - moved);
               S.chg[fi >> 5] |= 1u << (fi & 31);
               const int tw = ti >> 5;
               const uint32_t tb = 1u << (ti & 31);
               S.chg[tw] |= tb;
               uint32_t a_to = S.army[ti];
-              uint32_t *ta = &S.hdr[GRL_HDR_PLAYER0 + GRL_PL_TRUE_ARMY];
               ta[GRL_HDR_PER_PLAYER * p] -= moved;
               if (S.own[p * NW + tw] & tb) {
                 uint32_t sum = a_to + moved;
@@ -567,17 +589,11 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
               }
             }
           }
-          for (int p = 0; p < P; p++)
-#pragma unroll
-            for (int q = 0; q < PT; q++)
-              if (q == p) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ACTION_INDEX] = (uint32_t)aidx[q];
           if (overflow) S.hdr[GRL_HDR_OVERFLOW] = 1u;
         }
         __syncwarp();
         err = __shfl_sync(FULL, err, 0);
         n_orders = __shfl_sync(FULL, n_orders, 0);
-        ord_lo = __shfl_sync(FULL, ord_lo, 0);
-        ord_hi = __shfl_sync(FULL, ord_hi, 0);
 #pragma unroll
         for (int p = 0; p < PT; p++)
           if (p < P && act_lane) own[p] = S.own[p * NW + lane];
@@ -588,6 +604,8 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
 
         // ---- eliminations + tile turnover over the CACHED list (engine.go:118-152) --------
         if (n_orders > 0) {
+          ord_lo = __shfl_sync(FULL, ord_lo, 0);
+          ord_hi = __shfl_sync(FULL, ord_hi, 0);
           for (int o = 0; o < n_orders; o++) {
             uint32_t ob = (o < 4 ? (ord_lo >> (8 * o)) : (ord_hi >> (8 * (o - 4)))) & 0xffu;
             int el = (int)(ob & 0xfu), nw = (int)(ob >> 4);
@@ -612,7 +630,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
             alive &= ~(1u << el);
           }
           __syncwarp();
-          stats_update<PT>(prm, S, own, lst, chg, G, alive, lane, false);  // engine.go:107
+          stats_update<PT>(prm, S, own, lst, chg, G, alive, lane, N, NW);  // engine.go:107
         }
 
         if (err == 0) {
@@ -671,8 +689,8 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
             __syncwarp();
           }
           // ---- end of turn: stats, game over (turn_processor.go:170-179) --------------------
-          stats_update<PT>(prm, S, own, lst, chg, G, alive, lane, false);
-          int n_alive = __popc(alive & ((1u << P) - 1u));
+          stats_update<PT>(prm, S, own, lst, chg, G, alive, lane, N, NW);
+          int n_alive = __popc(alive & pmask);
           bool now_over = P > 1 ? (n_alive <= 1) : (n_alive == 0);  // win_conditions.go:38-44
           if (now_over && !over && lane == 0) S.hdr[GRL_HDR_FINISHED] += 1;
           over = now_over;
@@ -688,8 +706,8 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
 
     // ---- reward: CalculateRewardWithConfig(prev, curr, p) (rewards.go:45-85) -------------
     if (DO_STEP && stepped) {
-      int n_alive = __popc(alive & ((1u << P) - 1u));
-      int sole = n_alive == 1 ? (__ffs(alive & ((1u << P) - 1u)) - 1) : -1;
+      int n_alive = __popc(alive & pmask);
+      int sole = n_alive == 1 ? (__ffs(alive & pmask) - 1) : -1;
       int total_army = 0;
 #pragma unroll
       for (int p = 0; p < PT; p++)
@@ -772,7 +790,6 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
 
     // ---- read-outs ---------------------------------------------------------------------------
     if (DO_OUT) {
-      const uint32_t pmask = (1u << P) - 1u;
       if (lane == 0) {
         if (prm.done) prm.done[game] = over ? 1 : 0;
         if (prm.winner) {  // engine.go:248-263
@@ -807,7 +824,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
               uint32_t bu = __shfl_sync(FULL, U, srcl) >> sh, br = __shfl_sync(FULL, R, srcl) >> sh;
               uint32_t bd = __shfl_sync(FULL, D, srcl) >> sh, bl = __shfl_sync(FULL, Lm, srcl) >> sh;
               uint32_t w = spread8(bu) | (spread8(br) << 1) | (spread8(bd) << 2) | (spread8(bl) << 3);
-              if (k < words) dst[k] = w;
+              if (k < words) __stcs(dst + k, w);
             }
           }
         }
@@ -819,29 +836,37 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
 #pragma unroll
         for (int p = 0; p < PT; p++) any_own |= own[p];
         const uint32_t CG = C | G;
+        float *gbase = prm.obs + (size_t)game * P * GRL_OBS_CHANNELS * N;
+        if ((N & 3) == 0) {
+          // 128-bit path: a lane writes 4 consecutive tiles of each channel plane; the army
+          // conversion and the terrain nibbles are shared by all players' views
+          const int cs = N / 4;  // channel stride in float4
+          for (int q0 = 0; q0 * 4 < N; q0 += 32) {
+            const int q = q0 + lane;
+            const int t0 = 4 * q;
+            const int srcl = (t0 >> 5) & 31, sh = t0 & 31;
+            const uint32_t mM = (__shfl_sync(FULL, M, srcl) >> sh) & 0xfu;
+            const uint32_t mCG = (__shfl_sync(FULL, CG, srcl) >> sh) & 0xfu;
+            const uint32_t mAny = (__shfl_sync(FULL, any_own, srcl) >> sh) & 0xfu;
+            const bool live = t0 < N;
+            float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+            if (live) {
+              const uint2 aw = *reinterpret_cast<const uint2 *>(S.army + t0);
+              f0 = army_frac(aw.x & 0xffffu);
+              f1 = army_frac(aw.x >> 16);
+              f2 = army_frac(aw.y & 0xffffu);
+              f3 = army_frac(aw.y >> 16);
+            }
 #pragma unroll
-        for (int p = 0; p < PT; p++) {
-          if (p < P) {
-            const uint32_t V = prm.fog ? vis[p] : g.valid;
-            const uint32_t w7 = V, w8 = ~V & g.valid, w6 = V & M, nm = V & ~M;
-            const uint32_t w5 = nm & CG, w2 = nm & own[p], w3 = nm & any_own & ~own[p], w4 = nm & ~any_own;
-            float *base = prm.obs + ((size_t)game * P + p) * GRL_OBS_CHANNELS * N;
-            if ((N & 3) == 0) {
-              // 128-bit path: a lane writes 4 consecutive tiles of each channel plane
-              for (int q0 = 0; q0 * 4 < N; q0 += 32) {
-                const int q = q0 + lane;
-                const int t0 = 4 * q;
-                const int srcl = (t0 >> 5) & 31, sh = t0 & 31;
-                const uint32_t n7 = (__shfl_sync(FULL, w7, srcl) >> sh) & 0xfu, n8 = (__shfl_sync(FULL, w8, srcl) >> sh) & 0xfu;
-                const uint32_t n6 = (__shfl_sync(FULL, w6, srcl) >> sh) & 0xfu, n5 = (__shfl_sync(FULL, w5, srcl) >> sh) & 0xfu;
-                const uint32_t n2 = (__shfl_sync(FULL, w2, srcl) >> sh) & 0xfu, n3 = (__shfl_sync(FULL, w3, srcl) >> sh) & 0xfu;
-                const uint32_t n4 = (__shfl_sync(FULL, w4, srcl) >> sh) & 0xfu;
-                if (t0 < N) {
-                  const uint2 aw = *reinterpret_cast<const uint2 *>(S.army + t0);
-                  const float f0 = army_frac(aw.x & 0xffffu), f1 = army_frac(aw.x >> 16);
-                  const float f2 = army_frac(aw.y & 0xffffu), f3 = army_frac(aw.y >> 16);
-                  float4 *o = reinterpret_cast<float4 *>(base + t0);
-                  const int cs = N / 4;  // channel stride in float4
+            for (int p = 0; p < PT; p++) {
+              if (p < P) {
+                const uint32_t nV = prm.fog ? ((__shfl_sync(FULL, vis[p], srcl) >> sh) & 0xfu) : 0xfu;
+                const uint32_t nO = (__shfl_sync(FULL, own[p], srcl) >> sh) & 0xfu;
+                if (live) {
+                  const uint32_t nm = nV & ~mM;
+                  const uint32_t n2 = nm & nO, n3 = nm & mAny & ~nO, n4 = nm & ~mAny, n5 = nm & mCG, n6 = nV & mM;
+                  const uint32_t n7 = nV, n8 = nV ^ 0xfu;
+                  float4 *o = reinterpret_cast<float4 *>(gbase + (size_t)p * GRL_OBS_CHANNELS * N + t0);
 #define NIBF(n) make_float4(((n)&1u) ? 1.f : 0.f, ((n)&2u) ? 1.f : 0.f, ((n)&4u) ? 1.f : 0.f, ((n)&8u) ? 1.f : 0.f)
 #define NIBA(n) make_float4(((n)&1u) ? f0 : 0.f, ((n)&2u) ? f1 : 0.f, ((n)&4u) ? f2 : 0.f, ((n)&8u) ? f3 : 0.f)
                   __stcs(o + 0 * cs, NIBA(n2));
@@ -857,17 +882,25 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
 #undef NIBA
                 }
               }
-            } else {
-              // generic path (N % 4 != 0, e.g. 15x15): one tile per lane, coalesced 32-bit stores
-              for (int i = 0; i < NW; i++) {
-                const int t = 32 * i + lane;
-                const uint32_t b7 = (__shfl_sync(FULL, w7, i) >> lane) & 1u, b8 = (__shfl_sync(FULL, w8, i) >> lane) & 1u;
-                const uint32_t b6 = (__shfl_sync(FULL, w6, i) >> lane) & 1u, b5 = (__shfl_sync(FULL, w5, i) >> lane) & 1u;
-                const uint32_t b2 = (__shfl_sync(FULL, w2, i) >> lane) & 1u, b3 = (__shfl_sync(FULL, w3, i) >> lane) & 1u;
-                const uint32_t b4 = (__shfl_sync(FULL, w4, i) >> lane) & 1u;
-                if (t < N) {
-                  const float f = army_frac((uint32_t)S.army[t]);
-                  float *o = base + t;
+            }
+          }
+        } else {
+          // generic path (N % 4 != 0, e.g. 15x15): one tile per lane, coalesced 32-bit stores
+          for (int i = 0; i < NW; i++) {
+            const int t = 32 * i + lane;
+            const uint32_t bM = (__shfl_sync(FULL, M, i) >> lane) & 1u, bCG = (__shfl_sync(FULL, CG, i) >> lane) & 1u;
+            const uint32_t bAny = (__shfl_sync(FULL, any_own, i) >> lane) & 1u;
+            const bool live = t < N;
+            const float f = live ? army_frac((uint32_t)S.army[t]) : 0.f;
+#pragma unroll
+            for (int p = 0; p < PT; p++) {
+              if (p < P) {
+                const uint32_t bV = prm.fog ? ((__shfl_sync(FULL, vis[p], i) >> lane) & 1u) : 1u;
+                const uint32_t bO = (__shfl_sync(FULL, own[p], i) >> lane) & 1u;
+                if (live) {
+                  const uint32_t nm = bV & ~bM;
+                  const uint32_t b2 = nm & bO, b3 = nm & bAny & ~bO, b4 = nm & ~bAny & 1u, b5 = nm & bCG, b6 = bV & bM;
+                  float *o = gbase + (size_t)p * GRL_OBS_CHANNELS * N + t;
                   __stcs(o + 0 * N, b2 ? f : 0.f);
                   __stcs(o + 1 * N, b3 ? f : 0.f);
                   __stcs(o + 2 * N, b2 ? 1.f : 0.f);
@@ -875,8 +908,8 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
                   __stcs(o + 4 * N, b4 ? 1.f : 0.f);
                   __stcs(o + 5 * N, b5 ? 1.f : 0.f);
                   __stcs(o + 6 * N, b6 ? 1.f : 0.f);
-                  __stcs(o + 7 * N, b7 ? 1.f : 0.f);
-                  __stcs(o + 8 * N, b8 ? 1.f : 0.f);
+                  __stcs(o + 7 * N, bV ? 1.f : 0.f);
+                  __stcs(o + 8 * N, bV ? 0.f : 1.f);
                 }
               }
             }
@@ -1135,10 +1168,10 @@ size_t grl_turn_smem_bytes(const GrlLayout &L) {
   return (size_t)GRL_WARPS_PER_CTA * (size_t)(L.slab_words + L.static_words + 2 * GRL_MAX_ACTIONS) * 4u;
 }
 
-template <int PT, bool S, bool O>
+template <int PT, int TW, int TH, bool S, bool O>
 static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream) {
   size_t smem = grl_turn_smem_bytes(prm.L);
-  auto kern = grl_turn_kernel<PT, S, O>;
+  auto kern = grl_turn_kernel<PT, TW, TH, S, O>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1147,11 +1180,22 @@ static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+template <int PT, int TW, int TH>
+static cudaError_t launch_turn_g(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream) {
+  if (do_step && do_out) return launch_turn_t<PT, TW, TH, true, true>(prm, stream);
+  if (do_step) return launch_turn_t<PT, TW, TH, true, false>(prm, stream);
+  return launch_turn_t<PT, TW, TH, false, true>(prm, stream);
+}
+
+// the BASELINE board sizes get kernels with the geometry baked in; everything else is generic
 template <int PT>
 static cudaError_t launch_turn_p(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream) {
-  if (do_step && do_out) return launch_turn_t<PT, true, true>(prm, stream);
-  if (do_step) return launch_turn_t<PT, true, false>(prm, stream);
-  return launch_turn_t<PT, false, true>(prm, stream);
+  if (PT <= 4) {
+    if (prm.W == 20 && prm.H == 20) return launch_turn_g<PT, 20, 20>(prm, do_step, do_out, stream);
+    if (prm.W == 15 && prm.H == 15) return launch_turn_g<PT, 15, 15>(prm, do_step, do_out, stream);
+    if (prm.W == 10 && prm.H == 10) return launch_turn_g<PT, 10, 10>(prm, do_step, do_out, stream);
+  }
+  return launch_turn_g<PT, 0, 0>(prm, do_step, do_out, stream);
 }
 
 static int player_template(int P) { return P <= 2 ? 2 : (P <= 4 ? 4 : 8); }
