@@ -302,6 +302,12 @@ def run_cuda(args):
     total_steps = sum_over_ranks(env_steps)
     value = total_steps / (ms_max * 1e-3)
     del drec
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms_max / K, "lib": os.environ.get("GRL_LIB_PATH", "default"),
+                              "clocks": clocks}))
+        e.close()
+        return 0
 
     # ---------------- end-to-end arm: host actions in, host results out, every step ----------
     h_reward = torch.empty((B, P), dtype=torch.float32).pin_memory()
@@ -401,6 +407,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU, help="games resident per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident arm only (kernel experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -13,7 +13,8 @@ from ._abi import BoundLibrary, Config, StepOutputs, StatePlanes, ACTION_DTYPE  
 from .engine import BatchedEngine, make_actions, make_config, set_action  # noqa: F401
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libgrlcuda.so")
+# GRL_LIB_PATH selects an experiment build of the same CUDA library (profiling variants)
+LIB_PATH = os.environ.get("GRL_LIB_PATH") or os.path.join(_PKG_DIR, "csrc", "libgrlcuda.so")
 
 _lib = None
 

@@ -34,17 +34,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """defines/out build experiment variants (e.g. -DGRL_PERSISTENT=1) next to the product library."""
+    if not force and out == LIB and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = ([nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+           + ["-o", out] + SOURCES)
     proc = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout)
         raise RuntimeError("nvcc failed building libgrlcuda.so")
     if verbose:
         print(proc.stdout)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

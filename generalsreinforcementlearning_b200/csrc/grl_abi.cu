@@ -57,6 +57,9 @@ struct grl_env {
   uint32_t *d_geom = nullptr;
   Scratch scratch[SL_COUNT];
   int use_tma = 1;
+  int prefetch_dist = 0;       // > 0: warp of game g prefetches the slab of game g+dist into L2
+  size_t l2_window_bytes = 0;  // > 0: launch the turn kernel with a persisting-L2 window over the state
+  float l2_hit_ratio = 1.0f;
   uint64_t launches = 0;
   int host_threads = 1;
 };
@@ -110,6 +113,9 @@ GrlKParams base_params(const grl_env *env) {
   p.grow_interval = c.normal_growth_interval;
   p.env_id_base = c.env_id_base;
   p.use_tma = env->use_tma;
+  p.prefetch_dist = env->prefetch_dist;
+  p.l2_window_bytes = env->l2_window_bytes;
+  p.l2_hit_ratio = env->l2_hit_ratio;
   const grl_reward_config &r = c.reward;
   const float rw[11] = {r.win_game,        r.lose_game,        r.capture_city, r.lose_city, r.capture_general, r.lose_general,
                         r.territory_gained, r.territory_lost, r.army_gained,  r.army_lost, r.army_advantage};
@@ -479,6 +485,8 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   env->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (hw > 0 ? hw : 1);
   const char *no_tma = getenv("GRL_NO_TMA");
   env->use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
+  const char *pf = getenv("GRL_PREFETCH_DIST");
+  env->prefetch_dist = pf ? atoi(pf) : 0;
   auto bail = [&](int code) {
     grl_destroy(env);
     return code;
@@ -488,9 +496,34 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   env->stream = env->own_stream;
   const size_t sbytes = (size_t)cfg->num_envs * env->L.slab_words * 4;
   const size_t tbytes = (size_t)cfg->num_envs * env->L.static_words * 4;
-  if (cudaMalloc((void **)&env->d_state, sbytes) != cudaSuccess || cudaMalloc((void **)&env->d_static, tbytes) != cudaSuccess ||
-      cudaMalloc((void **)&env->d_geom, 96 * 4) != cudaSuccess)
+  // one allocation [state | terrain | geometry]: a single L2 access-policy window can cover it
+  const size_t sbytes_al = (sbytes + 255) & ~(size_t)255, tbytes_al = (tbytes + 255) & ~(size_t)255;
+  if (cudaMalloc((void **)&env->d_state, sbytes_al + tbytes_al + 96 * 4) != cudaSuccess)
     return bail(fail(GRL_ERR_NOMEM, "cudaMalloc of %zu state bytes: %s", sbytes + tbytes, cudaGetErrorString(cudaGetLastError())));
+  env->d_static = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(env->d_state) + sbytes_al);
+  env->d_geom = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(env->d_static) + tbytes_al);
+  env->l2_window_bytes = 0;
+  {
+    // Keep the game state resident in the 126 MB L2 across steps when it fits: the observation
+    // stream is written evict-first, the slabs are re-read and re-written every turn.
+    const char *l2 = getenv("GRL_L2_PERSIST");
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cfg->device);
+    // Opt-in (GRL_L2_PERSIST=1): measured 2.3x SLOWER at 65,536 20x20 games on B200 — carving 95 MB
+    // of persisting L2 starves the 2 GB/step observation write stream (profiles/r1_variants.md).
+    if (l2 && l2[0] == '1' && max_persist > 0 && max_window > 0) {
+      size_t want = sbytes_al + tbytes_al;
+      size_t window = want < (size_t)max_window ? want : (size_t)max_window;
+      size_t carve = want < (size_t)max_persist ? want : (size_t)max_persist;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+        env->l2_window_bytes = window;
+        env->l2_hit_ratio = carve >= window ? 1.0f : (float)((double)carve / (double)window);
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
   uint32_t geom[96];
   make_geom(cfg->width, cfg->height, geom);
   if (cudaMemsetAsync(env->d_state, 0, sbytes, env->stream) != cudaSuccess ||
@@ -511,9 +544,7 @@ int grl_destroy(grl_env *env) {
   if (env->stream) cudaStreamSynchronize(env->stream);
   for (auto &s : env->scratch)
     if (s.ptr) cudaFree(s.ptr);
-  if (env->d_state) cudaFree(env->d_state);
-  if (env->d_static) cudaFree(env->d_static);
-  if (env->d_geom) cudaFree(env->d_geom);
+  if (env->d_state) cudaFree(env->d_state);  // d_static and d_geom live in the same allocation
   if (env->own_stream) cudaStreamDestroy(env->own_stream);
   delete env;
   return GRL_OK;

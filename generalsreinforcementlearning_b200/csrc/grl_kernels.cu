@@ -21,13 +21,30 @@
 //   reward              internal/experience/rewards.go:45-175
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/grlcuda.h"
 #include "grl_launch.h"
 #include "grl_layout.h"
 
 #define FULL 0xffffffffu
+#ifndef GRL_WARPS_PER_CTA
 #define GRL_WARPS_PER_CTA 8
+#endif
+
+// Scheduling variants (profiles/ records the comparison):
+//   GRL_PERSISTENT  resident CTAs loop over games and prefetch the next slab (TMA double buffer)
+//   GRL_CTA_SYNC    with GRL_PERSISTENT: keep a CTA's warps in the same phase (instruction-cache locality)
+#ifndef GRL_PERSISTENT
+#define GRL_PERSISTENT 0
+#endif
+#ifndef GRL_CTA_SYNC
+#define GRL_CTA_SYNC 0
+#endif
+#ifndef GRL_OBS_UNROLL
+#define GRL_OBS_UNROLL 1
+#endif
+constexpr int kObsUnroll = GRL_OBS_UNROLL;
 
 // ---------------------------------------------------------------------------------------
 // small helpers
@@ -125,6 +142,7 @@ __device__ __forceinline__ SlabView make_view(uint32_t *s, const uint32_t *st, c
 // sum of army over the tiles of a linear bitmask (word `lane` in x); slow path helper
 __device__ __forceinline__ int sum_army_over(uint32_t x, const uint16_t *army, int NW, int N, int lane) {
   int acc = 0;
+#pragma unroll 1
   for (int i = 0; i < NW; i++) {
     uint32_t xw = __shfl_sync(FULL, x, i);
     int t = 32 * i + lane;
@@ -167,10 +185,11 @@ __device__ __forceinline__ void tma_store(void *dst_gmem, const void *src_smem, 
                "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void tma_store_commit_wait() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+__device__ __forceinline__ void tma_prefetch_l2(const void *src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -311,6 +330,21 @@ __device__ __forceinline__ PackedAction sample_policy_action(const GrlKParams &p
 // and x/y arithmetic become immediates.  TW == 0 reads the geometry from the parameter block.
 // ---------------------------------------------------------------------------------------
 
+// ---- rare / optional phases, deliberately NOT inlined: they talk to the kernel through the
+// shared-memory slab, so the common path of the turn kernel stays small in the instruction cache.
+
+// Synthetic policy for all players from the pre-turn state; writes decoded moves into s_act.
+template <int PT>
+__device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t *s_act,
+                                          uint32_t alive, uint32_t turn_before, int game, int lane, int W, int H, int N,
+                                          int NW);
+
+// Elimination orders: tile turnover over the eliminated player's cached list, then the stats
+// rebuild of engine.go:101-109.  Reads and writes own/list/changed/vchg words in the slab.
+template <int PT>
+__device__ __noinline__ uint32_t elimination_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t alive,
+                                                   int n_orders, uint32_t ord_lo, uint32_t ord_hi, int lane, int N, int NW);
+
 // One decoded move, staged in shared memory as two words.  The checks that depend only on the
 // action itself (core/action.go:58-79) run on one lane per slot, in parallel; the checks that
 // depend on the board (ownership, army, mountain) run in the serial phase.
@@ -343,14 +377,18 @@ __device__ __forceinline__ uint2 decode_action(uint2 raw, int W, int H, int P) {
 
 template <int PT>
 struct TurnOccupancy {  // CTAs of 256 threads per SM the register budget is tuned for
-  static constexpr int kMinBlocks = PT <= 2 ? 4 : (PT <= 4 ? 3 : 2);
+#ifdef GRL_MIN_BLOCKS
+  static constexpr int kMinBlocks = GRL_MIN_BLOCKS;
+#else
+  static constexpr int kMinBlocks = (PT <= 2 ? 4 : (PT <= 4 ? 3 : 2)) * 8 / GRL_WARPS_PER_CTA;
+#endif
 };
 
 template <int PT, int TW, int TH, bool DO_STEP, bool DO_OUT>
 __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMinBlocks)
     grl_turn_kernel(const __grid_constant__ GrlKParams prm) {
   extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ __align__(8) uint64_t s_bar[GRL_WARPS_PER_CTA];
+  __shared__ __align__(8) uint64_t s_bar[2 * GRL_WARPS_PER_CTA];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GrlLayout &L = prm.L;
   const int P = prm.P;
@@ -359,13 +397,10 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
   const int N = TW ? TW * TH : prm.N;
   const int NW = TW ? (TW * TH + 31) / 32 : prm.NW;
   const int act_words = 2 * GRL_MAX_ACTIONS;
-  const int per_warp = L.slab_words + L.static_words + act_words;
-  uint32_t *s = smem + warp * per_warp;
-  uint32_t *st = s + L.slab_words;
-  uint32_t *s_act = st + L.static_words;
-  SlabView S = make_view(s, st, L);
-  S.C = st + NW;
-  S.G = st + 2 * NW;
+  const int buf_words = L.slab_words + L.static_words;
+  const int per_warp = 2 * buf_words + act_words;  // two slab buffers: the next game's slab is prefetched
+  uint32_t *wbase = smem + warp * per_warp;
+  uint32_t *s_act = wbase + 2 * buf_words;
 
   Geo g;
   g.lane = lane;
@@ -375,42 +410,75 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
   g.ncl = prm.geom[64 + lane];
   const bool act_lane = lane < NW;
   const uint32_t pmask = (1u << P) - 1u;
+  const bool use_policy = DO_STEP && (prm.flags & GRL_STEP_FLAG_RANDOM_POLICY) != 0;
+  const bool read_actions = DO_STEP && !use_policy && prm.actions != nullptr;
+  const int stride = gridDim.x * GRL_WARPS_PER_CTA;
+  int game = blockIdx.x * GRL_WARPS_PER_CTA + warp;
 
+  uint64_t *bars = &s_bar[2 * warp];
   if (prm.use_tma && lane == 0) {
-    mbar_init(&s_bar[warp], 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t tma_phase = 0;
+  uint32_t phase_bits = 0;  // bit b = parity the next wait on buffer b expects
+  int cur = 0;
+  uint2 next_act = make_uint2(0u, 0u);
+  // prime the pipeline: this warp's first game
+  if (game < prm.B) {
+    if (prm.use_tma && lane == 0) {
+      mbar_expect_tx(&bars[0], (uint32_t)buf_words * 4u);
+      tma_load(wbase, prm.state + (size_t)game * L.slab_words, (uint32_t)L.slab_words * 4u, &bars[0]);
+      tma_load(wbase + L.slab_words, prm.statics + (size_t)game * L.static_words, (uint32_t)L.static_words * 4u, &bars[0]);
+    }
+    if (read_actions && lane < prm.A)
+      next_act = __ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)game * prm.A + lane);
+    // warm L2 for a CTA that will be scheduled a couple of waves from now
+    if (prm.use_tma && prm.prefetch_dist > 0 && lane == 0 && game + prm.prefetch_dist < prm.B) {
+      tma_prefetch_l2(prm.state + (size_t)(game + prm.prefetch_dist) * L.slab_words, (uint32_t)L.slab_words * 4u);
+      tma_prefetch_l2(prm.statics + (size_t)(game + prm.prefetch_dist) * L.static_words, (uint32_t)L.static_words * 4u);
+    }
+  }
 
-  for (int game = blockIdx.x * GRL_WARPS_PER_CTA + warp; game < prm.B; game += gridDim.x * GRL_WARPS_PER_CTA) {
+  for (; game < prm.B; game += stride) {
+#if GRL_PERSISTENT && GRL_CTA_SYNC
+    __syncthreads();  // warps that ran out of games have exited and no longer count
+#endif
+    uint32_t *s = wbase + cur * buf_words;
+    uint32_t *st = s + L.slab_words;
+    SlabView S = make_view(s, st, L);
     uint32_t *gslab = prm.state + (size_t)game * L.slab_words;
     const uint32_t *gstat = prm.statics + (size_t)game * L.static_words;
 
     // ---- stage the slab in shared memory ---------------------------------------------
-    if (prm.use_tma) {
-      fence_proxy_async_smem();  // generic-proxy accesses of the previous game precede the bulk write
-      __syncwarp();
-      if (lane == 0) {
-        mbar_expect_tx(&s_bar[warp], (uint32_t)(L.slab_words + L.static_words) * 4u);
-        tma_load(s, gslab, (uint32_t)L.slab_words * 4u, &s_bar[warp]);
-        tma_load(st, gstat, (uint32_t)L.static_words * 4u, &s_bar[warp]);
-      }
-    }
-    // the action slots do not depend on the slab: decode them while the bulk copy is in flight
-    const bool use_policy = DO_STEP && (prm.flags & GRL_STEP_FLAG_RANDOM_POLICY) != 0;
+    // decode this game's action slots (loaded one game ahead) while its slab lands
     if (DO_STEP) {
       if (lane < GRL_MAX_ACTIONS) {
         uint2 d = make_uint2(0u, 0xffffffffu);
-        if (!use_policy && prm.actions != nullptr && lane < prm.A)
-          d = decode_action(__ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)game * prm.A + lane), W, H, P);
+        if (read_actions && lane < prm.A) d = decode_action(next_act, W, H, P);
         s_act[2 * lane] = d.x;
         s_act[2 * lane + 1] = d.y;
       }
     }
     if (prm.use_tma) {
-      mbar_wait(&s_bar[warp], tma_phase);
-      tma_phase ^= 1u;
+      mbar_wait(&bars[cur], (phase_bits >> cur) & 1u);
+      phase_bits ^= 1u << cur;
+      // prefetch the next game's slab into the other buffer; its previous contents were handed
+      // to a bulk store at the end of the last iteration, which must have finished reading them
+      const int nxt = game + stride;
+      if (nxt < prm.B) {
+        if (lane == 0) {
+          if (DO_STEP) tma_store_wait_read();
+          uint32_t *ns = wbase + (cur ^ 1) * buf_words;
+          mbar_expect_tx(&bars[cur ^ 1], (uint32_t)buf_words * 4u);
+          tma_load(ns, prm.state + (size_t)nxt * L.slab_words, (uint32_t)L.slab_words * 4u, &bars[cur ^ 1]);
+          tma_load(ns + L.slab_words, prm.statics + (size_t)nxt * L.static_words, (uint32_t)L.static_words * 4u,
+                   &bars[cur ^ 1]);
+        }
+        if (read_actions && lane < prm.A)
+          next_act = __ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)nxt * prm.A + lane);
+      }
     } else {
       const uint4 *src = reinterpret_cast<const uint4 *>(gslab);
       uint4 *dst = reinterpret_cast<uint4 *>(s);
@@ -418,6 +486,9 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
       const uint4 *src2 = reinterpret_cast<const uint4 *>(gstat);
       uint4 *dst2 = reinterpret_cast<uint4 *>(st);
       for (int k = lane; k < L.static_words / 4; k += 32) dst2[k] = __ldg(src2 + k);
+      const int nxt = game + stride;
+      if (nxt < prm.B && read_actions && lane < prm.A)
+        next_act = __ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)nxt * prm.A + lane);
     }
     __syncwarp();
 
@@ -465,22 +536,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
         turn += 1;  // turn_processor.go:125
 
         // ---- the synthetic policy reads the PRE-turn state (all players at once) ----------
-        if (use_policy) {
-          uint32_t gt1 = army_gt1_mask(S.army, NW, N, lane);
-          DirMasks dm = dir_targets(M, g);
-#pragma unroll
-          for (int p = 0; p < PT; p++) {
-            if (p < P && p < prm.A) {
-              uint32_t src = ((alive >> p) & 1u) ? (lst[p] & own[p] & gt1) : 0u;
-              PackedAction a = sample_policy_action(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn_before, g);
-              if (lane == 0 && a.present()) {
-                uint2 d = decode_action(make_uint2(a.lo, a.hi), W, H, P);
-                s_act[2 * p] = d.x;
-                s_act[2 * p + 1] = d.y;
-              }
-            }
-          }
-        }
+        if (use_policy) policy_phase<PT>(prm, s, st, s_act, alive, turn_before, game, lane, W, H, N, NW);
 
         // ---- fog of war, from LAST turn's vchg and the CURRENT lists (Q1) -----------------
         if (prm.fog) {
@@ -603,34 +659,21 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
         }
 
         // ---- eliminations + tile turnover over the CACHED list (engine.go:118-152) --------
-        if (n_orders > 0) {
+        if (n_orders > 0) {  // rare: kept out of line so the common path stays compact
           ord_lo = __shfl_sync(FULL, ord_lo, 0);
           ord_hi = __shfl_sync(FULL, ord_hi, 0);
-          for (int o = 0; o < n_orders; o++) {
-            uint32_t ob = (o < 4 ? (ord_lo >> (8 * o)) : (ord_hi >> (8 * (o - 4)))) & 0xffu;
-            int el = (int)(ob & 0xfu), nw = (int)(ob >> 4);
-            uint32_t X = 0;
+          alive = elimination_phase<PT>(prm, s, st, alive, n_orders, ord_lo, ord_hi, lane, N, NW);
 #pragma unroll
-            for (int q = 0; q < PT; q++)
-              if (q == el) X = lst[q] & own[q];
-#pragma unroll
-            for (int q = 0; q < PT; q++) {
-              if (q == el) own[q] &= ~X;
-              if (q == nw) own[q] |= X;
+          for (int p = 0; p < PT; p++) {
+            if (p < P && act_lane) {
+              own[p] = S.own[p * NW + lane];
+              lst[p] = S.list[p * NW + lane];
             }
-            chg |= X;
-            vch |= X;
-            int moved_army = 0;
-            if (__any_sync(FULL, X != 0u)) moved_army = sum_army_over(X, S.army, NW, N, lane);
-            if (lane == 0) {
-              S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * el + GRL_PL_TRUE_ARMY] -= (uint32_t)moved_army;
-              S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * nw + GRL_PL_TRUE_ARMY] += (uint32_t)moved_army;
-              S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * el + GRL_PL_GENERAL_IDX] = 0xffffffffu;
-            }
-            alive &= ~(1u << el);
           }
-          __syncwarp();
-          stats_update<PT>(prm, S, own, lst, chg, G, alive, lane, N, NW);  // engine.go:107
+          if (act_lane) {
+            chg = S.chg[lane];
+            vch = S.vch[lane];
+          }
         }
 
         if (err == 0) {
@@ -647,7 +690,8 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
           chg |= produced;
           if (__any_sync(FULL, produced != 0u)) {
             uint32_t overflow = 0;
-            if (grow) {  // dense: most owned tiles grow
+            if (grow) {  // dense: most owned tiles grow (1 turn in 25)
+#pragma unroll 1
               for (int i = 0; i < NW; i++) {
                 uint32_t wg = __shfl_sync(FULL, PG, i), wc = __shfl_sync(FULL, PC, i), wn = __shfl_sync(FULL, PN, i);
                 int t = 32 * i + lane;
@@ -776,7 +820,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
         S.hdr[GRL_HDR_FLAGS] = (alive & 0xffu) | (over ? GRL_FLAG_OVER : 0u) | (err << GRL_FLAG_ERR_SHIFT);
       __syncwarp();
       if (prm.use_tma) {
-        fence_proxy_async_smem();
+        fence_proxy_async_smem();  // make the generic-proxy writes visible to the bulk store
         __syncwarp();
         if (lane == 0) tma_store(gslab, s, (uint32_t)L.slab_words * 4u);
       } else {
@@ -841,6 +885,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
           // 128-bit path: a lane writes 4 consecutive tiles of each channel plane; the army
           // conversion and the terrain nibbles are shared by all players' views
           const int cs = N / 4;  // channel stride in float4
+#pragma unroll kObsUnroll
           for (int q0 = 0; q0 * 4 < N; q0 += 32) {
             const int q = q0 + lane;
             const int t0 = 4 * q;
@@ -849,40 +894,55 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
             const uint32_t mCG = (__shfl_sync(FULL, CG, srcl) >> sh) & 0xfu;
             const uint32_t mAny = (__shfl_sync(FULL, any_own, srcl) >> sh) & 0xfu;
             const bool live = t0 < N;
+            // armies are only read for visible owned tiles: skip the conversion when nobody owns
+            // a tile in this 128-tile chunk (most of the board, most of the game)
             float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-            if (live) {
-              const uint2 aw = *reinterpret_cast<const uint2 *>(S.army + t0);
-              f0 = army_frac(aw.x & 0xffffu);
-              f1 = army_frac(aw.x >> 16);
-              f2 = army_frac(aw.y & 0xffffu);
-              f3 = army_frac(aw.y >> 16);
+            if (__any_sync(FULL, live && (mAny & ~mM) != 0u)) {
+              if (live) {
+                const uint2 aw = *reinterpret_cast<const uint2 *>(S.army + t0);
+                f0 = army_frac(aw.x & 0xffffu);
+                f1 = army_frac(aw.x >> 16);
+                f2 = army_frac(aw.y & 0xffffu);
+                f3 = army_frac(aw.y >> 16);
+              }
             }
+#define NIBF(n) make_float4(((n)&1u) ? 1.f : 0.f, ((n)&2u) ? 1.f : 0.f, ((n)&4u) ? 1.f : 0.f, ((n)&8u) ? 1.f : 0.f)
+#define NIBA(n) make_float4(((n)&1u) ? f0 : 0.f, ((n)&2u) ? f1 : 0.f, ((n)&4u) ? f2 : 0.f, ((n)&8u) ? f3 : 0.f)
 #pragma unroll
             for (int p = 0; p < PT; p++) {
               if (p < P) {
                 const uint32_t nV = prm.fog ? ((__shfl_sync(FULL, vis[p], srcl) >> sh) & 0xfu) : 0xfu;
-                const uint32_t nO = (__shfl_sync(FULL, own[p], srcl) >> sh) & 0xfu;
-                if (live) {
-                  const uint32_t nm = nV & ~mM;
-                  const uint32_t n2 = nm & nO, n3 = nm & mAny & ~nO, n4 = nm & ~mAny, n5 = nm & mCG, n6 = nV & mM;
-                  const uint32_t n7 = nV, n8 = nV ^ 0xfu;
-                  float4 *o = reinterpret_cast<float4 *>(gbase + (size_t)p * GRL_OBS_CHANNELS * N + t0);
-#define NIBF(n) make_float4(((n)&1u) ? 1.f : 0.f, ((n)&2u) ? 1.f : 0.f, ((n)&4u) ? 1.f : 0.f, ((n)&8u) ? 1.f : 0.f)
-#define NIBA(n) make_float4(((n)&1u) ? f0 : 0.f, ((n)&2u) ? f1 : 0.f, ((n)&4u) ? f2 : 0.f, ((n)&8u) ? f3 : 0.f)
-                  __stcs(o + 0 * cs, NIBA(n2));
-                  __stcs(o + 1 * cs, NIBA(n3));
-                  __stcs(o + 2 * cs, NIBF(n2));
-                  __stcs(o + 3 * cs, NIBF(n3));
-                  __stcs(o + 4 * cs, NIBF(n4));
-                  __stcs(o + 5 * cs, NIBF(n5));
-                  __stcs(o + 6 * cs, NIBF(n6));
-                  __stcs(o + 7 * cs, NIBF(n7));
-                  __stcs(o + 8 * cs, NIBF(n8));
-#undef NIBF
-#undef NIBA
+                float4 *o = reinterpret_cast<float4 *>(gbase + (size_t)p * GRL_OBS_CHANNELS * N + t0);
+                if (!__any_sync(FULL, live && nV != 0u)) {
+                  // the whole chunk is fogged for this player: only the fog plane is non-zero
+                  // (serializer.go:50-60 skips every other channel of an invisible tile)
+                  if (live) {
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int c = 0; c < 8; c++) __stcs(o + c * cs, z);
+                    __stcs(o + 8 * cs, make_float4(1.f, 1.f, 1.f, 1.f));
+                  }
+                } else {
+                  const uint32_t nO = (__shfl_sync(FULL, own[p], srcl) >> sh) & 0xfu;
+                  if (live) {
+                    const uint32_t nm = nV & ~mM;
+                    const uint32_t n2 = nm & nO, n3 = nm & mAny & ~nO, n4 = nm & ~mAny, n5 = nm & mCG, n6 = nV & mM;
+                    const uint32_t n7 = nV, n8 = nV ^ 0xfu;
+                    __stcs(o + 0 * cs, NIBA(n2));
+                    __stcs(o + 1 * cs, NIBA(n3));
+                    __stcs(o + 2 * cs, NIBF(n2));
+                    __stcs(o + 3 * cs, NIBF(n3));
+                    __stcs(o + 4 * cs, NIBF(n4));
+                    __stcs(o + 5 * cs, NIBF(n5));
+                    __stcs(o + 6 * cs, NIBF(n6));
+                    __stcs(o + 7 * cs, NIBF(n7));
+                    __stcs(o + 8 * cs, NIBF(n8));
+                  }
                 }
               }
             }
+#undef NIBF
+#undef NIBA
           }
         } else {
           // generic path (N % 4 != 0, e.g. 15x15): one tile per lane, coalesced 32-bit stores
@@ -918,11 +978,104 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
       }
     }
 
-    if (DO_STEP && prm.use_tma) {
-      if (lane == 0) tma_store_commit_wait();  // the slab buffer is reused by the next game
+    if (prm.use_tma) {
+      if (DO_STEP && lane == 0) tma_store_commit();
+      fence_proxy_async_smem();  // this buffer's generic-proxy accesses precede its next bulk refill
+      cur ^= 1;
     }
     __syncwarp();
   }
+  if (DO_STEP && prm.use_tma && lane == 0) tma_store_wait_read();  // shared memory outlives the bulk stores
+}
+
+template <int PT>
+__device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t *s_act,
+                                          uint32_t alive, uint32_t turn_before, int game, int lane, int W, int H, int N,
+                                          int NW) {
+  const GrlLayout &L = prm.L;
+  const int P = prm.P;
+  SlabView S = make_view(s, st, L);
+  Geo g;
+  g.lane = lane;
+  g.W = W;
+  g.valid = prm.geom[lane];
+  g.nc0 = prm.geom[32 + lane];
+  g.ncl = prm.geom[64 + lane];
+  const bool act_lane = lane < NW;
+  const uint32_t M = act_lane ? S.M[lane] : 0u;
+  uint32_t gt1 = army_gt1_mask(S.army, NW, N, lane);
+  DirMasks dm = dir_targets(M, g);
+#pragma unroll 1
+  for (int p = 0; p < P && p < prm.A; p++) {
+    const uint32_t own = act_lane ? S.own[p * NW + lane] : 0u;
+    const uint32_t lst = act_lane ? S.list[p * NW + lane] : 0u;
+    uint32_t src = ((alive >> p) & 1u) ? (lst & own & gt1) : 0u;
+    PackedAction a = sample_policy_action(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn_before, g);
+    if (lane == 0 && a.present()) {
+      uint2 d = decode_action(make_uint2(a.lo, a.hi), W, H, P);
+      s_act[2 * p] = d.x;
+      s_act[2 * p + 1] = d.y;
+    }
+  }
+  __syncwarp();
+}
+
+template <int PT>
+__device__ __noinline__ uint32_t elimination_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t alive,
+                                                   int n_orders, uint32_t ord_lo, uint32_t ord_hi, int lane, int N, int NW) {
+  const GrlLayout &L = prm.L;
+  const int P = prm.P;
+  SlabView S = make_view(s, st, L);
+  const bool act_lane = lane < NW;
+  uint32_t own[PT], lst[PT];
+#pragma unroll
+  for (int p = 0; p < PT; p++) {
+    bool on = act_lane && p < P;
+    own[p] = on ? S.own[p * NW + lane] : 0u;
+    lst[p] = on ? S.list[p * NW + lane] : 0u;
+  }
+  uint32_t chg = act_lane ? S.chg[lane] : 0u;
+  uint32_t vch = act_lane ? S.vch[lane] : 0u;
+  const uint32_t G = act_lane ? S.G[lane] : 0u;
+#pragma unroll 1
+  for (int o = 0; o < n_orders; o++) {
+    uint32_t ob = (o < 4 ? (ord_lo >> (8 * o)) : (ord_hi >> (8 * (o - 4)))) & 0xffu;
+    int el = (int)(ob & 0xfu), nw = (int)(ob >> 4);
+    uint32_t X = 0;
+#pragma unroll
+    for (int q = 0; q < PT; q++)
+      if (q == el) X = lst[q] & own[q];  // still owned AND in the cached list (engine.go:130-137)
+#pragma unroll
+    for (int q = 0; q < PT; q++) {
+      if (q == el) own[q] &= ~X;
+      if (q == nw) own[q] |= X;
+    }
+    chg |= X;
+    vch |= X;
+    int moved_army = 0;
+    if (__any_sync(FULL, X != 0u)) moved_army = sum_army_over(X, S.army, NW, N, lane);
+    if (lane == 0) {
+      S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * el + GRL_PL_TRUE_ARMY] -= (uint32_t)moved_army;
+      S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * nw + GRL_PL_TRUE_ARMY] += (uint32_t)moved_army;
+      S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * el + GRL_PL_GENERAL_IDX] = 0xffffffffu;
+    }
+    alive &= ~(1u << el);
+  }
+  __syncwarp();
+  stats_update<PT>(prm, S, own, lst, chg, G, alive, lane, N, NW);  // engine.go:107
+  if (act_lane) {
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      if (p < P) {
+        S.own[p * NW + lane] = own[p];
+        S.list[p * NW + lane] = lst[p];
+      }
+    }
+    S.chg[lane] = chg;
+    S.vch[lane] = vch;
+  }
+  __syncwarp();
+  return alive;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1165,19 +1318,65 @@ static inline int grid_for(int items_per_cta_warps, int n) {
 }
 
 size_t grl_turn_smem_bytes(const GrlLayout &L) {
-  return (size_t)GRL_WARPS_PER_CTA * (size_t)(L.slab_words + L.static_words + 2 * GRL_MAX_ACTIONS) * 4u;
+  return (size_t)GRL_WARPS_PER_CTA * (size_t)(2 * (L.slab_words + L.static_words) + 2 * GRL_MAX_ACTIONS) * 4u;
+}
+
+// persistent launch: as many CTAs as stay resident (occupancy x SM count), each warp loops over games
+template <typename K>
+static int persistent_grid(K kern, size_t smem, int B) {
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GRL_WARPS_PER_CTA * 32, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  int need = (B + GRL_WARPS_PER_CTA - 1) / GRL_WARPS_PER_CTA;
+  int grid = sm_count * per_sm;
+  return need < grid ? (need < 1 ? 1 : need) : grid;
 }
 
 template <int PT, int TW, int TH, bool S, bool O>
 static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream) {
   size_t smem = grl_turn_smem_bytes(prm.L);
   auto kern = grl_turn_kernel<PT, TW, TH, S, O>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+  static size_t tuned_smem = ~(size_t)0;  // per instantiation: attribute + resident-CTA count
+  static int resident = 0;
+  if (tuned_smem != smem) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    resident = persistent_grid(kern, smem, 1 << 30);
+    tuned_smem = smem;
   }
-  kern<<<grid_for(GRL_WARPS_PER_CTA, prm.B), GRL_WARPS_PER_CTA * 32, smem, stream>>>(prm);
-  return cudaGetLastError();
+  int need = (prm.B + GRL_WARPS_PER_CTA - 1) / GRL_WARPS_PER_CTA;
+#if GRL_PERSISTENT
+  int grid = need < resident ? need : resident;
+#else
+  int grid = need;  // one game per warp: CTAs of a wave move through the phases together
+#endif
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(grid < 1 ? 1 : grid);
+  cfg.blockDim = dim3(GRL_WARPS_PER_CTA * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (prm.l2_window_bytes) {  // game state persists in L2; everything else streams through it
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = prm.state;
+    attr[0].val.accessPolicyWindow.num_bytes = prm.l2_window_bytes;
+    attr[0].val.accessPolicyWindow.hitRatio = prm.l2_hit_ratio;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, prm);
 }
 
 template <int PT, int TW, int TH>

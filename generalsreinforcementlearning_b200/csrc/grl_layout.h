@@ -86,5 +86,9 @@ struct GrlKParams {
   int fog, pg, pc, pn, grow_interval;
   int env_id_base;
   int use_tma;
+  int prefetch_dist;
   float rw[11];
+  // host-side launch hints (not read by device code)
+  unsigned long long l2_window_bytes;
+  float l2_hit_ratio;
 };
