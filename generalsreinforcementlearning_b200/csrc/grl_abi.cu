@@ -486,7 +486,7 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   const char *no_tma = getenv("GRL_NO_TMA");
   env->use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
   const char *pf = getenv("GRL_PREFETCH_DIST");
-  env->prefetch_dist = pf ? atoi(pf) : 0;
+  env->prefetch_dist = pf ? atoi(pf) : 8192;  // ~1.7 waves of resident warps ahead (profiles/r1_variants.md)
   auto bail = [&](int code) {
     grl_destroy(env);
     return code;

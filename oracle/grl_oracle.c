@@ -1299,13 +1299,73 @@ int grlo_visibility(grlo_env *e, uint8_t *visible, uint8_t *fog) {
   return GRL_OK;
 }
 
-int grlo_sample_actions(grlo_env *e, uint64_t policy_seed, grl_action *actions) {
-  if (!e || !actions) return GRL_ERR_INVALID_ARG;
+/* generic parallel range over [0,n): used by the batch read-outs below (test-speed only) */
+typedef struct {
+  void (*fn)(void *ctx, int i0, int i1);
+  void *ctx;
+  int i0, i1;
+} range_job_t;
+
+static void *range_run(void *arg) {
+  range_job_t *j = (range_job_t *)arg;
+  j->fn(j->ctx, j->i0, j->i1);
+  return NULL;
+}
+
+static void par_range(int nthreads, int n, void (*fn)(void *, int, int), void *ctx) {
+  int nt = nthreads;
+  if (nt > 256) nt = 256;
+  if (nt > n / 64) nt = n / 64; /* not worth a thread below ~64 items each */
+  if (nt <= 1) {
+    fn(ctx, 0, n);
+    return;
+  }
+  range_job_t jobs[256];
+  pthread_t th[256];
+  int per = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; t++) {
+    jobs[t].fn = fn;
+    jobs[t].ctx = ctx;
+    jobs[t].i0 = t * per > n ? n : t * per;
+    jobs[t].i1 = (t + 1) * per > n ? n : (t + 1) * per;
+    pthread_create(&th[t], NULL, range_run, &jobs[t]);
+  }
+  for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
+}
+
+typedef struct {
+  grlo_env *e;
+  uint64_t seed;
+  grl_action *actions;
+  uint64_t *out;
+  const uint32_t *buf;
+  size_t row_words;
+} batch_ctx_t;
+
+static void sample_range(void *c, int i0, int i1) {
+  batch_ctx_t *x = (batch_ctx_t *)c;
+  grlo_env *e = x->e;
   uint8_t *scratch = (uint8_t *)malloc((size_t)e->N * 4);
   int A = e->cfg.max_actions;
-  for (int b = 0; b < e->cfg.num_envs; b++)
-    sample_actions(&e->g[b], policy_seed, (uint64_t)(e->cfg.env_id_base + b), actions + (size_t)b * A, A, scratch);
+  for (int b = i0; b < i1; b++)
+    sample_actions(&e->g[b], x->seed, (uint64_t)(e->cfg.env_id_base + b), x->actions + (size_t)b * A, A, scratch);
   free(scratch);
+}
+
+static void hash_range(void *c, int i0, int i1) {
+  batch_ctx_t *x = (batch_ctx_t *)c;
+  for (int b = i0; b < i1; b++) x->out[b] = state_hash(&x->e->g[b]);
+}
+
+static void row_hash_range(void *c, int i0, int i1) {
+  batch_ctx_t *x = (batch_ctx_t *)c;
+  for (int r = i0; r < i1; r++) x->out[r] = row_hash(x->buf + (size_t)r * x->row_words, x->row_words);
+}
+
+int grlo_sample_actions(grlo_env *e, uint64_t policy_seed, grl_action *actions) {
+  if (!e || !actions) return GRL_ERR_INVALID_ARG;
+  batch_ctx_t x = {e, policy_seed, actions, NULL, NULL, 0};
+  par_range(e->nthreads, e->cfg.num_envs, sample_range, &x);
   return GRL_OK;
 }
 
@@ -1389,14 +1449,15 @@ int grlo_set_state(grlo_env *e, int32_t first, int32_t count, const grl_state_pl
 
 int grlo_state_hash(grlo_env *e, uint64_t *out) {
   if (!e || !out) return GRL_ERR_INVALID_ARG;
-  for (int b = 0; b < e->cfg.num_envs; b++) out[b] = state_hash(&e->g[b]);
+  batch_ctx_t x = {e, 0, NULL, out, NULL, 0};
+  par_range(e->nthreads, e->cfg.num_envs, hash_range, &x);
   return GRL_OK;
 }
 
 int grlo_buffer_hash(grlo_env *e, const void *buf, size_t row_words, int32_t rows, uint64_t *out) {
-  (void)e;
   if (!buf || !out || rows < 0) return GRL_ERR_INVALID_ARG;
-  for (int r = 0; r < rows; r++) out[r] = row_hash((const uint32_t *)buf + (size_t)r * row_words, row_words);
+  batch_ctx_t x = {e, 0, NULL, out, (const uint32_t *)buf, row_words};
+  par_range(e ? e->nthreads : 1, rows, row_hash_range, &x);
   return GRL_OK;
 }
 

@@ -83,3 +83,52 @@ def test_properties_at_headline_size(cuda_lib):
     before = e.state_hash()[:256].copy()
     e.step(None)
     assert np.array_equal(e.state_hash()[:256], before)
+
+
+@pytest.mark.parametrize("W,H,P,T", [(10, 10, 2, 500), (20, 20, 2, 500)])
+def test_10k_games_full_episode_replay(cuda_lib, oracle_lib, W, H, P, T):
+    """The north star's parity run: 10,000 seeded games played to the 500-turn episode cap
+    (generals_env.py:58) with the random-legal-move policy, then re-seeded with the next
+    block of seeds and played on.  Every turn: every game's full-state digest,
+    reward bits, done, winner, step_error and packed mask equal the oracle's; observation
+    digests every 25th turn.  The recorded actions are REPLAYED into the CUDA engine from the
+    oracle's draw, so the two engines see identical action sequences by construction."""
+    import torch
+
+    B = 10000
+    gc = new_engine(cuda_lib, W, H, P, B, host_threads=0)
+    oc = new_engine(oracle_lib, W, H, P, B, host_threads=0)
+    dev = torch.device("cuda:0")
+    obs = torch.empty((B, P, 9, H, W), dtype=torch.float32, device=dev)
+    go = gc.alloc_outputs_host()
+    del go["obs"]
+    oo = oc.alloc_outputs_host()
+    oo_small = {k: v for k, v in oo.items() if k != "obs"}
+    finished = errors = 0
+    for episode, turns in ((0, T), (1, 40)):
+        seeds = np.arange(B, dtype=np.int64) + 12345 + episode * B
+        gc.reset_seeded(seeds)
+        oc.reset_seeded(seeds)
+        assert np.array_equal(gc.state_hash(), oc.state_hash())
+        for t in range(turns):
+            acts = oc.sample_actions(2024 + episode)
+            with_obs = t % 25 == 24
+            gc.step_fused(acts, gc.outputs(obs=obs, **go))
+            oc.step_fused(acts, oc.outputs(**(oo if with_obs else oo_small)))
+            ctx = f"episode {episode} turn {t}"
+            assert np.array_equal(gc.state_hash(), oc.state_hash()), ctx
+            for k in go:
+                a, b = go[k], oo[k]
+                if a.dtype == np.float32:
+                    a, b = a.view(np.uint32), b.view(np.uint32)
+                assert np.array_equal(a, b), f"{ctx}: {k}"
+            if with_obs:
+                rows, words = B * P, 9 * W * H
+                assert np.array_equal(gc.buffer_hash(obs, words, rows), oc.buffer_hash(oo["obs"], words, rows)), ctx
+            errors += int((oo["step_error"] != 0).sum())
+        finished += int(oo["done"].sum())
+    assert np.array_equal(gc.stats(), oc.stats())
+    # the run must have exercised the abort path (Q5) — and, on the small board, game endings
+    assert errors > 0
+    if W == 10:
+        assert finished > 0

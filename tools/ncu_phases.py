@@ -28,7 +28,7 @@ PHASES = [
     ("scalar read-outs", "---- read-outs ---"),
     ("legal mask", "// engine legal-action mask, packed"),
     ("observation planes", "// observation planes: Serializer.StateToTensor"),
-    ("tail", "the slab buffer is reused by the next game"),
+    ("tail", "if (DO_STEP && lane == 0) tma_store_commit();"),
 ]
 
 
