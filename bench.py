@@ -360,10 +360,10 @@ def run_cuda(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        games = 4096
-        rate, dt, cores, n = time_oracle(games, 12, 2)
-        # scale the sample to ~10-20 s of CPU work
-        steps_c = int(max(12, min(480, 12 * 12.0 / max(dt, 1e-3))))
+        rate, dt, cores, n = time_oracle(4096, 12, 2)          # probe
+        # bounded sample: ~15 s of CPU work on this box, the same 400-turn rollouts
+        steps_c = 400
+        games = int(min(32768, max(2048, (rate * 15.0 / steps_c) // 1024 * 1024)))
         rate, dt, cores, n = time_oracle(games, steps_c, 2)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{games} games x {steps_c} turns ({n} env-steps, {dt:.1f} s) incl. observation/mask/reward; "

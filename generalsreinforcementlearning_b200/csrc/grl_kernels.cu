@@ -41,6 +41,9 @@
 #ifndef GRL_CTA_SYNC
 #define GRL_CTA_SYNC 0
 #endif
+#ifndef GRL_OBS_CHUNK_MAJOR
+#define GRL_OBS_CHUNK_MAJOR 0  // 1: the round-1a tile-chunk-major observation loop (comparison builds)
+#endif
 #ifndef GRL_OBS_UNROLL
 #define GRL_OBS_UNROLL 1
 #endif
@@ -384,11 +387,109 @@ struct TurnOccupancy {  // CTAs of 256 threads per SM the register budget is tun
 #endif
 };
 
+// Observation planes, PLANE-MAJOR store order, for baked geometries with N % 4 == 0
+// (Serializer.StateToTensor, serializer.go:37-109).  A warp writes its game's whole
+// [P][9][N] fp32 block as ONE linear sweep of 128-bit stores: measured 7.1 TB/s for this
+// order against 6.4 TB/s for tile-chunk-major (profiles/r1_variants.md).  Lane l owns the
+// tile quads q = l + 32c (c < NCH); every mask's nibbles for those quads are read once from
+// the shared-memory slab and packed 4 bits per chunk, so each channel's nibbles for ALL
+// chunks come from one LOP3 on the packed fields.  A nibble becomes a float4 of 0/1 through
+// a 16-entry shared-memory table (one LDS.128 per store instead of eight ALU selects).
+template <int PT, int N>
+__device__ __forceinline__ void obs_plane_major(const GrlKParams &prm, const SlabView &S, const float4 *lut, int P, int NW,
+                                                int game, int lane) {
+  constexpr int NQ = N / 4;
+  constexpr int NCH = (NQ + 31) / 32;
+  const int bsel = lane >> 1, bsh = 4 * (lane & 1);  // quad q -> byte q>>1, nibble q&1 of a mask's byte array
+  const uint8_t *bM = reinterpret_cast<const uint8_t *>(S.M);
+  const uint8_t *bC = reinterpret_cast<const uint8_t *>(S.C);
+  const uint8_t *bG = reinterpret_cast<const uint8_t *>(S.G);
+  uint32_t mM = 0, mCG = 0, mAny = 0, livem = 0;
+  uint32_t nV[PT], nO[PT];
+#pragma unroll
+  for (int p = 0; p < PT; p++) nV[p] = nO[p] = 0;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    const bool live = 32 * c + lane < NQ;
+    if (live) {
+      const int b = 16 * c + bsel;
+      livem |= 0xfu << (4 * c);
+      mM |= ((bM[b] >> bsh) & 0xfu) << (4 * c);
+      mCG |= (((bC[b] | bG[b]) >> bsh) & 0xfu) << (4 * c);
+#pragma unroll
+      for (int p = 0; p < PT; p++) {
+        if (p < P) {
+          const uint8_t *bo = reinterpret_cast<const uint8_t *>(S.own + p * NW);
+          const uint8_t *bv = reinterpret_cast<const uint8_t *>(S.vis + p * NW);
+          nO[p] |= ((bo[b] >> bsh) & 0xfu) << (4 * c);
+          nV[p] |= ((bv[b] >> bsh) & 0xfu) << (4 * c);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PT; p++) mAny |= nO[p];
+  // armies are read only where somebody owns a non-mountain tile of the quad
+  float f[NCH][4];
+  const uint32_t need = mAny & ~mM;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    f[c][0] = f[c][1] = f[c][2] = f[c][3] = 0.f;
+    if ((need >> (4 * c)) & 0xfu) {
+      const uint2 aw = *reinterpret_cast<const uint2 *>(S.army + 4 * (32 * c + lane));
+      f[c][0] = army_frac(aw.x & 0xffffu);
+      f[c][1] = army_frac(aw.x >> 16);
+      f[c][2] = army_frac(aw.y & 0xffffu);
+      f[c][3] = army_frac(aw.y >> 16);
+    }
+  }
+  const char *lutb = reinterpret_cast<const char *>(lut);
+  float4 *gq = reinterpret_cast<float4 *>(prm.obs + (size_t)game * P * GRL_OBS_CHANNELS * N) + lane;
+#pragma unroll
+  for (int p = 0; p < PT; p++) {
+    if (p < P) {
+      const uint32_t v = prm.fog ? nV[p] : livem;
+      const uint32_t nm = v & ~mM;
+      uint32_t ch[GRL_OBS_CHANNELS];
+      ch[0] = ch[2] = nm & nO[p];            // own (army, ownership)       serializer.go:75-90
+      ch[1] = ch[3] = nm & mAny & ~nO[p];    // enemy
+      ch[4] = nm & ~mAny;                    // neutral
+      ch[5] = nm & mCG;                      // city or general
+      ch[6] = v & mM;                        // mountain
+      ch[7] = v;                             // visible
+      ch[8] = ~v;                            // fog
+#pragma unroll
+      for (int k = 0; k < GRL_OBS_CHANNELS; k++) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+          if (32 * c + lane < NQ) {
+            const uint32_t idx16 = (c == 0 ? (ch[k] << 4) : (ch[k] >> (4 * c - 4))) & 0xf0u;
+            float4 val = *reinterpret_cast<const float4 *>(lutb + idx16);
+            if (k < 2) {
+              val.x *= f[c][0];
+              val.y *= f[c][1];
+              val.z *= f[c][2];
+              val.w *= f[c][3];
+            }
+            __stcs(gq + (p * GRL_OBS_CHANNELS + k) * NQ + 32 * c, val);
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int PT, int TW, int TH, bool DO_STEP, bool DO_OUT>
 __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMinBlocks)
     grl_turn_kernel(const __grid_constant__ GrlKParams prm) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t s_bar[2 * GRL_WARPS_PER_CTA];
+  __shared__ __align__(16) float4 s_lut[16];  // nibble -> four 0/1 floats (observation planes)
+  if (DO_OUT && threadIdx.x < 16) {
+    const uint32_t n = threadIdx.x;
+    s_lut[n] = make_float4((n & 1u) ? 1.f : 0.f, (n & 2u) ? 1.f : 0.f, (n & 4u) ? 1.f : 0.f, (n & 8u) ? 1.f : 0.f);
+  }
+  if (DO_OUT) __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GrlLayout &L = prm.L;
   const int P = prm.P;
@@ -881,7 +982,9 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
         for (int p = 0; p < PT; p++) any_own |= own[p];
         const uint32_t CG = C | G;
         float *gbase = prm.obs + (size_t)game * P * GRL_OBS_CHANNELS * N;
-        if ((N & 3) == 0) {
+        if (TW > 0 && ((TW * TH) & 3) == 0 && !GRL_OBS_CHUNK_MAJOR) {
+          obs_plane_major<PT, (TW > 0 ? TW * TH : 4)>(prm, S, s_lut, P, NW, game, lane);
+        } else if ((N & 3) == 0) {
           // 128-bit path: a lane writes 4 consecutive tiles of each channel plane; the army
           // conversion and the terrain nibbles are shared by all players' views
           const int cs = N / 4;  // channel stride in float4

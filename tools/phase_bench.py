@@ -1,0 +1,63 @@
+#!/usr/bin/env python3
+"""Time the turn kernel's instantiations separately on one GPU (CUDA events, kernel's stream):
+step only (no read-outs), read-outs only (observe), fused, fused without obs, fused obs only.
+usage: python tools/phase_bench.py [W H P B]"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+from generalsreinforcementlearning_b200 import load_library
+from generalsreinforcementlearning_b200.engine import BatchedEngine, make_config
+
+
+def main():
+    W, H, P, B = (int(v) for v in sys.argv[1:5]) if len(sys.argv) >= 5 else (20, 20, 2, 65536)
+    lib = load_library()
+    dev = torch.device("cuda:0")
+    e = BatchedEngine(lib, make_config(lib, num_envs=B, width=W, height=H, num_players=P, host_threads=0))
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    e.set_stream(stream.cuda_stream)
+    seeds = np.arange(B, dtype=np.int64) + 12345
+    T = 60
+    e.reset_seeded(seeds)
+    rec = torch.empty((T + 5, B, e.A, 8), dtype=torch.uint8, device=dev)
+    done = torch.empty(B, dtype=torch.uint8, device=dev)
+    for t in range(T + 5):
+        e.sample_actions(2024, rec[t])
+        e.step_fused(rec[t], e.outputs(done=done))
+    obs = torch.empty((B, P, 9, H, W), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, P, e.mask_words), dtype=torch.int32, device=dev)
+    reward = torch.empty((B, P), dtype=torch.float32, device=dev)
+    modes = {
+        "fused(obs+mask+reward+done)": lambda t: e.step_fused(rec[t], e.outputs(obs=obs, mask_bits=mask, reward=reward, done=done)),
+        "step only": lambda t: e.step(rec[t]),
+        "fused(mask+reward+done)": lambda t: e.step_fused(rec[t], e.outputs(mask_bits=mask, reward=reward, done=done)),
+        "fused(obs only)": lambda t: e.step_fused(rec[t], e.outputs(obs=obs)),
+        "observe(obs+mask) no step": lambda t: e.observe(e.outputs(obs=obs, mask_bits=mask, reward=reward, done=done)),
+        "observe(obs) no step": lambda t: e.observe(e.outputs(obs=obs)),
+    }
+    res = {}
+    for name, fn in modes.items():
+        e.reset_seeded(seeds)
+        for t in range(5):
+            fn(t)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for t in range(5, 5 + T):
+            fn(t)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        res[name] = round(e0.elapsed_time(e1) / T, 4)
+    print(json.dumps({"config": [W, H, P, B], "tma": os.environ.get("GRL_NO_TMA", "0") != "1",
+                      "prefetch": os.environ.get("GRL_PREFETCH_DIST", "default"), "ms_per_launch": res}))
+
+
+if __name__ == "__main__":
+    main()
