@@ -50,7 +50,7 @@ def algorithmic_bytes_per_env_step(W, H, P):
     NA = (N + 7) & ~7
     hdr = (8 + 5 * P + 3) & ~3
     off_army = (hdr + (3 * P + 2) * NW + 3) & ~3
-    slab = ((off_army + NA // 2 + 3) & ~3) * 4
+    slab = ((off_army + NA // 2 + 7) & ~7) * 4
     static = ((3 * NW + 3) & ~3) * 4
     obs = 9 * N * 4 * P
     mask = ((4 * N + 31) // 32) * 4 * P

@@ -41,6 +41,13 @@
 #ifndef GRL_CTA_SYNC
 #define GRL_CTA_SYNC 0
 #endif
+// GRL_DIRTY_WB: write back only the 32-byte sectors of the slab that the turn changed (the
+// bulk load lands the slab twice; the second copy is the comparison snapshot).  A turn dirties
+// ~40 % of a 20x20 slab's sectors; scattered state writes cost the observation store stream
+// about three times their byte share (tools/micro/store_readmix.cu, profiles/r1_variants.md).
+#ifndef GRL_DIRTY_WB
+#define GRL_DIRTY_WB (!GRL_PERSISTENT)
+#endif
 #ifndef GRL_OBS_CHUNK_MAJOR
 #define GRL_OBS_CHUNK_MAJOR 0  // 1: the round-1a tile-chunk-major observation loop (comparison builds)
 #endif
@@ -529,9 +536,12 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
   // prime the pipeline: this warp's first game
   if (game < prm.B) {
     if (prm.use_tma && lane == 0) {
-      mbar_expect_tx(&bars[0], (uint32_t)buf_words * 4u);
+      const bool snap = GRL_DIRTY_WB && DO_STEP;
+      mbar_expect_tx(&bars[0], (uint32_t)(buf_words + (snap ? L.slab_words : 0)) * 4u);
       tma_load(wbase, prm.state + (size_t)game * L.slab_words, (uint32_t)L.slab_words * 4u, &bars[0]);
       tma_load(wbase + L.slab_words, prm.statics + (size_t)game * L.static_words, (uint32_t)L.static_words * 4u, &bars[0]);
+      if (snap)  // pre-turn snapshot for the dirty-sector write-back (an L2 hit on the same lines)
+        tma_load(wbase + buf_words, prm.state + (size_t)game * L.slab_words, (uint32_t)L.slab_words * 4u, &bars[0]);
     }
     if (read_actions && lane < prm.A)
       next_act = __ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)game * prm.A + lane);
@@ -920,7 +930,21 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
       if (lane == 0)
         S.hdr[GRL_HDR_FLAGS] = (alive & 0xffu) | (over ? GRL_FLAG_OVER : 0u) | (err << GRL_FLAG_ERR_SHIFT);
       __syncwarp();
-      if (prm.use_tma) {
+      if (prm.use_tma && GRL_DIRTY_WB) {
+        // sector k = words [8k, 8k+8) of the slab (slabs are 32-byte aligned and a whole number of sectors)
+        const uint4 *now4 = reinterpret_cast<const uint4 *>(s);
+        const uint4 *old4 = reinterpret_cast<const uint4 *>(wbase + buf_words);
+        uint4 *dst4 = reinterpret_cast<uint4 *>(gslab);
+        for (int k = lane; k < L.slab_words / 8; k += 32) {
+          const uint4 a0 = now4[2 * k], a1 = now4[2 * k + 1], b0 = old4[2 * k], b1 = old4[2 * k + 1];
+          const uint32_t diff = (a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) |
+                                (a1.z ^ b1.z) | (a1.w ^ b1.w);
+          if (diff) {
+            dst4[2 * k] = a0;
+            dst4[2 * k + 1] = a1;
+          }
+        }
+      } else if (prm.use_tma) {
         fence_proxy_async_smem();  // make the generic-proxy writes visible to the bulk store
         __syncwarp();
         if (lane == 0) tma_store(gslab, s, (uint32_t)L.slab_words * 4u);
@@ -1082,13 +1106,13 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
     }
 
     if (prm.use_tma) {
-      if (DO_STEP && lane == 0) tma_store_commit();
+      if (DO_STEP && !GRL_DIRTY_WB && lane == 0) tma_store_commit();
       fence_proxy_async_smem();  // this buffer's generic-proxy accesses precede its next bulk refill
       cur ^= 1;
     }
     __syncwarp();
   }
-  if (DO_STEP && prm.use_tma && lane == 0) tma_store_wait_read();  // shared memory outlives the bulk stores
+  if (DO_STEP && !GRL_DIRTY_WB && prm.use_tma && lane == 0) tma_store_wait_read();  // shared memory outlives the bulk stores
 }
 
 template <int PT>

@@ -44,7 +44,7 @@ struct GrlLayout {
   int N, P, NW, NA;
   int hdr_words;
   int off_own, off_list, off_vis, off_changed, off_vchg, off_army;
-  int slab_words;    // multiple of 4
+  int slab_words;    // multiple of 8: a slab is a whole number of 32-byte sectors
   int static_words;  // multiple of 4: [M][C][G]
 };
 
@@ -61,7 +61,7 @@ static inline GrlLayout grl_make_layout(int W, int H, int P) {
   L.off_changed = L.off_vis + P * L.NW;
   L.off_vchg = L.off_changed + L.NW;
   L.off_army = (L.off_vchg + L.NW + 3) & ~3;
-  L.slab_words = (L.off_army + L.NA / 2 + 3) & ~3;
+  L.slab_words = (L.off_army + L.NA / 2 + 7) & ~7;
   L.static_words = (3 * L.NW + 3) & ~3;
   return L;
 }
