@@ -62,6 +62,12 @@ struct grl_env {
   float l2_hit_ratio = 1.0f;
   uint64_t launches = 0;
   int host_threads = 1;
+  // host-buffer calls split the batch into sub-ranges on these streams so that the copies of one
+  // sub-range overlap the kernel of another (created on first use)
+  static constexpr int kPipe = 4;
+  cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_start = nullptr, ev_done[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+  int pipe_chunks = 4;  // GRL_PIPE_CHUNKS=1 disables the pipelining
 };
 
 namespace {
@@ -99,6 +105,8 @@ GrlKParams base_params(const grl_env *env) {
   p.statics = env->d_static;
   p.geom = env->d_geom;
   p.B = c.num_envs;
+  p.game0 = 0;
+  p.game_end = c.num_envs;
   p.W = c.width;
   p.H = c.height;
   p.N = env->N;
@@ -359,6 +367,16 @@ int flush_out(grl_env *env, OutBuf &ob, bool &need_sync) {
   return GRL_OK;
 }
 
+int ensure_pipe(grl_env *env) {
+  if (env->ev_start) return GRL_OK;
+  CUDA_TRY(cudaEventCreateWithFlags(&env->ev_start, cudaEventDisableTiming));
+  for (int k = 0; k < grl_env::kPipe; k++) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&env->pipe[k], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&env->ev_done[k], cudaEventDisableTiming));
+  }
+  return GRL_OK;
+}
+
 int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t policy_seed, const grl_step_outputs *out,
              bool do_step) {
   const grl_config &c = env->cfg;
@@ -367,54 +385,89 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
   GrlKParams prm = base_params(env);
   prm.flags = flags;
   prm.policy_seed = policy_seed;
-  bool need_sync = false;
+  const size_t act_stride = (size_t)c.max_actions * sizeof(grl_action);
+  bool actions_staged = false;
   if (do_step && actions && !(flags & GRL_STEP_FLAG_RANDOM_POLICY)) {
     if (is_device_ptr(actions)) {
       prm.actions = actions;
     } else {
       void *d = nullptr;
-      const size_t bytes = B * (size_t)c.max_actions * sizeof(grl_action);
-      int st = ensure(env, SL_ACTIONS, bytes, &d);
+      int st = ensure(env, SL_ACTIONS, B * act_stride, &d);
       if (st) return st;
-      CUDA_TRY(cudaMemcpyAsync(d, actions, bytes, cudaMemcpyHostToDevice, env->stream));
       prm.actions = d;
-      need_sync = true;  // the caller's buffer must be consumed before we return
+      actions_staged = true;  // the caller's buffer must be consumed before we return
     }
   }
-  OutBuf obs, mask, reward, done, winner, serr, aidx;
   const bool do_out = out != nullptr;
+  struct Plane {
+    OutBuf ob;
+    size_t stride;  // bytes per env
+  } planes[7];
+  int n_planes = 0;
+  bool any_staged = actions_staged;
   if (do_out) {
     const size_t words = (4 * N + 31) / 32;
-    int st;
-    if ((st = bind_out(env, SL_OBS, out->obs, B * P * GRL_OBS_CHANNELS * N * 4, obs))) return st;
-    if ((st = bind_out(env, SL_MASK, out->mask_bits, B * P * words * 4, mask))) return st;
-    if ((st = bind_out(env, SL_REWARD, out->reward, B * P * 4, reward))) return st;
-    if ((st = bind_out(env, SL_DONE, out->done, B, done))) return st;
-    if ((st = bind_out(env, SL_WINNER, out->winner, B, winner))) return st;
-    if ((st = bind_out(env, SL_ERR, out->step_error, B, serr))) return st;
-    if ((st = bind_out(env, SL_AIDX, out->action_index, B * P * 4, aidx))) return st;
-    prm.obs = (float *)obs.dev;
-    prm.mask_bits = (uint32_t *)mask.dev;
-    prm.reward = (float *)reward.dev;
-    prm.done = (uint8_t *)done.dev;
-    prm.winner = (int8_t *)winner.dev;
-    prm.step_error = (uint8_t *)serr.dev;
-    prm.action_index = (int32_t *)aidx.dev;
+    const Slot slots[7] = {SL_OBS, SL_MASK, SL_REWARD, SL_DONE, SL_WINNER, SL_ERR, SL_AIDX};
+    void *user[7] = {out->obs, out->mask_bits, out->reward, out->done, out->winner, out->step_error, out->action_index};
+    const size_t strides[7] = {P * GRL_OBS_CHANNELS * N * 4, P * words * 4, P * 4, 1, 1, 1, P * 4};
+    for (int i = 0; i < 7; i++) {
+      planes[i].stride = strides[i];
+      int st = bind_out(env, slots[i], user[i], B * strides[i], planes[i].ob);
+      if (st) return st;
+      any_staged = any_staged || planes[i].ob.staged;
+    }
+    n_planes = 7;
+    prm.obs = (float *)planes[0].ob.dev;
+    prm.mask_bits = (uint32_t *)planes[1].ob.dev;
+    prm.reward = (float *)planes[2].ob.dev;
+    prm.done = (uint8_t *)planes[3].ob.dev;
+    prm.winner = (int8_t *)planes[4].ob.dev;
+    prm.step_error = (uint8_t *)planes[5].ob.dev;
+    prm.action_index = (int32_t *)planes[6].ob.dev;
   }
   if (!do_step && !do_out) return GRL_OK;
-  CUDA_TRY(grl_launch_turn(prm, do_step, do_out, env->stream));
-  env->launches++;
-  if (do_out) {
-    int st;
-    if ((st = flush_out(env, obs, need_sync))) return st;
-    if ((st = flush_out(env, mask, need_sync))) return st;
-    if ((st = flush_out(env, reward, need_sync))) return st;
-    if ((st = flush_out(env, done, need_sync))) return st;
-    if ((st = flush_out(env, winner, need_sync))) return st;
-    if ((st = flush_out(env, serr, need_sync))) return st;
-    if ((st = flush_out(env, aidx, need_sync))) return st;
+
+  if (!any_staged) {  // device buffers only: one asynchronous launch on the env's stream
+    CUDA_TRY(grl_launch_turn(prm, do_step, do_out, env->stream));
+    env->launches++;
+    return GRL_OK;
   }
-  if (need_sync) CUDA_TRY(cudaStreamSynchronize(env->stream));
+
+  // Host buffers: pipeline sub-ranges of the batch over side streams — H2D(actions) -> kernel ->
+  // D2H(results) per sub-range — so PCIe copies overlap the other sub-ranges' kernels.
+  int chunks = (B >= 8192 && env->pipe_chunks > 1) ? env->pipe_chunks : 1;
+  if (chunks > grl_env::kPipe) chunks = grl_env::kPipe;
+  if (chunks > 1) {
+    int st = ensure_pipe(env);
+    if (st) return st;
+    CUDA_TRY(cudaEventRecord(env->ev_start, env->stream));
+  }
+  const size_t per = ((B + chunks - 1) / chunks + 7) & ~(size_t)7;
+  for (int k = 0; k < chunks; k++) {
+    const size_t g0 = std::min(B, (size_t)k * per), g1 = std::min(B, g0 + per);
+    if (g0 >= g1) continue;
+    cudaStream_t sq = chunks > 1 ? env->pipe[k] : env->stream;
+    if (chunks > 1) CUDA_TRY(cudaStreamWaitEvent(sq, env->ev_start, 0));
+    if (actions_staged)
+      CUDA_TRY(cudaMemcpyAsync((char *)const_cast<void *>(prm.actions) + g0 * act_stride, (const char *)actions + g0 * act_stride,
+                               (g1 - g0) * act_stride, cudaMemcpyHostToDevice, sq));
+    GrlKParams pk = prm;
+    pk.game0 = (int)g0;
+    pk.game_end = (int)g1;
+    CUDA_TRY(grl_launch_turn(pk, do_step, do_out, sq));
+    env->launches++;
+    for (int i = 0; i < n_planes; i++) {
+      const OutBuf &ob = planes[i].ob;
+      if (ob.staged)
+        CUDA_TRY(cudaMemcpyAsync((char *)ob.user + g0 * planes[i].stride, (const char *)ob.dev + g0 * planes[i].stride,
+                                 (g1 - g0) * planes[i].stride, cudaMemcpyDeviceToHost, sq));
+    }
+    if (chunks > 1) {
+      CUDA_TRY(cudaEventRecord(env->ev_done[k], sq));
+      CUDA_TRY(cudaStreamWaitEvent(env->stream, env->ev_done[k], 0));
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(env->stream));  // host buffers are valid (and consumed) on return
   return GRL_OK;
 }
 
@@ -485,6 +538,8 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   env->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (hw > 0 ? hw : 1);
   const char *no_tma = getenv("GRL_NO_TMA");
   env->use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
+  const char *pc = getenv("GRL_PIPE_CHUNKS");
+  if (pc && atoi(pc) >= 1) env->pipe_chunks = atoi(pc);
   const char *pf = getenv("GRL_PREFETCH_DIST");
   env->prefetch_dist = pf ? atoi(pf) : 8192;  // ~1.7 waves of resident warps ahead (profiles/r1_variants.md)
   auto bail = [&](int code) {
@@ -545,6 +600,11 @@ int grl_destroy(grl_env *env) {
   for (auto &s : env->scratch)
     if (s.ptr) cudaFree(s.ptr);
   if (env->d_state) cudaFree(env->d_state);  // d_static and d_geom live in the same allocation
+  for (int k = 0; k < grl_env::kPipe; k++) {
+    if (env->pipe[k]) cudaStreamDestroy(env->pipe[k]);
+    if (env->ev_done[k]) cudaEventDestroy(env->ev_done[k]);
+  }
+  if (env->ev_start) cudaEventDestroy(env->ev_start);
   if (env->own_stream) cudaStreamDestroy(env->own_stream);
   delete env;
   return GRL_OK;

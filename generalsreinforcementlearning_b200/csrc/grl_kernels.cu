@@ -521,7 +521,8 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
   const bool use_policy = DO_STEP && (prm.flags & GRL_STEP_FLAG_RANDOM_POLICY) != 0;
   const bool read_actions = DO_STEP && !use_policy && prm.actions != nullptr;
   const int stride = gridDim.x * GRL_WARPS_PER_CTA;
-  int game = blockIdx.x * GRL_WARPS_PER_CTA + warp;
+  int game = prm.game0 + blockIdx.x * GRL_WARPS_PER_CTA + warp;
+  const int game_end = prm.game_end;
 
   uint64_t *bars = &s_bar[2 * warp];
   if (prm.use_tma && lane == 0) {
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
   int cur = 0;
   uint2 next_act = make_uint2(0u, 0u);
   // prime the pipeline: this warp's first game
-  if (game < prm.B) {
+  if (game < game_end) {
     if (prm.use_tma && lane == 0) {
       const bool snap = GRL_DIRTY_WB && DO_STEP;
       mbar_expect_tx(&bars[0], (uint32_t)(buf_words + (snap ? L.slab_words : 0)) * 4u);
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
     }
   }
 
-  for (; game < prm.B; game += stride) {
+  for (; game < game_end; game += stride) {
 #if GRL_PERSISTENT && GRL_CTA_SYNC
     __syncthreads();  // warps that ran out of games have exited and no longer count
 #endif
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
       // prefetch the next game's slab into the other buffer; its previous contents were handed
       // to a bulk store at the end of the last iteration, which must have finished reading them
       const int nxt = game + stride;
-      if (nxt < prm.B) {
+      if (nxt < game_end) {
         if (lane == 0) {
           if (DO_STEP) tma_store_wait_read();
           uint32_t *ns = wbase + (cur ^ 1) * buf_words;
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
       uint4 *dst2 = reinterpret_cast<uint4 *>(st);
       for (int k = lane; k < L.static_words / 4; k += 32) dst2[k] = __ldg(src2 + k);
       const int nxt = game + stride;
-      if (nxt < prm.B && read_actions && lane < prm.A)
+      if (nxt < game_end && read_actions && lane < prm.A)
         next_act = __ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)nxt * prm.A + lane);
     }
     __syncwarp();
@@ -1480,7 +1481,7 @@ static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream) {
     resident = persistent_grid(kern, smem, 1 << 30);
     tuned_smem = smem;
   }
-  int need = (prm.B + GRL_WARPS_PER_CTA - 1) / GRL_WARPS_PER_CTA;
+  int need = (prm.game_end - prm.game0 + GRL_WARPS_PER_CTA - 1) / GRL_WARPS_PER_CTA;
 #if GRL_PERSISTENT
   int grid = need < resident ? need : resident;
 #else

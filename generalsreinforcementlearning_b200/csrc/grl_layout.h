@@ -82,6 +82,7 @@ struct GrlKParams {
   unsigned long long policy_seed;
   uint32_t flags;
   int B, W, H, N, P, NW, A;
+  int game0, game_end;      // the turn kernel processes envs [game0, game_end) (host-buffer calls pipeline sub-ranges)
   GrlLayout L;
   int fog, pg, pc, pn, grow_interval;
   int env_id_base;
