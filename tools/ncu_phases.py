@@ -28,7 +28,7 @@ PHASES = [
     ("scalar read-outs", "---- read-outs ---"),
     ("legal mask", "// engine legal-action mask, packed"),
     ("observation planes", "// observation planes: Serializer.StateToTensor"),
-    ("tail", "if (DO_STEP && lane == 0) tma_store_commit();"),
+    ("tail", "generic-proxy accesses precede its next bulk refill"),
 ]
 
 
@@ -60,8 +60,13 @@ def main():
     body = rows[hdr_i + 1:hdr_i + 1 + len(seq)]
     inst, samp = defaultdict(int), defaultdict(int)
     phase = "prologue"
+    # the plane-major observation writer is an inlined helper defined above the kernel
+    obs_lo = next((i + 1 for i, l in enumerate(src) if "void obs_plane_major(" in l), None)
+    obs_hi = marks[0][1]
     for (f, line), r in zip(seq, body):
-        if f and f.endswith("grl_kernels.cu") and marks[0][1] <= line < kernel_end:
+        if f and f.endswith("grl_kernels.cu") and obs_lo and obs_lo <= line < obs_hi:
+            phase = "observation planes"
+        elif f and f.endswith("grl_kernels.cu") and marks[0][1] <= line < kernel_end:
             for (name, lo), (_, hi) in zip(marks, marks[1:]):
                 if lo <= line < hi:
                     phase = name
