@@ -34,6 +34,8 @@ MASK_ENGINE_URDL_BITS = 2
 MASK_ENGINE_HALF_BITS = 3
 
 STEP_FLAG_RANDOM_POLICY = 1
+ACTION_FLAG_SKIP_ENV = 1
+GRL_GYM_CHANNELS = 9
 
 ACTION_DTYPE = np.dtype(
     [
@@ -44,7 +46,7 @@ ACTION_DTYPE = np.dtype(
         ("to_y", "i1"),
         ("move_all", "u1"),
         ("present", "u1"),
-        ("reserved", "u1"),
+        ("flags", "u1"),
     ]
 )
 assert ACTION_DTYPE.itemsize == 8
@@ -105,6 +107,10 @@ class StepOutputs(C.Structure):
     ]
 
 
+class GymOutputs(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("mask", C.c_void_p), ("stats", C.c_void_p)]
+
+
 STATE_FIELDS = (
     ("owner", np.int32, "N"),
     ("army", np.int32, "N"),
@@ -147,6 +153,7 @@ ABI_FUNCTIONS = {
     "observe": (C.c_int, [C.c_void_p, C.POINTER(StepOutputs)]),
     "mask": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "visibility": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gym_observe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GymOutputs)]),
     "sample_actions": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "get_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(StatePlanes)]),
     "set_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(StatePlanes)]),

@@ -5,6 +5,7 @@
 // logic runs in grl_kernels.cu.  There is no CPU fallback: every entry point that
 // touches game state launches CUDA work and fails with GRL_ERR_CUDA if it cannot.
 #include <cuda_runtime.h>
+#include <cmath>
 
 #include <algorithm>
 #include <cstdarg>
@@ -55,6 +56,7 @@ struct grl_env {
   uint32_t *d_state = nullptr;
   uint32_t *d_static = nullptr;
   uint32_t *d_geom = nullptr;
+  float *d_logtab = nullptr;  // float32(log(a + 1) / 10) for a in 0..65535 (generals_env.py:324), built on first use
   Scratch scratch[SL_COUNT];
   int use_tma = 1;
   int prefetch_dist = 0;       // > 0: warp of game g prefetches the slab of game g+dist into L2
@@ -599,6 +601,7 @@ int grl_destroy(grl_env *env) {
   if (env->stream) cudaStreamSynchronize(env->stream);
   for (auto &s : env->scratch)
     if (s.ptr) cudaFree(s.ptr);
+  if (env->d_logtab) cudaFree(env->d_logtab);
   if (env->d_state) cudaFree(env->d_state);  // d_static and d_geom live in the same allocation
   for (int k = 0; k < grl_env::kPipe; k++) {
     if (env->pipe[k]) cudaStreamDestroy(env->pipe[k]);
@@ -742,6 +745,36 @@ int grl_visibility(grl_env *env, uint8_t *visible, uint8_t *fog) {
   bool need_sync = false;
   if ((st = flush_out(env, v, need_sync))) return st;
   if ((st = flush_out(env, f, need_sync))) return st;
+  if (need_sync) CUDA_TRY(cudaStreamSynchronize(env->stream));
+  return GRL_OK;
+}
+
+int grl_gym_observe(grl_env *env, int32_t max_turns, const grl_gym_outputs *out) {
+  if (!env || !out || max_turns < 1) return fail(GRL_ERR_INVALID_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(env->cfg.device));
+  const grl_config &c = env->cfg;
+  const size_t B = (size_t)c.num_envs, P = (size_t)c.num_players, N = (size_t)env->N;
+  if (!env->d_logtab) {
+    // the client computes np.log(army + 1) / 10.0 in float64 and stores it into a float32 array
+    std::vector<float> tab(65536);
+    for (int a = 0; a < 65536; a++) tab[a] = (float)(std::log((double)a + 1.0) / 10.0);
+    if (cudaMalloc((void **)&env->d_logtab, tab.size() * 4) != cudaSuccess)
+      return fail(GRL_ERR_NOMEM, "cudaMalloc of the log table: %s", cudaGetErrorString(cudaGetLastError()));
+    CUDA_TRY(cudaMemcpyAsync(env->d_logtab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, env->stream));
+    CUDA_TRY(cudaStreamSynchronize(env->stream));
+  }
+  OutBuf obs, mask, stats;
+  int st;
+  if ((st = bind_out(env, SL_OBS, out->obs, B * P * GRL_GYM_CHANNELS * N * 4, obs))) return st;
+  if ((st = bind_out(env, SL_MISC, out->mask, B * P * N * 5, mask))) return st;
+  if ((st = bind_out(env, SL_MISC2, out->stats, B * P * 4 * 4, stats))) return st;
+  GrlKParams prm = base_params(env);
+  CUDA_TRY(grl_launch_gym(prm, max_turns, env->d_logtab, (float *)obs.dev, (uint8_t *)mask.dev, (int32_t *)stats.dev, env->stream));
+  env->launches++;
+  bool need_sync = false;
+  if ((st = flush_out(env, obs, need_sync))) return st;
+  if ((st = flush_out(env, mask, need_sync))) return st;
+  if ((st = flush_out(env, stats, need_sync))) return st;
   if (need_sync) CUDA_TRY(cudaStreamSynchronize(env->stream));
   return GRL_OK;
 }

@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
 
     // ---- stage the slab in shared memory ---------------------------------------------
     // decode this game's action slots (loaded one game ahead) while its slab lands
+    bool skip = false;  // GRL_ACTION_FLAG_SKIP_ENV on slot 0: this env takes no turn in this call
     if (DO_STEP) {
       if (lane < GRL_MAX_ACTIONS) {
         uint2 d = make_uint2(0u, 0xffffffffu);
@@ -572,6 +573,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
         s_act[2 * lane] = d.x;
         s_act[2 * lane + 1] = d.y;
       }
+      if (read_actions) skip = ((__shfl_sync(FULL, next_act.y, 0) >> 24) & GRL_ACTION_FLAG_SKIP_ENV) != 0u;
     }
     if (prm.use_tma) {
       mbar_wait(&bars[cur], (phase_bits >> cur) & 1u);
@@ -632,7 +634,9 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
       prev_true_army[p] = p < P ? (int)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY] : 0;
 
     if (DO_STEP) {
-      if (over) {
+      if (skip) {
+        err = (flags >> GRL_FLAG_ERR_SHIFT) & 0xffu;  // Step is not called: everything stays as it was
+      } else if (over) {
         // turn_processor.go:95-113: ErrGameOver, nothing mutated
         err = GRL_STEP_GAME_OVER;
         if (lane == 0) {
@@ -1328,6 +1332,66 @@ __global__ void grl_visibility_kernel(const GrlKParams prm, uint8_t *__restrict_
   }
 }
 
+// generals_gym read-outs (python/generals_gym/generals_env.py:291-387) of every player's
+// fog-filtered proto view (internal/grpc/gameserver/server.go:556-582).  One thread per
+// (env, player, tile); channel planes are written coalesced over tiles.  Not on the turn path.
+__global__ void grl_gym_kernel(const GrlKParams prm, int max_turns, const float *__restrict__ logtab, float *__restrict__ obs,
+                               uint8_t *__restrict__ mask, int32_t *__restrict__ stats) {
+  const GrlLayout &L = prm.L;
+  const int N = prm.N, P = prm.P, NW = prm.NW, W = prm.W, H = prm.H;
+  const size_t total = (size_t)prm.B * P * N;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int t = (int)(idx % N);
+    const int p = (int)((idx / N) % P);
+    const int game = (int)(idx / ((size_t)N * P));
+    const uint32_t *s = prm.state + (size_t)game * L.slab_words;
+    const uint32_t *stt = prm.statics + (size_t)game * L.static_words;
+    const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+    const bool vis = prm.fog ? bit_of(s + L.off_vis + p * NW, t) : true;
+    const bool mine = vis && bit_of(s + L.off_own + p * NW, t);
+    bool owned = false;
+    for (int q = 0; q < P; q++) owned = owned || bit_of(s + L.off_own + q * NW, t);
+    const bool mnt = bit_of(stt, t), city = bit_of(stt + NW, t), gen = bit_of(stt + 2 * NW, t);
+    const uint32_t a = vis ? army[t] : 0u;  // hidden and fogged tiles show no owner and no army
+    if (obs) {
+      float *o = obs + ((size_t)game * P + p) * GRL_GYM_CHANNELS * N + t;
+      const double tf = fmin((double)s[GRL_HDR_TURN] / (double)max_turns, 1.0);
+      o[0 * N] = vis ? 1.f : 0.f;
+      o[1 * N] = mine ? 0.5f : ((vis && owned) ? 1.f : 0.f);
+      o[2 * N] = a > 0u ? logtab[a] : 0.f;
+      o[3 * N] = (!mnt && !city && !gen) ? 1.f : 0.f;  // a hidden tile is a normal tile by definition
+      o[4 * N] = mnt ? 1.f : 0.f;
+      o[5 * N] = city ? 1.f : 0.f;
+      o[6 * N] = gen ? 1.f : 0.f;
+      o[7 * N] = (float)tf;
+      o[8 * N] = 0.f;
+    }
+    if (mask) {
+      const int x = t % W, y = t / W;
+      const bool src = mine && a > 1u;
+      const bool up = src && y > 0 && !bit_of(stt, t - W);
+      const bool right = src && x < W - 1 && !bit_of(stt, t + 1);
+      const bool down = src && y < H - 1 && !bit_of(stt, t + W);
+      const bool left = src && x > 0 && !bit_of(stt, t - 1);
+      uint8_t *m = mask + (((size_t)game * P + p) * N + t) * 5;
+      m[0] = up;
+      m[1] = right;
+      m[2] = down;
+      m[3] = left;
+      m[4] = up || right || down || left;
+    }
+    if (stats && t == 0) {
+      int tiles = 0;
+      for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + p * NW + k]);
+      int32_t *so = stats + ((size_t)game * P + p) * 4;
+      so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ARMY_COUNT];
+      so[1] = tiles;
+      so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> p) & 1u);
+      so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_GENERAL_IDX];
+    }
+  }
+}
+
 // packed engine mask with the half-move replica: [B][P][rep][words]
 __global__ void grl_mask_replicate_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t rows, int words,
                                           int rep) {
@@ -1571,6 +1635,13 @@ cudaError_t grl_launch_mask_bytes(const GrlKParams &prm, int variant, uint8_t *o
 cudaError_t grl_launch_visibility(const GrlKParams &prm, uint8_t *visible, uint8_t *fog, cudaStream_t stream) {
   size_t total = (size_t)prm.B * prm.P * prm.N;
   grl_visibility_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(prm, visible, fog);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *logtab, float *obs, uint8_t *mask, int32_t *stats,
+                           cudaStream_t stream) {
+  size_t total = (size_t)prm.B * prm.P * prm.N;
+  grl_gym_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(prm, max_turns, logtab, obs, mask, stats);
   return cudaGetLastError();
 }
 

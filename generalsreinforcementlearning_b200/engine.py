@@ -17,7 +17,7 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 
 from . import _abi
-from ._abi import ACTION_DTYPE, BoundLibrary, Config, StatePlanes, StepOutputs
+from ._abi import ACTION_DTYPE, BoundLibrary, Config, GymOutputs, StatePlanes, StepOutputs
 
 
 def _ptr(buf) -> Optional[int]:
@@ -152,6 +152,13 @@ class BatchedEngine:
 
     def observe(self, out: StepOutputs) -> None:
         self.lib.check(self.lib.observe(self._h, C.byref(out)), "observe")
+
+    def gym_observe(self, max_turns: int, obs=None, mask=None, stats=None) -> None:
+        """generals_gym read-outs for every (env, player): obs [B,P,9,H,W] f32, mask [B,P,N*5] u8,
+        stats [B,P,4] i32 (python/generals_gym/generals_env.py:291-387)."""
+        o = GymOutputs()
+        o.obs, o.mask, o.stats = _ptr(obs), _ptr(mask), _ptr(stats)
+        self.lib.check(self.lib.gym_observe(self._h, int(max_turns), C.byref(o)), "gym_observe")
 
     def sample_actions(self, policy_seed: int, actions=None):
         if actions is None:

@@ -1,0 +1,205 @@
+"""``generals_gym``-compatible VECTOR environment backed directly by the C ABI.
+
+Contract mirrored from the reference's ``python/generals_gym/generals_env.py`` (one game
+per gRPC round trip there; B games per kernel launch here):
+
+  observation  float32 ``(9, H, W)`` in [0, 1] per env        generals_env.py:111-116, 291-342
+  action       ``Discrete(W*H*5)``: tile*5 + {up,right,down,left,half}      :118-120, 389-441
+  mask         ``info["valid_actions_mask"]`` bool ``(W*H*5,)``             :344-387
+  reward       the client-side shaping of ``_calculate_reward``             :499-561
+  terminated   game status left IN_PROGRESS; truncated at ``max_turns``     :277-279
+  invalid action (mask false): no turn is taken, reward -0.1                :226-229
+
+The agent is player 0; the opponent is the reference's default random opponent (a uniformly
+random full move, ``_submit_random_opponent_action`` :443-497) drawn on the device, or a second
+action tensor for self-play.  Observations, masks, rewards and flags are torch tensors on the
+engine's device — nothing crosses PCIe per step.  Finished or truncated envs are re-seeded
+automatically (``info["final_observation"]`` keeps the pre-reset view), as Gymnasium vector
+envs do.
+
+This module needs neither ``gymnasium`` (absent from the image) nor gRPC.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _abi
+from .engine import BatchedEngine, make_config
+
+# direction order of the client: up, right, down, left (generals_env.py:369, 413)
+_DX = (0, 1, 0, -1)
+_DY = (-1, 0, 1, 0)
+
+
+class Box:
+    """Minimal stand-in for gymnasium.spaces.Box (shape/dtype/bounds only)."""
+
+    def __init__(self, low, high, shape, dtype):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = int(n)
+
+
+class GeneralsVecEnv:
+    metadata = {"render_modes": ["ansi"], "render_fps": 4}
+
+    def __init__(self, num_envs: int, board_width: int = 15, board_height: int = 15, max_players: int = 2,
+                 fog_of_war: bool = True, max_turns: int = 500, device: int = 0, seed: int = 12345,
+                 self_play: bool = False, lib=None, host_threads: int = 0):
+        import torch
+
+        if max_players != 2:
+            raise ValueError("generals_gym drives 2-player games (generals_env.py:68)")
+        if lib is None:
+            from . import load_library
+
+            lib = load_library()
+        self.torch = torch
+        self.num_envs, self.W, self.H, self.P = num_envs, board_width, board_height, max_players
+        self.board_size = self.N = board_width * board_height
+        self.max_turns, self.self_play = max_turns, self_play
+        self.engine = BatchedEngine(lib, make_config(lib, num_envs=num_envs, width=board_width, height=board_height,
+                                                     num_players=max_players, device=device, max_actions=max_players,
+                                                     fog_of_war=1 if fog_of_war else 0, host_threads=host_threads))
+        self.on_device = lib.prefix == "grl_"
+        self.device = torch.device("cuda", device) if self.on_device else torch.device("cpu")
+        self.single_observation_space = Box(0.0, 1.0, (9, board_height, board_width), np.float32)
+        self.single_action_space = Discrete(self.N * 5)
+        self.observation_space = Box(0.0, 1.0, (num_envs, 9, board_height, board_width), np.float32)
+        self.action_space = Discrete(self.N * 5)
+        B, P, N, dev = num_envs, self.P, self.N, self.device
+        self._obs = torch.zeros((B, P, 9, self.H, self.W), dtype=torch.float32, device=dev)
+        self._mask = torch.zeros((B, P, N * 5), dtype=torch.uint8, device=dev)
+        self._stats = torch.zeros((B, P, 4), dtype=torch.int32, device=dev)
+        self._prev_stats = torch.zeros_like(self._stats)
+        self._actions = torch.zeros((B, P, 8), dtype=torch.uint8, device=dev)  # grl_action[B][P]
+        self._done = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self._winner = torch.zeros(B, dtype=torch.int8, device=dev)
+        self._err = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self._turns = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._episode = np.zeros(B, dtype=np.int64)
+        self._base_seed = int(seed)
+        self._gen = torch.Generator(device=dev)
+        self._gen.manual_seed(int(seed))
+        tile = torch.arange(N, device=dev)
+        self._fx, self._fy = (tile % self.W).to(torch.int64), (tile // self.W).to(torch.int64)
+        self._dx = torch.tensor(_DX, device=dev, dtype=torch.int64)
+        self._dy = torch.tensor(_DY, device=dev, dtype=torch.int64)
+
+    # ------------------------------------------------------------------ helpers
+    def _seeds(self, env_ids: np.ndarray) -> np.ndarray:
+        return self._base_seed + env_ids.astype(np.int64) + self._episode[env_ids] * self.num_envs
+
+    def _refresh(self):
+        self.engine.gym_observe(self.max_turns, self._obs, self._mask, self._stats)
+
+    def _encode(self, slot: int, action_idx, valid):
+        """Action index -> grl_action bytes of player ``slot`` (generals_env.py:389-441).  A half
+        move goes to the FIRST IN-BOUNDS direction in the order up, right, down, left — the
+        reference's own simplification (:420-427)."""
+        t = self.torch
+        a = action_idx.to(t.int64)
+        tile, info = a // 5, a % 5
+        fx, fy = self._fx[tile], self._fy[tile]
+        half = info == 4
+        d = t.where(half, t.zeros_like(info), info)
+        tx, ty = fx + self._dx[d], fy + self._dy[d]
+        if bool(half.any()):
+            hx, hy = tx.clone(), ty.clone()
+            found = t.zeros_like(half)
+            for k in range(4):
+                nx, ny = fx + _DX[k], fy + _DY[k]
+                ok = (nx >= 0) & (nx < self.W) & (ny >= 0) & (ny < self.H) & ~found
+                hx, hy = t.where(ok, nx, hx), t.where(ok, ny, hy)
+                found |= ok
+            tx, ty = t.where(half, hx, tx), t.where(half, hy, ty)
+        rec = self._actions[:, slot]
+        rec[:, 0] = slot
+        rec[:, 1], rec[:, 2] = fx.to(t.uint8), fy.to(t.uint8)
+        rec[:, 3], rec[:, 4] = (tx & 0xff).to(t.uint8), (ty & 0xff).to(t.uint8)
+        rec[:, 5] = (~half).to(t.uint8)        # Action.half == False -> MoveAll
+        rec[:, 6] = valid.to(t.uint8)          # present
+        rec[:, 7] = 0
+
+    def _random_opponent(self):
+        """A uniformly random legal full move of player 1 (generals_env.py:443-497); none if it has none."""
+        t = self.torch
+        m = self._mask[:, 1].view(self.num_envs, self.N, 5)[:, :, :4].reshape(self.num_envs, -1).to(t.float32)
+        has = m.sum(1) > 0
+        pick = t.multinomial(m + (~has).unsqueeze(1).to(t.float32), 1, generator=self._gen).squeeze(1)
+        return (pick // 4) * 5 + pick % 4, has
+
+    # ------------------------------------------------------------------ gym API
+    def reset(self, seed: Optional[int] = None, options=None) -> Tuple[Any, Dict[str, Any]]:
+        if seed is not None:
+            self._base_seed = int(seed)
+            self._gen.manual_seed(int(seed))
+        self._episode[:] = 0
+        ids = np.arange(self.num_envs)
+        self.engine.reset_seeded(self._seeds(ids))
+        self._turns.zero_()
+        self._refresh()
+        return self._obs[:, 0], {"valid_actions_mask": self._mask[:, 0].bool(), "turn": self._turns.clone()}
+
+    def step(self, action, opponent_action=None):
+        """action: int64 [B] indices into Discrete(N*5) for player 0 (and ``opponent_action`` for
+        player 1 under self-play).  Returns (obs, reward, terminated, truncated, info)."""
+        t = self.torch
+        B = self.num_envs
+        action = t.as_tensor(action, device=self.device).to(t.int64)
+        valid = self._mask[:, 0].gather(1, action.unsqueeze(1)).squeeze(1).bool()
+        self._encode(0, action, valid)
+        if opponent_action is not None:
+            oa = t.as_tensor(opponent_action, device=self.device).to(t.int64)
+            ov = self._mask[:, 1].gather(1, oa.unsqueeze(1)).squeeze(1).bool()
+        else:
+            oa, ov = self._random_opponent()
+        self._encode(1, oa, ov)
+        # an invalid agent action is rejected client-side: that env takes no turn (:226-229)
+        self._actions[:, 0, 7] = (~valid).to(t.uint8) * _abi.ACTION_FLAG_SKIP_ENV
+        self._prev_stats.copy_(self._stats)
+        self.engine.step_fused(self._actions, self.engine.outputs(done=self._done, winner=self._winner, step_error=self._err))
+        # the server rejects an invalid move before the turn runs (action_validator.go:126-127);
+        # the turn that did run may still have aborted (step_error) — the client only sees states
+        self._turns += valid.to(t.int32)
+        self._refresh()
+        st, pv = self._stats.to(t.float64), self._prev_stats.to(t.float64)
+        terminated = (self._done != 0) & valid
+        truncated = (self._turns >= self.max_turns) & valid
+        # _calculate_reward (:499-561), python floats
+        shaped = (st[:, 0, 1] - pv[:, 0, 1]) * 1.0 + (st[:, 0, 0] - pv[:, 0, 0]) * 0.01
+        shaped = shaped + 50.0 * ((self._prev_stats[:, 1, 2] == 1) & (self._stats[:, 1, 2] == 0)).to(t.float64)
+        win = self._winner == 0
+        reward = t.where(terminated, t.where(win, t.full_like(shaped, 100.0), t.full_like(shaped, -100.0)), shaped)
+        reward = t.where(valid, reward, t.full_like(shaped, -0.1))
+        info: Dict[str, Any] = {"turn": self._turns.clone(), "invalid_action": ~valid,
+                                "winner": self._winner.to(t.int32), "step_error": self._err.clone()}
+        finished = terminated | truncated
+        if bool(finished.any()):
+            ids = finished.nonzero(as_tuple=True)[0]
+            info["final_observation"] = self._obs[ids, 0].clone()
+            info["final_env_ids"] = ids
+            ids_np = ids.cpu().numpy()
+            self._episode[ids_np] += 1
+            self.engine.reset_seeded(self._seeds(ids_np), ids_np.astype(np.int32))
+            self._turns[ids] = 0
+            self._refresh()
+        info["valid_actions_mask"] = self._mask[:, 0].bool()
+        return self._obs[:, 0], reward, terminated, truncated, info
+
+    def opponent_view(self):
+        """Player 1's observation and mask (self-play)."""
+        return self._obs[:, 1], self._mask[:, 1].bool()
+
+    def render(self, env: int = 0, player: int = 0) -> str:
+        from .render import render_board
+
+        return render_board(self.engine, env, player)
+
+    def close(self):
+        self.engine.close()

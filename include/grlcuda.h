@@ -87,8 +87,14 @@ typedef struct grl_action {
   int8_t to_x, to_y;
   uint8_t move_all; /* 1: leave one behind; 0: move half, floor, min 1 (core/movement.go:40-49) */
   uint8_t present;
-  uint8_t reserved;
+  uint8_t flags;    /* GRL_ACTION_FLAG_*; read from slot 0 of an env only */
 } grl_action;
+
+/* Slot 0 of an env may carry this flag: the env takes NO turn in this call (its game is still
+ * waiting for its players' actions — the per-game turn barrier of
+ * internal/grpc/gameserver/game_manager.go:559-600; or the gym client rejected the action
+ * before submitting it, generals_env.py:226-229).  State and read-outs are left unchanged. */
+#define GRL_ACTION_FLAG_SKIP_ENV 1
 
 /* ---- reward weights (experience/rewards.go:9-37) ------------------------ */
 typedef struct grl_reward_config {
@@ -164,6 +170,18 @@ typedef struct grl_state_planes {
   int32_t *step_error;   /* [count]                                                  */
 } grl_state_planes;
 
+/* ---- generals_gym read-outs of player p's fog-filtered view (the proto view of
+ *      internal/grpc/gameserver/server.go:556-582 fed through
+ *      python/generals_gym/generals_env.py:291-387); any NULL member is skipped -------------- */
+#define GRL_GYM_CHANNELS 9
+typedef struct grl_gym_outputs {
+  float *obs;      /* [B][P][9][H][W] _get_observation: visible, ownership 0/.5/1, log(army+1)/10,
+                      one-hot normal/mountain/city/general, turn/max_turns, 0 */
+  uint8_t *mask;   /* [B][P][N*5] _get_valid_actions_mask: tile*5 + {up,right,down,left,half} */
+  int32_t *stats;  /* [B][P][4] PlayerState: army_count, tile_count (cached list length), alive,
+                      general_idx (server.go:528-553) */
+} grl_gym_outputs;
+
 /* flags for grl_step / grl_step_fused */
 enum {
   GRL_STEP_FLAG_NONE = 0,
@@ -216,6 +234,10 @@ int grl_observe(grl_env *env, const grl_step_outputs *out);
 int grl_mask(grl_env *env, int variant, void *out);
 /* visible/fog: bytes [B][P][N] (PlayerVisibility.VisibleTiles / FogTiles). */
 int grl_visibility(grl_env *env, uint8_t *visible, uint8_t *fog);
+
+/* generals_gym observation / mask / player stats of the current state for every (env, player).
+ * max_turns normalises channel 7 (generals_env.py:337). */
+int grl_gym_observe(grl_env *env, int32_t max_turns, const grl_gym_outputs *out);
 
 /* Draw the synthetic policy's actions for the current state into `actions`
  * ([B][max_actions], slot p = player p's move, empty when it has none). */

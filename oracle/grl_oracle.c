@@ -21,6 +21,7 @@
  *
  * Exports the ABI of include/grlcuda.h with the prefix grlo_ (host pointers only).
  */
+#include <math.h>
 #include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -1183,6 +1184,12 @@ static void *job_run(void *arg) {
         sample_actions(g, j->seed, (uint64_t)(e->cfg.env_id_base + b), slots, A, scratch);
         acts = slots;
       }
+      /* GRL_ACTION_FLAG_SKIP_ENV: the game is still waiting at its turn barrier
+         (game_manager.go:559-600) — Step is simply not called for it */
+      if (acts && !(j->flags & GRL_STEP_FLAG_RANDOM_POLICY) && (acts[0].flags & GRL_ACTION_FLAG_SKIP_ENV)) {
+        write_outputs(e, b, j->out, scratch);
+        continue;
+      }
       process_turn(g, &e->cfg, acts, A, j->cnt);
     }
     write_outputs(e, b, j->out, scratch);
@@ -1366,6 +1373,109 @@ int grlo_sample_actions(grlo_env *e, uint64_t policy_seed, grl_action *actions) 
   if (!e || !actions) return GRL_ERR_INVALID_ARG;
   batch_ctx_t x = {e, policy_seed, actions, NULL, NULL, 0};
   par_range(e->nthreads, e->cfg.num_envs, sample_range, &x);
+  return GRL_OK;
+}
+
+/* ---- generals_gym read-outs ------------------------------------------------------------
+ * The proto view of one player (server.go:556-582 convertGameStateToProto), then
+ * GeneralsEnv._get_observation / _get_valid_actions_mask (generals_env.py:291-387). */
+typedef struct {
+  int type, owner, army, visible;
+} view_tile_t;
+
+static void proto_view(const game_t *g, int p, view_tile_t *v) {
+  for (int i = 0; i < g->N; i++) {
+    int vis = g->fog ? (int)((g->T[i].vis >> p) & 1u) : 1;
+    int fogt = g->fog && !vis && g->T[i].type != GRL_TILE_NORMAL;
+    v[i].type = g->T[i].type;
+    v[i].owner = g->T[i].owner;
+    v[i].army = g->T[i].army;
+    v[i].visible = vis;
+    if (!vis && !fogt) { /* completely hidden */
+      v[i].type = GRL_TILE_NORMAL;
+      v[i].owner = -1;
+      v[i].army = 0;
+    } else if (fogt && !vis) { /* in fog: type shown, state hidden */
+      v[i].owner = -1;
+      v[i].army = 0;
+    }
+  }
+}
+
+static void gym_range(void *c, int i0, int i1);
+
+typedef struct {
+  grlo_env *e;
+  int max_turns;
+  const grl_gym_outputs *out;
+} gym_ctx_t;
+
+static void gym_range(void *c, int i0, int i1) {
+  gym_ctx_t *x = (gym_ctx_t *)c;
+  grlo_env *e = x->e;
+  int N = e->N, P = e->cfg.num_players, W = e->cfg.width, H = e->cfg.height;
+  view_tile_t *v = (view_tile_t *)malloc(sizeof(view_tile_t) * (size_t)N);
+  static const int DX[4] = {0, 1, 0, -1}, DY[4] = {-1, 0, 1, 0}; /* generals_env.py:369 */
+  for (int b = i0; b < i1; b++) {
+    const game_t *g = &e->g[b];
+    for (int p = 0; p < P; p++) {
+      proto_view(g, p, v);
+      size_t bp = (size_t)b * P + p;
+      if (x->out->obs) {
+        float *o = x->out->obs + bp * GRL_GYM_CHANNELS * N;
+        memset(o, 0, sizeof(float) * (size_t)GRL_GYM_CHANNELS * N);
+        double tf = (double)g->turn / (double)x->max_turns;
+        if (tf > 1.0) tf = 1.0;
+        for (int i = 0; i < N; i++) {
+          if (v[i].visible) o[0 * N + i] = 1.0f;
+          if (v[i].owner == p)
+            o[1 * N + i] = 0.5f;
+          else if (v[i].owner >= 0)
+            o[1 * N + i] = 1.0f;
+          if (v[i].army > 0) o[2 * N + i] = (float)(log((double)v[i].army + 1.0) / 10.0);
+          if (v[i].type == GRL_TILE_NORMAL)
+            o[3 * N + i] = 1.0f;
+          else if (v[i].type == GRL_TILE_MOUNTAIN)
+            o[4 * N + i] = 1.0f;
+          else if (v[i].type == GRL_TILE_CITY)
+            o[5 * N + i] = 1.0f;
+          else if (v[i].type == GRL_TILE_GENERAL)
+            o[6 * N + i] = 1.0f;
+          o[7 * N + i] = (float)tf;
+        }
+      }
+      if (x->out->mask) {
+        uint8_t *m = x->out->mask + bp * (size_t)N * 5;
+        memset(m, 0, (size_t)N * 5);
+        for (int y = 0; y < H; y++)
+          for (int xx = 0; xx < W; xx++) {
+            int idx = y * W + xx;
+            if (v[idx].owner != p || v[idx].army <= 1) continue;
+            for (int d = 0; d < 4; d++) {
+              int nx = xx + DX[d], ny = y + DY[d];
+              if (nx < 0 || nx >= W || ny < 0 || ny >= H) continue;
+              if (v[ny * W + nx].type == GRL_TILE_MOUNTAIN) continue;
+              m[idx * 5 + d] = 1;
+              m[idx * 5 + 4] = 1;
+            }
+          }
+      }
+      if (x->out->stats) {
+        int32_t *st = x->out->stats + bp * 4;
+        st[0] = g->pl[p].army_count;
+        st[1] = g->pl[p].n_owned;
+        st[2] = g->pl[p].alive;
+        st[3] = g->pl[p].general_idx;
+      }
+    }
+  }
+  free(v);
+}
+
+int grlo_gym_observe(grlo_env *e, int32_t max_turns, const grl_gym_outputs *out) {
+  if (!e || !out || max_turns < 1) return GRL_ERR_INVALID_ARG;
+  gym_ctx_t x = {e, max_turns, out};
+  par_range(e->nthreads, e->cfg.num_envs, gym_range, &x);
   return GRL_OK;
 }
 
