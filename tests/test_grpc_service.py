@@ -1,0 +1,294 @@
+"""The gRPC GameService / ExperienceService front end served over the CPU
+oracle library: wire contract, validation order, turn barrier, fog-filtered views, experience
+records.  When /root/reference is present (this container only) the reference's OWN generated
+client stubs are pointed at the server as well."""
+import os
+import sys
+
+import grpc
+import numpy as np
+import pytest
+
+from generalsreinforcementlearning_b200 import _abi
+from generalsreinforcementlearning_b200.grpc_schema import common, experience, game
+from generalsreinforcementlearning_b200.grpc_service import Stub, serve, validate_move
+from helpers import new_engine
+
+GAME = "generals.game.v1.GameService"
+EXP = "generals.experience.v1.ExperienceService"
+DIRS = [(0, -1), (1, 0), (0, 1), (-1, 0)]  # engine mask order: up, right, down, left
+
+
+@pytest.fixture()
+def server(oracle_lib):
+    srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=8, seed=1000)
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    yield gs, Stub(ch, GAME), Stub(ch, EXP), ch, port
+    ch.close()
+    srv.stop(0)
+    gs.close()
+
+
+def _start(stub, W=8, H=8, collect=False):
+    cfg = game.GameConfig(width=W, height=H, max_players=2, fog_of_war=True, collect_experiences=collect)
+    gid = stub.CreateGame(game.CreateGameRequest(config=cfg)).game_id
+    j = [stub.JoinGame(game.JoinGameRequest(game_id=gid, player_name=n)) for n in ("alice", "bob")]
+    return gid, j
+
+
+def _legal_action(state, rng, turn):
+    mask = np.array(state.action_mask, bool)
+    W = state.board.width
+    idx = np.nonzero(mask)[0]
+    if len(idx) == 0:
+        return None
+    k = int(idx[rng.integers(len(idx))])
+    t, d = k // 4, k % 4
+    a = game.Action(type=common.ACTION_TYPE_MOVE, turn_number=turn, half=bool(rng.integers(2)))
+    getattr(a, "from").x, getattr(a, "from").y = t % W, t // W
+    a.to.x, a.to.y = t % W + DIRS[d][0], t // W + DIRS[d][1]
+    return a
+
+
+def test_lifecycle_and_validation_order(server):
+    gs, stub, _, _, _ = server
+    r = stub.CreateGame(game.CreateGameRequest())
+    assert r.game_id == "game-1" and (r.config.width, r.config.height, r.config.max_players, r.config.fog_of_war) == (20, 20, 2, True)
+    gid, (j0, j1) = _start(stub)
+    assert (j0.player_id, j0.player_token) == (0, f"token-{gid}-0") and j1.player_id == 1
+    # the first joiner saw the lobby placeholder, the second the running game
+    assert j0.initial_state.current_phase == common.GAME_PHASE_LOBBY and j0.initial_state.status == common.GAME_STATUS_WAITING
+    assert j1.initial_state.current_phase == common.GAME_PHASE_RUNNING and j1.initial_state.status == common.GAME_STATUS_IN_PROGRESS
+    # re-join by name returns the same identity; a third player is refused
+    assert stub.JoinGame(game.JoinGameRequest(game_id=gid, player_name="alice")).player_token == j0.player_token
+    with pytest.raises(grpc.RpcError) as e:
+        stub.JoinGame(game.JoinGameRequest(game_id=gid, player_name="carol"))
+    assert e.value.code() == grpc.StatusCode.FAILED_PRECONDITION  # no longer in the lobby phase
+    with pytest.raises(grpc.RpcError) as e:
+        stub.JoinGame(game.JoinGameRequest(game_id="game-99", player_name="x"))
+    assert e.value.code() == grpc.StatusCode.NOT_FOUND
+    with pytest.raises(grpc.RpcError) as e:
+        stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=0, player_token="nope"))
+    assert e.value.code() == grpc.StatusCode.PERMISSION_DENIED
+    # SubmitAction failures come back in-band, in the reference's precedence
+    sub = lambda **kw: stub.SubmitAction(game.SubmitActionRequest(**kw))
+    assert sub(game_id="game-99").error_code == common.ERROR_CODE_GAME_NOT_FOUND
+    lobby = stub.CreateGame(game.CreateGameRequest()).game_id
+    assert sub(game_id=lobby, player_id=0).error_code == common.ERROR_CODE_INVALID_PHASE
+    assert sub(game_id=gid, player_id=0, player_token="bad").error_code == common.ERROR_CODE_INVALID_PLAYER
+    st = stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=0, player_token=j0.player_token)).state
+    a = _legal_action(st, np.random.default_rng(0), turn=5)
+    r = sub(game_id=gid, player_id=0, player_token=j0.player_token, action=a)
+    assert r.error_code == common.ERROR_CODE_INVALID_TURN and "expected 0, got 5" in r.error_message
+    bad = game.Action(type=common.ACTION_TYPE_MOVE, turn_number=0)
+    getattr(bad, "from").x = 0
+    bad.to.x = 5
+    r = sub(game_id=gid, player_id=0, player_token=j0.player_token, action=bad)
+    assert r.error_code == common.ERROR_CODE_INVALID_TURN and "action validation failed" in r.error_message
+    # idempotency: the cached response is returned, the action is not applied twice
+    a.turn_number = 0
+    r1 = sub(game_id=gid, player_id=0, player_token=j0.player_token, action=a, idempotency_key="k1")
+    r2 = sub(game_id=gid, player_id=0, player_token=j0.player_token, action=a, idempotency_key="k1")
+    assert r1.success and r2.success and r1.next_turn_number == r2.next_turn_number == 1
+    assert stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=0, player_token=j0.player_token)).state.turn == 0
+    # the turn runs when the LAST player has submitted (an empty request = no action this turn)
+    assert sub(game_id=gid, player_id=1, player_token=j1.player_token).success
+    assert stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=0, player_token=j0.player_token)).state.turn == 1
+
+
+def test_served_games_follow_the_engine_exactly(server, oracle_lib):
+    """Two games interleaved on one pool; each must equal a private engine fed the same moves."""
+    _served_games_follow(server, oracle_lib)
+
+
+@pytest.fixture()
+def cuda_server(cuda_lib):
+    srv, gs, port = serve("127.0.0.1:0", lib=cuda_lib, slots_per_pool=64, seed=1000)
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    yield gs, Stub(ch, GAME), Stub(ch, EXP), ch, port
+    ch.close()
+    srv.stop(0)
+    gs.close()
+
+
+@pytest.mark.gpu
+def test_served_games_on_the_gpu_follow_the_oracle(cuda_server, oracle_lib):
+    """The same service over libgrlcuda.so (device-resident pools); mirrors are oracle engines."""
+    _served_games_follow(cuda_server, oracle_lib)
+
+
+@pytest.mark.gpu
+def test_experience_stream_on_the_gpu(cuda_server, oracle_lib):
+    _experience_stream_records(cuda_server, oracle_lib)
+
+
+def _served_games_follow(server, oracle_lib):
+    gs, stub, _, _, _ = server
+    rng = np.random.default_rng(7)
+    games = [_start(stub, 8, 8) for _ in range(2)]
+    mirrors = []
+    for i, (gid, _) in enumerate(games):
+        m = new_engine(oracle_lib, 8, 8, 2, 1)
+        m.reset_seeded([1000 + int(gid.split("-")[1])])
+        mirrors.append(m)
+    for turn in range(40):
+        for (gid, js), m in zip(games, mirrors):
+            if rng.random() < 0.25:
+                continue  # this game sits this round out: the other one must not be disturbed
+            acts = np.zeros((1, m.A), _abi.ACTION_DTYPE)
+            for j in js:
+                st = stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)).state
+                if st.current_phase != common.GAME_PHASE_RUNNING:
+                    break
+                a = _legal_action(st, rng, st.turn)
+                req = game.SubmitActionRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)
+                if a is not None:
+                    req.action.CopyFrom(a)
+                    f = getattr(a, "from")
+                    s = acts[0, j.player_id]
+                    s["player_id"], s["from_x"], s["from_y"], s["to_x"], s["to_y"] = j.player_id, f.x, f.y, a.to.x, a.to.y
+                    s["move_all"], s["present"] = (0 if a.half else 1), 1
+                resp = stub.SubmitAction(req)
+                assert resp.success or resp.error_code == common.ERROR_CODE_UNSPECIFIED, resp.error_message
+            else:
+                m.step(acts)
+    for (gid, js), m in zip(games, mirrors):
+        g = gs.games[gid]
+        served = g.pool.engine.get_state(g.slot, 1)
+        want = m.get_state()
+        for k in want:
+            assert np.array_equal(served[k], want[k]), (gid, k)
+        # and the fog-filtered proto view is what the client contract says
+        vis, fog = m.visibility()
+        for j in js:
+            st = stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)).state
+            assert st.turn == int(want["turn"][0]) and len(st.board.tiles) == 64
+            for i, t in enumerate(st.board.tiles):
+                v, f = bool(vis[0, j.player_id, i]), bool(fog[0, j.player_id, i])
+                assert (t.visible, t.fog_of_war) == (v, f)
+                if v:
+                    assert (t.owner_id, t.army_count) == (int(want["owner"][0, i]), int(want["army"][0, i]))
+                else:
+                    assert (t.owner_id, t.army_count) == (-1, 0)
+                    assert t.type == (common.TILE_TYPE_NORMAL if not f else {1: 2, 2: 3, 3: 4}[int(want["type"][0, i])])
+            assert list(st.action_mask) == list(m.get_legal_action_mask(0, j.player_id))
+            assert [p.tile_count for p in st.players] == [int(want["owned"][0, p].sum()) for p in range(2)]
+
+
+def test_experience_stream_records(server, oracle_lib):
+    _experience_stream_records(server, oracle_lib)
+
+
+def _experience_stream_records(server, oracle_lib):
+    gs, stub, xstub, _, _ = server
+    gid, js = _start(stub, 6, 6, collect=True)
+    m = new_engine(oracle_lib, 6, 6, 2, 1)
+    m.reset_seeded([1000 + int(gid.split("-")[1])])
+    rng = np.random.default_rng(3)
+    expected = []
+    for turn in range(12):
+        prev = m.alloc_outputs_host()
+        m.observe(m.outputs(obs=prev["obs"]))
+        prev_mask = m.mask(_abi.MASK_SERIALIZER_UDLR)
+        acts = np.zeros((1, m.A), _abi.ACTION_DTYPE)
+        for j in js:
+            st = stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)).state
+            a = _legal_action(st, rng, st.turn)
+            req = game.SubmitActionRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)
+            if a is not None and not (turn == 4 and j.player_id == 1):  # player 1 passes on turn 4: no record for it
+                req.action.CopyFrom(a)
+                f = getattr(a, "from")
+                s = acts[0, j.player_id]
+                s["player_id"], s["from_x"], s["from_y"], s["to_x"], s["to_y"] = j.player_id, f.x, f.y, a.to.x, a.to.y
+                s["move_all"], s["present"] = (0 if a.half else 1), 1
+            assert stub.SubmitAction(req).success
+        out = m.alloc_outputs_host()
+        m.step_fused(acts, m.outputs(**out))
+        for p in range(2):
+            if out["action_index"][0, p] >= 0:
+                expected.append((p, int(out["action_index"][0, p]), out["reward"][0, p], prev["obs"][0, p].copy(),
+                                 out["obs"][0, p].copy(), prev_mask[0, p].astype(bool), int(m.get_state()["turn"][0])))
+    got = []
+    for b in xstub.StreamExperienceBatches(experience.StreamExperiencesRequest(game_ids=[gid], batch_size=5, follow=False)):
+        assert len(b.experiences) <= 5
+        got.extend(b.experiences)
+    assert len(got) == len(expected) == 23
+    for x, (p, a, r, s0, s1, mk, turn) in zip(got, expected):
+        assert (x.game_id, x.player_id, x.action, x.turn, x.done) == (gid, p, a, turn, False)
+        assert np.float32(x.reward).view(np.uint32) == np.float32(r).view(np.uint32)
+        assert list(x.state.shape) == [9, 6, 6]
+        assert np.array_equal(np.array(x.state.data, np.float32).view(np.uint32), s0.reshape(-1).view(np.uint32))
+        assert np.array_equal(np.array(x.next_state.data, np.float32).view(np.uint32), s1.reshape(-1).view(np.uint32))
+        assert list(x.action_mask) == list(mk)
+    singles = list(xstub.StreamExperiences(experience.StreamExperiencesRequest(player_ids=[1], min_turn=3, follow=False)))
+    assert singles and all(x.player_id == 1 and x.turn >= 3 for x in singles)
+    stats = xstub.GetExperienceStats(experience.GetExperienceStatsRequest())
+    assert stats.total_experiences == 23 and stats.total_games == 1 and stats.experiences_per_player[0] == 12
+    dup = xstub.SubmitExperiences(experience.SubmitExperiencesRequest(experiences=got[:3] + got[:1]))
+    assert (dup.accepted, dup.rejected) == (3, 1)
+
+
+def test_stream_game_updates(server):
+    gs, stub, _, ch, _ = server
+    gid, js = _start(stub, 8, 8)
+    it = stub.StreamGame(game.StreamGameRequest(game_id=gid, player_id=0, player_token=js[0].player_token))
+    first = next(it)
+    assert first.WhichOneof("update") == "full_state" and first.full_state.turn == 0
+    rng = np.random.default_rng(1)
+    for j in js:
+        st = stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)).state
+        req = game.SubmitActionRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)
+        req.action.CopyFrom(_legal_action(st, rng, 0))
+        assert stub.SubmitAction(req).success
+    upd = next(it)
+    # a 2-move turn touches fewer than N/5 tiles: the server sends a delta (server.go:638-777)
+    assert upd.WhichOneof("update") == "delta" and upd.delta.turn == 1
+    assert 0 < len(upd.delta.tile_updates) < 64 // 5 and len(upd.delta.player_updates) == 2
+    it.cancel()
+
+
+def test_validate_move_precedence():
+    W = H = 3
+    owner = [0, -1, -1, -1, -1, -1, -1, -1, 1]
+    army = [5, 0, 0, 0, 0, 0, 0, 0, 1]
+    typ = [1, 3, 0, 0, 0, 0, 0, 0, 1]
+    v = lambda *a: validate_move(owner, army, typ, W, H, *a)
+    assert v(0, -1, 0, 0, 0) == _abi.STEP_INVALID_COORDINATES and v(0, 0, 0, 3, 0) == _abi.STEP_INVALID_COORDINATES
+    assert v(0, 0, 0, 0, 0) == _abi.STEP_MOVE_TO_SELF and v(0, 0, 0, 1, 1) == _abi.STEP_NOT_ADJACENT
+    assert v(1, 0, 0, 0, 1) == _abi.STEP_NOT_OWNED and v(1, 2, 2, 2, 1) == _abi.STEP_INSUFFICIENT_ARMY
+    assert v(0, 0, 0, 1, 0) == _abi.STEP_TARGET_IS_MOUNTAIN and v(0, 0, 0, 0, 1) == 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/python/generals_pb"), reason="reference stubs not on this box")
+def test_reference_generated_stubs_talk_to_this_server(server):
+    """The reference's own protoc output (python/generals_pb) as the client: wire compatibility."""
+    gs, _, _, _, port = server
+    sys.path.insert(0, "/root/reference/python")
+    try:
+        from generals_pb.common.v1 import common_pb2
+        from generals_pb.game.v1 import game_pb2, game_pb2_grpc
+    finally:
+        sys.path.pop(0)
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    stub = game_pb2_grpc.GameServiceStub(ch)
+    gid = stub.CreateGame(game_pb2.CreateGameRequest(config=game_pb2.GameConfig(width=7, height=5, max_players=2, fog_of_war=True))).game_id
+    j = [stub.JoinGame(game_pb2.JoinGameRequest(game_id=gid, player_name=n)) for n in ("p0", "p1")]
+    st = stub.GetGameState(game_pb2.GetGameStateRequest(game_id=gid, player_id=0, player_token=j[0].player_token)).state
+    assert st.status == common_pb2.GAME_STATUS_IN_PROGRESS and st.current_phase == common_pb2.GAME_PHASE_RUNNING
+    assert (st.board.width, st.board.height, len(st.board.tiles), len(st.action_mask)) == (7, 5, 35, 140)
+    gens = [t for t in st.board.tiles if t.type == common_pb2.TILE_TYPE_GENERAL and t.visible]
+    assert len(gens) == 1 and gens[0].owner_id == 0 and gens[0].army_count == 2  # engine_initializer: general army 2... 
+    k = list(st.action_mask).index(True)
+    t, d = k // 4, k % 4
+    a = game_pb2.Action(type=common_pb2.ACTION_TYPE_MOVE, turn_number=0, half=False)
+    getattr(a, "from").x, getattr(a, "from").y = t % 7, t // 7
+    a.to.x, a.to.y = t % 7 + DIRS[d][0], t // 7 + DIRS[d][1]
+    target = a.to.y * 7 + a.to.x
+    before = (st.board.tiles[target].owner_id, st.board.tiles[target].army_count)
+    assert stub.SubmitAction(game_pb2.SubmitActionRequest(game_id=gid, player_id=0, player_token=j[0].player_token, action=a)).success
+    assert stub.SubmitAction(game_pb2.SubmitActionRequest(game_id=gid, player_id=1, player_token=j[1].player_token)).success
+    st = stub.GetGameState(game_pb2.GetGameStateRequest(game_id=gid, player_id=0, player_token=j[0].player_token)).state
+    after = (st.board.tiles[target].owner_id, st.board.tiles[target].army_count)
+    # one army moved: an empty tile is captured with 1, a defended one (a 40-army city) loses 1
+    assert st.turn == 1 and after == ((0, 1) if before[1] == 0 else (before[0], before[1] - 1))
+    ch.close()
