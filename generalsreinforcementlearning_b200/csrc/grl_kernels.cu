@@ -56,6 +56,11 @@
 #endif
 constexpr int kObsUnroll = GRL_OBS_UNROLL;
 
+// per-warp shared-memory words of the linear observation writer (only baked boards with N % 4 != 0)
+__host__ __device__ constexpr int grl_obs_scratch_words(int TW, int TH, int PT, int NW) {
+  return (TW > 0 && ((TW * TH) & 3) != 0) ? ((PT * GRL_OBS_CHANNELS * (NW + 1) + TW * TH + 4 + 3) & ~3) : 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------
@@ -486,6 +491,90 @@ __device__ __forceinline__ void obs_plane_major(const GrlKParams &prm, const Sla
   }
 }
 
+// Observation planes for baked geometries with N % 4 != 0 (15x15): the game's [P][9][N] block is
+// still ONE linear, 16-byte aligned sweep of 128-bit stores — channel planes start at odd float
+// offsets there, so a float4 is addressed by its position e in the BLOCK, not in a plane:
+// plane = e / N, tile = e % N.  The nine channel bitmasks of every player are staged in shared
+// memory (one pad word each, so a 4-bit window may straddle the last word), armies are converted
+// once into a float plane, and each store costs two LDS for the window, one table lookup and — on
+// the two army planes — four scalar LDS.  The <= 3 floats before/after the aligned body and the
+// float4s that straddle two planes (P*9-1 of them) take a per-element path.
+template <int N>
+__device__ __forceinline__ float obs_element(const uint32_t *chm, const float *frac, int NWP, int e) {
+  const int plane = e / N, t = e - plane * N;
+  const uint32_t bit = (chm[plane * NWP + (t >> 5)] >> (t & 31)) & 1u;
+  return bit ? ((plane % GRL_OBS_CHANNELS) < 2 ? frac[t] : 1.f) : 0.f;
+}
+
+template <int PT, int N>
+__device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView &S, const float4 *lut, uint32_t *scratch,
+                                           const uint32_t (&own)[PT], const uint32_t (&vis)[PT], uint32_t M, uint32_t CG,
+                                           uint32_t valid, int P, int NW, int game, int lane) {
+  const int NWP = NW + 1;
+  uint32_t *chm = scratch;                                                   // [P*9][NWP]
+  float *frac = reinterpret_cast<float *>(scratch + PT * GRL_OBS_CHANNELS * NWP);  // [N + 4]
+  uint32_t any_own = 0;
+#pragma unroll
+  for (int p = 0; p < PT; p++) any_own |= own[p];
+  if (lane < NWP) {
+    const bool w = lane < NW;
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      if (p < P) {
+        const uint32_t v = w ? (prm.fog ? vis[p] : valid) : 0u;
+        const uint32_t nm = v & ~M;
+        uint32_t *c = chm + p * GRL_OBS_CHANNELS * NWP + lane;
+        const uint32_t mine = w ? (nm & own[p]) : 0u, enemy = w ? (nm & any_own & ~own[p]) : 0u;
+        c[0 * NWP] = mine;
+        c[1 * NWP] = enemy;
+        c[2 * NWP] = mine;
+        c[3 * NWP] = enemy;
+        c[4 * NWP] = w ? (nm & ~any_own) : 0u;
+        c[5 * NWP] = w ? (nm & CG) : 0u;
+        c[6 * NWP] = w ? (v & M) : 0u;
+        c[7 * NWP] = v;
+        c[8 * NWP] = w ? (~v & valid) : 0u;
+      }
+    }
+  }
+  for (int t = lane; t < N + 4; t += 32) frac[t] = t < N ? army_frac((uint32_t)S.army[t]) : 0.f;
+  __syncwarp();
+
+  const int total = P * GRL_OBS_CHANNELS * N;  // floats in this game's block
+  float *base = prm.obs + (size_t)game * total;
+  const int head = (int)((4u - (uint32_t)(((size_t)game * total) & 3u)) & 3u);  // floats before the 16-byte aligned body
+  const int body4 = (total - head) / 4;
+  const int tail0 = head + 4 * body4;
+  if (lane < head) __stcs(base + lane, obs_element<N>(chm, frac, NWP, lane));
+  if (lane < total - tail0) __stcs(base + tail0 + lane, obs_element<N>(chm, frac, NWP, tail0 + lane));
+  const char *lutb = reinterpret_cast<const char *>(lut);
+  float4 *body = reinterpret_cast<float4 *>(base + head);
+#pragma unroll 2
+  for (int i = lane; i < body4; i += 32) {
+    const int e = head + 4 * i;
+    const int plane = e / N, t = e - plane * N;
+    float4 val;
+    if (t + 3 < N) {
+      const uint32_t *wp = chm + plane * NWP + (t >> 5);
+      const uint32_t nib = __funnelshift_r(wp[0], wp[1], t & 31) & 0xfu;
+      val = *reinterpret_cast<const float4 *>(lutb + nib * 16u);
+      if ((plane % GRL_OBS_CHANNELS) < 2 && nib) {
+        val.x *= frac[t];
+        val.y *= frac[t + 1];
+        val.z *= frac[t + 2];
+        val.w *= frac[t + 3];
+      }
+    } else {  // straddles two planes
+      val.x = obs_element<N>(chm, frac, NWP, e);
+      val.y = obs_element<N>(chm, frac, NWP, e + 1);
+      val.z = obs_element<N>(chm, frac, NWP, e + 2);
+      val.w = obs_element<N>(chm, frac, NWP, e + 3);
+    }
+    __stcs(body + i, val);
+  }
+  __syncwarp();
+}
+
 template <int PT, int TW, int TH, bool DO_STEP, bool DO_OUT>
 __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMinBlocks)
     grl_turn_kernel(const __grid_constant__ GrlKParams prm) {
@@ -507,8 +596,12 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
   const int act_words = 2 * GRL_MAX_ACTIONS;
   const int buf_words = L.slab_words + L.static_words;
   const int per_warp = 2 * buf_words + act_words;  // two slab buffers: the next game's slab is prefetched
-  uint32_t *wbase = smem + warp * per_warp;
+  // baked geometries with N % 4 != 0 stage channel masks + an army-fraction plane per warp (obs_linear)
+  const int obs_scratch = grl_obs_scratch_words(TW, TH, PT, NW);
+  const int per_warp_all = per_warp + obs_scratch;
+  uint32_t *wbase = smem + warp * per_warp_all;
   uint32_t *s_act = wbase + 2 * buf_words;
+  uint32_t *s_obs = s_act + act_words;
 
   Geo g;
   g.lane = lane;
@@ -1013,6 +1106,8 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
         float *gbase = prm.obs + (size_t)game * P * GRL_OBS_CHANNELS * N;
         if (TW > 0 && ((TW * TH) & 3) == 0 && !GRL_OBS_CHUNK_MAJOR) {
           obs_plane_major<PT, (TW > 0 ? TW * TH : 4)>(prm, S, s_lut, P, NW, game, lane);
+        } else if (TW > 0 && ((TW * TH) & 3) != 0 && !GRL_OBS_CHUNK_MAJOR) {
+          obs_linear<PT, (TW > 0 ? TW * TH : 5)>(prm, S, s_lut, s_obs, own, vis, M, CG, g.valid, P, NW, game, lane);
         } else if ((N & 3) == 0) {
           // 128-bit path: a lane writes 4 consecutive tiles of each channel plane; the army
           // conversion and the terrain nibbles are shared by all players' views
@@ -1509,8 +1604,9 @@ static inline int grid_for(int items_per_cta_warps, int n) {
   return ctas < 1 ? 1 : ctas;
 }
 
-size_t grl_turn_smem_bytes(const GrlLayout &L) {
-  return (size_t)GRL_WARPS_PER_CTA * (size_t)(2 * (L.slab_words + L.static_words) + 2 * GRL_MAX_ACTIONS) * 4u;
+size_t grl_turn_smem_bytes(const GrlLayout &L, int TW, int TH, int PT) {
+  return (size_t)GRL_WARPS_PER_CTA *
+         (size_t)(2 * (L.slab_words + L.static_words) + 2 * GRL_MAX_ACTIONS + grl_obs_scratch_words(TW, TH, PT, L.NW)) * 4u;
 }
 
 // persistent launch: as many CTAs as stay resident (occupancy x SM count), each warp loops over games
@@ -1533,7 +1629,7 @@ static int persistent_grid(K kern, size_t smem, int B) {
 
 template <int PT, int TW, int TH, bool S, bool O>
 static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream) {
-  size_t smem = grl_turn_smem_bytes(prm.L);
+  size_t smem = grl_turn_smem_bytes(prm.L, TW, TH, PT);
   auto kern = grl_turn_kernel<PT, TW, TH, S, O>;
   static size_t tuned_smem = ~(size_t)0;  // per instantiation: attribute + resident-CTA count
   static int resident = 0;

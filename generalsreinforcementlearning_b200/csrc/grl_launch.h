@@ -4,7 +4,6 @@
 
 #include "grl_layout.h"
 
-size_t grl_turn_smem_bytes(const GrlLayout &L);
 cudaError_t grl_launch_turn(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream);
 cudaError_t grl_launch_reset(const GrlKParams &prm, const uint32_t *src_state, const uint32_t *src_static,
                              const int32_t *env_ids, int n, cudaStream_t stream);
