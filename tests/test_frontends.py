@@ -307,3 +307,44 @@ def test_vector_env_on_device(cuda_lib):
     assert torch.equal(o2, GeneralsVecEnv.reset(env, seed=21)[0])
     env.close()
     env2.close()
+
+
+def test_go_rand_and_demo_policy(oracle_lib):
+    """GoRand (python) == the oracle's C generator == the canonical Go outputs; the demo policy
+    of demo_helpers.go:12-62 only ever proposes moves the engine accepts."""
+    import ctypes as C
+
+    from generalsreinforcementlearning_b200.demo_policy import GoRand, demo_actions_for
+    from helpers import ctypes_fn
+
+    r = GoRand(1)
+    assert [r.int63() for _ in range(3)] == [5577006791947779410, 8674665223082153551, 6129484611666145821]
+    r = GoRand(1)
+    assert [r.intn(100) for _ in range(10)] == [81, 87, 47, 59, 81, 18, 25, 40, 56, 0]
+    fn = ctypes_fn(oracle_lib, "test_gorand", C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p])
+    for seed in (12345, 42, -7, 0, (1 << 31) + 5):
+        out = np.zeros(50, np.int64)
+        assert fn(seed, 0, 0, 50, out.ctypes.data) == 0
+        r = GoRand(seed)
+        assert [r.int63() for _ in range(50)] == out.tolist(), seed
+        assert fn(seed, 1, 37, 50, out.ctypes.data) == 0
+        r = GoRand(seed)
+        assert [r.intn(37) for _ in range(50)] == out.tolist(), seed
+    r = GoRand(1)  # rand.New(rand.NewSource(1)).Float64() / Float32(): the well-known first values
+    assert abs(r.float64() - 0.6046602879796196) < 1e-16
+    r = GoRand(1)
+    assert abs(r.float32() - 0.6046603) < 1e-7
+    e = new_engine(oracle_lib, 10, 10, 2, 1)
+    e.reset_seeded([12345])
+    rng = GoRand(99)
+    played = 0
+    for _ in range(200):
+        acts = demo_actions_for(e, 0, rng)
+        played += int(acts["present"].sum())
+        before = e.get_state()["turn"][0]
+        e.step(acts)
+        st = e.get_state()
+        assert st["turn"][0] == before + 1
+        # a move legal at submission can only be invalidated by the OTHER player's move of the same turn
+        assert st["step_error"][0] in (0, _abi.STEP_NOT_OWNED, _abi.STEP_INSUFFICIENT_ARMY)
+    assert 60 < played < 200, "each player moves with probability 0.3 per turn"
