@@ -60,6 +60,7 @@ struct grl_env {
   Scratch scratch[SL_COUNT];
   int use_tma = 1;
   int prefetch_dist = 0;       // > 0: warp of game g prefetches the slab of game g+dist into L2
+  int lanes_per_game = 0;      // 32: one game per warp even on small boards (GRL_LANES_PER_GAME)
   size_t l2_window_bytes = 0;  // > 0: launch the turn kernel with a persisting-L2 window over the state
   float l2_hit_ratio = 1.0f;
   uint64_t launches = 0;
@@ -124,6 +125,7 @@ GrlKParams base_params(const grl_env *env) {
   p.env_id_base = c.env_id_base;
   p.use_tma = env->use_tma;
   p.prefetch_dist = env->prefetch_dist;
+  p.lanes_per_game = env->lanes_per_game;
   p.l2_window_bytes = env->l2_window_bytes;
   p.l2_hit_ratio = env->l2_hit_ratio;
   const grl_reward_config &r = c.reward;
@@ -540,6 +542,8 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   env->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (hw > 0 ? hw : 1);
   const char *no_tma = getenv("GRL_NO_TMA");
   env->use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
+  const char *lpg = getenv("GRL_LANES_PER_GAME");
+  env->lanes_per_game = lpg ? atoi(lpg) : 0;
   const char *pc = getenv("GRL_PIPE_CHUNKS");
   if (pc && atoi(pc) >= 1) env->pipe_chunks = atoi(pc);
   const char *pf = getenv("GRL_PREFETCH_DIST");

@@ -1,6 +1,8 @@
 // grl_kernels.cu — sm_100a kernels of the batched Generals.io turn engine.
 //
-// One warp owns one game.  Every boolean plane of a game (ownership per player, the
+// A GROUP of LG lanes owns one game (LG = 32, 16, 8 or 4: the smallest power of two >= the NW
+// words a board's bit planes span), so a warp steps 32/LG games at once and small boards do not
+// leave most lanes idle.  Every boolean plane of a game (ownership per player, the
 // reference's cached OwnedTiles lists, visibility per player, the changed / visibility-
 // changed tile sets, terrain) is an N-bit LINEAR bitmask, N = W*H <= 1024, held as one
 // 32-bit word per lane.  Stencils (3x3 fog dilation, the 5x5 "affected players" probe,
@@ -48,13 +50,14 @@
 #ifndef GRL_DIRTY_WB
 #define GRL_DIRTY_WB (!GRL_PERSISTENT)
 #endif
+// GRL_PACKED_SNAPSHOT (default 0): packed groups (LG < 32) skip the snapshot and write the whole slab back,
+// which frees shared memory for a fourth CTA per SM (15x15 x 262,144 games: 0.974 -> 0.877 ms).
+#ifndef GRL_PACKED_SNAPSHOT
+#define GRL_PACKED_SNAPSHOT 0
+#endif
 #ifndef GRL_OBS_CHUNK_MAJOR
 #define GRL_OBS_CHUNK_MAJOR 0  // 1: the round-1a tile-chunk-major observation loop (comparison builds)
 #endif
-#ifndef GRL_OBS_UNROLL
-#define GRL_OBS_UNROLL 1
-#endif
-constexpr int kObsUnroll = GRL_OBS_UNROLL;
 
 // per-warp shared-memory words of the linear observation writer (only baked boards with N % 4 != 0)
 __host__ __device__ constexpr int grl_obs_scratch_words(int TW, int TH, int PT, int NW) {
@@ -93,34 +96,54 @@ __device__ __forceinline__ float army_frac(uint32_t army) {
   return army >= 1000u ? 1.0f : v;  // serializer.go:84-88 clip
 }
 
-// Per-lane geometry words and linear-bitmask stencils.
+// Per-lane geometry words and linear-bitmask stencils.  `lane` is the lane's index INSIDE its
+// group; all cross-lane traffic is segmented (width LG) and synchronises on the group's member mask.
 struct Geo {
   uint32_t valid, nc0, ncl;  // tiles that exist / x != 0 / x != W-1, word `lane`
   int W;
-  int lane;
+  int lane;      // 0..LG-1
+  int shift;     // first warp lane of the group
+  uint32_t seg;  // member mask of the group
 };
 
-__device__ __forceinline__ uint32_t word_prev(uint32_t v, int lane) {
-  uint32_t p = __shfl_up_sync(FULL, v, 1);
-  return lane == 0 ? 0u : p;
+template <int LG>
+__device__ __forceinline__ uint32_t word_prev(uint32_t v, const Geo &g) {
+  uint32_t p = __shfl_up_sync(g.seg, v, 1, LG);
+  return g.lane == 0 ? 0u : p;
 }
-__device__ __forceinline__ uint32_t word_next(uint32_t v, int lane) {
-  uint32_t n = __shfl_down_sync(FULL, v, 1);
-  return lane == 31 ? 0u : n;
+template <int LG>
+__device__ __forceinline__ uint32_t word_next(uint32_t v, const Geo &g) {
+  uint32_t n = __shfl_down_sync(g.seg, v, 1, LG);
+  return g.lane == LG - 1 ? 0u : n;
 }
 // bit t of result = bit (t-k) of v
-__device__ __forceinline__ uint32_t shl_bits(uint32_t v, int k, int lane) {
-  return __funnelshift_lc(word_prev(v, lane), v, k);
+template <int LG>
+__device__ __forceinline__ uint32_t shl_bits(uint32_t v, int k, const Geo &g) {
+  return __funnelshift_lc(word_prev<LG>(v, g), v, k);
 }
 // bit t of result = bit (t+k) of v
-__device__ __forceinline__ uint32_t shr_bits(uint32_t v, int k, int lane) {
-  return __funnelshift_rc(v, word_next(v, lane), k);
+template <int LG>
+__device__ __forceinline__ uint32_t shr_bits(uint32_t v, int k, const Geo &g) {
+  return __funnelshift_rc(v, word_next<LG>(v, g), k);
 }
 // in-bounds 3x3 neighbourhood union (visibility_optimized.go:9-13,118-128)
+template <int LG>
 __device__ __forceinline__ uint32_t dilate3(uint32_t v, const Geo &g) {
-  uint32_t h = v | (shl_bits(v, 1, g.lane) & g.nc0) | (shr_bits(v, 1, g.lane) & g.ncl);
-  uint32_t r = h | shl_bits(h, g.W, g.lane) | shr_bits(h, g.W, g.lane);
+  uint32_t h = v | (shl_bits<LG>(v, 1, g) & g.nc0) | (shr_bits<LG>(v, 1, g) & g.ncl);
+  uint32_t r = h | shl_bits<LG>(h, g.W, g) | shr_bits<LG>(h, g.W, g);
   return r & g.valid;
+}
+
+__device__ __forceinline__ Geo make_geo(const GrlKParams &prm, int W, int lane, int LG) {
+  Geo g;
+  g.lane = lane % LG;
+  g.shift = lane - g.lane;
+  g.seg = LG == 32 ? FULL : (((1u << (LG & 31)) - 1u) << g.shift);
+  g.W = W;
+  g.valid = prm.geom[g.lane];
+  g.nc0 = prm.geom[32 + g.lane];
+  g.ncl = prm.geom[64 + g.lane];
+  return g;
 }
 
 // bits 0..7 of b spread to bit positions 0,4,8,...,28
@@ -155,16 +178,20 @@ __device__ __forceinline__ SlabView make_view(uint32_t *s, const uint32_t *st, c
 }
 
 // sum of army over the tiles of a linear bitmask (word `lane` in x); slow path helper
-__device__ __forceinline__ int sum_army_over(uint32_t x, const uint16_t *army, int NW, int N, int lane) {
+template <int LG>
+__device__ __forceinline__ int sum_army_over(uint32_t x, const uint16_t *army, int NW, int N, const Geo &g) {
   int acc = 0;
 #pragma unroll 1
   for (int i = 0; i < NW; i++) {
-    uint32_t xw = __shfl_sync(FULL, x, i);
-    int t = 32 * i + lane;
-    int a = (t < N) ? (int)army[t] : 0;
-    acc += ((xw >> lane) & 1u) ? a : 0;
+    uint32_t xw = __shfl_sync(g.seg, x, i, LG);
+#pragma unroll
+    for (int b = g.lane; b < 32; b += LG) {
+      int t = 32 * i + b;
+      int a = (t < N) ? (int)army[t] : 0;
+      acc += ((xw >> b) & 1u) ? a : 0;
+    }
   }
-  return __reduce_add_sync(FULL, acc);
+  return __reduce_add_sync(g.seg, acc);
 }
 
 // TMA bulk copies (cp.async.bulk, SASS UBLKCP) for the state slabs -------------------------
@@ -213,11 +240,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // cached-list statistics (internal/game/stats.go:8-144) on register words.
 // armyCount[p] = trueArmy[p] - (armies on tiles p owns that are missing from its list).
 // ---------------------------------------------------------------------------------------
-template <int PT>
+template <int PT, int LG>
 __device__ __forceinline__ void stats_update(const GrlKParams &prm, SlabView &S, const uint32_t (&own)[PT],
-                                             uint32_t (&lst)[PT], uint32_t chg, uint32_t G, uint32_t &alive, int lane,
+                                             uint32_t (&lst)[PT], uint32_t chg, uint32_t G, uint32_t &alive, const Geo &g,
                                              int N, int NW) {
-  int c = __reduce_add_sync(FULL, __popc(chg));
+  int c = __reduce_add_sync(g.seg, __popc(chg));
   if (c == 0) return;               // stats.go:11-15 (turn > 0 inside a step)
   const bool full = c > N / 5;      // stats.go:20-25
 #pragma unroll
@@ -227,18 +254,18 @@ __device__ __forceinline__ void stats_update(const GrlKParams &prm, SlabView &S,
       uint32_t orphan = own[p] & ~lst[p];
       int true_army = (int)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY];
       int corr = 0;
-      if (__any_sync(FULL, orphan != 0u)) corr = sum_army_over(orphan, S.army, NW, N, lane);
+      if (__any_sync(g.seg, orphan != 0u)) corr = sum_army_over<LG>(orphan, S.army, NW, N, g);
       uint32_t gen = lst[p] & G;
-      int gi = gen ? (32 * lane + 31 - __clz(gen)) : -1;
-      gi = __reduce_max_sync(FULL, gi);
-      if (lane == 0) {
+      int gi = gen ? (32 * g.lane + 31 - __clz(gen)) : -1;
+      gi = __reduce_max_sync(g.seg, gi);
+      if (g.lane == 0) {
         S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ARMY_COUNT] = (uint32_t)(true_army - corr);
         S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_GENERAL_IDX] = (uint32_t)gi;
       }
       alive = gi >= 0 ? (alive | (1u << p)) : (alive & ~(1u << p));
     }
   }
-  __syncwarp();
+  __syncwarp(g.seg);
 }
 
 // engine legal-move direction masks for one player (rules/legal_moves.go:19-73):
@@ -246,24 +273,29 @@ __device__ __forceinline__ void stats_update(const GrlKParams &prm, SlabView &S,
 struct DirMasks {
   uint32_t up, right, down, left;
 };
+template <int LG>
 __device__ __forceinline__ DirMasks dir_targets(uint32_t M, const Geo &g) {
   uint32_t free_ = g.valid & ~M;
   DirMasks d;
-  d.up = shl_bits(free_, g.W, g.lane);            // tile t-W exists and is not a mountain
-  d.down = shr_bits(free_, g.W, g.lane);          // tile t+W
-  d.left = shl_bits(free_, 1, g.lane) & g.nc0;    // tile t-1, x != 0
-  d.right = shr_bits(free_, 1, g.lane) & g.ncl;   // tile t+1, x != W-1
+  d.up = shl_bits<LG>(free_, g.W, g);            // tile t-W exists and is not a mountain
+  d.down = shr_bits<LG>(free_, g.W, g);          // tile t+W
+  d.left = shl_bits<LG>(free_, 1, g) & g.nc0;    // tile t-1, x != 0
+  d.right = shr_bits<LG>(free_, 1, g) & g.ncl;   // tile t+1, x != W-1
   return d;
 }
 
-// army > 1 per tile as a linear bitmask (word `lane`)
-__device__ __forceinline__ uint32_t army_gt1_mask(const uint16_t *army, int NW, int N, int lane) {
+// army > 1 per tile as a linear bitmask (word `lane`): the group's lanes test LG tiles per ballot
+template <int LG>
+__device__ __forceinline__ uint32_t army_gt1_mask(const uint16_t *army, int NW, int N, const Geo &g) {
   uint32_t mine = 0;
   for (int i = 0; i < NW; i++) {
-    int t = 32 * i + lane;
-    bool gt = (t < N) && army[t] > 1;
-    uint32_t w = __ballot_sync(FULL, gt);
-    if (lane == i) mine = w;
+#pragma unroll
+    for (int r = 0; r < 32 / LG; r++) {
+      int t = 32 * i + r * LG + g.lane;
+      bool gt = (t < N) && army[t] > 1;
+      uint32_t w = __ballot_sync(g.seg, gt) >> g.shift;  // LG bits
+      if (g.lane == i) mine |= w << (r * LG);
+    }
   }
   return mine;
 }
@@ -289,20 +321,21 @@ __device__ __forceinline__ PackedAction pack_action(int player, int fx, int fy, 
 
 // Synthetic policy: player p draws uniformly from the set bits of its engine mask
 // in flat-index order (tile-major, dirs U,R,D,L).  Warp-uniform result.
+template <int LG>
 __device__ __forceinline__ PackedAction sample_policy_action(const GrlKParams &prm, const DirMasks &dm, uint32_t src,
                                                              int p, uint64_t env_global, uint32_t turn, const Geo &g) {
   PackedAction none;
   none.lo = none.hi = 0;
   uint32_t U = src & dm.up, R = src & dm.right, D = src & dm.down, Lm = src & dm.left;
   int cnt = __popc(U) + __popc(R) + __popc(D) + __popc(Lm);
-  int total = __reduce_add_sync(FULL, cnt);
+  int total = __reduce_add_sync(g.seg, cnt);
   if (total == 0) return none;
   uint64_t r = policy_draw(prm.policy_seed, env_global, (uint64_t)turn, (uint64_t)p);
   int k = (int)((uint32_t)r % (uint32_t)total);
-  int incl = cnt;  // inclusive prefix sum over lanes
+  int incl = cnt;  // inclusive prefix sum over the group's lanes
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(FULL, incl, o);
+  for (int o = 1; o < LG; o <<= 1) {
+    int v = __shfl_up_sync(g.seg, incl, o, LG);
     if (g.lane >= o) incl += v;
   }
   int excl = incl - cnt;
@@ -329,8 +362,8 @@ __device__ __forceinline__ PackedAction sample_policy_action(const GrlKParams &p
     }
   }
   int packed = mine ? ((32 * g.lane + b) * 4 + dir) : 0;
-  uint32_t who = __ballot_sync(FULL, mine);
-  packed = __shfl_sync(FULL, packed, __ffs(who) - 1);
+  uint32_t who = __ballot_sync(g.seg, mine) >> g.shift;
+  packed = __shfl_sync(g.seg, packed, __ffs(who) - 1, LG);
   int tile = packed >> 2;
   dir = packed & 3;
   int fx = tile % prm.W, fy = tile / prm.W;
@@ -349,16 +382,15 @@ __device__ __forceinline__ PackedAction sample_policy_action(const GrlKParams &p
 // shared-memory slab, so the common path of the turn kernel stays small in the instruction cache.
 
 // Synthetic policy for all players from the pre-turn state; writes decoded moves into s_act.
-template <int PT>
+template <int PT, int LG>
 __device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t *s_act,
-                                          uint32_t alive, uint32_t turn_before, int game, int lane, int W, int H, int N,
-                                          int NW);
+                                          uint32_t alive, uint32_t turn_before, int game, Geo g, int W, int H, int N, int NW);
 
 // Elimination orders: tile turnover over the eliminated player's cached list, then the stats
 // rebuild of engine.go:101-109.  Reads and writes own/list/changed/vchg words in the slab.
-template <int PT>
+template <int PT, int LG>
 __device__ __noinline__ uint32_t elimination_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t alive,
-                                                   int n_orders, uint32_t ord_lo, uint32_t ord_hi, int lane, int N, int NW);
+                                                   int n_orders, uint32_t ord_lo, uint32_t ord_hi, Geo g, int N, int NW);
 
 // One decoded move, staged in shared memory as two words.  The checks that depend only on the
 // action itself (core/action.go:58-79) run on one lane per slot, in parallel; the checks that
@@ -390,12 +422,13 @@ __device__ __forceinline__ uint2 decode_action(uint2 raw, int W, int H, int P) {
   return make_uint2(w, (uint32_t)aidx);
 }
 
-template <int PT>
+template <int PT, int LG>
 struct TurnOccupancy {  // CTAs of 256 threads per SM the register budget is tuned for
 #ifdef GRL_MIN_BLOCKS
   static constexpr int kMinBlocks = GRL_MIN_BLOCKS;
 #else
-  static constexpr int kMinBlocks = (PT <= 2 ? 4 : (PT <= 4 ? 3 : 2)) * 8 / GRL_WARPS_PER_CTA;
+  // packed groups (LG < 32) carry 32/LG slabs per warp in shared memory: 3 CTAs fit
+  static constexpr int kMinBlocks = (LG < 32 && GRL_PACKED_SNAPSHOT) ? 3 : (PT <= 2 ? 4 : (PT <= 4 ? 3 : 2)) * 8 / GRL_WARPS_PER_CTA;
 #endif
 };
 
@@ -508,32 +541,36 @@ __device__ __forceinline__ float obs_element(const uint32_t *chm, const float *f
 
 template <int PT, int N>
 __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView &S, const float4 *lut, uint32_t *scratch,
-                                           const uint32_t (&own)[PT], const uint32_t (&vis)[PT], uint32_t M, uint32_t CG,
-                                           uint32_t valid, int P, int NW, int game, int lane) {
+                                           int P, int NW, int game, int lane) {
   const int NWP = NW + 1;
   uint32_t *chm = scratch;                                                   // [P*9][NWP]
   float *frac = reinterpret_cast<float *>(scratch + PT * GRL_OBS_CHANNELS * NWP);  // [N + 4]
-  uint32_t any_own = 0;
-#pragma unroll
-  for (int p = 0; p < PT; p++) any_own |= own[p];
   if (lane < NWP) {
     const bool w = lane < NW;
+    const uint32_t valid = w ? prm.geom[lane] : 0u;
+    const uint32_t M = w ? S.M[lane] : 0u;
+    const uint32_t CG = w ? (S.C[lane] | S.G[lane]) : 0u;
+    uint32_t any_own = 0;
+#pragma unroll
+    for (int p = 0; p < PT; p++)
+      if (p < P && w) any_own |= S.own[p * NW + lane];
 #pragma unroll
     for (int p = 0; p < PT; p++) {
       if (p < P) {
-        const uint32_t v = w ? (prm.fog ? vis[p] : valid) : 0u;
+        const uint32_t own = w ? S.own[p * NW + lane] : 0u;
+        const uint32_t v = w ? (prm.fog ? S.vis[p * NW + lane] : valid) : 0u;
         const uint32_t nm = v & ~M;
         uint32_t *c = chm + p * GRL_OBS_CHANNELS * NWP + lane;
-        const uint32_t mine = w ? (nm & own[p]) : 0u, enemy = w ? (nm & any_own & ~own[p]) : 0u;
+        const uint32_t mine = nm & own, enemy = nm & any_own & ~own;
         c[0 * NWP] = mine;
         c[1 * NWP] = enemy;
         c[2 * NWP] = mine;
         c[3 * NWP] = enemy;
-        c[4 * NWP] = w ? (nm & ~any_own) : 0u;
-        c[5 * NWP] = w ? (nm & CG) : 0u;
-        c[6 * NWP] = w ? (v & M) : 0u;
+        c[4 * NWP] = nm & ~any_own;
+        c[5 * NWP] = nm & CG;
+        c[6 * NWP] = v & M;
         c[7 * NWP] = v;
-        c[8 * NWP] = w ? (~v & valid) : 0u;
+        c[8 * NWP] = ~v & valid;
       }
     }
   }
@@ -575,11 +612,14 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
   __syncwarp();
 }
 
-template <int PT, int TW, int TH, bool DO_STEP, bool DO_OUT>
-__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMinBlocks)
+template <int PT, int TW, int TH, int LG, bool DO_STEP, bool DO_OUT>
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>::kMinBlocks)
     grl_turn_kernel(const __grid_constant__ GrlKParams prm) {
+  constexpr int GPW = 32 / LG;  // games per warp
+  static_assert(LG == 32 || LG == 16 || LG == 8 || LG == 4, "a group is 4, 8, 16 or 32 lanes");
+  static_assert(LG >= PT || LG == 32, "per-player scalars are written by one lane each");
   extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ __align__(8) uint64_t s_bar[2 * GRL_WARPS_PER_CTA];
+  __shared__ __align__(8) uint64_t s_bar[GRL_WARPS_PER_CTA * GPW];
   __shared__ __align__(16) float4 s_lut[16];  // nibble -> four 0/1 floats (observation planes)
   if (DO_OUT && threadIdx.x < 16) {
     const uint32_t n = threadIdx.x;
@@ -594,132 +634,110 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
   const int N = TW ? TW * TH : prm.N;
   const int NW = TW ? (TW * TH + 31) / 32 : prm.NW;
   const int act_words = 2 * GRL_MAX_ACTIONS;
-  const int buf_words = L.slab_words + L.static_words;
-  const int per_warp = 2 * buf_words + act_words;  // two slab buffers: the next game's slab is prefetched
+  // per game: [slab | terrain | pre-turn snapshot of the slab | decoded action slots]
+  constexpr bool kSnap = GRL_DIRTY_WB && (LG == 32 || GRL_PACKED_SNAPSHOT);
+  const int per_game = (kSnap ? 2 : 1) * L.slab_words + L.static_words + act_words;
   // baked geometries with N % 4 != 0 stage channel masks + an army-fraction plane per warp (obs_linear)
   const int obs_scratch = grl_obs_scratch_words(TW, TH, PT, NW);
-  const int per_warp_all = per_warp + obs_scratch;
-  uint32_t *wbase = smem + warp * per_warp_all;
-  uint32_t *s_act = wbase + 2 * buf_words;
-  uint32_t *s_obs = s_act + act_words;
+  uint32_t *wbase = smem + warp * (GPW * per_game + obs_scratch);
+  uint32_t *s_obs = wbase + GPW * per_game;
 
-  Geo g;
-  g.lane = lane;
-  g.W = W;
-  g.valid = prm.geom[lane];
-  g.nc0 = prm.geom[32 + lane];
-  g.ncl = prm.geom[64 + lane];
-  const bool act_lane = lane < NW;
+  const Geo g = make_geo(prm, W, lane, LG);
+  const int l = g.lane;            // lane inside the group
+  const int sub = g.shift / LG;    // group inside the warp
+  uint32_t *s = wbase + sub * per_game;
+  uint32_t *st = s + L.slab_words;
+  uint32_t *snap = st + L.static_words;
+  uint32_t *s_act = snap + (kSnap ? L.slab_words : 0);
+  const bool act_lane = l < NW;
   const uint32_t pmask = (1u << P) - 1u;
   const bool use_policy = DO_STEP && (prm.flags & GRL_STEP_FLAG_RANDOM_POLICY) != 0;
   const bool read_actions = DO_STEP && !use_policy && prm.actions != nullptr;
-  const int stride = gridDim.x * GRL_WARPS_PER_CTA;
-  int game = prm.game0 + blockIdx.x * GRL_WARPS_PER_CTA + warp;
+  const int warp_game0 = prm.game0 + (blockIdx.x * GRL_WARPS_PER_CTA + warp) * GPW;
+  const int game = warp_game0 + sub;
   const int game_end = prm.game_end;
+  const bool gv = game < game_end;  // uniform over the group
 
-  uint64_t *bars = &s_bar[2 * warp];
-  if (prm.use_tma && lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+  uint64_t *bar = &s_bar[warp * GPW + sub];
+  if (prm.use_tma && l == 0) {
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
-  uint32_t phase_bits = 0;  // bit b = parity the next wait on buffer b expects
-  int cur = 0;
-  uint2 next_act = make_uint2(0u, 0u);
-  // prime the pipeline: this warp's first game
-  if (game < game_end) {
-    if (prm.use_tma && lane == 0) {
-      const bool snap = GRL_DIRTY_WB && DO_STEP;
-      mbar_expect_tx(&bars[0], (uint32_t)(buf_words + (snap ? L.slab_words : 0)) * 4u);
-      tma_load(wbase, prm.state + (size_t)game * L.slab_words, (uint32_t)L.slab_words * 4u, &bars[0]);
-      tma_load(wbase + L.slab_words, prm.statics + (size_t)game * L.static_words, (uint32_t)L.static_words * 4u, &bars[0]);
-      if (snap)  // pre-turn snapshot for the dirty-sector write-back (an L2 hit on the same lines)
-        tma_load(wbase + buf_words, prm.state + (size_t)game * L.slab_words, (uint32_t)L.slab_words * 4u, &bars[0]);
-    }
-    if (read_actions && lane < prm.A)
-      next_act = __ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)game * prm.A + lane);
-    // warm L2 for a CTA that will be scheduled a couple of waves from now
-    if (prm.use_tma && prm.prefetch_dist > 0 && lane == 0 && game + prm.prefetch_dist < prm.B) {
-      tma_prefetch_l2(prm.state + (size_t)(game + prm.prefetch_dist) * L.slab_words, (uint32_t)L.slab_words * 4u);
-      tma_prefetch_l2(prm.statics + (size_t)(game + prm.prefetch_dist) * L.static_words, (uint32_t)L.static_words * 4u);
-    }
-  }
+  __syncwarp(g.seg);
 
-  for (; game < game_end; game += stride) {
-#if GRL_PERSISTENT && GRL_CTA_SYNC
-    __syncthreads();  // warps that ran out of games have exited and no longer count
-#endif
-    uint32_t *s = wbase + cur * buf_words;
-    uint32_t *st = s + L.slab_words;
-    SlabView S = make_view(s, st, L);
+  SlabView S = make_view(s, st, L);
+  uint32_t own[PT], lst[PT], vis[PT];
+#pragma unroll
+  for (int p = 0; p < PT; p++) own[p] = lst[p] = vis[p] = 0u;
+  uint32_t M = 0u, alive = 0u, err = 0u;
+  bool over = false;
+
+  if (gv) {
     uint32_t *gslab = prm.state + (size_t)game * L.slab_words;
     const uint32_t *gstat = prm.statics + (size_t)game * L.static_words;
 
     // ---- stage the slab in shared memory ---------------------------------------------
-    // decode this game's action slots (loaded one game ahead) while its slab lands
-    bool skip = false;  // GRL_ACTION_FLAG_SKIP_ENV on slot 0: this env takes no turn in this call
-    if (DO_STEP) {
-      if (lane < GRL_MAX_ACTIONS) {
-        uint2 d = make_uint2(0u, 0xffffffffu);
-        if (read_actions && lane < prm.A) d = decode_action(next_act, W, H, P);
-        s_act[2 * lane] = d.x;
-        s_act[2 * lane + 1] = d.y;
-      }
-      if (read_actions) skip = ((__shfl_sync(FULL, next_act.y, 0) >> 24) & GRL_ACTION_FLAG_SKIP_ENV) != 0u;
-    }
     if (prm.use_tma) {
-      mbar_wait(&bars[cur], (phase_bits >> cur) & 1u);
-      phase_bits ^= 1u << cur;
-      // prefetch the next game's slab into the other buffer; its previous contents were handed
-      // to a bulk store at the end of the last iteration, which must have finished reading them
-      const int nxt = game + stride;
-      if (nxt < game_end) {
-        if (lane == 0) {
-          if (DO_STEP) tma_store_wait_read();
-          uint32_t *ns = wbase + (cur ^ 1) * buf_words;
-          mbar_expect_tx(&bars[cur ^ 1], (uint32_t)buf_words * 4u);
-          tma_load(ns, prm.state + (size_t)nxt * L.slab_words, (uint32_t)L.slab_words * 4u, &bars[cur ^ 1]);
-          tma_load(ns + L.slab_words, prm.statics + (size_t)nxt * L.static_words, (uint32_t)L.static_words * 4u,
-                   &bars[cur ^ 1]);
+      if (l == 0) {
+        const bool want_snap = kSnap && DO_STEP;
+        mbar_expect_tx(bar, (uint32_t)(L.slab_words + L.static_words + (want_snap ? L.slab_words : 0)) * 4u);
+        tma_load(s, gslab, (uint32_t)L.slab_words * 4u, bar);
+        tma_load(st, gstat, (uint32_t)L.static_words * 4u, bar);
+        if (want_snap)  // pre-turn snapshot for the dirty-sector write-back (an L2 hit on the same lines)
+          tma_load(snap, gslab, (uint32_t)L.slab_words * 4u, bar);
+        // warm L2 for a CTA that will be scheduled a couple of waves from now
+        if (prm.prefetch_dist > 0 && game + prm.prefetch_dist < prm.B) {
+          tma_prefetch_l2(prm.state + (size_t)(game + prm.prefetch_dist) * L.slab_words, (uint32_t)L.slab_words * 4u);
+          tma_prefetch_l2(prm.statics + (size_t)(game + prm.prefetch_dist) * L.static_words, (uint32_t)L.static_words * 4u);
         }
-        if (read_actions && lane < prm.A)
-          next_act = __ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)nxt * prm.A + lane);
       }
     } else {
       const uint4 *src = reinterpret_cast<const uint4 *>(gslab);
       uint4 *dst = reinterpret_cast<uint4 *>(s);
-      for (int k = lane; k < L.slab_words / 4; k += 32) dst[k] = src[k];
+      for (int k = l; k < L.slab_words / 4; k += LG) dst[k] = src[k];
       const uint4 *src2 = reinterpret_cast<const uint4 *>(gstat);
       uint4 *dst2 = reinterpret_cast<uint4 *>(st);
-      for (int k = lane; k < L.static_words / 4; k += 32) dst2[k] = __ldg(src2 + k);
-      const int nxt = game + stride;
-      if (nxt < game_end && read_actions && lane < prm.A)
-        next_act = __ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)nxt * prm.A + lane);
+      for (int k = l; k < L.static_words / 4; k += LG) dst2[k] = __ldg(src2 + k);
     }
-    __syncwarp();
+    // decode this game's action slots while its slab lands
+    bool skip = false;  // GRL_ACTION_FLAG_SKIP_ENV on slot 0: this env takes no turn in this call
+    if (DO_STEP) {
+      uint32_t slot0_hi = 0u;
+      for (int sl = l; sl < GRL_MAX_ACTIONS; sl += LG) {
+        uint2 d = make_uint2(0u, 0xffffffffu);
+        if (read_actions && sl < prm.A) {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(prm.actions) + (size_t)game * prm.A + sl);
+          if (sl == 0) slot0_hi = raw.y;
+          d = decode_action(raw, W, H, P);
+        }
+        s_act[2 * sl] = d.x;
+        s_act[2 * sl + 1] = d.y;
+      }
+      if (read_actions) skip = ((__shfl_sync(g.seg, slot0_hi, 0, LG) >> 24) & GRL_ACTION_FLAG_SKIP_ENV) != 0u;
+    }
+    if (prm.use_tma) mbar_wait(bar, 0u);
+    __syncwarp(g.seg);
 
     // ---- mask words into registers -----------------------------------------------------
-    uint32_t own[PT], lst[PT], vis[PT], own_prev[PT];
+    uint32_t own_prev[PT];
 #pragma unroll
     for (int p = 0; p < PT; p++) {
       bool on = act_lane && p < P;
-      own[p] = on ? S.own[p * NW + lane] : 0u;
-      lst[p] = on ? S.list[p * NW + lane] : 0u;
-      vis[p] = on ? S.vis[p * NW + lane] : 0u;
+      own[p] = on ? S.own[p * NW + l] : 0u;
+      lst[p] = on ? S.list[p * NW + l] : 0u;
+      vis[p] = on ? S.vis[p * NW + l] : 0u;
       own_prev[p] = own[p];
     }
-    uint32_t chg = act_lane ? S.chg[lane] : 0u;
-    uint32_t vch = act_lane ? S.vch[lane] : 0u;
-    const uint32_t M = act_lane ? S.M[lane] : 0u;
-    const uint32_t C = act_lane ? S.C[lane] : 0u;
-    const uint32_t G = act_lane ? S.G[lane] : 0u;
+    uint32_t chg = act_lane ? S.chg[l] : 0u;
+    uint32_t vch = act_lane ? S.vch[l] : 0u;
+    M = act_lane ? S.M[l] : 0u;
+    const uint32_t C = act_lane ? S.C[l] : 0u;
+    const uint32_t G = act_lane ? S.G[l] : 0u;
 
     uint32_t turn = S.hdr[GRL_HDR_TURN];
     uint32_t flags = S.hdr[GRL_HDR_FLAGS];
-    uint32_t alive = flags & 0xffu;
-    bool over = (flags & GRL_FLAG_OVER) != 0;
-    uint32_t err = 0;
+    alive = flags & 0xffu;
+    over = (flags & GRL_FLAG_OVER) != 0;
     bool stepped = false;
     int prev_true_army[PT];
 #pragma unroll
@@ -732,7 +750,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
       } else if (over) {
         // turn_processor.go:95-113: ErrGameOver, nothing mutated
         err = GRL_STEP_GAME_OVER;
-        if (lane == 0) {
+        if (l == 0) {
           S.hdr[GRL_HDR_REJECTED] += 1;
           for (int p = 0; p < P; p++) {
             S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_REWARD] = 0u;
@@ -745,24 +763,24 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
         turn += 1;  // turn_processor.go:125
 
         // ---- the synthetic policy reads the PRE-turn state (all players at once) ----------
-        if (use_policy) policy_phase<PT>(prm, s, st, s_act, alive, turn_before, game, lane, W, H, N, NW);
+        if (use_policy) policy_phase<PT, LG>(prm, s, st, s_act, alive, turn_before, game, g, W, H, N, NW);
 
         // ---- fog of war, from LAST turn's vchg and the CURRENT lists (Q1) -----------------
         if (prm.fog) {
-          int nv = __reduce_add_sync(FULL, __popc(vch));
+          int nv = __reduce_add_sync(g.seg, __popc(vch));
           if (nv > N / 10) {  // visibility_optimized.go:22-25 -> full :33-53
 #pragma unroll
             for (int p = 0; p < PT; p++)
-              if (p < P) vis[p] = ((alive >> p) & 1u) ? dilate3(lst[p], g) : 0u;
+              if (p < P) vis[p] = ((alive >> p) & 1u) ? dilate3<LG>(lst[p], g) : 0u;
           } else if (nv > 0) {  // incremental :56-97
-            uint32_t d3 = dilate3(vch, g);
-            uint32_t d5 = dilate3(d3, g);
+            uint32_t d3 = dilate3<LG>(vch, g);
+            uint32_t d5 = dilate3<LG>(d3, g);
 #pragma unroll
             for (int p = 0; p < PT; p++) {
               if (p < P) {
-                bool affected = __any_sync(FULL, (own[p] & d5) != 0u);  // owners read NOW (:100-115)
-                vis[p] &= ~d3;                                          // all players' bits cleared (:131-149)
-                if (affected && ((alive >> p) & 1u)) vis[p] |= dilate3(lst[p], g);
+                bool affected = __any_sync(g.seg, (own[p] & d5) != 0u);  // owners read NOW (:100-115)
+                vis[p] &= ~d3;                                           // all players' bits cleared (:131-149)
+                if (affected && ((alive >> p) & 1u)) vis[p] |= dilate3<LG>(lst[p], g);
               }
             }
           }
@@ -771,16 +789,16 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
         chg = 0u;
         vch = 0u;
         if (act_lane) {
-          S.chg[lane] = 0u;
-          S.vch[lane] = 0u;
+          S.chg[l] = 0u;
+          S.vch[l] = 0u;
         }
-        if (lane < P) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ACTION_INDEX] = 0xffffffffu;
-        __syncwarp();
+        if (l < P) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * l + GRL_PL_ACTION_INDEX] = 0xffffffffu;
+        __syncwarp(g.seg);
 
         // ---- actions: serial by definition, one lane, on the shared-memory slab -----------
         uint32_t ord_lo = 0, ord_hi = 0;  // up to 8 orders, one byte each: eliminated | capturer<<4
         int n_orders = 0;
-        if (lane == 0) {
+        if (l == 0) {
           uint32_t processed = 0;
           uint32_t overflow = 0;
           const uint32_t alive_start = alive;  // action_processor.go:56-60 reads Alive as of now
@@ -856,32 +874,32 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
           }
           if (overflow) S.hdr[GRL_HDR_OVERFLOW] = 1u;
         }
-        __syncwarp();
-        err = __shfl_sync(FULL, err, 0);
-        n_orders = __shfl_sync(FULL, n_orders, 0);
+        __syncwarp(g.seg);
+        err = __shfl_sync(g.seg, err, 0, LG);
+        n_orders = __shfl_sync(g.seg, n_orders, 0, LG);
 #pragma unroll
         for (int p = 0; p < PT; p++)
-          if (p < P && act_lane) own[p] = S.own[p * NW + lane];
+          if (p < P && act_lane) own[p] = S.own[p * NW + l];
         if (act_lane) {
-          chg = S.chg[lane];
-          vch = S.vch[lane];
+          chg = S.chg[l];
+          vch = S.vch[l];
         }
 
         // ---- eliminations + tile turnover over the CACHED list (engine.go:118-152) --------
         if (n_orders > 0) {  // rare: kept out of line so the common path stays compact
-          ord_lo = __shfl_sync(FULL, ord_lo, 0);
-          ord_hi = __shfl_sync(FULL, ord_hi, 0);
-          alive = elimination_phase<PT>(prm, s, st, alive, n_orders, ord_lo, ord_hi, lane, N, NW);
+          ord_lo = __shfl_sync(g.seg, ord_lo, 0, LG);
+          ord_hi = __shfl_sync(g.seg, ord_hi, 0, LG);
+          alive = elimination_phase<PT, LG>(prm, s, st, alive, n_orders, ord_lo, ord_hi, g, N, NW);
 #pragma unroll
           for (int p = 0; p < PT; p++) {
             if (p < P && act_lane) {
-              own[p] = S.own[p * NW + lane];
-              lst[p] = S.list[p * NW + lane];
+              own[p] = S.own[p * NW + l];
+              lst[p] = S.list[p * NW + l];
             }
           }
           if (act_lane) {
-            chg = S.chg[lane];
-            vch = S.vch[lane];
+            chg = S.chg[l];
+            vch = S.vch[l];
           }
         }
 
@@ -891,28 +909,31 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
 #pragma unroll
           for (int p = 0; p < PT; p++)
             if (p < P && ((alive >> p) & 1u)) AL |= lst[p];
-          const bool grow = (turn % (uint32_t)prm.grow_interval) == 0u;
+          const bool grow = prm.grow_interval == 25 ? (turn % 25u) == 0u : (turn % (uint32_t)prm.grow_interval) == 0u;
           uint32_t PG = prm.pg > 0 ? (AL & G) : 0u;
           uint32_t PC = prm.pc > 0 ? (AL & C) : 0u;
           uint32_t PN = (grow && prm.pn > 0) ? (AL & ~(G | C | M)) : 0u;
           uint32_t produced = PG | PC | PN;
           chg |= produced;
-          if (__any_sync(FULL, produced != 0u)) {
+          if (__any_sync(g.seg, produced != 0u)) {
             uint32_t overflow = 0;
             if (grow) {  // dense: most owned tiles grow (1 turn in 25)
 #pragma unroll 1
               for (int i = 0; i < NW; i++) {
-                uint32_t wg = __shfl_sync(FULL, PG, i), wc = __shfl_sync(FULL, PC, i), wn = __shfl_sync(FULL, PN, i);
-                int t = 32 * i + lane;
-                uint32_t add = (((wg >> lane) & 1u) ? (uint32_t)prm.pg : 0u) + (((wc >> lane) & 1u) ? (uint32_t)prm.pc : 0u) +
-                               (((wn >> lane) & 1u) ? (uint32_t)prm.pn : 0u);
-                if (add) {
-                  uint32_t a = (uint32_t)S.army[t] + add;
-                  if (a > 65535u) {
-                    a = 65535u;
-                    overflow = 1;
+                uint32_t wg = __shfl_sync(g.seg, PG, i, LG), wc = __shfl_sync(g.seg, PC, i, LG), wn = __shfl_sync(g.seg, PN, i, LG);
+#pragma unroll
+                for (int b = l; b < 32; b += LG) {
+                  int t = 32 * i + b;
+                  uint32_t add = (((wg >> b) & 1u) ? (uint32_t)prm.pg : 0u) + (((wc >> b) & 1u) ? (uint32_t)prm.pc : 0u) +
+                                 (((wn >> b) & 1u) ? (uint32_t)prm.pn : 0u);
+                  if (add) {
+                    uint32_t a = (uint32_t)S.army[t] + add;
+                    if (a > 65535u) {
+                      a = 65535u;
+                      overflow = 1;
+                    }
+                    S.army[t] = (uint16_t)a;
                   }
-                  S.army[t] = (uint16_t)a;
                 }
               }
             } else {  // sparse: generals and cities only
@@ -920,7 +941,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
               while (w) {
                 int b = __ffs(w) - 1;
                 w &= w - 1u;
-                int t = 32 * lane + b;
+                int t = 32 * l + b;
                 uint32_t add = ((PG >> b) & 1u) ? (uint32_t)prm.pg : (uint32_t)prm.pc;
                 uint32_t a = (uint32_t)S.army[t] + add;
                 if (a > 65535u) {
@@ -930,25 +951,25 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
                 S.army[t] = (uint16_t)a;
               }
             }
-            if (__any_sync(FULL, overflow != 0u) && lane == 0) S.hdr[GRL_HDR_OVERFLOW] = 1u;
+            if (__any_sync(g.seg, overflow != 0u) && l == 0) S.hdr[GRL_HDR_OVERFLOW] = 1u;
 #pragma unroll
             for (int p = 0; p < PT; p++) {
               if (p < P) {
                 int d = prm.pg * __popc(PG & own[p]) + prm.pc * __popc(PC & own[p]) + prm.pn * __popc(PN & own[p]);
-                d = __reduce_add_sync(FULL, d);
-                if (lane == 0) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY] += (uint32_t)d;
+                d = __reduce_add_sync(g.seg, d);
+                if (l == 0) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY] += (uint32_t)d;
               }
             }
-            __syncwarp();
+            __syncwarp(g.seg);
           }
           // ---- end of turn: stats, game over (turn_processor.go:170-179) --------------------
-          stats_update<PT>(prm, S, own, lst, chg, G, alive, lane, N, NW);
+          stats_update<PT, LG>(prm, S, own, lst, chg, G, alive, g, N, NW);
           int n_alive = __popc(alive & pmask);
           bool now_over = P > 1 ? (n_alive <= 1) : (n_alive == 0);  // win_conditions.go:38-44
-          if (now_over && !over && lane == 0) S.hdr[GRL_HDR_FINISHED] += 1;
+          if (now_over && !over && l == 0) S.hdr[GRL_HDR_FINISHED] += 1;
           over = now_over;
         }
-        if (lane == 0) {
+        if (l == 0) {
           S.hdr[GRL_HDR_STEPS] += 1;
           if (err) S.hdr[GRL_HDR_ERRORS] += 1;
         }
@@ -971,12 +992,12 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
 #pragma unroll
       for (int p = 0; p < PT; p++) {
         if (p < P) {
-          int d_tiles = __reduce_add_sync(FULL, __popc(own[p]) - __popc(own_prev[p]));
+          int d_tiles = __reduce_add_sync(g.seg, __popc(own[p]) - __popc(own_prev[p]));
           uint32_t gained = own[p] & ~own_prev[p], lost = own_prev[p] & ~own[p];
           int cc = 0, gg = 0;
-          if (__any_sync(FULL, ((gained | lost) & (C | G)) != 0u)) {
-            cc = __reduce_add_sync(FULL, __popc(gained & C) | (__popc(lost & C) << 16));
-            gg = __reduce_add_sync(FULL, __popc(gained & G & any_prev) | (__popc(lost & G) << 16));
+          if (__any_sync(g.seg, ((gained | lost) & (C | G)) != 0u)) {
+            cc = __reduce_add_sync(g.seg, __popc(gained & C) | (__popc(lost & C) << 16));
+            gg = __reduce_add_sync(g.seg, __popc(gained & G & any_prev) | (__popc(lost & G) << 16));
           }
           int cur_army = (int)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY];
           float r = 0.0f;
@@ -1001,10 +1022,10 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
             if (total_army != 0) adv = __fdiv_rn((float)(cur_army - (total_army - cur_army)), (float)total_army);
             r = __fadd_rn(r, __fmul_rn(adv, prm.rw[10]));
           }
-          if (lane == 0) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_REWARD] = __float_as_uint(r);
+          if (l == 0) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_REWARD] = __float_as_uint(r);
         }
       }
-      if (turn_err != 0 && lane == 0)  // aborted turn: no experience is emitted (engine.go:111-113)
+      if (turn_err != 0 && l == 0)  // aborted turn: no experience is emitted (engine.go:111-113)
         for (int p = 0; p < P; p++) S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ACTION_INDEX] = 0xffffffffu;
     }
 
@@ -1015,25 +1036,25 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
 #pragma unroll
           for (int p = 0; p < PT; p++) {
             if (p < P) {
-              S.own[p * NW + lane] = own[p];
-              S.list[p * NW + lane] = lst[p];
-              S.vis[p * NW + lane] = vis[p];
+              S.own[p * NW + l] = own[p];
+              S.list[p * NW + l] = lst[p];
+              S.vis[p * NW + l] = vis[p];
             }
           }
-          S.chg[lane] = chg;
-          S.vch[lane] = vch;
+          S.chg[l] = chg;
+          S.vch[l] = vch;
         }
-        if (lane == 0) S.hdr[GRL_HDR_TURN] = turn;
+        if (l == 0) S.hdr[GRL_HDR_TURN] = turn;
       }
-      if (lane == 0)
+      if (l == 0)
         S.hdr[GRL_HDR_FLAGS] = (alive & 0xffu) | (over ? GRL_FLAG_OVER : 0u) | (err << GRL_FLAG_ERR_SHIFT);
-      __syncwarp();
-      if (prm.use_tma && GRL_DIRTY_WB) {
+      __syncwarp(g.seg);
+      if (prm.use_tma && kSnap) {
         // sector k = words [8k, 8k+8) of the slab (slabs are 32-byte aligned and a whole number of sectors)
         const uint4 *now4 = reinterpret_cast<const uint4 *>(s);
-        const uint4 *old4 = reinterpret_cast<const uint4 *>(wbase + buf_words);
+        const uint4 *old4 = reinterpret_cast<const uint4 *>(snap);
         uint4 *dst4 = reinterpret_cast<uint4 *>(gslab);
-        for (int k = lane; k < L.slab_words / 8; k += 32) {
+        for (int k = l; k < L.slab_words / 8; k += LG) {
           const uint4 a0 = now4[2 * k], a1 = now4[2 * k + 1], b0 = old4[2 * k], b1 = old4[2 * k + 1];
           const uint32_t diff = (a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) |
                                 (a1.z ^ b1.z) | (a1.w ^ b1.w);
@@ -1042,22 +1063,18 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
             dst4[2 * k + 1] = a1;
           }
         }
-      } else if (prm.use_tma) {
-        fence_proxy_async_smem();  // make the generic-proxy writes visible to the bulk store
-        __syncwarp();
-        if (lane == 0) tma_store(gslab, s, (uint32_t)L.slab_words * 4u);
       } else {
         const uint4 *src = reinterpret_cast<const uint4 *>(s);
         uint4 *dst = reinterpret_cast<uint4 *>(gslab);
-        for (int k = lane; k < L.slab_words / 4; k += 32) dst[k] = src[k];
+        for (int k = l; k < L.slab_words / 4; k += LG) dst[k] = src[k];
       }
     } else {
       err = (flags >> GRL_FLAG_ERR_SHIFT) & 0xffu;
     }
 
-    // ---- read-outs ---------------------------------------------------------------------------
+    // ---- scalar read-outs (one lane per value) -------------------------------------------------
     if (DO_OUT) {
-      if (lane == 0) {
+      if (l == 0) {
         if (prm.done) prm.done[game] = over ? 1 : 0;
         if (prm.winner) {  // engine.go:248-263
           int n_alive = __popc(alive & pmask);
@@ -1065,194 +1082,193 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT>::kMi
         }
         if (prm.step_error) prm.step_error[game] = (uint8_t)err;
       }
-      if (lane < P) {
+      if (l < P) {
         if (prm.reward)
-          prm.reward[(size_t)game * P + lane] =
-              __uint_as_float(S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_REWARD]);
+          prm.reward[(size_t)game * P + l] = __uint_as_float(S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * l + GRL_PL_REWARD]);
         if (prm.action_index)
-          prm.action_index[(size_t)game * P + lane] =
-              (int32_t)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ACTION_INDEX];
+          prm.action_index[(size_t)game * P + l] =
+              (int32_t)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * l + GRL_PL_ACTION_INDEX];
       }
+    }
+  }
+  if (!DO_OUT) return;
+  __syncwarp();  // every group's slab in shared memory is final: the plane read-outs below are warp-wide
 
-      // engine legal-action mask, packed in the reference's flat index order (t*4 + dir, U,R,D,L)
-      if (prm.mask_bits) {
-        uint32_t gt1 = army_gt1_mask(S.army, NW, N, lane);
-        DirMasks dm = dir_targets(M, g);
-        const int words = (4 * N + 31) / 32;
+  // engine legal-action mask, packed in the reference's flat index order (t*4 + dir, U,R,D,L)
+  if (prm.mask_bits) {
+    const int words = (4 * N + 31) / 32;
+    if (gv) {
+      const uint32_t gt1 = army_gt1_mask<LG>(S.army, NW, N, g);
+      const DirMasks dm = dir_targets<LG>(M, g);
 #pragma unroll
-        for (int p = 0; p < PT; p++) {
-          if (p < P) {
-            uint32_t src = ((alive >> p) & 1u) ? (lst[p] & own[p] & gt1) : 0u;
-            uint32_t U = src & dm.up, R = src & dm.right, D = src & dm.down, Lm = src & dm.left;
-            uint32_t *dst = prm.mask_bits + ((size_t)game * P + p) * words;
+      for (int p = 0; p < PT; p++) {
+        if (p < P) {
+          const uint32_t src = ((alive >> p) & 1u) ? (lst[p] & own[p] & gt1) : 0u;
+          const uint32_t U = src & dm.up, R = src & dm.right, D = src & dm.down, Lm = src & dm.left;
+          uint32_t *dst = prm.mask_bits + ((size_t)game * P + p) * words;
+          if (LG == 32) {
             for (int k0 = 0; k0 < words; k0 += 32) {
-              int k = k0 + lane;  // output word k covers tiles 8k..8k+7 = byte k&3 of mask word k>>2
+              int k = k0 + l;  // output word k covers tiles 8k..8k+7 = byte k&3 of mask word k>>2
               int srcl = (k >> 2) & 31, sh = (k & 3) * 8;
               uint32_t bu = __shfl_sync(FULL, U, srcl) >> sh, br = __shfl_sync(FULL, R, srcl) >> sh;
               uint32_t bd = __shfl_sync(FULL, D, srcl) >> sh, bl = __shfl_sync(FULL, Lm, srcl) >> sh;
               uint32_t w = spread8(bu) | (spread8(br) << 1) | (spread8(bd) << 2) | (spread8(bl) << 3);
               if (k < words) __stcs(dst + k, w);
             }
-          }
-        }
-      }
-
-      // observation planes: Serializer.StateToTensor (serializer.go:37-109)
-      if (prm.obs) {
-        uint32_t any_own = 0;
+          } else {  // packed groups: a lane expands its own word into output words 4l..4l+3
 #pragma unroll
-        for (int p = 0; p < PT; p++) any_own |= own[p];
-        const uint32_t CG = C | G;
-        float *gbase = prm.obs + (size_t)game * P * GRL_OBS_CHANNELS * N;
-        if (TW > 0 && ((TW * TH) & 3) == 0 && !GRL_OBS_CHUNK_MAJOR) {
-          obs_plane_major<PT, (TW > 0 ? TW * TH : 4)>(prm, S, s_lut, P, NW, game, lane);
-        } else if (TW > 0 && ((TW * TH) & 3) != 0 && !GRL_OBS_CHUNK_MAJOR) {
-          obs_linear<PT, (TW > 0 ? TW * TH : 5)>(prm, S, s_lut, s_obs, own, vis, M, CG, g.valid, P, NW, game, lane);
-        } else if ((N & 3) == 0) {
-          // 128-bit path: a lane writes 4 consecutive tiles of each channel plane; the army
-          // conversion and the terrain nibbles are shared by all players' views
-          const int cs = N / 4;  // channel stride in float4
-#pragma unroll kObsUnroll
-          for (int q0 = 0; q0 * 4 < N; q0 += 32) {
-            const int q = q0 + lane;
-            const int t0 = 4 * q;
-            const int srcl = (t0 >> 5) & 31, sh = t0 & 31;
-            const uint32_t mM = (__shfl_sync(FULL, M, srcl) >> sh) & 0xfu;
-            const uint32_t mCG = (__shfl_sync(FULL, CG, srcl) >> sh) & 0xfu;
-            const uint32_t mAny = (__shfl_sync(FULL, any_own, srcl) >> sh) & 0xfu;
-            const bool live = t0 < N;
-            // armies are only read for visible owned tiles: skip the conversion when nobody owns
-            // a tile in this 128-tile chunk (most of the board, most of the game)
-            float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-            if (__any_sync(FULL, live && (mAny & ~mM) != 0u)) {
-              if (live) {
-                const uint2 aw = *reinterpret_cast<const uint2 *>(S.army + t0);
-                f0 = army_frac(aw.x & 0xffffu);
-                f1 = army_frac(aw.x >> 16);
-                f2 = army_frac(aw.y & 0xffffu);
-                f3 = army_frac(aw.y >> 16);
-              }
-            }
-#define NIBF(n) make_float4(((n)&1u) ? 1.f : 0.f, ((n)&2u) ? 1.f : 0.f, ((n)&4u) ? 1.f : 0.f, ((n)&8u) ? 1.f : 0.f)
-#define NIBA(n) make_float4(((n)&1u) ? f0 : 0.f, ((n)&2u) ? f1 : 0.f, ((n)&4u) ? f2 : 0.f, ((n)&8u) ? f3 : 0.f)
-#pragma unroll
-            for (int p = 0; p < PT; p++) {
-              if (p < P) {
-                const uint32_t nV = prm.fog ? ((__shfl_sync(FULL, vis[p], srcl) >> sh) & 0xfu) : 0xfu;
-                float4 *o = reinterpret_cast<float4 *>(gbase + (size_t)p * GRL_OBS_CHANNELS * N + t0);
-                if (!__any_sync(FULL, live && nV != 0u)) {
-                  // the whole chunk is fogged for this player: only the fog plane is non-zero
-                  // (serializer.go:50-60 skips every other channel of an invisible tile)
-                  if (live) {
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int c = 0; c < 8; c++) __stcs(o + c * cs, z);
-                    __stcs(o + 8 * cs, make_float4(1.f, 1.f, 1.f, 1.f));
-                  }
-                } else {
-                  const uint32_t nO = (__shfl_sync(FULL, own[p], srcl) >> sh) & 0xfu;
-                  if (live) {
-                    const uint32_t nm = nV & ~mM;
-                    const uint32_t n2 = nm & nO, n3 = nm & mAny & ~nO, n4 = nm & ~mAny, n5 = nm & mCG, n6 = nV & mM;
-                    const uint32_t n7 = nV, n8 = nV ^ 0xfu;
-                    __stcs(o + 0 * cs, NIBA(n2));
-                    __stcs(o + 1 * cs, NIBA(n3));
-                    __stcs(o + 2 * cs, NIBF(n2));
-                    __stcs(o + 3 * cs, NIBF(n3));
-                    __stcs(o + 4 * cs, NIBF(n4));
-                    __stcs(o + 5 * cs, NIBF(n5));
-                    __stcs(o + 6 * cs, NIBF(n6));
-                    __stcs(o + 7 * cs, NIBF(n7));
-                    __stcs(o + 8 * cs, NIBF(n8));
-                  }
-                }
-              }
-            }
-#undef NIBF
-#undef NIBA
-          }
-        } else {
-          // generic path (N % 4 != 0, e.g. 15x15): one tile per lane, coalesced 32-bit stores
-          for (int i = 0; i < NW; i++) {
-            const int t = 32 * i + lane;
-            const uint32_t bM = (__shfl_sync(FULL, M, i) >> lane) & 1u, bCG = (__shfl_sync(FULL, CG, i) >> lane) & 1u;
-            const uint32_t bAny = (__shfl_sync(FULL, any_own, i) >> lane) & 1u;
-            const bool live = t < N;
-            const float f = live ? army_frac((uint32_t)S.army[t]) : 0.f;
-#pragma unroll
-            for (int p = 0; p < PT; p++) {
-              if (p < P) {
-                const uint32_t bV = prm.fog ? ((__shfl_sync(FULL, vis[p], i) >> lane) & 1u) : 1u;
-                const uint32_t bO = (__shfl_sync(FULL, own[p], i) >> lane) & 1u;
-                if (live) {
-                  const uint32_t nm = bV & ~bM;
-                  const uint32_t b2 = nm & bO, b3 = nm & bAny & ~bO, b4 = nm & ~bAny & 1u, b5 = nm & bCG, b6 = bV & bM;
-                  float *o = gbase + (size_t)p * GRL_OBS_CHANNELS * N + t;
-                  __stcs(o + 0 * N, b2 ? f : 0.f);
-                  __stcs(o + 1 * N, b3 ? f : 0.f);
-                  __stcs(o + 2 * N, b2 ? 1.f : 0.f);
-                  __stcs(o + 3 * N, b3 ? 1.f : 0.f);
-                  __stcs(o + 4 * N, b4 ? 1.f : 0.f);
-                  __stcs(o + 5 * N, b5 ? 1.f : 0.f);
-                  __stcs(o + 6 * N, b6 ? 1.f : 0.f);
-                  __stcs(o + 7 * N, bV ? 1.f : 0.f);
-                  __stcs(o + 8 * N, bV ? 0.f : 1.f);
-                }
-              }
+            for (int q = 0; q < 4; q++) {
+              const int k = 4 * l + q, sh = 8 * q;
+              const uint32_t w = spread8(U >> sh) | (spread8(R >> sh) << 1) | (spread8(D >> sh) << 2) | (spread8(Lm >> sh) << 3);
+              if (act_lane && k < words) __stcs(dst + k, w);
             }
           }
         }
       }
-    }
-
-    if (prm.use_tma) {
-      if (DO_STEP && !GRL_DIRTY_WB && lane == 0) tma_store_commit();
-      fence_proxy_async_smem();  // this buffer's generic-proxy accesses precede its next bulk refill
-      cur ^= 1;
     }
     __syncwarp();
   }
-  if (DO_STEP && !GRL_DIRTY_WB && prm.use_tma && lane == 0) tma_store_wait_read();  // shared memory outlives the bulk stores
+
+  // observation planes: Serializer.StateToTensor (serializer.go:37-109)
+  if (prm.obs) {
+    if (TW > 0 && !GRL_OBS_CHUNK_MAJOR) {
+      // baked boards: the whole warp writes one game's block after the other, from the slabs in shared memory
+#pragma unroll 1
+      for (int gi = 0; gi < GPW; gi++) {
+        const int game_g = warp_game0 + gi;
+        if (game_g >= game_end) break;
+        uint32_t *sg = wbase + gi * per_game;
+        const SlabView Sg = make_view(sg, sg + L.slab_words, L);
+        if (((TW * TH) & 3) == 0)
+          obs_plane_major<PT, (TW > 0 && ((TW * TH) & 3) == 0 ? TW * TH : 4)>(prm, Sg, s_lut, P, NW, game_g, lane);
+        else
+          obs_linear<PT, (TW > 0 ? TW * TH : 5)>(prm, Sg, s_lut, s_obs, P, NW, game_g, lane);
+      }
+    } else if (gv) {
+      // generic geometries (LG == 32: one game per warp), from the mask words in registers
+      uint32_t any_own = 0;
+#pragma unroll
+      for (int p = 0; p < PT; p++) any_own |= own[p];
+      const uint32_t C = act_lane ? S.C[l] : 0u;
+      const uint32_t G = act_lane ? S.G[l] : 0u;
+      const uint32_t CG = C | G;
+      float *gbase = prm.obs + (size_t)game * P * GRL_OBS_CHANNELS * N;
+      if ((N & 3) == 0) {
+        // 128-bit path: a lane writes 4 consecutive tiles of each channel plane; the army
+        // conversion and the terrain nibbles are shared by all players' views
+        const int cs = N / 4;  // channel stride in float4
+        for (int q0 = 0; q0 * 4 < N; q0 += 32) {
+          const int q = q0 + lane;
+          const int t0 = 4 * q;
+          const int srcl = (t0 >> 5) & 31, sh = t0 & 31;
+          const uint32_t mM = (__shfl_sync(FULL, M, srcl) >> sh) & 0xfu;
+          const uint32_t mCG = (__shfl_sync(FULL, CG, srcl) >> sh) & 0xfu;
+          const uint32_t mAny = (__shfl_sync(FULL, any_own, srcl) >> sh) & 0xfu;
+          const bool live = t0 < N;
+          float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+          if (__any_sync(FULL, live && (mAny & ~mM) != 0u)) {
+            if (live) {
+              const uint2 aw = *reinterpret_cast<const uint2 *>(S.army + t0);
+              f0 = army_frac(aw.x & 0xffffu);
+              f1 = army_frac(aw.x >> 16);
+              f2 = army_frac(aw.y & 0xffffu);
+              f3 = army_frac(aw.y >> 16);
+            }
+          }
+#define NIBF(n) make_float4(((n)&1u) ? 1.f : 0.f, ((n)&2u) ? 1.f : 0.f, ((n)&4u) ? 1.f : 0.f, ((n)&8u) ? 1.f : 0.f)
+#define NIBA(n) make_float4(((n)&1u) ? f0 : 0.f, ((n)&2u) ? f1 : 0.f, ((n)&4u) ? f2 : 0.f, ((n)&8u) ? f3 : 0.f)
+#pragma unroll
+          for (int p = 0; p < PT; p++) {
+            if (p < P) {
+              const uint32_t nV = prm.fog ? ((__shfl_sync(FULL, vis[p], srcl) >> sh) & 0xfu) : 0xfu;
+              const uint32_t nO = (__shfl_sync(FULL, own[p], srcl) >> sh) & 0xfu;
+              float4 *o = reinterpret_cast<float4 *>(gbase + (size_t)p * GRL_OBS_CHANNELS * N + t0);
+              if (live) {
+                const uint32_t nm = nV & ~mM;
+                const uint32_t n2 = nm & nO, n3 = nm & mAny & ~nO, n4 = nm & ~mAny, n5 = nm & mCG, n6 = nV & mM;
+                const uint32_t n7 = nV, n8 = nV ^ 0xfu;
+                __stcs(o + 0 * cs, NIBA(n2));
+                __stcs(o + 1 * cs, NIBA(n3));
+                __stcs(o + 2 * cs, NIBF(n2));
+                __stcs(o + 3 * cs, NIBF(n3));
+                __stcs(o + 4 * cs, NIBF(n4));
+                __stcs(o + 5 * cs, NIBF(n5));
+                __stcs(o + 6 * cs, NIBF(n6));
+                __stcs(o + 7 * cs, NIBF(n7));
+                __stcs(o + 8 * cs, NIBF(n8));
+              }
+            }
+          }
+#undef NIBF
+#undef NIBA
+        }
+      } else {
+        // N % 4 != 0: one tile per lane, coalesced 32-bit stores
+        for (int i = 0; i < NW; i++) {
+          const int t = 32 * i + lane;
+          const uint32_t bM = (__shfl_sync(FULL, M, i) >> lane) & 1u, bCG = (__shfl_sync(FULL, CG, i) >> lane) & 1u;
+          const uint32_t bAny = (__shfl_sync(FULL, any_own, i) >> lane) & 1u;
+          const bool live = t < N;
+          const float f = live ? army_frac((uint32_t)S.army[t]) : 0.f;
+#pragma unroll
+          for (int p = 0; p < PT; p++) {
+            if (p < P) {
+              const uint32_t bV = prm.fog ? ((__shfl_sync(FULL, vis[p], i) >> lane) & 1u) : 1u;
+              const uint32_t bO = (__shfl_sync(FULL, own[p], i) >> lane) & 1u;
+              if (live) {
+                const uint32_t nm = bV & ~bM;
+                const uint32_t b2 = nm & bO, b3 = nm & bAny & ~bO, b4 = nm & ~bAny & 1u, b5 = nm & bCG, b6 = bV & bM;
+                float *o = gbase + (size_t)p * GRL_OBS_CHANNELS * N + t;
+                __stcs(o + 0 * N, b2 ? f : 0.f);
+                __stcs(o + 1 * N, b3 ? f : 0.f);
+                __stcs(o + 2 * N, b2 ? 1.f : 0.f);
+                __stcs(o + 3 * N, b3 ? 1.f : 0.f);
+                __stcs(o + 4 * N, b4 ? 1.f : 0.f);
+                __stcs(o + 5 * N, b5 ? 1.f : 0.f);
+                __stcs(o + 6 * N, b6 ? 1.f : 0.f);
+                __stcs(o + 7 * N, bV ? 1.f : 0.f);
+                __stcs(o + 8 * N, bV ? 0.f : 1.f);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
 }
 
-template <int PT>
+template <int PT, int LG>
 __device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t *s_act,
-                                          uint32_t alive, uint32_t turn_before, int game, int lane, int W, int H, int N,
-                                          int NW) {
+                                          uint32_t alive, uint32_t turn_before, int game, Geo g, int W, int H, int N, int NW) {
   const GrlLayout &L = prm.L;
   const int P = prm.P;
   SlabView S = make_view(s, st, L);
-  Geo g;
-  g.lane = lane;
-  g.W = W;
-  g.valid = prm.geom[lane];
-  g.nc0 = prm.geom[32 + lane];
-  g.ncl = prm.geom[64 + lane];
-  const bool act_lane = lane < NW;
-  const uint32_t M = act_lane ? S.M[lane] : 0u;
-  uint32_t gt1 = army_gt1_mask(S.army, NW, N, lane);
-  DirMasks dm = dir_targets(M, g);
+  const bool act_lane = g.lane < NW;
+  const uint32_t M = act_lane ? S.M[g.lane] : 0u;
+  uint32_t gt1 = army_gt1_mask<LG>(S.army, NW, N, g);
+  DirMasks dm = dir_targets<LG>(M, g);
 #pragma unroll 1
   for (int p = 0; p < P && p < prm.A; p++) {
-    const uint32_t own = act_lane ? S.own[p * NW + lane] : 0u;
-    const uint32_t lst = act_lane ? S.list[p * NW + lane] : 0u;
+    const uint32_t own = act_lane ? S.own[p * NW + g.lane] : 0u;
+    const uint32_t lst = act_lane ? S.list[p * NW + g.lane] : 0u;
     uint32_t src = ((alive >> p) & 1u) ? (lst & own & gt1) : 0u;
-    PackedAction a = sample_policy_action(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn_before, g);
-    if (lane == 0 && a.present()) {
+    PackedAction a = sample_policy_action<LG>(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn_before, g);
+    if (g.lane == 0 && a.present()) {
       uint2 d = decode_action(make_uint2(a.lo, a.hi), W, H, P);
       s_act[2 * p] = d.x;
       s_act[2 * p + 1] = d.y;
     }
   }
-  __syncwarp();
+  __syncwarp(g.seg);
 }
 
-template <int PT>
+template <int PT, int LG>
 __device__ __noinline__ uint32_t elimination_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t alive,
-                                                   int n_orders, uint32_t ord_lo, uint32_t ord_hi, int lane, int N, int NW) {
+                                                   int n_orders, uint32_t ord_lo, uint32_t ord_hi, Geo g, int N, int NW) {
   const GrlLayout &L = prm.L;
   const int P = prm.P;
   SlabView S = make_view(s, st, L);
+  const int lane = g.lane;
   const bool act_lane = lane < NW;
   uint32_t own[PT], lst[PT];
 #pragma unroll
@@ -1280,7 +1296,7 @@ __device__ __noinline__ uint32_t elimination_phase(const GrlKParams &prm, uint32
     chg |= X;
     vch |= X;
     int moved_army = 0;
-    if (__any_sync(FULL, X != 0u)) moved_army = sum_army_over(X, S.army, NW, N, lane);
+    if (__any_sync(g.seg, X != 0u)) moved_army = sum_army_over<LG>(X, S.army, NW, N, g);
     if (lane == 0) {
       S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * el + GRL_PL_TRUE_ARMY] -= (uint32_t)moved_army;
       S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * nw + GRL_PL_TRUE_ARMY] += (uint32_t)moved_army;
@@ -1288,8 +1304,8 @@ __device__ __noinline__ uint32_t elimination_phase(const GrlKParams &prm, uint32
     }
     alive &= ~(1u << el);
   }
-  __syncwarp();
-  stats_update<PT>(prm, S, own, lst, chg, G, alive, lane, N, NW);  // engine.go:107
+  __syncwarp(g.seg);
+  stats_update<PT, LG>(prm, S, own, lst, chg, G, alive, g, N, NW);  // engine.go:107
   if (act_lane) {
 #pragma unroll
     for (int p = 0; p < PT; p++) {
@@ -1301,7 +1317,7 @@ __device__ __noinline__ uint32_t elimination_phase(const GrlKParams &prm, uint32
     S.chg[lane] = chg;
     S.vch[lane] = vch;
   }
-  __syncwarp();
+  __syncwarp(g.seg);
   return alive;
 }
 
@@ -1317,12 +1333,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GrlLayout &L = prm.L;
   const int P = prm.P, NW = prm.NW, N = prm.N;
-  Geo g;
-  g.lane = lane;
-  g.W = prm.W;
-  g.valid = prm.geom[lane];
-  g.nc0 = prm.geom[32 + lane];
-  g.ncl = prm.geom[64 + lane];
+  const Geo g = make_geo(prm, prm.W, lane, 32);
   for (int i = blockIdx.x * GRL_WARPS_PER_CTA + warp; i < n; i += gridDim.x * GRL_WARPS_PER_CTA) {
     const int game = env_ids ? env_ids[i] : i;
     if (game < 0 || game >= prm.B) continue;
@@ -1340,12 +1351,12 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
     for (int p = 0; p < PT; p++) {
       if (p < P) {
         uint32_t own = act ? ss[L.off_own + p * NW + lane] : 0u;
-        int total = sum_army_over(own, army, NW, N, lane);
+        int total = sum_army_over<32>(own, army, NW, N, g);
         uint32_t gen = own & G;
         int gi = gen ? (32 * lane + 31 - __clz(gen)) : -1;
         gi = __reduce_max_sync(FULL, gi);
         if (gi >= 0) alive |= 1u << p;
-        uint32_t v = (gi >= 0 && prm.fog) ? dilate3(own, g) : 0u;  // players start Alive; stats then sets Alive = has general
+        uint32_t v = (gi >= 0 && prm.fog) ? dilate3<32>(own, g) : 0u;  // players start Alive; stats then sets Alive = has general
         if (act) {
           ds[L.off_own + p * NW + lane] = own;
           ds[L.off_list + p * NW + lane] = own;
@@ -1551,12 +1562,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32) grl_sample_kernel(cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GrlLayout &L = prm.L;
   const int P = prm.P, NW = prm.NW, N = prm.N;
-  Geo g;
-  g.lane = lane;
-  g.W = prm.W;
-  g.valid = prm.geom[lane];
-  g.nc0 = prm.geom[32 + lane];
-  g.ncl = prm.geom[64 + lane];
+  const Geo g = make_geo(prm, prm.W, lane, 32);
   for (int game = blockIdx.x * GRL_WARPS_PER_CTA + warp; game < prm.B; game += gridDim.x * GRL_WARPS_PER_CTA) {
     const uint32_t *s = prm.state + (size_t)game * L.slab_words;
     const uint32_t *stt = prm.statics + (size_t)game * L.static_words;
@@ -1565,8 +1571,8 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32) grl_sample_kernel(cons
     const uint32_t M = act ? stt[lane] : 0u;
     const uint32_t flags = s[GRL_HDR_FLAGS];
     const uint32_t turn = s[GRL_HDR_TURN];
-    uint32_t gt1 = army_gt1_mask(army, NW, N, lane);
-    DirMasks dm = dir_targets(M, g);
+    uint32_t gt1 = army_gt1_mask<32>(army, NW, N, g);
+    DirMasks dm = dir_targets<32>(M, g);
     if (lane < prm.A) out[(size_t)game * prm.A + lane] = make_uint2(0u, 0u);
     __syncwarp();
     if (flags & GRL_FLAG_OVER) continue;
@@ -1576,7 +1582,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32) grl_sample_kernel(cons
         uint32_t own = act ? s[L.off_own + p * NW + lane] : 0u;
         uint32_t lst = act ? s[L.off_list + p * NW + lane] : 0u;
         uint32_t src = ((flags >> p) & 1u) ? (lst & own & gt1) : 0u;
-        PackedAction a = sample_policy_action(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn, g);
+        PackedAction a = sample_policy_action<32>(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn, g);
         if (lane == 0) out[(size_t)game * prm.A + p] = make_uint2(a.lo, a.hi);
       }
     }
@@ -1604,49 +1610,28 @@ static inline int grid_for(int items_per_cta_warps, int n) {
   return ctas < 1 ? 1 : ctas;
 }
 
-size_t grl_turn_smem_bytes(const GrlLayout &L, int TW, int TH, int PT) {
-  return (size_t)GRL_WARPS_PER_CTA *
-         (size_t)(2 * (L.slab_words + L.static_words) + 2 * GRL_MAX_ACTIONS + grl_obs_scratch_words(TW, TH, PT, L.NW)) * 4u;
+static size_t grl_turn_smem_bytes(const GrlLayout &L, int TW, int TH, int PT, int LG) {
+  const bool snap = GRL_DIRTY_WB && (LG == 32 || GRL_PACKED_SNAPSHOT);
+  const int per_game = (snap ? 2 : 1) * L.slab_words + L.static_words + 2 * GRL_MAX_ACTIONS;
+  return (size_t)GRL_WARPS_PER_CTA * (size_t)((32 / LG) * per_game + grl_obs_scratch_words(TW, TH, PT, L.NW)) * 4u;
 }
 
-// persistent launch: as many CTAs as stay resident (occupancy x SM count), each warp loops over games
-template <typename K>
-static int persistent_grid(K kern, size_t smem, int B) {
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (sm_count <= 0) sm_count = 148;
-  }
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GRL_WARPS_PER_CTA * 32, smem) != cudaSuccess || per_sm < 1)
-    per_sm = 1;
-  int need = (B + GRL_WARPS_PER_CTA - 1) / GRL_WARPS_PER_CTA;
-  int grid = sm_count * per_sm;
-  return need < grid ? (need < 1 ? 1 : need) : grid;
-}
-
-template <int PT, int TW, int TH, bool S, bool O>
+template <int PT, int TW, int TH, int LG, bool S, bool O>
 static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream) {
-  size_t smem = grl_turn_smem_bytes(prm.L, TW, TH, PT);
-  auto kern = grl_turn_kernel<PT, TW, TH, S, O>;
-  static size_t tuned_smem = ~(size_t)0;  // per instantiation: attribute + resident-CTA count
-  static int resident = 0;
+  size_t smem = grl_turn_smem_bytes(prm.L, TW, TH, PT, LG);
+  auto kern = grl_turn_kernel<PT, TW, TH, LG, S, O>;
+  static size_t tuned_smem = ~(size_t)0;  // per instantiation
   if (tuned_smem != smem) {
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    resident = persistent_grid(kern, smem, 1 << 30);
     tuned_smem = smem;
   }
-  int need = (prm.game_end - prm.game0 + GRL_WARPS_PER_CTA - 1) / GRL_WARPS_PER_CTA;
-#if GRL_PERSISTENT
-  int grid = need < resident ? need : resident;
-#else
-  int grid = need;  // one game per warp: CTAs of a wave move through the phases together
-#endif
+  // a CTA steps GRL_WARPS_PER_CTA * (32 / LG) games; CTAs of a wave move through the load -> turn ->
+  // store phases out of step with each other, which keeps the observation store stream busy
+  const int per_cta = GRL_WARPS_PER_CTA * (32 / LG);
+  int grid = (prm.game_end - prm.game0 + per_cta - 1) / per_cta;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(grid < 1 ? 1 : grid);
@@ -1667,22 +1652,42 @@ static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream) {
   return cudaLaunchKernelEx(&cfg, kern, prm);
 }
 
-template <int PT, int TW, int TH>
+template <int PT, int TW, int TH, int LG>
 static cudaError_t launch_turn_g(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream) {
-  if (do_step && do_out) return launch_turn_t<PT, TW, TH, true, true>(prm, stream);
-  if (do_step) return launch_turn_t<PT, TW, TH, true, false>(prm, stream);
-  return launch_turn_t<PT, TW, TH, false, true>(prm, stream);
+  if (do_step && do_out) return launch_turn_t<PT, TW, TH, LG, true, true>(prm, stream);
+  if (do_step) return launch_turn_t<PT, TW, TH, LG, true, false>(prm, stream);
+  return launch_turn_t<PT, TW, TH, LG, false, true>(prm, stream);
 }
 
-// the BASELINE board sizes get kernels with the geometry baked in; everything else is generic
+// the BASELINE board sizes get kernels with the geometry baked in and the lane group sized to the
+// board (10x10: 4 words -> 8 games per warp; 15x15: 8 words -> 4 games per warp); everything else is
+// generic with one game per warp.  GRL_LANES_PER_GAME=32 (environment) forces one game per warp.
 template <int PT>
 static cudaError_t launch_turn_p(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream) {
-  if (PT <= 4) {
-    if (prm.W == 20 && prm.H == 20) return launch_turn_g<PT, 20, 20>(prm, do_step, do_out, stream);
-    if (prm.W == 15 && prm.H == 15) return launch_turn_g<PT, 15, 15>(prm, do_step, do_out, stream);
-    if (prm.W == 10 && prm.H == 10) return launch_turn_g<PT, 10, 10>(prm, do_step, do_out, stream);
+  const int lpg = prm.lanes_per_game;
+  if constexpr (PT <= 4) {
+    if (prm.W == 20 && prm.H == 20) {
+      if (lpg == 16) return launch_turn_g<PT, 20, 20, 16>(prm, do_step, do_out, stream);
+      return launch_turn_g<PT, 20, 20, 32>(prm, do_step, do_out, stream);
+    }
+    // measured on B200 (profiles/r1_variants.md): 10x10 is fastest with 8 lanes per game at every batch size;
+    // 15x15 with 8 lanes from ~128 K games up, with one game per warp below that (fewer, longer-lived CTAs
+    // cost more in the last wave than the turn phase gains)
+    const int games = prm.game_end - prm.game0;
+    if (prm.W == 15 && prm.H == 15) {
+      const int pick = lpg ? lpg : (games >= 131072 ? 8 : 32);
+      if (pick == 8) return launch_turn_g<PT, 15, 15, 8>(prm, do_step, do_out, stream);
+      if (pick == 16) return launch_turn_g<PT, 15, 15, 16>(prm, do_step, do_out, stream);
+      return launch_turn_g<PT, 15, 15, 32>(prm, do_step, do_out, stream);
+    }
+    if (prm.W == 10 && prm.H == 10) {
+      const int pick = lpg ? lpg : 8;
+      if (pick == 4) return launch_turn_g<PT, 10, 10, 4>(prm, do_step, do_out, stream);
+      if (pick == 8) return launch_turn_g<PT, 10, 10, 8>(prm, do_step, do_out, stream);
+      return launch_turn_g<PT, 10, 10, 32>(prm, do_step, do_out, stream);
+    }
   }
-  return launch_turn_g<PT, 0, 0>(prm, do_step, do_out, stream);
+  return launch_turn_g<PT, 0, 0, 32>(prm, do_step, do_out, stream);
 }
 
 static int player_template(int P) { return P <= 2 ? 2 : (P <= 4 ? 4 : 8); }

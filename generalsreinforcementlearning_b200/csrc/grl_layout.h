@@ -88,6 +88,7 @@ struct GrlKParams {
   int env_id_base;
   int use_tma;
   int prefetch_dist;
+  int lanes_per_game;       // host-side launch hint: 32 forces one game per warp (0 = sized to the board)
   float rw[11];
   // host-side launch hints (not read by device code)
   unsigned long long l2_window_bytes;
