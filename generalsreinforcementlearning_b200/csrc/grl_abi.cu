@@ -67,10 +67,10 @@ struct grl_env {
   int host_threads = 1;
   // host-buffer calls split the batch into sub-ranges on these streams so that the copies of one
   // sub-range overlap the kernel of another (created on first use)
-  static constexpr int kPipe = 4;
-  cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_start = nullptr, ev_done[kPipe] = {nullptr, nullptr, nullptr, nullptr};
-  int pipe_chunks = 4;  // GRL_PIPE_CHUNKS=1 disables the pipelining
+  static constexpr int kPipe = 8;
+  cudaStream_t pipe[kPipe] = {};
+  cudaEvent_t ev_start = nullptr, ev_done[kPipe] = {};
+  int pipe_chunks = 6;  // GRL_PIPE_CHUNKS=1 disables the pipelining (e2e: 160 M env-steps/s at 1, 169 M at 4, 170 M at 6-8)
 };
 
 namespace {

@@ -607,6 +607,28 @@ class GameServer:
             r.newest_experience.CopyFrom(xs[-1].collected_at)
         return r
 
+    def ingest_records(self, records, width: int, height: int, game_prefix: str = "env") -> int:
+        """Feed device-gathered experience records (``sharding.pack_experience`` /
+        ``gather_experience`` dicts of tensors) into the stream store, as the per-game
+        collectors do for served games.  ``mask_bits`` must hold the serializer mask bytes
+        ([R, 4*W*H], GRL_MASK_SERIALIZER_UDLR).  Returns the number of records added."""
+        host = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in records.items()}
+        n = int(host["action"].shape[0])
+        out = []
+        for i in range(n):
+            x = experience.Experience(experience_id=str(uuid.uuid4()), game_id=f"{game_prefix}-{int(host['env_id'][i])}",
+                                      player_id=int(host["player"][i]), turn=int(host["turn"][i]), action=int(host["action"][i]),
+                                      reward=float(host["reward"][i]), done=bool(host["done"][i]))
+            x.state.shape.extend([9, height, width])
+            x.state.data.extend(host["state"][i].reshape(-1).tolist())
+            x.next_state.shape.extend([9, height, width])
+            x.next_state.data.extend(host["next_state"][i].reshape(-1).tolist())
+            x.action_mask.extend(host["mask_bits"][i].reshape(-1).astype(bool).tolist())
+            _now(x.collected_at)
+            out.append(x)
+        self.store.add(out)
+        return n
+
     # ------------------------------------------------------------------ plumbing
     def add_to_server(self, server: grpc.Server) -> None:
         for sname, methods in SERVICES.items():

@@ -81,3 +81,34 @@ def test_two_gpu_shards_and_nccl_gather(cuda_lib, tmp_path):
     assert np.array_equal(last["reward"].view(np.uint32), out["reward"][env, ply].view(np.uint32))
     assert np.allclose(last["next_state_sum"], out["obs"][env, ply].sum(axis=(1, 2, 3)))
     assert np.array_equal(r0["stats"], r1["stats"]) and np.array_equal(r0["stats"], e.stats().astype(np.int64))
+
+
+def _selfplay_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import selfplay_experience
+
+    selfplay_experience.run(rank, world, games_per_gpu=1024, turns=6, sample=40,
+                            out_path=os.path.join(tmp, "selfplay.json") if rank == 0 else None)
+    import torch.distributed as dist
+
+    dist.destroy_process_group()
+
+
+def test_selfplay_experience_to_grpc_learner(cuda_lib, tmp_path):
+    """BASELINE config 5 in small: self-play shards -> NCCL gather -> gRPC batches of 32 on the learner rank."""
+    import json
+
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 2)
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_selfplay_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = json.load(open(os.path.join(tmp_path, "selfplay.json")))
+    assert r["env_steps"] == world * 1024 * 6
+    assert r["gathered"] == world * 40 * 6          # the per-turn sample of every rank arrived
+    assert r["streamed"] == r["gathered"]           # and all of it went out through the ExperienceService
+    assert r["full_batches"] >= r["gathered"] // 32 - 2
