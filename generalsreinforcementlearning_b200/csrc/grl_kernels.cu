@@ -55,6 +55,10 @@
 #ifndef GRL_PACKED_SNAPSHOT
 #define GRL_PACKED_SNAPSHOT 0
 #endif
+// GRL_OBS_LUT: nibble -> float4 through the shared-memory table (1) or eight ALU selects (0)
+#ifndef GRL_OBS_LUT
+#define GRL_OBS_LUT 1
+#endif
 #ifndef GRL_OBS_CHUNK_MAJOR
 #define GRL_OBS_CHUNK_MAJOR 0  // 1: the round-1a tile-chunk-major observation loop (comparison builds)
 #endif
@@ -508,8 +512,13 @@ __device__ __forceinline__ void obs_plane_major(const GrlKParams &prm, const Sla
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
           if (32 * c + lane < NQ) {
+#if GRL_OBS_LUT
             const uint32_t idx16 = (c == 0 ? (ch[k] << 4) : (ch[k] >> (4 * c - 4))) & 0xf0u;
             float4 val = *reinterpret_cast<const float4 *>(lutb + idx16);
+#else
+            const uint32_t nb = ch[k] >> (4 * c);
+            float4 val = make_float4((nb & 1u) ? 1.f : 0.f, (nb & 2u) ? 1.f : 0.f, (nb & 4u) ? 1.f : 0.f, (nb & 8u) ? 1.f : 0.f);
+#endif
             if (k < 2) {
               val.x *= f[c][0];
               val.y *= f[c][1];

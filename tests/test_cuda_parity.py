@@ -313,3 +313,40 @@ def test_army_overflow_is_flagged_not_wrapped(cuda_lib):
     t = e.get_state()
     assert t["army"][0, 0] == 65535
     assert t["step_error"][0] == _abi.STEP_ARMY_OVERFLOW
+
+
+@pytest.mark.parametrize("W,H,P,LG", [(10, 10, 2, 4), (10, 10, 4, 4), (10, 10, 2, 8), (10, 10, 3, 8), (10, 10, 2, 32),
+                                       (15, 15, 2, 8), (15, 15, 4, 8), (15, 15, 3, 16), (15, 15, 2, 32),
+                                       (20, 20, 2, 16), (20, 20, 4, 16)])
+def test_lane_group_variants(cuda_lib, oracle_lib, W, H, P, LG, monkeypatch):
+    """Every compiled lanes-per-game instantiation (GRL_LANES_PER_GAME), with a batch that leaves the
+    last warp partly filled, invalid moves (error turns) mixed in, and the in-kernel policy."""
+    monkeypatch.setenv("GRL_LANES_PER_GAME", str(LG))
+    gc, _ = rollout_compare(cuda_lib, oracle_lib, W, H, P, B=37, T=60, seed=LG * 10 + P, err_rate=0.05)
+    assert gc.stats()[1] > 0, "the run must contain error turns"
+    rollout_compare(cuda_lib, oracle_lib, W, H, P, B=5, T=40, seed=LG + P, policy_in_kernel=True)
+
+
+def test_lane_groups_dense_endgames(cuda_lib, oracle_lib, monkeypatch):
+    """Packed groups through eliminations, tile turnover and game endings: dense 10x10 battles where each
+    group of a warp is at a different stage (some games over, some aborting, some eliminating)."""
+    for LG in (4, 8):
+        monkeypatch.setenv("GRL_LANES_PER_GAME", str(LG))
+        W = H = 10
+        P, B = 4, 29
+        rng = np.random.default_rng(LG)
+        s = blank_state(W, H, P, B)
+        for c in range(B):
+            owners = rng.integers(-1, P, W * H)
+            s["owner"][c] = owners
+            s["army"][c] = np.where(owners >= 0, rng.integers(1, 60, W * H), rng.integers(0, 3, W * H))
+            s["type"][c] = rng.choice([NORMAL, NORMAL, NORMAL, CITY, MOUNTAIN], W * H)
+            for p in range(P):  # one general each, weakly defended so captures happen
+                i = int(rng.integers(0, W * H))
+                s["owner"][c, i], s["army"][c, i], s["type"][c, i] = p, int(rng.integers(1, 4)), GENERAL
+            mnt = s["type"][c] == MOUNTAIN
+            s["owner"][c][mnt], s["army"][c][mnt] = -1, 0
+        full_stats(s)
+        full_fog(s, W, H)
+        gc, _ = rollout_compare(cuda_lib, oracle_lib, W, H, P, B=B, T=150, seed=77 + LG, init=s, err_rate=0.02)
+        assert gc.stats()[2] > 0, "some games must finish"

@@ -25,10 +25,9 @@ PHASES = [
     ("stats / game over", "---- end of turn: stats, game over"),
     ("reward", "---- reward: CalculateRewardWithConfig"),
     ("slab write-back", "---- write the state back"),
-    ("scalar read-outs", "---- read-outs ---"),
+    ("scalar read-outs", "---- scalar read-outs"),
     ("legal mask", "// engine legal-action mask, packed"),
     ("observation planes", "// observation planes: Serializer.StateToTensor"),
-    ("tail", "generic-proxy accesses precede its next bulk refill"),
 ]
 
 
