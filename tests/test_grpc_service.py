@@ -292,3 +292,84 @@ def test_reference_generated_stubs_talk_to_this_server(server):
     # one army moved: an empty tile is captured with 1, a defended one (a 40-army city) loses 1
     assert st.turn == 1 and after == ((0, 1) if before[1] == 0 else (before[0], before[1] - 1))
     ch.close()
+
+
+# ---- the reference's own server tests, transliterated (internal/grpc/gameserver/*_test.go) ------
+def test_reference_server_kats(oracle_lib):
+    srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=4, seed=5, max_games=7)
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    stub = Stub(ch, GAME)
+    try:
+        # server_test.go:50-82 TestCreateGame
+        r = stub.CreateGame(game.CreateGameRequest(config=game.GameConfig(width=20, height=20, max_players=4, fog_of_war=True)))
+        assert r.game_id and (r.config.width, r.config.height, r.config.max_players) == (20, 20, 4)
+        r2 = stub.CreateGame(game.CreateGameRequest())
+        assert r2.game_id and r2.game_id != r.game_id
+        assert (r2.config.width, r2.config.height, r2.config.max_players) == (20, 20, 2)
+        # server_test.go:84-151 TestJoinGame
+        gid = stub.CreateGame(game.CreateGameRequest(config=game.GameConfig(width=20, height=20, max_players=2))).game_id
+        j = stub.JoinGame(game.JoinGameRequest(game_id=gid, player_name="player-1"))
+        assert j.player_id == 0 and j.player_token and j.initial_state.game_id == gid
+        assert j.initial_state.status == common.GAME_STATUS_WAITING
+        j2 = stub.JoinGame(game.JoinGameRequest(game_id=gid, player_name="player-1"))
+        assert (j2.player_id, j2.player_token) == (0, j.player_token)
+        j3 = stub.JoinGame(game.JoinGameRequest(game_id=gid, player_name="player-2"))
+        assert j3.player_id == 1 and j3.player_token and j3.player_token != j.player_token
+        assert j3.initial_state.status == common.GAME_STATUS_IN_PROGRESS
+        with pytest.raises(grpc.RpcError) as e:
+            stub.JoinGame(game.JoinGameRequest(game_id=gid, player_name="player-3"))
+        assert "cannot join game" in e.value.details()
+        with pytest.raises(grpc.RpcError) as e:
+            stub.JoinGame(game.JoinGameRequest(game_id="non-existent", player_name="player-4"))
+        assert "not found" in e.value.details()
+        # server_test.go:153-211 TestGetGameState: a lobby game shows the placeholder board
+        g10 = stub.CreateGame(game.CreateGameRequest(config=game.GameConfig(width=10, height=10, max_players=2))).game_id
+        jj = stub.JoinGame(game.JoinGameRequest(game_id=g10, player_name="test-player"))
+        st = stub.GetGameState(game.GetGameStateRequest(game_id=g10, player_id=jj.player_id, player_token=jj.player_token)).state
+        assert st.game_id == g10 and st.status == common.GAME_STATUS_WAITING
+        assert (st.board.width, st.board.height, len(st.board.tiles)) == (10, 10, 100)
+        with pytest.raises(grpc.RpcError) as e:
+            stub.GetGameState(game.GetGameStateRequest(game_id=g10, player_id=jj.player_id, player_token="invalid-token"))
+        assert "invalid player credentials" in e.value.details()
+        with pytest.raises(grpc.RpcError) as e:
+            stub.GetGameState(game.GetGameStateRequest(game_id="non-existent", player_id=0, player_token="t"))
+        assert "not found" in e.value.details()
+        # idempotency_test.go:98-147 TestIdempotencyForErrors: a lobby game refuses actions, and caches the refusal
+        a0 = game.Action(turn_number=0)
+        e1 = stub.SubmitAction(game.SubmitActionRequest(game_id=g10, player_id=0, player_token=jj.player_token, action=a0,
+                                                        idempotency_key="error-test-key"))
+        e2 = stub.SubmitAction(game.SubmitActionRequest(game_id=g10, player_id=0, player_token=jj.player_token, action=a0,
+                                                        idempotency_key="error-test-key"))
+        assert not e1.success and e1.error_code == common.ERROR_CODE_INVALID_PHASE
+        assert (e2.success, e2.error_code, e2.error_message) == (e1.success, e1.error_code, e1.error_message)
+        # idempotency_test.go:14-96 TestIdempotencyWithSameKey + :149-200 TestIdempotencyAcrossPlayers
+        jk = stub.JoinGame(game.JoinGameRequest(game_id=g10, player_name="Player2"))
+        wait = game.Action(type=common.ACTION_TYPE_UNSPECIFIED, turn_number=0)
+        s1 = stub.SubmitAction(game.SubmitActionRequest(game_id=g10, player_id=0, player_token=jj.player_token, action=wait,
+                                                        idempotency_key="shared-key-123"))
+        s2 = stub.SubmitAction(game.SubmitActionRequest(game_id=g10, player_id=0, player_token=jj.player_token, action=wait,
+                                                        idempotency_key="shared-key-123"))
+        assert s1.success and (s2.success, s2.error_code, s2.error_message, s2.next_turn_number) == (
+            s1.success, s1.error_code, s1.error_message, s1.next_turn_number)
+        s3 = stub.SubmitAction(game.SubmitActionRequest(game_id=g10, player_id=1, player_token=jk.player_token, action=wait,
+                                                        idempotency_key="shared-key-123"))
+        assert s3.success, "different players may use the same idempotency key"
+        st = stub.GetGameState(game.GetGameStateRequest(game_id=g10, player_id=0, player_token=jj.player_token)).state
+        assert st.turn == 1, "the game advanced only one turn"
+        # stream_test.go:177-212
+        with pytest.raises(grpc.RpcError) as e:
+            next(stub.StreamGame(game.StreamGameRequest(game_id=g10, player_id=999, player_token="invalid-token")))
+        assert "invalid player credentials" in e.value.details()
+        with pytest.raises(grpc.RpcError) as e:
+            next(stub.StreamGame(game.StreamGameRequest(game_id="non-existent-game", player_id=0, player_token="token")))
+        assert "not found" in e.value.details()
+        # max_games_test.go:13-46 (this server was started with max_games=7; 4 exist)
+        for _ in range(3):
+            assert stub.CreateGame(game.CreateGameRequest()).game_id
+        with pytest.raises(grpc.RpcError) as e:
+            stub.CreateGame(game.CreateGameRequest())
+        assert e.value.code() == grpc.StatusCode.RESOURCE_EXHAUSTED and "server at capacity" in e.value.details()
+    finally:
+        ch.close()
+        srv.stop(0)
+        gs.close()
