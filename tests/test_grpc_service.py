@@ -373,3 +373,40 @@ def test_reference_server_kats(oracle_lib):
         ch.close()
         srv.stop(0)
         gs.close()
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/python/experience_stream_client.py"), reason="reference client not on this box")
+def test_reference_experience_stream_client_consumes_this_server(server):
+    """The reference's OWN trainer-side client (python/experience_stream_client.py, unmodified) streams
+    batches from this server and decodes them into the numpy records its trainers use."""
+    gs, stub, _, _, port = server
+    gid, js = _start(stub, 6, 6, collect=True)
+    rng = np.random.default_rng(11)
+    for turn in range(10):
+        for j in js:
+            st = stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)).state
+            req = game.SubmitActionRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)
+            a = _legal_action(st, rng, st.turn)
+            if a is not None:
+                req.action.CopyFrom(a)
+            assert stub.SubmitAction(req).success
+    sys.path.insert(0, "/root/reference/python")
+    try:
+        from experience_stream_client import ExperienceConfig, ExperienceStreamClient
+    finally:
+        sys.path.pop(0)
+    client = ExperienceStreamClient(ExperienceConfig(server_address=f"127.0.0.1:{port}", game_ids=[gid], batch_size=8, follow=True))
+    client.connect()
+    client.start_streaming()
+    try:
+        batch = client.get_batch(16, timeout=10.0)
+    finally:
+        client.stop_event.set()
+        client.disconnect()
+    assert len(batch) == 16
+    for x in batch:
+        assert x["game_id"] == gid and x["state"].shape == (9, 6, 6) and x["next_state"].shape == (9, 6, 6)
+        assert x["state"].dtype == np.float32 and x["action_mask"].shape == (6 * 6 * 4,)
+        assert 0 <= x["action"] < 144 and x["action_mask"][x["action"]], "the recorded action was legal in the recorded state"
+        assert x["state"][7].sum() > 0 and np.array_equal(x["state"][7] + x["state"][8], np.ones((6, 6), np.float32))
+    assert client.get_stats()["total_batches"] >= 2
