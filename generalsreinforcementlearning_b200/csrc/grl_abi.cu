@@ -61,6 +61,7 @@ struct grl_env {
   int use_tma = 1;
   int prefetch_dist = 0;       // > 0: warp of game g prefetches the slab of game g+dist into L2
   int lanes_per_game = 0;      // 32: one game per warp even on small boards (GRL_LANES_PER_GAME)
+  int host_mapgen = 0;         // GRL_HOST_MAPGEN=1: generate seeded maps on the host (comparison / cross-check)
   size_t l2_window_bytes = 0;  // > 0: launch the turn kernel with a persisting-L2 window over the state
   float l2_hit_ratio = 1.0f;
   uint64_t launches = 0;
@@ -542,6 +543,8 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   env->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (hw > 0 ? hw : 1);
   const char *no_tma = getenv("GRL_NO_TMA");
   env->use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
+  const char *hm = getenv("GRL_HOST_MAPGEN");
+  env->host_mapgen = (hm && hm[0] == '1') ? 1 : 0;
   const char *lpg = getenv("GRL_LANES_PER_GAME");
   env->lanes_per_game = lpg ? atoi(lpg) : 0;
   const char *pc = getenv("GRL_PIPE_CHUNKS");
@@ -649,10 +652,63 @@ int grl_mapgen(const grl_config *cfg, int64_t seed, int32_t *owner, int32_t *arm
   return GRL_OK;
 }
 
+// Seeded reset with the maps generated on the device (grl_mapgen_gpu.cu): seeds up, one mapgen
+// thread per map into zero-filled staging slabs, then the turn-0 set-up kernel.  No host mapgen,
+// no slab upload.
+static int reset_seeded_device(grl_env *env, const int32_t *env_ids, int32_t n, const int64_t *seeds) {
+  const grl_config &c = env->cfg;
+  const GrlLayout &L = env->L;
+  if (env_ids)
+    for (int i = 0; i < n; i++)
+      if (env_ids[i] < 0 || env_ids[i] >= c.num_envs) return fail(GRL_ERR_INVALID_ARG, "env id %d out of range", env_ids[i]);
+  if (!env_ids && n > c.num_envs) return fail(GRL_ERR_INVALID_ARG, "n exceeds num_envs");
+  grl::MapParams hp = grl::DefaultMapParams(c.width, c.height, c.num_players, c.city_ratio, c.city_start_army, c.min_general_spacing);
+  GrlMapParams mp = {hp.players, hp.city_ratio, hp.city_start_army, hp.spacing, hp.veins, hp.min_vein, hp.max_vein};
+  const int chunk = 262144;
+  for (int c0 = 0; c0 < n; c0 += chunk) {
+    const int cn = std::min(chunk, n - c0);
+    void *d_slabs = nullptr, *d_statics = nullptr, *d_seeds = nullptr;
+    int st;
+    const size_t slab_bytes = (size_t)cn * L.slab_words * 4, stat_bytes = (size_t)cn * L.static_words * 4;
+    if ((st = ensure(env, SL_MISC, slab_bytes + 16, &d_slabs))) return st;
+    if ((st = ensure(env, SL_MISC2, stat_bytes + (size_t)cn * 4 + 16, &d_statics))) return st;
+    if ((st = ensure(env, SL_ACTIONS, (size_t)cn * 8 + 16, &d_seeds))) return st;
+    int *d_failed = reinterpret_cast<int *>(reinterpret_cast<char *>(d_seeds) + (size_t)cn * 8);
+    CUDA_TRY(cudaMemsetAsync(d_slabs, 0, slab_bytes, env->stream));
+    CUDA_TRY(cudaMemsetAsync(d_statics, 0, stat_bytes, env->stream));
+    CUDA_TRY(cudaMemsetAsync(d_failed, 0, 4, env->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_seeds, seeds + c0, (size_t)cn * 8, cudaMemcpyHostToDevice, env->stream));
+    int32_t *d_ids = nullptr;
+    std::vector<int32_t> ids;
+    if (env_ids || c0 != 0) {
+      const int32_t *src = env_ids ? env_ids + c0 : nullptr;
+      if (!src) {
+        ids.resize(cn);
+        for (int i = 0; i < cn; i++) ids[i] = c0 + i;
+        src = ids.data();
+      }
+      d_ids = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(d_statics) + stat_bytes);
+      CUDA_TRY(cudaMemcpyAsync(d_ids, src, (size_t)cn * 4, cudaMemcpyHostToDevice, env->stream));
+    }
+    CUDA_TRY(grl_launch_mapgen(L, c.width, c.height, mp, (const long long *)d_seeds, cn, (uint32_t *)d_slabs, (uint32_t *)d_statics,
+                               d_failed, env->stream));
+    GrlKParams prm = base_params(env);
+    CUDA_TRY(grl_launch_reset(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, cn, env->stream));
+    env->launches += 2;
+    int failed = 0;
+    CUDA_TRY(cudaMemcpyAsync(&failed, d_failed, 4, cudaMemcpyDeviceToHost, env->stream));
+    CUDA_TRY(cudaStreamSynchronize(env->stream));
+    if (failed) return fail(GRL_ERR_MAPGEN, "unable to place a general (seed %lld)", (long long)seeds[c0 + failed - 1]);
+  }
+  return GRL_OK;
+}
+
 int grl_reset_seeded(grl_env *env, const int32_t *env_ids, int32_t n, const int64_t *seeds) {
   if (!env || !seeds || n < 0) return fail(GRL_ERR_INVALID_ARG, "bad argument");
   if (n == 0) return GRL_OK;
   CUDA_TRY(cudaSetDevice(env->cfg.device));
+  // maps are generated on the device unless the batch is tiny or GRL_HOST_MAPGEN=1 asks for the host path
+  if (!env->host_mapgen && n >= 64) return reset_seeded_device(env, env_ids, n, seeds);
   const grl_config &c = env->cfg;
   const int N = env->N;
   grl::MapParams mp = grl::DefaultMapParams(c.width, c.height, c.num_players, c.city_ratio, c.city_start_army, c.min_general_spacing);

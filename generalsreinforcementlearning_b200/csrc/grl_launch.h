@@ -18,3 +18,11 @@ cudaError_t grl_launch_state_hash(const GrlKParams &prm, uint64_t *out, cudaStre
 cudaError_t grl_launch_buffer_hash(const uint32_t *buf, size_t row_words, int rows, uint64_t *out, cudaStream_t stream);
 cudaError_t grl_launch_stats(const GrlKParams &prm, unsigned long long *out, cudaStream_t stream);
 cudaError_t grl_launch_mark_over(const GrlKParams &prm, cudaStream_t stream);
+
+// device-side map generation (grl_mapgen_gpu.cu); mirrors grl::MapParams
+#define GRL_MAX_PLAYERS_DEV 8
+struct GrlMapParams {
+  int players, city_ratio, city_start_army, spacing, veins, min_vein, max_vein;
+};
+cudaError_t grl_launch_mapgen(const GrlLayout &L, int W, int H, const GrlMapParams &mp, const long long *seeds, int n,
+                              uint32_t *slabs, uint32_t *statics, int *failed, cudaStream_t stream);

@@ -1,0 +1,212 @@
+// grl_mapgen_gpu.cu — the reference's procedural maps generated ON THE DEVICE, one thread per map.
+//
+// Host map generation (grl_mapgen.cpp) costs ~3 us of wall time per 20x20 map on 16 cores — most of
+// it Go's math/rand seeding, 1,841 Lehmer steps per seed — which for 65,536 games is as long as
+// stepping the whole 500-turn episode.  The algorithm is embarrassingly parallel over maps and
+// every draw is integer arithmetic, so the same restatement of mapgen/generator.go:25-253 and of
+// go1.24 math/rand runs here with the generator state (607 x uint64) in per-thread local memory.
+// A thread writes its map straight into the staging slabs the reset kernel consumes (ownership
+// bit, uint16 armies, terrain masks), so a seeded reset never touches the host.
+// Bit-identical to the host path by construction; tests compare the two and the oracle.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "grl_launch.h"
+#include "grl_layout.h"
+
+namespace {
+
+constexpr int kLen = 607;
+constexpr int kTap = 273;
+constexpr int32_t kInt32Max = 2147483647;
+
+__constant__ int64_t c_cooked[kLen] = {
+#include "go_rng_cooked.inc"
+};
+
+struct GoRandDev {  // rng.go (*rngSource) + rand.go
+  uint64_t vec[kLen];
+  int tap, feed;
+
+  __device__ static int32_t lehmer(int32_t x) {  // 48271 * x mod (2^31 - 1), Schrage
+    const int32_t hi = x / 44488, lo = x % 44488;
+    x = 48271 * lo - 3399 * hi;
+    return x < 0 ? x + kInt32Max : x;
+  }
+  __device__ void seed(int64_t s) {
+    tap = 0;
+    feed = kLen - kTap;
+    s %= kInt32Max;
+    if (s < 0) s += kInt32Max;
+    if (s == 0) s = 89482311;
+    int32_t x = (int32_t)s;
+    for (int i = -20; i < kLen; ++i) {
+      x = lehmer(x);
+      if (i < 0) continue;
+      uint64_t u = (uint64_t)x << 40;
+      x = lehmer(x);
+      u ^= (uint64_t)x << 20;
+      x = lehmer(x);
+      u ^= (uint64_t)x;
+      vec[i] = u ^ (uint64_t)c_cooked[i];
+    }
+  }
+  __device__ uint64_t u64() {
+    if (--tap < 0) tap += kLen;
+    if (--feed < 0) feed += kLen;
+    uint64_t x = vec[feed] + vec[tap];
+    vec[feed] = x;
+    return x;
+  }
+  __device__ int64_t int63() { return (int64_t)(u64() & 0x7fffffffffffffffULL); }
+  __device__ int32_t int31() { return (int32_t)(int63() >> 32); }
+  __device__ uint32_t u32() { return (uint32_t)(int63() >> 31); }
+  __device__ int intn(int n) {  // rand.go Intn, n <= 2^31-1
+    if ((n & (n - 1)) == 0) return int31() & (n - 1);
+    const int32_t limit = (int32_t)((1u << 31) - 1 - (1u << 31) % (uint32_t)n);
+    int32_t v = int31();
+    while (v > limit) v = int31();
+    return v % n;
+  }
+  __device__ int32_t lemire(int32_t n) {  // rand.go int31n, used by Shuffle
+    uint32_t v = u32();
+    uint64_t prod = (uint64_t)v * (uint64_t)n;
+    uint32_t low = (uint32_t)prod;
+    if (low < (uint32_t)n) {
+      const uint32_t thresh = (uint32_t)(-n) % (uint32_t)n;
+      while (low < thresh) {
+        v = u32();
+        prod = (uint64_t)v * (uint64_t)n;
+        low = (uint32_t)prod;
+      }
+    }
+    return (int32_t)(prod >> 32);
+  }
+};
+
+struct MapDev {  // occupancy as linear bitmasks (tile t = bit t&31 of word t>>5), N <= 1024
+  uint32_t taken[32];  // anything that is not a neutral normal tile
+  uint32_t *M, *C, *G;  // terrain masks in the staging static slab
+  uint16_t *army;
+  __device__ bool open(int t) const { return !((taken[t >> 5] >> (t & 31)) & 1u); }
+  __device__ void take(int t) { taken[t >> 5] |= 1u << (t & 31); }
+};
+
+__device__ bool far_enough(int W, int idx, const int *seats, int n, int spacing) {
+  const int x = idx % W, y = idx / W;
+  for (int k = 0; k < n; ++k) {
+    const int ox = seats[k] % W, oy = seats[k] / W;
+    if (abs(x - ox) + abs(y - oy) < spacing) return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+// staging buffers must be zero-filled; one thread writes map i into slab i / static slab i
+__global__ void __launch_bounds__(128)
+    grl_mapgen_kernel(GrlLayout L, int W, int H, GrlMapParams mp, const long long *__restrict__ seeds, int n,
+                      uint32_t *__restrict__ slabs, uint32_t *__restrict__ statics, int *__restrict__ failed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int N = W * H, NW = L.NW;
+  uint32_t *slab = slabs + (size_t)i * L.slab_words;
+  uint32_t *stat = statics + (size_t)i * L.static_words;
+  MapDev b;
+  for (int k = 0; k < 32; ++k) b.taken[k] = 0u;
+  b.M = stat;
+  b.C = stat + NW;
+  b.G = stat + 2 * NW;
+  b.army = reinterpret_cast<uint16_t *>(slab + L.off_army);
+  GoRandDev rng;
+  rng.seed(seeds[i]);
+
+  // generator.go:77-142 mountain veins
+  for (int vein = 0; vein < mp.veins; ++vein) {
+    int cx = -1, cy = -1;
+    for (int attempt = 0; attempt < 100; ++attempt) {
+      const int sx = rng.intn(W);
+      const int sy = rng.intn(H);
+      if (b.open(sy * W + sx)) {
+        cx = sx;
+        cy = sy;
+        break;
+      }
+    }
+    if (cx < 0) continue;
+    int t = cy * W + cx;
+    b.take(t);
+    b.M[t >> 5] |= 1u << (t & 31);
+    int length = mp.min_vein;
+    if (mp.max_vein > mp.min_vein) length += rng.intn(mp.max_vein - mp.min_vein + 1);
+    for (int step = 1; step < length; ++step) {
+      // rand.Shuffle(4, swap) of the directions up, right, down, left, packed 2 bits each
+      uint32_t order = 0xE4u;  // slots 3,2,1,0 = 3,2,1,0
+      for (int a = 3; a > 0; --a) {
+        const int j = rng.lemire(a + 1);
+        const uint32_t va = (order >> (2 * a)) & 3u, vj = (order >> (2 * j)) & 3u;
+        order = (order & ~((3u << (2 * a)) | (3u << (2 * j)))) | (vj << (2 * a)) | (va << (2 * j));
+      }
+      int options[4], n_options = 0;
+      for (int d = 0; d < 4; ++d) {
+        const int dir = (order >> (2 * d)) & 3;
+        const int nx = cx + (dir == 1) - (dir == 3), ny = cy + (dir == 2) - (dir == 0);
+        if (nx < 0 || nx >= W || ny < 0 || ny >= H) continue;
+        if (b.open(ny * W + nx)) options[n_options++] = ny * W + nx;
+      }
+      if (n_options == 0) break;
+      const int pick = rng.intn(n_options);
+      int next = options[0];
+      for (int d = 1; d < 4; ++d)
+        if (d == pick) next = options[d];
+      cx = next % W;
+      cy = next / W;
+      b.take(next);
+      b.M[next >> 5] |= 1u << (next & 31);
+    }
+  }
+  // generator.go:144-164 cities
+  {
+    const int want = N / mp.city_ratio;
+    int placed = 0;
+    for (int attempts = 0; placed < want && attempts < want * 20; ++attempts) {
+      const int x = rng.intn(W);
+      const int y = rng.intn(H);
+      const int t = y * W + x;
+      if (b.open(t)) {
+        b.take(t);
+        b.C[t >> 5] |= 1u << (t & 31);
+        b.army[t] = (uint16_t)mp.city_start_army;
+        ++placed;
+      }
+    }
+  }
+  // generator.go:166-253 generals
+  int seats[GRL_MAX_PLAYERS_DEV];
+  for (int pid = 0; pid < mp.players; ++pid) {
+    int chosen = -1;
+    for (int attempt = 0; attempt < N && chosen < 0; ++attempt) {
+      const int x = rng.intn(W);
+      const int y = rng.intn(H);
+      const int t = y * W + x;
+      if (b.open(t) && far_enough(W, t, seats, pid, mp.spacing)) chosen = t;
+    }
+    for (int t = 0; t < N && chosen < 0; ++t)  // row-major fallback
+      if (b.open(t) && far_enough(W, t, seats, pid, mp.spacing)) chosen = t;
+    if (chosen < 0) {
+      atomicExch(failed, i + 1);
+      return;
+    }
+    b.take(chosen);
+    b.G[chosen >> 5] |= 1u << (chosen & 31);
+    b.army[chosen] = 2;
+    slab[L.off_own + pid * NW + (chosen >> 5)] |= 1u << (chosen & 31);
+    seats[pid] = chosen;
+  }
+}
+
+cudaError_t grl_launch_mapgen(const GrlLayout &L, int W, int H, const GrlMapParams &mp, const long long *seeds, int n,
+                              uint32_t *slabs, uint32_t *statics, int *failed, cudaStream_t stream) {
+  grl_mapgen_kernel<<<(n + 127) / 128, 128, 0, stream>>>(L, W, H, mp, seeds, n, slabs, statics, failed);
+  return cudaGetLastError();
+}
