@@ -94,7 +94,8 @@ def _selfplay_worker(rank, world, port, tmp):
                             out_path=os.path.join(tmp, "selfplay.json") if rank == 0 else None)
     import torch.distributed as dist
 
-    dist.destroy_process_group()
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def test_selfplay_experience_to_grpc_learner(cuda_lib, tmp_path):
