@@ -82,6 +82,7 @@ class GeneralsVecEnv:
         self._winner = torch.zeros(B, dtype=torch.int8, device=dev)
         self._err = torch.zeros(B, dtype=torch.uint8, device=dev)
         self._turns = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._calls = torch.zeros(B, dtype=torch.int32, device=dev)   # step() calls this episode (incl. rejected actions)
         self._episode = np.zeros(B, dtype=np.int64)
         self._base_seed = int(seed)
         self._gen = torch.Generator(device=dev)
@@ -143,6 +144,7 @@ class GeneralsVecEnv:
         ids = np.arange(self.num_envs)
         self.engine.reset_seeded(self._seeds(ids))
         self._turns.zero_()
+        self._calls.zero_()
         self._refresh()
         return self._obs[:, 0], {"valid_actions_mask": self._mask[:, 0].bool(), "turn": self._turns.clone()}
 
@@ -167,10 +169,13 @@ class GeneralsVecEnv:
         # the server rejects an invalid move before the turn runs (action_validator.go:126-127);
         # the turn that did run may still have aborted (step_error) — the client only sees states
         self._turns += valid.to(t.int32)
+        self._calls += 1
         self._refresh()
         st, pv = self._stats.to(t.float64), self._prev_stats.to(t.float64)
         terminated = (self._done != 0) & valid
-        truncated = (self._turns >= self.max_turns) & valid
+        # the episode is cut at max_turns turns; an agent that keeps submitting rejected actions takes no turns, so
+        # it is also cut after max_turns step() calls (what the reference's trainers do: vector_env.py:170)
+        truncated = ((self._turns >= self.max_turns) & valid) | (self._calls >= self.max_turns)
         # _calculate_reward (:499-561), python floats
         shaped = (st[:, 0, 1] - pv[:, 0, 1]) * 1.0 + (st[:, 0, 0] - pv[:, 0, 0]) * 0.01
         shaped = shaped + 50.0 * ((self._prev_stats[:, 1, 2] == 1) & (self._stats[:, 1, 2] == 0)).to(t.float64)
@@ -188,9 +193,18 @@ class GeneralsVecEnv:
             self._episode[ids_np] += 1
             self.engine.reset_seeded(self._seeds(ids_np), ids_np.astype(np.int32))
             self._turns[ids] = 0
+            self._calls[ids] = 0
             self._refresh()
         info["valid_actions_mask"] = self._mask[:, 0].bool()
         return self._obs[:, 0], reward, terminated, truncated, info
+
+    def sample_actions(self, generator=None):
+        """A uniformly random VALID action per env (envs without one get action 0, which is rejected)."""
+        t = self.torch
+        m = self._mask[:, 0].to(t.float32)
+        none = m.sum(1) == 0
+        m[:, 0] += none.to(t.float32)
+        return t.multinomial(m, 1, generator=generator or self._gen).squeeze(1)
 
     def opponent_view(self):
         """Player 1's observation and mask (self-play)."""
