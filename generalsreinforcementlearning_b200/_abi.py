@@ -154,6 +154,7 @@ ABI_FUNCTIONS = {
     "mask": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "visibility": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gym_observe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GymOutputs)]),
+    "gym_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "sample_actions": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "get_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(StatePlanes)]),
     "set_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(StatePlanes)]),

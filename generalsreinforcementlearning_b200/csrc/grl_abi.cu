@@ -839,6 +839,21 @@ int grl_gym_observe(grl_env *env, int32_t max_turns, const grl_gym_outputs *out)
   return GRL_OK;
 }
 
+int grl_gym_encode(grl_env *env, const int64_t *action_idx, int32_t player, int32_t slot, const uint8_t *mask,
+                   int32_t skip_invalid, grl_action *actions, uint8_t *valid) {
+  if (!env || !action_idx || !mask || !actions) return fail(GRL_ERR_INVALID_ARG, "null argument");
+  const grl_config &c = env->cfg;
+  if (player < 0 || player >= c.num_players || slot < 0 || slot >= c.max_actions)
+    return fail(GRL_ERR_INVALID_ARG, "player %d / slot %d out of range", player, slot);
+  CUDA_TRY(cudaSetDevice(c.device));
+  if (!is_device_ptr(action_idx) || !is_device_ptr(mask) || !is_device_ptr(actions) || (valid && !is_device_ptr(valid)))
+    return fail(GRL_ERR_UNSUPPORTED, "grl_gym_encode takes device pointers (it is the device-side glue of the vector env)");
+  GrlKParams prm = base_params(env);
+  CUDA_TRY(grl_launch_gym_encode(prm, (const long long *)action_idx, player, slot, mask, skip_invalid, actions, valid, env->stream));
+  env->launches++;
+  return GRL_OK;
+}
+
 int grl_sample_actions(grl_env *env, uint64_t policy_seed, grl_action *actions) {
   if (!env || !actions) return fail(GRL_ERR_INVALID_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(env->cfg.device));

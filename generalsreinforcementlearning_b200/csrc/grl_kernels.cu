@@ -1507,6 +1507,39 @@ __global__ void grl_gym_kernel(const GrlKParams prm, int max_turns, const float 
   }
 }
 
+// GeneralsEnv._action_index_to_game_action (generals_env.py:389-441), one thread per env
+__global__ void grl_gym_encode_kernel(const GrlKParams prm, const long long *__restrict__ action_idx, int player, int slot,
+                                      const uint8_t *__restrict__ mask, int skip_invalid, uint2 *__restrict__ actions,
+                                      uint8_t *__restrict__ valid) {
+  const int N = prm.N, P = prm.P, W = prm.W, H = prm.H, A = prm.A;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < prm.B; b += gridDim.x * blockDim.x) {
+    const long long a = action_idx[b];
+    const bool ok = a >= 0 && a < (long long)N * 5 && mask[((size_t)b * P + player) * N * 5 + a] != 0;
+    uint2 rec = make_uint2(0u, 0u);
+    if (ok) {
+      const int from_idx = (int)(a / 5), info = (int)(a % 5);
+      const int fx = from_idx % W, fy = from_idx / W;
+      int tx = fx, ty = fy;
+      if (info < 4) {
+        tx = fx + (info == 1) - (info == 3);
+        ty = fy + (info == 2) - (info == 0);
+      } else {  // half move: the first in-bounds direction in the order up, right, down, left
+        if (fy - 1 >= 0) ty = fy - 1;
+        else if (fx + 1 < W) tx = fx + 1;
+        else if (fy + 1 < H) ty = fy + 1;
+        else tx = fx - 1;
+      }
+      const PackedAction pa = pack_action(player, fx, fy, tx, ty, info != 4);
+      rec = make_uint2(pa.lo, pa.hi);
+    }
+    if (!ok && skip_invalid && slot == 0) rec.y |= (uint32_t)GRL_ACTION_FLAG_SKIP_ENV << 24;
+    actions[(size_t)b * A + slot] = rec;
+    if (!ok && skip_invalid && slot != 0)
+      reinterpret_cast<uint8_t *>(actions + (size_t)b * A)[7] |= GRL_ACTION_FLAG_SKIP_ENV;
+    if (valid) valid[b] = ok ? 1 : 0;
+  }
+}
+
 // packed engine mask with the half-move replica: [B][P][rep][words]
 __global__ void grl_mask_replicate_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t rows, int words,
                                           int rep) {
@@ -1752,6 +1785,13 @@ cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *lo
                            cudaStream_t stream) {
   size_t total = (size_t)prm.B * prm.P * prm.N;
   grl_gym_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(prm, max_turns, logtab, obs, mask, stats);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_gym_encode(const GrlKParams &prm, const long long *action_idx, int player, int slot, const uint8_t *mask,
+                                  int skip_invalid, void *actions, uint8_t *valid, cudaStream_t stream) {
+  grl_gym_encode_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm, action_idx, player, slot, mask, skip_invalid,
+                                                                           (uint2 *)actions, valid);
   return cudaGetLastError();
 }
 

@@ -12,6 +12,8 @@ cudaError_t grl_launch_mask_bytes(const GrlKParams &prm, int variant, uint8_t *o
 cudaError_t grl_launch_visibility(const GrlKParams &prm, uint8_t *visible, uint8_t *fog, cudaStream_t stream);
 cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *logtab, float *obs, uint8_t *mask, int32_t *stats,
                            cudaStream_t stream);
+cudaError_t grl_launch_gym_encode(const GrlKParams &prm, const long long *action_idx, int player, int slot, const uint8_t *mask,
+                                  int skip_invalid, void *actions, uint8_t *valid, cudaStream_t stream);
 cudaError_t grl_launch_mask_replicate(const uint32_t *in, uint32_t *out, size_t rows, int words, int rep,
                                       cudaStream_t stream);
 cudaError_t grl_launch_state_hash(const GrlKParams &prm, uint64_t *out, cudaStream_t stream);

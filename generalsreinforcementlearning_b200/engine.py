@@ -94,6 +94,16 @@ class BatchedEngine:
         """Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream)."""
         self.lib.check(self.lib.set_stream(self._h, cuda_stream), "set_stream")
 
+    def use_torch_stream(self) -> None:
+        """Issue this engine's work on torch's CURRENT CUDA stream, so that kernels reading or writing
+        torch tensors are ordered with the torch ops around them (the engine's own stream is
+        non-blocking: without this, hand-offs through device tensors need explicit synchronisation)."""
+        import torch
+
+        if self.lib.prefix == "grl_" and torch.cuda.is_available():
+            with torch.cuda.device(self.cfg.device):
+                self.set_stream(torch.cuda.current_stream().cuda_stream)
+
     # -- reset ---------------------------------------------------------------
     def reset_seeded(self, seeds: Sequence[int], env_ids: Optional[Sequence[int]] = None) -> None:
         seeds = np.ascontiguousarray(seeds, dtype=np.int64)
@@ -159,6 +169,11 @@ class BatchedEngine:
         o = GymOutputs()
         o.obs, o.mask, o.stats = _ptr(obs), _ptr(mask), _ptr(stats)
         self.lib.check(self.lib.gym_observe(self._h, int(max_turns), C.byref(o)), "gym_observe")
+
+    def gym_encode(self, action_idx, player: int, slot: int, mask, skip_invalid: bool, actions, valid) -> None:
+        """Discrete(N*5) indices -> grl_action slots, rejecting indices the gym mask forbids."""
+        self.lib.check(self.lib.gym_encode(self._h, _ptr(action_idx), int(player), int(slot), _ptr(mask),
+                                           1 if skip_invalid else 0, _ptr(actions), _ptr(valid)), "gym_encode")
 
     def sample_actions(self, policy_seed: int, actions=None):
         if actions is None:

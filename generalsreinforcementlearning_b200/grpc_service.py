@@ -89,6 +89,7 @@ class EnginePool:
         self.engine = BatchedEngine(lib, make_config(lib, num_envs=slots, width=W, height=H, num_players=P,
                                                      max_actions=P, device=device, host_threads=1))
         dev = torch.device("cuda", device) if lib.prefix == "grl_" else torch.device("cpu")
+        self.engine.use_torch_stream()
         S, N = slots, self.N
         self.obs = torch.zeros((S, P, 9, H, W), dtype=torch.float32, device=dev)       # StateToTensor of every slot
         self.ser_mask = torch.zeros((S, P, N * 4), dtype=torch.uint8, device=dev)     # serializer mask (U,D,L,R)

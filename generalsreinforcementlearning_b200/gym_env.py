@@ -67,6 +67,7 @@ class GeneralsVecEnv:
                                                      num_players=max_players, device=device, max_actions=max_players,
                                                      fog_of_war=1 if fog_of_war else 0, host_threads=host_threads))
         self.on_device = lib.prefix == "grl_"
+        self.engine.use_torch_stream()   # the env hands tensors between torch ops and engine kernels every step
         self.device = torch.device("cuda", device) if self.on_device else torch.device("cpu")
         self.single_observation_space = Box(0.0, 1.0, (9, board_height, board_width), np.float32)
         self.single_action_space = Discrete(self.N * 5)
@@ -82,15 +83,13 @@ class GeneralsVecEnv:
         self._winner = torch.zeros(B, dtype=torch.int8, device=dev)
         self._err = torch.zeros(B, dtype=torch.uint8, device=dev)
         self._turns = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._valid = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self._opp_draws = 0
         self._calls = torch.zeros(B, dtype=torch.int32, device=dev)   # step() calls this episode (incl. rejected actions)
         self._episode = np.zeros(B, dtype=np.int64)
         self._base_seed = int(seed)
         self._gen = torch.Generator(device=dev)
         self._gen.manual_seed(int(seed))
-        tile = torch.arange(N, device=dev)
-        self._fx, self._fy = (tile % self.W).to(torch.int64), (tile // self.W).to(torch.int64)
-        self._dx = torch.tensor(_DX, device=dev, dtype=torch.int64)
-        self._dy = torch.tensor(_DY, device=dev, dtype=torch.int64)
 
     # ------------------------------------------------------------------ helpers
     def _seeds(self, env_ids: np.ndarray) -> np.ndarray:
@@ -99,41 +98,14 @@ class GeneralsVecEnv:
     def _refresh(self):
         self.engine.gym_observe(self.max_turns, self._obs, self._mask, self._stats)
 
-    def _encode(self, slot: int, action_idx, valid):
-        """Action index -> grl_action bytes of player ``slot`` (generals_env.py:389-441).  A half
-        move goes to the FIRST IN-BOUNDS direction in the order up, right, down, left — the
-        reference's own simplification (:420-427)."""
-        t = self.torch
-        a = action_idx.to(t.int64)
-        tile, info = a // 5, a % 5
-        fx, fy = self._fx[tile], self._fy[tile]
-        half = info == 4
-        d = t.where(half, t.zeros_like(info), info)
-        tx, ty = fx + self._dx[d], fy + self._dy[d]
-        if bool(half.any()):
-            hx, hy = tx.clone(), ty.clone()
-            found = t.zeros_like(half)
-            for k in range(4):
-                nx, ny = fx + _DX[k], fy + _DY[k]
-                ok = (nx >= 0) & (nx < self.W) & (ny >= 0) & (ny < self.H) & ~found
-                hx, hy = t.where(ok, nx, hx), t.where(ok, ny, hy)
-                found |= ok
-            tx, ty = t.where(half, hx, tx), t.where(half, hy, ty)
-        rec = self._actions[:, slot]
-        rec[:, 0] = slot
-        rec[:, 1], rec[:, 2] = fx.to(t.uint8), fy.to(t.uint8)
-        rec[:, 3], rec[:, 4] = (tx & 0xff).to(t.uint8), (ty & 0xff).to(t.uint8)
-        rec[:, 5] = (~half).to(t.uint8)        # Action.half == False -> MoveAll
-        rec[:, 6] = valid.to(t.uint8)          # present
-        rec[:, 7] = 0
-
     def _random_opponent(self):
-        """A uniformly random legal full move of player 1 (generals_env.py:443-497); none if it has none."""
-        t = self.torch
-        m = self._mask[:, 1].view(self.num_envs, self.N, 5)[:, :, :4].reshape(self.num_envs, -1).to(t.float32)
-        has = m.sum(1) > 0
-        pick = t.multinomial(m + (~has).unsqueeze(1).to(t.float32), 1, generator=self._gen).squeeze(1)
-        return (pick // 4) * 5 + pick % 4, has
+        """The reference's default opponent: a uniformly random legal FULL move of player 1
+        (generals_env.py:443-497), none if it has none.  Drawn on the device by the library's
+        counter-based sampler (grl_sample_actions fills one slot per player; slot 0 is overwritten
+        by the agent's action afterwards)."""
+        self._opp_draws += 1
+        self.engine.sample_actions(self._base_seed * 1000003 + self._opp_draws, self._actions)
+        self._actions[:, 1, 5] = 1      # move_all: the random opponent never sends half moves (:483)
 
     # ------------------------------------------------------------------ gym API
     def reset(self, seed: Optional[int] = None, options=None) -> Tuple[Any, Dict[str, Any]]:
@@ -153,17 +125,15 @@ class GeneralsVecEnv:
         player 1 under self-play).  Returns (obs, reward, terminated, truncated, info)."""
         t = self.torch
         B = self.num_envs
-        action = t.as_tensor(action, device=self.device).to(t.int64)
-        valid = self._mask[:, 0].gather(1, action.unsqueeze(1)).squeeze(1).bool()
-        self._encode(0, action, valid)
+        action = t.as_tensor(action, device=self.device).to(t.int64).contiguous()
         if opponent_action is not None:
-            oa = t.as_tensor(opponent_action, device=self.device).to(t.int64)
-            ov = self._mask[:, 1].gather(1, oa.unsqueeze(1)).squeeze(1).bool()
+            oa = t.as_tensor(opponent_action, device=self.device).to(t.int64).contiguous()
+            self.engine.gym_encode(oa, 1, 1, self._mask, False, self._actions, None)
         else:
-            oa, ov = self._random_opponent()
-        self._encode(1, oa, ov)
+            self._random_opponent()
         # an invalid agent action is rejected client-side: that env takes no turn (:226-229)
-        self._actions[:, 0, 7] = (~valid).to(t.uint8) * _abi.ACTION_FLAG_SKIP_ENV
+        self.engine.gym_encode(action, 0, 0, self._mask, True, self._actions, self._valid)
+        valid = self._valid.bool()
         self._prev_stats.copy_(self._stats)
         self.engine.step_fused(self._actions, self.engine.outputs(done=self._done, winner=self._winner, step_error=self._err))
         # the server rejects an invalid move before the turn runs (action_validator.go:126-127);

@@ -239,6 +239,16 @@ int grl_visibility(grl_env *env, uint8_t *visible, uint8_t *fog);
  * max_turns normalises channel 7 (generals_env.py:337). */
 int grl_gym_observe(grl_env *env, int32_t max_turns, const grl_gym_outputs *out);
 
+/* generals_gym action decoding for one player (generals_env.py:389-441): action_idx[b] = tile*5 +
+ * {up,right,down,left,half} becomes a grl_action in slot `slot` of env b (a half move goes to the first
+ * in-bounds direction in the order up,right,down,left — the client's own simplification).  An index whose
+ * entry in `mask` (the [B][P][N*5] plane of grl_gym_observe) is false is REJECTED like the client does
+ * before submitting: the slot is left empty, valid[b] = 0 and, when skip_invalid != 0, slot 0 of that env
+ * gets GRL_ACTION_FLAG_SKIP_ENV.  libgrlcuda.so requires device pointers here (it is the device-side glue
+ * of the vector env); the oracle takes host pointers. */
+int grl_gym_encode(grl_env *env, const int64_t *action_idx, int32_t player, int32_t slot, const uint8_t *mask,
+                   int32_t skip_invalid, grl_action *actions, uint8_t *valid);
+
 /* Draw the synthetic policy's actions for the current state into `actions`
  * ([B][max_actions], slot p = player p's move, empty when it has none). */
 int grl_sample_actions(grl_env *env, uint64_t policy_seed, grl_action *actions);

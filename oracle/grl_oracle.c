@@ -1472,6 +1472,46 @@ static void gym_range(void *c, int i0, int i1) {
   free(v);
 }
 
+/* GeneralsEnv._action_index_to_game_action (generals_env.py:389-441) */
+int grlo_gym_encode(grlo_env *e, const int64_t *action_idx, int32_t player, int32_t slot, const uint8_t *mask,
+                    int32_t skip_invalid, grl_action *actions, uint8_t *valid) {
+  if (!e || !action_idx || !mask || !actions) return GRL_ERR_INVALID_ARG;
+  int N = e->N, P = e->cfg.num_players, W = e->cfg.width, H = e->cfg.height, A = e->cfg.max_actions;
+  if (player < 0 || player >= P || slot < 0 || slot >= A) return GRL_ERR_INVALID_ARG;
+  static const int DX[4] = {0, 1, 0, -1}, DY[4] = {-1, 0, 1, 0};
+  for (int b = 0; b < e->cfg.num_envs; b++) {
+    int64_t a = action_idx[b];
+    int ok = a >= 0 && a < (int64_t)N * 5 && mask[((size_t)b * P + player) * N * 5 + a];
+    grl_action *rec = &actions[(size_t)b * A + slot];
+    memset(rec, 0, sizeof(*rec));
+    if (ok) {
+      int from_idx = (int)(a / 5), info = (int)(a % 5);
+      int fx = from_idx % W, fy = from_idx / W, tx = fx, ty = fy;
+      if (info < 4) {
+        tx = fx + DX[info];
+        ty = fy + DY[info];
+      } else { /* half move: the first in-bounds direction */
+        for (int d = 0; d < 4; d++) {
+          tx = fx + DX[d];
+          ty = fy + DY[d];
+          if (tx >= 0 && tx < W && ty >= 0 && ty < H) break;
+        }
+      }
+      rec->player_id = (int8_t)player;
+      rec->from_x = (int8_t)fx;
+      rec->from_y = (int8_t)fy;
+      rec->to_x = (int8_t)tx;
+      rec->to_y = (int8_t)ty;
+      rec->move_all = info != 4; /* Action.half == false -> MoveAll (converters.go:123) */
+      rec->present = 1;
+    } else if (skip_invalid) {
+      actions[(size_t)b * A].flags |= GRL_ACTION_FLAG_SKIP_ENV;
+    }
+    if (valid) valid[b] = (uint8_t)ok;
+  }
+  return GRL_OK;
+}
+
 int grlo_gym_observe(grlo_env *e, int32_t max_turns, const grl_gym_outputs *out) {
   if (!e || !out || max_turns < 1) return GRL_ERR_INVALID_ARG;
   gym_ctx_t x = {e, max_turns, out};

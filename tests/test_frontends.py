@@ -349,3 +349,61 @@ def test_go_rand_and_demo_policy(oracle_lib):
         # a move legal at submission can only be invalidated by the OTHER player's move of the same turn
         assert st["step_error"][0] in (0, _abi.STEP_NOT_OWNED, _abi.STEP_INSUFFICIENT_ARMY)
     assert 60 < played < 200, "each player moves with probability 0.3 per turn"
+
+
+def _python_decode(a, W, H):
+    """generals_env.py:389-441 for a valid index."""
+    frm, info = a // 5, a % 5
+    fx, fy = frm % W, frm // W
+    dirs = [(0, -1), (1, 0), (0, 1), (-1, 0)]
+    if info < 4:
+        tx, ty = fx + dirs[info][0], fy + dirs[info][1]
+    else:
+        for dx, dy in dirs:
+            tx, ty = fx + dx, fy + dy
+            if 0 <= tx < W and 0 <= ty < H:
+                break
+    return fx, fy, tx, ty, info != 4
+
+
+def _gym_encode_case(lib, to_dev):
+    W, H, P, B = 7, 6, 2, 64
+    e = _played(lib, W, H, P, B, 25)
+    obs, mask, stats = gym_readouts(e, 100)
+    rng = np.random.default_rng(9)
+    idx = rng.integers(-3, W * H * 5 + 3, B).astype(np.int64)
+    for b in range(0, B, 2):  # half of the envs get a valid index (if they have one)
+        ok = np.nonzero(mask[b, 0])[0]
+        if len(ok):
+            idx[b] = ok[rng.integers(len(ok))]
+    acts = make_actions(B, e.A)
+    acts["player_id"][:, 1], acts["present"][:, 1] = 1, 1   # a pre-filled opponent slot must survive
+    valid = np.zeros(B, np.uint8)
+    d_idx, d_mask, d_acts, d_valid = to_dev(idx), to_dev(mask), to_dev(acts.view(np.uint8).reshape(B, e.A, 8)), to_dev(valid)
+    e.gym_encode(d_idx, 0, 0, d_mask, True, d_acts, d_valid)
+    acts = np.asarray(d_acts.cpu() if hasattr(d_acts, "cpu") else d_acts).reshape(B, e.A, 8).view(_abi.ACTION_DTYPE).reshape(B, e.A)
+    valid = np.asarray(d_valid.cpu() if hasattr(d_valid, "cpu") else d_valid)
+    assert valid.sum() > 0 and (valid == 0).sum() > 0
+    for b in range(B):
+        a = int(idx[b])
+        ok = 0 <= a < W * H * 5 and bool(mask[b, 0, a])
+        assert bool(valid[b]) == ok
+        r = acts[b, 0]
+        if ok:
+            fx, fy, tx, ty, mv = _python_decode(a, W, H)
+            assert (r["player_id"], r["from_x"], r["from_y"], r["to_x"], r["to_y"], r["move_all"], r["present"], r["flags"]) == (
+                0, fx, fy, tx, ty, int(mv), 1, 0)
+        else:
+            assert r["present"] == 0 and r["flags"] == _abi.ACTION_FLAG_SKIP_ENV
+        assert acts[b, 1]["present"] == 1 and acts[b, 1]["player_id"] == 1
+
+
+def test_gym_encode_oracle(oracle_lib):
+    _gym_encode_case(oracle_lib, lambda a: a)
+
+
+@pytest.mark.gpu
+def test_gym_encode_cuda(cuda_lib):
+    import torch
+
+    _gym_encode_case(cuda_lib, lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda())

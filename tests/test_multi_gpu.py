@@ -27,6 +27,7 @@ def _worker(rank, world, port, total, T, tmp):
     lib = load_library()
     sh = sharding.shard_from_env(total)
     e = sharding.create_sharded_engine(lib, sh, device=rank, width=20, height=20, num_players=2, host_threads=0)
+    e.use_torch_stream()
     e.reset_seeded(sh.seeds(12345))
     B, P, H, W = sh.count, 2, 20, 20
     mk = lambda *shape, dt=torch.float32: torch.zeros(shape, dtype=dt, device=dev)

@@ -42,6 +42,7 @@ def run(rank, world, games_per_gpu=4096, turns=20, sample=64, out_path=None, por
     P = 2
     sh = sharding.shard_for(games_per_gpu * world, world, rank)
     e = sharding.create_sharded_engine(lib, sh, device=local, width=W, height=H, num_players=P, host_threads=0)
+    e.use_torch_stream()
     e.reset_seeded(sh.seeds(12345))
     B = sh.count
     mk = lambda *shape, dt=torch.float32: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
