@@ -197,8 +197,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64+f32", "data": "synthetic",
-        "config": {"workload": "20x20 2p fog-on random-legal-move rollouts, seeds 12345+i", "games_per_step": games,
-                   "episode_cap": 500},
+        "config": {"workload": "20x20 2p fog-on random-legal-move rollouts (BASELINE headline config; seeds 12345+i; "
+                               "the counter-based policy's moves recorded once and replayed from host memory)",
+                   "games_per_step": games, "players": P, "board": [W, H], "episode_cap": 500,
+                   "parallelism": f"one game per job over {cores} host threads (bounded sample of the GPU arm's workload)"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{games} games x {args.steps} turns ({n} env-steps) with observation, mask and reward "
                                    "generation; C restatement of the Go engine (Go toolchain unavailable)"},
