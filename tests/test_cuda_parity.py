@@ -379,3 +379,22 @@ def test_device_mapgen_matches_host_and_oracle(cuda_lib, oracle_lib, W, H, P, mo
     dev.reset_seeded(seeds[: len(ids)] + 99, ids)
     orc.reset_seeded(seeds[: len(ids)] + 99, ids)
     assert np.array_equal(dev.state_hash(), orc.state_hash())
+
+
+@pytest.mark.parametrize("W,H,P", [(10, 10, 2), (15, 15, 2), (20, 20, 2), (20, 20, 4), (9, 9, 2)])
+def test_fog_disabled_parity(cuda_lib, oracle_lib, W, H, P):
+    """GameState.FogOfWarEnabled == false (the reference's tests build such engines by hand): every tile is
+    visible to every player in the observation planes; the baked plane-major / linear / packed writers
+    and the generic one must all agree with the oracle."""
+    rollout_compare(cuda_lib, oracle_lib, W, H, P, B=41, T=50, seed=5 + P, err_rate=0.03, fog_of_war=0)
+    g, o = new_engine(cuda_lib, W, H, P, 9, fog_of_war=0), new_engine(oracle_lib, W, H, P, 9, fog_of_war=0)
+    for e in (g, o):
+        e.reset_seeded(np.arange(9, dtype=np.int64) + 3)
+        for _ in range(20):
+            e.step(None, _abi.STEP_FLAG_RANDOM_POLICY, 1)
+    for e in (g, o):
+        e.obs_gym = np.zeros((9, P, 9, H, W), np.float32)
+        e.mask_gym = np.zeros((9, P, W * H * 5), np.uint8)
+        e.gym_observe(100, e.obs_gym, e.mask_gym, None)
+    assert np.array_equal(g.obs_gym.view(np.uint32), o.obs_gym.view(np.uint32)) and np.array_equal(g.mask_gym, o.mask_gym)
+    assert (g.obs_gym[:, :, 0] == 1.0).all(), "without fog every tile is visible"
