@@ -147,11 +147,15 @@ def test_dense_battle_parity(cuda_lib, oracle_lib, W, H, P):
     assert st[2] > 0, "no game finished: the elimination path was not exercised"
 
 
-def test_multiple_actions_per_player(cuda_lib, oracle_lib):
-    """UI-style submission: several moves per player per turn, applied in stable player-id order."""
-    W = H = 8
-    P, B, A = 2, 64, 6
-    rng = np.random.default_rng(9)
+@pytest.mark.parametrize("W,H,P,A,LG", [(8, 8, 2, 6, 0), (10, 10, 4, 12, 4), (10, 10, 2, 12, 8), (15, 15, 3, 9, 8), (20, 20, 4, 12, 16)])
+def test_multiple_actions_per_player(cuda_lib, oracle_lib, W, H, P, A, LG, monkeypatch):
+    """UI-style submission: several moves per player per turn (up to the 12-slot cap), applied in stable
+    player-id order — on the generic kernel and on packed lane groups, where a group's lanes decode
+    more than one slot each."""
+    if LG:
+        monkeypatch.setenv("GRL_LANES_PER_GAME", str(LG))
+    B = 45
+    rng = np.random.default_rng(9 + A)
     init = dense_battle_state(rng, W, H, P, B)
     gc = new_engine(cuda_lib, W, H, P, B, max_actions=A)
     oc = new_engine(oracle_lib, W, H, P, B, max_actions=A)
