@@ -132,3 +132,44 @@ def test_10k_games_full_episode_replay(cuda_lib, oracle_lib, W, H, P, T):
     assert errors > 0
     if W == 10:
         assert finished > 0
+
+
+def test_step_is_cuda_graph_capturable(cuda_lib, oracle_lib):
+    """With device buffers a fused step is exactly one kernel launch on the env's stream, so a rollout
+    segment can be captured in a CUDA graph (launch-bound small batches).  Eight self-play turns are
+    captured once and replayed; the state must equal the oracle's after every replay."""
+    import torch
+
+    W, H, P, B, K = 10, 10, 2, 512, 8
+    e = new_engine(cuda_lib, W, H, P, B)
+    o = new_engine(oracle_lib, W, H, P, B)
+    seeds = np.arange(B, dtype=np.int64) + 77
+    e.reset_seeded(seeds)
+    o.reset_seeded(seeds)
+    dev = torch.device("cuda:0")
+    obs = torch.zeros((K, B, P, 9, H, W), dtype=torch.float32, device=dev)  # one observation buffer per captured turn
+    reward = torch.zeros((K, B, P), dtype=torch.float32, device=dev)
+    done = torch.zeros((K, B), dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        e.use_torch_stream()
+        for k in range(K):  # warm-up outside the capture (kernel attributes are set on first launch)
+            e.step_fused(None, e.outputs(obs=obs[k], reward=reward[k], done=done[k]), _abi.STEP_FLAG_RANDOM_POLICY, 5)
+    side.synchronize()
+    for k in range(K):
+        o.step(None, _abi.STEP_FLAG_RANDOM_POLICY, 5)
+    assert np.array_equal(e.state_hash(), o.state_hash())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for k in range(K):
+            e.step_fused(None, e.outputs(obs=obs[k], reward=reward[k], done=done[k]), _abi.STEP_FLAG_RANDOM_POLICY, 5)
+    oo = o.alloc_outputs_host()
+    for rep in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        for k in range(K):
+            o.step_fused(None, o.outputs(**oo), _abi.STEP_FLAG_RANDOM_POLICY, 5)
+        assert np.array_equal(e.state_hash(), o.state_hash()), f"replay {rep}"
+        assert np.array_equal(reward[K - 1].cpu().numpy().view(np.uint32), oo["reward"].view(np.uint32))
+        assert np.array_equal(obs[K - 1].cpu().numpy().view(np.uint32), oo["obs"].view(np.uint32))
+    assert int(e.get_state(0, 1)["turn"][0]) == K * 4
