@@ -1712,12 +1712,10 @@ static cudaError_t launch_turn_p(const GrlKParams &prm, bool do_step, bool do_ou
       if (lpg == 16) return launch_turn_g<PT, 20, 20, 16>(prm, do_step, do_out, stream);
       return launch_turn_g<PT, 20, 20, 32>(prm, do_step, do_out, stream);
     }
-    // measured on B200 (profiles/r1_variants.md): 10x10 is fastest with 8 lanes per game at every batch size;
-    // 15x15 with 8 lanes from ~128 K games up, with one game per warp below that (fewer, longer-lived CTAs
-    // cost more in the last wave than the turn phase gains)
-    const int games = prm.game_end - prm.game0;
+    // measured on B200 (profiles/r1_variants.md): with the packed groups writing the whole slab back (no snapshot in
+    // shared memory, four CTAs per SM) 8 lanes per game is fastest for 10x10 and 15x15 at every batch size
     if (prm.W == 15 && prm.H == 15) {
-      const int pick = lpg ? lpg : (games >= 131072 ? 8 : 32);
+      const int pick = lpg ? lpg : 8;
       if (pick == 8) return launch_turn_g<PT, 15, 15, 8>(prm, do_step, do_out, stream);
       if (pick == 16) return launch_turn_g<PT, 15, 15, 16>(prm, do_step, do_out, stream);
       return launch_turn_g<PT, 15, 15, 32>(prm, do_step, do_out, stream);
