@@ -156,7 +156,7 @@ def load_oracle():
     return BoundLibrary(path, "grlo_")
 
 
-def time_oracle(games, steps, warmup, threads=0):
+def time_oracle(games, steps, warmup, threads=0, with_readouts=True):
     """The CPU arm: C restatement of the Go engine (oracle/), one game per job, all host threads.
     Bounded sample of the same workload: `games` 20x20x2p games, seeds BASE_SEED+i, the same
     recorded random-legal-move actions replayed from host memory."""
@@ -175,12 +175,13 @@ def time_oracle(games, steps, warmup, threads=0):
     e.reset_seeded(seeds)
     out = e.alloc_outputs_host()
     outs = e.outputs(obs=out["obs"], mask_bits=out["mask_bits"], reward=out["reward"], done=out["done"])
+    run = (lambda a: e.step_fused(a, outs)) if with_readouts else (lambda a: e.step(a))
     for t in range(warmup):
-        e.step_fused(rec[t], outs)
+        run(rec[t])
     s0 = int(e.stats()[0])
     t0 = time.perf_counter()
     for t in range(warmup, warmup + steps):
-        e.step_fused(rec[t], outs)
+        run(rec[t])
     dt = time.perf_counter() - t0
     done_steps = int(e.stats()[0]) - s0
     e.close()
@@ -369,7 +370,9 @@ def run_cuda(args):
         steps_c = 400
         games = int(min(32768, max(2048, (rate * 15.0 / steps_c) // 1024 * 1024)))
         rate, dt, cores, n = time_oracle(games, steps_c, 2)
+        rate_bare, dt_bare, _, n_bare = time_oracle(8192, 100, 2, with_readouts=False)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "value_turn_only": rate_bare,  # ProcessTurn alone, no observation / mask generation
                "sample": f"{games} games x {steps_c} turns ({n} env-steps, {dt:.1f} s) incl. observation/mask/reward; "
                          "C restatement of the Go engine (oracle/), Go toolchain unavailable"}
 
