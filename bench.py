@@ -386,7 +386,9 @@ def run_cuda(args):
                    "cache": f"working set {(alg['total'] * B) / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                    "parallelism": f"games sharded by env index over {world} GPU(s), no collective on the step path"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": "per step: actions H2D from pinned host, reward/done/winner/step_error D2H; obs+mask stay in HBM"},
+                "what": "per step through grl_step_fused with HOST buffers: actions copied host->device from pinned memory, "
+                        "reward/done/winner/step_error delivered to pinned host memory (written in place by the kernel); "
+                        "observation and mask planes stay in HBM for an on-GPU learner"},
         "e2e_host_obs": {"value": e2e_full, "unit": UNIT, "h2d_bytes_per_step": h2d_f, "d2h_bytes_per_step": d2h_f,
                          "steps": k_full, "what": "as e2e plus every observation tensor and mask copied to the host"},
         "gpu_launches": int(launches),

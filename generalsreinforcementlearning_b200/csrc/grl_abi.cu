@@ -71,6 +71,8 @@ struct grl_env {
   static constexpr int kPipe = 8;
   cudaStream_t pipe[kPipe] = {};
   cudaEvent_t ev_start = nullptr, ev_done[kPipe] = {};
+  int zero_copy = 1;    // GRL_ZERO_COPY (default 1; e2e 169.8 -> 179.0 M env-steps/s): 1 = small result planes in pinned host memory are written by the kernel
+                        // directly (no D2H copies), 2 = + actions read in place, 3 = + observation / mask planes
   int pipe_chunks = 6;  // GRL_PIPE_CHUNKS=1 disables the pipelining (e2e: 160 M env-steps/s at 1, 169 M at 4, 170 M at 6-8)
 };
 
@@ -85,6 +87,18 @@ bool is_device_ptr(const void *p) {
     return false;
   }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Pinned (page-locked, mapped) host memory is addressable from the device under unified addressing:
+// returns the device alias of such a buffer, nullptr for pageable host memory or device memory.
+void *pinned_device_alias(const void *p) {
+  if (!p) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
 int ensure(grl_env *env, Slot s, size_t bytes, void **out) {
@@ -391,10 +405,14 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
   prm.flags = flags;
   prm.policy_seed = policy_seed;
   const size_t act_stride = (size_t)c.max_actions * sizeof(grl_action);
-  bool actions_staged = false;
+  bool actions_staged = false, zero_copied = false;
   if (do_step && actions && !(flags & GRL_STEP_FLAG_RANDOM_POLICY)) {
+    void *alias = env->zero_copy >= 2 ? pinned_device_alias(actions) : nullptr;
     if (is_device_ptr(actions)) {
       prm.actions = actions;
+    } else if (alias) {
+      prm.actions = alias;  // read in place over PCIe; the call still returns only after the kernel has consumed it
+      zero_copied = true;
     } else {
       void *d = nullptr;
       int st = ensure(env, SL_ACTIONS, B * act_stride, &d);
@@ -417,6 +435,15 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
     const size_t strides[7] = {P * GRL_OBS_CHANNELS * N * 4, P * words * 4, P * 4, 1, 1, 1, P * 4};
     for (int i = 0; i < 7; i++) {
       planes[i].stride = strides[i];
+      const bool small = i >= 2;  // reward, done, winner, step_error, action_index
+      void *alias = (env->zero_copy >= 3 || (env->zero_copy >= 1 && small)) ? pinned_device_alias(user[i]) : nullptr;
+      if (alias) {  // the kernel writes the caller's pinned buffer directly
+        planes[i].ob.user = user[i];
+        planes[i].ob.dev = alias;
+        planes[i].ob.bytes = B * strides[i];
+        zero_copied = true;
+        continue;
+      }
       int st = bind_out(env, slots[i], user[i], B * strides[i], planes[i].ob);
       if (st) return st;
       any_staged = any_staged || planes[i].ob.staged;
@@ -432,9 +459,10 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
   }
   if (!do_step && !do_out) return GRL_OK;
 
-  if (!any_staged) {  // device buffers only: one asynchronous launch on the env's stream
+  if (!any_staged) {  // device (or device-addressable) buffers only: one launch on the env's stream
     CUDA_TRY(grl_launch_turn(prm, do_step, do_out, env->stream));
     env->launches++;
+    if (zero_copied) CUDA_TRY(cudaStreamSynchronize(env->stream));  // host buffers are valid / consumed on return
     return GRL_OK;
   }
 
@@ -547,6 +575,8 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   env->host_mapgen = (hm && hm[0] == '1') ? 1 : 0;
   const char *lpg = getenv("GRL_LANES_PER_GAME");
   env->lanes_per_game = lpg ? atoi(lpg) : 0;
+  const char *zc = getenv("GRL_ZERO_COPY");
+  env->zero_copy = zc ? atoi(zc) : 1;
   const char *pc = getenv("GRL_PIPE_CHUNKS");
   if (pc && atoi(pc) >= 1) env->pipe_chunks = atoi(pc);
   const char *pf = getenv("GRL_PREFETCH_DIST");

@@ -402,3 +402,37 @@ def test_fog_disabled_parity(cuda_lib, oracle_lib, W, H, P):
         e.gym_observe(100, e.obs_gym, e.mask_gym, None)
     assert np.array_equal(g.obs_gym.view(np.uint32), o.obs_gym.view(np.uint32)) and np.array_equal(g.mask_gym, o.mask_gym)
     assert (g.obs_gym[:, :, 0] == 1.0).all(), "without fog every tile is visible"
+
+
+def test_pinned_host_results_are_written_in_place(cuda_lib, oracle_lib):
+    """Result planes in PINNED host memory (what a trainer's host loop allocates) are written by the kernel
+    directly — no staging copy — and must hold the oracle's values when the call returns; pageable buffers
+    of the same call take the staged path."""
+    import torch
+
+    W, H, P, B = 20, 20, 2, 9000   # >= 8192: the staged planes of the call go through the pipelined sub-ranges
+    gc, oc = new_engine(cuda_lib, W, H, P, B, host_threads=0), new_engine(oracle_lib, W, H, P, B, host_threads=0)
+    seeds = np.arange(B, dtype=np.int64) + 4242
+    gc.reset_seeded(seeds)
+    oc.reset_seeded(seeds)
+    pin = lambda *shape, dt: torch.zeros(shape, dtype=dt).pin_memory()  # noqa: E731
+    reward, done = pin(B, P, dt=torch.float32), pin(B, dt=torch.uint8)
+    winner, err, aidx = pin(B, dt=torch.int8), pin(B, dt=torch.uint8), pin(B, P, dt=torch.int32)
+    mask = np.zeros((B, P, gc.mask_words), np.uint32)          # pageable: staged
+    acts_pinned = torch.zeros((B, gc.A, 8), dtype=torch.uint8).pin_memory()
+    oo = oc.alloc_outputs_host()
+    rng = np.random.default_rng(1)
+    for t in range(25):
+        acts = oc.sample_actions(31)
+        corrupt_actions(rng, acts, W, H, 0.05)
+        acts_pinned.copy_(torch.from_numpy(acts.view(np.uint8).reshape(B, gc.A, 8)))
+        reward.fill_(-7.0)
+        done.fill_(9)
+        gc.step_fused(acts_pinned, gc.outputs(mask_bits=mask, reward=reward, done=done, winner=winner, step_error=err,
+                                              action_index=aidx))
+        oc.step_fused(acts, oc.outputs(**oo))
+        assert np.array_equal(reward.numpy().view(np.uint32), oo["reward"].view(np.uint32)), f"turn {t}"
+        assert np.array_equal(done.numpy(), oo["done"]) and np.array_equal(winner.numpy(), oo["winner"])
+        assert np.array_equal(err.numpy(), oo["step_error"]) and np.array_equal(aidx.numpy(), oo["action_index"])
+        assert np.array_equal(mask, oo["mask_bits"])
+    assert np.array_equal(gc.state_hash(), oc.state_hash())
