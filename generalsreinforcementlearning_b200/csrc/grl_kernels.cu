@@ -1450,59 +1450,85 @@ __global__ void grl_visibility_kernel(const GrlKParams prm, uint8_t *__restrict_
 // generals_gym read-outs (python/generals_gym/generals_env.py:291-387) of every player's
 // fog-filtered proto view (internal/grpc/gameserver/server.go:556-582).  One thread per
 // (env, player, tile); channel planes are written coalesced over tiles.  Not on the turn path.
-__global__ void grl_gym_kernel(const GrlKParams prm, int max_turns, const float *__restrict__ logtab, float *__restrict__ obs,
-                               uint8_t *__restrict__ mask, int32_t *__restrict__ stats) {
+__global__ void __launch_bounds__(256)
+    grl_gym_kernel(const GrlKParams prm, int max_turns, const float *__restrict__ logtab, float *__restrict__ obs,
+                   uint8_t *__restrict__ mask, int32_t *__restrict__ stats) {
   const GrlLayout &L = prm.L;
   const int N = prm.N, P = prm.P, NW = prm.NW, W = prm.W, H = prm.H;
   const size_t total = (size_t)prm.B * P * N;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int t = (int)(idx % N);
-    const int p = (int)((idx / N) % P);
-    const int game = (int)(idx / ((size_t)N * P));
-    const uint32_t *s = prm.state + (size_t)game * L.slab_words;
-    const uint32_t *stt = prm.statics + (size_t)game * L.static_words;
-    const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
-    const bool vis = prm.fog ? bit_of(s + L.off_vis + p * NW, t) : true;
-    const bool mine = vis && bit_of(s + L.off_own + p * NW, t);
-    bool owned = false;
-    for (int q = 0; q < P; q++) owned = owned || bit_of(s + L.off_own + q * NW, t);
-    const bool mnt = bit_of(stt, t), city = bit_of(stt + NW, t), gen = bit_of(stt + 2 * NW, t);
-    const uint32_t a = vis ? army[t] : 0u;  // hidden and fogged tiles show no owner and no army
-    if (obs) {
-      float *o = obs + ((size_t)game * P + p) * GRL_GYM_CHANNELS * N + t;
-      const double tf = fmin((double)s[GRL_HDR_TURN] / (double)max_turns, 1.0);
-      o[0 * N] = vis ? 1.f : 0.f;
-      o[1 * N] = mine ? 0.5f : ((vis && owned) ? 1.f : 0.f);
-      o[2 * N] = a > 0u ? logtab[a] : 0.f;
-      o[3 * N] = (!mnt && !city && !gen) ? 1.f : 0.f;  // a hidden tile is a normal tile by definition
-      o[4 * N] = mnt ? 1.f : 0.f;
-      o[5 * N] = city ? 1.f : 0.f;
-      o[6 * N] = gen ? 1.f : 0.f;
-      o[7 * N] = (float)tf;
-      o[8 * N] = 0.f;
+  const int lane = threadIdx.x & 31;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  // every lane of a warp runs the same number of iterations: the mask bytes are transposed through shuffles
+  for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total; base += step) {
+    const size_t idx = base + lane;
+    const bool live = idx < total;
+    uint32_t flags = 0;  // bit d = mask[idx*5 + d]
+    if (live) {
+      int t, p, game;
+      if (total <= 0xffffffffull) {  // 32-bit index arithmetic whenever it fits (64-bit div/mod is ~100 instructions)
+        const uint32_t i32 = (uint32_t)idx, gp = i32 / (uint32_t)N;
+        t = (int)(i32 - gp * (uint32_t)N);
+        game = (int)(gp / (uint32_t)P);
+        p = (int)(gp - (uint32_t)game * (uint32_t)P);
+      } else {
+        t = (int)(idx % N);
+        p = (int)((idx / N) % P);
+        game = (int)(idx / ((size_t)N * P));
+      }
+      const uint32_t *s = prm.state + (size_t)game * L.slab_words;
+      const uint32_t *stt = prm.statics + (size_t)game * L.static_words;
+      const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+      const bool vis = prm.fog ? bit_of(s + L.off_vis + p * NW, t) : true;
+      const bool mine = vis && bit_of(s + L.off_own + p * NW, t);
+      bool owned = false;
+      for (int q = 0; q < P; q++) owned = owned || bit_of(s + L.off_own + q * NW, t);
+      const bool mnt = bit_of(stt, t), city = bit_of(stt + NW, t), gen = bit_of(stt + 2 * NW, t);
+      const uint32_t a = vis ? army[t] : 0u;  // hidden and fogged tiles show no owner and no army
+      if (obs) {
+        float *o = obs + ((size_t)game * P + p) * GRL_GYM_CHANNELS * N + t;
+        // min(turn / max_turns, 1.0) is computed in float64 by the client and stored as float32; for integers
+        // below 2^24 the correctly rounded float32 quotient is the same number (no double-rounding case exists
+        // for denominators below 2^28), and the B200's float64 rate would make this the kernel's hot spot
+        const float tf = fminf(__fdiv_rn((float)s[GRL_HDR_TURN], (float)max_turns), 1.0f);
+        __stcs(o + 0 * N, vis ? 1.f : 0.f);
+        __stcs(o + 1 * N, mine ? 0.5f : ((vis && owned) ? 1.f : 0.f));
+        __stcs(o + 2 * N, a > 0u ? logtab[a] : 0.f);
+        __stcs(o + 3 * N, (!mnt && !city && !gen) ? 1.f : 0.f);  // a hidden tile is a normal tile by definition
+        __stcs(o + 4 * N, mnt ? 1.f : 0.f);
+        __stcs(o + 5 * N, city ? 1.f : 0.f);
+        __stcs(o + 6 * N, gen ? 1.f : 0.f);
+        __stcs(o + 7 * N, tf);
+        __stcs(o + 8 * N, 0.f);
+      }
+      if (mask) {
+        const int x = t % W, y = t / W;
+        const bool src = mine && a > 1u;
+        const bool up = src && y > 0 && !bit_of(stt, t - W);
+        const bool right = src && x < W - 1 && !bit_of(stt, t + 1);
+        const bool down = src && y < H - 1 && !bit_of(stt, t + W);
+        const bool left = src && x > 0 && !bit_of(stt, t - 1);
+        flags = (up ? 1u : 0u) | (right ? 2u : 0u) | (down ? 4u : 0u) | (left ? 8u : 0u) | ((up || right || down || left) ? 16u : 0u);
+      }
+      if (stats && t == 0) {
+        int tiles = 0;
+        for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + p * NW + k]);
+        int32_t *so = stats + ((size_t)game * P + p) * 4;
+        so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ARMY_COUNT];
+        so[1] = tiles;
+        so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> p) & 1u);
+        so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_GENERAL_IDX];
+      }
     }
     if (mask) {
-      const int x = t % W, y = t / W;
-      const bool src = mine && a > 1u;
-      const bool up = src && y > 0 && !bit_of(stt, t - W);
-      const bool right = src && x < W - 1 && !bit_of(stt, t + 1);
-      const bool down = src && y < H - 1 && !bit_of(stt, t + W);
-      const bool left = src && x > 0 && !bit_of(stt, t - 1);
-      uint8_t *m = mask + (((size_t)game * P + p) * N + t) * 5;
-      m[0] = up;
-      m[1] = right;
-      m[2] = down;
-      m[3] = left;
-      m[4] = up || right || down || left;
-    }
-    if (stats && t == 0) {
-      int tiles = 0;
-      for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + p * NW + k]);
-      int32_t *so = stats + ((size_t)game * P + p) * 4;
-      so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_ARMY_COUNT];
-      so[1] = tiles;
-      so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> p) & 1u);
-      so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_GENERAL_IDX];
+      // the warp's 32 x 5 mask bytes are contiguous in memory (address = idx*5 + d): lane i writes bytes
+      // i, i+32, ... so that every store instruction covers one 32-byte run instead of a stride-5 scatter
+      uint8_t *mb = mask + base * 5;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        const int j = 32 * r + lane;
+        const uint32_t v = __shfl_sync(FULL, flags, j / 5);
+        if (base + j / 5 < total) mb[j] = (uint8_t)((v >> (j % 5)) & 1u);
+      }
     }
   }
 }

@@ -75,7 +75,7 @@ class GeneralsVecEnv:
         self.action_space = Discrete(self.N * 5)
         B, P, N, dev = num_envs, self.P, self.N, self.device
         self._obs = torch.zeros((B, P, 9, self.H, self.W), dtype=torch.float32, device=dev)
-        self._mask = torch.zeros((B, P, N * 5), dtype=torch.uint8, device=dev)
+        self._mask = torch.zeros((B, P, N * 5), dtype=torch.bool, device=dev)   # the kernel writes 0/1 bytes
         self._stats = torch.zeros((B, P, 4), dtype=torch.int32, device=dev)
         self._prev_stats = torch.zeros_like(self._stats)
         self._actions = torch.zeros((B, P, 8), dtype=torch.uint8, device=dev)  # grl_action[B][P]
@@ -118,7 +118,7 @@ class GeneralsVecEnv:
         self._turns.zero_()
         self._calls.zero_()
         self._refresh()
-        return self._obs[:, 0], {"valid_actions_mask": self._mask[:, 0].bool(), "turn": self._turns.clone()}
+        return self._obs[:, 0], {"valid_actions_mask": self._mask[:, 0], "turn": self._turns.clone()}
 
     def step(self, action, opponent_action=None):
         """action: int64 [B] indices into Discrete(N*5) for player 0 (and ``opponent_action`` for
@@ -165,7 +165,7 @@ class GeneralsVecEnv:
             self._turns[ids] = 0
             self._calls[ids] = 0
             self._refresh()
-        info["valid_actions_mask"] = self._mask[:, 0].bool()
+        info["valid_actions_mask"] = self._mask[:, 0]   # a view of the env's mask plane: valid until the next step()
         return self._obs[:, 0], reward, terminated, truncated, info
 
     def sample_actions(self, generator=None):
@@ -178,7 +178,7 @@ class GeneralsVecEnv:
 
     def opponent_view(self):
         """Player 1's observation and mask (self-play)."""
-        return self._obs[:, 1], self._mask[:, 1].bool()
+        return self._obs[:, 1], self._mask[:, 1]
 
     def render(self, env: int = 0, player: int = 0) -> str:
         from .render import render_board

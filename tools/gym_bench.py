@@ -23,12 +23,21 @@ def main():
             obs, r, term, trunc, info = env.step(act())
         torch.cuda.synchronize()
         steps = 60
+        t_policy = t_env = 0.0
         t0 = time.perf_counter()
         for _ in range(steps):
-            obs, r, term, trunc, info = env.step(act())
-        torch.cuda.synchronize()
+            a0 = time.perf_counter()
+            action = act()
+            torch.cuda.synchronize()
+            a1 = time.perf_counter()
+            obs, r, term, trunc, info = env.step(action)
+            torch.cuda.synchronize()
+            t_policy += a1 - a0
+            t_env += time.perf_counter() - a1
         dt = time.perf_counter() - t0
-        out.append({"envs": B, "board": W, "env_steps_per_s": round(B * steps / dt), "ms_per_vector_step": round(1e3 * dt / steps, 3)})
+        out.append({"envs": B, "board": W, "env_steps_per_s": round(B * steps / dt), "ms_per_vector_step": round(1e3 * dt / steps, 3),
+                    "ms_env_step": round(1e3 * t_env / steps, 3), "ms_random_policy": round(1e3 * t_policy / steps, 3),
+                    "env_only_steps_per_s": round(B * steps / t_env)})
         env.close()
     print(json.dumps(out))
 
