@@ -231,6 +231,26 @@ __device__ __forceinline__ void tma_store(void *dst_gmem, const void *src_smem, 
                "r"(bytes)
                : "memory");
 }
+// GRL_L2_HINT=1: the state slabs carry an L2::evict_last policy on their bulk loads, prefetches and write-back
+// stores (the observation stream is already evict-first through st.global.cs)
+#ifndef GRL_L2_HINT
+#define GRL_L2_HINT 0
+#endif
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st_hint_v4(uint4 *a, uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_l2(const void *src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
@@ -690,10 +710,17 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
       if (l == 0) {
         const bool want_snap = kSnap && DO_STEP;
         mbar_expect_tx(bar, (uint32_t)(L.slab_words + L.static_words + (want_snap ? L.slab_words : 0)) * 4u);
+#if GRL_L2_HINT
+        const uint64_t pol = policy_evict_last();
+        tma_load_hint(s, gslab, (uint32_t)L.slab_words * 4u, bar, pol);
+        tma_load_hint(st, gstat, (uint32_t)L.static_words * 4u, bar, pol);
+        if (want_snap) tma_load_hint(snap, gslab, (uint32_t)L.slab_words * 4u, bar, pol);
+#else
         tma_load(s, gslab, (uint32_t)L.slab_words * 4u, bar);
         tma_load(st, gstat, (uint32_t)L.static_words * 4u, bar);
         if (want_snap)  // pre-turn snapshot for the dirty-sector write-back (an L2 hit on the same lines)
           tma_load(snap, gslab, (uint32_t)L.slab_words * 4u, bar);
+#endif
         // warm L2 for a CTA that will be scheduled a couple of waves from now
         if (prm.prefetch_dist > 0 && game + prm.prefetch_dist < prm.B) {
           tma_prefetch_l2(prm.state + (size_t)(game + prm.prefetch_dist) * L.slab_words, (uint32_t)L.slab_words * 4u);
@@ -1068,8 +1095,14 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
           const uint32_t diff = (a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) |
                                 (a1.z ^ b1.z) | (a1.w ^ b1.w);
           if (diff) {
+#if GRL_L2_HINT
+            const uint64_t pol = policy_evict_last();
+            st_hint_v4(dst4 + 2 * k, a0, pol);
+            st_hint_v4(dst4 + 2 * k + 1, a1, pol);
+#else
             dst4[2 * k] = a0;
             dst4[2 * k + 1] = a1;
+#endif
           }
         }
       } else {
