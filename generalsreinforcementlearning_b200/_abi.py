@@ -111,6 +111,13 @@ class GymOutputs(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("mask", C.c_void_p), ("stats", C.c_void_p)]
 
 
+class GymStepIO(C.Structure):
+    _fields_ = [("action", C.c_void_p), ("opponent_action", C.c_void_p), ("out", GymOutputs), ("actions", C.c_void_p),
+                ("prev_stats", C.c_void_p), ("turns", C.c_void_p), ("calls", C.c_void_p), ("reward", C.c_void_p),
+                ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("valid", C.c_void_p), ("done", C.c_void_p),
+                ("winner", C.c_void_p), ("step_error", C.c_void_p), ("n_finished", C.c_void_p)]
+
+
 STATE_FIELDS = (
     ("owner", np.int32, "N"),
     ("army", np.int32, "N"),
@@ -155,6 +162,7 @@ ABI_FUNCTIONS = {
     "visibility": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gym_observe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GymOutputs)]),
     "gym_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "gym_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(GymStepIO)]),
     "sample_actions": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "get_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(StatePlanes)]),
     "set_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(StatePlanes)]),

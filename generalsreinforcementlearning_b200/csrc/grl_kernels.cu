@@ -23,6 +23,7 @@
 //   reward              internal/experience/rewards.go:45-175
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/grlcuda.h"
@@ -1566,6 +1567,185 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// generals_gym read-outs, warp-per-game version: the game's masks are staged once in shared memory
+// and every player's [9][N] observation block is written as one linear, 16-byte aligned sweep of
+// 128-bit stores (as the turn kernel's observation writer does); the N*5 mask bytes go out as an
+// aligned 32-bit sweep.  Shared-memory words per warp: see grl_gym_smem_words().
+__host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N) {
+  return ((3 * P + 5 + 5 * P) * (NW + 1) + N + 4 + 3) & ~3;
+}
+
+struct GymPlanes {  // shared-memory views of one game (each mask has NW + 1 words, the last one zero)
+  const uint32_t *vis, *mine, *enemy;  // [P][NWP]
+  const uint32_t *normal, *M, *C, *G;  // [NWP]
+  const float *logv;                   // [N + 4]
+  float tf;
+  int NWP, N;
+};
+
+__device__ __forceinline__ float gym_value(const GymPlanes &g, int p, int plane, int t) {
+  const int w = t >> 5, b = t & 31;
+  switch (plane) {
+    case 0: return ((g.vis[p * g.NWP + w] >> b) & 1u) ? 1.f : 0.f;
+    case 1: return ((g.mine[p * g.NWP + w] >> b) & 1u) ? 0.5f : (((g.enemy[p * g.NWP + w] >> b) & 1u) ? 1.f : 0.f);
+    case 2: return ((g.vis[p * g.NWP + w] >> b) & 1u) ? g.logv[t] : 0.f;
+    case 3: return ((g.normal[w] >> b) & 1u) ? 1.f : 0.f;
+    case 4: return ((g.M[w] >> b) & 1u) ? 1.f : 0.f;
+    case 5: return ((g.C[w] >> b) & 1u) ? 1.f : 0.f;
+    case 6: return ((g.G[w] >> b) & 1u) ? 1.f : 0.f;
+    case 7: return g.tf;
+    default: return 0.f;
+  }
+}
+
+__device__ __forceinline__ uint32_t nib_at(const uint32_t *m, int t) {
+  return __funnelshift_r(m[t >> 5], m[(t >> 5) + 1], t & 31) & 0xfu;
+}
+#define GYM_NIB4(n, a) make_float4(((n)&1u) ? (a) : 0.f, ((n)&2u) ? (a) : 0.f, ((n)&4u) ? (a) : 0.f, ((n)&8u) ? (a) : 0.f)
+
+__device__ __forceinline__ float4 gym_value4(const GymPlanes &g, int p, int plane, int t) {  // t + 3 < N
+  switch (plane) {
+    case 0: { const uint32_t n = nib_at(g.vis + p * g.NWP, t); return GYM_NIB4(n, 1.f); }
+    case 1: {
+      const uint32_t a = nib_at(g.mine + p * g.NWP, t), e = nib_at(g.enemy + p * g.NWP, t);
+      return make_float4((a & 1u) ? 0.5f : ((e & 1u) ? 1.f : 0.f), (a & 2u) ? 0.5f : ((e & 2u) ? 1.f : 0.f),
+                         (a & 4u) ? 0.5f : ((e & 4u) ? 1.f : 0.f), (a & 8u) ? 0.5f : ((e & 8u) ? 1.f : 0.f));
+    }
+    case 2: {
+      const uint32_t n = nib_at(g.vis + p * g.NWP, t);
+      return make_float4((n & 1u) ? g.logv[t] : 0.f, (n & 2u) ? g.logv[t + 1] : 0.f, (n & 4u) ? g.logv[t + 2] : 0.f,
+                         (n & 8u) ? g.logv[t + 3] : 0.f);
+    }
+    case 3: { const uint32_t n = nib_at(g.normal, t); return GYM_NIB4(n, 1.f); }
+    case 4: { const uint32_t n = nib_at(g.M, t); return GYM_NIB4(n, 1.f); }
+    case 5: { const uint32_t n = nib_at(g.C, t); return GYM_NIB4(n, 1.f); }
+    case 6: { const uint32_t n = nib_at(g.G, t); return GYM_NIB4(n, 1.f); }
+    case 7: return make_float4(g.tf, g.tf, g.tf, g.tf);
+    default: return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
+    grl_gym_warp_kernel(const __grid_constant__ GrlKParams prm, int max_turns, const float *__restrict__ logtab,
+                        float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GrlLayout &L = prm.L;
+  const int N = prm.N, P = prm.P, NW = prm.NW, NWP = NW + 1;
+  const Geo g = make_geo(prm, prm.W, lane, 32);
+  uint32_t *sw = smem + warp * grl_gym_smem_words(P, NW, N);
+  uint32_t *s_vis = sw, *s_mine = s_vis + P * NWP, *s_enemy = s_mine + P * NWP;
+  uint32_t *s_normal = s_enemy + P * NWP, *s_M = s_normal + NWP, *s_C = s_M + NWP, *s_G = s_C + NWP, *s_pad = s_G + NWP;
+  uint32_t *s_dir = s_pad + NWP;  // [P][5][NWP]: up, right, down, left, any
+  float *s_logv = reinterpret_cast<float *>(s_dir + 5 * P * NWP);
+  for (int game = blockIdx.x * GRL_WARPS_PER_CTA + warp; game < prm.B; game += gridDim.x * GRL_WARPS_PER_CTA) {
+    const uint32_t *s = prm.state + (size_t)game * L.slab_words;
+    const uint32_t *stt = prm.statics + (size_t)game * L.static_words;
+    const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+    const bool w = lane < NW;
+    const uint32_t M = w ? stt[lane] : 0u, C = w ? stt[NW + lane] : 0u, G = w ? stt[2 * NW + lane] : 0u;
+    uint32_t any_own = 0;
+    for (int p = 0; p < P; p++) any_own |= w ? s[L.off_own + p * NW + lane] : 0u;
+    const uint32_t gt1 = army_gt1_mask<32>(army, NW, N, g);
+    const DirMasks dm = dir_targets<32>(M, g);
+    if (lane < NWP) {
+      s_normal[lane] = g.valid & ~(M | C | G) & (w ? ~0u : 0u);
+      s_M[lane] = M;
+      s_C[lane] = C;
+      s_G[lane] = G;
+    }
+    for (int p = 0; p < P; p++) {
+      const uint32_t own = w ? s[L.off_own + p * NW + lane] : 0u;
+      const uint32_t v = w ? (prm.fog ? s[L.off_vis + p * NW + lane] : g.valid) : 0u;
+      const uint32_t mine = v & own, src = mine & gt1;
+      if (lane < NWP) {
+        s_vis[p * NWP + lane] = v;
+        s_mine[p * NWP + lane] = mine;
+        s_enemy[p * NWP + lane] = v & any_own & ~own;
+        uint32_t *d = s_dir + p * 5 * NWP + lane;
+        const uint32_t up = src & dm.up, right = src & dm.right, down = src & dm.down, left = src & dm.left;
+        d[0 * NWP] = up;
+        d[1 * NWP] = right;
+        d[2 * NWP] = down;
+        d[3 * NWP] = left;
+        d[4 * NWP] = up | right | down | left;
+      }
+    }
+    for (int t = lane; t < N + 4; t += 32) s_logv[t] = t < N ? logtab[army[t]] : 0.f;  // logtab[0] == 0
+    __syncwarp();
+
+    GymPlanes gp;
+    gp.vis = s_vis;
+    gp.mine = s_mine;
+    gp.enemy = s_enemy;
+    gp.normal = s_normal;
+    gp.M = s_M;
+    gp.C = s_C;
+    gp.G = s_G;
+    gp.logv = s_logv;
+    gp.NWP = NWP;
+    gp.N = N;
+    gp.tf = fminf(__fdiv_rn((float)s[GRL_HDR_TURN], (float)max_turns), 1.0f);
+    if (obs) {
+      const int block = GRL_GYM_CHANNELS * N;  // floats per (game, player)
+      for (int p = 0; p < P; p++) {
+        const size_t off = ((size_t)game * P + p) * block;
+        float *base = obs + off;
+        const int head = (int)((4u - (uint32_t)(off & 3u)) & 3u);
+        const int body4 = (block - head) / 4, tail0 = head + 4 * body4;
+        if (lane < head) __stcs(base + lane, gym_value(gp, p, lane / N, lane % N));
+        if (lane < block - tail0) __stcs(base + tail0 + lane, gym_value(gp, p, (tail0 + lane) / N, (tail0 + lane) % N));
+        float4 *body = reinterpret_cast<float4 *>(base + head);
+        for (int i = lane; i < body4; i += 32) {
+          const int e = head + 4 * i, plane = e / N, t = e - plane * N;
+          float4 val;
+          if (t + 3 < N) {
+            val = gym_value4(gp, p, plane, t);
+          } else {
+            val.x = gym_value(gp, p, plane, t);
+            val.y = gym_value(gp, p, (e + 1) / N, (e + 1) % N);
+            val.z = gym_value(gp, p, (e + 2) / N, (e + 2) % N);
+            val.w = gym_value(gp, p, (e + 3) / N, (e + 3) % N);
+          }
+          __stcs(body + i, val);
+        }
+      }
+    }
+    if (mask) {
+      const int bytes = N * 5;
+      for (int p = 0; p < P; p++) {
+        const uint32_t *d = s_dir + p * 5 * NWP;
+        const size_t off = ((size_t)game * P + p) * bytes;
+        uint8_t *base = mask + off;
+        auto flag = [&](int j) -> uint32_t {  // byte j = direction j%5 of tile j/5
+          const int t = j / 5, k = j - 5 * t;
+          return (d[k * NWP + (t >> 5)] >> (t & 31)) & 1u;
+        };
+        const int head = (int)((4u - (uint32_t)(off & 3u)) & 3u);
+        const int body4 = (bytes - head) / 4, tail0 = head + 4 * body4;
+        if (lane < head) base[lane] = (uint8_t)flag(lane);
+        if (lane < bytes - tail0) base[tail0 + lane] = (uint8_t)flag(tail0 + lane);
+        uint32_t *body = reinterpret_cast<uint32_t *>(base + head);
+        for (int i = lane; i < body4; i += 32) {
+          const int j = head + 4 * i;
+          body[i] = flag(j) | (flag(j + 1) << 8) | (flag(j + 2) << 16) | (flag(j + 3) << 24);
+        }
+      }
+    }
+    if (stats && lane < P) {
+      int tiles = 0;
+      for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + lane * NW + k]);
+      int32_t *so = stats + ((size_t)game * P + lane) * 4;
+      so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ARMY_COUNT];
+      so[1] = tiles;
+      so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> lane) & 1u);
+      so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_GENERAL_IDX];
+    }
+    __syncwarp();
+  }
+}
+#undef GYM_NIB4
+
 // GeneralsEnv._action_index_to_game_action (generals_env.py:389-441), one thread per env
 __global__ void grl_gym_encode_kernel(const GrlKParams prm, const long long *__restrict__ action_idx, int player, int slot,
                                       const uint8_t *__restrict__ mask, int skip_invalid, uint2 *__restrict__ actions,
@@ -1597,6 +1777,50 @@ __global__ void grl_gym_encode_kernel(const GrlKParams prm, const long long *__r
       reinterpret_cast<uint8_t *>(actions + (size_t)b * A)[7] |= GRL_ACTION_FLAG_SKIP_ENV;
     if (valid) valid[b] = ok ? 1 : 0;
   }
+}
+
+// The tail of GeneralsEnv.step (generals_env.py:268-289) and its client-side reward (:499-561), one thread per env.
+// `force_full` patches the random opponent's slot to a full move (the reference's random opponent never sends
+// half moves, :483).
+__global__ void grl_gym_patch_kernel(const GrlKParams prm, uint2 *__restrict__ actions, int slot) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < prm.B; b += gridDim.x * blockDim.x)
+    reinterpret_cast<uint8_t *>(actions + (size_t)b * prm.A + slot)[5] = 1;  // grl_action.move_all
+}
+
+__global__ void grl_gym_finish_kernel(const GrlKParams prm, int max_turns, const int32_t *__restrict__ stats,
+                                      const int32_t *__restrict__ prev_stats, const uint8_t *__restrict__ valid_in,
+                                      const uint8_t *__restrict__ done, const int8_t *__restrict__ winner,
+                                      int32_t *__restrict__ turns, int32_t *__restrict__ calls, double *__restrict__ reward,
+                                      uint8_t *__restrict__ terminated, uint8_t *__restrict__ truncated,
+                                      int32_t *__restrict__ n_finished) {
+  const int P = prm.P;
+  int mine = 0;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < prm.B; b += gridDim.x * blockDim.x) {
+    const int valid = valid_in[b] ? 1 : 0;
+    const int tn = turns[b] + valid, cl = calls[b] + 1;
+    turns[b] = tn;
+    calls[b] = cl;
+    const bool term = done[b] && valid;
+    const bool trunc = (tn >= max_turns && valid) || cl >= max_turns;
+    const int32_t *cur = stats + (size_t)b * P * 4, *prev = prev_stats + (size_t)b * P * 4;
+    double r = 0.0;
+    if (!valid) {
+      r = -0.1;
+    } else if (term) {
+      r = winner[b] == 0 ? 100.0 : -100.0;
+    } else {
+      r += (double)(cur[1] - prev[1]) * 1.0;
+      r += (double)(cur[0] - prev[0]) * 0.01;
+      for (int q = 1; q < P; q++)
+        if (prev[q * 4 + 2] == 1 && cur[q * 4 + 2] == 0) r += 50.0;
+    }
+    reward[b] = r;
+    terminated[b] = term ? 1 : 0;
+    truncated[b] = trunc ? 1 : 0;
+    mine += (term || trunc) ? 1 : 0;
+  }
+  mine = __reduce_add_sync(FULL, mine);
+  if (n_finished && (threadIdx.x & 31) == 0 && mine) atomicAdd(n_finished, mine);
 }
 
 // packed engine mask with the half-move replica: [B][P][rep][words]
@@ -1840,6 +2064,21 @@ cudaError_t grl_launch_visibility(const GrlKParams &prm, uint8_t *visible, uint8
 
 cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *logtab, float *obs, uint8_t *mask, int32_t *stats,
                            cudaStream_t stream) {
+  // warp-per-game kernel with linear 128-bit sweeps; GRL_GYM_FLAT=1 keeps the thread-per-tile version for comparison
+  static const bool flat = [] { const char *e = getenv("GRL_GYM_FLAT"); return e && e[0] == '1'; }();
+  if (!flat) {
+    const size_t smem = (size_t)GRL_WARPS_PER_CTA * grl_gym_smem_words(prm.P, prm.NW, prm.N) * 4u;
+    static size_t tuned = 0;
+    if (smem > 48 * 1024 && smem > tuned) {
+      cudaError_t e = cudaFuncSetAttribute(grl_gym_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      tuned = smem;
+    }
+    int grid = grid_for(GRL_WARPS_PER_CTA, prm.B);
+    if (grid > 148 * 16) grid = 148 * 16;
+    grl_gym_warp_kernel<<<grid, GRL_WARPS_PER_CTA * 32, smem, stream>>>(prm, max_turns, logtab, obs, mask, stats);
+    return cudaGetLastError();
+  }
   size_t total = (size_t)prm.B * prm.P * prm.N;
   grl_gym_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(prm, max_turns, logtab, obs, mask, stats);
   return cudaGetLastError();
@@ -1849,6 +2088,19 @@ cudaError_t grl_launch_gym_encode(const GrlKParams &prm, const long long *action
                                   int skip_invalid, void *actions, uint8_t *valid, cudaStream_t stream) {
   grl_gym_encode_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm, action_idx, player, slot, mask, skip_invalid,
                                                                            (uint2 *)actions, valid);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_gym_patch(const GrlKParams &prm, void *actions, int slot, cudaStream_t stream) {
+  grl_gym_patch_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm, (uint2 *)actions, slot);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_gym_finish(const GrlKParams &prm, int max_turns, const int32_t *stats, const int32_t *prev_stats,
+                                  const uint8_t *valid, const uint8_t *done, const int8_t *winner, int32_t *turns, int32_t *calls,
+                                  double *reward, uint8_t *terminated, uint8_t *truncated, int32_t *n_finished, cudaStream_t stream) {
+  grl_gym_finish_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm, max_turns, stats, prev_stats, valid, done, winner, turns,
+                                                                           calls, reward, terminated, truncated, n_finished);
   return cudaGetLastError();
 }
 

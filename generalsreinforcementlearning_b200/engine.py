@@ -17,7 +17,7 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 
 from . import _abi
-from ._abi import ACTION_DTYPE, BoundLibrary, Config, GymOutputs, StatePlanes, StepOutputs
+from ._abi import ACTION_DTYPE, BoundLibrary, Config, GymOutputs, GymStepIO, StatePlanes, StepOutputs
 
 
 def _ptr(buf) -> Optional[int]:
@@ -174,6 +174,18 @@ class BatchedEngine:
         """Discrete(N*5) indices -> grl_action slots, rejecting indices the gym mask forbids."""
         self.lib.check(self.lib.gym_encode(self._h, _ptr(action_idx), int(player), int(slot), _ptr(mask),
                                            1 if skip_invalid else 0, _ptr(actions), _ptr(valid)), "gym_encode")
+
+    def gym_step(self, max_turns: int, opponent_seed: int, **planes) -> None:
+        """One GeneralsEnv.step() for every env (grl_gym_step).  Keyword planes: action, opponent_action, obs, mask,
+        stats, actions, prev_stats, turns, calls, reward, terminated, truncated, valid, done, winner, step_error,
+        n_finished."""
+        io = GymStepIO()
+        for k, v in planes.items():
+            if k in ("obs", "mask", "stats"):
+                setattr(io.out, k, _ptr(v))
+            else:
+                setattr(io, k, _ptr(v))
+        self.lib.check(self.lib.gym_step(self._h, int(max_turns), int(opponent_seed), C.byref(io)), "gym_step")
 
     def sample_actions(self, policy_seed: int, actions=None):
         if actions is None:

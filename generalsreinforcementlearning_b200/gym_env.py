@@ -84,6 +84,10 @@ class GeneralsVecEnv:
         self._err = torch.zeros(B, dtype=torch.uint8, device=dev)
         self._turns = torch.zeros(B, dtype=torch.int32, device=dev)
         self._valid = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self._term = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self._trunc = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self._reward = torch.zeros(B, dtype=torch.float64, device=dev)
+        self._nfin = torch.zeros(1, dtype=torch.int32, device=dev)
         self._opp_draws = 0
         self._calls = torch.zeros(B, dtype=torch.int32, device=dev)   # step() calls this episode (incl. rejected actions)
         self._episode = np.zeros(B, dtype=np.int64)
@@ -97,15 +101,6 @@ class GeneralsVecEnv:
 
     def _refresh(self):
         self.engine.gym_observe(self.max_turns, self._obs, self._mask, self._stats)
-
-    def _random_opponent(self):
-        """The reference's default opponent: a uniformly random legal FULL move of player 1
-        (generals_env.py:443-497), none if it has none.  Drawn on the device by the library's
-        counter-based sampler (grl_sample_actions fills one slot per player; slot 0 is overwritten
-        by the agent's action afterwards)."""
-        self._opp_draws += 1
-        self.engine.sample_actions(self._base_seed * 1000003 + self._opp_draws, self._actions)
-        self._actions[:, 1, 5] = 1      # move_all: the random opponent never sends half moves (:483)
 
     # ------------------------------------------------------------------ gym API
     def reset(self, seed: Optional[int] = None, options=None) -> Tuple[Any, Dict[str, Any]]:
@@ -122,40 +117,29 @@ class GeneralsVecEnv:
 
     def step(self, action, opponent_action=None):
         """action: int64 [B] indices into Discrete(N*5) for player 0 (and ``opponent_action`` for
-        player 1 under self-play).  Returns (obs, reward, terminated, truncated, info)."""
+        player 1 under self-play; otherwise the reference's default random opponent, a uniformly
+        random legal full move drawn on the device).  Returns (obs, reward, terminated, truncated, info).
+
+        The whole step is ONE library call (``grl_gym_step``): action decoding with the client-side
+        rejection of masked-out indices (that env takes no turn, reward -0.1, generals_env.py:226-229),
+        the turn, the gym read-outs, the client's reward (:499-561, float64) and the episode flags."""
         t = self.torch
-        B = self.num_envs
         action = t.as_tensor(action, device=self.device).to(t.int64).contiguous()
+        oa = None
         if opponent_action is not None:
             oa = t.as_tensor(opponent_action, device=self.device).to(t.int64).contiguous()
-            self.engine.gym_encode(oa, 1, 1, self._mask, False, self._actions, None)
-        else:
-            self._random_opponent()
-        # an invalid agent action is rejected client-side: that env takes no turn (:226-229)
-        self.engine.gym_encode(action, 0, 0, self._mask, True, self._actions, self._valid)
-        valid = self._valid.bool()
-        self._prev_stats.copy_(self._stats)
-        self.engine.step_fused(self._actions, self.engine.outputs(done=self._done, winner=self._winner, step_error=self._err))
-        # the server rejects an invalid move before the turn runs (action_validator.go:126-127);
-        # the turn that did run may still have aborted (step_error) — the client only sees states
-        self._turns += valid.to(t.int32)
-        self._calls += 1
-        self._refresh()
-        st, pv = self._stats.to(t.float64), self._prev_stats.to(t.float64)
-        terminated = (self._done != 0) & valid
-        # the episode is cut at max_turns turns; an agent that keeps submitting rejected actions takes no turns, so
-        # it is also cut after max_turns step() calls (what the reference's trainers do: vector_env.py:170)
-        truncated = ((self._turns >= self.max_turns) & valid) | (self._calls >= self.max_turns)
-        # _calculate_reward (:499-561), python floats
-        shaped = (st[:, 0, 1] - pv[:, 0, 1]) * 1.0 + (st[:, 0, 0] - pv[:, 0, 0]) * 0.01
-        shaped = shaped + 50.0 * ((self._prev_stats[:, 1, 2] == 1) & (self._stats[:, 1, 2] == 0)).to(t.float64)
-        win = self._winner == 0
-        reward = t.where(terminated, t.where(win, t.full_like(shaped, 100.0), t.full_like(shaped, -100.0)), shaped)
-        reward = t.where(valid, reward, t.full_like(shaped, -0.1))
-        info: Dict[str, Any] = {"turn": self._turns.clone(), "invalid_action": ~valid,
+        self._opp_draws += 1
+        self.engine.gym_step(self.max_turns, self._base_seed * 1000003 + self._opp_draws, action=action, opponent_action=oa,
+                             obs=self._obs, mask=self._mask, stats=self._stats, actions=self._actions,
+                             prev_stats=self._prev_stats, turns=self._turns, calls=self._calls, reward=self._reward,
+                             terminated=self._term, truncated=self._trunc, valid=self._valid, done=self._done,
+                             winner=self._winner, step_error=self._err, n_finished=self._nfin)
+        terminated, truncated = self._term.bool(), self._trunc.bool()
+        info: Dict[str, Any] = {"turn": self._turns.clone(), "invalid_action": ~self._valid.bool(),
                                 "winner": self._winner.to(t.int32), "step_error": self._err.clone()}
-        finished = terminated | truncated
-        if bool(finished.any()):
+        reward = self._reward.clone()
+        if int(self._nfin.item()) > 0:   # the one host read of the step: does any env start a new episode?
+            finished = terminated | truncated
             ids = finished.nonzero(as_tuple=True)[0]
             info["final_observation"] = self._obs[ids, 0].clone()
             info["final_env_ids"] = ids

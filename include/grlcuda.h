@@ -249,6 +249,28 @@ int grl_gym_observe(grl_env *env, int32_t max_turns, const grl_gym_outputs *out)
 int grl_gym_encode(grl_env *env, const int64_t *action_idx, int32_t player, int32_t slot, const uint8_t *mask,
                    int32_t skip_invalid, grl_action *actions, uint8_t *valid);
 
+/* One GeneralsEnv.step() for every env in a single call (generals_env.py:210-289): decode the agent's
+ * (player 0) action and reject it client-side when the mask forbids it (that env then takes no turn,
+ * reward -0.1); the opponent (player 1) plays `opponent_action` or, when that is NULL, a uniformly random
+ * legal full move; Step; the gym read-outs of the new state; the client-side reward (:499-561, float64);
+ * terminated (game left IN_PROGRESS) / truncated (turns or step() calls reached max_turns).
+ * libgrlcuda.so requires device pointers for every plane; nothing is copied to the host. */
+typedef struct grl_gym_step_io {
+  const int64_t *action;          /* [B] in: Discrete(N*5) indices of player 0                              */
+  const int64_t *opponent_action; /* [B] in: indices of player 1, or NULL for the random opponent           */
+  grl_gym_outputs out;            /* in/out: mask and stats of the CURRENT state are read, all three rewritten */
+  grl_action *actions;            /* [B][max_actions] scratch                                                */
+  int32_t *prev_stats;            /* [B][P][4] scratch                                                       */
+  int32_t *turns, *calls;         /* [B] in/out: turns taken / step() calls of the running episode           */
+  double *reward;                 /* [B] out                                                                  */
+  uint8_t *terminated, *truncated, *valid; /* [B] out                                                        */
+  uint8_t *done;                  /* [B] out: Engine.IsGameOver                                              */
+  int8_t *winner;                 /* [B] out                                                                  */
+  uint8_t *step_error;            /* [B] out                                                                  */
+  int32_t *n_finished;            /* [1] out: number of envs with terminated | truncated                      */
+} grl_gym_step_io;
+int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const grl_gym_step_io *io);
+
 /* Draw the synthetic policy's actions for the current state into `actions`
  * ([B][max_actions], slot p = player p's move, empty when it has none). */
 int grl_sample_actions(grl_env *env, uint64_t policy_seed, grl_action *actions);

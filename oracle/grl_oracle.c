@@ -1512,6 +1512,61 @@ int grlo_gym_encode(grlo_env *e, const int64_t *action_idx, int32_t player, int3
   return GRL_OK;
 }
 
+int grlo_gym_observe(grlo_env *e, int32_t max_turns, const grl_gym_outputs *out);
+
+/* GeneralsEnv.step (generals_env.py:210-289) for every env; reward :499-561 in float64 like the client */
+int grlo_gym_step(grlo_env *e, int32_t max_turns, uint64_t opponent_seed, const grl_gym_step_io *io) {
+  if (!e || !io || !io->action || !io->out.mask || !io->out.stats || !io->actions || !io->prev_stats || !io->turns ||
+      !io->calls || !io->reward || !io->terminated || !io->truncated || !io->valid || !io->done || !io->winner ||
+      !io->step_error || max_turns < 1)
+    return GRL_ERR_INVALID_ARG;
+  int B = e->cfg.num_envs, P = e->cfg.num_players, A = e->cfg.max_actions;
+  if (P < 2 || A < 2) return GRL_ERR_INVALID_ARG;
+  memcpy(io->prev_stats, io->out.stats, sizeof(int32_t) * (size_t)B * P * 4);
+  int st;
+  if (io->opponent_action) {
+    memset(io->actions, 0, sizeof(grl_action) * (size_t)B * A);
+    if ((st = grlo_gym_encode(e, io->opponent_action, 1, 1, io->out.mask, 0, io->actions, NULL))) return st;
+  } else { /* the random opponent: a uniformly random legal FULL move (:443-497) */
+    if ((st = grlo_sample_actions(e, opponent_seed, io->actions))) return st;
+    for (int b = 0; b < B; b++) io->actions[(size_t)b * A + 1].move_all = 1;
+  }
+  if ((st = grlo_gym_encode(e, io->action, 0, 0, io->out.mask, 1, io->actions, io->valid))) return st;
+  grl_step_outputs so;
+  memset(&so, 0, sizeof(so));
+  so.done = io->done;
+  so.winner = io->winner;
+  so.step_error = io->step_error;
+  if ((st = grlo_step_fused(e, io->actions, 0, 0, &so))) return st;
+  if ((st = grlo_gym_observe(e, max_turns, &io->out))) return st;
+  int finished = 0;
+  for (int b = 0; b < B; b++) {
+    int valid = io->valid[b];
+    io->turns[b] += valid;
+    io->calls[b] += 1;
+    int terminated = io->done[b] && valid;
+    int truncated = (io->turns[b] >= max_turns && valid) || io->calls[b] >= max_turns;
+    const int32_t *cur = io->out.stats + (size_t)b * P * 4, *prev = io->prev_stats + (size_t)b * P * 4;
+    double r = 0.0;
+    if (!valid) {
+      r = -0.1;
+    } else if (terminated) {
+      r = io->winner[b] == 0 ? 100.0 : -100.0;
+    } else {
+      r += (double)(cur[1] - prev[1]) * 1.0;
+      r += (double)(cur[0] - prev[0]) * 0.01;
+      for (int q = 1; q < P; q++)
+        if (prev[q * 4 + 2] == 1 && cur[q * 4 + 2] == 0) r += 50.0;
+    }
+    io->reward[b] = r;
+    io->terminated[b] = (uint8_t)terminated;
+    io->truncated[b] = (uint8_t)truncated;
+    finished += terminated || truncated;
+  }
+  if (io->n_finished) *io->n_finished = finished;
+  return GRL_OK;
+}
+
 int grlo_gym_observe(grlo_env *e, int32_t max_turns, const grl_gym_outputs *out) {
   if (!e || !out || max_turns < 1) return GRL_ERR_INVALID_ARG;
   gym_ctx_t x = {e, max_turns, out};
