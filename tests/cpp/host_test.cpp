@@ -1,0 +1,727 @@
+// host_test.cpp — the reference's Go tests for the turn path, transliterated against the C++ host mirror
+// (generalsreinforcementlearning_b200/host).  Each TEST names the Go test it follows; the asserted values
+// are the reference's own.  The binary takes the library to bind:
+//
+//   host_test --lib <path/libgrlcuda.so> --prefix grl_      (GPU box: the product, `-m gpu`)
+//   host_test --lib <path/libgrloracle.so> --prefix grlo_   (no GPU: the CPU oracle's copy of the ABI —
+//                                                            checks the host layer's own logic)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../generalsreinforcementlearning_b200/host/grl_engine.hpp"
+
+using namespace grl;
+using core::MoveAction;
+using core::Tile;
+
+static std::shared_ptr<Library> g_lib;
+static int g_failures = 0, g_checks = 0;
+static const char *g_current = "";
+
+#define EXPECT(cond, ...)                                                          \
+  do {                                                                             \
+    g_checks++;                                                                    \
+    if (!(cond)) {                                                                 \
+      g_failures++;                                                                \
+      std::printf("  FAIL %s:%d [%s] %s — ", __FILE__, __LINE__, g_current, #cond); \
+      std::printf(__VA_ARGS__);                                                    \
+      std::printf("\n");                                                           \
+    }                                                                              \
+  } while (0)
+#define EXPECT_EQ(want, got, ...) EXPECT((want) == (got), __VA_ARGS__)
+#define REQUIRE(cond, ...)          \
+  do {                              \
+    const bool require_ok_ = bool(cond); \
+    EXPECT(require_ok_, __VA_ARGS__);    \
+    if (!require_ok_) return;       \
+  } while (0)
+
+struct TestCase {
+  const char *name;
+  std::function<void()> fn;
+};
+static std::vector<TestCase> &registry() {
+  static std::vector<TestCase> r;
+  return r;
+}
+struct Registrar {
+  Registrar(const char *n, std::function<void()> f) { registry().push_back({n, std::move(f)}); }
+};
+#define TEST(name)                          \
+  static void name();                       \
+  static Registrar reg_##name(#name, name); \
+  static void name()
+
+// ---- helpers in the style of the Go tests -------------------------------------------------------
+static std::shared_ptr<rand::Rand> newTestRNG() { return rand::New(rand::NewSource(12345)); }  // engine_test.go:15-17
+
+static std::unique_ptr<game::Engine> newEngine(int w, int h, int players, game::ExperienceCollector *c = nullptr) {
+  game::GameConfig cfg;
+  cfg.Width = w;
+  cfg.Height = h;
+  cfg.Players = players;
+  cfg.Rng = newTestRNG();
+  cfg.ExperienceCollector = c;
+  return game::NewEngine(context::Background(), cfg, g_lib);
+}
+
+// createTestEngineForActionMask (action_mask_test.go:16-55): a blank board, players alive with empty lists.
+static std::shared_ptr<game::EnginePool> g_keep;  // keeps hand-built engines' pools alive for a test
+static std::unique_ptr<game::Engine> createTestEngineForActionMask(int w, int h, int players) {
+  g_keep = std::make_shared<game::EnginePool>(g_lib, 1, w, h, players);
+  return g_keep->NewEngineFromBoard(*core::NewBoard(w, h), players);
+}
+
+// engine.updatePlayerStats() as the Go tests call it at turn 0 after editing the board by hand: the full
+// rebuild of stats.go:33-63.  Test-side only (the product computes stats on the device every turn); the
+// edited state is then uploaded to HBM.
+static void updatePlayerStats(game::Engine &e) {
+  game::GameState *gs = e.gs();
+  for (game::Player &p : gs->Players) {
+    p.OwnedTiles.clear();
+    p.ArmyCount = 0;
+    p.GeneralIdx = -1;
+  }
+  for (int i = 0; i < int(gs->Board->T.size()); i++) {
+    const Tile &t = gs->Board->T[i];
+    if (t.Owner < 0 || t.Owner >= int(gs->Players.size())) continue;
+    game::Player &p = gs->Players[t.Owner];
+    p.OwnedTiles.push_back(i);
+    p.ArmyCount += t.Army;
+    if (t.IsGeneral()) p.GeneralIdx = i;
+  }
+  for (game::Player &p : gs->Players) p.Alive = p.GeneralIdx != -1;
+  e.Upload();
+}
+
+static Tile mk(int owner, int army, int type) {
+  Tile t;
+  t.Owner = owner;
+  t.Army = army;
+  t.Type = type;
+  return t;
+}
+
+// ---- internal/game/engine_test.go -----------------------------------------------------------------
+TEST(TestNewEngine) {  // engine_test.go:25-63
+  int width = 8, height = 8, numPlayers = 2;
+  auto engine = newEngine(width, height, numPlayers);
+  REQUIRE(engine != nullptr, "Engine should not be nil");
+  game::GameState *gs = engine->gs();
+  REQUIRE(gs->Board != nullptr, "Board should not be nil");
+  EXPECT_EQ(width, gs->Board->W, "Board width mismatch");
+  EXPECT_EQ(height, gs->Board->H, "Board height mismatch");
+  REQUIRE(int(gs->Players.size()) == numPlayers, "Incorrect number of players");
+  EXPECT(!engine->IsGameOver(), "Game should not be over at start");
+  EXPECT_EQ(0, gs->Turn, "Initial turn should be 0");
+  int generalsFound = 0;
+  for (int i = 0; i < numPlayers; i++) {
+    const game::Player &player = gs->Players[i];
+    EXPECT(player.Alive, "Player %d should be alive", i);
+    EXPECT(player.GeneralIdx != -1, "Player %d should have a general assigned", i);
+    if (player.GeneralIdx != -1) {
+      const Tile &g = gs->Board->T[player.GeneralIdx];
+      EXPECT_EQ(i, g.Owner, "General tile owner mismatch for player %d", i);
+      EXPECT(g.IsGeneral(), "General tile type mismatch for player %d", i);
+      generalsFound++;
+    }
+    EXPECT(player.ArmyCount >= 1, "Player %d should have at least 1 army", i);
+  }
+  EXPECT_EQ(numPlayers, generalsFound, "All players should have a general on the board");
+}
+
+TEST(TestEngine_Step_BasicTurn) {  // engine_test.go:65-86
+  auto engine = newEngine(5, 5, 1);
+  REQUIRE(engine != nullptr, "Engine should not be nil");
+  int initialTurn = engine->gs()->Turn;
+  int initialArmy = engine->gs()->Players[0].ArmyCount;
+  core::Error err = engine->Step(context::Background(), {});
+  REQUIRE(!err, "Step: %s", err.String().c_str());
+  EXPECT_EQ(initialTurn + 1, engine->gs()->Turn, "Turn should increment");
+  EXPECT_EQ(initialArmy + 1, engine->gs()->Players[0].ArmyCount, "general production");
+  EXPECT(!engine->IsGameOver(), "Game should not be over with 1 player and no actions");
+}
+
+TEST(TestEngine_Step_GameOverReturnError) {  // engine_test.go:88-102
+  auto engine = newEngine(5, 5, 1);
+  REQUIRE(engine != nullptr, "nil engine");
+  engine->SetGameOver(true);  // engine.gameOver = true
+  core::Error err = engine->Step(context::Background(), {});
+  EXPECT(errors::Is(err, core::ErrGameOver), "Step should return ErrGameOver, got %s", err.String().c_str());
+  EXPECT(err.String().find("game turn 0 [step]: game is over") != std::string::npos, "message: %s", err.String().c_str());
+}
+
+TEST(TestEngine_Step_ContextCancelled) {  // turn_processor.go:31-36, 79-93
+  auto engine = newEngine(5, 5, 1);
+  REQUIRE(engine != nullptr, "nil engine");
+  context::Context ctx = context::Context::WithCancel();
+  ctx.Cancel();
+  core::Error err = engine->Step(ctx, {});
+  EXPECT(errors::Is(err, context::Canceled), "expected context.Canceled");
+  EXPECT_EQ(0, engine->gs()->Turn, "a cancelled Step takes no turn");
+}
+
+TEST(TestEngine_ProcessTurnProduction) {  // engine_test.go:104-182, through Step on turn 25 and turn 24
+  for (int scenario = 0; scenario < 2; scenario++) {
+    auto engine = newEngine(5, 5, 1);
+    REQUIRE(engine != nullptr, "nil engine");
+    game::GameState *gs = engine->gs();
+    int playerID = 0;
+    int generalIdx = gs->Players[0].GeneralIdx;
+    REQUIRE(generalIdx != -1, "Player should have a general");
+    int cityIdx = -1, landIdx = -1;
+    for (int i = 0; i < int(gs->Board->T.size()); i++) {
+      Tile &t = gs->Board->T[i];
+      if (t.Type == core::TileNormal && t.IsNeutral()) {
+        t = mk(playerID, 5, core::TileCity);
+        cityIdx = i;
+        break;
+      }
+    }
+    REQUIRE(cityIdx != -1, "Could not place a test city");
+    for (int i = 0; i < int(gs->Board->T.size()); i++) {
+      Tile &t = gs->Board->T[i];
+      if (t.Type == core::TileNormal && t.IsNeutral() && i != cityIdx && i != generalIdx) {
+        t.Owner = playerID;
+        t.Army = 2;
+        landIdx = i;
+        break;
+      }
+    }
+    REQUIRE(landIdx != -1, "Could not place test land");
+    // Step increments the turn first, so start one before the turn under test.
+    gs->Turn = scenario == 0 ? 24 : 23;
+    updatePlayerStats(*engine);
+    int g0 = gs->Board->T[generalIdx].Army, c0 = gs->Board->T[cityIdx].Army, l0 = gs->Board->T[landIdx].Army;
+    core::Error err = engine->Step(context::Background(), {});
+    REQUIRE(!err, "Step: %s", err.String().c_str());
+    gs = engine->gs();
+    EXPECT_EQ(g0 + 1, gs->Board->T[generalIdx].Army, "General production mismatch (scenario %d)", scenario);
+    EXPECT_EQ(c0 + 1, gs->Board->T[cityIdx].Army, "City production mismatch (scenario %d)", scenario);
+    EXPECT_EQ(l0 + (scenario == 0 ? 1 : 0), gs->Board->T[landIdx].Army, "Normal land production (scenario %d)", scenario);
+  }
+}
+
+TEST(TestEngine_PlayerEliminationAndTileTurnover) {  // engine_test.go:184-248
+  auto engine = newEngine(5, 5, 2);
+  REQUIRE(engine != nullptr, "nil engine");
+  game::GameState *gs = engine->gs();
+  core::Board &board = *gs->Board;
+  int p0AttackerIdx = board.Idx(0, 0);
+  board.T[p0AttackerIdx] = mk(0, 20, core::TileNormal);
+  int p1GeneralOriginalIdx = gs->Players[1].GeneralIdx;
+  REQUIRE(p1GeneralOriginalIdx != -1, "Player 1 should have a general from NewEngine");
+  int p1NewGeneralIdx = board.Idx(0, 1);
+  if (p1GeneralOriginalIdx != p1NewGeneralIdx) board.T[p1GeneralOriginalIdx] = mk(core::NeutralID, 0, core::TileNormal);
+  board.T[p1NewGeneralIdx] = mk(1, 1, core::TileGeneral);
+  gs->Players[1].GeneralIdx = p1NewGeneralIdx;
+  int p1CityIdx = board.Idx(1, 1);
+  board.T[p1CityIdx] = mk(1, 5, core::TileCity);
+  int p1LandIdx = board.Idx(2, 2);
+  board.T[p1LandIdx] = mk(1, 3, core::TileNormal);
+  REQUIRE(gs->Players[0].GeneralIdx != p1NewGeneralIdx, "Test setup conflict");
+  updatePlayerStats(*engine);
+
+  MoveAction action;
+  action.PlayerID = 0;
+  action.FromX = 0, action.FromY = 0, action.ToX = 0, action.ToY = 1;
+  action.MoveAll = true;
+  core::Error err = engine->Step(context::Background(), {action});
+  REQUIRE(!err, "Step should not error during capture: %s", err.String().c_str());
+
+  gs = engine->gs();
+  EXPECT(!gs->Players[1].Alive, "Player 1 should be eliminated");
+  EXPECT_EQ(-1, gs->Players[1].GeneralIdx, "Player 1 should have no general index");
+  EXPECT(gs->Players[0].Alive, "Player 0 should still be alive");
+  EXPECT_EQ(0, gs->Board->T[p1NewGeneralIdx].Owner, "Captured general tile should be owned by Player 0");
+  EXPECT_EQ(19, gs->Board->T[p1NewGeneralIdx].Army, "20 - 1 left - 1 defender + 1 production");
+  EXPECT_EQ(0, gs->Board->T[p1CityIdx].Owner, "Player 1's city should now be owned by Player 0");
+  EXPECT_EQ(6, gs->Board->T[p1CityIdx].Army, "5 + 1 production");
+  EXPECT_EQ(0, gs->Board->T[p1LandIdx].Owner, "Player 1's land should now be owned by Player 0");
+  EXPECT_EQ(3, gs->Board->T[p1LandIdx].Army, "no production for normal tiles on turn 1");
+  EXPECT(engine->IsGameOver(), "Game should be over after elimination");
+  EXPECT_EQ(0, engine->GetWinner(), "Player 0 should be the winner");
+}
+
+TEST(TestEngine_Step_ActionFromDeadPlayer) {  // engine_test.go:250-303
+  auto engine = newEngine(5, 5, 2);
+  REQUIRE(engine != nullptr, "nil engine");
+  game::GameState *gs = engine->gs();
+  core::Board &board = *gs->Board;
+  if (gs->Players[1].GeneralIdx != -1) board.T[gs->Players[1].GeneralIdx] = mk(core::NeutralID, 0, core::TileNormal);
+  gs->Players[1].Alive = false;
+  gs->Players[1].GeneralIdx = -1;
+  int p0TileIdx = board.Idx(0, 0);
+  board.T[p0TileIdx] = mk(0, 10, core::TileNormal);
+  int p1OwnedTileIdx = board.Idx(1, 1);
+  board.T[p1OwnedTileIdx] = mk(1, 5, core::TileNormal);
+  // the Go test edits tiles without refreshing the cached lists; P0's move validates against ownership only
+  engine->Upload();
+
+  MoveAction dead, live;
+  dead.PlayerID = 1, dead.FromX = 1, dead.FromY = 1, dead.ToX = 1, dead.ToY = 2, dead.MoveAll = true;
+  live.PlayerID = 0, live.FromX = 0, live.FromY = 0, live.ToX = 0, live.ToY = 1, live.MoveAll = true;
+  core::Error err = engine->Step(context::Background(), {dead, live});
+  REQUIRE(!err, "Step: %s", err.String().c_str());
+  gs = engine->gs();
+  EXPECT_EQ(1, gs->Board->T[p1OwnedTileIdx].Owner, "P1's tile ownership should not change");
+  EXPECT_EQ(5, gs->Board->T[p1OwnedTileIdx].Army, "P1's tile army should not change");
+  EXPECT_EQ(1, gs->Board->T[p0TileIdx].Army, "P0's original tile should have 1 army left");
+  const Tile &target = gs->Board->T[gs->Board->Idx(0, 1)];
+  EXPECT_EQ(0, target.Owner, "P0 should own target tile (0,1)");
+  EXPECT_EQ(9, target.Army, "P0's target tile army count is wrong");
+  EXPECT(gs->Players[0].Alive, "Player 0 should be alive");
+  EXPECT(!gs->Players[1].Alive, "Player 1 should remain dead");
+}
+
+// ---- internal/game/action_mask_test.go -------------------------------------------------------------
+static int countTrue(const std::vector<bool> &m) {
+  int n = 0;
+  for (bool b : m) n += b ? 1 : 0;
+  return n;
+}
+
+TEST(TestGetLegalActionMask_BasicScenario) {  // action_mask_test.go:57-103
+  auto engine = createTestEngineForActionMask(3, 3, 2);
+  REQUIRE(engine != nullptr, "nil engine");
+  int centerIdx = engine->gs()->Board->Idx(1, 1);
+  engine->gs()->Board->T[centerIdx].Owner = 0;
+  engine->gs()->Board->T[centerIdx].Army = 5;
+  engine->gs()->Players[0].OwnedTiles = {centerIdx};
+  engine->Upload();
+  std::vector<bool> mask = engine->GetLegalActionMask(0);
+  EXPECT_EQ(36, int(mask.size()), "mask length");
+  int base = (1 * 3 + 1) * 4;
+  EXPECT(mask[base + 0], "Should be able to move up");
+  EXPECT(mask[base + 1], "Should be able to move right");
+  EXPECT(mask[base + 2], "Should be able to move down");
+  EXPECT(mask[base + 3], "Should be able to move left");
+  EXPECT_EQ(4, countTrue(mask), "Should have exactly 4 legal moves");
+}
+
+TEST(TestGetLegalActionMask_EdgeTiles) {  // action_mask_test.go:105-127
+  auto engine = createTestEngineForActionMask(3, 3, 1);
+  REQUIRE(engine != nullptr, "nil engine");
+  int cornerIdx = engine->gs()->Board->Idx(0, 0);
+  engine->gs()->Board->T[cornerIdx].Owner = 0;
+  engine->gs()->Board->T[cornerIdx].Army = 3;
+  engine->gs()->Players[0].OwnedTiles = {cornerIdx};
+  engine->Upload();
+  std::vector<bool> mask = engine->GetLegalActionMask(0);
+  EXPECT(!mask[0], "Cannot move up from top edge");
+  EXPECT(mask[1], "Should be able to move right");
+  EXPECT(mask[2], "Should be able to move down");
+  EXPECT(!mask[3], "Cannot move left from left edge");
+}
+
+TEST(TestGetLegalActionMask_InsufficientArmy) {  // action_mask_test.go:129-167
+  auto engine = createTestEngineForActionMask(3, 3, 1);
+  REQUIRE(engine != nullptr, "nil engine");
+  core::Board &b = *engine->gs()->Board;
+  int t1 = b.Idx(0, 0), t2 = b.Idx(1, 1);
+  b.T[t1].Owner = 0, b.T[t1].Army = 1;
+  b.T[t2].Owner = 0, b.T[t2].Army = 2;
+  engine->gs()->Players[0].OwnedTiles = {t1, t2};
+  engine->Upload();
+  std::vector<bool> mask = engine->GetLegalActionMask(0);
+  for (int d = 0; d < 4; d++) EXPECT(!mask[t1 * 4 + d], "Should not be able to move from tile with 1 army");
+  bool any = false;
+  for (int d = 0; d < 4; d++) any = any || mask[t2 * 4 + d];
+  EXPECT(any, "Should have at least one legal move from tile with 2 armies");
+}
+
+TEST(TestGetLegalActionMask_Mountains) {  // action_mask_test.go:169-202
+  auto engine = createTestEngineForActionMask(3, 3, 1);
+  REQUIRE(engine != nullptr, "nil engine");
+  core::Board &b = *engine->gs()->Board;
+  int c = b.Idx(1, 1);
+  b.T[c].Owner = 0, b.T[c].Army = 5;
+  engine->gs()->Players[0].OwnedTiles = {c};
+  for (int dx = -1; dx <= 1; dx++)
+    for (int dy = -1; dy <= 1; dy++)
+      if (dx || dy) b.T[b.Idx(1 + dx, 1 + dy)].Type = core::TileMountain;
+  engine->Upload();
+  std::vector<bool> mask = engine->GetLegalActionMask(0);
+  for (int d = 0; d < 4; d++) EXPECT(!mask[c * 4 + d], "Should not be able to move to mountain tile");
+}
+
+TEST(TestGetLegalActionMask_DeadPlayer) {  // action_mask_test.go:204-222
+  auto engine = createTestEngineForActionMask(3, 3, 2);
+  REQUIRE(engine != nullptr, "nil engine");
+  core::Board &b = *engine->gs()->Board;
+  int t = b.Idx(1, 1);
+  b.T[t].Owner = 0, b.T[t].Army = 10;
+  engine->gs()->Players[0].OwnedTiles = {t};
+  engine->gs()->Players[0].Alive = false;
+  engine->Upload();
+  EXPECT_EQ(0, countTrue(engine->GetLegalActionMask(0)), "Dead player should have no legal moves");
+}
+
+TEST(TestGetLegalActionMask_InvalidPlayer) {  // action_mask_test.go:224-243
+  auto engine = createTestEngineForActionMask(3, 3, 2);
+  REQUIRE(engine != nullptr, "nil engine");
+  std::vector<bool> mask = engine->GetLegalActionMask(-1);
+  EXPECT_EQ(36, int(mask.size()), "len");
+  EXPECT_EQ(0, countTrue(mask), "Invalid player should have no legal moves");
+  mask = engine->GetLegalActionMask(5);
+  EXPECT_EQ(36, int(mask.size()), "len");
+  EXPECT_EQ(0, countTrue(mask), "Invalid player should have no legal moves");
+}
+
+TEST(TestGetLegalActionMask_ComplexScenario) {  // action_mask_test.go:245-292
+  auto engine = createTestEngineForActionMask(5, 5, 2);
+  REQUIRE(engine != nullptr, "nil engine");
+  core::Board &b = *engine->gs()->Board;
+  const int tiles[4][3] = {{1, 1, 5}, {2, 1, 1}, {3, 3, 3}, {0, 0, 2}};
+  std::vector<int> owned;
+  for (auto &t : tiles) {
+    int idx = b.Idx(t[0], t[1]);
+    b.T[idx].Owner = 0, b.T[idx].Army = t[2];
+    owned.push_back(idx);
+  }
+  engine->gs()->Players[0].OwnedTiles = owned;
+  b.T[b.Idx(1, 2)].Type = core::TileMountain;
+  engine->Upload();
+  std::vector<bool> mask = engine->GetLegalActionMask(0);
+  int legal = countTrue(mask);
+  EXPECT(legal > 0, "Should have some legal moves");
+  EXPECT(legal < 20, "Should not have too many legal moves");
+  EXPECT_EQ(9, legal, "(1,1): U,R,L = 3; (3,3): 4; (0,0): R,D = 2");
+  EXPECT(!mask[(1 * 5 + 1) * 4 + 2], "Should not be able to move into mountain");
+}
+
+// ---- internal/game/core/action_test.go:23-186: every case through the host-side Validate AND through
+//      Step on the device (same sentinel either way) ----------------------------------------------------
+struct ValidateCase {
+  const char *name;
+  MoveAction action;
+  int fromOwner, fromArmy;  // tile (FromX,FromY) when in bounds; owner -2: leave the board untouched
+  bool mountainTarget;
+  const core::Sentinel *want;  // nullptr: valid
+};
+
+static MoveAction mv(int fx, int fy, int tx, int ty, bool all = false) {
+  MoveAction m;
+  m.PlayerID = 0, m.FromX = fx, m.FromY = fy, m.ToX = tx, m.ToY = ty, m.MoveAll = all;
+  return m;
+}
+
+TEST(TestMoveAction_Validate) {
+  const int W = 5, H = 5;
+  const std::vector<ValidateCase> cases = {
+      {"ValidMove", mv(1, 1, 1, 2, true), 0, 5, false, nullptr},
+      {"FromXNegative", mv(-1, 1, 0, 1), 0, 5, false, &core::ErrInvalidCoordinates},
+      {"FromXTooLarge", mv(W, 1, 0, 1), 0, 5, false, &core::ErrInvalidCoordinates},
+      {"FromYNegative", mv(1, -1, 1, 0), 0, 5, false, &core::ErrInvalidCoordinates},
+      {"FromYTooLarge", mv(1, H, 1, 0), 0, 5, false, &core::ErrInvalidCoordinates},
+      {"ToXNegative", mv(1, 1, -1, 1), 0, 5, false, &core::ErrInvalidCoordinates},
+      {"ToXTooLarge", mv(1, 1, W, 1), 0, 5, false, &core::ErrInvalidCoordinates},
+      {"ToYNegative", mv(1, 1, 1, -1), 0, 5, false, &core::ErrInvalidCoordinates},
+      {"ToYTooLarge", mv(1, 1, 1, H), 0, 5, false, &core::ErrInvalidCoordinates},
+      {"MoveToSelf", mv(1, 1, 1, 1), 0, 10, false, &core::ErrMoveToSelf},
+      {"NotAdjacent", mv(1, 1, 3, 3), 0, 10, false, &core::ErrNotAdjacent},
+      {"NotAdjacentButSameRowFar", mv(1, 1, 3, 1), 0, 10, false, &core::ErrNotAdjacent},
+      {"NotOwned", mv(1, 1, 1, 2), 1, 10, false, &core::ErrNotOwned},
+      {"InsufficientArmy_ArmyIs1", mv(1, 1, 1, 2), 0, 1, false, &core::ErrInsufficientArmy},
+      {"InsufficientArmy_ArmyIs0", mv(1, 1, 1, 2), 0, 0, false, &core::ErrInsufficientArmy},
+      {"TargetIsMountain", mv(1, 1, 1, 2), 0, 10, true, &core::ErrTargetIsMountain},
+  };
+  for (const ValidateCase &tc : cases) {
+    auto board = core::NewBoard(W, H);
+    if (board->InBounds(tc.action.FromX, tc.action.FromY)) {
+      Tile &f = board->T[board->Idx(tc.action.FromX, tc.action.FromY)];
+      f.Owner = tc.fromOwner;
+      f.Army = tc.fromArmy;
+    }
+    if (tc.mountainTarget) board->T[board->Idx(tc.action.ToX, tc.action.ToY)].Type = core::TileMountain;
+    core::Error err = tc.action.Validate(*board, 0);
+    if (tc.want)
+      EXPECT(errors::Is(err, *tc.want), "%s: Validate gave %s", tc.name, err.String().c_str());
+    else
+      EXPECT(!err, "%s: Validate gave %s", tc.name, err.String().c_str());
+
+    // the same case through Engine.Step: the device reports the same sentinel (step_error plane)
+    game::EnginePool pool(g_lib, 1, W, H, 2);
+    auto engine = pool.NewEngineFromBoard(*board, 2);
+    REQUIRE(engine != nullptr, "nil engine");
+    core::Error serr = engine->Step(context::Background(), {tc.action});
+    if (tc.want) {
+      EXPECT(errors::Is(serr, *tc.want), "%s: Step gave %s", tc.name, serr.String().c_str());
+      EXPECT(serr.String().find("game turn 1 [action processing]: game turn 1 [processing actions]: ") == 0,
+             "%s: wrapping %s", tc.name, serr.String().c_str());
+    } else {
+      EXPECT(!serr, "%s: Step gave %s", tc.name, serr.String().c_str());
+    }
+    EXPECT_EQ(1, engine->gs()->Turn, "%s: the turn counter advances even when the action fails (SURVEY Q5)", tc.name);
+  }
+}
+
+// ---- internal/game/core/movement_test.go:71-235 TestApplyMoveAction_BasicMovement, at engine level ------
+TEST(TestApplyMoveAction_BasicMovement) {
+  struct Row {
+    const char *name;
+    int fo, fa, to, ta;
+    bool moveAll;
+    int expFrom, expTo, expOwner;
+  };
+  const Row rows[] = {
+      {"move all to own tile", 0, 10, 0, 5, true, 1, 14, 0},
+      {"move half to own tile", 0, 10, 0, 5, false, 5, 10, 0},
+      {"capture neutral tile", 0, 10, -1, 3, true, 1, 6, 0},
+      {"failed attack on enemy tile", 0, 5, 1, 10, true, 1, 6, 1},
+      {"exact army match (no capture)", 0, 6, 1, 5, true, 1, 0, 1},
+      {"move half with odd number", 0, 3, 0, 0, false, 2, 1, 0},
+  };
+  for (const Row &r : rows) {
+    auto board = core::NewBoard(3, 3);
+    board->T[0] = mk(r.fo, r.fa, core::TileNormal);
+    board->T[1] = mk(r.to, r.ta, core::TileNormal);
+    game::EnginePool pool(g_lib, 1, 3, 3, 2);
+    auto engine = pool.NewEngineFromBoard(*board, 2);
+    REQUIRE(engine != nullptr, "nil engine");
+    core::Error err = engine->Step(context::Background(), {mv(0, 0, 1, 0, r.moveAll)});
+    EXPECT(!err, "%s: %s", r.name, err.String().c_str());
+    game::GameState gs = engine->GameState();
+    EXPECT_EQ(r.expFrom, gs.Board->T[0].Army, "%s: from army", r.name);
+    EXPECT_EQ(r.expTo, gs.Board->T[1].Army, "%s: to army", r.name);
+    EXPECT_EQ(r.expOwner, gs.Board->T[1].Owner, "%s: to owner", r.name);
+    std::map<int, bool> changed = engine->GetChangedTiles();
+    EXPECT(changed.count(0) && changed.count(1), "%s: both tiles enter ChangedTiles (movement.go:57-60)", r.name);
+    bool captured = r.expOwner == 0 && r.to != 0;
+    EXPECT_EQ(captured ? size_t(1) : size_t(0), engine->GetVisibilityChangedTiles().count(1), "%s: vis-changed", r.name);
+  }
+}
+
+// ---- visibility.go:153-190 / visibility_optimized.go:166-195 ------------------------------------------
+TEST(TestComputePlayerVisibility) {
+  auto engine = newEngine(8, 8, 2);
+  REQUIRE(engine != nullptr, "nil engine");
+  game::GameState gs = engine->GameState();
+  for (int p = 0; p < 2; p++) {
+    game::PlayerVisibility vis = engine->ComputePlayerVisibility(p);
+    REQUIRE(int(vis.VisibleTiles.size()) == 64 && int(vis.FogTiles.size()) == 64, "sizes");
+    auto gxy = gs.Board->XY(gs.Players[p].GeneralIdx);
+    for (int i = 0; i < 64; i++) {
+      auto xy = gs.Board->XY(i);
+      bool near = std::abs(xy.first - gxy.first) <= 1 && std::abs(xy.second - gxy.second) <= 1;
+      EXPECT_EQ(near, bool(vis.VisibleTiles[i]), "player %d tile %d: 3x3 around the general at turn 0", p, i);
+      EXPECT_EQ(gs.Board->T[i].IsVisibleTo(p), bool(vis.VisibleTiles[i]), "bitfield agrees");
+      EXPECT_EQ(!near && gs.Board->T[i].Type != core::TileNormal, bool(vis.FogTiles[i]), "fog = special tiles out of sight");
+    }
+  }
+}
+
+// ---- experience_collector.go:4-10 + turn_processor.go:182-217 + experience/collector.go:30-98 ----------
+struct RecordingCollector : game::ExperienceCollector {
+  int transitions = 0, ends = 0;
+  int prevTurn = -1, currTurn = -1;
+  std::map<int, game::Action> lastActions;
+  int prevArmyAtFrom = -1;
+  void OnStateTransition(const game::GameState *prev, const game::GameState *curr,
+                         const std::map<int, game::Action> &actions) override {
+    transitions++;
+    prevTurn = prev->Turn;
+    currTurn = curr->Turn;
+    lastActions = actions;
+    for (const auto &kv : actions) prevArmyAtFrom = prev->Board->T[kv.second.From.ToIndex(prev->Board->W)].Army;
+  }
+  void OnGameEnd(const game::GameState *) override { ends++; }
+};
+
+TEST(TestExperienceCollection) {
+  RecordingCollector rec;
+  auto engine = newEngine(5, 5, 2, &rec);
+  REQUIRE(engine != nullptr, "nil engine");
+  EXPECT(engine->GetExperienceCollector() == &rec, "collector attached");
+  // let the general grow, then move it out
+  for (int i = 0; i < 2; i++) REQUIRE(!engine->Step(context::Background(), {}), "idle step");
+  EXPECT_EQ(2, rec.transitions, "OnStateTransition runs every turn, with an empty action map when nobody moved (got %d)", rec.transitions);
+  game::GameState gs = engine->GameState();
+  int g = gs.Players[0].GeneralIdx;
+  auto xy = gs.Board->XY(g);
+  std::vector<bool> mask = engine->GetLegalActionMask(0);
+  const int dxs[4] = {0, 1, 0, -1}, dys[4] = {-1, 0, 1, 0};
+  int dir = -1;
+  for (int d = 0; d < 4; d++)
+    if (mask[g * 4 + d]) {
+      dir = d;
+      break;
+    }
+  REQUIRE(dir >= 0, "the general (army 4) has a legal move");
+  MoveAction m = mv(xy.first, xy.second, xy.first + dxs[dir], xy.second + dys[dir], true);
+  std::vector<float> before = engine->StateTensor(0);
+  std::vector<bool> smask = engine->SerializerActionMask(0);
+  int armyBefore = gs.Board->T[g].Army;
+  REQUIRE(!engine->Step(context::Background(), {m}), "move step");
+  EXPECT_EQ(3, rec.transitions, "one more transition");
+  EXPECT_EQ(2, rec.prevTurn, "prev state is the clone taken before Turn++");
+  EXPECT_EQ(3, rec.currTurn, "curr state is the engine's state after the turn");
+  EXPECT_EQ(armyBefore, rec.prevArmyAtFrom, "prev state is a deep copy (state.go:37-70)");
+  REQUIRE(rec.lastActions.count(0) == 1, "player 0's action is in the map");
+  EXPECT(rec.lastActions[0].From == m.GetFrom() && rec.lastActions[0].To == m.GetTo(), "action coordinates");
+  const experience::Transition *t = engine->LastTransition(0);
+  REQUIRE(t != nullptr, "transition for the acting player");
+  EXPECT(engine->LastTransition(1) == nullptr, "no record for a player that did not act (collector.go:33-36)");
+  EXPECT_EQ(3, t->Turn, "Turn = currState.Turn");
+  EXPECT(t->State == before, "State = StateToTensor(prevState)");
+  EXPECT(t->NextState == engine->StateTensor(0), "NextState = StateToTensor(currState)");
+  EXPECT(t->ActionMask == smask, "ActionMask = GenerateActionMask(prevState)");
+  // ActionToIndex uses the serializer's direction order up,down,left,right (serializer.go:179-198)
+  const int udlr[4] = {0, 3, 1, 2};  // engine dir U,R,D,L -> serializer dir
+  EXPECT_EQ(g * 4 + udlr[dir], t->Action, "action index");
+  EXPECT(t->ActionMask[t->Action], "the move taken was legal in the serializer's mask");
+  EXPECT(!t->Done, "game not over");
+  EXPECT(std::fabs(t->Reward - engine->LastReward(0)) == 0.f, "reward plane");
+  // territory +1 (0.01) + army: general 4 -> 1 stays +1 production, 3 move to a neutral tile ...: just sign
+  EXPECT(t->Reward > 0.f, "capturing a neutral tile is rewarded, got %g", double(t->Reward));
+  EXPECT_EQ(0, rec.ends, "OnGameEnd only when the game ends");
+}
+
+// ---- the pool: many games, one launch per turn --------------------------------------------------------
+TEST(TestEnginePool_SlotsAreIndependentGames) {
+  const int B = 6, W = 10, H = 10, P = 2;
+  game::EnginePool pool(g_lib, B, W, H, P);
+  std::vector<std::unique_ptr<game::Engine>> slots, solo;
+  for (int i = 0; i < B; i++) {
+    game::GameConfig cfg;
+    cfg.Width = W, cfg.Height = H, cfg.Players = P;
+    cfg.Rng = rand::New(rand::NewSource(12345 + i));
+    slots.push_back(pool.NewEngine(context::Background(), cfg));
+    solo.push_back(game::NewEngine(context::Background(), cfg, g_lib));
+    REQUIRE(slots.back() && solo.back(), "engines");
+  }
+  game::GameConfig extra;
+  extra.Width = W, extra.Height = H, extra.Players = P;
+  EXPECT(pool.NewEngine(context::Background(), extra) == nullptr, "a full pool hands out nil");
+  extra.Width = 7;
+  EXPECT(pool.NewEngine(context::Background(), extra) == nullptr, "so does a shape mismatch");
+
+  uint64_t launches0 = pool.LaunchCount();
+  for (int turn = 0; turn < 30; turn++) {
+    // every other slot sits out every third turn (its players have not all submitted yet)
+    std::map<int, std::vector<core::Action>> perSlot;
+    for (int i = 0; i < B; i++) {
+      if (i % 2 == 1 && turn % 3 == 2) continue;
+      std::vector<core::Action> acts;
+      for (int p = 0; p < P; p++) {
+        std::vector<bool> mask = slots[i]->GetLegalActionMask(p);
+        int n = countTrue(mask);
+        if (!n) continue;
+        int k = (turn * 7 + i * 3 + p) % n;
+        for (int a = 0; a < int(mask.size()); a++)
+          if (mask[a] && k-- == 0) {
+            const int dxs[4] = {0, 1, 0, -1}, dys[4] = {-1, 0, 1, 0};
+            int tile = a / 4, d = a % 4;
+            MoveAction m = mv(tile % W, tile / W, tile % W + dxs[d], tile / W + dys[d], (turn + p) % 2 == 0);
+            m.PlayerID = p;
+            acts.push_back(m);
+            break;
+          }
+      }
+      perSlot[i] = acts;
+    }
+    std::map<int, core::Error> errs = pool.StepAll(context::Background(), perSlot);
+    EXPECT_EQ(perSlot.size(), errs.size(), "one error entry per stepped slot");
+    for (const auto &kv : perSlot) {
+      EXPECT(!errs[kv.first], "slot %d turn %d: %s", kv.first, turn, errs[kv.first].String().c_str());
+      core::Error e2 = solo[kv.first]->Step(context::Background(), kv.second);
+      EXPECT(!e2, "solo %d: %s", kv.first, e2.String().c_str());
+    }
+    for (int i = 0; i < B; i++) {
+      game::GameState a = slots[i]->GameState(), b = solo[i]->GameState();
+      bool same = a.Turn == b.Turn && a.ChangedTiles == b.ChangedTiles;
+      for (int t = 0; same && t < W * H; t++) {
+        const Tile &x = a.Board->T[t], &y = b.Board->T[t];
+        same = x.Owner == y.Owner && x.Army == y.Army && x.Type == y.Type && x.VisibleBitfield == y.VisibleBitfield;
+      }
+      for (int p = 0; same && p < P; p++)
+        same = a.Players[p].OwnedTiles == b.Players[p].OwnedTiles && a.Players[p].ArmyCount == b.Players[p].ArmyCount;
+      EXPECT(same, "slot %d equals its private engine after turn %d", i, turn);
+    }
+  }
+  if (g_lib->path().find("libgrlcuda") != std::string::npos) {
+    // masks and state reads launch read-out kernels too; the turns themselves are one launch per StepAll
+    EXPECT(pool.LaunchCount() - launches0 >= 30, "the CUDA library launched kernels (%llu)",
+           (unsigned long long)(pool.LaunchCount() - launches0));
+  }
+  slots[2].reset();  // a finished game frees its slot
+  game::GameConfig again;
+  again.Width = W, again.Height = H, again.Players = P;
+  again.Rng = newTestRNG();
+  auto reused = pool.NewEngine(context::Background(), again);
+  REQUIRE(reused != nullptr, "freed slot is reusable");
+  EXPECT_EQ(2, reused->Slot(), "same slot");
+  EXPECT_EQ(0, reused->gs()->Turn, "fresh game");
+}
+
+// ---- rendering.go:34-143 ----------------------------------------------------------------------------
+TEST(TestBoardRendering) {
+  auto engine = createTestEngineForActionMask(3, 2, 2);
+  REQUIRE(engine != nullptr, "nil engine");
+  core::Board &b = *engine->gs()->Board;
+  b.T[0] = mk(0, 7, core::TileGeneral);
+  b.T[1] = mk(0, 12, core::TileNormal);
+  b.T[2] = mk(-1, 0, core::TileMountain);
+  b.T[3] = mk(-1, 40, core::TileCity);
+  b.T[4] = mk(-1, 0, core::TileNormal);
+  b.T[5] = mk(1, 150, core::TileNormal);
+  for (Tile &t : b.T) t.VisibleBitfield = 1;  // player 0 sees everything
+  b.T[5].VisibleBitfield = 2;                 // except the far corner
+  engine->Upload();
+  const std::string R = "\033[0m", G = "\033[90m", Wh = "\033[37m", Red = "\033[31m", Blue = "\033[34m";
+  std::string want = "     0 1 2\n";
+  want += " 0 " + Red + "A\xE2\x99\x94" + R + " " + Red + "A12" + R + " " + G + " \xE2\x96\xB2" + R + " \n";
+  want += " 1 " + Wh + " \xE2\xAC\xA2" + R + " " + G + " \xC2\xB7" + R + " " + G + " " + R + " \n";
+  want += "\n\xC2\xB7=empty \xE2\xAC\xA2=city \xE2\x99\x94=general \xE2\x96\xB2=mountain A-H=players\n";
+  EXPECT(engine->Board(0) == want, "Board(0):\n%s\nwant:\n%s", engine->Board(0).c_str(), want.c_str());
+  std::string all = engine->Board(-1);  // spectator: no fog (rendering.go:96)
+  EXPECT(all.find(Blue + "B+" + R) != std::string::npos, "spectator sees player 1's 150-army tile as B+");
+}
+
+// ---- the product binding must not fall back to anything ---------------------------------------------
+TEST(TestLibraryMissingFailsLoudly) {
+  bool threw = false;
+  try {
+    Library::Open("/nonexistent/libgrlcuda.so", "grl_");
+  } catch (const std::runtime_error &) {
+    threw = true;
+  }
+  EXPECT(threw, "a missing library is an error, not a fallback");
+}
+
+int main(int argc, char **argv) {
+  std::string lib, prefix = "grl_", only;
+  for (int i = 1; i < argc; i++) {
+    if (!std::strcmp(argv[i], "--lib") && i + 1 < argc) lib = argv[++i];
+    else if (!std::strcmp(argv[i], "--prefix") && i + 1 < argc) prefix = argv[++i];
+    else if (!std::strcmp(argv[i], "--only") && i + 1 < argc) only = argv[++i];
+  }
+  try {
+    g_lib = lib.empty() ? Library::Default() : Library::Open(lib, prefix);
+  } catch (const std::exception &e) {
+    std::printf("cannot bind the engine library: %s\n", e.what());
+    return 2;
+  }
+  std::printf("bound %s (prefix %s)\n", g_lib->path().c_str(), prefix.c_str());
+  int ran = 0;
+  for (const TestCase &t : registry()) {
+    if (!only.empty() && only != t.name) continue;
+    g_current = t.name;
+    int before = g_failures;
+    try {
+      t.fn();
+    } catch (const std::exception &e) {
+      g_failures++;
+      std::printf("  EXCEPTION [%s] %s\n", t.name, e.what());
+    }
+    g_keep.reset();
+    std::printf("%s %s\n", g_failures == before ? "ok  " : "FAIL", t.name);
+    ran++;
+  }
+  std::printf("%d tests, %d checks, %d failures\n", ran, g_checks, g_failures);
+  return g_failures ? 1 : 0;
+}
