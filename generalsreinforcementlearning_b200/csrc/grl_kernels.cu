@@ -347,15 +347,16 @@ __device__ __forceinline__ PackedAction pack_action(int player, int fx, int fy, 
 // Synthetic policy: player p draws uniformly from the set bits of its engine mask
 // in flat-index order (tile-major, dirs U,R,D,L).  Warp-uniform result.
 template <int LG>
-__device__ __forceinline__ PackedAction sample_policy_action(const GrlKParams &prm, const DirMasks &dm, uint32_t src,
-                                                             int p, uint64_t env_global, uint32_t turn, const Geo &g) {
+__device__ __forceinline__ PackedAction sample_policy_action(const GrlKParams &prm, uint64_t seed, const DirMasks &dm,
+                                                             uint32_t src, int p, uint64_t env_global, uint32_t turn,
+                                                             const Geo &g) {
   PackedAction none;
   none.lo = none.hi = 0;
   uint32_t U = src & dm.up, R = src & dm.right, D = src & dm.down, Lm = src & dm.left;
   int cnt = __popc(U) + __popc(R) + __popc(D) + __popc(Lm);
   int total = __reduce_add_sync(g.seg, cnt);
   if (total == 0) return none;
-  uint64_t r = policy_draw(prm.policy_seed, env_global, (uint64_t)turn, (uint64_t)p);
+  uint64_t r = policy_draw(seed, env_global, (uint64_t)turn, (uint64_t)p);
   int k = (int)((uint32_t)r % (uint32_t)total);
   int incl = cnt;  // inclusive prefix sum over the group's lanes
 #pragma unroll
@@ -410,6 +411,25 @@ __device__ __forceinline__ PackedAction sample_policy_action(const GrlKParams &p
 template <int PT, int LG>
 __device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t *s_act,
                                           uint32_t alive, uint32_t turn_before, int game, Geo g, int W, int H, int N, int NW);
+
+// Fused gym step, before the turn: decode the agent's (player 0) Discrete(N*5) index against the gym mask of the
+// CURRENT state (client-side rejection, generals_env.py:226-229), then the opponent's index or the random
+// opponent's draw; decoded moves go to s_act.  Returns whether the agent's action is valid.
+template <int PT, int LG>
+__device__ __noinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK &gk, uint32_t *s, const uint32_t *st,
+                                           uint32_t *s_act, uint32_t alive, bool over, uint32_t turn_before, int game, Geo g,
+                                           int W, int H, int N, int NW);
+__host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N);
+template <int NT>
+__device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+                                         float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats,
+                                         const uint32_t *s, const uint32_t *stt, uint32_t *sw, int game, int lane,
+                                         const Geo &g);
+template <int PT, int N>
+__device__ __forceinline__ void gym_emit_quads(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+                                               float *__restrict__ obs, uint8_t *__restrict__ mask,
+                                               int32_t *__restrict__ stats, const uint32_t *s, const uint32_t *stt,
+                                               const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g);
 
 // Elimination orders: tile turnover over the eliminated player's cached list, then the stats
 // rebuild of engine.go:101-109.  Reads and writes own/list/changed/vchg words in the slab.
@@ -642,9 +662,10 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
   __syncwarp();
 }
 
-template <int PT, int TW, int TH, int LG, bool DO_STEP, bool DO_OUT>
+template <int PT, int TW, int TH, int LG, bool DO_STEP, bool DO_OUT, bool GYM>
 __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>::kMinBlocks)
-    grl_turn_kernel(const __grid_constant__ GrlKParams prm) {
+    grl_turn_kernel(const __grid_constant__ GrlKParams prm, const __grid_constant__ GrlGymK gk) {
+  static_assert(!GYM || (DO_STEP && DO_OUT), "the fused gym step is a turn plus read-outs");
   constexpr int GPW = 32 / LG;  // games per warp
   static_assert(LG == 32 || LG == 16 || LG == 8 || LG == 4, "a group is 4, 8, 16 or 32 lanes");
   static_assert(LG >= PT || LG == 32, "per-player scalars are written by one lane each");
@@ -668,7 +689,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
   constexpr bool kSnap = GRL_DIRTY_WB && (LG == 32 || GRL_PACKED_SNAPSHOT);
   const int per_game = (kSnap ? 2 : 1) * L.slab_words + L.static_words + act_words;
   // baked geometries with N % 4 != 0 stage channel masks + an army-fraction plane per warp (obs_linear)
-  const int obs_scratch = grl_obs_scratch_words(TW, TH, PT, NW);
+  const int obs_scratch = GYM ? grl_gym_smem_words(P, NW, N) : grl_obs_scratch_words(TW, TH, PT, NW);
   uint32_t *wbase = smem + warp * (GPW * per_game + obs_scratch);
   uint32_t *s_obs = wbase + GPW * per_game;
 
@@ -682,7 +703,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
   const bool act_lane = l < NW;
   const uint32_t pmask = (1u << P) - 1u;
   const bool use_policy = DO_STEP && (prm.flags & GRL_STEP_FLAG_RANDOM_POLICY) != 0;
-  const bool read_actions = DO_STEP && !use_policy && prm.actions != nullptr;
+  const bool read_actions = DO_STEP && !GYM && !use_policy && prm.actions != nullptr;
   const int warp_game0 = prm.game0 + (blockIdx.x * GRL_WARPS_PER_CTA + warp) * GPW;
   const int game = warp_game0 + sub;
   const int game_end = prm.game_end;
@@ -780,6 +801,16 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
 #pragma unroll
     for (int p = 0; p < PT; p++)
       prev_true_army[p] = p < P ? (int)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p + GRL_PL_TRUE_ARMY] : 0;
+
+    // ---- fused gym step: the client's pre-turn PlayerState (reward baseline) and its action decoding ----
+    int gym_army0 = 0, gym_tiles0 = 0;
+    uint32_t gym_alive0 = 0u;
+    if constexpr (GYM) {
+      gym_army0 = (int)S.hdr[GRL_HDR_PLAYER0 + GRL_PL_ARMY_COUNT];
+      gym_tiles0 = __reduce_add_sync(g.seg, __popc(lst[0]));
+      gym_alive0 = alive;
+      skip = !gym_pre_phase<PT, LG>(prm, gk, s, st, s_act, alive, over, turn, game, g, W, H, N, NW);
+    }
 
     if (DO_STEP) {
       if (skip) {
@@ -1133,9 +1164,59 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
               (int32_t)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * l + GRL_PL_ACTION_INDEX];
       }
     }
+
+    // ---- fused gym step: the tail of GeneralsEnv.step (generals_env.py:268-289) and the client's reward
+    //      (:499-561, float64) from the PlayerState before and after the turn --------------------------
+    if constexpr (GYM) {
+      const int tiles1 = __reduce_add_sync(g.seg, act_lane ? __popc(S.list[l]) : 0);
+      if (l == 0) {
+        const int valid = skip ? 0 : 1;
+        const int tn = gk.turns[game] + valid, cl = gk.calls[game] + 1;
+        gk.turns[game] = tn;
+        gk.calls[game] = cl;
+        const bool term = over && valid;
+        const bool trunc = (tn >= gk.max_turns && valid) || cl >= gk.max_turns;
+        double r = 0.0;
+        if (!valid) {
+          r = -0.1;
+        } else if (term) {
+          const int n_alive = __popc(alive & pmask);
+          r = (n_alive == 1 && (alive & 1u)) ? 100.0 : -100.0;
+        } else {
+          // one rounding per Python statement (generals_env.py:523-547): no FMA contraction
+          r = __dadd_rn(r, __dmul_rn((double)(tiles1 - gym_tiles0), 1.0));
+          r = __dadd_rn(r, __dmul_rn((double)((int)S.hdr[GRL_HDR_PLAYER0 + GRL_PL_ARMY_COUNT] - gym_army0), 0.01));
+          for (int q = 1; q < P; q++)
+            if (((gym_alive0 >> q) & 1u) && !((alive >> q) & 1u)) r = __dadd_rn(r, 50.0);
+        }
+        gk.reward[game] = r;
+        gk.valid[game] = (uint8_t)valid;
+        gk.terminated[game] = term ? 1 : 0;
+        gk.truncated[game] = trunc ? 1 : 0;
+        if ((term || trunc) && gk.n_finished) atomicAdd(gk.n_finished, 1);
+      }
+    }
   }
   if (!DO_OUT) return;
   __syncwarp();  // every group's slab in shared memory is final: the plane read-outs below are warp-wide
+
+  if constexpr (GYM) {
+    // the client's read-outs of the new state, one game of the warp after the other (obs, N*5 mask, PlayerState)
+    const Geo g32 = make_geo(prm, W, lane, 32);
+#pragma unroll 1
+    for (int gi = 0; gi < GPW; gi++) {
+      const int game_g = warp_game0 + gi;
+      if (game_g >= game_end) break;
+      const uint32_t *sg = wbase + gi * per_game;
+      if constexpr (TW > 0 && ((TW * TH) & 3) == 0)
+        gym_emit_quads<PT, (TW > 0 && ((TW * TH) & 3) == 0 ? TW * TH : 4)>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg,
+                                                                          sg + L.slab_words, s_lut, s_obs, game_g, lane, g32);
+      else
+        gym_emit<(TW > 0 ? TW * TH : 0)>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg, sg + L.slab_words, s_obs,
+                                         game_g, lane, g32);
+    }
+    return;
+  }
 
   // engine legal-action mask, packed in the reference's flat index order (t*4 + dir, U,R,D,L)
   if (prm.mask_bits) {
@@ -1295,7 +1376,7 @@ __device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, co
     const uint32_t own = act_lane ? S.own[p * NW + g.lane] : 0u;
     const uint32_t lst = act_lane ? S.list[p * NW + g.lane] : 0u;
     uint32_t src = ((alive >> p) & 1u) ? (lst & own & gt1) : 0u;
-    PackedAction a = sample_policy_action<LG>(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn_before, g);
+    PackedAction a = sample_policy_action<LG>(prm, prm.policy_seed, dm, src, p, (uint64_t)(prm.env_id_base + game), turn_before, g);
     if (g.lane == 0 && a.present()) {
       uint2 d = decode_action(make_uint2(a.lo, a.hi), W, H, P);
       s_act[2 * p] = d.x;
@@ -1303,6 +1384,77 @@ __device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, co
     }
   }
   __syncwarp(g.seg);
+}
+
+template <int PT, int LG>
+__device__ __noinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK &gk, uint32_t *s, const uint32_t *st,
+                                           uint32_t *s_act, uint32_t alive, bool over, uint32_t turn_before, int game, Geo g,
+                                           int W, int H, int N, int NW) {
+  const GrlLayout &L = prm.L;
+  const int P = prm.P;
+  SlabView S = make_view(s, st, L);
+  const bool act_lane = g.lane < NW;
+  const uint32_t M = act_lane ? S.M[g.lane] : 0u;
+  const uint32_t gt1 = army_gt1_mask<LG>(S.army, NW, N, g);
+  const DirMasks dm = dir_targets<LG>(M, g);
+  // _get_valid_actions_mask (generals_env.py:344-387) of player p's fog-filtered view, tested at one index
+  auto gym_ok = [&](long long a, int p) -> bool {
+    if (a < 0 || a >= (long long)N * 5) return false;  // uniform over the group
+    const int t = (int)(a / 5), k = (int)(a % 5);
+    const uint32_t own = act_lane ? S.own[p * NW + g.lane] : 0u;
+    const uint32_t v = act_lane ? (prm.fog ? S.vis[p * NW + g.lane] : g.valid) : 0u;
+    const uint32_t src = v & own & gt1;
+    const uint32_t U = src & dm.up, R = src & dm.right, D = src & dm.down, Lm = src & dm.left;
+    const uint32_t sel = k == 0 ? U : (k == 1 ? R : (k == 2 ? D : (k == 3 ? Lm : (U | R | D | Lm))));
+    return ((__shfl_sync(g.seg, sel, t >> 5, LG) >> (t & 31)) & 1u) != 0u;
+  };
+  // _action_index_to_game_action (generals_env.py:389-441)
+  auto put = [&](long long a, int p, int slot) {
+    const int from_idx = (int)(a / 5), info = (int)(a % 5);
+    const int fx = from_idx % W, fy = from_idx / W;
+    int tx = fx, ty = fy;
+    if (info < 4) {
+      tx = fx + (info == 1) - (info == 3);
+      ty = fy + (info == 2) - (info == 0);
+    } else {  // half move: the first in-bounds direction in the order up, right, down, left
+      if (fy - 1 >= 0) ty = fy - 1;
+      else if (fx + 1 < W) tx = fx + 1;
+      else if (fy + 1 < H) ty = fy + 1;
+      else tx = fx - 1;
+    }
+    const PackedAction pa = pack_action(p, fx, fy, tx, ty, info != 4);
+    const uint2 d = decode_action(make_uint2(pa.lo, pa.hi), W, H, P);
+    if (g.lane == 0) {
+      s_act[2 * slot] = d.x;
+      s_act[2 * slot + 1] = d.y;
+    }
+  };
+  const long long a0 = gk.action[game];
+  const bool ok0 = gym_ok(a0, 0);
+  if (ok0) put(a0, 0, 0);
+  if (gk.opponent_action) {
+    const long long a1 = gk.opponent_action[game];
+    if (gym_ok(a1, 1)) put(a1, 1, 1);
+  } else if (!over) {
+    // the reference's default opponent (generals_env.py:443-497): a uniformly random legal FULL move; the
+    // synthetic policy's draw keyed (opponent_seed, env, turn, player), players beyond 1 keep its half-move bit
+#pragma unroll 1
+    for (int p = 1; p < P && p < prm.A; p++) {
+      const uint32_t own = act_lane ? S.own[p * NW + g.lane] : 0u;
+      const uint32_t lst = act_lane ? S.list[p * NW + g.lane] : 0u;
+      const uint32_t src = ((alive >> p) & 1u) ? (lst & own & gt1) : 0u;
+      PackedAction a = sample_policy_action<LG>(prm, gk.opponent_seed, dm, src, p, (uint64_t)(prm.env_id_base + game),
+                                                turn_before, g);
+      if (p == 1) a.hi |= 1u << 8;  // move_all
+      if (g.lane == 0 && a.present()) {
+        const uint2 d = decode_action(make_uint2(a.lo, a.hi), W, H, P);
+        s_act[2 * p] = d.x;
+        s_act[2 * p + 1] = d.y;
+      }
+    }
+  }
+  __syncwarp(g.seg);
+  return ok0;
 }
 
 template <int PT, int LG>
@@ -1625,22 +1777,22 @@ __device__ __forceinline__ float4 gym_value4(const GymPlanes &g, int p, int plan
   }
 }
 
-__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
-    grl_gym_warp_kernel(const __grid_constant__ GrlKParams prm, int max_turns, const float *__restrict__ logtab,
-                        float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// One game's gym read-outs by a whole warp.  `s` / `stt` are the game's slab and terrain words (global
+// memory in grl_gym_warp_kernel, the shared-memory copy in the fused gym step); `sw` is the warp's
+// scratch of grl_gym_smem_words() words; `g` is the full-warp (LG = 32) geometry.  NT > 0 bakes the tile
+// count in (the element -> (plane, tile) divisions become multiplications).
+template <int NT>
+__device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+                                         float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats,
+                                         const uint32_t *s, const uint32_t *stt, uint32_t *sw, int game, int lane,
+                                         const Geo &g) {
   const GrlLayout &L = prm.L;
-  const int N = prm.N, P = prm.P, NW = prm.NW, NWP = NW + 1;
-  const Geo g = make_geo(prm, prm.W, lane, 32);
-  uint32_t *sw = smem + warp * grl_gym_smem_words(P, NW, N);
+  const int N = NT ? NT : prm.N, P = prm.P, NW = NT ? (NT + 31) / 32 : prm.NW, NWP = NW + 1;
   uint32_t *s_vis = sw, *s_mine = s_vis + P * NWP, *s_enemy = s_mine + P * NWP;
   uint32_t *s_normal = s_enemy + P * NWP, *s_M = s_normal + NWP, *s_C = s_M + NWP, *s_G = s_C + NWP, *s_pad = s_G + NWP;
   uint32_t *s_dir = s_pad + NWP;  // [P][5][NWP]: up, right, down, left, any
   float *s_logv = reinterpret_cast<float *>(s_dir + 5 * P * NWP);
-  for (int game = blockIdx.x * GRL_WARPS_PER_CTA + warp; game < prm.B; game += gridDim.x * GRL_WARPS_PER_CTA) {
-    const uint32_t *s = prm.state + (size_t)game * L.slab_words;
-    const uint32_t *stt = prm.statics + (size_t)game * L.static_words;
+  {
     const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
     const bool w = lane < NW;
     const uint32_t M = w ? stt[lane] : 0u, C = w ? stt[NW + lane] : 0u, G = w ? stt[2 * NW + lane] : 0u;
@@ -1744,6 +1896,184 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
     __syncwarp();
   }
 }
+
+// The same read-outs for baked boards with N % 4 == 0 (10x10, 20x20), from the slab in SHARED memory, in the
+// plane-major order of obs_plane_major: lane l owns the tile quads q = l + 32c, reads every mask's nibble for its
+// quads once (packed 4 bits per chunk), converts its quads' armies once, and the warp writes the game's
+// [P][9][N] block as one linear sweep of 128-bit stores with compile-time addressing.  The N*5 mask bytes of a
+// player (tile-major, {up,right,down,left,any} per tile) are 20 bytes per quad: a lane assembles its five words,
+// the warp stages them in shared memory and copies them out as a linear sweep.
+template <int PT, int N>
+__device__ __forceinline__ void gym_emit_quads(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+                                               float *__restrict__ obs, uint8_t *__restrict__ mask,
+                                               int32_t *__restrict__ stats, const uint32_t *s, const uint32_t *stt,
+                                               const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g) {
+  static_assert(N % 4 == 0 && N <= 512, "quads of four tiles, at most four chunks of 32 quads");
+  constexpr int NQ = N / 4, NCH = (NQ + 31) / 32, NW = (N + 31) / 32;
+  const GrlLayout &L = prm.L;
+  const int P = prm.P;
+  const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+  const bool w = lane < NW;
+  // ---- the four direction masks of every player in word layout -> shared memory [P][4][NW] ------------
+  uint32_t *s_dir = sw, *s_stage = sw + PT * 4 * NW;
+  if (mask) {
+    const uint32_t M = w ? stt[lane] : 0u;
+    const uint32_t gt1 = army_gt1_mask<32>(army, NW, N, g);
+    const DirMasks dm = dir_targets<32>(M, g);
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      if (p < P && w) {
+        const uint32_t own = s[L.off_own + p * NW + lane];
+        const uint32_t v = prm.fog ? s[L.off_vis + p * NW + lane] : g.valid;
+        const uint32_t src = v & own & gt1;
+        s_dir[(p * 4 + 0) * NW + lane] = src & dm.up;
+        s_dir[(p * 4 + 1) * NW + lane] = src & dm.right;
+        s_dir[(p * 4 + 2) * NW + lane] = src & dm.down;
+        s_dir[(p * 4 + 3) * NW + lane] = src & dm.left;
+      }
+    }
+    __syncwarp();
+  }
+  // ---- nibbles of this lane's quads ---------------------------------------------------------------------
+  const int bsel = lane >> 1, bsh = 4 * (lane & 1);  // quad q -> byte q>>1, nibble q&1 of a mask's byte array
+  const uint8_t *bM = reinterpret_cast<const uint8_t *>(stt);
+  const uint8_t *bC = reinterpret_cast<const uint8_t *>(stt + NW);
+  const uint8_t *bG = reinterpret_cast<const uint8_t *>(stt + 2 * NW);
+  uint32_t mM = 0, mC = 0, mG = 0, mAny = 0, livem = 0;
+  uint32_t nV[PT], nO[PT];
+#pragma unroll
+  for (int p = 0; p < PT; p++) nV[p] = nO[p] = 0;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    if (32 * c + lane < NQ) {
+      const int b = 16 * c + bsel;
+      livem |= 0xfu << (4 * c);
+      mM |= ((bM[b] >> bsh) & 0xfu) << (4 * c);
+      mC |= ((bC[b] >> bsh) & 0xfu) << (4 * c);
+      mG |= ((bG[b] >> bsh) & 0xfu) << (4 * c);
+#pragma unroll
+      for (int p = 0; p < PT; p++) {
+        if (p < P) {
+          const uint8_t *bo = reinterpret_cast<const uint8_t *>(s + L.off_own + p * NW);
+          const uint8_t *bv = reinterpret_cast<const uint8_t *>(s + L.off_vis + p * NW);
+          nO[p] |= ((bo[b] >> bsh) & 0xfu) << (4 * c);
+          nV[p] |= ((bv[b] >> bsh) & 0xfu) << (4 * c);
+        }
+      }
+    }
+  }
+  uint32_t seen = 0;  // tiles some player sees: the only ones whose army reaches an observation
+#pragma unroll
+  for (int p = 0; p < PT; p++) {
+    mAny |= nO[p];
+    if (!prm.fog) nV[p] = livem;
+    seen |= nV[p];
+  }
+  if (obs) {
+    float f[NCH][4];  // log(army + 1) / 10 of the lane's quads
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      f[c][0] = f[c][1] = f[c][2] = f[c][3] = 0.f;
+      if ((seen >> (4 * c)) & 0xfu) {
+        const uint2 aw = *reinterpret_cast<const uint2 *>(army + 4 * (32 * c + lane));
+        f[c][0] = __ldg(logtab + (aw.x & 0xffffu));
+        f[c][1] = __ldg(logtab + (aw.x >> 16));
+        f[c][2] = __ldg(logtab + (aw.y & 0xffffu));
+        f[c][3] = __ldg(logtab + (aw.y >> 16));
+      }
+    }
+    const float tf = fminf(__fdiv_rn((float)s[GRL_HDR_TURN], (float)max_turns), 1.0f);
+    const float4 tf4 = make_float4(tf, tf, tf, tf), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const char *lutb = reinterpret_cast<const char *>(lut);
+    auto nib4 = [&](uint32_t field, int c) -> float4 {  // chunk c's nibble of a packed field -> four 0/1 floats
+      const uint32_t idx16 = (c == 0 ? (field << 4) : (field >> (4 * c - 4))) & 0xf0u;
+      return *reinterpret_cast<const float4 *>(lutb + idx16);
+    };
+    float4 *gq = reinterpret_cast<float4 *>(obs + (size_t)game * P * GRL_GYM_CHANNELS * N) + lane;
+    const uint32_t mN = livem & ~(mM | mC | mG);
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      if (p < P) {
+        const uint32_t v = nV[p], mine = v & nO[p], enemy = v & mAny & ~nO[p];
+        float4 *gp = gq + p * GRL_GYM_CHANNELS * NQ;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+          if (32 * c + lane < NQ) {
+            const float4 vv = nib4(v, c), a = nib4(mine, c), e = nib4(enemy, c);
+            __stcs(gp + 0 * NQ + 32 * c, vv);
+            // ownership: 0.5 own, 1.0 enemy (mine and enemy are disjoint)
+            __stcs(gp + 1 * NQ + 32 * c, make_float4(__fmaf_rn(a.x, 0.5f, e.x), __fmaf_rn(a.y, 0.5f, e.y),
+                                                     __fmaf_rn(a.z, 0.5f, e.z), __fmaf_rn(a.w, 0.5f, e.w)));
+            __stcs(gp + 2 * NQ + 32 * c, make_float4(vv.x * f[c][0], vv.y * f[c][1], vv.z * f[c][2], vv.w * f[c][3]));
+            __stcs(gp + 3 * NQ + 32 * c, nib4(mN, c));
+            __stcs(gp + 4 * NQ + 32 * c, nib4(mM, c));
+            __stcs(gp + 5 * NQ + 32 * c, nib4(mC, c));
+            __stcs(gp + 6 * NQ + 32 * c, nib4(mG, c));
+            __stcs(gp + 7 * NQ + 32 * c, tf4);
+            __stcs(gp + 8 * NQ + 32 * c, zero4);
+          }
+        }
+      }
+    }
+  }
+  if (mask) {
+    constexpr int MW = 5 * NQ;  // words of one player's mask
+    for (int p = 0; p < P; p++) {
+      const uint8_t *bd = reinterpret_cast<const uint8_t *>(s_dir + p * 4 * NW);
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        const int q = 32 * c + lane;
+        if (q < NQ) {
+          const int b = 16 * c + bsel;
+          const uint32_t U = (bd[b] >> bsh) & 0xfu, R = (bd[4 * NW + b] >> bsh) & 0xfu;
+          const uint32_t D = (bd[8 * NW + b] >> bsh) & 0xfu, Lm = (bd[12 * NW + b] >> bsh) & 0xfu, A = U | R | D | Lm;
+          // byte 5i+k of the quad = direction k of its tile i:  U0 R0 D0 L0 | A0 U1 R1 D1 | L1 A1 U2 R2 | D2 L2 A2 U3 | R3 D3 L3 A3
+          auto bit = [](uint32_t n, int i, int at) -> uint32_t { return ((n >> i) & 1u) << (8 * at); };
+          uint32_t *o = s_stage + 5 * q;
+          o[0] = bit(U, 0, 0) | bit(R, 0, 1) | bit(D, 0, 2) | bit(Lm, 0, 3);
+          o[1] = bit(A, 0, 0) | bit(U, 1, 1) | bit(R, 1, 2) | bit(D, 1, 3);
+          o[2] = bit(Lm, 1, 0) | bit(A, 1, 1) | bit(U, 2, 2) | bit(R, 2, 3);
+          o[3] = bit(D, 2, 0) | bit(Lm, 2, 1) | bit(A, 2, 2) | bit(U, 3, 3);
+          o[4] = bit(R, 3, 0) | bit(D, 3, 1) | bit(Lm, 3, 2) | bit(A, 3, 3);
+        }
+      }
+      __syncwarp();
+      uint8_t *base = mask + ((size_t)game * P + p) * (size_t)(N * 5);
+      if constexpr (MW % 4 == 0) {
+        uint4 *dst = reinterpret_cast<uint4 *>(base);
+        const uint4 *src = reinterpret_cast<const uint4 *>(s_stage);
+        for (int i = lane; i < MW / 4; i += 32) __stcs(dst + i, src[i]);
+      } else {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(base);
+        for (int i = lane; i < MW; i += 32) __stcs(dst + i, s_stage[i]);
+      }
+      __syncwarp();
+    }
+  }
+  if (stats && lane < P) {
+    int tiles = 0;
+    for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + lane * NW + k]);
+    int32_t *so = stats + ((size_t)game * P + lane) * 4;
+    so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ARMY_COUNT];
+    so[1] = tiles;
+    so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> lane) & 1u);
+    so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_GENERAL_IDX];
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
+    grl_gym_warp_kernel(const __grid_constant__ GrlKParams prm, int max_turns, const float *__restrict__ logtab,
+                        float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GrlLayout &L = prm.L;
+  const Geo g = make_geo(prm, prm.W, lane, 32);
+  uint32_t *sw = smem + warp * grl_gym_smem_words(prm.P, prm.NW, prm.N);
+  for (int game = blockIdx.x * GRL_WARPS_PER_CTA + warp; game < prm.B; game += gridDim.x * GRL_WARPS_PER_CTA)
+    gym_emit<0>(prm, max_turns, logtab, obs, mask, stats, prm.state + (size_t)game * L.slab_words,
+                prm.statics + (size_t)game * L.static_words, sw, game, lane, g);
+}
 #undef GYM_NIB4
 
 // GeneralsEnv._action_index_to_game_action (generals_env.py:389-441), one thread per env
@@ -1809,10 +2139,10 @@ __global__ void grl_gym_finish_kernel(const GrlKParams prm, int max_turns, const
     } else if (term) {
       r = winner[b] == 0 ? 100.0 : -100.0;
     } else {
-      r += (double)(cur[1] - prev[1]) * 1.0;
-      r += (double)(cur[0] - prev[0]) * 0.01;
+      r = __dadd_rn(r, __dmul_rn((double)(cur[1] - prev[1]), 1.0));  // no FMA contraction (one rounding per statement)
+      r = __dadd_rn(r, __dmul_rn((double)(cur[0] - prev[0]), 0.01));
       for (int q = 1; q < P; q++)
-        if (prev[q * 4 + 2] == 1 && cur[q * 4 + 2] == 0) r += 50.0;
+        if (prev[q * 4 + 2] == 1 && cur[q * 4 + 2] == 0) r = __dadd_rn(r, 50.0);
     }
     reward[b] = r;
     terminated[b] = term ? 1 : 0;
@@ -1907,7 +2237,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32) grl_sample_kernel(cons
         uint32_t own = act ? s[L.off_own + p * NW + lane] : 0u;
         uint32_t lst = act ? s[L.off_list + p * NW + lane] : 0u;
         uint32_t src = ((flags >> p) & 1u) ? (lst & own & gt1) : 0u;
-        PackedAction a = sample_policy_action<32>(prm, dm, src, p, (uint64_t)(prm.env_id_base + game), turn, g);
+        PackedAction a = sample_policy_action<32>(prm, prm.policy_seed, dm, src, p, (uint64_t)(prm.env_id_base + game), turn, g);
         if (lane == 0) out[(size_t)game * prm.A + p] = make_uint2(a.lo, a.hi);
       }
     }
@@ -1935,16 +2265,20 @@ static inline int grid_for(int items_per_cta_warps, int n) {
   return ctas < 1 ? 1 : ctas;
 }
 
-static size_t grl_turn_smem_bytes(const GrlLayout &L, int TW, int TH, int PT, int LG) {
+static size_t grl_turn_smem_bytes(const GrlLayout &L, int TW, int TH, int PT, int LG, bool gym) {
   const bool snap = GRL_DIRTY_WB && (LG == 32 || GRL_PACKED_SNAPSHOT);
   const int per_game = (snap ? 2 : 1) * L.slab_words + L.static_words + 2 * GRL_MAX_ACTIONS;
-  return (size_t)GRL_WARPS_PER_CTA * (size_t)((32 / LG) * per_game + grl_obs_scratch_words(TW, TH, PT, L.NW)) * 4u;
+  const int scratch = gym ? grl_gym_smem_words(L.P, L.NW, L.N) : grl_obs_scratch_words(TW, TH, PT, L.NW);
+  return (size_t)GRL_WARPS_PER_CTA * (size_t)((32 / LG) * per_game + scratch) * 4u;
 }
 
-template <int PT, int TW, int TH, int LG, bool S, bool O>
-static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream) {
-  size_t smem = grl_turn_smem_bytes(prm.L, TW, TH, PT, LG);
-  auto kern = grl_turn_kernel<PT, TW, TH, LG, S, O>;
+template <int PT, int TW, int TH, int LG, bool S, bool O, bool GYM = false>
+static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream, const GrlGymK *gym = nullptr) {
+  size_t smem = grl_turn_smem_bytes(prm.L, TW, TH, PT, LG, GYM);
+  auto kern = grl_turn_kernel<PT, TW, TH, LG, S, O, GYM>;
+  GrlGymK gk;
+  memset(&gk, 0, sizeof gk);
+  if (gym) gk = *gym;
   static size_t tuned_smem = ~(size_t)0;  // per instantiation
   if (tuned_smem != smem) {
     if (smem > 48 * 1024) {
@@ -1974,7 +2308,7 @@ static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  return cudaLaunchKernelEx(&cfg, kern, prm);
+  return cudaLaunchKernelEx(&cfg, kern, prm, gk);
 }
 
 template <int PT, int TW, int TH, int LG>
@@ -2014,6 +2348,25 @@ static cudaError_t launch_turn_p(const GrlKParams &prm, bool do_step, bool do_ou
 }
 
 static int player_template(int P) { return P <= 2 ? 2 : (P <= 4 ? 4 : 8); }
+
+// The fused gym step (one GeneralsEnv.step() per env in ONE launch): the default lane group of each baked board.
+template <int PT>
+static cudaError_t launch_gym_step_p(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream) {
+  if constexpr (PT <= 4) {
+    if (prm.W == 20 && prm.H == 20) return launch_turn_t<PT, 20, 20, 32, true, true, true>(prm, stream, &gk);
+    if (prm.W == 15 && prm.H == 15) return launch_turn_t<PT, 15, 15, 8, true, true, true>(prm, stream, &gk);
+    if (prm.W == 10 && prm.H == 10) return launch_turn_t<PT, 10, 10, 8, true, true, true>(prm, stream, &gk);
+  }
+  return launch_turn_t<PT, 0, 0, 32, true, true, true>(prm, stream, &gk);
+}
+
+cudaError_t grl_launch_gym_step(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream) {
+  switch (player_template(prm.P)) {
+    case 2: return launch_gym_step_p<2>(prm, gk, stream);
+    case 4: return launch_gym_step_p<4>(prm, gk, stream);
+    default: return launch_gym_step_p<8>(prm, gk, stream);
+  }
+}
 
 cudaError_t grl_launch_turn(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream) {
   switch (player_template(prm.P)) {

@@ -12,6 +12,7 @@ cudaError_t grl_launch_mask_bytes(const GrlKParams &prm, int variant, uint8_t *o
 cudaError_t grl_launch_visibility(const GrlKParams &prm, uint8_t *visible, uint8_t *fog, cudaStream_t stream);
 cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *logtab, float *obs, uint8_t *mask, int32_t *stats,
                            cudaStream_t stream);
+cudaError_t grl_launch_gym_step(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream);
 cudaError_t grl_launch_gym_encode(const GrlKParams &prm, const long long *action_idx, int player, int slot, const uint8_t *mask,
                                   int skip_invalid, void *actions, uint8_t *valid, cudaStream_t stream);
 cudaError_t grl_launch_gym_patch(const GrlKParams &prm, void *actions, int slot, cudaStream_t stream);

@@ -94,3 +94,20 @@ struct GrlKParams {
   unsigned long long l2_window_bytes;
   float l2_hit_ratio;
 };
+
+// Second parameter block of the turn kernel, read only by its fused gym-step instantiation
+// (grl_gym_step: one GeneralsEnv.step() for every env in a single launch).
+struct GrlGymK {
+  const long long *action;           // [B] Discrete(N*5) indices of player 0
+  const long long *opponent_action;  // [B] or nullptr: the random opponent
+  const float *logtab;               // log(a + 1) / 10 for every uint16 army
+  float *obs;                        // [B][P][9][N]
+  uint8_t *mask;                     // [B][P][N*5]
+  int32_t *stats;                    // [B][P][4]
+  int32_t *turns, *calls;            // [B]
+  double *reward;                    // [B]
+  uint8_t *terminated, *truncated, *valid;
+  int32_t *n_finished;
+  unsigned long long opponent_seed;
+  int max_turns;
+};

@@ -1,0 +1,131 @@
+"""grl_gym_step — one ``GeneralsEnv.step()`` (python/generals_gym/generals_env.py:210-289) for every env.
+
+The CUDA library runs it as ONE launch (the turn kernel's gym instantiation: action decoding with the
+client-side rejection, the random opponent's draw, the turn, the client's observation / N*5 mask /
+PlayerState read-outs, the float64 reward and the episode flags); the oracle runs the same contract on the
+CPU.  Every output plane is compared bit for bit at every step, including rejected actions, truncation,
+self-play opponents and boards on each lane-group instantiation."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from generalsreinforcementlearning_b200.engine import BatchedEngine, make_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _planes(torch, dev, B, P, N, H, W):
+    z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+    return dict(obs=z((B, P, 9, H, W), torch.float32), mask=z((B, P, N * 5), torch.uint8), stats=z((B, P, 4), torch.int32),
+                actions=z((B, P, 8), torch.uint8), prev_stats=z((B, P, 4), torch.int32), turns=z(B, torch.int32),
+                calls=z(B, torch.int32), reward=z(B, torch.float64), terminated=z(B, torch.uint8),
+                truncated=z(B, torch.uint8), valid=z(B, torch.uint8), done=z(B, torch.uint8), winner=z(B, torch.int8),
+                step_error=z(B, torch.uint8), n_finished=z(1, torch.int32))
+
+
+def _pick(mask_row, rng, want_invalid):
+    """k-th set (or, for a rejected action, unset) entry of one env's mask."""
+    idx = np.flatnonzero(mask_row == (0 if want_invalid else 1))
+    if len(idx) == 0:
+        return int(rng.integers(0, len(mask_row)))
+    return int(idx[rng.integers(0, len(idx))])
+
+
+def gym_rollout(lib, W, H, P, B, steps, max_turns, self_play, seed=77):
+    """Drive grl_gym_step with actions drawn (host RNG) from the library's own mask plane; returns the trace of
+    every output plane after every step."""
+    import torch
+
+    on_device = lib.prefix == "grl_"
+    dev = torch.device("cuda", 0) if on_device else torch.device("cpu")
+    e = BatchedEngine(lib, make_config(lib, num_envs=B, width=W, height=H, num_players=P, max_actions=P, host_threads=1))
+    if on_device:
+        e.use_torch_stream()
+    e.reset_seeded(np.arange(B, dtype=np.int64) + 12345)
+    N = W * H
+    pl = _planes(torch, dev, B, P, N, H, W)
+    e.gym_observe(max_turns, pl["obs"], pl["mask"], pl["stats"])
+    rng = np.random.default_rng(seed)
+    trace = []
+    for t in range(steps):
+        m = pl["mask"].cpu().numpy()
+        act = np.zeros(B, np.int64)
+        opp = np.zeros(B, np.int64)
+        for b in range(B):
+            bad = rng.random() < 0.08
+            act[b] = _pick(m[b, 0], rng, bad)
+            opp[b] = _pick(m[b, 1], rng, rng.random() < 0.05)
+        if t % 7 == 3:
+            act[0], opp[1 % B] = -1, N * 5 + 3          # out-of-range indices are rejected too
+        a = torch.as_tensor(act, device=dev)
+        oa = torch.as_tensor(opp, device=dev) if self_play else None
+        e.gym_step(max_turns, 1000 + t, action=a, opponent_action=oa, **pl)
+        if on_device:
+            torch.cuda.synchronize()
+        snap = {k: v.cpu().numpy().copy() for k, v in pl.items() if k not in ("actions", "prev_stats")}
+        snap["hash"] = e.state_hash().copy()
+        trace.append(snap)
+    launches = e.launch_count()
+    e.close()
+    return trace, launches
+
+
+def _compare(ta, tb, what):
+    assert len(ta) == len(tb)
+    for t, (a, b) in enumerate(zip(ta, tb)):
+        for k in a:
+            x, y = a[k], b[k]
+            if x.dtype == np.float32:
+                x, y = x.view(np.uint32), y.view(np.uint32)
+            elif x.dtype == np.float64:
+                x, y = x.view(np.uint64), y.view(np.uint64)
+            if not np.array_equal(x, y):
+                bad = np.argwhere(x != y)
+                raise AssertionError(f"{what}: plane {k!r} differs at step {t}, first at {bad[0].tolist()} "
+                                     f"({len(bad)} cells): {a[k][tuple(bad[0])]} vs {b[k][tuple(bad[0])]}")
+
+
+CASES = [  # W, H, P, B, steps, max_turns, self_play
+    (10, 10, 2, 203, 45, 30, False),    # 8 lanes per game, partial last warp, truncation by turns and by calls
+    (15, 15, 2, 130, 40, 500, True),    # 8 lanes per game, self-play opponent indices
+    (20, 20, 2, 96, 60, 500, False),    # one game per warp
+    (20, 20, 4, 40, 50, 35, False),     # four players: players 2,3 keep the synthetic policy's half-move bit
+    (7, 13, 3, 33, 40, 500, True),      # generic geometry
+    (5, 5, 2, 64, 80, 500, False),      # tiny boards finish: terminated, +-100, eliminated-opponent bonus
+]
+
+
+def test_oracle_gym_step_is_deterministic(oracle_lib):
+    a, _ = gym_rollout(oracle_lib, 8, 8, 2, 24, 30, 20, False)
+    b, _ = gym_rollout(oracle_lib, 8, 8, 2, 24, 30, 20, False)
+    _compare(a, b, "oracle twice")
+    assert any(s["truncated"].any() for s in a) and any((s["valid"] == 0).any() for s in a)
+    rej = [(s["reward"][s["valid"] == 0]) for s in a if (s["valid"] == 0).any()]
+    assert all((r == -0.1).all() for r in rej), "a rejected action costs -0.1 and takes no turn"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,P,B,steps,max_turns,self_play", CASES)
+def test_cuda_gym_step_matches_oracle(cuda_lib, oracle_lib, W, H, P, B, steps, max_turns, self_play):
+    g, launches = gym_rollout(cuda_lib, W, H, P, B, steps, max_turns, self_play)
+    o, _ = gym_rollout(oracle_lib, W, H, P, B, steps, max_turns, self_play)
+    _compare(g, o, f"cuda vs oracle {W}x{H}x{P}p")
+    if os.environ.get("GRL_GYM_UNFUSED") != "1":
+        # reset (mapgen + turn-0) and the initial read-out aside, a step is ONE launch; state_hash adds one per step
+        assert launches <= 3 + 2 * steps + 2, f"{launches} launches for {steps} fused steps"
+    if (W, H) == (5, 5):
+        assert any(s["terminated"].any() for s in g), "5x5 games end within 80 steps"
+
+
+@pytest.mark.gpu
+def test_cuda_gym_step_unfused_sequence_matches_oracle(cuda_lib):
+    """The round-1 seven-launch sequence stays available (GRL_GYM_UNFUSED=1) and agrees with the oracle too —
+    so fused == unfused == oracle.  The switch is read once per process, hence the subprocess."""
+    env = dict(os.environ, GRL_GYM_UNFUSED="1")
+    proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.abspath(__file__), "-k",
+                           "matches_oracle and not unfused"], env=env, cwd=ROOT, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert proc.returncode == 0, proc.stdout[-3000:]

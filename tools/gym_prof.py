@@ -2,7 +2,7 @@ import sys; sys.path.insert(0,'/root/repo')
 import torch
 from torch.profiler import profile, ProfilerActivity
 from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
-env=GeneralsVecEnv(65536,15,15,max_turns=500,seed=3)
+env=GeneralsVecEnv(65536,int(sys.argv[1]) if len(sys.argv)>1 else 15,int(sys.argv[1]) if len(sys.argv)>1 else 15,max_turns=500,seed=3)
 obs,info=env.reset()
 for _ in range(5): obs,r,te,tr,info=env.step(env.sample_actions())
 acts=[env.sample_actions() for _ in range(1)]
