@@ -61,6 +61,9 @@
 #define GRL_OBS_LUT 1
 #endif
 #ifndef GRL_OBS_CHUNK_MAJOR
+#ifndef GRL_STRADDLE_INLINE
+#define GRL_STRADDLE_INLINE 0
+#endif
 #define GRL_OBS_CHUNK_MAJOR 0  // 1: the round-1a tile-chunk-major observation loop (comparison builds)
 #endif
 
@@ -430,6 +433,11 @@ __device__ __forceinline__ void gym_emit_quads(const GrlKParams &prm, int max_tu
                                                float *__restrict__ obs, uint8_t *__restrict__ mask,
                                                int32_t *__restrict__ stats, const uint32_t *s, const uint32_t *stt,
                                                const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g);
+template <int PT, int N>
+__device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+                                                float *__restrict__ obs, uint8_t *__restrict__ mask,
+                                                int32_t *__restrict__ stats, const uint32_t *s, const uint32_t *stt,
+                                                const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g);
 
 // Elimination orders: tile turnover over the eliminated player's cached list, then the stats
 // rebuild of engine.go:101-109.  Reads and writes own/list/changed/vchg words in the slab.
@@ -640,22 +648,44 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
   for (int i = lane; i < body4; i += 32) {
     const int e = head + 4 * i;
     const int plane = e / N, t = e - plane * N;
+    const int k = plane % GRL_OBS_CHANNELS;
+    const uint32_t *wp = chm + plane * NWP + (t >> 5);
+    uint32_t nib = __funnelshift_r(wp[0], wp[1], t & 31) & 0xfu;  // rows are zero from bit N on
     float4 val;
     if (t + 3 < N) {
-      const uint32_t *wp = chm + plane * NWP + (t >> 5);
-      const uint32_t nib = __funnelshift_r(wp[0], wp[1], t & 31) & 0xfu;
       val = *reinterpret_cast<const float4 *>(lutb + nib * 16u);
-      if ((plane % GRL_OBS_CHANNELS) < 2 && nib) {
+      if (k < 2 && nib) {
         val.x *= frac[t];
         val.y *= frac[t + 1];
         val.z *= frac[t + 2];
         val.w *= frac[t + 3];
       }
-    } else {  // straddles two planes
+    } else {
+#if GRL_STRADDLE_INLINE == 2  // comparison builds: four per-element evaluations
       val.x = obs_element<N>(chm, frac, NWP, e);
       val.y = obs_element<N>(chm, frac, NWP, e + 1);
       val.z = obs_element<N>(chm, frac, NWP, e + 2);
       val.w = obs_element<N>(chm, frac, NWP, e + 3);
+#else
+      // the float4 straddles two planes (P*9-1 of them per game, but in 17 of a 15x15 game's 32 rounds one lane
+      // of the warp is here): the first r tiles close this plane, the rest open the next one.  Kept short — the
+      // whole warp waits for it — and kept a full 128-bit store: completing the sector with a later or scalar
+      // store costs more in partial-sector writes than it saves (measured 1.02 ms against 0.88 ms per 262,144 games).
+      const int r = N - t;  // 1..3
+      nib |= (chm[(plane + 1) * NWP] << r) & 0xfu;
+      val = *reinterpret_cast<const float4 *>(lutb + nib * 16u);
+      const bool armyA = k < 2, armyB = k == 0 || k == GRL_OBS_CHANNELS - 1;  // the next plane is k+1, or the next view's 0
+      if (armyA || armyB) {
+        const float f0 = armyA ? frac[t] : 1.f;                                                   // tile t is always ours
+        const float f1 = (1 < r) ? (armyA ? frac[t + 1] : 1.f) : (armyB ? frac[1 - r] : 1.f);
+        const float f2 = (2 < r) ? (armyA ? frac[t + 2] : 1.f) : (armyB ? frac[2 - r] : 1.f);
+        const float f3 = armyB ? frac[3 - r] : 1.f;                                               // tile 3 is always theirs
+        val.x *= f0;
+        val.y *= f1;
+        val.z *= f2;
+        val.w *= f3;
+      }
+#endif
     }
     __stcs(body + i, val);
   }
@@ -1211,9 +1241,11 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
       if constexpr (TW > 0 && ((TW * TH) & 3) == 0)
         gym_emit_quads<PT, (TW > 0 && ((TW * TH) & 3) == 0 ? TW * TH : 4)>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg,
                                                                           sg + L.slab_words, s_lut, s_obs, game_g, lane, g32);
+      else if constexpr (TW > 0)
+        gym_emit_linear<PT, (TW > 0 ? TW * TH : 5)>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg, sg + L.slab_words,
+                                                    s_lut, s_obs, game_g, lane, g32);
       else
-        gym_emit<(TW > 0 ? TW * TH : 0)>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg, sg + L.slab_words, s_obs,
-                                         game_g, lane, g32);
+        gym_emit<0>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg, sg + L.slab_words, s_obs, game_g, lane, g32);
     }
     return;
   }
@@ -1724,7 +1756,15 @@ __global__ void __launch_bounds__(256)
 // 128-bit stores (as the turn kernel's observation writer does); the N*5 mask bytes go out as an
 // aligned 32-bit sweep.  Shared-memory words per warp: see grl_gym_smem_words().
 __host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N) {
-  return ((3 * P + 5 + 5 * P) * (NW + 1) + N + 4 + 3) & ~3;
+  const int PT = P <= 2 ? 2 : (P <= 4 ? 4 : 8);
+  const int generic = (3 * P + 5 + 5 * P) * (NW + 1) + N + 4;                 // gym_emit
+  const int quads = PT * 4 * NW + 5 * ((N + 3) / 4);                           // gym_emit_quads: dir rows + one player's mask
+  const int lin_obs = (PT * GRL_GYM_CHANNELS + PT) * (NW + 1) + N + 4;         // gym_emit_linear: channel masks + log plane
+  const int lin_mask = (P * N * 5 + 8 + 3) / 4;                                //                  ... or the game's mask bytes
+  const int linear = PT * 4 * NW + (lin_obs > lin_mask ? lin_obs : lin_mask);
+  int m = generic > quads ? generic : quads;
+  m = m > linear ? m : linear;
+  return (m + 3) & ~3;
 }
 
 struct GymPlanes {  // shared-memory views of one game (each mask has NW + 1 words, the last one zero)
@@ -2027,14 +2067,19 @@ __device__ __forceinline__ void gym_emit_quads(const GrlKParams &prm, int max_tu
           const int b = 16 * c + bsel;
           const uint32_t U = (bd[b] >> bsh) & 0xfu, R = (bd[4 * NW + b] >> bsh) & 0xfu;
           const uint32_t D = (bd[8 * NW + b] >> bsh) & 0xfu, Lm = (bd[12 * NW + b] >> bsh) & 0xfu, A = U | R | D | Lm;
-          // byte 5i+k of the quad = direction k of its tile i:  U0 R0 D0 L0 | A0 U1 R1 D1 | L1 A1 U2 R2 | D2 L2 A2 U3 | R3 D3 L3 A3
-          auto bit = [](uint32_t n, int i, int at) -> uint32_t { return ((n >> i) & 1u) << (8 * at); };
+          // byte 5i+k of the quad = direction k of its tile i:  U0 R0 D0 L0 | A0 U1 R1 D1 | L1 A1 U2 R2 | D2 L2 A2 U3 | R3 D3 L3 A3.
+          // Each nibble is spread to one 0/1 byte per tile (a multiply and a mask), then five byte permutes
+          // pairs interleave the direction words into the 5-byte records.
+          auto spread = [](uint32_t n) -> uint32_t { return (n * 0x00204081u) & 0x01010101u; };
+          const uint32_t Ub = spread(U), Rb = spread(R), Db = spread(D), Lb = spread(Lm), Ab = spread(A);
+          const uint32_t UR = __byte_perm(Ub, Rb, 0x5140), URh = __byte_perm(Ub, Rb, 0x7362);  // U0 R0 U1 R1 | U2 R2 U3 R3
+          const uint32_t DL = __byte_perm(Db, Lb, 0x5140), DLh = __byte_perm(Db, Lb, 0x7362);  // D0 L0 D1 L1 | D2 L2 D3 L3
           uint32_t *o = s_stage + 5 * q;
-          o[0] = bit(U, 0, 0) | bit(R, 0, 1) | bit(D, 0, 2) | bit(Lm, 0, 3);
-          o[1] = bit(A, 0, 0) | bit(U, 1, 1) | bit(R, 1, 2) | bit(D, 1, 3);
-          o[2] = bit(Lm, 1, 0) | bit(A, 1, 1) | bit(U, 2, 2) | bit(R, 2, 3);
-          o[3] = bit(D, 2, 0) | bit(Lm, 2, 1) | bit(A, 2, 2) | bit(U, 3, 3);
-          o[4] = bit(R, 3, 0) | bit(D, 3, 1) | bit(Lm, 3, 2) | bit(A, 3, 3);
+          o[0] = __byte_perm(UR, DL, 0x5410);
+          o[1] = __byte_perm(__byte_perm(UR, DL, 0x6320), Ab, 0x3214);
+          o[2] = __byte_perm(__byte_perm(DL, URh, 0x5403), Ab, 0x3250);
+          o[3] = __byte_perm(__byte_perm(DLh, URh, 0x6010), Ab, 0x3610);
+          o[4] = __byte_perm(__byte_perm(URh, DLh, 0x0763), Ab, 0x7210);
         }
       }
       __syncwarp();
@@ -2049,6 +2094,169 @@ __device__ __forceinline__ void gym_emit_quads(const GrlKParams &prm, int max_tu
       }
       __syncwarp();
     }
+  }
+  if (stats && lane < P) {
+    int tiles = 0;
+    for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + lane * NW + k]);
+    int32_t *so = stats + ((size_t)game * P + lane) * 4;
+    so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ARMY_COUNT];
+    so[1] = tiles;
+    so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> lane) & 1u);
+    so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_GENERAL_IDX];
+  }
+  __syncwarp();
+}
+
+// The same read-outs for baked boards with N % 4 != 0 (15x15), from the slab in SHARED memory: like obs_linear,
+// the game's [P][9][N] block is one linear, 16-byte aligned sweep of 128-bit stores addressed by position in the
+// block (plane = e / N, tile = e % N, compile-time N), a 4-bit window of the plane's staged channel mask going
+// through the nibble table.  The game's [P][N*5] mask bytes are assembled per tile in shared memory, pre-shifted
+// by the block's misalignment, and leave as an aligned 32-bit sweep.
+template <int PT, int N>
+__device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+                                                float *__restrict__ obs, uint8_t *__restrict__ mask,
+                                                int32_t *__restrict__ stats, const uint32_t *s, const uint32_t *stt,
+                                                const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g) {
+  constexpr int NW = (N + 31) / 32, NWP = NW + 1, CH = GRL_GYM_CHANNELS;
+  const GrlLayout &L = prm.L;
+  const int P = prm.P;
+  const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+  uint32_t *s_dir = sw;                                          // [PT][4][NW]
+  uint32_t *chm = sw + PT * 4 * NW;                              // [PT*9][NWP] channel masks
+  uint32_t *minem = chm + PT * CH * NWP;                         // [PT][NWP]   own tiles in sight (the 0.5 of plane 1)
+  float *logv = reinterpret_cast<float *>(minem + PT * NWP);     // [N + 4]
+  uint8_t *stage = reinterpret_cast<uint8_t *>(chm);             // the mask bytes reuse the observation staging
+  const bool w = lane < NW;
+  const uint32_t M = w ? stt[lane] : 0u, C = w ? stt[NW + lane] : 0u, G = w ? stt[2 * NW + lane] : 0u;
+  if (mask) {
+    const uint32_t gt1 = army_gt1_mask<32>(army, NW, N, g);
+    const DirMasks dm = dir_targets<32>(M, g);
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      if (p < P && w) {
+        const uint32_t own = s[L.off_own + p * NW + lane];
+        const uint32_t v = prm.fog ? s[L.off_vis + p * NW + lane] : g.valid;
+        const uint32_t src = v & own & gt1;
+        s_dir[(p * 4 + 0) * NW + lane] = src & dm.up;
+        s_dir[(p * 4 + 1) * NW + lane] = src & dm.right;
+        s_dir[(p * 4 + 2) * NW + lane] = src & dm.down;
+        s_dir[(p * 4 + 3) * NW + lane] = src & dm.left;
+      }
+    }
+  }
+  if (obs) {
+    if (lane < NWP) {
+      const uint32_t valid = w ? g.valid : 0u;
+      uint32_t any_own = 0;
+#pragma unroll
+      for (int p = 0; p < PT; p++)
+        if (p < P && w) any_own |= s[L.off_own + p * NW + lane];
+#pragma unroll
+      for (int p = 0; p < PT; p++) {
+        if (p < P) {
+          const uint32_t own = w ? s[L.off_own + p * NW + lane] : 0u;
+          const uint32_t v = w ? (prm.fog ? s[L.off_vis + p * NW + lane] : valid) : 0u;
+          uint32_t *c = chm + p * CH * NWP + lane;
+          c[0 * NWP] = v;
+          c[1 * NWP] = v & any_own & ~own;  // enemy -> 1.0; own tiles come from minem -> 0.5
+          c[2 * NWP] = v;                   // x log(army + 1) / 10
+          c[3 * NWP] = valid & ~(M | C | G);
+          c[4 * NWP] = M;
+          c[5 * NWP] = C;
+          c[6 * NWP] = G;
+          c[7 * NWP] = valid;               // x turn / max_turns
+          c[8 * NWP] = 0u;
+          minem[p * NWP + lane] = v & own;
+        }
+      }
+    }
+    for (int t = lane; t < N + 4; t += 32) logv[t] = t < N ? __ldg(logtab + army[t]) : 0.f;  // logtab[0] == 0
+    __syncwarp();
+
+    const float tf = fminf(__fdiv_rn((float)s[GRL_HDR_TURN], (float)max_turns), 1.0f);
+    auto elem = [&](int e) -> float {
+      const int plane = e / N, t = e - plane * N, k = plane % CH;
+      const uint32_t bit = (chm[plane * NWP + (t >> 5)] >> (t & 31)) & 1u;
+      if (k == 1) return ((minem[(plane / CH) * NWP + (t >> 5)] >> (t & 31)) & 1u) ? 0.5f : (bit ? 1.f : 0.f);
+      if (k == 2) return bit ? logv[t] : 0.f;
+      if (k == 7) return tf;
+      return bit ? 1.f : 0.f;
+    };
+    const int total = P * CH * N;  // floats in this game's block
+    float *base = obs + (size_t)game * total;
+    const int head = (int)((4u - (uint32_t)(((size_t)game * total) & 3u)) & 3u);
+    const int body4 = (total - head) / 4;
+    const int tail0 = head + 4 * body4;
+    if (lane < head) __stcs(base + lane, elem(lane));
+    if (lane < total - tail0) __stcs(base + tail0 + lane, elem(tail0 + lane));
+    const char *lutb = reinterpret_cast<const char *>(lut);
+    float4 *body = reinterpret_cast<float4 *>(base + head);
+#pragma unroll 2
+    for (int i = lane; i < body4; i += 32) {
+      const int e = head + 4 * i;
+      const int plane = e / N, t = e - plane * N;
+      if (t + 3 < N) {  // a float4 that straddles two planes is left to the pass below
+        float4 val;
+        const int k = plane % CH;
+        const uint32_t *wp = chm + plane * NWP + (t >> 5);
+        const uint32_t nib = __funnelshift_r(wp[0], wp[1], t & 31) & 0xfu;
+        val = *reinterpret_cast<const float4 *>(lutb + nib * 16u);
+        if (k == 1) {
+          const uint32_t *mp = minem + (plane / CH) * NWP + (t >> 5);
+          const uint32_t nb2 = __funnelshift_r(mp[0], mp[1], t & 31) & 0xfu;
+          const float4 m = *reinterpret_cast<const float4 *>(lutb + nb2 * 16u);
+          val = make_float4(__fmaf_rn(m.x, 0.5f, val.x), __fmaf_rn(m.y, 0.5f, val.y), __fmaf_rn(m.z, 0.5f, val.z),
+                            __fmaf_rn(m.w, 0.5f, val.w));
+        } else if (k == 2) {
+          if (nib) {
+            val.x *= logv[t];
+            val.y *= logv[t + 1];
+            val.z *= logv[t + 2];
+            val.w *= logv[t + 3];
+          }
+        } else if (k == 7) {
+          val = make_float4(tf, tf, tf, tf);
+        }
+        __stcs(body + i, val);
+      }
+    }
+    // the P*9-1 float4s that straddle two planes, one per lane in one extra round of full 128-bit stores (see obs_linear)
+    for (int j = lane; j < P * CH - 1; j += 32) {
+      const int b = (j + 1) * N - head;  // plane boundary, in floats from the start of the aligned body
+      if ((b & 3) && (b >> 2) < body4) {
+        const int e = head + (b & ~3);
+        __stcs(body + (b >> 2), make_float4(elem(e), elem(e + 1), elem(e + 2), elem(e + 3)));
+      }
+    }
+  }
+  __syncwarp();
+  if (mask) {
+    const int total = P * N * 5;  // bytes of this game's block [P][N*5]
+    const size_t goff = (size_t)game * total;
+    const int mis = (int)(goff & 3u);
+    for (int p = 0; p < P; p++) {
+      const uint32_t *d = s_dir + p * 4 * NW;
+      for (int t = lane; t < N; t += 32) {
+        const int wd = t >> 5, b = t & 31;
+        const uint32_t U = (d[wd] >> b) & 1u, R = (d[NW + wd] >> b) & 1u, D = (d[2 * NW + wd] >> b) & 1u,
+                       Lm = (d[3 * NW + wd] >> b) & 1u;
+        uint8_t *o = stage + mis + (p * N + t) * 5;
+        o[0] = (uint8_t)U;
+        o[1] = (uint8_t)R;
+        o[2] = (uint8_t)D;
+        o[3] = (uint8_t)Lm;
+        o[4] = (uint8_t)(U | R | D | Lm);
+      }
+    }
+    __syncwarp();
+    uint8_t *base = mask + goff;
+    const int head = (4 - mis) & 3;
+    const int body4 = (total - head) / 4, tail0 = head + 4 * body4;
+    if (lane < head) base[lane] = stage[mis + lane];
+    if (lane < total - tail0) base[tail0 + lane] = stage[mis + tail0 + lane];
+    uint32_t *dst = reinterpret_cast<uint32_t *>(base + head);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(stage + mis + head);
+    for (int i = lane; i < body4; i += 32) __stcs(dst + i, src[i]);
   }
   if (stats && lane < P) {
     int tiles = 0;

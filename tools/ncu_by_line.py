@@ -27,7 +27,12 @@ def main():
                 break
         m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', l)
         if m:
-            cur = int(m.group(2))
+            # instructions inlined from CUDA headers are charged to the line of OUR file that inlined them
+            if m.group(1).endswith(".cu") or not m.group(4):
+                if m.group(1).endswith(".cu"):
+                    cur = int(m.group(2))
+            else:
+                cur = int(m.group(4)) if m.group(3).endswith(".cu") else cur
             inlined = int(m.group(4)) if m.group(4) else None
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", l):
@@ -55,10 +60,10 @@ def main():
     print(f"{'line':>5} {'inst%':>6} {'stall%':>6}  source")
     for line in sorted(inst, key=lambda l: -(inst[l] / total_i + samp[l] / total_s)):
         pi, ps = 100 * inst[line] / total_i, 100 * samp[line] / total_s
-        if pi < 0.3 and ps < 0.3:
+        if pi < 0.3 and ps < 0.3 and "--all" not in sys.argv:
             continue
         s = text[line - 1].strip()[:110] if text and line and line <= len(text) else ""
-        print(f"{line!s:>5} {pi:6.2f} {ps:6.2f}  {s}")
+        print(f"{line!s:>5} {pi:8.4f} {ps:8.4f}  {s}")
 
 
 if __name__ == "__main__":
