@@ -61,8 +61,19 @@
 #define GRL_OBS_LUT 1
 #endif
 #ifndef GRL_OBS_CHUNK_MAJOR
+// 1: the per-game scalar results (done, winner, step_error, reward, action_index) are staged per CTA in shared
+// memory and written by one warp as contiguous runs; 0 (default): one lane per value straight to global memory.
+// Measured on B200 (profiles/r1_variants.md): staging is 0.3 % slower device-resident, 0.3 % slower through
+// pinned host planes at 20x20 and 2 % slower at 15x15 — the end-of-CTA barrier costs more than the runs save.
+#ifndef GRL_STAGE_SCALARS
+#define GRL_STAGE_SCALARS 0
+#endif
+// observation float4s that straddle two planes (boards with N % 4 != 0): 2 (default) = four per-element evaluations
+// inside the sweep; 0 = a short branch-free merge of the two planes' windows.  Measured at 15x15 x 262,144 games:
+// 0.880 ms (2) vs 0.899 ms (0); taking them out of the sweep (a later round of 128-bit stores, or scalar stores)
+// 1.02-1.03 ms: a warp store with a 16-byte hole, completed later, costs far more than the divergent branch.
 #ifndef GRL_STRADDLE_INLINE
-#define GRL_STRADDLE_INLINE 0
+#define GRL_STRADDLE_INLINE 2
 #endif
 #define GRL_OBS_CHUNK_MAJOR 0  // 1: the round-1a tile-chunk-major observation loop (comparison builds)
 #endif
@@ -702,6 +713,11 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t s_bar[GRL_WARPS_PER_CTA * GPW];
   __shared__ __align__(16) float4 s_lut[16];  // nibble -> four 0/1 floats (observation planes)
+#if GRL_STAGE_SCALARS
+  constexpr int GPC = GRL_WARPS_PER_CTA * GPW;  // games per CTA
+  __shared__ uint8_t s_sc_done[DO_OUT ? GPC : 1], s_sc_winner[DO_OUT ? GPC : 1], s_sc_err[DO_OUT ? GPC : 1];
+  __shared__ uint32_t s_sc_reward[DO_OUT ? GPC * PT : 1], s_sc_aidx[DO_OUT ? GPC * PT : 1];
+#endif
   if (DO_OUT && threadIdx.x < 16) {
     const uint32_t n = threadIdx.x;
     s_lut[n] = make_float4((n & 1u) ? 1.f : 0.f, (n & 2u) ? 1.f : 0.f, (n & 4u) ? 1.f : 0.f, (n & 8u) ? 1.f : 0.f);
@@ -1178,6 +1194,19 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
 
     // ---- scalar read-outs (one lane per value) -------------------------------------------------
     if (DO_OUT) {
+#if GRL_STAGE_SCALARS
+      const int gc = warp * GPW + sub;  // this game's index inside the CTA
+      if (l == 0) {
+        s_sc_done[gc] = over ? 1 : 0;
+        const int n_alive = __popc(alive & pmask);  // engine.go:248-263
+        s_sc_winner[gc] = (uint8_t)(int8_t)((over && n_alive == 1) ? (__ffs(alive & pmask) - 1) : -1);
+        s_sc_err[gc] = (uint8_t)err;
+      }
+      if (l < P) {
+        s_sc_reward[gc * P + l] = S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * l + GRL_PL_REWARD];
+        s_sc_aidx[gc * P + l] = S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * l + GRL_PL_ACTION_INDEX];
+      }
+#else
       if (l == 0) {
         if (prm.done) prm.done[game] = over ? 1 : 0;
         if (prm.winner) {  // engine.go:248-263
@@ -1193,6 +1222,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
           prm.action_index[(size_t)game * P + l] =
               (int32_t)S.hdr[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * l + GRL_PL_ACTION_INDEX];
       }
+#endif
     }
 
     // ---- fused gym step: the tail of GeneralsEnv.step (generals_env.py:268-289) and the client's reward
@@ -1230,6 +1260,28 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
   if (!DO_OUT) return;
   __syncwarp();  // every group's slab in shared memory is final: the plane read-outs below are warp-wide
 
+  // The CTA's scalar results leave as contiguous runs written by its first warp once every warp has finished its
+  // planes: one transaction per plane and CTA instead of one partial-sector write per game and value (which is
+  // also one PCIe write each when the caller's result planes live in pinned host memory).
+  auto flush_scalars = [&]() {
+#if GRL_STAGE_SCALARS
+    __syncthreads();
+    if (warp == 0) {
+      const int cta_game0 = prm.game0 + blockIdx.x * GPC;
+      const int n = min(GPC, game_end - cta_game0);
+      for (int i = lane; i < n; i += 32) {
+        if (prm.done) prm.done[cta_game0 + i] = s_sc_done[i];
+        if (prm.winner) prm.winner[cta_game0 + i] = (int8_t)s_sc_winner[i];
+        if (prm.step_error) prm.step_error[cta_game0 + i] = s_sc_err[i];
+      }
+      for (int i = lane; i < n * P; i += 32) {
+        if (prm.reward) prm.reward[(size_t)cta_game0 * P + i] = __uint_as_float(s_sc_reward[i]);
+        if (prm.action_index) prm.action_index[(size_t)cta_game0 * P + i] = (int32_t)s_sc_aidx[i];
+      }
+    }
+#endif
+  };
+
   if constexpr (GYM) {
     // the client's read-outs of the new state, one game of the warp after the other (obs, N*5 mask, PlayerState)
     const Geo g32 = make_geo(prm, W, lane, 32);
@@ -1247,6 +1299,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
       else
         gym_emit<0>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg, sg + L.slab_words, s_obs, game_g, lane, g32);
     }
+    flush_scalars();
     return;
   }
 
@@ -1391,6 +1444,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
       }
     }
   }
+  flush_scalars();
 }
 
 template <int PT, int LG>
@@ -2195,11 +2249,11 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
     for (int i = lane; i < body4; i += 32) {
       const int e = head + 4 * i;
       const int plane = e / N, t = e - plane * N;
-      if (t + 3 < N) {  // a float4 that straddles two planes is left to the pass below
-        float4 val;
-        const int k = plane % CH;
-        const uint32_t *wp = chm + plane * NWP + (t >> 5);
-        const uint32_t nib = __funnelshift_r(wp[0], wp[1], t & 31) & 0xfu;
+      const int k = plane % CH;
+      const uint32_t *wp = chm + plane * NWP + (t >> 5);
+      uint32_t nib = __funnelshift_r(wp[0], wp[1], t & 31) & 0xfu;  // rows are zero from bit N on
+      float4 val;
+      if (t + 3 < N) {
         val = *reinterpret_cast<const float4 *>(lutb + nib * 16u);
         if (k == 1) {
           const uint32_t *mp = minem + (plane / CH) * NWP + (t >> 5);
@@ -2217,16 +2271,33 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
         } else if (k == 7) {
           val = make_float4(tf, tf, tf, tf);
         }
-        __stcs(body + i, val);
+      } else {
+        // the float4 straddles two planes: its first r tiles close plane k, the rest open plane k+1 (or the next
+        // view's plane 0).  Short and branch-free (the whole warp waits for the one lane that is here), and still
+        // one full 128-bit store (see obs_linear).
+        const int r = N - t;  // 1..3
+        const int p = plane / CH;
+        nib |= (chm[(plane + 1) * NWP] << r) & 0xfu;
+        val = *reinterpret_cast<const float4 *>(lutb + nib * 16u);
+        // plane 1 adds 0.5 on the view's own tiles
+        const uint32_t *mp = minem + p * NWP;
+        const uint32_t mA = k == 1 ? (__funnelshift_r(mp[t >> 5], mp[(t >> 5) + 1], t & 31) & 0xfu) : 0u;
+        const uint32_t mB = k == 0 ? ((mp[0] << r) & 0xfu) : 0u;
+        const float4 m = *reinterpret_cast<const float4 *>(lutb + (mA | mB) * 16u);
+        val = make_float4(__fmaf_rn(m.x, 0.5f, val.x), __fmaf_rn(m.y, 0.5f, val.y), __fmaf_rn(m.z, 0.5f, val.z),
+                          __fmaf_rn(m.w, 0.5f, val.w));
+        // plane 2 scales by log(army + 1) / 10, plane 7 is the turn fraction
+        const bool logA = k == 2, logB = k == 1, tfA = k == 7, tfB = k == 6;
+        const float f0 = logA ? logv[t] : 1.f;
+        const float f1 = (1 < r) ? (logA ? logv[t + 1] : 1.f) : (logB ? logv[1 - r] : 1.f);
+        const float f2 = (2 < r) ? (logA ? logv[t + 2] : 1.f) : (logB ? logv[2 - r] : 1.f);
+        const float f3 = logB ? logv[3 - r] : 1.f;
+        val.x = tfA ? tf : val.x * f0;
+        val.y = ((1 < r) ? tfA : tfB) ? tf : val.y * f1;
+        val.z = ((2 < r) ? tfA : tfB) ? tf : val.z * f2;
+        val.w = tfB ? tf : val.w * f3;
       }
-    }
-    // the P*9-1 float4s that straddle two planes, one per lane in one extra round of full 128-bit stores (see obs_linear)
-    for (int j = lane; j < P * CH - 1; j += 32) {
-      const int b = (j + 1) * N - head;  // plane boundary, in floats from the start of the aligned body
-      if ((b & 3) && (b >> 2) < body4) {
-        const int e = head + (b & ~3);
-        __stcs(body + (b >> 2), make_float4(elem(e), elem(e + 1), elem(e + 2), elem(e + 3)));
-      }
+      __stcs(body + i, val);
     }
   }
   __syncwarp();

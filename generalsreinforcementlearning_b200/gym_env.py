@@ -13,7 +13,10 @@ per gRPC round trip there; B games per kernel launch here):
 The agent is player 0; the opponent is the reference's default random opponent (a uniformly
 random full move, ``_submit_random_opponent_action`` :443-497) drawn on the device, or a second
 action tensor for self-play.  Observations, masks, rewards and flags are torch tensors on the
-engine's device — nothing crosses PCIe per step.  Finished or truncated envs are re-seeded
+engine's device — nothing crosses PCIe per step except one 4-byte "did any episode end" flag.  The tensors step()
+returns are the env's own (double-buffered) output planes: the observation, mask and turn are valid until the next
+step(), reward / terminated / truncated / the other info entries until the one after; clone what must live longer.
+Finished or truncated envs are re-seeded
 automatically (``info["final_observation"]`` keeps the pre-reset view), as Gymnasium vector
 envs do.
 
@@ -80,13 +83,17 @@ class GeneralsVecEnv:
         self._prev_stats = torch.zeros_like(self._stats)
         self._actions = torch.zeros((B, P, 8), dtype=torch.uint8, device=dev)  # grl_action[B][P]
         self._done = torch.zeros(B, dtype=torch.uint8, device=dev)
-        self._winner = torch.zeros(B, dtype=torch.int8, device=dev)
-        self._err = torch.zeros(B, dtype=torch.uint8, device=dev)
         self._turns = torch.zeros(B, dtype=torch.int32, device=dev)
-        self._valid = torch.zeros(B, dtype=torch.uint8, device=dev)
-        self._term = torch.zeros(B, dtype=torch.uint8, device=dev)
-        self._trunc = torch.zeros(B, dtype=torch.uint8, device=dev)
-        self._reward = torch.zeros(B, dtype=torch.float64, device=dev)
+        # per-step result planes, double-buffered: what step() returns stays valid until the step after next, so the
+        # hot loop hands out the kernel's own output tensors instead of cloning them (flags are written as 0/1 bytes
+        # straight into bool tensors)
+        self._out = [dict(reward=torch.zeros(B, dtype=torch.float64, device=dev),
+                          terminated=torch.zeros(B, dtype=torch.bool, device=dev),
+                          truncated=torch.zeros(B, dtype=torch.bool, device=dev),
+                          valid=torch.zeros(B, dtype=torch.bool, device=dev),
+                          winner=torch.zeros(B, dtype=torch.int8, device=dev),
+                          step_error=torch.zeros(B, dtype=torch.uint8, device=dev)) for _ in range(2)]
+        self._flip = 0
         self._nfin = torch.zeros(1, dtype=torch.int32, device=dev)
         self._opp_draws = 0
         self._calls = torch.zeros(B, dtype=torch.int32, device=dev)   # step() calls this episode (incl. rejected actions)
@@ -124,32 +131,38 @@ class GeneralsVecEnv:
         rejection of masked-out indices (that env takes no turn, reward -0.1, generals_env.py:226-229),
         the turn, the gym read-outs, the client's reward (:499-561, float64) and the episode flags."""
         t = self.torch
-        action = t.as_tensor(action, device=self.device).to(t.int64).contiguous()
+        action = t.as_tensor(action, device=self.device)
+        if action.dtype != t.int64 or not action.is_contiguous():
+            action = action.to(t.int64).contiguous()
         oa = None
         if opponent_action is not None:
             oa = t.as_tensor(opponent_action, device=self.device).to(t.int64).contiguous()
         self._opp_draws += 1
+        self._flip ^= 1
+        o = self._out[self._flip]
         self.engine.gym_step(self.max_turns, self._base_seed * 1000003 + self._opp_draws, action=action, opponent_action=oa,
                              obs=self._obs, mask=self._mask, stats=self._stats, actions=self._actions,
-                             prev_stats=self._prev_stats, turns=self._turns, calls=self._calls, reward=self._reward,
-                             terminated=self._term, truncated=self._trunc, valid=self._valid, done=self._done,
-                             winner=self._winner, step_error=self._err, n_finished=self._nfin)
-        terminated, truncated = self._term.bool(), self._trunc.bool()
-        info: Dict[str, Any] = {"turn": self._turns.clone(), "invalid_action": ~self._valid.bool(),
-                                "winner": self._winner.to(t.int32), "step_error": self._err.clone()}
-        reward = self._reward.clone()
+                             prev_stats=self._prev_stats, turns=self._turns, calls=self._calls, reward=o["reward"],
+                             terminated=o["terminated"], truncated=o["truncated"], valid=o["valid"], done=self._done,
+                             winner=o["winner"], step_error=o["step_error"], n_finished=self._nfin)
+        terminated, truncated, reward = o["terminated"], o["truncated"], o["reward"]
+        # info tensors are the env's own planes: valid until the next step() (turn, mask) or the one after (the rest)
+        info: Dict[str, Any] = {"invalid_action": ~o["valid"], "winner": o["winner"], "step_error": o["step_error"]}
+        turn = self._turns
         if int(self._nfin.item()) > 0:   # the one host read of the step: does any env start a new episode?
             finished = terminated | truncated
             ids = finished.nonzero(as_tuple=True)[0]
             info["final_observation"] = self._obs[ids, 0].clone()
             info["final_env_ids"] = ids
+            turn = self._turns.clone()       # the finished envs' turn counters restart below
             ids_np = ids.cpu().numpy()
             self._episode[ids_np] += 1
             self.engine.reset_seeded(self._seeds(ids_np), ids_np.astype(np.int32))
             self._turns[ids] = 0
             self._calls[ids] = 0
             self._refresh()
-        info["valid_actions_mask"] = self._mask[:, 0]   # a view of the env's mask plane: valid until the next step()
+        info["turn"] = turn
+        info["valid_actions_mask"] = self._mask[:, 0]
         return self._obs[:, 0], reward, terminated, truncated, info
 
     def sample_actions(self, generator=None):

@@ -16,7 +16,8 @@ VARIANTS = {
     "w16": ["GRL_WARPS_PER_CTA=16"],
     "mb5": ["GRL_MIN_BLOCKS=5"],
     "mb6": ["GRL_MIN_BLOCKS=6"],
-    "straddle_inline": ["GRL_STRADDLE_INLINE=2"],
+    "straddle_merge": ["GRL_STRADDLE_INLINE=0"],
+    "staged_scalars": ["GRL_STAGE_SCALARS=1"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
