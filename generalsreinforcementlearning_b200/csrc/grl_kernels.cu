@@ -433,7 +433,14 @@ template <int PT, int LG>
 __device__ __noinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK &gk, uint32_t *s, const uint32_t *st,
                                            uint32_t *s_act, uint32_t alive, bool over, uint32_t turn_before, int game, Geo g,
                                            int W, int H, int N, int NW);
-__host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N);
+#define GRL_GYM_EMIT_GENERIC 0
+#define GRL_GYM_EMIT_QUADS 1
+#define GRL_GYM_EMIT_LINEAR 2
+// which read-out writer a geometry uses: baked boards with N % 4 == 0 -> quads, other baked boards -> linear
+__host__ __device__ constexpr int grl_gym_emit_mode(int TW, int TH) {
+  return TW > 0 ? (((TW * TH) & 3) == 0 ? GRL_GYM_EMIT_QUADS : GRL_GYM_EMIT_LINEAR) : GRL_GYM_EMIT_GENERIC;
+}
+__host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N, int mode);
 template <int NT>
 __device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
                                          float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats,
@@ -735,7 +742,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
   constexpr bool kSnap = GRL_DIRTY_WB && (LG == 32 || GRL_PACKED_SNAPSHOT);
   const int per_game = (kSnap ? 2 : 1) * L.slab_words + L.static_words + act_words;
   // baked geometries with N % 4 != 0 stage channel masks + an army-fraction plane per warp (obs_linear)
-  const int obs_scratch = GYM ? grl_gym_smem_words(P, NW, N) : grl_obs_scratch_words(TW, TH, PT, NW);
+  const int obs_scratch = GYM ? grl_gym_smem_words(P, NW, N, grl_gym_emit_mode(TW, TH)) : grl_obs_scratch_words(TW, TH, PT, NW);
   uint32_t *wbase = smem + warp * (GPW * per_game + obs_scratch);
   uint32_t *s_obs = wbase + GPW * per_game;
 
@@ -1809,15 +1816,18 @@ __global__ void __launch_bounds__(256)
 // and every player's [9][N] observation block is written as one linear, 16-byte aligned sweep of
 // 128-bit stores (as the turn kernel's observation writer does); the N*5 mask bytes go out as an
 // aligned 32-bit sweep.  Shared-memory words per warp: see grl_gym_smem_words().
-__host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N) {
+__host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N, int mode) {
   const int PT = P <= 2 ? 2 : (P <= 4 ? 4 : 8);
-  const int generic = (3 * P + 5 + 5 * P) * (NW + 1) + N + 4;                 // gym_emit
-  const int quads = PT * 4 * NW + 5 * ((N + 3) / 4);                           // gym_emit_quads: dir rows + one player's mask
-  const int lin_obs = (PT * GRL_GYM_CHANNELS + PT) * (NW + 1) + N + 4;         // gym_emit_linear: channel masks + log plane
-  const int lin_mask = (P * N * 5 + 8 + 3) / 4;                                //                  ... or the game's mask bytes
-  const int linear = PT * 4 * NW + (lin_obs > lin_mask ? lin_obs : lin_mask);
-  int m = generic > quads ? generic : quads;
-  m = m > linear ? m : linear;
+  int m;
+  if (mode == GRL_GYM_EMIT_QUADS) {  // gym_emit_quads: dir rows + one player's mask words
+    m = PT * 4 * NW + 5 * ((N + 3) / 4);
+  } else if (mode == GRL_GYM_EMIT_LINEAR) {  // gym_emit_linear: dir rows + (channel masks + log plane | the game's mask bytes)
+    const int lin_obs = (PT * GRL_GYM_CHANNELS + PT) * (NW + 1) + N + 4;
+    const int lin_mask = (P * N * 5 + 8 + 3) / 4;
+    m = PT * 4 * NW + (lin_obs > lin_mask ? lin_obs : lin_mask);
+  } else {  // gym_emit
+    m = (3 * P + 5 + 5 * P) * (NW + 1) + N + 4;
+  }
   return (m + 3) & ~3;
 }
 
@@ -2348,7 +2358,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GrlLayout &L = prm.L;
   const Geo g = make_geo(prm, prm.W, lane, 32);
-  uint32_t *sw = smem + warp * grl_gym_smem_words(prm.P, prm.NW, prm.N);
+  uint32_t *sw = smem + warp * grl_gym_smem_words(prm.P, prm.NW, prm.N, GRL_GYM_EMIT_GENERIC);
   for (int game = blockIdx.x * GRL_WARPS_PER_CTA + warp; game < prm.B; game += gridDim.x * GRL_WARPS_PER_CTA)
     gym_emit<0>(prm, max_turns, logtab, obs, mask, stats, prm.state + (size_t)game * L.slab_words,
                 prm.statics + (size_t)game * L.static_words, sw, game, lane, g);
@@ -2547,7 +2557,7 @@ static inline int grid_for(int items_per_cta_warps, int n) {
 static size_t grl_turn_smem_bytes(const GrlLayout &L, int TW, int TH, int PT, int LG, bool gym) {
   const bool snap = GRL_DIRTY_WB && (LG == 32 || GRL_PACKED_SNAPSHOT);
   const int per_game = (snap ? 2 : 1) * L.slab_words + L.static_words + 2 * GRL_MAX_ACTIONS;
-  const int scratch = gym ? grl_gym_smem_words(L.P, L.NW, L.N) : grl_obs_scratch_words(TW, TH, PT, L.NW);
+  const int scratch = gym ? grl_gym_smem_words(L.P, L.NW, L.N, grl_gym_emit_mode(TW, TH)) : grl_obs_scratch_words(TW, TH, PT, L.NW);
   return (size_t)GRL_WARPS_PER_CTA * (size_t)((32 / LG) * per_game + scratch) * 4u;
 }
 
@@ -2699,7 +2709,7 @@ cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *lo
   // warp-per-game kernel with linear 128-bit sweeps; GRL_GYM_FLAT=1 keeps the thread-per-tile version for comparison
   static const bool flat = [] { const char *e = getenv("GRL_GYM_FLAT"); return e && e[0] == '1'; }();
   if (!flat) {
-    const size_t smem = (size_t)GRL_WARPS_PER_CTA * grl_gym_smem_words(prm.P, prm.NW, prm.N) * 4u;
+    const size_t smem = (size_t)GRL_WARPS_PER_CTA * grl_gym_smem_words(prm.P, prm.NW, prm.N, GRL_GYM_EMIT_GENERIC) * 4u;
     static size_t tuned = 0;
     if (smem > 48 * 1024 && smem > tuned) {
       cudaError_t e = cudaFuncSetAttribute(grl_gym_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -81,9 +81,9 @@ def main():
         os.remove(f)
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "generalsreinforcementlearning_b200", "csrc", "libgrlcuda.so")],
                    cwd="/tmp/dis", capture_output=True)
-    cub = [f for f in glob.glob("/tmp/dis/grl_kernels*.cubin")][0]
+    cub = [f for f in glob.glob("/tmp/dis/grl_kernels.sm_100a.cubin")][0]
     open("/tmp/dis/k.dis", "w").write(subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout)
-    mangled = f"_Z15grl_turn_kernelILi{2 if P <= 2 else 4}ELi{W}ELi{H}ELi32ELb1ELb1EEv10GrlKParams"
+    mangled = f"_Z15grl_turn_kernelILi{2 if P <= 2 else 4}ELi{W}ELi{H}ELi32ELb1ELb1ELb0EEv10GrlKParams7GrlGymK"
     ph = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_phases.py"), "/tmp/ncu_src.csv", "/tmp/dis/k.dis", mangled,
                          os.path.join(ROOT, "generalsreinforcementlearning_b200", "csrc", "grl_kernels.cu"), str(games)],
                         capture_output=True, text=True)
