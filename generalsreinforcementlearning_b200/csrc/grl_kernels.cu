@@ -72,6 +72,29 @@
 // inside the sweep; 0 = a short branch-free merge of the two planes' windows.  Measured at 15x15 x 262,144 games:
 // 0.880 ms (2) vs 0.899 ms (0); taking them out of the sweep (a later round of 128-bit stores, or scalar stores)
 // 1.02-1.03 ms: a warp store with a 16-byte hole, completed later, costs far more than the divergent branch.
+// running (plane, tile) counters in obs_linear instead of a division per store: measured SLOWER (0.9125 vs 0.8748 ms
+// per 262,144 15x15 games) — the independent index computations schedule better than the loop-carried chain
+// store policy of the linear observation writer.  A store-only stream of the 15x15 layout (blocks that start and end
+// mid-sector) runs at 6.6 TB/s with the default policy against 6.1 with evict-first (tools/micro/store_holes.cu), but in
+// the kernel the default policy lets the observation stream evict the prefetched state: 0.950 vs 0.877 ms per 262,144 games.
+// 1 (default): st.global.cs
+#ifndef GRL_LINEAR_STCS
+#define GRL_LINEAR_STCS 1
+#endif
+#if GRL_LINEAR_STCS
+#define GRL_LIN_ST(p, v) __stcs((p), (v))
+#else
+#define GRL_LIN_ST(p, v) (*(p) = (v))
+#endif
+// 1 (default): the games of a warp (lane groups) write their observation blocks as ONE sector-complete run: the 32-byte
+// sector shared by two consecutive games' blocks is written whole by the later game's pass (tools/micro/store_holes.cu:
+// 7.0 vs 6.1 TB/s for the 15x15 layout)
+#ifndef GRL_OBS_JOIN
+#define GRL_OBS_JOIN 1
+#endif
+#ifndef GRL_OBS_INCR
+#define GRL_OBS_INCR 0
+#endif
 #ifndef GRL_STRADDLE_INLINE
 #define GRL_STRADDLE_INLINE 2
 #endif
@@ -323,9 +346,23 @@ __device__ __forceinline__ DirMasks dir_targets(uint32_t M, const Geo &g) {
   return d;
 }
 
-// army > 1 per tile as a linear bitmask (word `lane`): the group's lanes test LG tiles per ballot
+// army > 1 per tile as a linear bitmask (word `lane`).  Lane l tests its own 32 tiles from four 128-bit loads of
+// the uint16 army plane, two tiles per 32-bit word at a time (halfword != 0 after clearing bit 0, by the carry
+// trick), so the cost does not depend on how many games share the warp.  (The first version balloted LG tiles per
+// step: 32 serial ballots per 15x15 game, 375 warp instructions per game and 19 % of the stall samples there.)
+__device__ __forceinline__ uint32_t gt1_pair(uint32_t x) {  // bit 0: low halfword > 1, bit 1: high halfword > 1
+  const uint32_t y = x & 0xfffefffeu;
+  const uint32_t z = ((y & 0x7fff7fffu) + 0x7fff7fffu) | y;  // bit 15 / bit 31: halfword != 0
+  return ((z >> 15) & 1u) | ((z >> 30) & 2u);
+}
+#ifndef GRL_GT1_BALLOT
+#define GRL_GT1_BALLOT 0
+#endif
 template <int LG>
 __device__ __forceinline__ uint32_t army_gt1_mask(const uint16_t *army, int NW, int N, const Geo &g) {
+  // one game per warp keeps the ballot version: 13 ballots for 20x20 cost about the same as 13 active lanes doing the
+  // vector version, and measured 1.4 % faster there (0.3423 vs 0.347 ms per 65,536 games)
+  if (GRL_GT1_BALLOT || LG == 32) {
   uint32_t mine = 0;
   for (int i = 0; i < NW; i++) {
 #pragma unroll
@@ -337,6 +374,20 @@ __device__ __forceinline__ uint32_t army_gt1_mask(const uint16_t *army, int NW, 
     }
   }
   return mine;
+  }
+  uint32_t m = 0;
+  if (g.lane < NW) {
+    const int NA = (N + 7) & ~7;  // the plane holds NA entries (grl_layout.h): a group of 8 tiles is inside it or not at all
+    const uint4 *a4 = reinterpret_cast<const uint4 *>(army + 32 * g.lane);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (32 * g.lane + 8 * j < NA) {
+        const uint4 q = a4[j];
+        m |= (gt1_pair(q.x) | (gt1_pair(q.y) << 2) | (gt1_pair(q.z) << 4) | (gt1_pair(q.w) << 6)) << (8 * j);
+      }
+    }
+  }
+  return m & g.valid;
 }
 
 struct PackedAction {  // grl_action as one 64-bit word (little endian field order)
@@ -617,7 +668,8 @@ __device__ __forceinline__ float obs_element(const uint32_t *chm, const float *f
 
 template <int PT, int N>
 __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView &S, const float4 *lut, uint32_t *scratch,
-                                           int P, int NW, int game, int lane) {
+                                           int P, int NW, int game, int lane, const uint32_t *prev_slab = nullptr,
+                                           bool next_in_warp = false) {
   const int NWP = NW + 1;
   uint32_t *chm = scratch;                                                   // [P*9][NWP]
   float *frac = reinterpret_cast<float *>(scratch + PT * GRL_OBS_CHANNELS * NWP);  // [N + 4]
@@ -655,19 +707,63 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
 
   const int total = P * GRL_OBS_CHANNELS * N;  // floats in this game's block
   float *base = prm.obs + (size_t)game * total;
-  const int head = (int)((4u - (uint32_t)(((size_t)game * total) & 3u)) & 3u);  // floats before the 16-byte aligned body
-  const int body4 = (total - head) / 4;
-  const int tail0 = head + 4 * body4;
-  if (lane < head) __stcs(base + lane, obs_element<N>(chm, frac, NWP, lane));
-  if (lane < total - tail0) __stcs(base + tail0 + lane, obs_element<N>(chm, frac, NWP, tail0 + lane));
+  // A 15x15 block is 16,200 bytes: it starts and ends mid-sector, and a 32-byte sector completed by two different store
+  // instructions costs the memory system far more than its bytes (tools/micro/store_holes.cu).  Consecutive games of one
+  // warp therefore join their blocks into one sector-complete run: the sector two blocks share is written WHOLE by the
+  // later game's pass (lanes 0-1, one instruction) — its first `lead` floats are the tail of the previous game's last
+  // plane (player P-1, channel 8 = fog), evaluated from that game's slab, which is still in shared memory.
+  const int lead = (int)(((size_t)game * total) & 7u);           // floats of this block's first sector that belong to the previous block
+  const int trail = (int)(((size_t)(game + 1) * total) & 7u);    // floats of this block in the sector it shares with the next block
+  const bool join_prev = GRL_OBS_JOIN && prev_slab != nullptr && lead != 0;
+  const bool join_next = GRL_OBS_JOIN && next_in_warp && trail != 0;
+  int head, end;
+  if (join_prev) {
+    if (lane < 2) {
+      const uint32_t *pv = prev_slab + prm.L.off_vis + (P - 1) * NW;
+      float v4[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int pos = 4 * lane + c;
+        if (pos < lead) {
+          const int t = N - lead + pos;
+          const uint32_t seen = prm.fog ? ((pv[t >> 5] >> (t & 31)) & 1u) : 1u;
+          v4[c] = seen ? 0.f : 1.f;
+        } else {
+          v4[c] = obs_element<N>(chm, frac, NWP, pos - lead);
+        }
+      }
+      GRL_LIN_ST(reinterpret_cast<float4 *>(base - lead) + lane, make_float4(v4[0], v4[1], v4[2], v4[3]));
+    }
+    head = 8 - lead;
+  } else {
+    head = (int)((4u - (uint32_t)(((size_t)game * total) & 3u)) & 3u);  // floats before the 16-byte aligned body
+    if (lane < head) GRL_LIN_ST(base + lane, obs_element<N>(chm, frac, NWP, lane));
+  }
+  if (join_next) {
+    end = total - trail;  // the shared sector is left to the next game's pass
+  } else {
+    end = head + 4 * ((total - head) / 4);
+    if (lane < total - end) GRL_LIN_ST(base + end + lane, obs_element<N>(chm, frac, NWP, end + lane));
+  }
+  const int body4 = (end - head) / 4;
   const char *lutb = reinterpret_cast<const char *>(lut);
   float4 *body = reinterpret_cast<float4 *>(base + head);
+#if GRL_OBS_INCR
+  // (plane, tile, channel) of a lane's float4 advance by 128 floats per round: running counters instead of a
+  // division and a modulo per store (N > 128, so a round crosses at most one plane boundary)
+  int e = head + 4 * lane;
+  int plane = e / N, t = e - plane * N, k = plane % GRL_OBS_CHANNELS;
+  const uint32_t *row = chm + plane * NWP;
+#endif
 #pragma unroll 2
   for (int i = lane; i < body4; i += 32) {
+#if !GRL_OBS_INCR
     const int e = head + 4 * i;
     const int plane = e / N, t = e - plane * N;
     const int k = plane % GRL_OBS_CHANNELS;
-    const uint32_t *wp = chm + plane * NWP + (t >> 5);
+    const uint32_t *row = chm + plane * NWP;
+#endif
+    const uint32_t *wp = row + (t >> 5);
     uint32_t nib = __funnelshift_r(wp[0], wp[1], t & 31) & 0xfu;  // rows are zero from bit N on
     float4 val;
     if (t + 3 < N) {
@@ -705,7 +801,17 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
       }
 #endif
     }
-    __stcs(body + i, val);
+    GRL_LIN_ST(body + i, val);
+#if GRL_OBS_INCR
+    e += 128;
+    t += 128;
+    while (t >= N) {  // once at most for the boards that come here (N > 128)
+      t -= N;
+      plane += 1;
+      row += NWP;
+      k = k == GRL_OBS_CHANNELS - 1 ? 0 : k + 1;
+    }
+#endif
   }
   __syncwarp();
 }
@@ -1358,7 +1464,9 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
         if (((TW * TH) & 3) == 0)
           obs_plane_major<PT, (TW > 0 && ((TW * TH) & 3) == 0 ? TW * TH : 4)>(prm, Sg, s_lut, P, NW, game_g, lane);
         else
-          obs_linear<PT, (TW > 0 ? TW * TH : 5)>(prm, Sg, s_lut, s_obs, P, NW, game_g, lane);
+          obs_linear<PT, (TW > 0 ? TW * TH : 5)>(prm, Sg, s_lut, s_obs, P, NW, game_g, lane,
+                                                 gi > 0 ? wbase + (gi - 1) * per_game : nullptr,
+                                                 gi + 1 < GPW && game_g + 1 < game_end);
       }
     } else if (gv) {
       // generic geometries (LG == 32: one game per warp), from the mask words in registers

@@ -18,6 +18,10 @@ VARIANTS = {
     "mb6": ["GRL_MIN_BLOCKS=6"],
     "straddle_merge": ["GRL_STRADDLE_INLINE=0"],
     "staged_scalars": ["GRL_STAGE_SCALARS=1"],
+    "obs_incr": ["GRL_OBS_INCR=1"],
+    "linear_st": ["GRL_LINEAR_STCS=0"],
+    "obs_nojoin": ["GRL_OBS_JOIN=0"],
+    "gt1_ballot": ["GRL_GT1_BALLOT=1"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
