@@ -326,7 +326,7 @@ int reset_from_planes(grl_env *env, const int32_t *env_ids, int n, const int32_t
     slabs.assign((size_t)cn * L.slab_words, 0u);
     statics.assign((size_t)cn * L.static_words, 0u);
     std::vector<const char *> errs(cn, nullptr);
-    parallel_for(cn, env->host_threads, [&](int i) {
+    parallel_for(cn, cn < 8 ? 1 : env->host_threads, [&](int i) {
       HostGame g;
       const size_t off = (size_t)(c0 + i) * N;
       g.owner.assign(owner + off, owner + off + N);
@@ -737,14 +737,16 @@ int grl_reset_seeded(grl_env *env, const int32_t *env_ids, int32_t n, const int6
   if (!env || !seeds || n < 0) return fail(GRL_ERR_INVALID_ARG, "bad argument");
   if (n == 0) return GRL_OK;
   CUDA_TRY(cudaSetDevice(env->cfg.device));
-  // maps are generated on the device unless the batch is tiny or GRL_HOST_MAPGEN=1 asks for the host path
-  if (!env->host_mapgen && n >= 64) return reset_seeded_device(env, env_ids, n, seeds);
+  // maps are generated on the device unless the batch is tiny or GRL_HOST_MAPGEN=1 asks for the host path.  (One device
+  // thread per map takes ~0.2 ms whatever n is; the host generator ~30 us per map, plus ~50 us per worker thread it
+  // spawns — a vector env re-seeds a few dozen envs per step, so that path has to stay out of thread-spawn territory.)
+  if (!env->host_mapgen && n >= 8) return reset_seeded_device(env, env_ids, n, seeds);
   const grl_config &c = env->cfg;
   const int N = env->N;
   grl::MapParams mp = grl::DefaultMapParams(c.width, c.height, c.num_players, c.city_ratio, c.city_start_army, c.min_general_spacing);
   std::vector<int32_t> owner((size_t)n * N), army((size_t)n * N), type((size_t)n * N);
   std::vector<uint8_t> ok(n, 1);
-  parallel_for(n, env->host_threads, [&](int i) {
+  parallel_for(n, n < 8 ? 1 : env->host_threads, [&](int i) {
     ok[i] = grl::GenerateMap(c.width, c.height, mp, seeds[i], owner.data() + (size_t)i * N, army.data() + (size_t)i * N,
                              type.data() + (size_t)i * N)
                 ? 1
@@ -870,6 +872,28 @@ int grl_gym_observe(grl_env *env, int32_t max_turns, const grl_gym_outputs *out)
   if ((st = flush_out(env, mask, need_sync))) return st;
   if ((st = flush_out(env, stats, need_sync))) return st;
   if (need_sync) CUDA_TRY(cudaStreamSynchronize(env->stream));
+  return GRL_OK;
+}
+
+int grl_gym_observe_envs(grl_env *env, int32_t max_turns, const int32_t *env_ids, int32_t n, const grl_gym_outputs *out) {
+  if (!env || !out || !env_ids || max_turns < 1 || n < 0) return fail(GRL_ERR_INVALID_ARG, "bad argument");
+  if (n == 0) return GRL_OK;
+  CUDA_TRY(cudaSetDevice(env->cfg.device));
+  const grl_config &c = env->cfg;
+  for (int i = 0; i < n; i++)
+    if (env_ids[i] < 0 || env_ids[i] >= c.num_envs) return fail(GRL_ERR_INVALID_ARG, "env id %d out of range", env_ids[i]);
+  // the planes are written in place at the listed envs' rows: they have to be device memory
+  if ((out->obs && !is_device_ptr(out->obs)) || (out->mask && !is_device_ptr(out->mask)) || (out->stats && !is_device_ptr(out->stats)))
+    return fail(GRL_ERR_UNSUPPORTED, "grl_gym_observe_envs takes device pointers for the planes");
+  int st;
+  if ((st = ensure_logtab(env))) return st;
+  void *d_ids = nullptr;
+  if ((st = ensure(env, SL_AIDX, (size_t)n * 4, &d_ids))) return st;
+  CUDA_TRY(cudaMemcpyAsync(d_ids, env_ids, (size_t)n * 4, cudaMemcpyHostToDevice, env->stream));
+  GrlKParams prm = base_params(env);
+  CUDA_TRY(grl_launch_gym(prm, max_turns, env->d_logtab, out->obs, out->mask, out->stats, env->stream, (const int32_t *)d_ids, n));
+  env->launches++;
+  CUDA_TRY(cudaStreamSynchronize(env->stream));  // env_ids (pageable host memory) is consumed on return
   return GRL_OK;
 }
 

@@ -96,14 +96,18 @@
 #define GRL_OBS_INCR 0
 #endif
 #ifndef GRL_STRADDLE_INLINE
-#define GRL_STRADDLE_INLINE 2
+#define GRL_STRADDLE_INLINE 3
 #endif
 #define GRL_OBS_CHUNK_MAJOR 0  // 1: the round-1a tile-chunk-major observation loop (comparison builds)
 #endif
 
 // per-warp shared-memory words of the linear observation writer (only baked boards with N % 4 != 0)
 __host__ __device__ constexpr int grl_obs_scratch_words(int TW, int TH, int PT, int NW) {
-  return (TW > 0 && ((TW * TH) & 3) != 0) ? ((PT * GRL_OBS_CHANNELS * (NW + 1) + TW * TH + 4 + 3) & ~3) : 0;
+  // channel masks [PT*9][NW+1] + army-fraction plane [N+4], rounded to 16 bytes, + the P*9-1 precomputed float4s that
+  // straddle two planes
+  return (TW > 0 && ((TW * TH) & 3) != 0)
+             ? (((PT * GRL_OBS_CHANNELS * (NW + 1) + TW * TH + 4 + 3) & ~3) + 4 * PT * GRL_OBS_CHANNELS)
+             : 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -673,6 +677,7 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
   const int NWP = NW + 1;
   uint32_t *chm = scratch;                                                   // [P*9][NWP]
   float *frac = reinterpret_cast<float *>(scratch + PT * GRL_OBS_CHANNELS * NWP);  // [N + 4]
+  float4 *sf = reinterpret_cast<float4 *>(scratch + ((PT * GRL_OBS_CHANNELS * NWP + N + 4 + 3) & ~3));  // [PT*9] straddlers
   if (lane < NWP) {
     const bool w = lane < NW;
     const uint32_t valid = w ? prm.geom[lane] : 0u;
@@ -746,6 +751,21 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
     if (lane < total - end) GRL_LIN_ST(base + end + lane, obs_element<N>(chm, frac, NWP, end + lane));
   }
   const int body4 = (end - head) / 4;
+#if GRL_STRADDLE_INLINE == 3
+  // The P*9-1 float4s that straddle two planes are evaluated here, one per lane, and parked in shared memory: inside
+  // the sweep the per-element branch is divergent — one lane straddles in 17 of a 15x15 game's 32 rounds and the whole
+  // warp pays four element evaluations each time (592 of 3,183 warp instructions per game).  The store itself stays in
+  // the sweep: a 16-byte hole completed later costs far more than any of this (tools/micro/store_holes.cu).
+  for (int j = lane; j < P * GRL_OBS_CHANNELS - 1; j += 32) {
+    const int b = (j + 1) * N - head;  // plane boundary, in floats from the start of the aligned body
+    if ((b & 3) && b > 0 && (b >> 2) < body4) {
+      const int e = head + (b & ~3);
+      sf[j] = make_float4(obs_element<N>(chm, frac, NWP, e), obs_element<N>(chm, frac, NWP, e + 1),
+                          obs_element<N>(chm, frac, NWP, e + 2), obs_element<N>(chm, frac, NWP, e + 3));
+    }
+  }
+  __syncwarp();
+#endif
   const char *lutb = reinterpret_cast<const char *>(lut);
   float4 *body = reinterpret_cast<float4 *>(base + head);
 #if GRL_OBS_INCR
@@ -775,7 +795,9 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
         val.w *= frac[t + 3];
       }
     } else {
-#if GRL_STRADDLE_INLINE == 2  // comparison builds: four per-element evaluations
+#if GRL_STRADDLE_INLINE == 3  // evaluated before the sweep, one per lane
+      val = sf[plane];
+#elif GRL_STRADDLE_INLINE == 2  // comparison builds: four per-element evaluations
       val.x = obs_element<N>(chm, frac, NWP, e);
       val.y = obs_element<N>(chm, frac, NWP, e + 1);
       val.z = obs_element<N>(chm, frac, NWP, e + 2);
@@ -1930,7 +1952,7 @@ __host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N, int mode
   if (mode == GRL_GYM_EMIT_QUADS) {  // gym_emit_quads: dir rows + one player's mask words
     m = PT * 4 * NW + 5 * ((N + 3) / 4);
   } else if (mode == GRL_GYM_EMIT_LINEAR) {  // gym_emit_linear: dir rows + (channel masks + log plane | the game's mask bytes)
-    const int lin_obs = (PT * GRL_GYM_CHANNELS + PT) * (NW + 1) + N + 4;
+    const int lin_obs = (((PT * GRL_GYM_CHANNELS + PT) * (NW + 1) + N + 4 + 3) & ~3) + 4 * PT * GRL_GYM_CHANNELS + 4;
     const int lin_mask = (P * N * 5 + 8 + 3) / 4;
     m = PT * 4 * NW + (lin_obs > lin_mask ? lin_obs : lin_mask);
   } else {  // gym_emit
@@ -2297,6 +2319,7 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
   uint32_t *chm = sw + PT * 4 * NW;                              // [PT*9][NWP] channel masks
   uint32_t *minem = chm + PT * CH * NWP;                         // [PT][NWP]   own tiles in sight (the 0.5 of plane 1)
   float *logv = reinterpret_cast<float *>(minem + PT * NWP);     // [N + 4]
+  float4 *sf = reinterpret_cast<float4 *>(sw + ((PT * 4 * NW + (PT * CH + PT) * NWP + N + 4 + 3) & ~3));  // [PT*9] straddlers
   uint8_t *stage = reinterpret_cast<uint8_t *>(chm);             // the mask bytes reuse the observation staging
   const bool w = lane < NW;
   const uint32_t M = w ? stt[lane] : 0u, C = w ? stt[NW + lane] : 0u, G = w ? stt[2 * NW + lane] : 0u;
@@ -2363,6 +2386,14 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
     if (lane < total - tail0) __stcs(base + tail0 + lane, elem(tail0 + lane));
     const char *lutb = reinterpret_cast<const char *>(lut);
     float4 *body = reinterpret_cast<float4 *>(base + head);
+    for (int j = lane; j < P * CH - 1; j += 32) {  // the float4s that straddle two planes
+      const int b = (j + 1) * N - head;
+      if ((b & 3) && (b >> 2) < body4) {
+        const int e = head + (b & ~3);
+        sf[j] = make_float4(elem(e), elem(e + 1), elem(e + 2), elem(e + 3));
+      }
+    }
+    __syncwarp();
 #pragma unroll 2
     for (int i = lane; i < body4; i += 32) {
       const int e = head + 4 * i;
@@ -2390,30 +2421,7 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
           val = make_float4(tf, tf, tf, tf);
         }
       } else {
-        // the float4 straddles two planes: its first r tiles close plane k, the rest open plane k+1 (or the next
-        // view's plane 0).  Short and branch-free (the whole warp waits for the one lane that is here), and still
-        // one full 128-bit store (see obs_linear).
-        const int r = N - t;  // 1..3
-        const int p = plane / CH;
-        nib |= (chm[(plane + 1) * NWP] << r) & 0xfu;
-        val = *reinterpret_cast<const float4 *>(lutb + nib * 16u);
-        // plane 1 adds 0.5 on the view's own tiles
-        const uint32_t *mp = minem + p * NWP;
-        const uint32_t mA = k == 1 ? (__funnelshift_r(mp[t >> 5], mp[(t >> 5) + 1], t & 31) & 0xfu) : 0u;
-        const uint32_t mB = k == 0 ? ((mp[0] << r) & 0xfu) : 0u;
-        const float4 m = *reinterpret_cast<const float4 *>(lutb + (mA | mB) * 16u);
-        val = make_float4(__fmaf_rn(m.x, 0.5f, val.x), __fmaf_rn(m.y, 0.5f, val.y), __fmaf_rn(m.z, 0.5f, val.z),
-                          __fmaf_rn(m.w, 0.5f, val.w));
-        // plane 2 scales by log(army + 1) / 10, plane 7 is the turn fraction
-        const bool logA = k == 2, logB = k == 1, tfA = k == 7, tfB = k == 6;
-        const float f0 = logA ? logv[t] : 1.f;
-        const float f1 = (1 < r) ? (logA ? logv[t + 1] : 1.f) : (logB ? logv[1 - r] : 1.f);
-        const float f2 = (2 < r) ? (logA ? logv[t + 2] : 1.f) : (logB ? logv[2 - r] : 1.f);
-        const float f3 = logB ? logv[3 - r] : 1.f;
-        val.x = tfA ? tf : val.x * f0;
-        val.y = ((1 < r) ? tfA : tfB) ? tf : val.y * f1;
-        val.z = ((2 < r) ? tfA : tfB) ? tf : val.z * f2;
-        val.w = tfB ? tf : val.w * f3;
+        val = sf[plane];  // evaluated before the sweep, one per lane (see obs_linear)
       }
       __stcs(body + i, val);
     }
@@ -2461,15 +2469,19 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
 
 __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
     grl_gym_warp_kernel(const __grid_constant__ GrlKParams prm, int max_turns, const float *__restrict__ logtab,
-                        float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats) {
+                        float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats,
+                        const int32_t *__restrict__ ids, int n_ids) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GrlLayout &L = prm.L;
   const Geo g = make_geo(prm, prm.W, lane, 32);
   uint32_t *sw = smem + warp * grl_gym_smem_words(prm.P, prm.NW, prm.N, GRL_GYM_EMIT_GENERIC);
-  for (int game = blockIdx.x * GRL_WARPS_PER_CTA + warp; game < prm.B; game += gridDim.x * GRL_WARPS_PER_CTA)
+  const int count = ids ? n_ids : prm.B;  // an id list restricts the read-outs to those envs
+  for (int i = blockIdx.x * GRL_WARPS_PER_CTA + warp; i < count; i += gridDim.x * GRL_WARPS_PER_CTA) {
+    const int game = ids ? ids[i] : i;
     gym_emit<0>(prm, max_turns, logtab, obs, mask, stats, prm.state + (size_t)game * L.slab_words,
                 prm.statics + (size_t)game * L.static_words, sw, game, lane, g);
+  }
 }
 #undef GYM_NIB4
 
@@ -2813,10 +2825,10 @@ cudaError_t grl_launch_visibility(const GrlKParams &prm, uint8_t *visible, uint8
 }
 
 cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *logtab, float *obs, uint8_t *mask, int32_t *stats,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const int32_t *ids, int n_ids) {
   // warp-per-game kernel with linear 128-bit sweeps; GRL_GYM_FLAT=1 keeps the thread-per-tile version for comparison
   static const bool flat = [] { const char *e = getenv("GRL_GYM_FLAT"); return e && e[0] == '1'; }();
-  if (!flat) {
+  if (!flat || ids) {
     const size_t smem = (size_t)GRL_WARPS_PER_CTA * grl_gym_smem_words(prm.P, prm.NW, prm.N, GRL_GYM_EMIT_GENERIC) * 4u;
     static size_t tuned = 0;
     if (smem > 48 * 1024 && smem > tuned) {
@@ -2824,11 +2836,12 @@ cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *lo
       if (e != cudaSuccess) return e;
       tuned = smem;
     }
-    int grid = grid_for(GRL_WARPS_PER_CTA, prm.B);
+    int grid = grid_for(GRL_WARPS_PER_CTA, ids ? n_ids : prm.B);
     if (grid > 148 * 16) grid = 148 * 16;
-    grl_gym_warp_kernel<<<grid, GRL_WARPS_PER_CTA * 32, smem, stream>>>(prm, max_turns, logtab, obs, mask, stats);
+    grl_gym_warp_kernel<<<grid, GRL_WARPS_PER_CTA * 32, smem, stream>>>(prm, max_turns, logtab, obs, mask, stats, ids, n_ids);
     return cudaGetLastError();
   }
+  if (ids) return cudaErrorNotSupported;  // the flat comparison kernel has no id list
   size_t total = (size_t)prm.B * prm.P * prm.N;
   grl_gym_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(prm, max_turns, logtab, obs, mask, stats);
   return cudaGetLastError();

@@ -11,7 +11,7 @@ cudaError_t grl_launch_sample(const GrlKParams &prm, void *out, cudaStream_t str
 cudaError_t grl_launch_mask_bytes(const GrlKParams &prm, int variant, uint8_t *out, cudaStream_t stream);
 cudaError_t grl_launch_visibility(const GrlKParams &prm, uint8_t *visible, uint8_t *fog, cudaStream_t stream);
 cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *logtab, float *obs, uint8_t *mask, int32_t *stats,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const int32_t *ids = nullptr, int n_ids = 0);
 cudaError_t grl_launch_gym_step(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream);
 cudaError_t grl_launch_gym_encode(const GrlKParams &prm, const long long *action_idx, int player, int slot, const uint8_t *mask,
                                   int skip_invalid, void *actions, uint8_t *valid, cudaStream_t stream);

@@ -170,6 +170,14 @@ class BatchedEngine:
         o.obs, o.mask, o.stats = _ptr(obs), _ptr(mask), _ptr(stats)
         self.lib.check(self.lib.gym_observe(self._h, int(max_turns), C.byref(o)), "gym_observe")
 
+    def gym_observe_envs(self, max_turns: int, env_ids, obs=None, mask=None, stats=None) -> None:
+        """The gym read-outs of the listed envs only (host int32 ids); other envs' rows are left untouched."""
+        ids = np.ascontiguousarray(env_ids, dtype=np.int32)
+        o = GymOutputs()
+        o.obs, o.mask, o.stats = _ptr(obs), _ptr(mask), _ptr(stats)
+        self.lib.check(self.lib.gym_observe_envs(self._h, int(max_turns), ids.ctypes.data, len(ids), C.byref(o)),
+                       "gym_observe_envs")
+
     def gym_encode(self, action_idx, player: int, slot: int, mask, skip_invalid: bool, actions, valid) -> None:
         """Discrete(N*5) indices -> grl_action slots, rejecting indices the gym mask forbids."""
         self.lib.check(self.lib.gym_encode(self._h, _ptr(action_idx), int(player), int(slot), _ptr(mask),

@@ -106,8 +106,11 @@ class GeneralsVecEnv:
     def _seeds(self, env_ids: np.ndarray) -> np.ndarray:
         return self._base_seed + env_ids.astype(np.int64) + self._episode[env_ids] * self.num_envs
 
-    def _refresh(self):
-        self.engine.gym_observe(self.max_turns, self._obs, self._mask, self._stats)
+    def _refresh(self, env_ids=None):
+        if env_ids is None:
+            self.engine.gym_observe(self.max_turns, self._obs, self._mask, self._stats)
+        else:   # only the re-seeded envs: the other rows already hold the step's read-outs
+            self.engine.gym_observe_envs(self.max_turns, env_ids, self._obs, self._mask, self._stats)
 
     # ------------------------------------------------------------------ gym API
     def reset(self, seed: Optional[int] = None, options=None) -> Tuple[Any, Dict[str, Any]]:
@@ -160,7 +163,7 @@ class GeneralsVecEnv:
             self.engine.reset_seeded(self._seeds(ids_np), ids_np.astype(np.int32))
             self._turns[ids] = 0
             self._calls[ids] = 0
-            self._refresh()
+            self._refresh(ids_np)
         info["turn"] = turn
         info["valid_actions_mask"] = self._mask[:, 0]
         return self._obs[:, 0], reward, terminated, truncated, info

@@ -238,6 +238,10 @@ int grl_visibility(grl_env *env, uint8_t *visible, uint8_t *fog);
 /* generals_gym observation / mask / player stats of the current state for every (env, player).
  * max_turns normalises channel 7 (generals_env.py:337). */
 int grl_gym_observe(grl_env *env, int32_t max_turns, const grl_gym_outputs *out);
+/* The same read-outs for the n listed envs only (env_ids: host int32[n]).  The planes keep their full
+ * [B][P][...] shape; entries of other envs are left untouched.  What a vector env calls after re-seeding the
+ * envs whose episode ended (generals_env.py:188-208 reset -> _get_observation / _get_info). */
+int grl_gym_observe_envs(grl_env *env, int32_t max_turns, const int32_t *env_ids, int32_t n, const grl_gym_outputs *out);
 
 /* generals_gym action decoding for one player (generals_env.py:389-441): action_idx[b] = tile*5 +
  * {up,right,down,left,half} becomes a grl_action in slot `slot` of env b (a half move goes to the first

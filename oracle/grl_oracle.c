@@ -1574,6 +1574,16 @@ int grlo_gym_observe(grlo_env *e, int32_t max_turns, const grl_gym_outputs *out)
   return GRL_OK;
 }
 
+int grlo_gym_observe_envs(grlo_env *e, int32_t max_turns, const int32_t *env_ids, int32_t n, const grl_gym_outputs *out) {
+  if (!e || !out || !env_ids || max_turns < 1 || n < 0) return GRL_ERR_INVALID_ARG;
+  gym_ctx_t x = {e, max_turns, out};
+  for (int i = 0; i < n; i++) {
+    if (env_ids[i] < 0 || env_ids[i] >= e->cfg.num_envs) return GRL_ERR_INVALID_ARG;
+    gym_range(&x, env_ids[i], env_ids[i] + 1);
+  }
+  return GRL_OK;
+}
+
 int grlo_get_state(grlo_env *e, int32_t first, int32_t count, const grl_state_planes *o) {
   if (!e || !o || first < 0 || count < 0 || first + count > e->cfg.num_envs) return GRL_ERR_INVALID_ARG;
   int N = e->N, P = e->cfg.num_players;

@@ -129,3 +129,49 @@ def test_cuda_gym_step_unfused_sequence_matches_oracle(cuda_lib):
                            "matches_oracle and not unfused"], env=env, cwd=ROOT, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True, timeout=900)
     assert proc.returncode == 0, proc.stdout[-3000:]
+
+
+def _partial_observe(lib, W, H, P, B, on_device):
+    """Play, observe everything, play on, re-observe a subset: those rows equal a full read-out, the others keep
+    the earlier one (grl_gym_observe_envs — what the vector env calls after re-seeding finished envs)."""
+    import torch
+
+    from generalsreinforcementlearning_b200 import _abi
+
+    dev = torch.device("cuda", 0) if on_device else torch.device("cpu")
+    e = BatchedEngine(lib, make_config(lib, num_envs=B, width=W, height=H, num_players=P, max_actions=P, host_threads=1))
+    e.reset_seeded(np.arange(B, dtype=np.int64) + 99)
+    N = W * H
+    mk = lambda: (torch.zeros((B, P, 9, H, W), dtype=torch.float32, device=dev), torch.zeros((B, P, N * 5), dtype=torch.uint8, device=dev),
+                  torch.zeros((B, P, 4), dtype=torch.int32, device=dev))
+    for _ in range(12):
+        e.step(None, _abi.STEP_FLAG_RANDOM_POLICY, 3)
+    part = mk()
+    e.gym_observe(500, *part)
+    before = [t.clone() for t in part]
+    for _ in range(9):
+        e.step(None, _abi.STEP_FLAG_RANDOM_POLICY, 4)
+    ids = np.array(sorted({0, B - 1, B // 2, 7 % B, 33 % B}), dtype=np.int32)
+    e.gym_observe_envs(500, ids, *part)
+    full = mk()
+    e.gym_observe(500, *full)
+    if on_device:
+        torch.cuda.synchronize()
+    sel = torch.zeros(B, dtype=torch.bool)
+    sel[torch.as_tensor(ids.astype(np.int64))] = True
+    for got, new, old, name in zip(part, full, before, ("obs", "mask", "stats")):
+        got, new, old = got.cpu(), new.cpu(), old.cpu()
+        assert torch.equal(got[sel], new[sel]), f"{name}: listed envs must hold the new read-out"
+        assert torch.equal(got[~sel], old[~sel]), f"{name}: other envs must be left untouched"
+        assert not torch.equal(new[~sel], old[~sel]), "the state did move on"
+    e.close()
+
+
+def test_oracle_gym_observe_envs(oracle_lib):
+    _partial_observe(oracle_lib, 8, 8, 2, 40, False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,P,B", [(15, 15, 2, 300), (20, 20, 2, 65), (9, 7, 3, 40)])
+def test_cuda_gym_observe_envs(cuda_lib, W, H, P, B):
+    _partial_observe(cuda_lib, W, H, P, B, True)

@@ -22,6 +22,7 @@ VARIANTS = {
     "linear_st": ["GRL_LINEAR_STCS=0"],
     "obs_nojoin": ["GRL_OBS_JOIN=0"],
     "gt1_ballot": ["GRL_GT1_BALLOT=1"],
+    "straddle_elem": ["GRL_STRADDLE_INLINE=2"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)

@@ -35,9 +35,28 @@ def main():
             t_policy += a1 - a0
             t_env += time.perf_counter() - a1
         dt = time.perf_counter() - t0
-        out.append({"envs": B, "board": W, "env_steps_per_s": round(B * steps / dt), "ms_per_vector_step": round(1e3 * dt / steps, 3),
-                    "ms_env_step": round(1e3 * t_env / steps, 3), "ms_random_policy": round(1e3 * t_policy / steps, 3),
-                    "env_only_steps_per_s": round(B * steps / t_env)})
+        rec = {"envs": B, "board": W, "env_steps_per_s": round(B * steps / dt), "ms_per_vector_step": round(1e3 * dt / steps, 3),
+               "ms_env_step": round(1e3 * t_env / steps, 3), "ms_random_policy": round(1e3 * t_policy / steps, 3),
+               "env_only_steps_per_s": round(B * steps / t_env)}
+        # steady state of a long run: episode ends are spread over time, so EVERY step re-seeds B/max_turns envs
+        # (device map generation, turn-0 set-up, read-outs of the new games) on top of the step itself
+        env._calls.copy_(torch.randint(0, env.max_turns, (B,), device=env._calls.device, dtype=torch.int32))
+        for _ in range(5):
+            env.step(act())
+        torch.cuda.synchronize()
+        t_env = 0.0
+        resets = 0
+        for _ in range(steps):
+            action = act()
+            torch.cuda.synchronize()
+            a1 = time.perf_counter()
+            obs, r, term, trunc, info = env.step(action)
+            torch.cuda.synchronize()
+            t_env += time.perf_counter() - a1
+            resets += int((term | trunc).sum())
+        rec.update({"steady_ms_env_step": round(1e3 * t_env / steps, 3), "steady_env_only_steps_per_s": round(B * steps / t_env),
+                    "steady_resets_per_step": round(resets / steps, 1)})
+        out.append(rec)
         env.close()
     print(json.dumps(out))
 
