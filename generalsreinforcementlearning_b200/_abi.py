@@ -162,6 +162,7 @@ ABI_FUNCTIONS = {
     "visibility": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gym_observe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GymOutputs)]),
     "gym_observe_envs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(GymOutputs)]),
+    "gym_sample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p]),
     "gym_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "gym_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(GymStepIO)]),
     "sample_actions": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),

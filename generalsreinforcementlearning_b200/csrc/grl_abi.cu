@@ -912,6 +912,17 @@ int grl_gym_encode(grl_env *env, const int64_t *action_idx, int32_t player, int3
   return GRL_OK;
 }
 
+int grl_gym_sample(grl_env *env, uint64_t seed, const uint8_t *mask, int32_t player, int64_t *action) {
+  if (!env || !mask || !action) return fail(GRL_ERR_INVALID_ARG, "null argument");
+  if (player < 0 || player >= env->cfg.num_players) return fail(GRL_ERR_INVALID_ARG, "player %d out of range", player);
+  CUDA_TRY(cudaSetDevice(env->cfg.device));
+  if (!is_device_ptr(mask) || !is_device_ptr(action)) return fail(GRL_ERR_UNSUPPORTED, "grl_gym_sample takes device pointers");
+  GrlKParams prm = base_params(env);
+  CUDA_TRY(grl_launch_gym_sample(prm, seed, mask, player, (long long *)action, env->stream));
+  env->launches++;
+  return GRL_OK;
+}
+
 int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const grl_gym_step_io *io) {
   if (!env || !io || max_turns < 1) return fail(GRL_ERR_INVALID_ARG, "bad argument");
   const grl_config &c = env->cfg;

@@ -2518,6 +2518,37 @@ __global__ void grl_gym_encode_kernel(const GrlKParams prm, const long long *__r
   }
 }
 
+// A uniformly random valid gym action per env: the k-th set byte of the env's N*5 mask bytes, one warp per env
+// (32 bytes per ballot; the draw is policy_draw(seed, global env, 0, player) mod the number of set bytes).
+__global__ void __launch_bounds__(256) grl_gym_sample_kernel(const GrlKParams prm, unsigned long long seed,
+                                                             const uint8_t *__restrict__ mask, int player,
+                                                             long long *__restrict__ action) {
+  const int lane = threadIdx.x & 31;
+  const int M = prm.N * 5;
+  for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < prm.B; b += (gridDim.x * blockDim.x) >> 5) {
+    const uint8_t *row = mask + ((size_t)b * prm.P + player) * M;
+    int total = 0;
+    for (int i = 0; i < M; i += 32) total += __popc(__ballot_sync(FULL, i + lane < M && row[i + lane] != 0));
+    long long pick = 0;
+    if (total > 0) {
+      const uint64_t r = policy_draw(seed, (uint64_t)(prm.env_id_base + b), 0ull, (uint64_t)player);
+      int k = (int)(r % (uint64_t)total);
+      for (int i = 0; i < M; i += 32) {
+        const uint32_t w = __ballot_sync(FULL, i + lane < M && row[i + lane] != 0);
+        const int c = __popc(w);
+        if (k < c) {
+          uint32_t v = w;
+          for (int j = 0; j < k; j++) v &= v - 1u;  // drop the k lowest set bits
+          pick = i + __ffs(v) - 1;
+          break;
+        }
+        k -= c;
+      }
+    }
+    if (lane == 0) action[b] = pick;
+  }
+}
+
 // The tail of GeneralsEnv.step (generals_env.py:268-289) and its client-side reward (:499-561), one thread per env.
 // `force_full` patches the random opponent's slot to a full move (the reference's random opponent never sends
 // half moves, :483).
@@ -2851,6 +2882,14 @@ cudaError_t grl_launch_gym_encode(const GrlKParams &prm, const long long *action
                                   int skip_invalid, void *actions, uint8_t *valid, cudaStream_t stream) {
   grl_gym_encode_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm, action_idx, player, slot, mask, skip_invalid,
                                                                            (uint2 *)actions, valid);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_gym_sample(const GrlKParams &prm, unsigned long long seed, const uint8_t *mask, int player, long long *action,
+                                  cudaStream_t stream) {
+  int grid = grid_for(8, prm.B);
+  if (grid > 148 * 16) grid = 148 * 16;
+  grl_gym_sample_kernel<<<grid, 256, 0, stream>>>(prm, seed, mask, player, action);
   return cudaGetLastError();
 }
 

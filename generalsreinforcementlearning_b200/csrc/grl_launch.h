@@ -15,6 +15,8 @@ cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *lo
 cudaError_t grl_launch_gym_step(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream);
 cudaError_t grl_launch_gym_encode(const GrlKParams &prm, const long long *action_idx, int player, int slot, const uint8_t *mask,
                                   int skip_invalid, void *actions, uint8_t *valid, cudaStream_t stream);
+cudaError_t grl_launch_gym_sample(const GrlKParams &prm, unsigned long long seed, const uint8_t *mask, int player, long long *action,
+                                  cudaStream_t stream);
 cudaError_t grl_launch_gym_patch(const GrlKParams &prm, void *actions, int slot, cudaStream_t stream);
 cudaError_t grl_launch_gym_finish(const GrlKParams &prm, int max_turns, const int32_t *stats, const int32_t *prev_stats,
                                   const uint8_t *valid, const uint8_t *done, const int8_t *winner, int32_t *turns, int32_t *calls,

@@ -178,6 +178,11 @@ class BatchedEngine:
         self.lib.check(self.lib.gym_observe_envs(self._h, int(max_turns), ids.ctypes.data, len(ids), C.byref(o)),
                        "gym_observe_envs")
 
+    def gym_sample(self, seed: int, mask, player: int, action) -> None:
+        """A uniformly random valid Discrete(N*5) action per env from the gym mask plane (int64 [B])."""
+        self.lib.check(self.lib.gym_sample(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(mask), int(player), _ptr(action)),
+                       "gym_sample")
+
     def gym_encode(self, action_idx, player: int, slot: int, mask, skip_invalid: bool, actions, valid) -> None:
         """Discrete(N*5) indices -> grl_action slots, rejecting indices the gym mask forbids."""
         self.lib.check(self.lib.gym_encode(self._h, _ptr(action_idx), int(player), int(slot), _ptr(mask),

@@ -96,6 +96,8 @@ class GeneralsVecEnv:
         self._flip = 0
         self._nfin = torch.zeros(1, dtype=torch.int32, device=dev)
         self._opp_draws = 0
+        self._sample_draws = 0
+        self._sampled = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
         self._calls = torch.zeros(B, dtype=torch.int32, device=dev)   # step() calls this episode (incl. rejected actions)
         self._episode = np.zeros(B, dtype=np.int64)
         self._base_seed = int(seed)
@@ -168,13 +170,20 @@ class GeneralsVecEnv:
         info["valid_actions_mask"] = self._mask[:, 0]
         return self._obs[:, 0], reward, terminated, truncated, info
 
-    def sample_actions(self, generator=None):
-        """A uniformly random VALID action per env (envs without one get action 0, which is rejected)."""
+    def sample_actions(self, generator=None, player: int = 0):
+        """A uniformly random VALID action per env (envs without one get action 0, which is rejected): the random
+        agent of the reference (python/generals_agent/random_agent.py) for every env in one kernel launch.  With a
+        torch ``generator`` the draw goes through ``torch.multinomial`` instead (slower: a [B, N*5] float pass)."""
         t = self.torch
-        m = self._mask[:, 0].to(t.float32)
-        none = m.sum(1) == 0
-        m[:, 0] += none.to(t.float32)
-        return t.multinomial(m, 1, generator=generator or self._gen).squeeze(1)
+        if generator is not None:
+            m = self._mask[:, player].to(t.float32)
+            none = m.sum(1) == 0
+            m[:, 0] += none.to(t.float32)
+            return t.multinomial(m, 1, generator=generator).squeeze(1)
+        self._sample_draws += 1
+        out = self._sampled[self._sample_draws & 1]
+        self.engine.gym_sample(self._base_seed * 7919 + self._sample_draws, self._mask, player, out)
+        return out
 
     def opponent_view(self):
         """Player 1's observation and mask (self-play)."""

@@ -253,6 +253,13 @@ int grl_gym_observe_envs(grl_env *env, int32_t max_turns, const int32_t *env_ids
 int grl_gym_encode(grl_env *env, const int64_t *action_idx, int32_t player, int32_t slot, const uint8_t *mask,
                    int32_t skip_invalid, grl_action *actions, uint8_t *valid);
 
+/* A uniformly random VALID action per env for `player`, drawn from the mask plane of grl_gym_observe /
+ * grl_gym_step (what the reference's random agent and its random opponent do with `valid_actions_mask`,
+ * python/generals_gym/generals_env.py:443-497, python/generals_agent/random_agent.py): action[b] = the k-th set entry of
+ * mask[b][player][:] in index order, k = draw(seed, global env id, player) mod the number of set entries; 0 (which the
+ * env rejects) when none is set.  libgrlcuda.so requires device pointers; the oracle takes host pointers. */
+int grl_gym_sample(grl_env *env, uint64_t seed, const uint8_t *mask, int32_t player, int64_t *action);
+
 /* One GeneralsEnv.step() for every env in a single call (generals_env.py:210-289): decode the agent's
  * (player 0) action and reject it client-side when the mask forbids it (that env then takes no turn,
  * reward -0.1); the opponent (player 1) plays `opponent_action` or, when that is NULL, a uniformly random

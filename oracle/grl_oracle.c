@@ -1512,6 +1512,30 @@ int grlo_gym_encode(grlo_env *e, const int64_t *action_idx, int32_t player, int3
   return GRL_OK;
 }
 
+/* a uniformly random valid gym action per env: the k-th set mask entry in index order (grlcuda.h) */
+int grlo_gym_sample(grlo_env *e, uint64_t seed, const uint8_t *mask, int32_t player, int64_t *action) {
+  if (!e || !mask || !action) return GRL_ERR_INVALID_ARG;
+  int P = e->cfg.num_players, M = e->N * 5;
+  if (player < 0 || player >= P) return GRL_ERR_INVALID_ARG;
+  for (int b = 0; b < e->cfg.num_envs; b++) {
+    const uint8_t *row = mask + ((size_t)b * P + player) * M;
+    int total = 0;
+    for (int i = 0; i < M; i++) total += row[i] != 0;
+    int64_t pick = 0;
+    if (total > 0) {
+      uint64_t r = policy_draw(seed, (uint64_t)(e->cfg.env_id_base + b), 0, (uint64_t)player);
+      int k = (int)(r % (uint64_t)total);
+      for (int i = 0; i < M; i++)
+        if (row[i] && k-- == 0) {
+          pick = i;
+          break;
+        }
+    }
+    action[b] = pick;
+  }
+  return GRL_OK;
+}
+
 int grlo_gym_observe(grlo_env *e, int32_t max_turns, const grl_gym_outputs *out);
 
 /* GeneralsEnv.step (generals_env.py:210-289) for every env; reward :499-561 in float64 like the client */

@@ -126,7 +126,7 @@ def test_cuda_gym_step_unfused_sequence_matches_oracle(cuda_lib):
     so fused == unfused == oracle.  The switch is read once per process, hence the subprocess."""
     env = dict(os.environ, GRL_GYM_UNFUSED="1")
     proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.abspath(__file__), "-k",
-                           "matches_oracle and not unfused"], env=env, cwd=ROOT, stdout=subprocess.PIPE,
+                           "gym_step_matches_oracle"], env=env, cwd=ROOT, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True, timeout=900)
     assert proc.returncode == 0, proc.stdout[-3000:]
 
@@ -140,6 +140,8 @@ def _partial_observe(lib, W, H, P, B, on_device):
 
     dev = torch.device("cuda", 0) if on_device else torch.device("cpu")
     e = BatchedEngine(lib, make_config(lib, num_envs=B, width=W, height=H, num_players=P, max_actions=P, host_threads=1))
+    if on_device:
+        e.use_torch_stream()
     e.reset_seeded(np.arange(B, dtype=np.int64) + 99)
     N = W * H
     mk = lambda: (torch.zeros((B, P, 9, H, W), dtype=torch.float32, device=dev), torch.zeros((B, P, N * 5), dtype=torch.uint8, device=dev),
@@ -175,3 +177,58 @@ def test_oracle_gym_observe_envs(oracle_lib):
 @pytest.mark.parametrize("W,H,P,B", [(15, 15, 2, 300), (20, 20, 2, 65), (9, 7, 3, 40)])
 def test_cuda_gym_observe_envs(cuda_lib, W, H, P, B):
     _partial_observe(cuda_lib, W, H, P, B, True)
+
+
+def _sampled_actions(lib, W, H, P, B, on_device, turns=25):
+    import torch
+
+    from generalsreinforcementlearning_b200 import _abi
+
+    dev = torch.device("cuda", 0) if on_device else torch.device("cpu")
+    e = BatchedEngine(lib, make_config(lib, num_envs=B, width=W, height=H, num_players=P, max_actions=P, host_threads=1,
+                                       env_id_base=1000))
+    if on_device:
+        e.use_torch_stream()   # the planes are filled by torch kernels and by the engine in turn
+    e.reset_seeded(np.arange(B, dtype=np.int64) + 5)
+    for _ in range(turns):
+        e.step(None, _abi.STEP_FLAG_RANDOM_POLICY, 3)
+    N = W * H
+    mask = torch.zeros((B, P, N * 5), dtype=torch.uint8, device=dev)
+    e.gym_observe(500, None, mask, None)
+    out = []
+    for p in range(P):
+        for seed in (1, 2, 2 ** 63 + 11):
+            a = torch.full((B,), -7, dtype=torch.int64, device=dev)
+            e.gym_sample(seed, mask, p, a)
+            out.append(a.cpu().numpy().copy())
+    m = mask.cpu().numpy()
+    e.close()
+    return m, out
+
+
+def test_oracle_gym_sample_draws_valid_actions(oracle_lib):
+    m, draws = _sampled_actions(oracle_lib, 8, 8, 2, 64, False)
+    P = m.shape[1]
+    k = 0
+    for p in range(P):
+        per_seed = []
+        for _ in range(3):
+            a = draws[k]; k += 1
+            has = m[:, p].any(1)
+            assert (m[np.arange(len(a)), p, a][has] == 1).all(), "a drawn action is valid wherever one exists"
+            assert (a[~has] == 0).all()
+            per_seed.append(a)
+        assert not np.array_equal(per_seed[0], per_seed[1]), "different seeds, different draws"
+    # uniform over the valid entries: over many envs every position class of the k-th-set-bit draw is used
+    first = np.array([np.flatnonzero(m[b, 0])[0] if m[b, 0].any() else 0 for b in range(m.shape[0])])
+    assert (draws[0] != first).any(), "not simply the first valid action"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,P,B", [(15, 15, 2, 300), (20, 20, 2, 70), (9, 7, 3, 33)])
+def test_cuda_gym_sample_matches_oracle(cuda_lib, oracle_lib, W, H, P, B):
+    mg, g = _sampled_actions(cuda_lib, W, H, P, B, True)
+    mo, o = _sampled_actions(oracle_lib, W, H, P, B, False)
+    assert np.array_equal(mg, mo)
+    for x, y in zip(g, o):
+        assert np.array_equal(x, y)
