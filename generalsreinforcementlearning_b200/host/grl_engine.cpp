@@ -343,6 +343,15 @@ std::map<int, core::Error> EnginePool::StepAll(const context::Context &ctx,
   return errs;
 }
 
+void EnginePool::StepBatch(const grl_action *actions, const grl_step_outputs *out, bool randomPolicy, uint64_t policySeed) {
+  const auto &f = lib_->fn();
+  Check(f.step_fused(env_, actions, randomPolicy ? GRL_STEP_FLAG_RANDOM_POLICY : GRL_STEP_FLAG_NONE, policySeed, out),
+        "grl_step_fused");
+  Check(f.sync(env_), "grl_sync");
+  for (Engine *e : engines_)
+    if (e) e->stale_ = true;  // gs(), IsGameOver(), GetWinner() re-read the slot from HBM on demand
+}
+
 // ---- Engine --------------------------------------------------------------------------------
 Engine::Engine(EnginePool *pool, int slot, std::shared_ptr<EnginePool> owned)
     : pool_(pool), owned_(std::move(owned)), slot_(slot) {}

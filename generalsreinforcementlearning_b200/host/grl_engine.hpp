@@ -31,6 +31,8 @@
 #include "grl_core.hpp"
 
 struct grl_env;  // include/grlcuda.h
+struct grl_action;
+struct grl_step_outputs;
 
 namespace grl {
 
@@ -171,6 +173,13 @@ class EnginePool {
   // Returns one error per stepped slot (nil entries included).
   std::map<int, core::Error> StepAll(const context::Context &ctx,
                                      const std::map<int, std::vector<core::Action>> &perSlot);
+
+  // The bulk form of the same call for callers that own whole batches (a self-play driver, a trainer): `actions` is
+  // the C ABI's [numEnvs][max_actions] array (host or device memory; nullptr with `randomPolicy` = every alive player
+  // plays the synthetic uniformly random legal move), `out` the C ABI's output planes (any member may be null).  One
+  // fused launch; per-slot views are refreshed lazily afterwards.
+  void StepBatch(const ::grl_action *actions, const ::grl_step_outputs *out, bool randomPolicy = false,
+                 uint64_t policySeed = 0);
 
   int NumEnvs() const { return B_; }
   int Width() const { return W_; }

@@ -658,6 +658,30 @@ TEST(TestEnginePool_SlotsAreIndependentGames) {
   EXPECT_EQ(0, reused->gs()->Turn, "fresh game");
 }
 
+TEST(TestEnginePool_StepBatch) {
+  // bulk callers hand the C ABI's arrays straight through; per-slot views follow
+  const int B = 512, W = 10, H = 10, P = 2;
+  game::EnginePool pool(g_lib, B, W, H, P);
+  std::vector<std::unique_ptr<game::Engine>> slots;
+  for (int i = 0; i < B; i++) {
+    game::GameConfig cfg;
+    cfg.Width = W, cfg.Height = H, cfg.Players = P;
+    cfg.Rng = rand::New(rand::NewSource(500 + i));
+    slots.push_back(pool.NewEngine(context::Background(), cfg));
+    REQUIRE(slots.back() != nullptr, "engine %d", i);
+  }
+  for (int t = 0; t < 40; t++) pool.StepBatch(nullptr, nullptr, /*randomPolicy=*/true, /*policySeed=*/9);
+  int moved = 0;
+  for (int i = 0; i < B; i += 37) {
+    game::GameState gs = slots[i]->GameState();
+    EXPECT_EQ(40, gs.Turn, "slot %d took 40 turns", i);
+    int tiles = int(gs.Players[0].OwnedTiles.size()) + int(gs.Players[1].OwnedTiles.size());
+    moved += tiles > 2;
+    EXPECT(!slots[i]->IsGameOver() || slots[i]->GetWinner() >= -1, "flags readable after a bulk step");
+  }
+  EXPECT(moved > 0, "the random policy expands territory");
+}
+
 // ---- rendering.go:34-143 ----------------------------------------------------------------------------
 TEST(TestBoardRendering) {
   auto engine = createTestEngineForActionMask(3, 2, 2);

@@ -34,14 +34,15 @@ def _pick(mask_row, rng, want_invalid):
     return int(idx[rng.integers(0, len(idx))])
 
 
-def gym_rollout(lib, W, H, P, B, steps, max_turns, self_play, seed=77):
+def gym_rollout(lib, W, H, P, B, steps, max_turns, self_play, seed=77, fog=1):
     """Drive grl_gym_step with actions drawn (host RNG) from the library's own mask plane; returns the trace of
     every output plane after every step."""
     import torch
 
     on_device = lib.prefix == "grl_"
     dev = torch.device("cuda", 0) if on_device else torch.device("cpu")
-    e = BatchedEngine(lib, make_config(lib, num_envs=B, width=W, height=H, num_players=P, max_actions=P, host_threads=1))
+    e = BatchedEngine(lib, make_config(lib, num_envs=B, width=W, height=H, num_players=P, max_actions=P, host_threads=1,
+                                       fog_of_war=fog))
     if on_device:
         e.use_torch_stream()
     e.reset_seeded(np.arange(B, dtype=np.int64) + 12345)
@@ -118,6 +119,15 @@ def test_cuda_gym_step_matches_oracle(cuda_lib, oracle_lib, W, H, P, B, steps, m
         assert launches <= 3 + 2 * steps + 2, f"{launches} launches for {steps} fused steps"
     if (W, H) == (5, 5):
         assert any(s["terminated"].any() for s in g), "5x5 games end within 80 steps"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,P,B", [(20, 20, 2, 40), (15, 15, 2, 70), (10, 10, 2, 90), (6, 9, 2, 33)])
+def test_cuda_gym_step_matches_oracle_without_fog(cuda_lib, oracle_lib, W, H, P, B):
+    """fog_of_war = 0: every tile is in sight for every player (each writer takes its own no-fog branch)."""
+    g, _ = gym_rollout(cuda_lib, W, H, P, B, 30, 500, False, fog=0)
+    o, _ = gym_rollout(oracle_lib, W, H, P, B, 30, 500, False, fog=0)
+    _compare(g, o, f"cuda vs oracle {W}x{H}x{P}p, no fog")
 
 
 @pytest.mark.gpu
