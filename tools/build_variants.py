@@ -23,6 +23,7 @@ VARIANTS = {
     "obs_nojoin": ["GRL_OBS_JOIN=0"],
     "gt1_ballot": ["GRL_GT1_BALLOT=1"],
     "straddle_elem": ["GRL_STRADDLE_INLINE=2"],
+    "obs_planewise": ["GRL_OBS_PLANEWISE=1"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
