@@ -118,6 +118,11 @@ class GymStepIO(C.Structure):
                 ("winner", C.c_void_p), ("step_error", C.c_void_p), ("n_finished", C.c_void_p)]
 
 
+class GymAutoresetIO(C.Structure):
+    _fields_ = [("terminated", C.c_void_p), ("truncated", C.c_void_p), ("episode", C.c_void_p), ("turns", C.c_void_p),
+                ("calls", C.c_void_p), ("out", GymOutputs), ("final_obs", C.c_void_p), ("n_reset", C.c_void_p)]
+
+
 STATE_FIELDS = (
     ("owner", np.int32, "N"),
     ("army", np.int32, "N"),
@@ -162,6 +167,7 @@ ABI_FUNCTIONS = {
     "visibility": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gym_observe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GymOutputs)]),
     "gym_observe_envs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(GymOutputs)]),
+    "gym_autoreset": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(GymAutoresetIO)]),
     "gym_sample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p]),
     "gym_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "gym_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(GymStepIO)]),

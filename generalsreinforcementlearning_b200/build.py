@@ -8,7 +8,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SOURCES = ["grl_kernels.cu", "grl_abi.cu", "grl_mapgen_gpu.cu", "grl_mapgen.cpp"]
-HEADERS = ["grl_layout.h", "grl_launch.h", "grl_mapgen.h", "go_rng_cooked.inc", "../../include/grlcuda.h"]
+HEADERS = ["grl_layout.h", "grl_launch.h", "grl_mapgen.h", "go_rng_cooked.inc", "go_rng_lehmer_pow.inc", "../../include/grlcuda.h"]
 LIB = os.path.join(CSRC, "libgrlcuda.so")
 
 NVCC_FLAGS = [

@@ -919,6 +919,47 @@ int grl_gym_encode(grl_env *env, const int64_t *action_idx, int32_t player, int3
   return GRL_OK;
 }
 
+int grl_gym_autoreset(grl_env *env, int32_t max_turns, int64_t base_seed, const grl_gym_autoreset_io *io) {
+  if (!env || !io || max_turns < 1) return fail(GRL_ERR_INVALID_ARG, "bad argument");
+  const grl_config &c = env->cfg;
+  const GrlLayout &L = env->L;
+  CUDA_TRY(cudaSetDevice(c.device));
+  const void *need[] = {io->terminated, io->truncated, io->episode, io->turns, io->calls};
+  for (const void *p : need)
+    if (!p || !is_device_ptr(p)) return fail(GRL_ERR_UNSUPPORTED, "grl_gym_autoreset takes device pointers for every plane");
+  const void *opt[] = {io->out.obs, io->out.mask, io->out.stats, io->final_obs, io->n_reset};
+  for (const void *p : opt)
+    if (p && !is_device_ptr(p)) return fail(GRL_ERR_UNSUPPORTED, "grl_gym_autoreset takes device pointers for every plane");
+  if (io->final_obs && !io->out.obs) return fail(GRL_ERR_INVALID_ARG, "final_obs needs the observation plane");
+  int st;
+  if ((st = ensure_logtab(env))) return st;
+  const int B = c.num_envs;
+  // staging for up to B new games (all envs end together when their episodes started together)
+  void *d_slabs = nullptr, *d_statics = nullptr, *d_misc = nullptr;
+  if ((st = ensure(env, SL_MISC, (size_t)B * L.slab_words * 4 + 16, &d_slabs))) return st;
+  if ((st = ensure(env, SL_MISC2, (size_t)B * L.static_words * 4 + 16, &d_statics))) return st;
+  if ((st = ensure(env, SL_ACTIONS, (size_t)B * 12 + 64, &d_misc))) return st;
+  long long *d_seeds = reinterpret_cast<long long *>(d_misc);
+  int32_t *d_ids = reinterpret_cast<int32_t *>(d_seeds + B);
+  int *d_count = reinterpret_cast<int *>(d_ids + B);  // [0] count, [1] mapgen failure
+  cudaStream_t sq = env->stream;
+  GrlKParams prm = base_params(env);
+  CUDA_TRY(cudaMemsetAsync(d_count, 0, 8, sq));
+  CUDA_TRY(grl_launch_gym_compact(prm, io->terminated, io->truncated, (long long)base_seed, (long long *)io->episode, io->turns, io->calls,
+                                  d_ids, d_seeds, d_count, sq));
+  if (io->final_obs) CUDA_TRY(grl_launch_gym_final_obs(prm, io->out.obs, io->final_obs, d_ids, d_count, sq));
+  CUDA_TRY(grl_launch_zero_rows((uint32_t *)d_slabs, L.slab_words, B, d_count, sq));
+  CUDA_TRY(grl_launch_zero_rows((uint32_t *)d_statics, L.static_words, B, d_count, sq));
+  grl::MapParams hp = grl::DefaultMapParams(c.width, c.height, c.num_players, c.city_ratio, c.city_start_army, c.min_general_spacing);
+  GrlMapParams mp = {hp.players, hp.city_ratio, hp.city_start_army, hp.spacing, hp.veins, hp.min_vein, hp.max_vein};
+  CUDA_TRY(grl_launch_mapgen(L, c.width, c.height, mp, d_seeds, B, (uint32_t *)d_slabs, (uint32_t *)d_statics, d_count + 1, sq, d_count));
+  CUDA_TRY(grl_launch_reset(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, B, sq, d_count));
+  CUDA_TRY(grl_launch_gym(prm, max_turns, env->d_logtab, io->out.obs, io->out.mask, io->out.stats, sq, d_ids, B, d_count));
+  if (io->n_reset) CUDA_TRY(cudaMemcpyAsync(io->n_reset, d_count, 4, cudaMemcpyDeviceToDevice, sq));
+  env->launches += io->final_obs ? 7 : 6;
+  return GRL_OK;
+}
+
 int grl_gym_sample(grl_env *env, uint64_t seed, const uint8_t *mask, int32_t player, int64_t *action) {
   if (!env || !mask || !action) return fail(GRL_ERR_INVALID_ARG, "null argument");
   if (player < 0 || player >= env->cfg.num_players) return fail(GRL_ERR_INVALID_ARG, "player %d out of range", player);

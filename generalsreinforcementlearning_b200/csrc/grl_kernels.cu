@@ -1797,8 +1797,10 @@ __device__ __noinline__ uint32_t elimination_phase(const GrlKParams &prm, uint32
 template <int PT>
 __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
     grl_reset_kernel(const __grid_constant__ GrlKParams prm, const uint32_t *__restrict__ src_state,
-                     const uint32_t *__restrict__ src_static, const int32_t *__restrict__ env_ids, int n) {
+                     const uint32_t *__restrict__ src_static, const int32_t *__restrict__ env_ids, int n,
+                     const int *__restrict__ n_dev) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (n_dev) n = min(n, *n_dev);  // device-side count (grl_gym_autoreset)
   const GrlLayout &L = prm.L;
   const int P = prm.P, NW = prm.NW, N = prm.N;
   const Geo g = make_geo(prm, prm.W, lane, 32);
@@ -2520,13 +2522,13 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
 __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
     grl_gym_warp_kernel(const __grid_constant__ GrlKParams prm, int max_turns, const float *__restrict__ logtab,
                         float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats,
-                        const int32_t *__restrict__ ids, int n_ids) {
+                        const int32_t *__restrict__ ids, int n_ids, const int *__restrict__ n_dev) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GrlLayout &L = prm.L;
   const Geo g = make_geo(prm, prm.W, lane, 32);
   uint32_t *sw = smem + warp * grl_gym_smem_words(prm.P, prm.NW, prm.N, GRL_GYM_EMIT_GENERIC);
-  const int count = ids ? n_ids : prm.B;  // an id list restricts the read-outs to those envs
+  const int count = ids ? (n_dev ? min(n_ids, *n_dev) : n_ids) : prm.B;  // an id list restricts the read-outs to those envs
   for (int i = blockIdx.x * GRL_WARPS_PER_CTA + warp; i < count; i += gridDim.x * GRL_WARPS_PER_CTA) {
     const int game = ids ? ids[i] : i;
     gym_emit<0>(prm, max_turns, logtab, obs, mask, stats, prm.state + (size_t)game * L.slab_words,
@@ -2566,6 +2568,43 @@ __global__ void grl_gym_encode_kernel(const GrlKParams prm, const long long *__r
       reinterpret_cast<uint8_t *>(actions + (size_t)b * A)[7] |= GRL_ACTION_FLAG_SKIP_ENV;
     if (valid) valid[b] = ok ? 1 : 0;
   }
+}
+
+// grl_gym_autoreset, step 1: the envs whose episode ended, compacted into an id list with their next seeds (device-side count)
+__global__ void grl_gym_compact_kernel(const GrlKParams prm, const uint8_t *__restrict__ terminated,
+                                       const uint8_t *__restrict__ truncated, long long base_seed, long long *__restrict__ episode,
+                                       int32_t *__restrict__ turns, int32_t *__restrict__ calls, int32_t *__restrict__ ids,
+                                       long long *__restrict__ seeds, int *__restrict__ count) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < prm.B; b += gridDim.x * blockDim.x) {
+    if (terminated[b] | truncated[b]) {
+      const int pos = atomicAdd(count, 1);
+      const long long ep = episode[b] + 1;
+      episode[b] = ep;
+      ids[pos] = b;
+      seeds[pos] = base_seed + b + ep * (long long)prm.B;
+      turns[b] = 0;
+      calls[b] = 0;
+    }
+  }
+}
+
+// step 2: player 0's last observation of every finished env, before its row is overwritten (one warp per env)
+__global__ void __launch_bounds__(256) grl_gym_final_obs_kernel(const GrlKParams prm, const float *__restrict__ obs,
+                                                                float *__restrict__ final_obs, const int32_t *__restrict__ ids,
+                                                                const int *__restrict__ count) {
+  const int lane = threadIdx.x & 31, n = *count, block = GRL_GYM_CHANNELS * prm.N;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
+    const int b = ids[i];
+    const float *src = obs + (size_t)b * prm.P * block;
+    float *dst = final_obs + (size_t)b * block;
+    for (int k = lane; k < block; k += 32) dst[k] = src[k];
+  }
+}
+
+// step 3: the staging rows the map generator fills have to start zeroed
+__global__ void grl_zero_rows_kernel(uint32_t *__restrict__ p, int row_words, int capacity, const int *__restrict__ count) {
+  const size_t total = (size_t)min(capacity, *count) * row_words;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) p[k] = 0u;
 }
 
 // A uniformly random valid gym action per env: the k-th set byte of the env's N*5 mask bytes, one warp per env
@@ -2867,12 +2906,13 @@ cudaError_t grl_launch_turn(const GrlKParams &prm, bool do_step, bool do_out, cu
 }
 
 cudaError_t grl_launch_reset(const GrlKParams &prm, const uint32_t *src_state, const uint32_t *src_static,
-                             const int32_t *env_ids, int n, cudaStream_t stream) {
+                             const int32_t *env_ids, int n, cudaStream_t stream, const int *n_dev) {
   int grid = grid_for(GRL_WARPS_PER_CTA, n);
+  if (n_dev && grid > 148 * 16) grid = 148 * 16;  // sized for the capacity: the kernel strides
   switch (player_template(prm.P)) {
-    case 2: grl_reset_kernel<2><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, src_state, src_static, env_ids, n); break;
-    case 4: grl_reset_kernel<4><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, src_state, src_static, env_ids, n); break;
-    default: grl_reset_kernel<8><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, src_state, src_static, env_ids, n); break;
+    case 2: grl_reset_kernel<2><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, src_state, src_static, env_ids, n, n_dev); break;
+    case 4: grl_reset_kernel<4><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, src_state, src_static, env_ids, n, n_dev); break;
+    default: grl_reset_kernel<8><<<grid, GRL_WARPS_PER_CTA * 32, 0, stream>>>(prm, src_state, src_static, env_ids, n, n_dev); break;
   }
   return cudaGetLastError();
 }
@@ -2906,7 +2946,7 @@ cudaError_t grl_launch_visibility(const GrlKParams &prm, uint8_t *visible, uint8
 }
 
 cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *logtab, float *obs, uint8_t *mask, int32_t *stats,
-                           cudaStream_t stream, const int32_t *ids, int n_ids) {
+                           cudaStream_t stream, const int32_t *ids, int n_ids, const int *n_dev) {
   // warp-per-game kernel with linear 128-bit sweeps; GRL_GYM_FLAT=1 keeps the thread-per-tile version for comparison
   static const bool flat = [] { const char *e = getenv("GRL_GYM_FLAT"); return e && e[0] == '1'; }();
   if (!flat || ids) {
@@ -2919,7 +2959,7 @@ cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *lo
     }
     int grid = grid_for(GRL_WARPS_PER_CTA, ids ? n_ids : prm.B);
     if (grid > 148 * 16) grid = 148 * 16;
-    grl_gym_warp_kernel<<<grid, GRL_WARPS_PER_CTA * 32, smem, stream>>>(prm, max_turns, logtab, obs, mask, stats, ids, n_ids);
+    grl_gym_warp_kernel<<<grid, GRL_WARPS_PER_CTA * 32, smem, stream>>>(prm, max_turns, logtab, obs, mask, stats, ids, n_ids, n_dev);
     return cudaGetLastError();
   }
   if (ids) return cudaErrorNotSupported;  // the flat comparison kernel has no id list
@@ -2932,6 +2972,25 @@ cudaError_t grl_launch_gym_encode(const GrlKParams &prm, const long long *action
                                   int skip_invalid, void *actions, uint8_t *valid, cudaStream_t stream) {
   grl_gym_encode_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm, action_idx, player, slot, mask, skip_invalid,
                                                                            (uint2 *)actions, valid);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_gym_compact(const GrlKParams &prm, const uint8_t *terminated, const uint8_t *truncated, long long base_seed,
+                                   long long *episode, int32_t *turns, int32_t *calls, int32_t *ids, long long *seeds, int *count,
+                                   cudaStream_t stream) {
+  grl_gym_compact_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm, terminated, truncated, base_seed, episode, turns, calls,
+                                                                            ids, seeds, count);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_gym_final_obs(const GrlKParams &prm, const float *obs, float *final_obs, const int32_t *ids, const int *count,
+                                     cudaStream_t stream) {
+  grl_gym_final_obs_kernel<<<148 * 4, 256, 0, stream>>>(prm, obs, final_obs, ids, count);
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_zero_rows(uint32_t *p, int row_words, int capacity, const int *count, cudaStream_t stream) {
+  grl_zero_rows_kernel<<<148 * 8, 256, 0, stream>>>(p, row_words, capacity, count);
   return cudaGetLastError();
 }
 

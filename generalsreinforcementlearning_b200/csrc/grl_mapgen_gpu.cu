@@ -1,12 +1,16 @@
-// grl_mapgen_gpu.cu — the reference's procedural maps generated ON THE DEVICE, one thread per map.
+// grl_mapgen_gpu.cu — the reference's procedural maps generated ON THE DEVICE, one warp per map.
 //
 // Host map generation (grl_mapgen.cpp) costs ~3 us of wall time per 20x20 map on 16 cores — most of
 // it Go's math/rand seeding, 1,841 Lehmer steps per seed — which for 65,536 games is as long as
 // stepping the whole 500-turn episode.  The algorithm is embarrassingly parallel over maps and
 // every draw is integer arithmetic, so the same restatement of mapgen/generator.go:25-253 and of
-// go1.24 math/rand runs here with the generator state (607 x uint64) in per-thread local memory.
-// A thread writes its map straight into the staging slabs the reset kernel consumes (ownership
-// bit, uint16 armies, terrain masks), so a seeded reset never touches the host.
+// go1.24 math/rand runs here.  A warp seeds the generator cooperatively (the k-th Lehmer state is
+// 48271^k * x_0, so the 607 state words are independent), keeps the state, the occupancy masks and the
+// army plane of its map in SHARED memory, lets lane 0 make the (inherently sequential) draws, and writes
+// the finished map into the staging slabs the reset kernel consumes with coalesced stores — a seeded
+// reset never touches the host.  (The first version ran one THREAD per map with the state in local memory:
+// every draw waited on two dependent local-memory loads, ≈ 130 us per map however few maps there were —
+// the critical path of a vector env that re-seeds a hundred-odd envs per step.)
 // Bit-identical to the host path by construction; tests compare the two and the oracle.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,32 +28,37 @@ __constant__ int64_t c_cooked[kLen] = {
 #include "go_rng_cooked.inc"
 };
 
+// 48271^k mod (2^31-1): x_k = 48271^k * x_0, so the 1,841 seeding steps become independent multiplications
+__constant__ int32_t c_lpow[1842] = {
+#include "go_rng_lehmer_pow.inc"
+};
+
 struct GoRandDev {  // rng.go (*rngSource) + rand.go
-  uint64_t vec[kLen];
+  uint64_t *vec;  // [kLen], shared memory
   int tap, feed;
 
-  __device__ static int32_t lehmer(int32_t x) {  // 48271 * x mod (2^31 - 1), Schrage
-    const int32_t hi = x / 44488, lo = x % 44488;
-    x = 48271 * lo - 3399 * hi;
-    return x < 0 ? x + kInt32Max : x;
-  }
-  __device__ void seed(int64_t s) {
+  // every lane of the warp calls this; lane l fills words l, l+32, ...
+  __device__ void seed(int64_t s, int lane) {
     tap = 0;
     feed = kLen - kTap;
     s %= kInt32Max;
     if (s < 0) s += kInt32Max;
     if (s == 0) s = 89482311;
-    int32_t x = (int32_t)s;
-    for (int i = -20; i < kLen; ++i) {
-      x = lehmer(x);
-      if (i < 0) continue;
-      uint64_t u = (uint64_t)x << 40;
-      x = lehmer(x);
-      u ^= (uint64_t)x << 20;
-      x = lehmer(x);
-      u ^= (uint64_t)x;
+    // rng.go seedrand runs 20 warm-up steps of x <- 48271 * x mod (2^31-1), then three per state word; the k-th
+    // state is 48271^k * x_0, so word i takes the independent products for k = 21+3i .. 23+3i
+    const uint64_t x0 = (uint64_t)s;
+    for (int i = lane; i < kLen; i += 32) {
+      const int k = 21 + 3 * i;
+      const uint64_t u = ((uint64_t)mulmod31(c_lpow[k], x0) << 40) ^ ((uint64_t)mulmod31(c_lpow[k + 1], x0) << 20) ^
+                         (uint64_t)mulmod31(c_lpow[k + 2], x0);
       vec[i] = u ^ (uint64_t)c_cooked[i];
     }
+  }
+  __device__ static uint32_t mulmod31(int32_t a, uint64_t x) {  // a * x mod (2^31 - 1), both in [1, 2^31 - 2]
+    uint64_t r = (uint64_t)(uint32_t)a * x;
+    r = (r >> 31) + (r & 0x7fffffffULL);
+    r = (r >> 31) + (r & 0x7fffffffULL);
+    return (uint32_t)(r >= 0x7fffffffULL ? r - 0x7fffffffULL : r);
   }
   __device__ uint64_t u64() {
     if (--tap < 0) tap += kLen;
@@ -84,9 +93,9 @@ struct GoRandDev {  // rng.go (*rngSource) + rand.go
   }
 };
 
-struct MapDev {  // occupancy as linear bitmasks (tile t = bit t&31 of word t>>5), N <= 1024
-  uint32_t taken[32];  // anything that is not a neutral normal tile
-  uint32_t *M, *C, *G;  // terrain masks in the staging static slab
+struct MapDev {  // occupancy as linear bitmasks (tile t = bit t&31 of word t>>5), N <= 1024; all in shared memory
+  uint32_t *taken;      // anything that is not a neutral normal tile
+  uint32_t *M, *C, *G;  // terrain masks
   uint16_t *army;
   __device__ bool open(int t) const { return !((taken[t >> 5] >> (t & 31)) & 1u); }
   __device__ void take(int t) { taken[t >> 5] |= 1u << (t & 31); }
@@ -103,23 +112,39 @@ __device__ bool far_enough(int W, int idx, const int *seats, int n, int spacing)
 
 }  // namespace
 
-// staging buffers must be zero-filled; one thread writes map i into slab i / static slab i
-__global__ void __launch_bounds__(128)
+// staging buffers must be zero-filled; one warp writes map i into slab i / static slab i
+constexpr int kMapWarps = 4;  // maps per CTA: 4 x (607 x 8 B state + 512 B masks + 2 KB armies) = 29.6 KB of shared memory
+
+__global__ void __launch_bounds__(kMapWarps * 32)
     grl_mapgen_kernel(GrlLayout L, int W, int H, GrlMapParams mp, const long long *__restrict__ seeds, int n,
-                      uint32_t *__restrict__ slabs, uint32_t *__restrict__ statics, int *__restrict__ failed) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                      uint32_t *__restrict__ slabs, uint32_t *__restrict__ statics, int *__restrict__ failed,
+                      const int *__restrict__ n_dev) {
+  __shared__ uint64_t s_vec[kMapWarps][kLen];
+  __shared__ uint32_t s_mask[kMapWarps][4][32];
+  __shared__ __align__(16) uint16_t s_army[kMapWarps][1024];
+  __shared__ int s_seat[kMapWarps][GRL_MAX_PLAYERS_DEV + 1];  // [players] = 1 when every general found a seat
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kMapWarps + warp;
+  if (n_dev) n = min(n, *n_dev);  // the launch covers the capacity; the number of maps lives on the device
+  if (i >= n) return;             // uniform over the warp
   const int N = W * H, NW = L.NW;
   uint32_t *slab = slabs + (size_t)i * L.slab_words;
   uint32_t *stat = statics + (size_t)i * L.static_words;
-  MapDev b;
-  for (int k = 0; k < 32; ++k) b.taken[k] = 0u;
-  b.M = stat;
-  b.C = stat + NW;
-  b.G = stat + 2 * NW;
-  b.army = reinterpret_cast<uint16_t *>(slab + L.off_army);
+  for (int k = lane; k < 4 * 32; k += 32) (&s_mask[warp][0][0])[k] = 0u;
+  for (int k = lane; k < 512; k += 32) reinterpret_cast<uint32_t *>(s_army[warp])[k] = 0u;
   GoRandDev rng;
-  rng.seed(seeds[i]);
+  rng.vec = s_vec[warp];
+  rng.seed(seeds[i], lane);
+  __syncwarp();
+  if (lane == 0) {
+  MapDev b;
+  b.taken = s_mask[warp][0];
+  b.M = s_mask[warp][1];
+  b.C = s_mask[warp][2];
+  b.G = s_mask[warp][3];
+  b.army = s_army[warp];
+  int *seats = s_seat[warp];
+  seats[mp.players] = 0;
 
   // generator.go:77-142 mountain veins
   for (int vein = 0; vein < mp.veins; ++vein) {
@@ -182,8 +207,8 @@ __global__ void __launch_bounds__(128)
     }
   }
   // generator.go:166-253 generals
-  int seats[GRL_MAX_PLAYERS_DEV];
-  for (int pid = 0; pid < mp.players; ++pid) {
+  bool ok = true;
+  for (int pid = 0; pid < mp.players && ok; ++pid) {
     int chosen = -1;
     for (int attempt = 0; attempt < N && chosen < 0; ++attempt) {
       const int x = rng.intn(W);
@@ -195,18 +220,36 @@ __global__ void __launch_bounds__(128)
       if (b.open(t) && far_enough(W, t, seats, pid, mp.spacing)) chosen = t;
     if (chosen < 0) {
       atomicExch(failed, i + 1);
-      return;
+      ok = false;
+      break;
     }
     b.take(chosen);
     b.G[chosen >> 5] |= 1u << (chosen & 31);
     b.army[chosen] = 2;
-    slab[L.off_own + pid * NW + (chosen >> 5)] |= 1u << (chosen & 31);
     seats[pid] = chosen;
+  }
+  seats[mp.players] = ok ? 1 : 0;
+  }  // lane 0
+  __syncwarp();
+
+  // ---- the finished map leaves shared memory with coalesced stores ---------------------------------------------
+  if (!s_seat[warp][mp.players]) return;
+  if (lane < NW) {
+    stat[lane] = s_mask[warp][1][lane];
+    stat[NW + lane] = s_mask[warp][2][lane];
+    stat[2 * NW + lane] = s_mask[warp][3][lane];
+  }
+  uint32_t *garmy = slab + L.off_army;
+  const uint32_t *sarmy = reinterpret_cast<const uint32_t *>(s_army[warp]);
+  for (int k = lane; k < L.NA / 2; k += 32) garmy[k] = sarmy[k];
+  if (lane < mp.players) {
+    const int t = s_seat[warp][lane];
+    slab[L.off_own + lane * NW + (t >> 5)] = 1u << (t & 31);  // the staging slab is zero-filled: one general per player
   }
 }
 
 cudaError_t grl_launch_mapgen(const GrlLayout &L, int W, int H, const GrlMapParams &mp, const long long *seeds, int n,
-                              uint32_t *slabs, uint32_t *statics, int *failed, cudaStream_t stream) {
-  grl_mapgen_kernel<<<(n + 127) / 128, 128, 0, stream>>>(L, W, H, mp, seeds, n, slabs, statics, failed);
+                              uint32_t *slabs, uint32_t *statics, int *failed, cudaStream_t stream, const int *n_dev) {
+  grl_mapgen_kernel<<<(n + kMapWarps - 1) / kMapWarps, kMapWarps * 32, 0, stream>>>(L, W, H, mp, seeds, n, slabs, statics, failed, n_dev);
   return cudaGetLastError();
 }

@@ -17,7 +17,7 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 
 from . import _abi
-from ._abi import ACTION_DTYPE, BoundLibrary, Config, GymOutputs, GymStepIO, StatePlanes, StepOutputs
+from ._abi import ACTION_DTYPE, BoundLibrary, Config, GymAutoresetIO, GymOutputs, GymStepIO, StatePlanes, StepOutputs
 
 
 def _ptr(buf) -> Optional[int]:
@@ -177,6 +177,17 @@ class BatchedEngine:
         o.obs, o.mask, o.stats = _ptr(obs), _ptr(mask), _ptr(stats)
         self.lib.check(self.lib.gym_observe_envs(self._h, int(max_turns), ids.ctypes.data, len(ids), C.byref(o)),
                        "gym_observe_envs")
+
+    def gym_autoreset(self, max_turns: int, base_seed: int, **planes) -> None:
+        """Re-seed every env whose episode ended in the last gym_step, on the device (grl_gym_autoreset).  Keyword
+        planes: terminated, truncated, episode, turns, calls, obs, mask, stats, final_obs, n_reset."""
+        io = GymAutoresetIO()
+        for k, v in planes.items():
+            if k in ("obs", "mask", "stats"):
+                setattr(io.out, k, _ptr(v))
+            else:
+                setattr(io, k, _ptr(v))
+        self.lib.check(self.lib.gym_autoreset(self._h, int(max_turns), int(base_seed), C.byref(io)), "gym_autoreset")
 
     def gym_sample(self, seed: int, mask, player: int, action) -> None:
         """A uniformly random valid Discrete(N*5) action per env from the gym mask plane (int64 [B])."""

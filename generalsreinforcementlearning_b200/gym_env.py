@@ -53,7 +53,7 @@ class GeneralsVecEnv:
 
     def __init__(self, num_envs: int, board_width: int = 15, board_height: int = 15, max_players: int = 2,
                  fog_of_war: bool = True, max_turns: int = 500, device: int = 0, seed: int = 12345,
-                 self_play: bool = False, lib=None, host_threads: int = 0):
+                 self_play: bool = False, lib=None, host_threads: int = 0, auto_reset: str = "host"):
         import torch
 
         if max_players != 2:
@@ -66,6 +66,14 @@ class GeneralsVecEnv:
         self.num_envs, self.W, self.H, self.P = num_envs, board_width, board_height, max_players
         self.board_size = self.N = board_width * board_height
         self.max_turns, self.self_play = max_turns, self_play
+        # "host": the step reads one 4-byte flag and re-seeds finished envs from the host (compact
+        # info["final_observation"] / ["final_env_ids"]).  "device": grl_gym_autoreset re-seeds them on the device with
+        # NO host read — step() never synchronises, so a training loop can enqueue steps ahead; info["final_observation"]
+        # is then a dense [B, 9, H, W] plane whose rows are valid where info["final_env_mask"] is set, and info["turn"]
+        # already shows 0 for the re-seeded envs.
+        if auto_reset not in ("host", "device"):
+            raise ValueError("auto_reset is 'host' or 'device'")
+        self.auto_reset = auto_reset
         self.engine = BatchedEngine(lib, make_config(lib, num_envs=num_envs, width=board_width, height=board_height,
                                                      num_players=max_players, device=device, max_actions=max_players,
                                                      fog_of_war=1 if fog_of_war else 0, host_threads=host_threads))
@@ -96,6 +104,9 @@ class GeneralsVecEnv:
         self._flip = 0
         self._nfin = torch.zeros(1, dtype=torch.int32, device=dev)
         self._opp_draws = 0
+        if auto_reset == "device":
+            self._episode_dev = torch.zeros(B, dtype=torch.int64, device=dev)
+            self._final_obs = torch.zeros((B, 9, self.H, self.W), dtype=torch.float32, device=dev)
         self._sample_draws = 0
         self._sampled = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
         self._calls = torch.zeros(B, dtype=torch.int32, device=dev)   # step() calls this episode (incl. rejected actions)
@@ -120,6 +131,8 @@ class GeneralsVecEnv:
             self._base_seed = int(seed)
             self._gen.manual_seed(int(seed))
         self._episode[:] = 0
+        if self.auto_reset == "device":
+            self._episode_dev.zero_()
         ids = np.arange(self.num_envs)
         self.engine.reset_seeded(self._seeds(ids))
         self._turns.zero_()
@@ -154,7 +167,13 @@ class GeneralsVecEnv:
         # info tensors are the env's own planes: valid until the next step() (turn, mask) or the one after (the rest)
         info: Dict[str, Any] = {"invalid_action": ~o["valid"], "winner": o["winner"], "step_error": o["step_error"]}
         turn = self._turns
-        if int(self._nfin.item()) > 0:   # the one host read of the step: does any env start a new episode?
+        if self.auto_reset == "device":
+            info["final_env_mask"] = terminated | truncated
+            self.engine.gym_autoreset(self.max_turns, self._base_seed, terminated=terminated, truncated=truncated,
+                                      episode=self._episode_dev, turns=self._turns, calls=self._calls, obs=self._obs,
+                                      mask=self._mask, stats=self._stats, final_obs=self._final_obs)
+            info["final_observation"] = self._final_obs
+        elif int(self._nfin.item()) > 0:   # the one host read of the step: does any env start a new episode?
             finished = terminated | truncated
             ids = finished.nonzero(as_tuple=True)[0]
             info["final_observation"] = self._obs[ids, 0].clone()

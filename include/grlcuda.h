@@ -282,6 +282,23 @@ typedef struct grl_gym_step_io {
 } grl_gym_step_io;
 int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const grl_gym_step_io *io);
 
+/* The auto-reset of a vector env, without a host round trip: every env whose episode ended in the last grl_gym_step
+ * (terminated | truncated) is re-seeded — episode[b] += 1, seed = base_seed + b + episode[b] * num_envs, the reference's map
+ * generator and turn-0 set-up (engine_initializer.go:34-87,218-225) — its turn/call counters are zeroed, player 0's last
+ * observation is kept in final_obs[b] (what Gymnasium vector envs hand out as "final_observation"), and the gym read-outs of
+ * the new games replace the finished ones' rows.  Nothing is read back: a training loop can enqueue step after step.
+ * libgrlcuda.so requires device pointers for every plane (one compaction + map generation + set-up + read-out launch
+ * sequence on the env's stream, sized by a device-side count); the oracle takes host pointers. */
+typedef struct grl_gym_autoreset_io {
+  const uint8_t *terminated, *truncated; /* [B] in: the flags of the last grl_gym_step                       */
+  int64_t *episode;                      /* [B] in/out: episodes finished so far per env                     */
+  int32_t *turns, *calls;                /* [B] in/out: zeroed for the re-seeded envs                        */
+  grl_gym_outputs out;                   /* in/out: rows of the re-seeded envs are rewritten                 */
+  float *final_obs;                      /* [B][9][H][W] out (may be NULL): player 0's view as the episode ended */
+  int32_t *n_reset;                      /* [1] out (may be NULL): number of envs re-seeded                  */
+} grl_gym_autoreset_io;
+int grl_gym_autoreset(grl_env *env, int32_t max_turns, int64_t base_seed, const grl_gym_autoreset_io *io);
+
 /* Draw the synthetic policy's actions for the current state into `actions`
  * ([B][max_actions], slot p = player p's move, empty when it has none). */
 int grl_sample_actions(grl_env *env, uint64_t policy_seed, grl_action *actions);

@@ -1608,6 +1608,32 @@ int grlo_gym_observe_envs(grlo_env *e, int32_t max_turns, const int32_t *env_ids
   return GRL_OK;
 }
 
+/* the auto-reset of a vector env (grlcuda.h): re-seed every env whose episode ended, keep player 0's last view */
+int grlo_gym_autoreset(grlo_env *e, int32_t max_turns, int64_t base_seed, const grl_gym_autoreset_io *io) {
+  if (!e || !io || max_turns < 1 || !io->terminated || !io->truncated || !io->episode || !io->turns || !io->calls)
+    return GRL_ERR_INVALID_ARG;
+  if (io->final_obs && !io->out.obs) return GRL_ERR_INVALID_ARG;
+  int B = e->cfg.num_envs, P = e->cfg.num_players, N = e->N, n = 0;
+  gym_ctx_t x = {e, max_turns, &io->out};
+  for (int b = 0; b < B; b++) {
+    if (!(io->terminated[b] | io->truncated[b])) continue;
+    io->episode[b] += 1;
+    int64_t seed = base_seed + b + io->episode[b] * (int64_t)B;
+    if (io->final_obs)
+      memcpy(io->final_obs + (size_t)b * GRL_GYM_CHANNELS * N, io->out.obs + (size_t)b * P * GRL_GYM_CHANNELS * N,
+             sizeof(float) * GRL_GYM_CHANNELS * (size_t)N);
+    int32_t id = b;
+    int st = grlo_reset_seeded(e, &id, 1, &seed);
+    if (st) return st;
+    io->turns[b] = 0;
+    io->calls[b] = 0;
+    gym_range(&x, b, b + 1);
+    n++;
+  }
+  if (io->n_reset) *io->n_reset = n;
+  return GRL_OK;
+}
+
 int grlo_get_state(grlo_env *e, int32_t first, int32_t count, const grl_state_planes *o) {
   if (!e || !o || first < 0 || count < 0 || first + count > e->cfg.num_envs) return GRL_ERR_INVALID_ARG;
   int N = e->N, P = e->cfg.num_players;

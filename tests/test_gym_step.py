@@ -242,3 +242,66 @@ def test_cuda_gym_sample_matches_oracle(cuda_lib, oracle_lib, W, H, P, B):
     assert np.array_equal(mg, mo)
     for x, y in zip(g, o):
         assert np.array_equal(x, y)
+
+
+def _drive_pair(a, b, steps, compare_final=True):
+    """Two vector envs stepped with the same actions; every returned tensor compared each step."""
+    import torch
+
+    oa, _ = a.reset()
+    ob, _ = b.reset()
+    resets = 0
+    for t in range(steps):
+        assert torch.equal(oa.cpu(), ob.cpu()), f"observation, step {t}"
+        act = a.sample_actions().cpu()
+        assert torch.equal(act, b.sample_actions().cpu()), f"sampled actions, step {t}"
+        if t % 5 == 2:
+            act = act.clone()
+            act[::7] = 0
+        ra, rb = a.step(act.to(a.device)), b.step(act.to(b.device))
+        oa, ob = ra[0], rb[0]
+        for k, name in ((1, "reward"), (2, "terminated"), (3, "truncated")):
+            assert torch.equal(ra[k].cpu(), rb[k].cpu()), f"{name}, step {t}"
+        assert torch.equal(ra[4]["valid_actions_mask"].cpu(), rb[4]["valid_actions_mask"].cpu()), f"mask, step {t}"
+        assert torch.equal(a._turns.cpu(), b._turns.cpu()) and torch.equal(a._calls.cpu(), b._calls.cpu()), f"counters, step {t}"
+        fin = (ra[2] | ra[3]).cpu()
+        resets += int(fin.sum())
+        if compare_final and fin.any():
+            fa = ra[4]["final_observation"].cpu()
+            fb = rb[4]["final_observation"].cpu()
+            fa = fa[fin] if fa.shape[0] == fin.shape[0] else fa
+            fb = fb[fin] if fb.shape[0] == fin.shape[0] else fb
+            assert torch.equal(fa, fb), f"final observation, step {t}"
+    return resets
+
+
+def test_vector_env_device_autoreset_equals_host_autoreset(oracle_lib):
+    """auto_reset='device' (grl_gym_autoreset: no host read, dense final_observation) re-seeds the same envs with the
+    same seeds as the host path and hands out the same tensors."""
+    from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
+
+    a = GeneralsVecEnv(40, 8, 8, max_turns=9, seed=5, lib=oracle_lib, host_threads=1, auto_reset="host")
+    b = GeneralsVecEnv(40, 8, 8, max_turns=9, seed=5, lib=oracle_lib, host_threads=1, auto_reset="device")
+    assert _drive_pair(a, b, 40) >= 120
+    a.close()
+    b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,B,max_turns", [(15, 300, 7), (20, 96, 9), (10, 1000, 6)])
+def test_cuda_device_autoreset_matches_oracle(cuda_lib, oracle_lib, W, B, max_turns):
+    """The device-side auto-reset (compaction, map generation, turn-0 set-up and read-outs sized by a device-side count)
+    against the oracle's, through several generations of episodes."""
+    from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
+
+    g = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=31, lib=cuda_lib, auto_reset="device")
+    o = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=31, lib=oracle_lib, host_threads=1, auto_reset="device")
+    assert _drive_pair(g, o, 4 * max_turns + 3) >= 3 * B
+    import numpy as np
+    assert np.array_equal(g.engine.state_hash(), o.engine.state_hash())
+    # and the device path equals the CUDA host path
+    h = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=31, lib=cuda_lib, auto_reset="host")
+    g2 = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=31, lib=cuda_lib, auto_reset="device")
+    _drive_pair(g2, h, 2 * max_turns + 2)
+    for e in (g, o, h, g2):
+        e.close()

@@ -199,3 +199,22 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def lehmer_pow_table(path):
+    """48271^k mod (2^31-1), k = 0..1841: the device map generator seeds Go's generator with independent
+    multiplications x_k = 48271^k * x_0 instead of 1,841 dependent Lehmer steps (grl_mapgen_gpu.cu)."""
+    p, a, vals = 2 ** 31 - 1, 48271, [1]
+    for _ in range(1841):
+        vals.append(vals[-1] * a % p)
+    with open(path, "w") as f:
+        f.write("// 48271^k mod (2^31 - 1) for k = 0..1841: jump-ahead table of the Lehmer generator Go's math/rand seeds with\n"
+                "// (rng.go seedrand); generated by tools/gen_rngcooked.py --lehmer-pow\n")
+        for i in range(0, len(vals), 8):
+            f.write(", ".join(str(v) for v in vals[i:i + 8]) + ",\n")
+
+
+if __name__ == "__main__" and "--lehmer-pow" in __import__("sys").argv:
+    import os
+    lehmer_pow_table(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "generalsreinforcementlearning_b200", "csrc",
+                                  "go_rng_lehmer_pow.inc"))

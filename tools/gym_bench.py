@@ -58,6 +58,20 @@ def main():
                     "steady_resets_per_step": round(resets / steps, 1)})
         out.append(rec)
         env.close()
+        # the same steady state with the device-side auto-reset: no host read in step(), one sync at the end
+        env = GeneralsVecEnv(B, W, W, max_turns=500, seed=3, auto_reset="device")
+        env.reset()
+        env._calls.copy_(torch.randint(0, env.max_turns, (B,), device=env._calls.device, dtype=torch.int32))
+        for _ in range(5):
+            env.step(env.sample_actions())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            env.step(env.sample_actions())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        rec.update({"device_reset_ms_per_vector_step": round(1e3 * dt / steps, 3), "device_reset_env_steps_per_s": round(B * steps / dt)})
+        env.close()
     print(json.dumps(out))
 
 
