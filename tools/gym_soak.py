@@ -21,9 +21,9 @@ from generalsreinforcementlearning_b200._abi import BoundLibrary
 from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
 
 
-def soak(cuda, oracle, W, B, max_turns, steps):
-    g = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=777, lib=cuda)
-    o = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=777, lib=oracle, host_threads=0)
+def soak(cuda, oracle, W, B, max_turns, steps, mode="host"):
+    g = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=777, lib=cuda, auto_reset=mode)
+    o = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=777, lib=oracle, host_threads=0, auto_reset=mode)
     og, _ = g.reset()
     oo, _ = o.reset()
     t0 = time.time()
@@ -55,11 +55,14 @@ def soak(cuda, oracle, W, B, max_turns, steps):
                 assert np.array_equal(g.engine.buffer_hash(mg, words, B * 2), o.engine.buffer_hash(o._mask.view(torch.uint8).numpy(), words, B * 2)), f"{ctx}: mask"
             else:
                 assert torch.equal(mg[:4096].cpu(), o._mask.view(torch.uint8)[:4096]), f"{ctx}: mask"
+        if mode == "device" and t % 20 == 19:
+            assert np.array_equal(g.engine.buffer_hash(g._final_obs, 9 * N, B), o.engine.buffer_hash(o._final_obs.numpy(), 9 * N, B)), f"{ctx}: final obs"
+            assert torch.equal(g._episode_dev.cpu(), o._episode_dev), f"{ctx}: episode counters"
         finished += int((ro[2] | ro[3]).sum())
         rejected += int(ro[4]["invalid_action"].sum())
     g.close()
     o.close()
-    return dict(board=[W, W], envs=B, max_turns=max_turns, steps=steps, env_steps_compared=B * steps, episodes_finished=finished,
+    return dict(board=[W, W], envs=B, max_turns=max_turns, steps=steps, auto_reset=mode, env_steps_compared=B * steps, episodes_finished=finished,
                 rejected_actions=rejected, mismatches=0, seconds=round(time.time() - t0, 1))
 
 
@@ -68,8 +71,9 @@ def main():
     oracle = BoundLibrary(os.path.join(ROOT, "oracle", "libgrloracle.so"), "grlo_")
     args = [int(v) for v in sys.argv[1:]]
     configs = [tuple(args[i:i + 4]) for i in range(0, len(args), 4)] or [(15, 65536, 120, 300), (20, 32768, 90, 200), (10, 65536, 60, 200)]
+    mode = os.environ.get("GRL_SOAK_RESET", "host")
     for cfg in configs:
-        print(json.dumps(soak(cuda, oracle, *cfg)), flush=True)
+        print(json.dumps(soak(cuda, oracle, *cfg, mode=mode)), flush=True)
 
 
 if __name__ == "__main__":
