@@ -2608,33 +2608,65 @@ __global__ void grl_zero_rows_kernel(uint32_t *__restrict__ p, int row_words, in
 }
 
 // A uniformly random valid gym action per env: the k-th set byte of the env's N*5 mask bytes, one warp per env
-// (32 bytes per ballot; the draw is policy_draw(seed, global env, 0, player) mod the number of set bytes).
+// (the draw is policy_draw(seed, global env, 0, player) mod the number of set bytes).  One pass over the bytes —
+// 32 per ballot, eight independent loads in flight per lane — parks the ballot words in shared memory; the k-th set
+// bit is then found there.  (Reading the bytes twice with one dependent load per ballot took 90 us per 65,536 envs.)
 __global__ void __launch_bounds__(256) grl_gym_sample_kernel(const GrlKParams prm, unsigned long long seed,
                                                              const uint8_t *__restrict__ mask, int player,
                                                              long long *__restrict__ action) {
-  const int lane = threadIdx.x & 31;
-  const int M = prm.N * 5;
+  __shared__ uint32_t s_w[8][GRL_MAX_DIM * GRL_MAX_DIM * 5 / 32];  // 160 ballot words per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int M = prm.N * 5, words = (M + 31) / 32;
+  uint32_t *sw = s_w[warp];
   for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < prm.B; b += (gridDim.x * blockDim.x) >> 5) {
     const uint8_t *row = mask + ((size_t)b * prm.P + player) * M;
     int total = 0;
-    for (int i = 0; i < M; i += 32) total += __popc(__ballot_sync(FULL, i + lane < M && row[i + lane] != 0));
+    for (int it0 = 0; it0 < words; it0 += 8) {
+      uint8_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = 32 * (it0 + u) + lane;
+        v[u] = i < M ? row[i] : (uint8_t)0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint32_t w = __ballot_sync(FULL, v[u] != 0);
+        if (it0 + u < words && lane == 0) sw[it0 + u] = w;
+        total += __popc(w);
+      }
+    }
+    __syncwarp();
     long long pick = 0;
     if (total > 0) {
       const uint64_t r = policy_draw(seed, (uint64_t)(prm.env_id_base + b), 0ull, (uint64_t)player);
       int k = (int)(r % (uint64_t)total);
-      for (int i = 0; i < M; i += 32) {
-        const uint32_t w = __ballot_sync(FULL, i + lane < M && row[i + lane] != 0);
+      // lane j counts words j, j+32, ...: the word holding the k-th set bit comes from a warp-wide prefix sum per stripe
+      for (int base = 0; base < words; base += 32) {
+        const uint32_t w = base + lane < words ? sw[base + lane] : 0u;
         const int c = __popc(w);
-        if (k < c) {
-          uint32_t v = w;
-          for (int j = 0; j < k; j++) v &= v - 1u;  // drop the k lowest set bits
-          pick = i + __ffs(v) - 1;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int stripe = __shfl_sync(FULL, incl, 31);
+        if (k < stripe) {
+          const bool mine = k >= incl - c && k < incl;
+          const uint32_t who = __ballot_sync(FULL, mine);
+          const int src = __ffs(who) - 1;
+          const uint32_t ww = __shfl_sync(FULL, w, src);
+          int kk = k - (__shfl_sync(FULL, incl, src) - __popc(ww));
+          uint32_t v = ww;
+          for (int j = 0; j < kk; j++) v &= v - 1u;  // drop the kk lowest set bits
+          pick = 32 * (base + src) + __ffs(v) - 1;
           break;
         }
-        k -= c;
+        k -= stripe;
       }
     }
     if (lane == 0) action[b] = pick;
+    __syncwarp();
   }
 }
 
