@@ -17,6 +17,8 @@ itself and its inputs (that step's actions) are already resident where the arm r
            step's actions copied host->device from pinned memory, reward/done/winner/error
            planes copied device->host (observations and masks stay in HBM for an on-GPU learner).
 `e2e_host_obs`: additionally copies every observation tensor and mask to the host (PCIe-bound).
+`gym_env` (N=1 only, informational): the generals_gym contract through GeneralsVecEnv at 65,536 envs of 15x15 — one
+grl_gym_step launch per step, the random agent, the device-side auto-reset — timed with CUDA events.
 """
 from __future__ import annotations
 
@@ -212,6 +214,40 @@ def run_reference(args):
     return 0
 
 
+def gym_contract_rate(envs=65536, board=15, steps=60):
+    """Extra, informational: the generals_gym contract through GeneralsVecEnv at the reference's default
+    board (15x15) — one grl_gym_step launch per step, the reference's random agent (grl_gym_sample) as the policy, episode
+    ends spread over time so that every step re-seeds envs on the device (grl_gym_autoreset).  Timed with CUDA events on
+    torch's stream (the env's stream); never allowed to break the headline line."""
+    try:
+        import torch
+
+        from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
+
+        env = GeneralsVecEnv(envs, board, board, max_turns=500, seed=12345, auto_reset="device")
+        env.reset()
+        env._calls.copy_(torch.randint(0, env.max_turns, (envs,), device=env._calls.device, dtype=torch.int32))
+        for _ in range(5):
+            env.step(env.sample_actions())
+        torch.cuda.synchronize()
+        l0 = env.engine.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            env.step(env.sample_actions())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = (env.engine.launch_count() - l0) / steps
+        env.close()
+        return {"value": envs / (ms * 1e-3), "unit": "env-steps/s", "envs": envs, "board": [board, board], "ms_per_vector_step": ms,
+                "launches_per_step": launches,
+                "what": "GeneralsVecEnv.step (one grl_gym_step launch) + random agent (grl_gym_sample) + device-side auto-reset of "
+                        "the ~130 envs whose episode ends each step (grl_gym_autoreset); reference gym path: 12 steps/s per env"}
+    except Exception as exc:  # noqa: BLE001 - informational figure only
+        return {"unavailable": repr(exc)[:200]}
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -402,6 +438,10 @@ def run_cuda(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if world == 1 and not args.no_cpu_baseline:
+        gym = gym_contract_rate()
+        if gym:
+            line["gym_env"] = gym
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
