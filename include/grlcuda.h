@@ -288,7 +288,10 @@ int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const 
  * observation is kept in final_obs[b] (what Gymnasium vector envs hand out as "final_observation"), and the gym read-outs of
  * the new games replace the finished ones' rows.  Nothing is read back: a training loop can enqueue step after step.
  * libgrlcuda.so requires device pointers for every plane (one compaction + map generation + set-up + read-out launch
- * sequence on the env's stream, sized by a device-side count); the oracle takes host pointers. */
+ * sequence on the env's stream, sized by a device-side count); the oracle takes host pointers.  A seed whose map cannot
+ * seat every general (mapgen/generator.go:252 — only on boards too small for the general spacing) is reported by
+ * grl_reset_seeded as GRL_ERR_MAPGEN; this asynchronous path leaves such an env without generals, i.e. finished, and it is
+ * re-seeded again on the next call. */
 typedef struct grl_gym_autoreset_io {
   const uint8_t *terminated, *truncated; /* [B] in: the flags of the last grl_gym_step                       */
   int64_t *episode;                      /* [B] in/out: episodes finished so far per env                     */
