@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../generalsreinforcementlearning_b200/host/grl_engine.hpp"
+#include "../../generalsreinforcementlearning_b200/host/grl_experience.hpp"
 
 using namespace grl;
 using core::MoveAction;
@@ -579,6 +580,123 @@ TEST(TestExperienceCollection) {
   // territory +1 (0.01) + army: general 4 -> 1 stays +1 production, 3 move to a neutral tile ...: just sign
   EXPECT(t->Reward > 0.f, "capturing a neutral tile is rewarded, got %g", double(t->Reward));
   EXPECT_EQ(0, rec.ends, "OnGameEnd only when the game ends");
+}
+
+// ---- internal/experience/buffer_test.go ------------------------------------------------------------------
+static experience::Experience createTestExperience(const std::string &id, int32_t turn) {  // buffer_test.go:16-34
+  experience::Experience e;
+  e.ExperienceId = id;
+  e.GameId = "test-game";
+  e.Turn = turn;
+  e.State.Shape = {9, 10, 10};
+  e.State.Data.assign(900, 0.f);
+  e.NextState = e.State;
+  e.Action = 42;
+  e.Reward = 1.0f;
+  return e;
+}
+
+TEST(TestBuffer_Creation) {  // buffer_test.go:36-44
+  experience::Buffer buffer(100);
+  EXPECT_EQ(100, buffer.Capacity(), "capacity");
+  EXPECT_EQ(0, buffer.Size(), "size");
+  EXPECT(!buffer.IsFull(), "not full");
+  EXPECT_EQ(10000, experience::Buffer(0).Capacity(), "default capacity (buffer.go:44-46)");
+}
+
+TEST(TestBuffer_AddAndGet) {  // buffer_test.go:46-68
+  experience::Buffer buffer(10);
+  for (int i = 0; i < 5; i++) EXPECT(!buffer.Add(createTestExperience(std::string(1, char('a' + i)), i)), "Add");
+  EXPECT_EQ(5, buffer.Size(), "size");
+  auto got = buffer.Get(3);
+  EXPECT_EQ(size_t(3), got.size(), "len");
+  EXPECT_EQ(2, buffer.Size(), "size after Get");
+  EXPECT(got[0].ExperienceId == "a" && got[1].ExperienceId == "b" && got[2].ExperienceId == "c", "FIFO order");
+}
+
+TEST(TestBuffer_CircularBehavior) {  // buffer_test.go:70-97
+  experience::Buffer buffer(3);
+  for (int i = 0; i < 5; i++) EXPECT(!buffer.Add(createTestExperience(std::string(1, char('a' + i)), i)), "Add");
+  EXPECT_EQ(3, buffer.Size(), "only the last 3");
+  EXPECT(buffer.IsFull(), "full");
+  experience::BufferStats stats = buffer.Stats();
+  EXPECT_EQ(int64_t(5), stats.TotalAdded, "TotalAdded");
+  EXPECT_EQ(int64_t(2), stats.TotalDropped, "TotalDropped");
+  auto all = buffer.GetAll();
+  EXPECT_EQ(size_t(3), all.size(), "len");
+  EXPECT(all[0].ExperienceId == "c" && all[1].ExperienceId == "d" && all[2].ExperienceId == "e", "a and b were dropped");
+}
+
+TEST(TestBuffer_AddBatch_Sample_Clear_Close) {  // buffer_test.go:99-157, 234-252
+  experience::Buffer buffer(10);
+  std::vector<experience::Experience> batch;
+  for (int i = 0; i < 7; i++) batch.push_back(createTestExperience(std::string(1, char('a' + i)), i));
+  EXPECT(!buffer.AddBatch(batch), "AddBatch");
+  EXPECT_EQ(7, buffer.Size(), "size");
+  EXPECT_EQ(size_t(3), buffer.Sample(3).size(), "sample fewer than available");
+  EXPECT_EQ(7, buffer.Size(), "sampling does not remove");
+  EXPECT_EQ(size_t(7), buffer.Sample(10).size(), "sample more than available");
+  auto latest = buffer.GetLatest(2);
+  EXPECT(latest.size() == 2 && latest[0].ExperienceId == "f" && latest[1].ExperienceId == "g", "GetLatest");
+  buffer.Clear();
+  EXPECT_EQ(0, buffer.Size(), "cleared");
+  EXPECT(!buffer.Add(createTestExperience("new", 0)), "can add after clear");
+  EXPECT(!buffer.Close(), "Close");
+  EXPECT(errors::Is(buffer.Add(createTestExperience("x", 0)), experience::ErrBufferClosed), "Add on a closed buffer");
+  EXPECT(errors::Is(buffer.Close(), experience::ErrBufferClosed), "double close");
+}
+
+// ---- internal/experience/collector_test.go: through a real engine, tensors from the device ----------------
+TEST(TestSimpleCollector) {
+  experience::SimpleCollector collector(100, "test-game-123");  // collector_test.go:12-20
+  EXPECT_EQ(100, collector.GetBuffer().Capacity(), "capacity");
+  EXPECT(collector.GameID() == "test-game-123", "game id");
+  EXPECT_EQ(0, collector.GetExperienceCount(), "empty");
+
+  auto engine = newEngine(5, 5, 2, &collector);
+  REQUIRE(engine != nullptr, "nil engine");
+  collector.Attach(engine.get());
+  for (int i = 0; i < 2; i++) REQUIRE(!engine->Step(context::Background(), {}), "idle step");
+  EXPECT_EQ(0, collector.GetExperienceCount(), "no record for a turn without actions (collector.go:33)");
+  // collector_test.go:60-95 TestSimpleCollector_MultipleActions: both players move, one record each
+  std::vector<core::Action> acts;
+  const int dxs[4] = {0, 1, 0, -1}, dys[4] = {-1, 0, 1, 0};
+  for (int p = 0; p < 2; p++) {
+    game::GameState gs = engine->GameState();
+    int g = gs.Players[p].GeneralIdx;
+    std::vector<bool> mask = engine->GetLegalActionMask(p);
+    for (int d = 0; d < 4; d++)
+      if (mask[g * 4 + d]) {
+        MoveAction m = mv(g % 5, g / 5, g % 5 + dxs[d], g / 5 + dys[d], true);
+        m.PlayerID = p;
+        acts.push_back(m);
+        break;
+      }
+  }
+  REQUIRE(acts.size() == 2, "both generals can move");
+  REQUIRE(!engine->Step(context::Background(), acts), "move step");
+  EXPECT_EQ(2, collector.GetExperienceCount(), "one experience per acting player");
+  auto exps = collector.GetExperiences();
+  REQUIRE(exps.size() == 2, "len");
+  for (const experience::Experience &exp : exps) {  // collector_test.go:22-58
+    EXPECT(exp.GameId == "test-game-123", "GameId");
+    EXPECT(exp.PlayerId == 0 || exp.PlayerId == 1, "PlayerId");
+    EXPECT_EQ(3, exp.Turn, "Turn = currState.Turn");
+    EXPECT(exp.State.Shape == (std::vector<int32_t>{9, 5, 5}) && exp.State.Data.size() == 225, "State tensor");
+    EXPECT(exp.NextState.Shape == (std::vector<int32_t>{9, 5, 5}) && exp.NextState.Data.size() == 225, "NextState tensor");
+    EXPECT_EQ(size_t(100), exp.ActionMask.size(), "ActionMask");
+    EXPECT(exp.Action >= 0 && exp.Action < 100 && exp.ActionMask[exp.Action], "the action taken is legal in the mask of the previous state");
+    EXPECT(!exp.Done, "not done");
+    EXPECT(exp.ExperienceId.size() == 36, "an id");
+    EXPECT(exp.Metadata.at("collector_version") == "1.0.0", "metadata");
+    // channel 7 (visible) of the previous state marks the acting general's 3x3 neighbourhood
+    float seen = 0;
+    for (int i = 0; i < 25; i++) seen += exp.State.Data[7 * 25 + i];
+    EXPECT(seen >= 4.f, "visible channel populated");
+  }
+  EXPECT(exps[0].PlayerId != exps[1].PlayerId, "one per player");
+  EXPECT(exps[0].ExperienceId != exps[1].ExperienceId, "unique ids");
+  EXPECT_EQ(0, collector.GetExperienceCount(), "GetExperiences drains the buffer");
 }
 
 // ---- the pool: many games, one launch per turn --------------------------------------------------------

@@ -1,7 +1,7 @@
 """The C++ host mirror of the reference's `internal/game` surface (generalsreinforcementlearning_b200/host).
 
 tests/cpp/host_test.cpp transliterates the reference's Go tests for the turn path (engine_test.go,
-action_mask_test.go, core/action_test.go, core/movement_test.go) against `grl::game::Engine`.  Without a GPU
+action_mask_test.go, core/action_test.go, core/movement_test.go, experience/buffer_test.go, experience/collector_test.go) against `grl::game::Engine`.  Without a GPU
 the binary binds the CPU oracle's copy of the C ABI, which checks the host layer's own logic (action packing,
 error synthesis, plane slicing, the turn barrier, the renderer); on the GPU box it binds libgrlcuda.so — the
 product path."""
