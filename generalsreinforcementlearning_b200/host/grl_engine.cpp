@@ -105,7 +105,106 @@ std::shared_ptr<Library> Library::Default() {
   throw std::runtime_error("grl: libgrlcuda.so not found (set GRLCUDA_LIB); tried:" + why);
 }
 
+// ---- math/rand ------------------------------------------------------------------------------
+namespace rand {
+namespace {
+constexpr int kLen = 607, kTap = 273;
+constexpr int64_t kInt32Max = 2147483647;
+const int64_t kCooked[kLen] = {
+#include "../csrc/go_rng_cooked.inc"
+};
+int32_t seedrand(int32_t x) {  // rng.go: x = 48271 * x mod (2^31 - 1), Schrage
+  const int32_t hi = x / 44488, lo = x % 44488;
+  x = 48271 * lo - 3399 * hi;
+  return x < 0 ? x + int32_t(kInt32Max) : x;
+}
+}  // namespace
+
+void Rand::Seed(int64_t s) {
+  seed = s;
+  draws = 0;
+  tap_ = 0;
+  feed_ = kLen - kTap;
+  s %= kInt32Max;
+  if (s < 0) s += kInt32Max;
+  if (s == 0) s = 89482311;
+  int32_t x = int32_t(s);
+  for (int i = -20; i < kLen; i++) {
+    x = seedrand(x);
+    if (i < 0) continue;
+    uint64_t u = uint64_t(x) << 40;
+    x = seedrand(x);
+    u ^= uint64_t(x) << 20;
+    x = seedrand(x);
+    u ^= uint64_t(x);
+    vec_[i] = u ^ uint64_t(kCooked[i]);
+  }
+}
+uint64_t Rand::Uint64() {
+  draws++;
+  if (--tap_ < 0) tap_ += kLen;
+  if (--feed_ < 0) feed_ += kLen;
+  const uint64_t x = vec_[feed_] + vec_[tap_];
+  vec_[feed_] = x;
+  return x;
+}
+int64_t Rand::Int63() { return int64_t(Uint64() & 0x7fffffffffffffffULL); }
+int32_t Rand::Int31n(int32_t n) {  // rand.go Int31n
+  if ((n & (n - 1)) == 0) return Int31() & (n - 1);
+  const int32_t mx = int32_t((1u << 31) - 1 - (1u << 31) % uint32_t(n));
+  int32_t v = Int31();
+  while (v > mx) v = Int31();
+  return v % n;
+}
+int Rand::Intn(int n) {
+  if (n <= 0) throw std::invalid_argument("invalid argument to Intn");
+  return Int31n(int32_t(n));
+}
+double Rand::Float64() {  // Go 1 value stream: float64(Int63()) / (1 << 63), re-drawn when it rounds to 1
+  for (;;) {
+    const double f = double(Int63()) / 9223372036854775808.0;
+    if (f != 1.0) return f;
+  }
+}
+float Rand::Float32() {
+  for (;;) {
+    const float f = float(Float64());
+    if (f != 1.0f) return f;
+  }
+}
+}  // namespace rand
+
 namespace game {
+
+std::vector<core::Action> GenerateRandomActions(Engine &g, rand::Rand &rng) {
+  std::vector<core::Action> actions;
+  const GameState state = g.GameState();
+  const core::Board &board = *state.Board;
+  static const int dirs[4][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}};
+  for (const Player &player : state.Players) {
+    if (!player.Alive) continue;
+    if (rng.Float32() > 0.3f) continue;
+    std::vector<core::MoveAction> validMoves;
+    for (int y = 0; y < board.H; y++) {
+      for (int x = 0; x < board.W; x++) {
+        const core::Tile &tile = board.T[board.Idx(x, y)];
+        if (tile.Owner != player.ID || tile.Army <= 1) continue;
+        for (const auto &dir : dirs) {
+          const int toX = x + dir[0], toY = y + dir[1];
+          if (toX < 0 || toX >= board.W || toY < 0 || toY >= board.H) continue;
+          if (board.T[board.Idx(toX, toY)].IsMountain()) continue;
+          core::MoveAction move;
+          move.PlayerID = player.ID;
+          move.FromX = x, move.FromY = y, move.ToX = toX, move.ToY = toY;
+          move.MoveAll = rng.Float32() < 0.7f;
+          validMoves.push_back(move);
+        }
+      }
+    }
+    if (!validMoves.empty()) actions.push_back(validMoves[rng.Intn(int(validMoves.size()))]);
+  }
+  return actions;
+}
 
 // ---- GameState (state.go) ------------------------------------------------------------------
 std::shared_ptr<GameState> GameState::Clone() const {
@@ -181,6 +280,8 @@ void EnginePool::Release(int slot) {
 std::unique_ptr<Engine> EnginePool::NewEngine(const context::Context &ctx, const GameConfig &cfg) {
   (void)ctx;
   if (cfg.Width != W_ || cfg.Height != H_ || cfg.Players != P_) return nullptr;
+  if (cfg.Rng && cfg.Rng->draws != 0)  // the device generator is seeded, not handed a state: only a fresh generator maps onto it
+    throw std::invalid_argument("grl: NewEngine needs a fresh rand.Rand (values were already drawn from cfg.Rng)");
   int slot = Acquire();
   if (slot < 0) return nullptr;
   int64_t seed = cfg.Rng ? cfg.Rng->seed

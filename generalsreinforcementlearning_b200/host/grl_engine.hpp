@@ -57,17 +57,34 @@ class Context {
 inline Context Background() { return Context(); }
 }  // namespace context
 
-// ---- math/rand, as far as NewEngine needs it: a fresh generator is fully described by its seed
-//      (engine_initializer.go:90-94 builds one from cfg.Rng or the clock) -------------------------
+// ---- math/rand (go1.24, the v1 value stream): rand.New(rand.NewSource(seed)) -----------------------------------
+//      NewEngine hands a FRESH generator's seed to the device map generator (engine_initializer.go:90-94 builds the
+//      generator from cfg.Rng; a fresh one is fully described by its seed); GenerateRandomActions draws from it on the
+//      host exactly as demo_helpers.go does.
 namespace rand {
 struct Source {
   int64_t seed;
 };
-struct Rand {
-  int64_t seed;
+class Rand {  // rng.go (*rngSource) + rand.go
+ public:
+  explicit Rand(int64_t seed) { Seed(seed); }
+  void Seed(int64_t seed);
+  int64_t Int63();
+  uint64_t Uint64();
+  int32_t Int31() { return int32_t(Int63() >> 32); }
+  int32_t Int31n(int32_t n);
+  int Intn(int n);
+  double Float64();
+  float Float32();
+  int64_t seed;            // what it was seeded with
+  uint64_t draws = 0;      // values drawn since (NewEngine needs draws == 0)
+
+ private:
+  uint64_t vec_[607];
+  int tap_ = 0, feed_ = 0;
 };
 inline Source NewSource(int64_t seed) { return Source{seed}; }
-inline std::shared_ptr<Rand> New(Source s) { return std::make_shared<Rand>(Rand{s.seed}); }
+inline std::shared_ptr<Rand> New(Source s) { return std::make_shared<Rand>(s.seed); }
 }  // namespace rand
 
 // ---- the bound C ABI ---------------------------------------------------------------------------
@@ -280,6 +297,11 @@ class Engine {
   ExperienceCollector *collector_ = nullptr;
   std::vector<experience::Transition> last_;
 };
+
+// demo_helpers.go:12-62: per alive player, with probability 0.3, one uniformly chosen legal move (every (tile, direction)
+// pair in row-major order, directions down, up, right, left, each with its own MoveAll draw) — the reference's demo
+// policy, drawing from Go's generator so that a seed replays the reference's choices.
+std::vector<core::Action> GenerateRandomActions(Engine &g, rand::Rand &rng);
 
 // engine.go:62-71: a private one-game engine (its own one-slot pool on `device`).  Batched callers use
 // EnginePool::NewEngine instead.

@@ -800,6 +800,43 @@ TEST(TestEnginePool_StepBatch) {
   EXPECT(moved > 0, "the random policy expands territory");
 }
 
+// ---- math/rand + demo_helpers.go:12-62 ----------------------------------------------------------------------
+TEST(TestGoRandAndGenerateRandomActions) {
+  rand::Rand r(1);  // the canonical first values of rand.New(rand.NewSource(1))
+  EXPECT(r.Int63() == 5577006791947779410LL && r.Int63() == 8674665223082153551LL && r.Int63() == 6129484611666145821LL, "Int63");
+  r.Seed(1);
+  const int want[10] = {81, 87, 47, 59, 81, 18, 25, 40, 56, 0};
+  for (int i = 0; i < 10; i++) EXPECT_EQ(want[i], r.Intn(100), "Intn(100) #%d", i);
+  r.Seed(1);
+  EXPECT(std::fabs(r.Float64() - 0.6046602879796196) < 1e-16, "Float64");
+  r.Seed(1);
+  EXPECT(std::fabs(r.Float32() - 0.6046603f) < 1e-7f, "Float32");
+
+  // the demo policy only ever proposes moves the engine accepts, and moves the game along
+  auto engine = newEngine(10, 10, 2);
+  REQUIRE(engine != nullptr, "nil engine");
+  rand::Rand rng(99);
+  int played = 0;
+  for (int t = 0; t < 200 && !engine->IsGameOver(); t++) {
+    std::vector<core::Action> acts = game::GenerateRandomActions(*engine, rng);
+    for (const core::Action &a : acts) EXPECT(!a.Validate(*engine->gs()->Board, a.PlayerID), "proposed moves validate");
+    played += int(acts.size());
+    core::Error err = engine->Step(context::Background(), acts);
+    EXPECT(!err, "turn %d: %s", t, err.String().c_str());
+  }
+  EXPECT(played > 20, "about 0.3 moves per player and turn (%d)", played);
+  int tiles = 0;
+  for (const game::Player &p : engine->gs()->Players) tiles += int(p.OwnedTiles.size());
+  EXPECT(tiles > 2, "territory grew");
+  // NewEngine takes the seed of a FRESH generator
+  game::GameConfig cfg;
+  cfg.Width = 8, cfg.Height = 8, cfg.Players = 2;
+  cfg.Rng = rand::New(rand::NewSource(12345));
+  auto a = game::NewEngine(context::Background(), cfg, g_lib), b = newEngine(8, 8, 2);
+  REQUIRE(a && b, "engines");
+  EXPECT(a->gs()->Players[0].GeneralIdx == b->gs()->Players[0].GeneralIdx, "same seed, same map");
+}
+
 // ---- rendering.go:34-143 ----------------------------------------------------------------------------
 TEST(TestBoardRendering) {
   auto engine = createTestEngineForActionMask(3, 2, 2);
