@@ -105,3 +105,46 @@ def test_single_move_arithmetic(oracle_lib, a_from, a_to, move_all, to_owner):
         assert (out["owner"][0, 1], out["army"][0, 1]) == (0, moved - a_to)
     else:
         assert (out["owner"][0, 1], out["army"][0, 1]) == (to_owner, a_to - moved)
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(boards(), st.integers(1, 12), st.integers(0, 2**31 - 1))
+def test_gym_step_invariants_on_arbitrary_boards(oracle_lib, board, steps, aseed):
+    """The gym contract on ANY board (python/generals_gym/generals_env.py): observations stay in [0, 1], exactly one type
+    plane is set per tile, the mask agrees with what the env accepts (an action the mask allows is never rejected, one it
+    forbids always is and leaves the game untouched at a cost of -0.1), `any` == OR of the four directions, and a
+    sampled action is always a masked-in one."""
+    W, H, P, s, seed = board
+    N = W * H
+    e = new_engine(oracle_lib, W, H, P, max_actions=P)
+    e.set_state(s)
+    z = lambda shape, dt: np.zeros(shape, dt)
+    pl = dict(obs=z((1, P, 9, H, W), np.float32), mask=z((1, P, N * 5), np.uint8), stats=z((1, P, 4), np.int32),
+              actions=z((1, P, 8), np.uint8), prev_stats=z((1, P, 4), np.int32), turns=z(1, np.int32), calls=z(1, np.int32),
+              reward=z(1, np.float64), terminated=z(1, np.uint8), truncated=z(1, np.uint8), valid=z(1, np.uint8),
+              done=z(1, np.uint8), winner=z(1, np.int8), step_error=z(1, np.uint8), n_finished=z(1, np.int32))
+    e.gym_observe(500, pl["obs"], pl["mask"], pl["stats"])
+    rng = np.random.default_rng(aseed)
+    for t in range(steps):
+        obs, mask = pl["obs"][0], pl["mask"][0]
+        assert obs.min() >= 0.0 and obs.max() <= 1.0
+        assert np.array_equal(obs[:, 3:7].sum(1), np.ones((P, H, W), np.float32)), "one type plane per tile"
+        m5 = mask.reshape(P, N, 5)
+        assert np.array_equal(m5[:, :, 4], m5[:, :, :4].max(2)), "half-move flag == any direction"
+        sampled = z(1, np.int64)
+        e.gym_sample(int(rng.integers(0, 2**62)), pl["mask"], 0, sampled)
+        if mask[0].any():
+            assert mask[0, sampled[0]] == 1, "sampled actions are valid"
+        forbid = rng.random() < 0.3 and not mask[0].all()
+        a = int(rng.choice(np.flatnonzero(mask[0] == 0))) if forbid else int(sampled[0])
+        before = e.state_hash().copy()
+        accepted = bool(mask[0, a]) if 0 <= a < N * 5 else False   # the mask plane is rewritten by the step
+        e.gym_step(500, int(rng.integers(0, 2**62)), action=np.array([a], np.int64), opponent_action=None, **pl)
+        assert bool(pl["valid"][0]) == accepted
+        if not accepted:
+            assert pl["reward"][0] == -0.1 and np.array_equal(before, e.state_hash()), "a rejected action takes no turn"
+            assert not pl["terminated"][0]
+        if pl["terminated"][0]:
+            assert pl["done"][0] == 1 and abs(pl["reward"][0]) == 100.0
+            break
+    e.close()
