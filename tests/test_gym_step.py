@@ -34,7 +34,7 @@ def _pick(mask_row, rng, want_invalid):
     return int(idx[rng.integers(0, len(idx))])
 
 
-def gym_rollout(lib, W, H, P, B, steps, max_turns, self_play, seed=77, fog=1):
+def gym_rollout(lib, W, H, P, B, steps, max_turns, self_play, seed=77, fog=1, init=None):
     """Drive grl_gym_step with actions drawn (host RNG) from the library's own mask plane; returns the trace of
     every output plane after every step."""
     import torch
@@ -46,6 +46,8 @@ def gym_rollout(lib, W, H, P, B, steps, max_turns, self_play, seed=77, fog=1):
     if on_device:
         e.use_torch_stream()
     e.reset_seeded(np.arange(B, dtype=np.int64) + 12345)
+    if init is not None:
+        e.set_state(init)
     N = W * H
     pl = _planes(torch, dev, B, P, N, H, W)
     e.gym_observe(max_turns, pl["obs"], pl["mask"], pl["stats"])
@@ -128,6 +130,21 @@ def test_cuda_gym_step_matches_oracle_without_fog(cuda_lib, oracle_lib, W, H, P,
     g, _ = gym_rollout(cuda_lib, W, H, P, B, 30, 500, False, fog=0)
     o, _ = gym_rollout(oracle_lib, W, H, P, B, 30, 500, False, fog=0)
     _compare(g, o, f"cuda vs oracle {W}x{H}x{P}p, no fog")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,P,B", [(10, 10, 2, 96), (15, 15, 2, 64), (20, 20, 2, 40), (8, 8, 3, 64), (10, 10, 4, 64)])
+def test_cuda_gym_step_matches_oracle_on_dense_battle_states(cuda_lib, oracle_lib, W, H, P, B):
+    """Hand-built crowded boards (several general-type tiles per player, stale cached lists, arbitrary visibility bits —
+    test_cuda_parity.dense_battle_state): eliminations, the +50 bonus, terminated episodes and orphaned tiles all occur
+    within a few steps, and every writer has to agree with the oracle on states no map generator produces."""
+    from test_cuda_parity import dense_battle_state
+
+    init = dense_battle_state(np.random.default_rng(W * 7 + P), W, H, P, B)
+    g, _ = gym_rollout(cuda_lib, W, H, P, B, 40, 500, False, init=init)
+    o, _ = gym_rollout(oracle_lib, W, H, P, B, 40, 500, False, init=init)
+    _compare(g, o, f"cuda vs oracle {W}x{H}x{P}p, dense battles")
+    assert any(s["terminated"].any() for s in o), "games end on these boards"
 
 
 @pytest.mark.gpu
