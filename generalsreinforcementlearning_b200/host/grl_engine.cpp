@@ -604,6 +604,7 @@ int Engine::GetWinner() {
 }
 
 std::vector<bool> Engine::GetLegalActionMask(int playerID) {
+  if (!pool_) throw std::runtime_error("grl: engine outlived its pool");
   const int N = pool_->W_ * pool_->H_, P = pool_->P_, B = pool_->B_;
   std::vector<bool> mask(size_t(N) * 4, false);
   if (playerID < 0 || playerID >= P) return mask;  // engine.go:273-276
@@ -615,6 +616,7 @@ std::vector<bool> Engine::GetLegalActionMask(int playerID) {
 }
 
 std::vector<bool> Engine::SerializerActionMask(int playerID) {
+  if (!pool_) throw std::runtime_error("grl: engine outlived its pool");
   const int N = pool_->W_ * pool_->H_, P = pool_->P_, B = pool_->B_;
   std::vector<bool> mask(size_t(N) * 4, false);
   if (playerID < 0 || playerID >= P) return mask;
@@ -626,6 +628,7 @@ std::vector<bool> Engine::SerializerActionMask(int playerID) {
 }
 
 PlayerVisibility Engine::ComputePlayerVisibility(int playerID) {
+  if (!pool_) throw std::runtime_error("grl: engine outlived its pool");
   const int N = pool_->W_ * pool_->H_, P = pool_->P_, B = pool_->B_;
   PlayerVisibility vis;
   vis.VisibleTiles.assign(N, false);
@@ -651,6 +654,7 @@ std::map<int, bool> Engine::GetChangedTiles() { return gs()->ChangedTiles; }
 std::map<int, bool> Engine::GetVisibilityChangedTiles() { return gs()->VisibilityChangedTiles; }
 
 std::vector<float> Engine::StateTensor(int playerID) {
+  if (!pool_) throw std::runtime_error("grl: engine outlived its pool");
   const int N = pool_->W_ * pool_->H_, P = pool_->P_, B = pool_->B_;
   if (playerID < 0 || playerID >= P) throw std::out_of_range("grl: StateTensor: player out of range");
   std::vector<float> all(size_t(B) * P * GRL_OBS_CHANNELS * N);
