@@ -975,9 +975,7 @@ int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const 
   if (!env || !io || max_turns < 1) return fail(GRL_ERR_INVALID_ARG, "bad argument");
   const grl_config &c = env->cfg;
   if (c.num_players < 2 || c.max_actions < 2) return fail(GRL_ERR_INVALID_ARG, "the gym step drives 2 players / 2 action slots");
-  // GRL_GYM_UNFUSED=1 keeps the round-1 sequence of seven launches (sample, patch, encode, turn, read-out, finish) for
-  // cross-checks; the default is ONE launch of the turn kernel's gym instantiation.
-  static const bool unfused = [] { const char *e = getenv("GRL_GYM_UNFUSED"); return e && e[0] == '1'; }();
+  // ONE launch: the turn kernel's gym instantiation (io->actions / io->prev_stats are scratch only the oracle uses).
   const void *need[] = {io->action, io->out.mask, io->out.stats, io->turns, io->calls, io->reward,
                         io->terminated, io->truncated, io->valid, io->done, io->winner, io->step_error};
   CUDA_TRY(cudaSetDevice(c.device));
@@ -986,66 +984,34 @@ int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const 
   if ((io->opponent_action && !is_device_ptr(io->opponent_action)) || (io->out.obs && !is_device_ptr(io->out.obs)) ||
       (io->n_finished && !is_device_ptr(io->n_finished)))
     return fail(GRL_ERR_UNSUPPORTED, "grl_gym_step takes device pointers for every plane");
-  const size_t B = (size_t)c.num_envs, P = (size_t)c.num_players;
   cudaStream_t sq = env->stream;
-  GrlKParams prm = base_params(env);
-  if (!unfused) {
-    int st0 = ensure_logtab(env);
-    if (st0) return st0;
-    GrlGymK gk;
-    memset(&gk, 0, sizeof gk);
-    gk.action = (const long long *)io->action;
-    gk.opponent_action = (const long long *)io->opponent_action;
-    gk.logtab = env->d_logtab;
-    gk.obs = io->out.obs;
-    gk.mask = io->out.mask;
-    gk.stats = io->out.stats;
-    gk.turns = io->turns;
-    gk.calls = io->calls;
-    gk.reward = io->reward;
-    gk.terminated = io->terminated;
-    gk.truncated = io->truncated;
-    gk.valid = io->valid;
-    gk.n_finished = io->n_finished;
-    gk.opponent_seed = opponent_seed;
-    gk.max_turns = max_turns;
-    GrlKParams pt = prm;
-    pt.actions = nullptr;
-    pt.done = io->done;
-    pt.winner = io->winner;
-    pt.step_error = io->step_error;
-    if (io->n_finished) CUDA_TRY(cudaMemsetAsync(io->n_finished, 0, 4, sq));
-    CUDA_TRY(grl_launch_gym_step(pt, gk, sq));
-    env->launches += 1;
-    return GRL_OK;
-  }
-  if (!io->actions || !io->prev_stats || !is_device_ptr(io->actions) || !is_device_ptr(io->prev_stats))
-    return fail(GRL_ERR_UNSUPPORTED, "grl_gym_step takes device pointers for every plane");
-  CUDA_TRY(cudaMemcpyAsync(io->prev_stats, io->out.stats, B * P * 16, cudaMemcpyDeviceToDevice, sq));
-  if (io->opponent_action) {
-    CUDA_TRY(cudaMemsetAsync(io->actions, 0, B * (size_t)c.max_actions * sizeof(grl_action), sq));
-    CUDA_TRY(grl_launch_gym_encode(prm, (const long long *)io->opponent_action, 1, 1, io->out.mask, 0, io->actions, nullptr, sq));
-    env->launches++;
-  } else {  // the reference's default opponent: a uniformly random legal FULL move
-    GrlKParams ps = prm;
-    ps.policy_seed = opponent_seed;
-    CUDA_TRY(grl_launch_sample(ps, io->actions, sq));
-    CUDA_TRY(grl_launch_gym_patch(prm, io->actions, 1, sq));
-    env->launches += 2;
-  }
-  CUDA_TRY(grl_launch_gym_encode(prm, (const long long *)io->action, 0, 0, io->out.mask, 1, io->actions, io->valid, sq));
-  GrlKParams pt = prm;
-  pt.actions = io->actions;
+  int st0 = ensure_logtab(env);
+  if (st0) return st0;
+  GrlGymK gk;
+  memset(&gk, 0, sizeof gk);
+  gk.action = (const long long *)io->action;
+  gk.opponent_action = (const long long *)io->opponent_action;
+  gk.logtab = env->d_logtab;
+  gk.obs = io->out.obs;
+  gk.mask = io->out.mask;
+  gk.stats = io->out.stats;
+  gk.turns = io->turns;
+  gk.calls = io->calls;
+  gk.reward = io->reward;
+  gk.terminated = io->terminated;
+  gk.truncated = io->truncated;
+  gk.valid = io->valid;
+  gk.n_finished = io->n_finished;
+  gk.opponent_seed = opponent_seed;
+  gk.max_turns = max_turns;
+  GrlKParams pt = base_params(env);
+  pt.actions = nullptr;
   pt.done = io->done;
   pt.winner = io->winner;
   pt.step_error = io->step_error;
-  CUDA_TRY(grl_launch_turn(pt, true, true, sq));
-  int st = grl_gym_observe(env, max_turns, &io->out);
-  if (st) return st;
   if (io->n_finished) CUDA_TRY(cudaMemsetAsync(io->n_finished, 0, 4, sq));
-  CUDA_TRY(grl_launch_gym_finish(prm, max_turns, io->out.stats, io->prev_stats, io->valid, io->done, io->winner, io->turns, io->calls,
-                                 io->reward, io->terminated, io->truncated, io->n_finished, sq));
-  env->launches += 3;
+  CUDA_TRY(grl_launch_gym_step(pt, gk, sq));
+  env->launches += 1;
   return GRL_OK;
 }
 

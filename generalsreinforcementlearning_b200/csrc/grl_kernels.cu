@@ -1695,6 +1695,13 @@ __device__ __noinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK 
       else if (fy + 1 < H) ty = fy + 1;
       else tx = fx - 1;
     }
+    // Server.SubmitAction -> ValidateCoreAction (internal/grpc/gameserver/server.go:241, action_validator.go:113-137):
+    // the server runs MoveAction.Validate on the board at submission and never buffers a refused action; the turn runs
+    // without it and the client, which ignores the response, still counts the step.  The client's mask guarantees
+    // everything Validate checks except the target of a half move, which it aims at the first in-bounds direction
+    // whatever stands there.
+    const int ti = ty * W + tx;
+    if (info == 4 && ((S.M[ti >> 5] >> (ti & 31)) & 1u)) return;
     const PackedAction pa = pack_action(p, fx, fy, tx, ty, info != 4);
     const uint2 d = decode_action(make_uint2(pa.lo, pa.hi), W, H, P);
     if (g.lane == 0) {
@@ -2684,50 +2691,6 @@ __global__ void __launch_bounds__(256) grl_gym_sample_kernel(const GrlKParams pr
   }
 }
 
-// The tail of GeneralsEnv.step (generals_env.py:268-289) and its client-side reward (:499-561), one thread per env.
-// `force_full` patches the random opponent's slot to a full move (the reference's random opponent never sends
-// half moves, :483).
-__global__ void grl_gym_patch_kernel(const GrlKParams prm, uint2 *__restrict__ actions, int slot) {
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < prm.B; b += gridDim.x * blockDim.x)
-    reinterpret_cast<uint8_t *>(actions + (size_t)b * prm.A + slot)[5] = 1;  // grl_action.move_all
-}
-
-__global__ void grl_gym_finish_kernel(const GrlKParams prm, int max_turns, const int32_t *__restrict__ stats,
-                                      const int32_t *__restrict__ prev_stats, const uint8_t *__restrict__ valid_in,
-                                      const uint8_t *__restrict__ done, const int8_t *__restrict__ winner,
-                                      int32_t *__restrict__ turns, int32_t *__restrict__ calls, double *__restrict__ reward,
-                                      uint8_t *__restrict__ terminated, uint8_t *__restrict__ truncated,
-                                      int32_t *__restrict__ n_finished) {
-  const int P = prm.P;
-  int mine = 0;
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < prm.B; b += gridDim.x * blockDim.x) {
-    const int valid = valid_in[b] ? 1 : 0;
-    const int tn = turns[b] + valid, cl = calls[b] + 1;
-    turns[b] = tn;
-    calls[b] = cl;
-    const bool term = done[b] && valid;
-    const bool trunc = (tn >= max_turns && valid) || cl >= max_turns;
-    const int32_t *cur = stats + (size_t)b * P * 4, *prev = prev_stats + (size_t)b * P * 4;
-    double r = 0.0;
-    if (!valid) {
-      r = -0.1;
-    } else if (term) {
-      r = winner[b] == 0 ? 100.0 : -100.0;
-    } else {
-      r = __dadd_rn(r, __dmul_rn((double)(cur[1] - prev[1]), 1.0));  // no FMA contraction (one rounding per statement)
-      r = __dadd_rn(r, __dmul_rn((double)(cur[0] - prev[0]), 0.01));
-      for (int q = 1; q < P; q++)
-        if (prev[q * 4 + 2] == 1 && cur[q * 4 + 2] == 0) r = __dadd_rn(r, 50.0);
-    }
-    reward[b] = r;
-    terminated[b] = term ? 1 : 0;
-    truncated[b] = trunc ? 1 : 0;
-    mine += (term || trunc) ? 1 : 0;
-  }
-  mine = __reduce_add_sync(FULL, mine);
-  if (n_finished && (threadIdx.x & 31) == 0 && mine) atomicAdd(n_finished, mine);
-}
-
 // packed engine mask with the half-move replica: [B][P][rep][words]
 __global__ void grl_mask_replicate_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t rows, int words,
                                           int rep) {
@@ -3045,19 +3008,6 @@ cudaError_t grl_launch_gym_sample(const GrlKParams &prm, unsigned long long seed
   int grid = grid_for(8, prm.B);
   if (grid > 148 * 16) grid = 148 * 16;
   grl_gym_sample_kernel<<<grid, 256, 0, stream>>>(prm, seed, mask, player, action);
-  return cudaGetLastError();
-}
-
-cudaError_t grl_launch_gym_patch(const GrlKParams &prm, void *actions, int slot, cudaStream_t stream) {
-  grl_gym_patch_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm, (uint2 *)actions, slot);
-  return cudaGetLastError();
-}
-
-cudaError_t grl_launch_gym_finish(const GrlKParams &prm, int max_turns, const int32_t *stats, const int32_t *prev_stats,
-                                  const uint8_t *valid, const uint8_t *done, const int8_t *winner, int32_t *turns, int32_t *calls,
-                                  double *reward, uint8_t *terminated, uint8_t *truncated, int32_t *n_finished, cudaStream_t stream) {
-  grl_gym_finish_kernel<<<flat_grid((size_t)prm.B, 256), 256, 0, stream>>>(prm, max_turns, stats, prev_stats, valid, done, winner, turns,
-                                                                           calls, reward, terminated, truncated, n_finished);
   return cudaGetLastError();
 }
 

@@ -23,10 +23,6 @@ cudaError_t grl_launch_gym_encode(const GrlKParams &prm, const long long *action
                                   int skip_invalid, void *actions, uint8_t *valid, cudaStream_t stream);
 cudaError_t grl_launch_gym_sample(const GrlKParams &prm, unsigned long long seed, const uint8_t *mask, int player, long long *action,
                                   cudaStream_t stream);
-cudaError_t grl_launch_gym_patch(const GrlKParams &prm, void *actions, int slot, cudaStream_t stream);
-cudaError_t grl_launch_gym_finish(const GrlKParams &prm, int max_turns, const int32_t *stats, const int32_t *prev_stats,
-                                  const uint8_t *valid, const uint8_t *done, const int8_t *winner, int32_t *turns, int32_t *calls,
-                                  double *reward, uint8_t *terminated, uint8_t *truncated, int32_t *n_finished, cudaStream_t stream);
 cudaError_t grl_launch_mask_replicate(const uint32_t *in, uint32_t *out, size_t rows, int words, int rep,
                                       cudaStream_t stream);
 cudaError_t grl_launch_state_hash(const GrlKParams &prm, uint64_t *out, cudaStream_t stream);

@@ -1556,6 +1556,17 @@ int grlo_gym_step(grlo_env *e, int32_t max_turns, uint64_t opponent_seed, const 
     for (int b = 0; b < B; b++) io->actions[(size_t)b * A + 1].move_all = 1;
   }
   if ((st = grlo_gym_encode(e, io->action, 0, 0, io->out.mask, 1, io->actions, io->valid))) return st;
+  /* Server.SubmitAction -> ActionValidator.ValidateCoreAction (internal/grpc/gameserver/server.go:241,
+   * action_validator.go:113-137): MoveAction.Validate against the board AT SUBMISSION; a refused action is never
+   * buffered and the turn runs without it.  The client does not look at the response, so it still counts the
+   * step.  What the client's own mask lets through and the server refuses: a half move, which the client aims
+   * at the first in-bounds direction whatever stands there (generals_env.py:421-428) -- at a mountain. */
+  for (int b = 0; b < B; b++)
+    for (int s = 0; s < 2; s++) {
+      grl_action *a = &io->actions[(size_t)b * A + s];
+      if (a->present && validate_move(&e->g[b], a->player_id, a->from_x, a->from_y, a->to_x, a->to_y) != GRL_STEP_OK)
+        a->present = 0;
+    }
   grl_step_outputs so;
   memset(&so, 0, sizeof(so));
   so.done = io->done;

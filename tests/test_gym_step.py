@@ -116,9 +116,8 @@ def test_cuda_gym_step_matches_oracle(cuda_lib, oracle_lib, W, H, P, B, steps, m
     g, launches = gym_rollout(cuda_lib, W, H, P, B, steps, max_turns, self_play)
     o, _ = gym_rollout(oracle_lib, W, H, P, B, steps, max_turns, self_play)
     _compare(g, o, f"cuda vs oracle {W}x{H}x{P}p")
-    if os.environ.get("GRL_GYM_UNFUSED") != "1":
-        # reset (mapgen + turn-0) and the initial read-out aside, a step is ONE launch; state_hash adds one per step
-        assert launches <= 3 + 2 * steps + 2, f"{launches} launches for {steps} fused steps"
+    # reset (mapgen + turn-0) and the initial read-out aside, a step is ONE launch; state_hash adds one per step
+    assert launches <= 3 + 2 * steps + 2, f"{launches} launches for {steps} fused steps"
     if (W, H) == (5, 5):
         assert any(s["terminated"].any() for s in g), "5x5 games end within 80 steps"
 
@@ -145,17 +144,6 @@ def test_cuda_gym_step_matches_oracle_on_dense_battle_states(cuda_lib, oracle_li
     o, _ = gym_rollout(oracle_lib, W, H, P, B, 40, 500, False, init=init)
     _compare(g, o, f"cuda vs oracle {W}x{H}x{P}p, dense battles")
     assert any(s["terminated"].any() for s in o), "games end on these boards"
-
-
-@pytest.mark.gpu
-def test_cuda_gym_step_unfused_sequence_matches_oracle(cuda_lib):
-    """The round-1 seven-launch sequence stays available (GRL_GYM_UNFUSED=1) and agrees with the oracle too —
-    so fused == unfused == oracle.  The switch is read once per process, hence the subprocess."""
-    env = dict(os.environ, GRL_GYM_UNFUSED="1")
-    proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.abspath(__file__), "-k",
-                           "gym_step_matches_oracle"], env=env, cwd=ROOT, stdout=subprocess.PIPE,
-                          stderr=subprocess.STDOUT, text=True, timeout=900)
-    assert proc.returncode == 0, proc.stdout[-3000:]
 
 
 def _partial_observe(lib, W, H, P, B, on_device):
