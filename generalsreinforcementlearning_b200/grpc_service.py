@@ -134,6 +134,8 @@ class GameInstance:
         self.timer: Optional[threading.Timer] = None
         self.started_at = 0.0
         self.prev_alive: List[bool] = []
+        self.last_activity = time.time()          # gameInstance.lastActivity (game_manager.go:160,562)
+        self.final = None                          # (state planes, engine masks) kept once the env slot is released
 
 
 class ExperienceStore:
@@ -165,7 +167,9 @@ class ExperienceStore:
 class GameServer:
     """Implements both services; register with ``add_to_server`` or use ``serve``."""
 
-    def __init__(self, lib=None, slots_per_pool: int = 256, device: int = 0, max_games: int = 0, seed: Optional[int] = None):
+    def __init__(self, lib=None, slots_per_pool: int = 256, device: int = 0, max_games: int = 0, seed: Optional[int] = None,
+                 finished_game_ttl: float = 600.0, abandoned_game_timeout: float = 1800.0, cleanup_interval: float = 300.0,
+                 reference_compat: bool = False):
         if lib is None:
             from . import load_library
 
@@ -178,9 +182,23 @@ class GameServer:
         self.store = ExperienceStore()
         self.seed = seed  # None: time-seeded maps like the reference (engine_initializer.go:91-94)
         self.submitted_ids = set()
+        # server.go:42-44: cleanupInterval 5 min, finishedGameTTL 10 min, abandonedGameTimeout 30 min
+        self.finished_game_ttl, self.abandoned_game_timeout = finished_game_ttl, abandoned_game_timeout
+        self.cleanup_interval = cleanup_interval
+        self._last_cleanup = time.time()
+        # collectExperiences copies MoveAction.From/To, the Coordinate fields
+        # (internal/game/turn_processor.go:194-199), but the server's convertProtoAction fills only FromX/FromY/ToX/ToY
+        # (internal/grpc/gameserver/converters.go:116-123): From == To == (0,0) and Serializer.ActionToIndex
+        # (experience/serializer.go:179-198) yields 0 for every move of a served game.  reference_compat=True reproduces
+        # that wire value; the default emits the index ActionToIndex defines for the move that was made, which is what
+        # a learner needs.
+        self.reference_compat = reference_compat
 
     # ------------------------------------------------------------------ GameService
     def CreateGame(self, req, ctx):
+        now = time.time()
+        if now - self._last_cleanup >= self.cleanup_interval or (self.max_games > 0 and len(self.games) >= self.max_games):
+            self.cleanup_games(now)
         with self.mu:
             if self.max_games > 0 and len(self.games) >= self.max_games:
                 ctx.abort(grpc.StatusCode.RESOURCE_EXHAUSTED,
@@ -208,6 +226,8 @@ class GameServer:
                 and 1 <= cfg.max_players <= _abi.GRL_MAX_PLAYERS):
             ctx.abort(grpc.StatusCode.INTERNAL, f"failed to start game engine for game {g.id}: unsupported board")
         pool = self._pool_for(cfg)
+        if not pool.free:
+            self.cleanup_games()
         with pool.lock:
             if not pool.free:
                 ctx.abort(grpc.StatusCode.RESOURCE_EXHAUSTED, f"failed to start game engine for game {g.id}: no free env slot")
@@ -220,7 +240,7 @@ class GameServer:
                 ctx.abort(grpc.StatusCode.INTERNAL, f"failed to start game engine for game {g.id}: {exc}")
             pool.refresh()
         g.pool, g.phase, g.current_turn, g.actions = pool, common.GAME_PHASE_RUNNING, 0, {}
-        g.started_at = time.time()
+        g.started_at = g.last_activity = time.time()
         g.prev_alive = [True] * cfg.max_players
         ev = game.GameUpdate()
         _now(ev.event.game_started.started_at)
@@ -243,6 +263,7 @@ class GameServer:
             pid = len(g.players)
             p = _Player(pid, req.player_name, f"token-{g.id}-{pid}")
             g.players.append(p)
+            g.last_activity = time.time()
             if len(g.players) == g.config.max_players:
                 self._start_engine(g, ctx)
                 start_timer = True
@@ -309,6 +330,7 @@ class GameServer:
                                   f"{_VALIDATE_MSG[code]}"))
         with g.mu:
             g.actions[req.player_id] = move
+            g.last_activity = time.time()
             all_in = len(g.actions) >= len(g.players)  # game_manager.go:554-573
         if all_in:
             if not self._process_turn(g):
@@ -424,7 +446,54 @@ class GameServer:
                 self._broadcast(g, lambda _pid, ev=ev: ev)
             if g.streams:
                 self._broadcast(g, lambda pid: self._stream_update(g, st, pid))
+            if g.phase == common.GAME_PHASE_ENDED:
+                self._release_slot(g, st)
         return True
+
+    def _release_slot(self, g: GameInstance, st=None):
+        """Hand the game's env slot back to its pool.  The reference keeps a finished game's engine until
+        cleanupGames drops the whole game (game_manager.go:257-343); here the engine is a slot of a shared batch, so
+        the final state is frozen on the host (GetGameState keeps answering from it) and the slot is reused at once —
+        a gym client creates a new game on every reset() (generals_env.py:167-177)."""
+        pool = g.pool
+        if pool is None or g.slot < 0:
+            return
+        with pool.lock:
+            if st is None:
+                st = pool.engine.get_state(g.slot, 1)
+            g.final = (st, pool.eng_mask[g.slot].cpu().numpy().copy())
+            pool.free.append(g.slot)
+            g.slot = -1
+
+    def cleanup_games(self, now: Optional[float] = None) -> int:
+        """GameManager.cleanupGames (game_manager.go:257-343): finished games leave after finished_game_ttl,
+        games without activity after abandoned_game_timeout; timers stopped, streams closed, slots released."""
+        now = time.time() if now is None else now
+        self._last_cleanup = now
+        with self.mu:
+            refs = list(self.games.items())
+        drop = []
+        for gid, g in refs:
+            with g.mu:
+                idle = now - g.last_activity
+                if (g.phase == common.GAME_PHASE_ENDED and idle > self.finished_game_ttl) or \
+                        (g.phase != common.GAME_PHASE_ENDED and idle > self.abandoned_game_timeout):
+                    drop.append((gid, g))
+        for gid, g in drop:
+            with g.mu:
+                if g.timer:
+                    g.timer.cancel()
+                if g.phase != common.GAME_PHASE_ENDED:
+                    g.phase = common.GAME_PHASE_ENDED     # an abandoned game stops accepting actions
+                self._release_slot(g)
+                g.idempotency.clear()
+            with g.stream_cv:                              # StreamManager.CloseAll
+                g.streams.clear()
+                g.stream_cv.notify_all()
+        with self.mu:
+            for gid, _ in drop:
+                self.games.pop(gid, None)
+        return len(drop)
 
     def _collect(self, g, prev_obs, prev_mask, over):
         """SimpleCollector.OnStateTransition (collector.go:30-98)."""
@@ -437,7 +506,8 @@ class GameServer:
             if aidx[pid] < 0:
                 continue
             x = experience.Experience(experience_id=str(uuid.uuid4()), game_id=g.id, player_id=pid, turn=g.current_turn,
-                                      action=int(aidx[pid]), reward=float(reward[pid]), done=over)
+                                      action=0 if self.reference_compat else int(aidx[pid]), reward=float(reward[pid]),
+                                      done=over)
             x.state.shape.extend([9, pool.H, pool.W])
             x.state.data.extend(prev_obs[pid].reshape(-1).tolist())
             x.next_state.shape.extend([9, pool.H, pool.W])
@@ -493,8 +563,14 @@ class GameServer:
             return s
         pool = g.pool
         with pool.lock:
-            st = pool.engine.get_state(g.slot, 1)
-            mask = pool.eng_mask[g.slot, viewer].cpu().numpy() if 0 <= viewer < pool.P else np.zeros(pool.N * 4, np.uint8)
+            if g.slot < 0:      # finished: the slot went back to the pool, the final state is frozen on the host
+                st, masks = g.final
+            else:
+                st, masks = pool.engine.get_state(g.slot, 1), None
+            if not 0 <= viewer < pool.P:
+                mask = np.zeros(pool.N * 4, np.uint8)
+            else:
+                mask = masks[viewer] if masks is not None else pool.eng_mask[g.slot, viewer].cpu().numpy()
         s.turn = int(st["turn"][0])
         s.players.extend(self._player_states(g, st, viewer))
         fog_on = bool(pool.engine.cfg.fog_of_war)

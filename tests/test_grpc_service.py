@@ -410,3 +410,94 @@ def test_reference_experience_stream_client_consumes_this_server(server):
         assert 0 <= x["action"] < 144 and x["action_mask"][x["action"]], "the recorded action was legal in the recorded state"
         assert x["state"][7].sum() > 0 and np.array_equal(x["state"][7] + x["state"][8], np.ones((6, 6), np.float32))
     assert client.get_stats()["total_batches"] >= 2
+
+
+# ---- env slots and finished games are released (GameManager.cleanupGames, game_manager.go:236-343) -------------------
+def _duel_board():
+    """5x5: player 0's stack at (3,4) stands next to player 1's general at (4,4): one move ends the game."""
+    owner, army, typ = np.full(25, -1, np.int32), np.zeros(25, np.int32), np.zeros(25, np.int32)
+    for (x, y, o, a, t) in ((0, 0, 0, 3, 1), (3, 4, 0, 25, 0), (4, 4, 1, 4, 1), (1, 0, 1, 5, 0)):
+        owner[y * 5 + x], army[y * 5 + x], typ[y * 5 + x] = o, a, t
+    return owner[None], army[None], typ[None]
+
+
+def _play_duel(gs, stub):
+    gid, js = _start(stub, 5, 5)
+    g = gs.games[gid]
+    with g.pool.lock:
+        g.pool.engine.reset_boards(*_duel_board(), env_ids=[g.slot])
+        g.pool.refresh()
+    strike = game.Action(type=common.ACTION_TYPE_MOVE, turn_number=0)
+    getattr(strike, "from").x, getattr(strike, "from").y = 3, 4
+    strike.to.x, strike.to.y = 4, 4
+    assert stub.SubmitAction(game.SubmitActionRequest(game_id=gid, player_id=0, player_token=js[0].player_token, action=strike)).success
+    assert stub.SubmitAction(game.SubmitActionRequest(game_id=gid, player_id=1, player_token=js[1].player_token)).success
+    return gid, js
+
+
+def test_more_games_than_env_slots_through_one_server(oracle_lib):
+    """A gym client creates a new game on every reset() (generals_env.py:167-177): a server must outlive its pool size."""
+    srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=3, seed=5, max_games=8, finished_game_ttl=600.0)
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    stub = Stub(ch, GAME)
+    try:
+        finished = []
+        for k in range(8):                       # 8 games through 3 slots
+            gid, js = _play_duel(gs, stub)
+            g = gs.games[gid]
+            assert g.phase == common.GAME_PHASE_ENDED and g.slot == -1, "the slot goes back when the game ends"
+            st = stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=1, player_token=js[1].player_token)).state
+            # the finished game keeps answering from its frozen final state
+            assert (st.status, st.current_phase, st.winner_id, st.turn) == (common.GAME_STATUS_FINISHED, common.GAME_PHASE_ENDED, 0, 1)
+            assert [p.status for p in st.players] == [common.PLAYER_STATUS_ACTIVE, common.PLAYER_STATUS_ELIMINATED]
+            r = stub.SubmitAction(game.SubmitActionRequest(game_id=gid, player_id=0, player_token=js[0].player_token))
+            assert r.error_code == common.ERROR_CODE_GAME_OVER
+            finished.append(gid)
+        assert len(gs.pools[(5, 5, 2)].free) == 3
+        # max_games counts finished games until their TTL passes (cleanupGames), then they leave the map
+        with pytest.raises(grpc.RpcError) as e:
+            stub.CreateGame(game.CreateGameRequest(config=game.GameConfig(width=5, height=5, max_players=2)))
+        assert e.value.code() == grpc.StatusCode.RESOURCE_EXHAUSTED
+        import time as _t
+        assert gs.cleanup_games(_t.time() + 601.0) == 8 and not gs.games
+        gid, _ = _play_duel(gs, stub)
+        assert gid == "game-9"
+        # abandoned games (no activity for abandoned_game_timeout) release their slots too
+        for _ in range(3):
+            _start(stub, 5, 5)
+        assert len(gs.pools[(5, 5, 2)].free) == 0
+        assert gs.cleanup_games(_t.time() + 1801.0) == 4
+        assert len(gs.pools[(5, 5, 2)].free) == 3 and not gs.games
+        _play_duel(gs, stub)
+    finally:
+        ch.close()
+        srv.stop(0)
+        gs.close()
+
+
+def test_reference_compat_emits_the_action_index_the_reference_server_emits(oracle_lib):
+    """on the reference's gRPC path Experience.action is always 0 (turn_processor.go:194-199 reads
+    MoveAction.From/To, converters.go:116-123 fills FromX/FromY/ToX/ToY).  Default: the real ActionToIndex."""
+    for compat in (False, True):
+        srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=2, seed=77, reference_compat=compat)
+        ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+        stub, xstub = Stub(ch, GAME), Stub(ch, EXP)
+        try:
+            gid, js = _start(stub, 6, 6, collect=True)
+            rng = np.random.default_rng(11)
+            for turn in range(6):
+                for j in js:
+                    st = stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)).state
+                    req = game.SubmitActionRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)
+                    req.action.CopyFrom(_legal_action(st, rng, st.turn))
+                    assert stub.SubmitAction(req).success
+            xs = list(xstub.StreamExperiences(experience.StreamExperiencesRequest(game_ids=[gid], follow=False)))
+            assert len(xs) == 12
+            if compat:
+                assert all(x.action == 0 for x in xs)
+            else:
+                assert any(x.action != 0 for x in xs) and all(x.action_mask[x.action] for x in xs)
+        finally:
+            ch.close()
+            srv.stop(0)
+            gs.close()
