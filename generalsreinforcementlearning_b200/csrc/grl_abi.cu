@@ -58,12 +58,8 @@ struct grl_env {
   uint32_t *d_geom = nullptr;
   float *d_logtab = nullptr;  // float32(log(a + 1) / 10) for a in 0..65535 (generals_env.py:324), built on first use
   Scratch scratch[SL_COUNT];
-  int use_tma = 1;
-  int prefetch_dist = 0;       // > 0: warp of game g prefetches the slab of game g+dist into L2
-  int lanes_per_game = 0;      // 32: one game per warp even on small boards (GRL_LANES_PER_GAME)
-  int host_mapgen = 0;         // GRL_HOST_MAPGEN=1: generate seeded maps on the host (comparison / cross-check)
-  size_t l2_window_bytes = 0;  // > 0: launch the turn kernel with a persisting-L2 window over the state
-  float l2_hit_ratio = 1.0f;
+  int prefetch_dist = 0;       // > 0: warp of game g prefetches the slab of game g+dist into L2 (GRL_PREFETCH_DIST)
+  int host_mapgen = 0;         // GRL_HOST_MAPGEN=1: generate seeded maps on the host (cross-check of the device generator)
   uint64_t launches = 0;
   int host_threads = 1;
   // host-buffer calls split the batch into sub-ranges on these streams so that the copies of one
@@ -71,9 +67,6 @@ struct grl_env {
   static constexpr int kPipe = 8;
   cudaStream_t pipe[kPipe] = {};
   cudaEvent_t ev_start = nullptr, ev_done[kPipe] = {};
-  int first_in_place = 1;  // GRL_FIRST_IN_PLACE (default 1; e2e 179.1 -> 180.1 M env-steps/s): see run_turn
-  int zero_copy = 1;    // GRL_ZERO_COPY (default 1; e2e 169.8 -> 179.0 M env-steps/s): 1 = small result planes in pinned host memory are written by the kernel
-                        // directly (no D2H copies), 2 = + actions read in place, 3 = + observation / mask planes
   int pipe_chunks = 6;  // GRL_PIPE_CHUNKS=1 disables the pipelining (e2e: 160 M env-steps/s at 1, 169 M at 4, 170 M at 6-8)
 };
 
@@ -139,11 +132,7 @@ GrlKParams base_params(const grl_env *env) {
   p.pn = c.production_normal;
   p.grow_interval = c.normal_growth_interval;
   p.env_id_base = c.env_id_base;
-  p.use_tma = env->use_tma;
   p.prefetch_dist = env->prefetch_dist;
-  p.lanes_per_game = env->lanes_per_game;
-  p.l2_window_bytes = env->l2_window_bytes;
-  p.l2_hit_ratio = env->l2_hit_ratio;
   const grl_reward_config &r = c.reward;
   const float rw[11] = {r.win_game,        r.lose_game,        r.capture_city, r.lose_city, r.capture_general, r.lose_general,
                         r.territory_gained, r.territory_lost, r.army_gained,  r.army_lost, r.army_advantage};
@@ -408,12 +397,8 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
   const size_t act_stride = (size_t)c.max_actions * sizeof(grl_action);
   bool actions_staged = false, zero_copied = false;
   if (do_step && actions && !(flags & GRL_STEP_FLAG_RANDOM_POLICY)) {
-    void *alias = env->zero_copy >= 2 ? pinned_device_alias(actions) : nullptr;
     if (is_device_ptr(actions)) {
       prm.actions = actions;
-    } else if (alias) {
-      prm.actions = alias;  // read in place over PCIe; the call still returns only after the kernel has consumed it
-      zero_copied = true;
     } else {
       void *d = nullptr;
       int st = ensure(env, SL_ACTIONS, B * act_stride, &d);
@@ -436,9 +421,10 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
     const size_t strides[7] = {P * GRL_OBS_CHANNELS * N * 4, P * words * 4, P * 4, 1, 1, 1, P * 4};
     for (int i = 0; i < 7; i++) {
       planes[i].stride = strides[i];
-      const bool small = i >= 2;  // reward, done, winner, step_error, action_index
-      void *alias = (env->zero_copy >= 3 || (env->zero_copy >= 1 && small)) ? pinned_device_alias(user[i]) : nullptr;
-      if (alias) {  // the kernel writes the caller's pinned buffer directly
+      // the small result planes (reward, done, winner, step_error, action_index) are written in place when the caller's
+      // buffers are pinned host memory: no D2H copy (e2e +5 %; writing the observation planes in place cost 10 %)
+      void *alias = i >= 2 ? pinned_device_alias(user[i]) : nullptr;
+      if (alias) {
         planes[i].ob.user = user[i];
         planes[i].ob.dev = alias;
         planes[i].ob.bytes = B * strides[i];
@@ -477,15 +463,15 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
     CUDA_TRY(cudaEventRecord(env->ev_start, env->stream));
   }
   const size_t per = ((B + chunks - 1) / chunks + 7) & ~(size_t)7;
-  void *first_alias = (actions_staged && env->first_in_place) ? pinned_device_alias(actions) : nullptr;
+  void *first_alias = actions_staged ? pinned_device_alias(actions) : nullptr;
   for (int k = 0; k < chunks; k++) {
     const size_t g0 = std::min(B, (size_t)k * per), g1 = std::min(B, g0 + per);
     if (g0 >= g1) continue;
     cudaStream_t sq = chunks > 1 ? env->pipe[k] : env->stream;
     if (chunks > 1) CUDA_TRY(cudaStreamWaitEvent(sq, env->ev_start, 0));
-    // GRL_FIRST_IN_PLACE=1: the first sub-range's kernel reads its actions in place from pinned host memory, so it starts
-    // without waiting for a copy (the other sub-ranges' copies overlap it)
-    const bool first_in_place = actions_staged && k == 0 && chunks > 1 && env->first_in_place && first_alias != nullptr;
+    // the first sub-range's kernel reads its actions in place from pinned host memory, so it starts without waiting for
+    // a copy (the other sub-ranges' copies overlap it)
+    const bool first_in_place = actions_staged && k == 0 && chunks > 1 && first_alias != nullptr;
     if (actions_staged && !first_in_place)
       CUDA_TRY(cudaMemcpyAsync((char *)const_cast<void *>(prm.actions) + g0 * act_stride, (const char *)actions + g0 * act_stride,
                                (g1 - g0) * act_stride, cudaMemcpyHostToDevice, sq));
@@ -575,15 +561,8 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   env->L = grl_make_layout(cfg->width, cfg->height, cfg->num_players);
   int hw = (int)std::thread::hardware_concurrency();
   env->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (hw > 0 ? hw : 1);
-  const char *no_tma = getenv("GRL_NO_TMA");
-  env->use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
   const char *hm = getenv("GRL_HOST_MAPGEN");
   env->host_mapgen = (hm && hm[0] == '1') ? 1 : 0;
-  const char *lpg = getenv("GRL_LANES_PER_GAME");
-  env->lanes_per_game = lpg ? atoi(lpg) : 0;
-  const char *zc = getenv("GRL_ZERO_COPY");
-  env->zero_copy = zc ? atoi(zc) : 1;
-  if (const char *fp = getenv("GRL_FIRST_IN_PLACE")) env->first_in_place = atoi(fp);
   const char *pc = getenv("GRL_PIPE_CHUNKS");
   if (pc && atoi(pc) >= 1) env->pipe_chunks = atoi(pc);
   const char *pf = getenv("GRL_PREFETCH_DIST");
@@ -597,34 +576,12 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   env->stream = env->own_stream;
   const size_t sbytes = (size_t)cfg->num_envs * env->L.slab_words * 4;
   const size_t tbytes = (size_t)cfg->num_envs * env->L.static_words * 4;
-  // one allocation [state | terrain | geometry]: a single L2 access-policy window can cover it
+  // one allocation [state | terrain | geometry]
   const size_t sbytes_al = (sbytes + 255) & ~(size_t)255, tbytes_al = (tbytes + 255) & ~(size_t)255;
   if (cudaMalloc((void **)&env->d_state, sbytes_al + tbytes_al + 96 * 4) != cudaSuccess)
     return bail(fail(GRL_ERR_NOMEM, "cudaMalloc of %zu state bytes: %s", sbytes + tbytes, cudaGetErrorString(cudaGetLastError())));
   env->d_static = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(env->d_state) + sbytes_al);
   env->d_geom = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(env->d_static) + tbytes_al);
-  env->l2_window_bytes = 0;
-  {
-    // Keep the game state resident in the 126 MB L2 across steps when it fits: the observation
-    // stream is written evict-first, the slabs are re-read and re-written every turn.
-    const char *l2 = getenv("GRL_L2_PERSIST");
-    int max_persist = 0, max_window = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cfg->device);
-    // Opt-in (GRL_L2_PERSIST=1): measured 2.3x SLOWER at 65,536 20x20 games on B200 — carving 95 MB
-    // of persisting L2 starves the 2 GB/step observation write stream (profiles/r1_variants.md).
-    if (l2 && l2[0] == '1' && max_persist > 0 && max_window > 0) {
-      size_t want = sbytes_al + tbytes_al;
-      size_t window = want < (size_t)max_window ? want : (size_t)max_window;
-      size_t carve = want < (size_t)max_persist ? want : (size_t)max_persist;
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
-        env->l2_window_bytes = window;
-        env->l2_hit_ratio = carve >= window ? 1.0f : (float)((double)carve / (double)window);
-      } else {
-        cudaGetLastError();
-      }
-    }
-  }
   uint32_t geom[96];
   make_geom(cfg->width, cfg->height, geom);
   if (cudaMemsetAsync(env->d_state, 0, sbytes, env->stream) != cudaSuccess ||

@@ -1,0 +1,538 @@
+// grl_gym.cuh — the generals_gym client's read-outs (python/generals_gym/generals_env.py:291-387 over the proto view of
+// internal/grpc/gameserver/server.go:556-582), written by a whole warp per game.
+#pragma once
+#include "grl_device.cuh"
+
+#define GRL_GYM_EMIT_GENERIC 0
+#define GRL_GYM_EMIT_QUADS 1
+#define GRL_GYM_EMIT_LINEAR 2
+// which read-out writer a geometry uses: baked boards with N % 4 == 0 -> quads, other baked boards -> linear
+__host__ __device__ constexpr int grl_gym_emit_mode(int TW, int TH) {
+  return TW > 0 ? (((TW * TH) & 3) == 0 ? GRL_GYM_EMIT_QUADS : GRL_GYM_EMIT_LINEAR) : GRL_GYM_EMIT_GENERIC;
+}
+
+// generals_gym read-outs, warp-per-game version: the game's masks are staged once in shared memory
+// and every player's [9][N] observation block is written as one linear, 16-byte aligned sweep of
+// 128-bit stores (as the turn kernel's observation writer does); the N*5 mask bytes go out as an
+// aligned 32-bit sweep.  Shared-memory words per warp: see grl_gym_smem_words().
+__host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N, int mode) {
+  const int PT = P <= 2 ? 2 : (P <= 4 ? 4 : 8);
+  int m;
+  if (mode == GRL_GYM_EMIT_QUADS) {  // gym_emit_quads: dir rows + one player's mask words
+    m = PT * 4 * NW + 5 * ((N + 3) / 4);
+  } else if (mode == GRL_GYM_EMIT_LINEAR) {  // gym_emit_linear: dir rows + (channel masks + log plane | the game's mask bytes)
+    const int lin_obs = (((PT * GRL_GYM_CHANNELS + PT) * (NW + 1) + N + 4 + 3) & ~3) + 4 * PT * GRL_GYM_CHANNELS + 4;
+    const int lin_mask = (P * N * 5 + 8 + 3) / 4;
+    m = PT * 4 * NW + (lin_obs > lin_mask ? lin_obs : lin_mask);
+  } else {  // gym_emit
+    m = (3 * P + 5 + 5 * P) * (NW + 1) + N + 4;
+  }
+  return (m + 3) & ~3;
+}
+
+struct GymPlanes {  // shared-memory views of one game (each mask has NW + 1 words, the last one zero)
+  const uint32_t *vis, *mine, *enemy;  // [P][NWP]
+  const uint32_t *normal, *M, *C, *G;  // [NWP]
+  const float *logv;                   // [N + 4]
+  float tf;
+  int NWP, N;
+};
+
+__device__ __forceinline__ float gym_value(const GymPlanes &g, int p, int plane, int t) {
+  const int w = t >> 5, b = t & 31;
+  switch (plane) {
+    case 0: return ((g.vis[p * g.NWP + w] >> b) & 1u) ? 1.f : 0.f;
+    case 1: return ((g.mine[p * g.NWP + w] >> b) & 1u) ? 0.5f : (((g.enemy[p * g.NWP + w] >> b) & 1u) ? 1.f : 0.f);
+    case 2: return ((g.vis[p * g.NWP + w] >> b) & 1u) ? g.logv[t] : 0.f;
+    case 3: return ((g.normal[w] >> b) & 1u) ? 1.f : 0.f;
+    case 4: return ((g.M[w] >> b) & 1u) ? 1.f : 0.f;
+    case 5: return ((g.C[w] >> b) & 1u) ? 1.f : 0.f;
+    case 6: return ((g.G[w] >> b) & 1u) ? 1.f : 0.f;
+    case 7: return g.tf;
+    default: return 0.f;
+  }
+}
+
+__device__ __forceinline__ uint32_t nib_at(const uint32_t *m, int t) {
+  return __funnelshift_r(m[t >> 5], m[(t >> 5) + 1], t & 31) & 0xfu;
+}
+#define GYM_NIB4(n, a) make_float4(((n)&1u) ? (a) : 0.f, ((n)&2u) ? (a) : 0.f, ((n)&4u) ? (a) : 0.f, ((n)&8u) ? (a) : 0.f)
+
+__device__ __forceinline__ float4 gym_value4(const GymPlanes &g, int p, int plane, int t) {  // t + 3 < N
+  switch (plane) {
+    case 0: { const uint32_t n = nib_at(g.vis + p * g.NWP, t); return GYM_NIB4(n, 1.f); }
+    case 1: {
+      const uint32_t a = nib_at(g.mine + p * g.NWP, t), e = nib_at(g.enemy + p * g.NWP, t);
+      return make_float4((a & 1u) ? 0.5f : ((e & 1u) ? 1.f : 0.f), (a & 2u) ? 0.5f : ((e & 2u) ? 1.f : 0.f),
+                         (a & 4u) ? 0.5f : ((e & 4u) ? 1.f : 0.f), (a & 8u) ? 0.5f : ((e & 8u) ? 1.f : 0.f));
+    }
+    case 2: {
+      const uint32_t n = nib_at(g.vis + p * g.NWP, t);
+      return make_float4((n & 1u) ? g.logv[t] : 0.f, (n & 2u) ? g.logv[t + 1] : 0.f, (n & 4u) ? g.logv[t + 2] : 0.f,
+                         (n & 8u) ? g.logv[t + 3] : 0.f);
+    }
+    case 3: { const uint32_t n = nib_at(g.normal, t); return GYM_NIB4(n, 1.f); }
+    case 4: { const uint32_t n = nib_at(g.M, t); return GYM_NIB4(n, 1.f); }
+    case 5: { const uint32_t n = nib_at(g.C, t); return GYM_NIB4(n, 1.f); }
+    case 6: { const uint32_t n = nib_at(g.G, t); return GYM_NIB4(n, 1.f); }
+    case 7: return make_float4(g.tf, g.tf, g.tf, g.tf);
+    default: return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// One game's gym read-outs by a whole warp.  `s` / `stt` are the game's slab and terrain words (global
+// memory in grl_gym_warp_kernel, the shared-memory copy in the fused gym step); `sw` is the warp's
+// scratch of grl_gym_smem_words() words; `g` is the full-warp (LG = 32) geometry.  NT > 0 bakes the tile
+// count in (the element -> (plane, tile) divisions become multiplications).
+template <int NT>
+__device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+                                         float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats,
+                                         const uint32_t *s, const uint32_t *stt, uint32_t *sw, int game, int lane,
+                                         const Geo &g) {
+  const GrlLayout &L = prm.L;
+  const int N = NT ? NT : prm.N, P = prm.P, NW = NT ? (NT + 31) / 32 : prm.NW, NWP = NW + 1;
+  uint32_t *s_vis = sw, *s_mine = s_vis + P * NWP, *s_enemy = s_mine + P * NWP;
+  uint32_t *s_normal = s_enemy + P * NWP, *s_M = s_normal + NWP, *s_C = s_M + NWP, *s_G = s_C + NWP, *s_pad = s_G + NWP;
+  uint32_t *s_dir = s_pad + NWP;  // [P][5][NWP]: up, right, down, left, any
+  float *s_logv = reinterpret_cast<float *>(s_dir + 5 * P * NWP);
+  {
+    const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+    const bool w = lane < NW;
+    const uint32_t M = w ? stt[lane] : 0u, C = w ? stt[NW + lane] : 0u, G = w ? stt[2 * NW + lane] : 0u;
+    uint32_t any_own = 0;
+    for (int p = 0; p < P; p++) any_own |= w ? s[L.off_own + p * NW + lane] : 0u;
+    const uint32_t gt1 = army_gt1_mask<32>(army, NW, N, g);
+    const DirMasks dm = dir_targets<32>(M, g);
+    if (lane < NWP) {
+      s_normal[lane] = g.valid & ~(M | C | G) & (w ? ~0u : 0u);
+      s_M[lane] = M;
+      s_C[lane] = C;
+      s_G[lane] = G;
+    }
+    for (int p = 0; p < P; p++) {
+      const uint32_t own = w ? s[L.off_own + p * NW + lane] : 0u;
+      const uint32_t v = w ? (prm.fog ? s[L.off_vis + p * NW + lane] : g.valid) : 0u;
+      const uint32_t mine = v & own, src = mine & gt1;
+      if (lane < NWP) {
+        s_vis[p * NWP + lane] = v;
+        s_mine[p * NWP + lane] = mine;
+        s_enemy[p * NWP + lane] = v & any_own & ~own;
+        uint32_t *d = s_dir + p * 5 * NWP + lane;
+        const uint32_t up = src & dm.up, right = src & dm.right, down = src & dm.down, left = src & dm.left;
+        d[0 * NWP] = up;
+        d[1 * NWP] = right;
+        d[2 * NWP] = down;
+        d[3 * NWP] = left;
+        d[4 * NWP] = up | right | down | left;
+      }
+    }
+    for (int t = lane; t < N + 4; t += 32) s_logv[t] = t < N ? logtab[army[t]] : 0.f;  // logtab[0] == 0
+    __syncwarp();
+
+    GymPlanes gp;
+    gp.vis = s_vis;
+    gp.mine = s_mine;
+    gp.enemy = s_enemy;
+    gp.normal = s_normal;
+    gp.M = s_M;
+    gp.C = s_C;
+    gp.G = s_G;
+    gp.logv = s_logv;
+    gp.NWP = NWP;
+    gp.N = N;
+    gp.tf = fminf(__fdiv_rn((float)s[GRL_HDR_TURN], (float)max_turns), 1.0f);
+    if (obs) {
+      const int block = GRL_GYM_CHANNELS * N;  // floats per (game, player)
+      for (int p = 0; p < P; p++) {
+        const size_t off = ((size_t)game * P + p) * block;
+        float *base = obs + off;
+        const int head = (int)((4u - (uint32_t)(off & 3u)) & 3u);
+        const int body4 = (block - head) / 4, tail0 = head + 4 * body4;
+        if (lane < head) __stcs(base + lane, gym_value(gp, p, lane / N, lane % N));
+        if (lane < block - tail0) __stcs(base + tail0 + lane, gym_value(gp, p, (tail0 + lane) / N, (tail0 + lane) % N));
+        float4 *body = reinterpret_cast<float4 *>(base + head);
+        for (int i = lane; i < body4; i += 32) {
+          const int e = head + 4 * i, plane = e / N, t = e - plane * N;
+          float4 val;
+          if (t + 3 < N) {
+            val = gym_value4(gp, p, plane, t);
+          } else {
+            val.x = gym_value(gp, p, plane, t);
+            val.y = gym_value(gp, p, (e + 1) / N, (e + 1) % N);
+            val.z = gym_value(gp, p, (e + 2) / N, (e + 2) % N);
+            val.w = gym_value(gp, p, (e + 3) / N, (e + 3) % N);
+          }
+          __stcs(body + i, val);
+        }
+      }
+    }
+    if (mask) {
+      const int bytes = N * 5;
+      for (int p = 0; p < P; p++) {
+        const uint32_t *d = s_dir + p * 5 * NWP;
+        const size_t off = ((size_t)game * P + p) * bytes;
+        uint8_t *base = mask + off;
+        auto flag = [&](int j) -> uint32_t {  // byte j = direction j%5 of tile j/5
+          const int t = j / 5, k = j - 5 * t;
+          return (d[k * NWP + (t >> 5)] >> (t & 31)) & 1u;
+        };
+        const int head = (int)((4u - (uint32_t)(off & 3u)) & 3u);
+        const int body4 = (bytes - head) / 4, tail0 = head + 4 * body4;
+        if (lane < head) base[lane] = (uint8_t)flag(lane);
+        if (lane < bytes - tail0) base[tail0 + lane] = (uint8_t)flag(tail0 + lane);
+        uint32_t *body = reinterpret_cast<uint32_t *>(base + head);
+        for (int i = lane; i < body4; i += 32) {
+          const int j = head + 4 * i;
+          body[i] = flag(j) | (flag(j + 1) << 8) | (flag(j + 2) << 16) | (flag(j + 3) << 24);
+        }
+      }
+    }
+    if (stats && lane < P) {
+      int tiles = 0;
+      for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + lane * NW + k]);
+      int32_t *so = stats + ((size_t)game * P + lane) * 4;
+      so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ARMY_COUNT];
+      so[1] = tiles;
+      so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> lane) & 1u);
+      so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_GENERAL_IDX];
+    }
+    __syncwarp();
+  }
+}
+
+// The same read-outs for baked boards with N % 4 == 0 (10x10, 20x20), from the slab in SHARED memory, in the
+// plane-major order of obs_plane_major: lane l owns the tile quads q = l + 32c, reads every mask's nibble for its
+// quads once (packed 4 bits per chunk), converts its quads' armies once, and the warp writes the game's
+// [P][9][N] block as one linear sweep of 128-bit stores with compile-time addressing.  The N*5 mask bytes of a
+// player (tile-major, {up,right,down,left,any} per tile) are 20 bytes per quad: a lane assembles its five words,
+// the warp stages them in shared memory and copies them out as a linear sweep.
+template <int PT, int N>
+__device__ __forceinline__ void gym_emit_quads(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+                                               float *__restrict__ obs, uint8_t *__restrict__ mask,
+                                               int32_t *__restrict__ stats, const uint32_t *s, const uint32_t *stt,
+                                               const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g) {
+  static_assert(N % 4 == 0 && N <= 512, "quads of four tiles, at most four chunks of 32 quads");
+  constexpr int NQ = N / 4, NCH = (NQ + 31) / 32, NW = (N + 31) / 32;
+  const GrlLayout &L = prm.L;
+  const int P = prm.P;
+  const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+  const bool w = lane < NW;
+  // ---- the four direction masks of every player in word layout -> shared memory [P][4][NW] ------------
+  uint32_t *s_dir = sw, *s_stage = sw + PT * 4 * NW;
+  if (mask) {
+    const uint32_t M = w ? stt[lane] : 0u;
+    const uint32_t gt1 = army_gt1_mask<32>(army, NW, N, g);
+    const DirMasks dm = dir_targets<32>(M, g);
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      if (p < P && w) {
+        const uint32_t own = s[L.off_own + p * NW + lane];
+        const uint32_t v = prm.fog ? s[L.off_vis + p * NW + lane] : g.valid;
+        const uint32_t src = v & own & gt1;
+        s_dir[(p * 4 + 0) * NW + lane] = src & dm.up;
+        s_dir[(p * 4 + 1) * NW + lane] = src & dm.right;
+        s_dir[(p * 4 + 2) * NW + lane] = src & dm.down;
+        s_dir[(p * 4 + 3) * NW + lane] = src & dm.left;
+      }
+    }
+    __syncwarp();
+  }
+  // ---- nibbles of this lane's quads ---------------------------------------------------------------------
+  const int bsel = lane >> 1, bsh = 4 * (lane & 1);  // quad q -> byte q>>1, nibble q&1 of a mask's byte array
+  const uint8_t *bM = reinterpret_cast<const uint8_t *>(stt);
+  const uint8_t *bC = reinterpret_cast<const uint8_t *>(stt + NW);
+  const uint8_t *bG = reinterpret_cast<const uint8_t *>(stt + 2 * NW);
+  uint32_t mM = 0, mC = 0, mG = 0, mAny = 0, livem = 0;
+  uint32_t nV[PT], nO[PT];
+#pragma unroll
+  for (int p = 0; p < PT; p++) nV[p] = nO[p] = 0;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    if (32 * c + lane < NQ) {
+      const int b = 16 * c + bsel;
+      livem |= 0xfu << (4 * c);
+      mM |= ((bM[b] >> bsh) & 0xfu) << (4 * c);
+      mC |= ((bC[b] >> bsh) & 0xfu) << (4 * c);
+      mG |= ((bG[b] >> bsh) & 0xfu) << (4 * c);
+#pragma unroll
+      for (int p = 0; p < PT; p++) {
+        if (p < P) {
+          const uint8_t *bo = reinterpret_cast<const uint8_t *>(s + L.off_own + p * NW);
+          const uint8_t *bv = reinterpret_cast<const uint8_t *>(s + L.off_vis + p * NW);
+          nO[p] |= ((bo[b] >> bsh) & 0xfu) << (4 * c);
+          nV[p] |= ((bv[b] >> bsh) & 0xfu) << (4 * c);
+        }
+      }
+    }
+  }
+  uint32_t seen = 0;  // tiles some player sees: the only ones whose army reaches an observation
+#pragma unroll
+  for (int p = 0; p < PT; p++) {
+    mAny |= nO[p];
+    if (!prm.fog) nV[p] = livem;
+    seen |= nV[p];
+  }
+  if (obs) {
+    float f[NCH][4];  // log(army + 1) / 10 of the lane's quads
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      f[c][0] = f[c][1] = f[c][2] = f[c][3] = 0.f;
+      if ((seen >> (4 * c)) & 0xfu) {
+        const uint2 aw = *reinterpret_cast<const uint2 *>(army + 4 * (32 * c + lane));
+        f[c][0] = __ldg(logtab + (aw.x & 0xffffu));
+        f[c][1] = __ldg(logtab + (aw.x >> 16));
+        f[c][2] = __ldg(logtab + (aw.y & 0xffffu));
+        f[c][3] = __ldg(logtab + (aw.y >> 16));
+      }
+    }
+    const float tf = fminf(__fdiv_rn((float)s[GRL_HDR_TURN], (float)max_turns), 1.0f);
+    const float4 tf4 = make_float4(tf, tf, tf, tf), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const char *lutb = reinterpret_cast<const char *>(lut);
+    auto nib4 = [&](uint32_t field, int c) -> float4 {  // chunk c's nibble of a packed field -> four 0/1 floats
+      const uint32_t idx16 = (c == 0 ? (field << 4) : (field >> (4 * c - 4))) & 0xf0u;
+      return *reinterpret_cast<const float4 *>(lutb + idx16);
+    };
+    float4 *gq = reinterpret_cast<float4 *>(obs + (size_t)game * P * GRL_GYM_CHANNELS * N) + lane;
+    const uint32_t mN = livem & ~(mM | mC | mG);
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      if (p < P) {
+        const uint32_t v = nV[p], mine = v & nO[p], enemy = v & mAny & ~nO[p];
+        float4 *gp = gq + p * GRL_GYM_CHANNELS * NQ;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+          if (32 * c + lane < NQ) {
+            const float4 vv = nib4(v, c), a = nib4(mine, c), e = nib4(enemy, c);
+            __stcs(gp + 0 * NQ + 32 * c, vv);
+            // ownership: 0.5 own, 1.0 enemy (mine and enemy are disjoint)
+            __stcs(gp + 1 * NQ + 32 * c, make_float4(__fmaf_rn(a.x, 0.5f, e.x), __fmaf_rn(a.y, 0.5f, e.y),
+                                                     __fmaf_rn(a.z, 0.5f, e.z), __fmaf_rn(a.w, 0.5f, e.w)));
+            __stcs(gp + 2 * NQ + 32 * c, make_float4(vv.x * f[c][0], vv.y * f[c][1], vv.z * f[c][2], vv.w * f[c][3]));
+            __stcs(gp + 3 * NQ + 32 * c, nib4(mN, c));
+            __stcs(gp + 4 * NQ + 32 * c, nib4(mM, c));
+            __stcs(gp + 5 * NQ + 32 * c, nib4(mC, c));
+            __stcs(gp + 6 * NQ + 32 * c, nib4(mG, c));
+            __stcs(gp + 7 * NQ + 32 * c, tf4);
+            __stcs(gp + 8 * NQ + 32 * c, zero4);
+          }
+        }
+      }
+    }
+  }
+  if (mask) {
+    constexpr int MW = 5 * NQ;  // words of one player's mask
+    for (int p = 0; p < P; p++) {
+      const uint8_t *bd = reinterpret_cast<const uint8_t *>(s_dir + p * 4 * NW);
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        const int q = 32 * c + lane;
+        if (q < NQ) {
+          const int b = 16 * c + bsel;
+          const uint32_t U = (bd[b] >> bsh) & 0xfu, R = (bd[4 * NW + b] >> bsh) & 0xfu;
+          const uint32_t D = (bd[8 * NW + b] >> bsh) & 0xfu, Lm = (bd[12 * NW + b] >> bsh) & 0xfu, A = U | R | D | Lm;
+          // byte 5i+k of the quad = direction k of its tile i:  U0 R0 D0 L0 | A0 U1 R1 D1 | L1 A1 U2 R2 | D2 L2 A2 U3 | R3 D3 L3 A3.
+          // Each nibble is spread to one 0/1 byte per tile (a multiply and a mask), then five byte permutes
+          // pairs interleave the direction words into the 5-byte records.
+          auto spread = [](uint32_t n) -> uint32_t { return (n * 0x00204081u) & 0x01010101u; };
+          const uint32_t Ub = spread(U), Rb = spread(R), Db = spread(D), Lb = spread(Lm), Ab = spread(A);
+          const uint32_t UR = __byte_perm(Ub, Rb, 0x5140), URh = __byte_perm(Ub, Rb, 0x7362);  // U0 R0 U1 R1 | U2 R2 U3 R3
+          const uint32_t DL = __byte_perm(Db, Lb, 0x5140), DLh = __byte_perm(Db, Lb, 0x7362);  // D0 L0 D1 L1 | D2 L2 D3 L3
+          uint32_t *o = s_stage + 5 * q;
+          o[0] = __byte_perm(UR, DL, 0x5410);
+          o[1] = __byte_perm(__byte_perm(UR, DL, 0x6320), Ab, 0x3214);
+          o[2] = __byte_perm(__byte_perm(DL, URh, 0x5403), Ab, 0x3250);
+          o[3] = __byte_perm(__byte_perm(DLh, URh, 0x6010), Ab, 0x3610);
+          o[4] = __byte_perm(__byte_perm(URh, DLh, 0x0763), Ab, 0x7210);
+        }
+      }
+      __syncwarp();
+      uint8_t *base = mask + ((size_t)game * P + p) * (size_t)(N * 5);
+      if constexpr (MW % 4 == 0) {
+        uint4 *dst = reinterpret_cast<uint4 *>(base);
+        const uint4 *src = reinterpret_cast<const uint4 *>(s_stage);
+        for (int i = lane; i < MW / 4; i += 32) __stcs(dst + i, src[i]);
+      } else {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(base);
+        for (int i = lane; i < MW; i += 32) __stcs(dst + i, s_stage[i]);
+      }
+      __syncwarp();
+    }
+  }
+  if (stats && lane < P) {
+    int tiles = 0;
+    for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + lane * NW + k]);
+    int32_t *so = stats + ((size_t)game * P + lane) * 4;
+    so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ARMY_COUNT];
+    so[1] = tiles;
+    so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> lane) & 1u);
+    so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_GENERAL_IDX];
+  }
+  __syncwarp();
+}
+
+// The same read-outs for baked boards with N % 4 != 0 (15x15), from the slab in SHARED memory: like obs_linear,
+// the game's [P][9][N] block is one linear, 16-byte aligned sweep of 128-bit stores addressed by position in the
+// block (plane = e / N, tile = e % N, compile-time N), a 4-bit window of the plane's staged channel mask going
+// through the nibble table.  The game's [P][N*5] mask bytes are assembled per tile in shared memory, pre-shifted
+// by the block's misalignment, and leave as an aligned 32-bit sweep.
+template <int PT, int N>
+__device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+                                                float *__restrict__ obs, uint8_t *__restrict__ mask,
+                                                int32_t *__restrict__ stats, const uint32_t *s, const uint32_t *stt,
+                                                const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g) {
+  constexpr int NW = (N + 31) / 32, NWP = NW + 1, CH = GRL_GYM_CHANNELS;
+  const GrlLayout &L = prm.L;
+  const int P = prm.P;
+  const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+  uint32_t *s_dir = sw;                                          // [PT][4][NW]
+  uint32_t *chm = sw + PT * 4 * NW;                              // [PT*9][NWP] channel masks
+  uint32_t *minem = chm + PT * CH * NWP;                         // [PT][NWP]   own tiles in sight (the 0.5 of plane 1)
+  float *logv = reinterpret_cast<float *>(minem + PT * NWP);     // [N + 4]
+  float4 *sf = reinterpret_cast<float4 *>(sw + ((PT * 4 * NW + (PT * CH + PT) * NWP + N + 4 + 3) & ~3));  // [PT*9] straddlers
+  uint8_t *stage = reinterpret_cast<uint8_t *>(chm);             // the mask bytes reuse the observation staging
+  const bool w = lane < NW;
+  const uint32_t M = w ? stt[lane] : 0u, C = w ? stt[NW + lane] : 0u, G = w ? stt[2 * NW + lane] : 0u;
+  if (mask) {
+    const uint32_t gt1 = army_gt1_mask<32>(army, NW, N, g);
+    const DirMasks dm = dir_targets<32>(M, g);
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      if (p < P && w) {
+        const uint32_t own = s[L.off_own + p * NW + lane];
+        const uint32_t v = prm.fog ? s[L.off_vis + p * NW + lane] : g.valid;
+        const uint32_t src = v & own & gt1;
+        s_dir[(p * 4 + 0) * NW + lane] = src & dm.up;
+        s_dir[(p * 4 + 1) * NW + lane] = src & dm.right;
+        s_dir[(p * 4 + 2) * NW + lane] = src & dm.down;
+        s_dir[(p * 4 + 3) * NW + lane] = src & dm.left;
+      }
+    }
+  }
+  if (obs) {
+    if (lane < NWP) {
+      const uint32_t valid = w ? g.valid : 0u;
+      uint32_t any_own = 0;
+#pragma unroll
+      for (int p = 0; p < PT; p++)
+        if (p < P && w) any_own |= s[L.off_own + p * NW + lane];
+#pragma unroll
+      for (int p = 0; p < PT; p++) {
+        if (p < P) {
+          const uint32_t own = w ? s[L.off_own + p * NW + lane] : 0u;
+          const uint32_t v = w ? (prm.fog ? s[L.off_vis + p * NW + lane] : valid) : 0u;
+          uint32_t *c = chm + p * CH * NWP + lane;
+          c[0 * NWP] = v;
+          c[1 * NWP] = v & any_own & ~own;  // enemy -> 1.0; own tiles come from minem -> 0.5
+          c[2 * NWP] = v;                   // x log(army + 1) / 10
+          c[3 * NWP] = valid & ~(M | C | G);
+          c[4 * NWP] = M;
+          c[5 * NWP] = C;
+          c[6 * NWP] = G;
+          c[7 * NWP] = valid;               // x turn / max_turns
+          c[8 * NWP] = 0u;
+          minem[p * NWP + lane] = v & own;
+        }
+      }
+    }
+    for (int t = lane; t < N + 4; t += 32) logv[t] = t < N ? __ldg(logtab + army[t]) : 0.f;  // logtab[0] == 0
+    __syncwarp();
+
+    const float tf = fminf(__fdiv_rn((float)s[GRL_HDR_TURN], (float)max_turns), 1.0f);
+    auto elem = [&](int e) -> float {
+      const int plane = e / N, t = e - plane * N, k = plane % CH;
+      const uint32_t bit = (chm[plane * NWP + (t >> 5)] >> (t & 31)) & 1u;
+      if (k == 1) return ((minem[(plane / CH) * NWP + (t >> 5)] >> (t & 31)) & 1u) ? 0.5f : (bit ? 1.f : 0.f);
+      if (k == 2) return bit ? logv[t] : 0.f;
+      if (k == 7) return tf;
+      return bit ? 1.f : 0.f;
+    };
+    const int total = P * CH * N;  // floats in this game's block
+    float *base = obs + (size_t)game * total;
+    const int head = (int)((4u - (uint32_t)(((size_t)game * total) & 3u)) & 3u);
+    const int body4 = (total - head) / 4;
+    const int tail0 = head + 4 * body4;
+    if (lane < head) __stcs(base + lane, elem(lane));
+    if (lane < total - tail0) __stcs(base + tail0 + lane, elem(tail0 + lane));
+    const char *lutb = reinterpret_cast<const char *>(lut);
+    float4 *body = reinterpret_cast<float4 *>(base + head);
+    for (int j = lane; j < P * CH - 1; j += 32) {  // the float4s that straddle two planes
+      const int b = (j + 1) * N - head;
+      if ((b & 3) && (b >> 2) < body4) {
+        const int e = head + (b & ~3);
+        sf[j] = make_float4(elem(e), elem(e + 1), elem(e + 2), elem(e + 3));
+      }
+    }
+    __syncwarp();
+#pragma unroll 2
+    for (int i = lane; i < body4; i += 32) {
+      const int e = head + 4 * i;
+      const int plane = e / N, t = e - plane * N;
+      const int k = plane % CH;
+      const uint32_t *wp = chm + plane * NWP + (t >> 5);
+      uint32_t nib = __funnelshift_r(wp[0], wp[1], t & 31) & 0xfu;  // rows are zero from bit N on
+      float4 val;
+      if (t + 3 < N) {
+        val = *reinterpret_cast<const float4 *>(lutb + nib * 16u);
+        if (k == 1) {
+          const uint32_t *mp = minem + (plane / CH) * NWP + (t >> 5);
+          const uint32_t nb2 = __funnelshift_r(mp[0], mp[1], t & 31) & 0xfu;
+          const float4 m = *reinterpret_cast<const float4 *>(lutb + nb2 * 16u);
+          val = make_float4(__fmaf_rn(m.x, 0.5f, val.x), __fmaf_rn(m.y, 0.5f, val.y), __fmaf_rn(m.z, 0.5f, val.z),
+                            __fmaf_rn(m.w, 0.5f, val.w));
+        } else if (k == 2) {
+          if (nib) {
+            val.x *= logv[t];
+            val.y *= logv[t + 1];
+            val.z *= logv[t + 2];
+            val.w *= logv[t + 3];
+          }
+        } else if (k == 7) {
+          val = make_float4(tf, tf, tf, tf);
+        }
+      } else {
+        val = sf[plane];  // evaluated before the sweep, one per lane (see obs_linear)
+      }
+      __stcs(body + i, val);
+    }
+  }
+  __syncwarp();
+  if (mask) {
+    const int total = P * N * 5;  // bytes of this game's block [P][N*5]
+    const size_t goff = (size_t)game * total;
+    const int mis = (int)(goff & 3u);
+    for (int p = 0; p < P; p++) {
+      const uint32_t *d = s_dir + p * 4 * NW;
+      for (int t = lane; t < N; t += 32) {
+        const int wd = t >> 5, b = t & 31;
+        const uint32_t U = (d[wd] >> b) & 1u, R = (d[NW + wd] >> b) & 1u, D = (d[2 * NW + wd] >> b) & 1u,
+                       Lm = (d[3 * NW + wd] >> b) & 1u;
+        uint8_t *o = stage + mis + (p * N + t) * 5;
+        o[0] = (uint8_t)U;
+        o[1] = (uint8_t)R;
+        o[2] = (uint8_t)D;
+        o[3] = (uint8_t)Lm;
+        o[4] = (uint8_t)(U | R | D | Lm);
+      }
+    }
+    __syncwarp();
+    uint8_t *base = mask + goff;
+    const int head = (4 - mis) & 3;
+    const int body4 = (total - head) / 4, tail0 = head + 4 * body4;
+    if (lane < head) base[lane] = stage[mis + lane];
+    if (lane < total - tail0) base[tail0 + lane] = stage[mis + tail0 + lane];
+    uint32_t *dst = reinterpret_cast<uint32_t *>(base + head);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(stage + mis + head);
+    for (int i = lane; i < body4; i += 32) __stcs(dst + i, src[i]);
+  }
+  if (stats && lane < P) {
+    int tiles = 0;
+    for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + lane * NW + k]);
+    int32_t *so = stats + ((size_t)game * P + lane) * 4;
+    so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ARMY_COUNT];
+    so[1] = tiles;
+    so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> lane) & 1u);
+    so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_GENERAL_IDX];
+  }
+  __syncwarp();
+}
+#undef GYM_NIB4

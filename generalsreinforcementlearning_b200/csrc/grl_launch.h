@@ -5,6 +5,15 @@
 #include "grl_layout.h"
 
 cudaError_t grl_launch_turn(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream);
+// per-geometry instantiations (grl_turn_*.cu)
+cudaError_t grl_launch_turn_20x20(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream);
+cudaError_t grl_launch_turn_15x15(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream);
+cudaError_t grl_launch_turn_10x10(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream);
+cudaError_t grl_launch_turn_generic(const GrlKParams &prm, bool do_step, bool do_out, cudaStream_t stream);
+cudaError_t grl_launch_gym_step_20x20(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream);
+cudaError_t grl_launch_gym_step_15x15(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream);
+cudaError_t grl_launch_gym_step_10x10(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream);
+cudaError_t grl_launch_gym_step_generic(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream);
 cudaError_t grl_launch_reset(const GrlKParams &prm, const uint32_t *src_state, const uint32_t *src_static,
                              const int32_t *env_ids, int n, cudaStream_t stream, const int *n_dev = nullptr);
 cudaError_t grl_launch_gym_compact(const GrlKParams &prm, const uint8_t *terminated, const uint8_t *truncated, long long base_seed,

@@ -86,13 +86,8 @@ struct GrlKParams {
   GrlLayout L;
   int fog, pg, pc, pn, grow_interval;
   int env_id_base;
-  int use_tma;
-  int prefetch_dist;
-  int lanes_per_game;       // host-side launch hint: 32 forces one game per warp (0 = sized to the board)
+  int prefetch_dist;        // > 0: the warp of game g prefetches the slab of game g + dist into L2
   float rw[11];
-  // host-side launch hints (not read by device code)
-  unsigned long long l2_window_bytes;
-  float l2_hit_ratio;
 };
 
 // Second parameter block of the turn kernel, read only by its fused gym-step instantiation

@@ -59,7 +59,7 @@ def main():
     alg = algorithmic_bytes_per_env_step(W, H, P)["total"]
     fused = res["fused(obs+mask+reward+done)"]
     print(json.dumps({"config": [W, H, P, B], "bytes_per_env_step": alg,
-                      "fused_GBs": round(alg * B / fused / 1e6, 1), "fused_Msteps": round(B / fused / 1e3, 1), "tma": os.environ.get("GRL_NO_TMA", "0") != "1",
+                      "fused_GBs": round(alg * B / fused / 1e6, 1), "fused_Msteps": round(B / fused / 1e3, 1),
                       "prefetch": os.environ.get("GRL_PREFETCH_DIST", "default"), "ms_per_launch": res}))
 
 
