@@ -351,3 +351,101 @@ __device__ __forceinline__ PackedAction sample_policy_action(const GrlKParams &p
   return pack_action(p, fx, fy, tx, ty, ((r >> 32) & 1ULL) != 0);
 }
 
+// ---- bit streams in shared memory (the linear read-out writers of grl_obs.cuh / grl_gym.cuh) ---------------------------
+__device__ __forceinline__ uint32_t lds32(uint32_t sa) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t sa) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa));
+  return v;
+}
+__device__ __forceinline__ uint32_t rotl4(uint32_t v) { return __funnelshift_l(v, v, 4); }
+// a value the compiler must keep in a register instead of recomputing it at every use (shared-window addresses are
+// otherwise rematerialised inside the store loops: S2R + MOV + VIADD + LEA per access)
+__device__ __forceinline__ uint32_t pinned_reg(uint32_t v) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(v));
+  return v;
+}
+
+// The linear sweep of the bit-stream writers.  Lane l writes float4 k = k0 + l + 32 r of the run in round r: the 4-bit
+// field of its four floats sits at the same offset `sh` of a stream word in every round (words are stored rotated left by
+// 4, so rotating right by sh leaves 16 * field at bits 4-7: the byte offset of the field's entry in the 256-byte aligned
+// nibble -> float4 table).  Rounds are issued four at a time whenever all four are whole: the loads of a group are
+// independent, which hides the shared-memory latency a single round would expose.
+struct StreamSweep {
+  uint32_t lut_sa, sp;  // shared-window addresses: the table, this lane's stream word of the current round
+  int sh, k, k_end;     // field offset; this lane's float4 index in the current round; one past the last float4
+  float4 *op;           // this lane's float4 of the current round
+  __device__ __forceinline__ void init(const float4 *lut, const uint32_t *strm, float *base_al, int k_first, int k_end_, int lane) {
+    lut_sa = pinned_reg(smem_addr(lut));
+    sh = 4 * ((k_first + lane) & 7);
+    k = k_first + lane;
+    k_end = k_end_;
+    sp = smem_addr(strm) + 4u * (uint32_t)(k >> 3);
+    op = reinterpret_cast<float4 *>(base_al) + k;
+  }
+  __device__ __forceinline__ float4 entry(uint32_t w) const { return lds128(lut_sa | (__funnelshift_r(w, w, sh) & 0xf0u)); }
+  __device__ __forceinline__ int round_base(int lane) const { return k - lane; }  // first float4 of the current round
+  __device__ __forceinline__ void advance(int rounds) { k += 32 * rounds, sp += 16u * rounds, op += 32 * rounds; }
+  // `rounds` rounds of plain 0/1 floats
+  __device__ __forceinline__ void plain(int rounds, int lane) {
+    int r = 0;
+    for (; r + 4 <= rounds && round_base(lane) + 127 < k_end; r += 4) {
+      const uint32_t w0 = lds32(sp), w1 = lds32(sp + 16), w2 = lds32(sp + 32), w3 = lds32(sp + 48);
+      const float4 v0 = entry(w0), v1 = entry(w1), v2 = entry(w2), v3 = entry(w3);
+      __stcs(op, v0);
+      __stcs(op + 32, v1);
+      __stcs(op + 64, v2);
+      __stcs(op + 96, v3);
+      advance(4);
+    }
+    for (; r < rounds; r++) {
+      if (k < k_end) __stcs(op, entry(lds32(sp)));
+      advance(1);
+    }
+  }
+  // the rounds that overlap floats [qa, qz] of the run: their float4s take multipliers from F (F4[0] = float4 qa >> 2)
+  __device__ __forceinline__ void scaled(int qa, int qz, uint32_t F_sa, int lane) {
+    const int ka = qa >> 2, kz = qz >> 2;
+    const int rounds = ((kz - round_base(lane)) >> 5) + 1;
+    for (int r = 0; r < rounds; r++) {
+      if (k < k_end) {
+        float4 val = entry(lds32(sp));
+        if (k >= ka && k <= kz) {
+          const float4 m = lds128(F_sa + 16u * (uint32_t)(k - ka));
+          val.x *= m.x;
+          val.y *= m.y;
+          val.z *= m.z;
+          val.w *= m.w;
+        }
+        __stcs(op, val);
+      }
+      advance(1);
+    }
+  }
+  __device__ __forceinline__ int rounds_before(int q, int lane) const {  // whole rounds before the one that holds float q
+    const int kb0 = round_base(lane), ka = q >> 2;
+    return ka > kb0 ? (ka - kb0) >> 5 : 0;
+  }
+  __device__ __forceinline__ void finish(int lane) {
+    const int kb0 = round_base(lane);
+    plain(kb0 < k_end ? (k_end - kb0 + 31) >> 5 : 0, lane);
+  }
+};
+
+// OR one N-bit mask (word `lane` of it in `word`, lanes 0..NWC; lane NWC holds 0) into the stream at bit offset qs.
+// Called by lanes 0..NWC together; masks of one game are disjoint in the stream, words they share are OR-ed atomically.
+// ROT: store the words rotated left by 4 (the float writers' table lookup wants a 4-bit field at bits 4-7).
+template <int NWC, bool ROT>
+__device__ __forceinline__ void stream_or_mask(uint32_t *strm, uint32_t word, int qs, int lane) {
+  constexpr uint32_t kLanes = (2u << NWC) - 1u;  // lanes 0..NWC
+  uint32_t prev = __shfl_up_sync(kLanes, word, 1);
+  if (lane == 0) prev = 0u;
+  const uint32_t c = __funnelshift_l(prev, word, qs & 31);  // (word << sh) | (prev >> (32 - sh))
+  atomicOr(strm + (qs >> 5) + lane, ROT ? rotl4(c) : c);
+}
+
+

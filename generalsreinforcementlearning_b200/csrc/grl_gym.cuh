@@ -20,10 +20,11 @@ __host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N, int mode
   int m;
   if (mode == GRL_GYM_EMIT_QUADS) {  // gym_emit_quads: dir rows + one player's mask words
     m = PT * 4 * NW + 5 * ((N + 3) / 4);
-  } else if (mode == GRL_GYM_EMIT_LINEAR) {  // gym_emit_linear: dir rows + (channel masks + log plane | the game's mask bytes)
-    const int lin_obs = (((PT * GRL_GYM_CHANNELS + PT) * (NW + 1) + N + 4 + 3) & ~3) + 4 * PT * GRL_GYM_CHANNELS + 4;
-    const int lin_mask = (P * N * 5 + 8 + 3) / 4;
-    m = PT * 4 * NW + (lin_obs > lin_mask ? lin_obs : lin_mask);
+  } else if (mode == GRL_GYM_EMIT_LINEAR) {  // gym_emit_linear: concatenated direction streams + (F + bit stream | staged mask words)
+    const int dirs = 4 * (((PT * N + 31) / 32 + 1 + 3) & ~3);
+    const int lin_obs = ((2 * N + 8 + 3) & ~3) + ((((PT * GRL_GYM_CHANNELS * N + 7 + 31) / 32 + 1) + 3) & ~3);
+    const int lin_mask = 5 * ((PT * N + 3) / 4) + 12;
+    m = dirs + (lin_obs > lin_mask ? lin_obs : lin_mask);
   } else {  // gym_emit
     m = (3 * P + 5 + 5 * P) * (NW + 1) + N + 4;
   }
@@ -370,159 +371,184 @@ __device__ __forceinline__ void gym_emit_quads(const GrlKParams &prm, int max_tu
   __syncwarp();
 }
 
-// The same read-outs for baked boards with N % 4 != 0 (15x15), from the slab in SHARED memory: like obs_linear,
-// the game's [P][9][N] block is one linear, 16-byte aligned sweep of 128-bit stores addressed by position in the
-// block (plane = e / N, tile = e % N, compile-time N), a 4-bit window of the plane's staged channel mask going
-// through the nibble table.  The game's [P][N*5] mask bytes are assembled per tile in shared memory, pre-shifted
-// by the block's misalignment, and leave as an aligned 32-bit sweep.
+// The same read-outs for baked boards with N % 4 != 0 (15x15), from the slab in SHARED memory, with the bit-stream writer
+// of obs_linear (grl_obs.cuh): the game's [P][9][N] block is one linear, 16-byte aligned sweep of 128-bit stores; every
+// plane is a 0/1 mask in the stream, and the planes that are not 0/1 multiply the table value by an aligned float4 of a
+// per-view array F: ownership (0.5 on own tiles) and log-army are adjacent planes [1.. | 0.5 or 1 per tile | log per
+// tile | 1..], the turn plane is [1.. | turn/max_turns per tile | ..].  Plane 8 is all zeros, so the sector a block
+// shares with the next game of the warp is simply left to that game's pass.
+// The N*5 mask bytes of all players are one run of 5-byte tile records: the four direction masks of the views are
+// concatenated into P*N-bit streams, a lane expands a quad of four tiles into five words (as gym_emit_quads does), and the
+// staged words leave as an aligned 32-bit sweep shifted by the block's misalignment.
 template <int PT, int N>
 __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
                                                 float *__restrict__ obs, uint8_t *__restrict__ mask,
                                                 int32_t *__restrict__ stats, const uint32_t *s, const uint32_t *stt,
-                                                const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g) {
-  constexpr int NW = (N + 31) / 32, NWP = NW + 1, CH = GRL_GYM_CHANNELS;
+                                                const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g,
+                                                bool prev_in_warp, bool next_in_warp) {
+  constexpr int NWC = (N + 31) / 32, CH = GRL_GYM_CHANNELS;
+  constexpr int DW = ((PT * N + 31) / 32 + 1 + 3) & ~3;                                        // words of one direction stream
+  constexpr int FW = (2 * N + 8 + 3) & ~3;
+  constexpr int SW = (((PT * GRL_GYM_CHANNELS * N + 7 + 31) / 32 + 1) + 3) & ~3;
   const GrlLayout &L = prm.L;
-  const int P = prm.P;
+  const int P = prm.P, NW = NWC;
   const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
-  uint32_t *s_dir = sw;                                          // [PT][4][NW]
-  uint32_t *chm = sw + PT * 4 * NW;                              // [PT*9][NWP] channel masks
-  uint32_t *minem = chm + PT * CH * NWP;                         // [PT][NWP]   own tiles in sight (the 0.5 of plane 1)
-  float *logv = reinterpret_cast<float *>(minem + PT * NWP);     // [N + 4]
-  float4 *sf = reinterpret_cast<float4 *>(sw + ((PT * 4 * NW + (PT * CH + PT) * NWP + N + 4 + 3) & ~3));  // [PT*9] straddlers
-  uint8_t *stage = reinterpret_cast<uint8_t *>(chm);             // the mask bytes reuse the observation staging
-  const bool w = lane < NW;
+  uint32_t *s_dir = sw;                                // [4][DW]: up, right, down, left of every view, concatenated
+  float *F = reinterpret_cast<float *>(sw + 4 * DW);   // [2N + 8]
+  uint32_t *strm = sw + 4 * DW + FW;                   // [SW]
+  uint32_t *stage = sw + 4 * DW;                       // the mask words reuse F + stream
+  const bool w = lane < NWC;
+  const uint32_t valid = w ? g.valid : 0u;
   const uint32_t M = w ? stt[lane] : 0u, C = w ? stt[NW + lane] : 0u, G = w ? stt[2 * NW + lane] : 0u;
+  uint32_t any_own = 0;
+#pragma unroll
+  for (int p = 0; p < PT; p++)
+    if (p < P && w) any_own |= s[L.off_own + p * NW + lane];
+
+  if (obs) {
+    const int planes = P * CH, total = planes * N;
+    const size_t off = (size_t)game * total;
+    const bool join_prev = prev_in_warp && (off & 7u) != 0;   // the previous block's last floats are zeros (plane 8)
+    const int pre = join_prev ? (int)(off & 7u) : (int)(off & 3u);
+    const int qend = pre + total;
+    for (int k = lane; k < SW / 4; k += 32) reinterpret_cast<uint4 *>(strm)[k] = make_uint4(0u, 0u, 0u, 0u);
+    float lg[NWC];  // log(army + 1) / 10 of tiles lane, lane + 32, ...
+#pragma unroll
+    for (int j = 0; j < NWC; j++) {
+      const int t = lane + 32 * j;
+      lg[j] = t < N ? __ldg(logtab + army[t]) : 0.f;  // logtab[0] == 0
+    }
+    const float tf = fminf(__fdiv_rn((float)s[GRL_HDR_TURN], (float)max_turns), 1.0f);
+    __syncwarp();
+    if (lane <= NWC) {
+      int qs = pre;
+#pragma unroll
+      for (int p = 0; p < PT; p++) {
+        if (p < P) {
+          const uint32_t v = w ? (prm.fog ? s[L.off_vis + p * NW + lane] : valid) : 0u;
+          const uint32_t ch[CH - 1] = {v, v & any_own, v, valid & ~(M | C | G), M, C, G, valid};  // plane 8 stays zero
+#pragma unroll
+          for (int c = 0; c < CH - 1; c++) stream_or_mask<NWC, true>(strm, ch[c], qs + c * N, lane);
+          qs += CH * N;
+        }
+      }
+    }
+    __syncwarp();
+
+    float *base_al = obs + (off - pre);
+    const int k_first = (pre == 0 || join_prev) ? 0 : 1;
+    auto stream_bit = [&](int q) -> uint32_t { return (strm[q >> 5] >> ((q + 4) & 31)) & 1u; };
+    if (k_first && pre + lane < 4)  // floats before the aligned body: tiles 0.. of view 0's visibility plane
+      __stcs(base_al + pre + lane, stream_bit(pre + lane) ? 1.f : 0.f);
+    int k_end;
+    if (next_in_warp && (qend & 7) != 0) {
+      k_end = (qend >> 3) * 2;  // the shared sector is left to the next game's pass
+    } else {
+      k_end = qend >> 2;        // floats after the aligned body: zeros (plane 8)
+      const int q = 4 * k_end + lane;
+      if (q < qend) __stcs(base_al + q, 0.f);
+    }
+
+    StreamSweep swp;
+    swp.init(lut, strm, base_al, k_first, k_end, lane);
+    const uint32_t F_sa = smem_addr(F);
+    for (int p = 0; p < P; p++) {
+      const int qv = pre + p * CH * N;  // this view's first float
+      // ---- planes 1 (ownership: 0.5 on own tiles in sight, 1 on enemy tiles) and 2 (log army in sight) ----------------
+      const int qa = qv + N, sa = qa & 3;
+      swp.plain(swp.rounds_before(qa, lane), lane);
+      __syncwarp();  // F is free
+      {
+        const uint32_t mine = w ? ((prm.fog ? s[L.off_vis + p * NW + lane] : valid) & s[L.off_own + p * NW + lane]) : 0u;
+#pragma unroll
+        for (int j = 0; j < NWC; j++) {
+          const int t = lane + 32 * j;
+          const uint32_t mw = __shfl_sync(FULL, mine, j);
+          if (t < N) {
+            F[sa + t] = ((mw >> lane) & 1u) ? 0.5f : 1.f;
+            F[sa + N + t] = lg[j];
+          }
+        }
+        if (lane < sa) F[lane] = 1.f;
+        if (lane < 4) F[sa + 2 * N + lane] = 1.f;
+      }
+      __syncwarp();
+      swp.scaled(qa, qa + 2 * N - 1, F_sa, lane);
+      // ---- plane 7: min(turn / max_turns, 1) on every tile ------------------------------------------------------------
+      const int qt = qv + 7 * N, st = qt & 3;
+      swp.plain(swp.rounds_before(qt, lane), lane);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NWC; j++) {
+        const int t = lane + 32 * j;
+        if (t < N) F[st + t] = tf;
+      }
+      if (lane < st) F[lane] = 1.f;
+      if (lane < 4) F[st + N + lane] = 1.f;  // plane 8: zeros whatever the multiplier
+      __syncwarp();
+      swp.scaled(qt, qt + N - 1, F_sa, lane);
+    }
+    swp.finish(lane);
+  }
+  __syncwarp();
   if (mask) {
     const uint32_t gt1 = army_gt1_mask<32>(army, NW, N, g);
     const DirMasks dm = dir_targets<32>(M, g);
-#pragma unroll
-    for (int p = 0; p < PT; p++) {
-      if (p < P && w) {
-        const uint32_t own = s[L.off_own + p * NW + lane];
-        const uint32_t v = prm.fog ? s[L.off_vis + p * NW + lane] : g.valid;
-        const uint32_t src = v & own & gt1;
-        s_dir[(p * 4 + 0) * NW + lane] = src & dm.up;
-        s_dir[(p * 4 + 1) * NW + lane] = src & dm.right;
-        s_dir[(p * 4 + 2) * NW + lane] = src & dm.down;
-        s_dir[(p * 4 + 3) * NW + lane] = src & dm.left;
-      }
-    }
-  }
-  if (obs) {
-    if (lane < NWP) {
-      const uint32_t valid = w ? g.valid : 0u;
-      uint32_t any_own = 0;
-#pragma unroll
-      for (int p = 0; p < PT; p++)
-        if (p < P && w) any_own |= s[L.off_own + p * NW + lane];
+    for (int k = lane; k < DW; k += 32) reinterpret_cast<uint4 *>(s_dir)[k] = make_uint4(0u, 0u, 0u, 0u);  // 4 * DW words
+    __syncwarp();
+    if (lane <= NWC) {
 #pragma unroll
       for (int p = 0; p < PT; p++) {
         if (p < P) {
           const uint32_t own = w ? s[L.off_own + p * NW + lane] : 0u;
           const uint32_t v = w ? (prm.fog ? s[L.off_vis + p * NW + lane] : valid) : 0u;
-          uint32_t *c = chm + p * CH * NWP + lane;
-          c[0 * NWP] = v;
-          c[1 * NWP] = v & any_own & ~own;  // enemy -> 1.0; own tiles come from minem -> 0.5
-          c[2 * NWP] = v;                   // x log(army + 1) / 10
-          c[3 * NWP] = valid & ~(M | C | G);
-          c[4 * NWP] = M;
-          c[5 * NWP] = C;
-          c[6 * NWP] = G;
-          c[7 * NWP] = valid;               // x turn / max_turns
-          c[8 * NWP] = 0u;
-          minem[p * NWP + lane] = v & own;
+          const uint32_t src = v & own & gt1;
+          stream_or_mask<NWC, false>(s_dir + 0 * DW, src & dm.up, p * N, lane);
+          stream_or_mask<NWC, false>(s_dir + 1 * DW, src & dm.right, p * N, lane);
+          stream_or_mask<NWC, false>(s_dir + 2 * DW, src & dm.down, p * N, lane);
+          stream_or_mask<NWC, false>(s_dir + 3 * DW, src & dm.left, p * N, lane);
         }
       }
     }
-    for (int t = lane; t < N + 4; t += 32) logv[t] = t < N ? __ldg(logtab + army[t]) : 0.f;  // logtab[0] == 0
     __syncwarp();
-
-    const float tf = fminf(__fdiv_rn((float)s[GRL_HDR_TURN], (float)max_turns), 1.0f);
-    auto elem = [&](int e) -> float {
-      const int plane = e / N, t = e - plane * N, k = plane % CH;
-      const uint32_t bit = (chm[plane * NWP + (t >> 5)] >> (t & 31)) & 1u;
-      if (k == 1) return ((minem[(plane / CH) * NWP + (t >> 5)] >> (t & 31)) & 1u) ? 0.5f : (bit ? 1.f : 0.f);
-      if (k == 2) return bit ? logv[t] : 0.f;
-      if (k == 7) return tf;
-      return bit ? 1.f : 0.f;
-    };
-    const int total = P * CH * N;  // floats in this game's block
-    float *base = obs + (size_t)game * total;
-    const int head = (int)((4u - (uint32_t)(((size_t)game * total) & 3u)) & 3u);
-    const int body4 = (total - head) / 4;
-    const int tail0 = head + 4 * body4;
-    if (lane < head) __stcs(base + lane, elem(lane));
-    if (lane < total - tail0) __stcs(base + tail0 + lane, elem(tail0 + lane));
-    const char *lutb = reinterpret_cast<const char *>(lut);
-    float4 *body = reinterpret_cast<float4 *>(base + head);
-    for (int j = lane; j < P * CH - 1; j += 32) {  // the float4s that straddle two planes
-      const int b = (j + 1) * N - head;
-      if ((b & 3) && (b >> 2) < body4) {
-        const int e = head + (b & ~3);
-        sf[j] = make_float4(elem(e), elem(e + 1), elem(e + 2), elem(e + 3));
-      }
+    // The staged words are placed so that stage and destination agree modulo 16 bytes: word 0 of the first quad sits
+    // `woff` words into the staging area, where the block's first aligned word sits woff words into a 16-byte line.
+    const int tiles = P * N, quads = (tiles + 3) >> 2, bytes = tiles * 5;
+    const size_t goff = (size_t)game * bytes;
+    const int mis = (int)(goff & 3u), woff = (int)(((goff - mis) >> 2) & 3u);
+    const uint8_t *bd = reinterpret_cast<const uint8_t *>(s_dir);
+    if (lane < 4) stage[lane] = 0u;  // the words before the first quad's (read by the shifted copy, never stored)
+    for (int q = lane; q < quads; q += 32) {
+      const int b = q >> 1, bsh = 4 * (q & 1);
+      const uint32_t U = (bd[b] >> bsh) & 0xfu, R = (bd[4 * DW + b] >> bsh) & 0xfu;
+      const uint32_t D = (bd[8 * DW + b] >> bsh) & 0xfu, Lm = (bd[12 * DW + b] >> bsh) & 0xfu, A = U | R | D | Lm;
+      // byte 5i+k of the quad = direction k of its tile i:  U0 R0 D0 L0 | A0 U1 R1 D1 | L1 A1 U2 R2 | D2 L2 A2 U3 | R3 D3 L3 A3
+      auto spread = [](uint32_t n) -> uint32_t { return (n * 0x00204081u) & 0x01010101u; };
+      const uint32_t Ub = spread(U), Rb = spread(R), Db = spread(D), Lb = spread(Lm), Ab = spread(A);
+      const uint32_t UR = __byte_perm(Ub, Rb, 0x5140), URh = __byte_perm(Ub, Rb, 0x7362);
+      const uint32_t DL = __byte_perm(Db, Lb, 0x5140), DLh = __byte_perm(Db, Lb, 0x7362);
+      uint32_t *o = stage + 4 + woff + 5 * q;
+      o[0] = __byte_perm(UR, DL, 0x5410);
+      o[1] = __byte_perm(__byte_perm(UR, DL, 0x6320), Ab, 0x3214);
+      o[2] = __byte_perm(__byte_perm(DL, URh, 0x5403), Ab, 0x3250);
+      o[3] = __byte_perm(__byte_perm(DLh, URh, 0x6010), Ab, 0x3610);
+      o[4] = __byte_perm(__byte_perm(URh, DLh, 0x0763), Ab, 0x7210);
     }
     __syncwarp();
-#pragma unroll 2
-    for (int i = lane; i < body4; i += 32) {
-      const int e = head + 4 * i;
-      const int plane = e / N, t = e - plane * N;
-      const int k = plane % CH;
-      const uint32_t *wp = chm + plane * NWP + (t >> 5);
-      uint32_t nib = __funnelshift_r(wp[0], wp[1], t & 31) & 0xfu;  // rows are zero from bit N on
-      float4 val;
-      if (t + 3 < N) {
-        val = *reinterpret_cast<const float4 *>(lutb + nib * 16u);
-        if (k == 1) {
-          const uint32_t *mp = minem + (plane / CH) * NWP + (t >> 5);
-          const uint32_t nb2 = __funnelshift_r(mp[0], mp[1], t & 31) & 0xfu;
-          const float4 m = *reinterpret_cast<const float4 *>(lutb + nb2 * 16u);
-          val = make_float4(__fmaf_rn(m.x, 0.5f, val.x), __fmaf_rn(m.y, 0.5f, val.y), __fmaf_rn(m.z, 0.5f, val.z),
-                            __fmaf_rn(m.w, 0.5f, val.w));
-        } else if (k == 2) {
-          if (nib) {
-            val.x *= logv[t];
-            val.y *= logv[t + 1];
-            val.z *= logv[t + 2];
-            val.w *= logv[t + 3];
-          }
-        } else if (k == 7) {
-          val = make_float4(tf, tf, tf, tf);
-        }
-      } else {
-        val = sf[plane];  // evaluated before the sweep, one per lane (see obs_linear)
-      }
-      __stcs(body + i, val);
-    }
-  }
-  __syncwarp();
-  if (mask) {
-    const int total = P * N * 5;  // bytes of this game's block [P][N*5]
-    const size_t goff = (size_t)game * total;
-    const int mis = (int)(goff & 3u);
-    for (int p = 0; p < P; p++) {
-      const uint32_t *d = s_dir + p * 4 * NW;
-      for (int t = lane; t < N; t += 32) {
-        const int wd = t >> 5, b = t & 31;
-        const uint32_t U = (d[wd] >> b) & 1u, R = (d[NW + wd] >> b) & 1u, D = (d[2 * NW + wd] >> b) & 1u,
-                       Lm = (d[3 * NW + wd] >> b) & 1u;
-        uint8_t *o = stage + mis + (p * N + t) * 5;
-        o[0] = (uint8_t)U;
-        o[1] = (uint8_t)R;
-        o[2] = (uint8_t)D;
-        o[3] = (uint8_t)Lm;
-        o[4] = (uint8_t)(U | R | D | Lm);
-      }
-    }
-    __syncwarp();
-    uint8_t *base = mask + goff;
-    const int head = (4 - mis) & 3;
-    const int body4 = (total - head) / 4, tail0 = head + 4 * body4;
-    if (lane < head) base[lane] = stage[mis + lane];
-    if (lane < total - tail0) base[tail0 + lane] = stage[mis + tail0 + lane];
-    uint32_t *dst = reinterpret_cast<uint32_t *>(base + head);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(stage + mis + head);
-    for (int i = lane; i < body4; i += 32) __stcs(dst + i, src[i]);
+    // copy-out.  In "line" coordinates (16-byte lines from the aligned line that holds the block's first byte) staged
+    // word 4 + i holds the bytes of line word i shifted up by `mis` bytes: line word i = bytes [4i - mis, 4i - mis + 4)
+    // of the staged run = funnel(staged[4 + i - 1], staged[4 + i]) >> 8 (4 - mis).  The block covers line bytes
+    // [b0, b1): whole lines go out as 128-bit stores, the ragged ends as bytes.
+    const int b0 = 4 * woff + mis, b1 = b0 + bytes;
+    uint8_t *line0 = mask + goff - b0;                          // 16-byte aligned
+    const int shb = (32 - 8 * mis) & 31, adj = mis ? 0 : 1;
+    auto line_word = [&](int i) -> uint32_t { return __funnelshift_r(stage[3 + i + adj], stage[4 + i + adj], shb); };
+    const int l0 = (b0 + 15) >> 4, l1 = b1 >> 4;                // whole lines [l0, l1)
+    for (int l = l0 + lane; l < l1; l += 32)
+      __stcs(reinterpret_cast<uint4 *>(line0) + l, make_uint4(line_word(4 * l), line_word(4 * l + 1), line_word(4 * l + 2), line_word(4 * l + 3)));
+    // ragged ends: bytes [b0, 16 l0) and [16 l1, b1) (at most 15 each); byte x of the line space = byte x & 3 of line word x >> 2
+    for (int x = b0 + lane; x < 16 * l0 && x < b1; x += 32) line0[x] = (uint8_t)(line_word(x >> 2) >> (8 * (x & 3)));
+    for (int x = (l1 > l0 ? 16 * l1 : 16 * l0) + lane; x < b1; x += 32) line0[x] = (uint8_t)(line_word(x >> 2) >> (8 * (x & 3)));
   }
   if (stats && lane < P) {
     int tiles = 0;
@@ -535,4 +561,5 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
   }
   __syncwarp();
 }
+
 #undef GYM_NIB4

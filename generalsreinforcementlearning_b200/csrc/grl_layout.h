@@ -66,6 +66,9 @@ static inline GrlLayout grl_make_layout(int W, int H, int P) {
   return L;
 }
 
+// words of one packed observation record: own[P][NW] vis[P][NW] mountain[NW] city|general[NW] army u16[NA]
+static inline int grl_packed_words(const GrlLayout &L) { return ((2 * L.P + 2) * L.NW + L.NA / 2 + 3) & ~3; }
+
 // Kernel parameter block (passed by value, __grid_constant__).
 struct GrlKParams {
   uint32_t *state;          // [B][slab_words]
@@ -79,6 +82,7 @@ struct GrlKParams {
   int8_t *winner;
   uint8_t *step_error;
   int32_t *action_index;
+  uint32_t *obs_packed;     // [B][grl_packed_words(L)] packed observation records (include/grlcuda.h)
   unsigned long long policy_seed;
   uint32_t flags;
   int B, W, H, N, P, NW, A;

@@ -3,13 +3,14 @@
 #pragma once
 #include "grl_device.cuh"
 
-// per-warp shared-memory words of the linear observation writer (only baked boards with N % 4 != 0)
+// per-warp shared-memory words of the bit-stream observation writer (only baked boards with N % 4 != 0): the
+// army-multiplier array F [2N + 8] and the block's bit stream (one bit per float, up to 7 lead bits, one spare word)
+__host__ __device__ constexpr int grl_obs_region_words(int N) { return (2 * N + 8 + 3) & ~3; }
+__host__ __device__ constexpr int grl_obs_stream_words(int N, int PT) {
+  return (((PT * GRL_OBS_CHANNELS * N + 7 + 31) / 32 + 1) + 3) & ~3;
+}
 __host__ __device__ constexpr int grl_obs_scratch_words(int TW, int TH, int PT, int NW) {
-  // channel masks [PT*9][NW+1] + army-fraction plane [N+4], rounded to 16 bytes, + the P*9-1 precomputed float4s that
-  // straddle two planes
-  return (TW > 0 && ((TW * TH) & 3) != 0)
-             ? (((PT * GRL_OBS_CHANNELS * (NW + 1) + TW * TH + 4 + 3) & ~3) + 4 * PT * GRL_OBS_CHANNELS)
-             : 0;
+  return (TW > 0 && ((TW * TH) & 3) != 0) ? grl_obs_region_words(TW * TH) + grl_obs_stream_words(TW * TH, PT) : 0;
 }
 
 // Observation planes, PLANE-MAJOR store order, for baked geometries with N % 4 == 0
@@ -104,31 +105,49 @@ __device__ __forceinline__ void obs_plane_major(const GrlKParams &prm, const Sla
   }
 }
 
-// Observation planes for baked geometries with N % 4 != 0 (15x15): the game's [P][9][N] block is
-// still ONE linear, 16-byte aligned sweep of 128-bit stores — channel planes start at odd float
-// offsets there, so a float4 is addressed by its position e in the BLOCK, not in a plane:
-// plane = e / N, tile = e % N.  The nine channel bitmasks of every player are staged in shared
-// memory (one pad word each, so a 4-bit window may straddle the last word), armies are converted
-// once into a float plane, and each store costs two LDS for the window, one table lookup and — on
-// the two army planes — four scalar LDS.  The <= 3 floats before/after the aligned body and the
-// float4s that straddle two planes (P*9-1 of them) take a per-element path.
-template <int N>
-__device__ __forceinline__ float obs_element(const uint32_t *chm, const float *frac, int NWP, int e) {
-  const int plane = e / N, t = e - plane * N;
-  const uint32_t bit = (chm[plane * NWP + (t >> 5)] >> (t & 31)) & 1u;
-  return bit ? ((plane % GRL_OBS_CHANNELS) < 2 ? frac[t] : 1.f) : 0.f;
-}
-
+// ---- the bit-stream writer (baked geometries with N % 4 != 0: 15x15) -----------------------------------------------------
+// Channel planes start at odd float offsets there, so the game's [P][9][N] block is written as ONE linear sweep of
+// 16-byte aligned 128-bit stores addressed by position in the block, not in a plane.  All but the two army planes of a
+// view hold 0/1, so the block is first laid out as a BIT STREAM in shared memory — bit q of the stream is float q of the
+// run that starts at the block's aligned base — by OR-ing every channel mask in at its plane's bit offset (one funnel
+// shift per mask word).  A store is then: one stream word, a rotate and a mask for the lane's 4-bit field, one 16-entry
+// table lookup, one STG.128 — no division, no plane arithmetic, and the float4s that straddle two planes cost nothing
+// extra.  Stream words are kept rotated left by 4 so that rotating right by the field's offset leaves the field at bits
+// 4-7: the byte offset of its table entry.  The army planes (channels 0/1 of each view, two adjacent planes) multiply
+// the table value by an aligned float4 of F = [1.. | army/1000 per tile | the same again | 1..], rebuilt per view at
+// the view's own alignment.
+//
+// A 15x15 block is 16,200 bytes: it starts and ends mid-sector, and a 32-byte sector completed by two different store
+// instructions costs the memory system far more than its bytes (tools/micro/store_holes.cu).  Consecutive games of one
+// warp therefore join their blocks into one sector-complete run: the sector two blocks share is written WHOLE by the
+// later game's pass — its first floats are the tail of the previous game's last plane (player P-1, channel 8 = fog),
+// taken from that game's slab, which is still in shared memory, into the first bits of this game's stream.
 template <int PT, int N>
 __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView &S, const float4 *lut, uint32_t *scratch,
                                            int P, int NW, int game, int lane, const uint32_t *prev_slab = nullptr,
                                            bool next_in_warp = false) {
-  const int NWP = NW + 1;
-  uint32_t *chm = scratch;                                                   // [P*9][NWP]
-  float *frac = reinterpret_cast<float *>(scratch + PT * GRL_OBS_CHANNELS * NWP);  // [N + 4]
-  float4 *sf = reinterpret_cast<float4 *>(scratch + ((PT * GRL_OBS_CHANNELS * NWP + N + 4 + 3) & ~3));  // [PT*9] straddlers
-  if (lane < NWP) {
-    const bool w = lane < NW;
+  constexpr int NWC = (N + 31) / 32, CH = GRL_OBS_CHANNELS;
+  constexpr int SW = grl_obs_stream_words(N, PT);
+  float *F = reinterpret_cast<float *>(scratch);  // [2N + 8]
+  uint32_t *strm = scratch + grl_obs_region_words(N);
+  const int planes = P * CH, total = planes * N;  // floats in this game's block
+  const size_t off = (size_t)game * total;
+  // run coordinates: float q of the run is float q - pre of this block; the run starts at a sector (joined to the
+  // previous game of the warp) or at the 16-byte boundary at or before the block
+  const bool join_prev = prev_slab != nullptr && (off & 7u) != 0;
+  const int pre = join_prev ? (int)(off & 7u) : (int)(off & 3u);
+  const int qend = pre + total;
+
+  for (int w = lane; w < SW / 4; w += 32) reinterpret_cast<uint4 *>(strm)[w] = make_uint4(0u, 0u, 0u, 0u);
+  float fr[NWC];  // army / 1000 of tiles lane, lane + 32, ...
+#pragma unroll
+  for (int j = 0; j < NWC; j++) {
+    const int t = lane + 32 * j;
+    fr[j] = t < N ? army_frac((uint32_t)S.army[t]) : 0.f;
+  }
+  __syncwarp();
+  if (lane <= NWC) {
+    const bool w = lane < NWC;
     const uint32_t valid = w ? prm.geom[lane] : 0u;
     const uint32_t M = w ? S.M[lane] : 0u;
     const uint32_t CG = w ? (S.C[lane] | S.G[lane]) : 0u;
@@ -136,106 +155,65 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
 #pragma unroll
     for (int p = 0; p < PT; p++)
       if (p < P && w) any_own |= S.own[p * NW + lane];
+    int qs = pre;
 #pragma unroll
     for (int p = 0; p < PT; p++) {
       if (p < P) {
         const uint32_t own = w ? S.own[p * NW + lane] : 0u;
         const uint32_t v = w ? (prm.fog ? S.vis[p * NW + lane] : valid) : 0u;
         const uint32_t nm = v & ~M;
-        uint32_t *c = chm + p * GRL_OBS_CHANNELS * NWP + lane;
-        const uint32_t mine = nm & own, enemy = nm & any_own & ~own;
-        c[0 * NWP] = mine;
-        c[1 * NWP] = enemy;
-        c[2 * NWP] = mine;
-        c[3 * NWP] = enemy;
-        c[4 * NWP] = nm & ~any_own;
-        c[5 * NWP] = nm & CG;
-        c[6 * NWP] = v & M;
-        c[7 * NWP] = v;
-        c[8 * NWP] = ~v & valid;
-      }
-    }
-  }
-  for (int t = lane; t < N + 4; t += 32) frac[t] = t < N ? army_frac((uint32_t)S.army[t]) : 0.f;
-  __syncwarp();
-
-  const int total = P * GRL_OBS_CHANNELS * N;  // floats in this game's block
-  float *base = prm.obs + (size_t)game * total;
-  // A 15x15 block is 16,200 bytes: it starts and ends mid-sector, and a 32-byte sector completed by two different store
-  // instructions costs the memory system far more than its bytes (tools/micro/store_holes.cu).  Consecutive games of one
-  // warp therefore join their blocks into one sector-complete run: the sector two blocks share is written WHOLE by the
-  // later game's pass (lanes 0-1, one instruction) — its first `lead` floats are the tail of the previous game's last
-  // plane (player P-1, channel 8 = fog), evaluated from that game's slab, which is still in shared memory.
-  const int lead = (int)(((size_t)game * total) & 7u);           // floats of this block's first sector that belong to the previous block
-  const int trail = (int)(((size_t)(game + 1) * total) & 7u);    // floats of this block in the sector it shares with the next block
-  const bool join_prev = prev_slab != nullptr && lead != 0;
-  const bool join_next = next_in_warp && trail != 0;
-  int head, end;
-  if (join_prev) {
-    if (lane < 2) {
-      const uint32_t *pv = prev_slab + prm.L.off_vis + (P - 1) * NW;
-      float v4[4];
+        const uint32_t mine = nm & own, enemy = nm & any_own & ~own;   // serializer.go:75-90
+        const uint32_t ch[CH] = {mine, enemy, mine, enemy, nm & ~any_own, nm & CG, v & M, v, ~v & valid};
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int pos = 4 * lane + c;
-        if (pos < lead) {
-          const int t = N - lead + pos;
-          const uint32_t seen = prm.fog ? ((pv[t >> 5] >> (t & 31)) & 1u) : 1u;
-          v4[c] = seen ? 0.f : 1.f;
-        } else {
-          v4[c] = obs_element<N>(chm, frac, NWP, pos - lead);
+        for (int c = 0; c < CH; c++) {
+          stream_or_mask<NWC, true>(strm, ch[c], qs, lane);
+          qs += N;
         }
       }
-      __stcs(reinterpret_cast<float4 *>(base - lead) + lane, make_float4(v4[0], v4[1], v4[2], v4[3]));
     }
-    head = 8 - lead;
-  } else {
-    head = (int)((4u - (uint32_t)(((size_t)game * total) & 3u)) & 3u);  // floats before the 16-byte aligned body
-    if (lane < head) __stcs(base + lane, obs_element<N>(chm, frac, NWP, lane));
-  }
-  if (join_next) {
-    end = total - trail;  // the shared sector is left to the next game's pass
-  } else {
-    end = head + 4 * ((total - head) / 4);
-    if (lane < total - end) __stcs(base + end + lane, obs_element<N>(chm, frac, NWP, end + lane));
-  }
-  const int body4 = (end - head) / 4;
-  // The P*9-1 float4s that straddle two planes are evaluated here, one per lane, and parked in shared memory: inside
-  // the sweep the per-element branch is divergent — one lane straddles in 17 of a 15x15 game's 32 rounds and the whole
-  // warp pays four element evaluations each time (592 of 3,183 warp instructions per game).  The store itself stays in
-  // the sweep: a 16-byte hole completed later costs far more than any of this (tools/micro/store_holes.cu).
-  for (int j = lane; j < P * GRL_OBS_CHANNELS - 1; j += 32) {
-    const int b = (j + 1) * N - head;  // plane boundary, in floats from the start of the aligned body
-    if ((b & 3) && b > 0 && (b >> 2) < body4) {
-      const int e = head + (b & ~3);
-      sf[j] = make_float4(obs_element<N>(chm, frac, NWP, e), obs_element<N>(chm, frac, NWP, e + 1),
-                          obs_element<N>(chm, frac, NWP, e + 2), obs_element<N>(chm, frac, NWP, e + 3));
+    if (lane == 0 && join_prev && prm.fog) {  // the previous block's last `pre` floats: its last view's fog plane
+      const uint32_t *pv = prev_slab + prm.L.off_vis + (P - 1) * NW;
+      const int t = N - pre, wl = t >> 5;
+      const uint32_t lo = ~pv[wl] & prm.geom[wl], hi = wl + 1 < NWC ? (~pv[wl + 1] & prm.geom[wl + 1]) : 0u;
+      atomicOr(strm, rotl4(__funnelshift_r(lo, hi, t & 31) & ((1u << pre) - 1u)));
     }
   }
   __syncwarp();
-  const char *lutb = reinterpret_cast<const char *>(lut);
-  float4 *body = reinterpret_cast<float4 *>(base + head);
-#pragma unroll 2
-  for (int i = lane; i < body4; i += 32) {
-    const int e = head + 4 * i;
-    const int plane = e / N, t = e - plane * N;
-    const int k = plane % GRL_OBS_CHANNELS;
-    const uint32_t *row = chm + plane * NWP;
-    const uint32_t *wp = row + (t >> 5);
-    uint32_t nib = __funnelshift_r(wp[0], wp[1], t & 31) & 0xfu;  // rows are zero from bit N on
-    float4 val;
-    if (t + 3 < N) {
-      val = *reinterpret_cast<const float4 *>(lutb + nib * 16u);
-      if (k < 2 && nib) {
-        val.x *= frac[t];
-        val.y *= frac[t + 1];
-        val.z *= frac[t + 2];
-        val.w *= frac[t + 3];
-      }
-    } else {
-      val = sf[plane];  // evaluated before the sweep, one per lane
-    }
-    __stcs(body + i, val);
+
+  float *base_al = prm.obs + (off - pre);
+  const int k_first = (pre == 0 || join_prev) ? 0 : 1;
+  auto stream_bit = [&](int q) -> uint32_t { return (strm[q >> 5] >> ((q + 4) & 31)) & 1u; };
+  if (k_first && pre + lane < 4)  // floats before the aligned body: tiles 0.. of view 0's own-army plane
+    __stcs(base_al + pre + lane, stream_bit(pre + lane) ? fr[0] : 0.f);
+  int k_end;
+  if (next_in_warp && (qend & 7) != 0) {
+    k_end = (qend >> 3) * 2;  // the shared sector is left to the next game's pass
+  } else {
+    k_end = qend >> 2;        // floats after the aligned body: the last view's fog plane
+    const int q = 4 * k_end + lane;
+    if (q < qend) __stcs(base_al + q, stream_bit(q) ? 1.f : 0.f);
   }
+
+  StreamSweep sw;
+  sw.init(lut, strm, base_al, k_first, k_end, lane);
+  const uint32_t F_sa = smem_addr(F);
+  for (int p = 0; p < P; p++) {
+    const int qs = pre + p * CH * N, s = qs & 3;  // this view's two army planes: floats [qs, qs + 2N)
+    sw.plain(sw.rounds_before(qs, lane), lane);
+    __syncwarp();  // the previous view's army rounds are done with F
+#pragma unroll
+    for (int j = 0; j < NWC; j++) {
+      const int t = lane + 32 * j;
+      if (t < N) {
+        F[s + t] = fr[j];
+        F[s + N + t] = fr[j];
+      }
+    }
+    if (lane < s) F[lane] = 1.f;
+    if (lane < 4) F[s + 2 * N + lane] = 1.f;
+    __syncwarp();
+    sw.scaled(qs, qs + 2 * N - 1, F_sa, lane);
+  }
+  sw.finish(lane);
   __syncwarp();
 }

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
   static_assert(LG >= PT || LG == 32, "per-player scalars are written by one lane each");
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t s_bar[GRL_WARPS_PER_CTA * GPW];
-  __shared__ __align__(16) float4 s_lut[16];  // nibble -> four 0/1 floats (observation planes)
+  __shared__ __align__(256) float4 s_lut[16];  // nibble -> four 0/1 floats (observation planes)
   if (DO_OUT && threadIdx.x < 16) {
     const uint32_t n = threadIdx.x;
     s_lut[n] = make_float4((n & 1u) ? 1.f : 0.f, (n & 2u) ? 1.f : 0.f, (n & 4u) ? 1.f : 0.f, (n & 8u) ? 1.f : 0.f);
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
                                                                           sg + L.slab_words, s_lut, s_obs, game_g, lane, g32);
       else if constexpr (TW > 0)
         gym_emit_linear<PT, (TW > 0 ? TW * TH : 5)>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg, sg + L.slab_words,
-                                                    s_lut, s_obs, game_g, lane, g32);
+                                                    s_lut, s_obs, game_g, lane, g32, gi > 0, gi + 1 < GPW && game_g + 1 < game_end);
       else
         gym_emit<0>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg, sg + L.slab_words, s_obs, game_g, lane, g32);
     }

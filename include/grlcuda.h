@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GRL_ABI_VERSION 1
+#define GRL_ABI_VERSION 2 /* 2: grl_step_outputs.obs_packed, grl_obs_packed_words, grl_expand_obs */
 
 #define GRL_MAX_DIM 32      /* width, height <= 32: one 32-bit word spans a board row */
 #define GRL_MAX_PLAYERS 8   /* reference bitfield allows 32 (core/board.go:11); configs need <= 4 */
@@ -148,7 +148,24 @@ typedef struct grl_step_outputs {
   int32_t *action_index; /* [B][P]  Serializer.ActionToIndex of the player's submitted move
                                     (UDLR order, serializer.go:179-198); -1 when the player
                                     submitted none or the turn aborted (no experience)    */
+  uint32_t *obs_packed;  /* [B][grl_obs_packed_words()]  everything StateToTensor reads, bit-packed: the
+                                    record grl_expand_obs turns into `obs` bit for bit on the host
+                                    (for consumers in HOST memory: 1,120 B instead of 28,800 B per
+                                    20x20 2-player env-step across PCIe)                  */
 } grl_step_outputs;
+
+/* One packed observation record (32-bit words; NW = ceil(N/32), tile t = bit t&31 of word t>>5):
+ *   own [P][NW]   tiles owned by player p            vis [P][NW]   Tile.VisibleBitfield bit p (all ones without fog)
+ *   mountain [NW]                                    city_or_general [NW]
+ *   army uint16 [N rounded up to 8]                  (padded to a multiple of 4 words)
+ * Serializer.StateToTensor (experience/serializer.go:37-109) is a function of exactly these planes. */
+int32_t grl_obs_packed_words(int32_t width, int32_t height, int32_t num_players);
+
+/* Host-only (no device work): expand `count` packed records into StateToTensor's float32 tensors,
+ * obs[count][P][9][H][W], on `threads` host threads (0 = all cores).  Bit-identical to what the same step
+ * would have written into grl_step_outputs.obs. */
+int grl_expand_obs(int32_t width, int32_t height, int32_t num_players, const uint32_t *packed, int32_t count, float *obs,
+                   int32_t threads);
 
 /* ---- full state planes for parity / replay / checkpoint (host memory).
  * Arrays are [count][...]; NULL members are skipped. ----------------------- */

@@ -1,24 +1,24 @@
 #!/usr/bin/env python3
-"""Turn a round's ncu artefacts (gpurun_out/, scratch) into the committed summaries under profiles/.
+"""Turn one ncu report (gpurun_out/, scratch) into the committed summaries under profiles/.
 
-usage: ncu_summarize.py <tag> [games W H P]
-  gpurun_out/prof_<tag>.ncu-rep     (ncu --set full ... --import-source on)
-  gpurun_out/launches_<tag>.csv     (ncu --metrics gpu__time_duration.sum launch list)
-writes profiles/<tag>_ncu_full_summary.json, <tag>_launches.csv, <tag>_launch_shares.txt,
-       <tag>_phases.txt and profiles/traffic.json (dram bytes per launch of the turn kernel).
+usage: ncu_summarize.py <report.ncu-rep> <tag> <kernel substring> <games> <W> <H> <P> [--traffic] [--gym]
+  report: ncu --set full --clock-control none --import-source on ... -o <report>
+writes profiles/<tag>_ncu_summary.json (per-launch metrics, top stalls, dram traffic vs algorithmic bytes) and
+       profiles/<tag>_regions.txt (per-region instruction / stall shares, tools/ncu_regions.py);
+with --traffic also profiles/traffic.json, keyed by the hash of the sources the profiled library was built from
+(bench.py prints roofline.traffic only when that hash matches the library it runs).
 """
-import collections
 import csv
 import glob
 import json
 import os
-import shutil
 import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bench import algorithmic_bytes_per_env_step  # noqa: E402
+from generalsreinforcementlearning_b200 import build as grl_build  # noqa: E402
 
 KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread', 'launch__grid_size',
@@ -26,71 +26,79 @@ KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
         'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
-        'lts__t_sector_hit_rate.pct']
+        'lts__t_sector_hit_rate.pct', 'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit_warps']
 
 
 def main():
-    tag = sys.argv[1]
-    games, W, H, P = (int(v) for v in sys.argv[2:6]) if len(sys.argv) >= 6 else (65536, 20, 20, 2)
-    rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
+    rep, tag, kernel = sys.argv[1:4]
+    games, W, H, P = (int(v) for v in sys.argv[4:8])
+    gym = "--gym" in sys.argv
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
 
     def num(r, k):
         i = hdr.index(k)
-        return float(r[i]) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}.get(units[i], 1)
+        return float(r[i]) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'us': 1e-6, 'ms': 1e-3, 'ns': 1e-9,
+                              's': 1}.get(units[i], 1)
 
     stall = [h for h in hdr if 'smsp__average_warp' in h and 'issue_stalled' in h and 'ratio' in h and 'not_issued' not in h]
-    out, traffic = [], []
-    for r in rows[2:]:
+    out = []
+    sel = [r for r in rows[2:] if kernel in r[hdr.index('Kernel Name')] or kernel in r[hdr.index('Function Name')] if 'Function Name' in hdr] \
+        if 'Function Name' in hdr else [r for r in rows[2:] if kernel in r[hdr.index('Kernel Name')]]
+    sel = sel or rows[2:]
+    alg = algorithmic_bytes_per_env_step(W, H, P)["total"] * games
+    if gym:  # slab + static + indices read; slab + obs + N*5 mask + stats + scalars written
+        a = algorithmic_bytes_per_env_step(W, H, P)
+        alg = (a["read"] + a["write"] - a["mask"] + 5 * W * H * P + 16 * P + 24) * games
+    for r in sel:
         d = {k: f"{r[hdr.index(k)]} {units[hdr.index(k)]}".strip() for k in KEYS if k in hdr}
         top = sorted(stall, key=lambda h: -float(r[hdr.index(h)]))[:6]
         d['top_stalls_per_issue'] = {h.split('issue_stalled_')[1].split('_per_issue')[0]: round(float(r[hdr.index(h)]), 2) for h in top}
+        traffic = num(r, 'dram__bytes_read.sum') + num(r, 'dram__bytes_write.sum')
+        dur = num(r, 'gpu__time_duration.sum')
+        d['dram_bytes'] = traffic
+        d['dram_GBps'] = round(traffic / dur / 1e9, 1)
+        d['algorithmic_bytes'] = alg
+        d['algorithmic_GBps'] = round(alg / dur / 1e9, 1)
+        d['warp_inst_per_game'] = round(num(r, 'smsp__inst_executed.sum') / games, 1)
         out.append(d)
-        traffic.append(num(r, 'dram__bytes_read.sum') + num(r, 'dram__bytes_write.sum'))
     prof = os.path.join(ROOT, "profiles")
-    json.dump({"source": f"ncu --set full --clock-control none --import-source on -k regex:grl_turn_kernel -s 30 -c 2, "
-                         f"bench.py --steps 20 --warmup 3 --quick; {games} games {W}x{H}x{P}p; report gpurun_out/prof_{tag}.ncu-rep (scratch)",
-               "launches": out}, open(os.path.join(prof, f"{tag}_ncu_full_summary.json"), "w"), indent=1)
-    alg = algorithmic_bytes_per_env_step(W, H, P)["total"] * games
-    json.dump({"kernel": f"grl_turn_kernel<{P},{W},{H},true,true>", "dram_bytes_per_launch": sum(traffic) / len(traffic),
-               "dram_bytes_read": num(rows[2], 'dram__bytes_read.sum'), "dram_bytes_write": num(rows[2], 'dram__bytes_write.sum'),
-               "algorithmic_bytes_per_launch": alg, "traffic_over_algorithmic": sum(traffic) / len(traffic) / alg,
-               "source": f"profiles/{tag}_ncu_full_summary.json (ncu --set full, {games} games {W}x{H}x{P}p)"},
-              open(os.path.join(prof, "traffic.json"), "w"), indent=1)
-    # launch list
-    src = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
-    if os.path.exists(src):
-        shutil.copy(src, os.path.join(prof, f"{tag}_launches.csv"))
-        lr = list(csv.DictReader(l for l in open(src) if l.startswith('"')))
-        agg, cnt = collections.Counter(), collections.Counter()
-        for r in lr:
-            agg[r['Kernel Name'][:70]] += float(r['Metric Value'])
-            cnt[r['Kernel Name'][:70]] += 1
-        tot = sum(agg.values())
-        with open(os.path.join(prof, f"{tag}_launch_shares.txt"), "w") as f:
-            f.write(f"# share of device time by kernel over the ncu launch list ({len(lr)} launches; cold-cache, serialised)\n")
-            for k, v in agg.most_common():
-                f.write(f"{v / tot * 100:5.1f}%  n={cnt[k]:4d}  avg={v / cnt[k] / 1e3:8.1f} us  {k}\n")
-    # per-phase shares
+    json.dump({"source": f"ncu --set full --clock-control none --import-source on; {games} games {W}x{H}x{P}p; kernel filter {kernel!r}; "
+                         f"report {os.path.relpath(rep, ROOT)} (scratch)", "lib_source_hash": grl_build.source_hash(), "launches": out},
+              open(os.path.join(prof, f"{tag}_ncu_summary.json"), "w"), indent=1)
+    if "--traffic" in sys.argv:
+        t = sum(d['dram_bytes'] for d in out) / len(out)
+        json.dump({"kernel": f"grl_turn_kernel<{P},{W},{H}>", "dram_bytes_per_launch": t, "algorithmic_bytes_per_launch": alg,
+                   "traffic_over_algorithmic": t / alg, "lib_source_hash": grl_build.source_hash(),
+                   "source": f"profiles/{tag}_ncu_summary.json (ncu --set full, {games} games {W}x{H}x{P}p)"},
+                  open(os.path.join(prof, "traffic.json"), "w"), indent=1)
+    # per-region shares
     srcp = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     open("/tmp/ncu_src.csv", "w").write(srcp)
     os.makedirs("/tmp/dis", exist_ok=True)
     for f in glob.glob("/tmp/dis/*"):
         os.remove(f)
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "generalsreinforcementlearning_b200", "csrc", "libgrlcuda.so")],
-                   cwd="/tmp/dis", capture_output=True)
-    cub = [f for f in glob.glob("/tmp/dis/grl_kernels.sm_100a.cubin")][0]
-    open("/tmp/dis/k.dis", "w").write(subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout)
-    mangled = f"_Z15grl_turn_kernelILi{2 if P <= 2 else 4}ELi{W}ELi{H}ELi32ELb1ELb1ELb0EEv10GrlKParams7GrlGymK"
-    ph = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_phases.py"), "/tmp/ncu_src.csv", "/tmp/dis/k.dis", mangled,
-                         os.path.join(ROOT, "generalsreinforcementlearning_b200", "csrc", "grl_kernels.cu"), str(games)],
-                        capture_output=True, text=True)
-    open(os.path.join(prof, f"{tag}_phases.txt"), "w").write(ph.stdout + ph.stderr)
-    print(json.dumps(out[0], indent=1))
-    print(open(os.path.join(prof, "traffic.json")).read())
-    print(ph.stdout[-900:], ph.stderr[-300:])
+    subprocess.run(["cuobjdump", "-xelf", "all", grl_build.LIB], cwd="/tmp/dis", capture_output=True)
+    # "void grl_turn_kernel<2, 15, 15, 8, 1, 1, 0>(GrlKParams, GrlGymK)" -> the mangled template arguments
+    import re
+    m = re.search(r"grl_turn_kernel<([^>]*)>", out[0]['Kernel Name']) if out else None
+    if m:
+        a = [v.strip() for v in m.group(1).split(",")]
+        kernel = "grl_turn_kernelI" + "".join(f"Li{v}E" for v in a[:4]) + "".join(f"Lb{v}E" for v in a[4:]) + "E"
+    for cub in sorted(glob.glob("/tmp/dis/*.cubin")):
+        dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
+        secs = [l for l in dis.split("\n") if l.startswith("\t.section\t.text.") and kernel in l]
+        if secs:
+            open("/tmp/dis/k.dis", "w").write(dis)
+            name = secs[0].split(".text.")[1].split(",")[0]
+            print("kernel section", name)
+            ph = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), "/tmp/ncu_src.csv", "/tmp/dis/k.dis", name,
+                                 str(games)], capture_output=True, text=True)
+            open(os.path.join(prof, f"{tag}_regions.txt"), "w").write(ph.stdout + ph.stderr)
+            print(ph.stdout[-3500:], ph.stderr[-300:])
+            break
+    print(json.dumps(out[0] if out else {}, indent=1))
 
 
 if __name__ == "__main__":

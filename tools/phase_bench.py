@@ -56,11 +56,40 @@ def main():
         torch.cuda.synchronize()
         res[name] = round(e0.elapsed_time(e1) / T, 4)
     from bench import algorithmic_bytes_per_env_step
+    gym = {}
+    if P == 2 and "--no-gym" not in sys.argv:   # the fused gym step (grl_gym_step), device-timed launch by launch
+        from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
+        e.close()
+        env = GeneralsVecEnv(B, W, H, max_turns=500, seed=3, auto_reset="device")
+        env.reset()
+        for _ in range(30):
+            env.step(env.sample_actions())
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(T):
+            a = env.sample_actions()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            env._opp_draws += 1
+            env._flip ^= 1
+            o = env._out[env._flip]
+            e0.record()
+            env.engine.gym_step(env.max_turns, env._base_seed * 1000003 + env._opp_draws, action=a, opponent_action=None,
+                                obs=env._obs, mask=env._mask, stats=env._stats, actions=env._actions, prev_stats=env._prev_stats,
+                                turns=env._turns, calls=env._calls, reward=o["reward"], terminated=o["terminated"],
+                                truncated=o["truncated"], valid=o["valid"], done=env._done, winner=o["winner"],
+                                step_error=o["step_error"], n_finished=env._nfin)
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        a = algorithmic_bytes_per_env_step(W, H, P)
+        gym_bytes = a["read"] + a["write"] - a["mask"] + 5 * W * H * P + 16 * P + 24
+        gym = {"gym_step_ms": round(tot / T, 4), "gym_bytes_per_env_step": gym_bytes, "gym_GBs": round(gym_bytes * B / (tot / T) / 1e6, 1)}
+        env.close()
     alg = algorithmic_bytes_per_env_step(W, H, P)["total"]
     fused = res["fused(obs+mask+reward+done)"]
     print(json.dumps({"config": [W, H, P, B], "bytes_per_env_step": alg,
                       "fused_GBs": round(alg * B / fused / 1e6, 1), "fused_Msteps": round(B / fused / 1e3, 1),
-                      "prefetch": os.environ.get("GRL_PREFETCH_DIST", "default"), "ms_per_launch": res}))
+                      "prefetch": os.environ.get("GRL_PREFETCH_DIST", "default"), "ms_per_launch": res, **gym}))
 
 
 if __name__ == "__main__":
