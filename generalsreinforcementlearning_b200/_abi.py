@@ -104,6 +104,7 @@ class StepOutputs(C.Structure):
         ("winner", C.c_void_p),
         ("step_error", C.c_void_p),
         ("action_index", C.c_void_p),
+        ("obs_packed", C.c_void_p),
     ]
 
 
@@ -178,6 +179,8 @@ ABI_FUNCTIONS = {
     "buffer_hash": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]),
     "stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "launch_count": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "obs_packed_words": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
+    "expand_obs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
 }
 
 

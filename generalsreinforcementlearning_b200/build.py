@@ -12,7 +12,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SOURCES = ["grl_turn_20.cu", "grl_turn_15.cu", "grl_turn_10.cu", "grl_turn_generic.cu", "grl_kernels.cu", "grl_abi.cu",
-           "grl_mapgen_gpu.cu", "grl_mapgen.cpp"]
+           "grl_mapgen_gpu.cu", "grl_mapgen.cpp", "grl_expand.cpp"]
 HEADERS = ["grl_layout.h", "grl_launch.h", "grl_mapgen.h", "grl_device.cuh", "grl_obs.cuh", "grl_gym.cuh", "grl_turn.cuh", "go_rng_cooked.inc", "go_rng_lehmer_pow.inc", "../../include/grlcuda.h"]
 LIB = os.path.join(CSRC, "libgrlcuda.so")
 OBJ_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "obj")

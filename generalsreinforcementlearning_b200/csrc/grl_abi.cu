@@ -38,7 +38,7 @@ int fail(int status, const char *fmt, ...) {
     if (e__ != cudaSuccess) return fail(GRL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
 
-enum Slot { SL_ACTIONS, SL_OBS, SL_MASK, SL_REWARD, SL_DONE, SL_WINNER, SL_ERR, SL_AIDX, SL_MISC, SL_MISC2, SL_COUNT };
+enum Slot { SL_ACTIONS, SL_OBS, SL_MASK, SL_REWARD, SL_DONE, SL_WINNER, SL_ERR, SL_AIDX, SL_PACKED, SL_MISC, SL_MISC2, SL_COUNT };
 
 struct Scratch {
   void *ptr = nullptr;
@@ -411,19 +411,21 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
   struct Plane {
     OutBuf ob;
     size_t stride;  // bytes per env
-  } planes[7];
+  } planes[8];
   int n_planes = 0;
   bool any_staged = actions_staged;
   if (do_out) {
     const size_t words = (4 * N + 31) / 32;
-    const Slot slots[7] = {SL_OBS, SL_MASK, SL_REWARD, SL_DONE, SL_WINNER, SL_ERR, SL_AIDX};
-    void *user[7] = {out->obs, out->mask_bits, out->reward, out->done, out->winner, out->step_error, out->action_index};
-    const size_t strides[7] = {P * GRL_OBS_CHANNELS * N * 4, P * words * 4, P * 4, 1, 1, 1, P * 4};
-    for (int i = 0; i < 7; i++) {
+    const Slot slots[8] = {SL_OBS, SL_MASK, SL_REWARD, SL_DONE, SL_WINNER, SL_ERR, SL_AIDX, SL_PACKED};
+    void *user[8] = {out->obs, out->mask_bits, out->reward, out->done, out->winner, out->step_error, out->action_index,
+                     out->obs_packed};
+    const size_t strides[8] = {P * GRL_OBS_CHANNELS * N * 4, P * words * 4, P * 4, 1, 1, 1, P * 4,
+                               (size_t)grl_packed_words(env->L) * 4};
+    for (int i = 0; i < 8; i++) {
       planes[i].stride = strides[i];
       // the small result planes (reward, done, winner, step_error, action_index) are written in place when the caller's
       // buffers are pinned host memory: no D2H copy (e2e +5 %; writing the observation planes in place cost 10 %)
-      void *alias = i >= 2 ? pinned_device_alias(user[i]) : nullptr;
+      void *alias = (i >= 2 && i <= 6) ? pinned_device_alias(user[i]) : nullptr;
       if (alias) {
         planes[i].ob.user = user[i];
         planes[i].ob.dev = alias;
@@ -435,7 +437,7 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
       if (st) return st;
       any_staged = any_staged || planes[i].ob.staged;
     }
-    n_planes = 7;
+    n_planes = 8;
     prm.obs = (float *)planes[0].ob.dev;
     prm.mask_bits = (uint32_t *)planes[1].ob.dev;
     prm.reward = (float *)planes[2].ob.dev;
@@ -443,6 +445,7 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
     prm.winner = (int8_t *)planes[4].ob.dev;
     prm.step_error = (uint8_t *)planes[5].ob.dev;
     prm.action_index = (int32_t *)planes[6].ob.dev;
+    prm.obs_packed = (uint32_t *)planes[7].ob.dev;
   }
   if (!do_step && !do_out) return GRL_OK;
 

@@ -67,7 +67,12 @@ static inline GrlLayout grl_make_layout(int W, int H, int P) {
 }
 
 // words of one packed observation record: own[P][NW] vis[P][NW] mountain[NW] city|general[NW] army u16[NA]
-static inline int grl_packed_words(const GrlLayout &L) { return ((2 * L.P + 2) * L.NW + L.NA / 2 + 3) & ~3; }
+#ifdef __CUDACC__
+#define GRL_HD __host__ __device__
+#else
+#define GRL_HD
+#endif
+GRL_HD static inline int grl_packed_words(const GrlLayout &L) { return ((2 * L.P + 2) * L.NW + L.NA / 2 + 3) & ~3; }
 
 // Kernel parameter block (passed by value, __grid_constant__).
 struct GrlKParams {

@@ -620,6 +620,28 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
     return;
   }
 
+  // packed observation records (include/grlcuda.h): everything StateToTensor reads, as the slab holds it — for consumers
+  // in host memory, which expand them with grl_expand_obs (1/26 of the fp32 planes' bytes across PCIe at 20x20)
+  if (prm.obs_packed) {
+    const int PNW = P * NW, RW = grl_packed_words(L), AW = RW - 2 * PNW - 2 * NW;
+#pragma unroll 1
+    for (int gi = 0; gi < GPW; gi++) {
+      const int game_g = warp_game0 + gi;
+      if (game_g >= game_end) break;
+      const uint32_t *sg = wbase + gi * per_game, *stg = sg + L.slab_words;
+      uint32_t *rec = prm.obs_packed + (size_t)game_g * RW;
+      for (int k = lane; k < PNW; k += 32) {
+        __stcs(rec + k, sg[L.off_own + k]);
+        __stcs(rec + PNW + k, prm.fog ? sg[L.off_vis + k] : prm.geom[k % NW]);
+      }
+      for (int k = lane; k < NW; k += 32) {
+        __stcs(rec + 2 * PNW + k, stg[k]);
+        __stcs(rec + 2 * PNW + NW + k, stg[NW + k] | stg[2 * NW + k]);
+      }
+      for (int k = lane; k < AW; k += 32) __stcs(rec + 2 * PNW + 2 * NW + k, k < L.NA / 2 ? sg[L.off_army + k] : 0u);
+    }
+  }
+
   // engine legal-action mask, packed in the reference's flat index order (t*4 + dir, U,R,D,L)
   if (prm.mask_bits) {
     const int words = (4 * N + 31) / 32;

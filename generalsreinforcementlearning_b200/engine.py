@@ -136,12 +136,27 @@ class BatchedEngine:
         self.lib.check(self.lib.step(self._h, _ptr(actions), flags, policy_seed), "step")
 
     def outputs(self, obs=None, mask_bits=None, reward=None, done=None, winner=None, step_error=None,
-                action_index=None) -> StepOutputs:
+                action_index=None, obs_packed=None) -> StepOutputs:
         o = StepOutputs()
         o.obs, o.mask_bits, o.reward = _ptr(obs), _ptr(mask_bits), _ptr(reward)
         o.done, o.winner, o.step_error = _ptr(done), _ptr(winner), _ptr(step_error)
-        o.action_index = _ptr(action_index)
+        o.action_index, o.obs_packed = _ptr(action_index), _ptr(obs_packed)
         return o
+
+    @property
+    def packed_words(self) -> int:
+        """32-bit words of one packed observation record (grl_obs_packed_words)."""
+        return int(self.lib.obs_packed_words(self.W, self.H, self.P))
+
+    def expand_obs(self, packed: np.ndarray, out: Optional[np.ndarray] = None, threads: int = 0) -> np.ndarray:
+        """Host-side expansion of packed observation records [n, packed_words] into Serializer.StateToTensor's
+        float32 tensors [n, P, 9, H, W] (grl_expand_obs: no device work, bit-identical to the ``obs`` plane)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint32).reshape(-1, self.packed_words)
+        n = packed.shape[0]
+        if out is None:
+            out = np.empty((n, self.P, _abi.GRL_OBS_CHANNELS, self.H, self.W), np.float32)
+        self.lib.check(self.lib.expand_obs(self.W, self.H, self.P, _ptr(packed), n, _ptr(out), threads), "expand_obs")
+        return out
 
     def alloc_outputs_host(self) -> Dict[str, np.ndarray]:
         B, P, N = self.B, self.P, self.N

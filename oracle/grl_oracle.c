@@ -1145,6 +1145,59 @@ typedef struct {
   uint64_t cnt[4];
 } job_t;
 
+int32_t grlo_obs_packed_words(int32_t width, int32_t height, int32_t num_players) {
+  if (width < 1 || width > GRL_MAX_DIM || height < 1 || height > GRL_MAX_DIM || num_players < 1 || num_players > GRL_MAX_PLAYERS)
+    return 0;
+  int N = width * height, NW = (N + 31) / 32, NA = (N + 7) & ~7;
+  return ((2 * num_players + 2) * NW + NA / 2 + 3) & ~3;
+}
+
+/* the checker's own expansion of packed records: serializer.go:37-109 tile by tile from the record's planes */
+int grlo_expand_obs(int32_t width, int32_t height, int32_t num_players, const uint32_t *packed, int32_t count, float *obs,
+                    int32_t threads) {
+  (void)threads;
+  int RW = grlo_obs_packed_words(width, height, num_players);
+  if (!packed || !obs || count < 0 || RW == 0) return GRL_ERR_INVALID_ARG;
+  int N = width * height, P = num_players, NW = (N + 31) / 32;
+  for (int c = 0; c < count; c++) {
+    const uint32_t *rec = packed + (size_t)c * RW;
+    const uint16_t *army = (const uint16_t *)(rec + (2 * P + 2) * NW);
+    for (int p = 0; p < P; p++) {
+      float *out = obs + ((size_t)c * P + p) * GRL_OBS_CHANNELS * N;
+      memset(out, 0, sizeof(float) * (size_t)GRL_OBS_CHANNELS * N);
+      for (int i = 0; i < N; i++) {
+        int w = i >> 5;
+        uint32_t bit = 1u << (i & 31);
+        int owner = -1;
+        for (int q = 0; q < P; q++)
+          if (rec[q * NW + w] & bit) owner = q;
+        if (!(rec[(P + p) * NW + w] & bit)) {
+          out[8 * N + i] = 1.0f;
+          continue;
+        }
+        out[7 * N + i] = 1.0f;
+        if (rec[2 * P * NW + w] & bit) {
+          out[6 * N + i] = 1.0f;
+          continue;
+        }
+        if (rec[(2 * P + 1) * NW + w] & bit) out[5 * N + i] = 1.0f;
+        volatile float v = (float)army[i] / 1000.0f;
+        if (v > 1.0f) v = 1.0f;
+        if (owner == p) {
+          if (army[i] > 0) out[0 * N + i] = v;
+          out[2 * N + i] = 1.0f;
+        } else if (owner >= 0) {
+          if (army[i] > 0) out[1 * N + i] = v;
+          out[3 * N + i] = 1.0f;
+        } else {
+          out[4 * N + i] = 1.0f;
+        }
+      }
+    }
+  }
+  return GRL_OK;
+}
+
 static void write_outputs(grlo_env *e, int b, const grl_step_outputs *out, uint8_t *scratch) {
   game_t *g = &e->g[b];
   int N = e->N, P = g->P;
@@ -1168,6 +1221,22 @@ static void write_outputs(grlo_env *e, int b, const grl_step_outputs *out, uint8
   if (out->step_error) out->step_error[b] = (uint8_t)g->step_error;
   if (out->action_index)
     for (int p = 0; p < P; p++) out->action_index[(size_t)b * P + p] = g->action_index[p];
+  if (out->obs_packed) { /* include/grlcuda.h: own[P][NW] vis[P][NW] mountain[NW] city|general[NW] army u16[NA] */
+    int NW = (N + 31) / 32, RW = grlo_obs_packed_words(e->cfg.width, e->cfg.height, P);
+    uint32_t *rec = out->obs_packed + (size_t)b * RW;
+    memset(rec, 0, sizeof(uint32_t) * (size_t)RW);
+    uint16_t *army = (uint16_t *)(rec + (2 * P + 2) * NW);
+    for (int i = 0; i < N; i++) {
+      const tile_t *t = &g->T[i];
+      uint32_t bit = 1u << (i & 31);
+      if (t->owner >= 0) rec[t->owner * NW + (i >> 5)] |= bit;
+      for (int p = 0; p < P; p++)
+        if (!g->fog || ((t->vis >> p) & 1u)) rec[(P + p) * NW + (i >> 5)] |= bit;
+      if (t->type == GRL_TILE_MOUNTAIN) rec[2 * P * NW + (i >> 5)] |= bit;
+      if (t->type == GRL_TILE_CITY || t->type == GRL_TILE_GENERAL) rec[(2 * P + 1) * NW + (i >> 5)] |= bit;
+      army[i] = (uint16_t)t->army;
+    }
+  }
 }
 
 static void *job_run(void *arg) {

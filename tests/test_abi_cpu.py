@@ -36,7 +36,7 @@ def test_header_and_binding_agree():
 def test_product_exports_every_declared_symbol(product_lib):
     for name in header_functions():
         assert hasattr(product_lib.cdll, name), name
-    assert product_lib.abi_version() == 1
+    assert product_lib.abi_version() == 2
 
 
 def test_oracle_exports_the_same_abi(oracle_lib):
@@ -48,7 +48,7 @@ def test_struct_sizes_match_header():
     # grl_action is 8 bytes; grl_config is 16 int32 + 11 floats
     assert _abi.ACTION_DTYPE.itemsize == 8
     assert C.sizeof(Config) == 16 * 4 + 11 * 4
-    assert C.sizeof(_abi.StepOutputs) == 7 * 8
+    assert C.sizeof(_abi.StepOutputs) == 8 * 8
     assert C.sizeof(_abi.StatePlanes) == 14 * 8
 
 
@@ -93,3 +93,48 @@ def test_product_mapgen_matches_oracle(product_lib, oracle_lib, W, H, P):
         if outs[0][0] == 0:
             for x, y in zip(outs[0][1:], outs[1][1:]):
                 assert np.array_equal(x, y), seed
+
+
+@pytest.mark.parametrize("W,H,P,fog", [(20, 20, 2, 1), (15, 15, 2, 1), (10, 10, 2, 1), (20, 20, 4, 1), (7, 13, 3, 1),
+                                        (5, 5, 2, 1), (32, 32, 8, 1), (15, 15, 2, 0), (1, 1, 1, 1)])
+def test_packed_observation_records_expand_to_state_to_tensor(product_lib, oracle_lib, W, H, P, fog):
+    """grl_step_outputs.obs_packed + grl_expand_obs (the host-delivery path): the product's vectorised host expander
+    and the oracle's tile-by-tile one both turn the oracle's packed records into exactly the float32 tensors the same
+    step wrote (Serializer.StateToTensor, serializer.go:37-109), bit for bit."""
+    from generalsreinforcementlearning_b200.engine import BatchedEngine, make_config
+
+    B = 24
+    cfg = make_config(oracle_lib, num_envs=B, width=W, height=H, num_players=P, max_actions=max(2, P), host_threads=1,
+                      fog_of_war=fog)
+    e = BatchedEngine(oracle_lib, cfg)
+    if W * H >= 25:
+        e.reset_seeded(np.arange(B, dtype=np.int64) + 777)
+    else:   # no room for generals: a hand-made board
+        e.reset_boards(np.zeros((B, 1), np.int32), np.full((B, 1), 3, np.int32), np.ones((B, 1), np.int32))
+    RW = e.packed_words
+    N = W * H
+    assert RW == product_lib.obs_packed_words(W, H, P) == (((2 * P + 2) * ((N + 31) // 32) + ((N + 7) & ~7) // 2 + 3) & ~3)
+    out = e.alloc_outputs_host()
+    packed = np.zeros((B, RW), np.uint32)
+    for t in range(60):
+        e.step_fused(None, e.outputs(obs_packed=packed, **out), _abi.STEP_FLAG_RANDOM_POLICY, 9)
+        if t % 6:
+            continue
+        for lib in (product_lib, oracle_lib):
+            got = np.full((B, P, 9, H, W), np.nan, np.float32)
+            assert lib.expand_obs(W, H, P, packed.ctypes.data, B, got.ctypes.data, 3 if lib is product_lib else 1) == 0
+            assert np.array_equal(got.view(np.uint32), out["obs"].view(np.uint32)), (lib.prefix, t)
+    # armies at and above the clip (serializer.go:84-88) and the largest the plane holds
+    st = e.get_state()
+    st["army"][:, 0] = [999, 1000, 1001, 65535, 0, 1] * (B // 6)
+    e.set_state(st)
+    e.observe(e.outputs(obs=out["obs"], obs_packed=packed))
+    got = product_lib_expand(product_lib, W, H, P, packed)
+    assert np.array_equal(got.view(np.uint32), out["obs"].view(np.uint32))
+    e.close()
+
+
+def product_lib_expand(lib, W, H, P, packed):
+    got = np.empty((packed.shape[0], P, 9, H, W), np.float32)
+    assert lib.expand_obs(W, H, P, packed.ctypes.data, packed.shape[0], got.ctypes.data, 0) == 0
+    return got

@@ -411,3 +411,29 @@ def test_pinned_host_results_are_written_in_place(cuda_lib, oracle_lib):
         assert np.array_equal(err.numpy(), oo["step_error"]) and np.array_equal(aidx.numpy(), oo["action_index"])
         assert np.array_equal(mask, oo["mask_bits"])
     assert np.array_equal(gc.state_hash(), oc.state_hash())
+
+
+@pytest.mark.parametrize("W,H,P,fog", [(20, 20, 2, 1), (15, 15, 2, 1), (10, 10, 2, 1), (20, 20, 4, 1), (7, 13, 3, 1), (15, 15, 2, 0)])
+def test_packed_observation_records(cuda_lib, oracle_lib, W, H, P, fog):
+    """grl_step_outputs.obs_packed (the host-delivery read-out): the kernel's records equal the oracle's word for word,
+    and grl_expand_obs turns them into the very tensors the same launch wrote into `obs`."""
+    B = 301   # leaves the last warp partly filled on every lane-group size
+    gc = new_engine(cuda_lib, W, H, P, B, fog_of_war=fog)
+    oc = new_engine(oracle_lib, W, H, P, B, fog_of_war=fog)
+    seeds = np.arange(B, dtype=np.int64) + 4321
+    gc.reset_seeded(seeds)
+    oc.reset_seeded(seeds)
+    go, oo = gc.alloc_outputs_host(), oc.alloc_outputs_host()
+    gp, op = np.zeros((B, gc.packed_words), np.uint32), np.zeros((B, oc.packed_words), np.uint32)
+    for t in range(45):
+        gc.step_fused(None, gc.outputs(obs_packed=gp, **go), _abi.STEP_FLAG_RANDOM_POLICY, 5)
+        oc.step_fused(None, oc.outputs(obs_packed=op, **oo), _abi.STEP_FLAG_RANDOM_POLICY, 5)
+        assert np.array_equal(gp, op), f"packed records differ at turn {t}"
+        if t % 9 == 0:
+            assert np.array_equal(gc.expand_obs(gp).view(np.uint32), go["obs"].view(np.uint32)), t
+    # packed records alone (no fp32 planes in the launch), from device memory too
+    import torch
+    dp = torch.zeros((B, gc.packed_words), dtype=torch.int32, device="cuda")
+    gc.observe(gc.outputs(obs_packed=dp))
+    gc.sync()
+    assert np.array_equal(dp.cpu().numpy().view(np.uint32), op)
