@@ -54,6 +54,27 @@ _PHASE_STATUS = {  # converters.go:84-102
 }
 
 
+def _varint(n: int) -> bytes:
+    out = bytearray()
+    while True:
+        b7 = n & 0x7F
+        n >>= 7
+        if n:
+            out.append(b7 | 0x80)
+        else:
+            out.append(b7)
+            return bytes(out)
+
+
+def _tag(field: int, wire_type: int) -> bytes:
+    return _varint((field << 3) | wire_type)
+
+
+def _packed_field(field: int, payload: bytes) -> bytes:
+    """A length-delimited field: strings, sub-messages and packed repeated scalars."""
+    return _tag(field, 2) + _varint(len(payload)) + payload
+
+
 def _now(ts) -> None:
     t = time.time()
     ts.seconds, ts.nanos = int(t), int((t % 1) * 1e9)
@@ -684,25 +705,42 @@ class GameServer:
             r.newest_experience.CopyFrom(xs[-1].collected_at)
         return r
 
-    def ingest_records(self, records, width: int, height: int, game_prefix: str = "env") -> int:
-        """Feed device-gathered experience records (``sharding.pack_experience`` /
-        ``gather_experience`` dicts of tensors) into the stream store, as the per-game
-        collectors do for served games.  ``mask_bits`` must hold the serializer mask bytes
-        ([R, 4*W*H], GRL_MASK_SERIALIZER_UDLR).  Returns the number of records added."""
-        host = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in records.items()}
+    def ingest_records(self, records, width: int, height: int, game_prefix: str = "env", players: int = 2) -> int:
+        """Feed device-gathered experience records (``sharding.gather_experience`` dicts of tensors) into the stream
+        store, as the per-game collectors do for served games.  Either float32 records (``sharding.pack_experience``:
+        ``state`` / ``next_state`` tensors, ``mask_bits`` = the serializer mask bytes [R, 4*W*H],
+        GRL_MASK_SERIALIZER_UDLR) or compact ones (``sharding.pack_experience_packed``), which are expanded here on the
+        host (grl_expand_obs + the serializer mask derived from the packed record).  Messages are framed straight in
+        protobuf wire format from the arrays' bytes (a packed repeated float IS its little-endian bytes) instead of
+        element by element.  Returns the number of records added."""
+        if "state_packed" in records:
+            from . import sharding
+
+            host = sharding.expand_experience(records, self.lib, width, height, players)
+        else:
+            host = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in records.items()
+                    if k not in ("dropped", "counts")}
         n = int(host["action"].shape[0])
+        shape = _packed_field(1, b"".join(_varint(d) for d in (9, height, width)))
+        state = np.ascontiguousarray(host["state"], dtype="<f4").reshape(n, -1)
+        nxt = np.ascontiguousarray(host["next_state"], dtype="<f4").reshape(n, -1)
+        mask = np.ascontiguousarray(host["mask_bits"]).reshape(n, -1).astype(np.uint8)
+        reward = np.ascontiguousarray(host["reward"], dtype="<f4")
+        t = time.time()
+        stamp = _packed_field(11, _tag(1, 0) + _varint(int(t)) + _tag(2, 0) + _varint(int((t % 1) * 1e9)))
         out = []
         for i in range(n):
-            x = experience.Experience(experience_id=str(uuid.uuid4()), game_id=f"{game_prefix}-{int(host['env_id'][i])}",
-                                      player_id=int(host["player"][i]), turn=int(host["turn"][i]), action=int(host["action"][i]),
-                                      reward=float(host["reward"][i]), done=bool(host["done"][i]))
-            x.state.shape.extend([9, height, width])
-            x.state.data.extend(host["state"][i].reshape(-1).tolist())
-            x.next_state.shape.extend([9, height, width])
-            x.next_state.data.extend(host["next_state"][i].reshape(-1).tolist())
-            x.action_mask.extend(host["mask_bits"][i].reshape(-1).astype(bool).tolist())
-            _now(x.collected_at)
-            out.append(x)
+            gid = f"{game_prefix}-{int(host['env_id'][i])}".encode()
+            wire = b"".join((
+                _packed_field(1, str(uuid.uuid4()).encode()), _packed_field(2, gid),
+                _tag(3, 0), _varint(int(host["player"][i])), _tag(4, 0), _varint(int(host["turn"][i])),
+                _packed_field(5, shape + _packed_field(2, state[i].tobytes())),
+                _tag(6, 0), _varint(int(host["action"][i]) & 0xFFFFFFFFFFFFFFFF),
+                _tag(7, 5), reward[i].tobytes(),
+                _packed_field(8, shape + _packed_field(2, nxt[i].tobytes())),
+                (_tag(9, 0) + b"\x01") if host["done"][i] else b"",
+                _packed_field(10, (mask[i] != 0).astype(np.uint8).tobytes()), stamp))
+            out.append(experience.Experience.FromString(wire))
         self.store.add(out)
         return n
 

@@ -92,7 +92,7 @@ def _selfplay_worker(rank, world, port, tmp):
     import selfplay_experience
 
     selfplay_experience.run(rank, world, games_per_gpu=1024, turns=6, sample=40,
-                            out_path=os.path.join(tmp, "selfplay.json") if rank == 0 else None)
+                            out_path=os.path.join(tmp, "selfplay.json") if rank == 0 else None, start_turn=5)
     import torch.distributed as dist
 
     if dist.is_initialized():
@@ -110,7 +110,12 @@ def test_selfplay_experience_to_grpc_learner(cuda_lib, tmp_path):
     port = 29700 + (os.getpid() % 2000)
     mp.spawn(_selfplay_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     r = json.load(open(os.path.join(tmp_path, "selfplay.json")))
-    assert r["env_steps"] == world * 1024 * 6
-    assert r["gathered"] == world * 40 * 6          # the per-turn sample of every rank arrived
-    assert r["streamed"] == r["gathered"]           # and all of it went out through the ExperienceService
-    assert r["full_batches"] >= r["gathered"] // 32 - 2
+    assert r["env_steps_total"] == world * 1024 * 3 * (5 + 1 + 6)     # three phases, each rewound to turn 5
+    ga, st = r["gather_all"], r["stream"]
+    # every transition of every turn reached the learner's HBM, nothing dropped, nothing padded
+    assert ga["dropped"] == 0 and 1.9 * 1024 * world <= ga["experiences_per_turn"] <= 2 * 1024 * world
+    assert ga["nvlink_bytes_per_turn"] == (ga["experiences_per_turn"] * (world - 1) / world) * r["record_bytes"] or world == 1 or \
+        abs(ga["nvlink_bytes_per_turn"] - ga["experiences_per_turn"] * (world - 1) / world * r["record_bytes"]) < 0.1 * ga["nvlink_bytes_per_turn"]
+    assert st["gathered"] == world * 40 * 6          # the per-turn sample of every rank arrived
+    assert st["streamed"] == st["gathered"]          # and all of it went out through the ExperienceService
+    assert st["full_batches"] >= st["gathered"] // 32 - 2

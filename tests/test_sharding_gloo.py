@@ -49,17 +49,39 @@ def _worker(rank, world, port, total, T, tmp):
     e.reset_seeded(sh.seeds(12345))
     out = e.alloc_outputs_host()
     prev = {k: v.copy() for k, v in out.items()}
-    e.observe(e.outputs(obs=prev["obs"], mask_bits=prev["mask_bits"]))
+    packed, prev_packed = (np.zeros((sh.count, e.packed_words), np.uint32) for _ in range(2))
+    e.observe(e.outputs(obs=prev["obs"], mask_bits=prev["mask_bits"], obs_packed=prev_packed))
     hashes, gathered = [], []
     for t in range(T):
-        e.step_fused(None, e.outputs(**out), _abi.STEP_FLAG_RANDOM_POLICY, 99)
+        ser_mask = e.mask(_abi.MASK_SERIALIZER_UDLR)          # of the state BEFORE the step
+        e.step_fused(None, e.outputs(obs_packed=packed, **out), _abi.STEP_FLAG_RANDOM_POLICY, 99)
         hashes.append(e.state_hash().copy())
+        # the compact records: packed observation records before/after, expanded again on the learner
+        recp = sharding.pack_experience_packed(
+            torch.from_numpy(prev_packed.view(np.int32)), torch.from_numpy(packed.view(np.int32)),
+            torch.from_numpy(out["action_index"]), torch.from_numpy(out["reward"]), torch.from_numpy(out["done"]),
+            t + 1, env_id_base=sh.first)
+        gp = sharding.gather_experience(recp, dst=0)
+        sm = sharding.gather_experience({"m": torch.from_numpy(ser_mask[out["action_index"] >= 0]),
+                                         "k": torch.zeros(int((out["action_index"] >= 0).sum()), dtype=torch.int32)}, dst=0)
+        prev_packed[:] = packed
         rec = sharding.pack_experience(
             torch.from_numpy(prev["obs"]), torch.from_numpy(out["obs"]), torch.from_numpy(prev["mask_bits"].view(np.int32)),
             torch.from_numpy(out["action_index"]), torch.from_numpy(out["reward"]), torch.from_numpy(out["done"]),
             t + 1, env_id_base=sh.first)
         g = sharding.gather_experience(rec, capacity=2 * sh.count, dst=0)
+        # a capacity below what a rank holds is reported, never silent
+        lossy = sharding.gather_experience(rec, capacity=5, dst=0)
         if rank == 0:
+            assert int(g["dropped"].sum()) == 0 and g["counts"].tolist() == [int(c) for c in g["counts"]]
+            assert lossy["action"].shape[0] == int(lossy["counts"].sum()) <= 5 * world
+            assert (lossy["dropped"] + lossy["counts"]).tolist() == g["counts"].tolist()
+            ex = sharding.expand_experience(gp, lib, 10, 10, 2, threads=1)
+            for k in ("action", "reward", "done", "player", "turn", "env_id"):
+                assert np.array_equal(ex[k], g[k].numpy()), k
+            assert np.array_equal(ex["state"].view(np.uint32), g["state"].numpy().view(np.uint32))
+            assert np.array_equal(ex["next_state"].view(np.uint32), g["next_state"].numpy().view(np.uint32))
+            assert np.array_equal(ex["mask_bits"], sm["m"].numpy().astype(bool)), "serializer mask from the packed record"
             gathered.append({k: v.numpy() for k, v in g.items()})
         prev = {k: v.copy() for k, v in out.items()}
     stats = sharding.all_reduce_stats(e.stats())

@@ -3,13 +3,21 @@
 learner rank over NCCL and served from there through the gRPC ExperienceService in batches of 32.
 
   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/selfplay_experience.py \
-      [--games-per-gpu 4096] [--turns 20] [--sample 64]
+      [--games-per-gpu 65536] [--turns 40] [--sample 256] [--out profiles/r2_selfplay.json]
 
-Every rank steps its shard with the in-kernel random policy (device-resident observations).  Each
-turn a fixed-size sample of that turn's transitions (``--sample`` per rank) is packed on the device
-(state, action, reward, next state, done, serializer mask), gathered to rank 0 with NCCL
-(``sharding.gather_experience``), and fed into the service's store; a gRPC client on rank 0 drains
-``StreamExperienceBatches(batch_size=32)``.  Rank 0 prints one JSON line."""
+Every rank steps its shard with the in-kernel random policy.  What leaves the step kernel for the hand-off is the
+PACKED observation record of each game (grl_step_outputs.obs_packed, 1,120 B at 20x20) before and after the turn, so an
+experience record is 2,264 B instead of the 29 KB of two float32 tensors; the learner rebuilds state, next_state and the
+serializer action mask on its side (sharding.expand_experience).  Records travel as one byte buffer per rank with its
+actual row count (sharding.gather_experience: one count all-gather + one variable-size transfer per rank, no padding).
+
+Three measured phases, each `--turns` turns from the same mid-episode state (turn 100), timed on every rank between a
+barrier + cuda synchronize on both sides, max over ranks:
+  step_only     the turn kernel alone (the step path without any hand-off)
+  gather_all    + EVERY transition of every turn packed and gathered into the learner GPU's HBM
+  stream        + a per-turn sample of `--sample` records per rank gathered, expanded on the learner's host, framed as
+                Experience messages and drained by a gRPC client through StreamExperienceBatches(batch_size=32)
+Rank 0 prints one JSON line (and writes --out)."""
 import argparse
 import json
 import os
@@ -21,7 +29,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(rank, world, games_per_gpu=4096, turns=20, sample=64, out_path=None, port_base=None):
+def run(rank, world, games_per_gpu=4096, turns=20, sample=64, out_path=None, start_turn=100):
     import grpc
     import numpy as np
     import torch
@@ -43,26 +51,79 @@ def run(rank, world, games_per_gpu=4096, turns=20, sample=64, out_path=None, por
     sh = sharding.shard_for(games_per_gpu * world, world, rank)
     e = sharding.create_sharded_engine(lib, sh, device=local, width=W, height=H, num_players=P, host_threads=0)
     e.use_torch_stream()
-    e.reset_seeded(sh.seeds(12345))
     B = sh.count
+    RW = e.packed_words
     mk = lambda *shape, dt=torch.float32: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
-    obs, prev = mk(B, P, 9, H, W), mk(B, P, 9, H, W)
-    smask, pmask = mk(B, P, 4 * W * H, dt=torch.uint8), mk(B, P, 4 * W * H, dt=torch.uint8)
+    pk = [mk(B, RW, dt=torch.int32), mk(B, RW, dt=torch.int32)]          # packed records before / after the turn
     reward, done, aidx = mk(B, P), mk(B, dt=torch.uint8), mk(B, P, dt=torch.int32)
-    e.observe(e.outputs(obs=prev))
-    e.mask(_abi.MASK_SERIALIZER_UDLR, pmask)
+    record_bytes = 2 * RW * 4 + 4 + 4 + 1 + 4 + 4 + 4
 
+    def rewind():
+        e.reset_seeded(sh.seeds(12345))
+        for _ in range(start_turn):
+            e.step(None, _abi.STEP_FLAG_RANDOM_POLICY, 7)
+        e.observe(e.outputs(obs_packed=pk[0]))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(v):
+        if world > 1:
+            t = torch.tensor([v], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
+
+    def step(cur):
+        e.step_fused(None, e.outputs(obs_packed=pk[cur ^ 1], reward=reward, done=done, action_index=aidx),
+                     _abi.STEP_FLAG_RANDOM_POLICY, 7)
+
+    def phase(body):
+        rewind()
+        body(0, 0, warm=True)
+        barrier()
+        t0 = time.perf_counter()
+        cur = 1
+        for t in range(1, turns + 1):
+            body(t, cur, warm=False)
+            cur ^= 1
+        barrier()
+        return reduce_max(time.perf_counter() - t0)
+
+    # ---- phase 1: the step path alone ---------------------------------------------------------------------------------
+    dt_step = phase(lambda t, cur, warm: step(cur))
+
+    # ---- phase 2: every transition of every turn into the learner GPU's HBM ---------------------------------------------
+    got = {"records": 0, "nvlink_bytes": 0, "dropped": 0}
+
+    def gather_all(t, cur, warm):
+        step(cur)
+        rec = sharding.pack_experience_packed(pk[cur], pk[cur ^ 1], aidx, reward, done, start_turn + t + 1, env_id_base=sh.first)
+        g = sharding.gather_experience(rec, dst=0)
+        if rank == 0 and not warm:
+            counts = g["counts"].tolist()
+            got["records"] += sum(counts)
+            got["nvlink_bytes"] += (sum(counts) - counts[0]) * record_bytes
+            got["dropped"] += int(g["dropped"].sum())
+
+    dt_all = phase(gather_all)
+
+    # ---- phase 3: a per-turn sample through the learner's host into the gRPC stream ---------------------------------------
     server = gs = client = None
     streamed = []
     if rank == 0:
         from concurrent import futures
 
         gs = GameServer(lib=lib)
-        server = grpc.server(futures.ThreadPoolExecutor(max_workers=4))
+        server = grpc.server(futures.ThreadPoolExecutor(max_workers=4), options=[("grpc.max_send_message_length", 64 << 20)])
         gs.add_to_server(server)
         port = server.add_insecure_port("127.0.0.1:0")
         server.start()
-        stub = Stub(grpc.insecure_channel(f"127.0.0.1:{port}"), "generals.experience.v1.ExperienceService")
+        channel = grpc.insecure_channel(f"127.0.0.1:{port}", options=[("grpc.max_receive_message_length", 64 << 20)])
+        stub = Stub(channel, "generals.experience.v1.ExperienceService")
         stop = threading.Event()
 
         def drain():
@@ -79,35 +140,46 @@ def run(rank, world, games_per_gpu=4096, turns=20, sample=64, out_path=None, por
         drain.expect = 1 << 60
         client = threading.Thread(target=drain, daemon=True)
         client.start()
+    ingested = {"n": 0}
 
-    gathered = 0
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for t in range(turns):
-        e.step_fused(None, e.outputs(obs=obs, reward=reward, done=done, action_index=aidx), _abi.STEP_FLAG_RANDOM_POLICY, 7)
-        e.mask(_abi.MASK_SERIALIZER_UDLR, smask)
-        rec = sharding.pack_experience(prev, obs, pmask, aidx, reward, done, t + 1, env_id_base=sh.first)
-        rec = {k: v[:sample] for k, v in rec.items()}  # a fixed-size sample of this turn's transitions
-        g = sharding.gather_experience(rec, capacity=sample, dst=0) if world > 1 else rec
-        if rank == 0:
-            gathered += gs.ingest_records(g, W, H)
-        prev, obs = obs, prev
-        pmask, smask = smask, pmask
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    def stream(t, cur, warm):
+        step(cur)
+        rec = sharding.pack_experience_packed(pk[cur], pk[cur ^ 1], aidx, reward, done, start_turn + t + 1, env_id_base=sh.first,
+                                              limit=sample)
+        g = sharding.gather_experience(rec, dst=0)
+        if rank == 0 and not warm:
+            ingested["n"] += gs.ingest_records(g, W, H, players=P)
+
+    dt_stream = phase(stream)
     stats = sharding.all_reduce_stats(e.stats(), device=dev)
     result = None
     if rank == 0:
-        drain.expect = gathered
+        drain.expect = ingested["n"]
         stop.set()
-        client.join(timeout=20)
+        t_wait = time.perf_counter()
+        client.join(timeout=60)
+        drain_tail = time.perf_counter() - t_wait
         server.stop(0)
-        result = dict(n_gpus=world, games_per_gpu=games_per_gpu, turns=turns, env_steps=int(stats[0]),
-                      env_steps_per_s=float(stats[0]) / dt, gathered=gathered, streamed=int(sum(streamed)),
-                      batches=len(streamed), full_batches=int(sum(1 for n in streamed if n == 32)),
-                      note="step + observation + NCCL gather of a per-turn sample + proto conversion on the learner rank")
+        env_steps = B * world * turns
+        result = dict(
+            config="BASELINE configs[4]: 2-player 20x20 self-play -> NCCL gather to the learner rank -> gRPC batch 32",
+            n_gpus=world, games_per_gpu=games_per_gpu, turns_per_phase=turns, start_turn=start_turn,
+            record_bytes=record_bytes, fp32_record_bytes=2 * 9 * W * H * 4 + 4 * W * H // 8 + 21,
+            step_only=dict(ms_per_turn=1e3 * dt_step / turns, env_steps_per_s=env_steps / dt_step),
+            gather_all=dict(ms_per_turn=1e3 * dt_all / turns, env_steps_per_s=env_steps / dt_all,
+                            experiences_per_s_into_learner=got["records"] / dt_all, experiences_per_turn=got["records"] / turns,
+                            nvlink_bytes_per_turn=got["nvlink_bytes"] / turns, nvlink_GBps_into_learner=got["nvlink_bytes"] / dt_all / 1e9,
+                            dropped=got["dropped"], step_path_slowdown=dt_all / dt_step),
+            stream=dict(sample_per_rank_per_turn=sample, ms_per_turn=1e3 * dt_stream / turns, env_steps_per_s=env_steps / dt_stream,
+                        gathered=ingested["n"], streamed=int(sum(streamed)), batches=len(streamed),
+                        full_batches=int(sum(1 for n in streamed if n == 32)),
+                        experiences_per_s=ingested["n"] / dt_stream, grpc_batches_per_s=len(streamed) / (dt_stream + drain_tail),
+                        nvlink_bytes_per_turn=(world - 1) * sample * record_bytes, step_path_slowdown=dt_stream / dt_step),
+            env_steps_total=int(stats[0]),
+            note="wall clock between barrier + cuda synchronize on both sides, max over ranks; the stream phase includes the "
+                 "learner's host work (expansion to float32 tensors, protobuf framing) on rank 0's Python thread")
         if out_path:
-            json.dump(result, open(out_path, "w"))
+            json.dump(result, open(out_path, "w"), indent=1)
         gs.close()
     e.close()
     if world > 1:
@@ -117,12 +189,14 @@ def run(rank, world, games_per_gpu=4096, turns=20, sample=64, out_path=None, por
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--games-per-gpu", type=int, default=4096)
-    ap.add_argument("--turns", type=int, default=20)
-    ap.add_argument("--sample", type=int, default=64)
+    ap.add_argument("--games-per-gpu", type=int, default=65536)
+    ap.add_argument("--turns", type=int, default=40)
+    ap.add_argument("--sample", type=int, default=256)
+    ap.add_argument("--start-turn", type=int, default=100)
+    ap.add_argument("--out", default=None)
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    r = run(rank, world, a.games_per_gpu, a.turns, a.sample)
+    r = run(rank, world, a.games_per_gpu, a.turns, a.sample, a.out, a.start_turn)
     if rank == 0:
         print(json.dumps(r))
     if world > 1:
