@@ -11,10 +11,15 @@ experience record is 2,264 B instead of the 29 KB of two float32 tensors; the le
 serializer action mask on its side (sharding.expand_experience).  Records travel as one byte buffer per rank with its
 actual row count (sharding.gather_experience: one count all-gather + one variable-size transfer per rank, no padding).
 
-Three measured phases, each `--turns` turns from the same mid-episode state (turn 100), timed on every rank between a
+Four measured phases, each `--turns` turns from the same mid-episode state (turn 100), timed on every rank between a
 barrier + cuda synchronize on both sides, max over ranks:
   step_only     the turn kernel alone (the step path without any hand-off)
-  gather_all    + EVERY transition of every turn packed and gathered into the learner GPU's HBM
+  p2p_all       EVERY transition of every turn lands in the learner GPU's HBM with NO extra kernel and NO collective: the
+                turn kernel's own output pointers (obs_packed, reward, done, action_index) are this rank's rows of planes
+                that live on the learner GPU, mapped into every rank through NVLink peer memory
+                (torch.distributed._symmetric_memory), so the kernel's stores ARE the transfer; one device-side barrier
+                per turn tells the learner the turn has landed.  (+ the learner compacting the turn into records)
+  gather_all    the same hand-off through NCCL: records packed on each rank and gathered with send/recv
   stream        + a per-turn sample of `--sample` records per rank gathered, expanded on the learner's host, framed as
                 Experience messages and drained by a gRPC client through StreamExperienceBatches(batch_size=32)
 Rank 0 prints one JSON line (and writes --out)."""
@@ -96,7 +101,63 @@ def run(rank, world, games_per_gpu=4096, turns=20, sample=64, out_path=None, sta
     # ---- phase 1: the step path alone ---------------------------------------------------------------------------------
     dt_step = phase(lambda t, cur, warm: step(cur))
 
-    # ---- phase 2: every transition of every turn into the learner GPU's HBM ---------------------------------------------
+    # ---- phase 2: the turn kernel writes straight into the learner's HBM over NVLink peer memory --------------------------
+    p2p = None
+    if world > 1:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            total = sh.total_envs
+            n_pk, n_small = 2 * total * RW, total * P
+            words = n_pk + 2 * n_small + (total + 3) // 4
+            buf = symm_mem.empty(words, dtype=torch.int32, device=dev)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            learner = hdl.get_buffer(0, (words,), torch.int32, 0)            # rank 0's planes, as seen from this rank
+            L_pk = learner[:n_pk].view(2, total, RW)
+            L_reward = learner[n_pk:n_pk + n_small].view(torch.float32).view(total, P)
+            L_aidx = learner[n_pk + n_small:n_pk + 2 * n_small].view(total, P)
+            L_done = learner[n_pk + 2 * n_small:].view(torch.uint8)[:total]
+            rows = slice(sh.first, sh.first + B)
+            landed = {"records": 0}
+
+            def p2p_body(compact):
+                def body(t, cur, warm):
+                    if warm:
+                        e.observe(e.outputs(obs_packed=L_pk[0, rows]))
+                    e.step_fused(None, e.outputs(obs_packed=L_pk[cur ^ 1, rows], reward=L_reward[rows], done=L_done[rows],
+                                                 action_index=L_aidx[rows]), _abi.STEP_FLAG_RANDOM_POLICY, 7)
+                    hdl.barrier()                                           # device-side: every rank's turn has landed
+                    if rank == 0 and compact:                               # the learner forms this turn's records
+                        rec = sharding.pack_experience_packed(L_pk[cur], L_pk[cur ^ 1], L_aidx, L_reward, L_done, start_turn + t + 1)
+                        if not warm:
+                            landed["records"] += int(rec["action"].shape[0])
+                    if compact:
+                        hdl.barrier()                                       # the planes may be overwritten again
+                return body
+
+            dt_p2p = phase(p2p_body(False))
+            # what landed in the learner's planes is what this rank's kernel would have written at home
+            final = (turns + 1) & 1                                          # parity of the last turn's "after" plane
+            e.observe(e.outputs(obs_packed=pk[0], done=done))
+            torch.cuda.synchronize()
+            same = torch.equal(pk[0], L_pk[final, rows]) and torch.equal(done, L_done[rows])
+            ok = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            dt_p2p_c = phase(p2p_body(True))
+            per_turn = (world - 1) * B * (RW * 4 + P * 8 + 1)
+            p2p = dict(ms_per_turn=1e3 * dt_p2p / turns, env_steps_per_s=B * world * turns / dt_p2p,
+                       experiences_per_s_into_learner=2 * B * world * turns / dt_p2p, nvlink_bytes_per_turn=per_turn,
+                       nvlink_GBps_into_learner=per_turn * turns / dt_p2p / 1e9, step_path_slowdown=dt_p2p / dt_step,
+                       verified=bool(ok.item()),
+                       with_learner_compaction=dict(ms_per_turn=1e3 * dt_p2p_c / turns, experiences_per_s=landed["records"] / dt_p2p_c if rank == 0 else None,
+                                                    step_path_slowdown=dt_p2p_c / dt_step),
+                       how="turn kernel stores into learner-resident planes through NVLink peer memory "
+                           "(torch.distributed._symmetric_memory); one device-side barrier per turn; no NCCL call, no copy kernel")
+            del learner, L_pk, L_reward, L_aidx, L_done, hdl, buf
+        except Exception as exc:  # noqa: BLE001 - reported, the NCCL path below still runs
+            p2p = {"unavailable": repr(exc)[:300]}
+
+    # ---- phase 3: the same hand-off through NCCL: records packed per rank, gathered with send/recv --------------------------
     got = {"records": 0, "nvlink_bytes": 0, "dropped": 0}
 
     def gather_all(t, cur, warm):
@@ -111,7 +172,7 @@ def run(rank, world, games_per_gpu=4096, turns=20, sample=64, out_path=None, sta
 
     dt_all = phase(gather_all)
 
-    # ---- phase 3: a per-turn sample through the learner's host into the gRPC stream ---------------------------------------
+    # ---- phase 4: a per-turn sample through the learner's host into the gRPC stream ---------------------------------------
     server = gs = client = None
     streamed = []
     if rank == 0:
@@ -166,6 +227,7 @@ def run(rank, world, games_per_gpu=4096, turns=20, sample=64, out_path=None, sta
             n_gpus=world, games_per_gpu=games_per_gpu, turns_per_phase=turns, start_turn=start_turn,
             record_bytes=record_bytes, fp32_record_bytes=2 * 9 * W * H * 4 + 4 * W * H // 8 + 21,
             step_only=dict(ms_per_turn=1e3 * dt_step / turns, env_steps_per_s=env_steps / dt_step),
+            p2p_all=p2p,
             gather_all=dict(ms_per_turn=1e3 * dt_all / turns, env_steps_per_s=env_steps / dt_all,
                             experiences_per_s_into_learner=got["records"] / dt_all, experiences_per_turn=got["records"] / turns,
                             nvlink_bytes_per_turn=got["nvlink_bytes"] / turns, nvlink_GBps_into_learner=got["nvlink_bytes"] / dt_all / 1e9,
