@@ -10,7 +10,9 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("W,H,P,B,T", [(10, 10, 2, 65536, 40), (15, 15, 2, 32768, 30), (20, 20, 2, 16384, 60),
-                                        (20, 20, 4, 8192, 40)])
+                                        (20, 20, 4, 8192, 40),
+                                        # the BASELINE configurations at their FULL batch sizes (configs[2], the headline, configs[3])
+                                        (15, 15, 2, 262144, 20), (20, 20, 2, 65536, 20), (20, 20, 4, 65536, 20)])
 def test_digest_parity_at_scale(cuda_lib, oracle_lib, W, H, P, B, T):
     """Every env's full-state digest and its reward/done/mask planes match the oracle while
     both play the same counter-based random policy (BASELINE configs 2-4)."""
