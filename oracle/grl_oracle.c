@@ -1756,7 +1756,7 @@ int grlo_set_state(grlo_env *e, int32_t first, int32_t count, const grl_state_pl
       if (in->owner) g->T[i].owner = in->owner[k];
       if (in->army) g->T[i].army = in->army[k];
       if (in->type) g->T[i].type = in->type[k];
-      if (in->visible) g->T[i].vis = in->visible[k];
+      if (in->visible) g->T[i].vis = in->visible[k] & ((1u << P) - 1u); /* seats beyond P are not addressable (grlcuda.h) */
     }
     if (in->changed) {
       set_clear(g->changed, &g->n_changed, N);

@@ -448,3 +448,39 @@ def kat_fog_lags_one_turn(lib):
     assert (t["visible"][0, 1 * W + 3] & 1) == 1
     assert (t["visible"][0, 0 * W + 3] & 1) == 1 and (t["visible"][0, 2 * W + 3] & 1) == 1
     assert t["vis_changed"][0].sum() == 0
+
+
+# ---- Tile.VisibleBitfield (core/board_test.go:282-370 TestBoard_VisibilityMap / TestTileBitfieldVisibility) -----------
+def kat_visibility_bitfield(lib):
+    """Tile.SetVisible / IsVisibleTo over the uint32 bitfield, through the state codec (grl_state_planes.visible IS
+    Tile.VisibleBitfield) and the per-player read-out (grl_visibility = IsVisibleTo(p) per tile).  The reference's field
+    holds 32 players and ignores ids -1 and 32; this ABI seats GRL_MAX_PLAYERS = 8, so ids 8..31 (and the two invalid
+    ids) are not addressable at all: their bits are dropped by the codec, which is the only place they could enter."""
+    W = H = 3
+    P = 8
+    e = new_engine(lib, W, H, P)
+    s = blank_state(W, H, P)
+    centre = 1 * W + 1
+    # BasicVisibilityOperations: players 0, 3, 7 set, then 0 cleared
+    s["visible"][0, centre] = (1 << 0) | (1 << 3) | (1 << 7)
+    s["visible"][0, 0] = 0b10101010                      # BitfieldDirectManipulation
+    s["visible"][0, 1] = 0xFFFFFFFF                      # AllPlayersVisible (32 bits set in the reference's field)
+    s["visible"][0, 2] = 0xFFFFFFFF & ~(1 << 5)          # ... with one in the middle cleared
+    s["visible"][0, 3] = (1 << 31) | (1 << 8)            # ids beyond the 8 seats: nothing addressable remains
+    e.set_state(s)
+    vis, fog = e.visibility()
+    see = lambda t: [bool(vis[0, p, t]) for p in range(P)]  # noqa: E731
+    assert see(centre) == [True, False, False, True, False, False, False, True]
+    assert see(0) == [False, True, False, True, False, True, False, True]
+    assert see(1) == [True] * 8
+    assert see(2) == [True, True, True, True, True, False, True, True]
+    assert see(3) == [False] * 8 and see(5) == [False] * 8      # unset defaults to false (TestBoard_VisibilityMap)
+    assert not fog.any()                                          # normal tiles never show through fog
+    t = e.get_state()
+    assert t["visible"][0, centre] == 0b10001001 and t["visible"][0, 0] == 0b10101010
+    assert t["visible"][0, 1] == 0xFF and t["visible"][0, 2] == 0xFF & ~(1 << 5) and t["visible"][0, 3] == 0
+    s["visible"][0, centre] &= ~np.uint32(1)             # SetVisible(0, false)
+    e.set_state(s)
+    vis, _ = e.visibility()
+    assert [bool(vis[0, p, centre]) for p in range(P)] == [False, False, False, True, False, False, False, True]
+    e.close()

@@ -153,6 +153,10 @@ def test_replay_and_state_codec_roundtrip(oracle_lib, tmp_path):
     e.reset_seeded(seeds)
     w = replay.ReplayWriter(e, seeds, digest_every=10)
     for t in range(45):
+        if t % 9 == 4:   # a step taken with the in-kernel policy is recorded by its flags and seed alone
+            e.step(None, _abi.STEP_FLAG_RANDOM_POLICY, 1000 + t)
+            w.record(None, _abi.STEP_FLAG_RANDOM_POLICY, 1000 + t)
+            continue
         a = e.sample_actions(4)
         if t % 7 == 3:
             a[t % B, 0]["flags"] = _abi.ACTION_FLAG_SKIP_ENV
@@ -162,9 +166,14 @@ def test_replay_and_state_codec_roundtrip(oracle_lib, tmp_path):
     w.save(path)
     meta, actions = replay.load_replay(path)
     assert meta["turns"] == 45 and actions.shape == (45, B, e.A, 8)
+    assert meta["abi"] == oracle_lib.abi_version() == 2 and meta["config"]["normal_growth_interval"] == 25
     e2 = new_engine(oracle_lib, 10, 10, 2, B)
     assert replay.replay(e2, path) == 45
     assert np.array_equal(e2.state_hash(), e.state_hash())
+    # an engine with other rules is a configuration mismatch, not a divergence
+    for other in (dict(fog_of_war=0), dict(normal_growth_interval=10), dict(env_id_base=5), dict(production_city=2)):
+        with pytest.raises(ValueError, match="different configuration"):
+            replay.replay(new_engine(oracle_lib, 10, 10, 2, B, **other), path)
     # a tampered action stream is caught by the recorded digests
     actions[5, 0, 0, 3] ^= 1
     import io, json, zipfile

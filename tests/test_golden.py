@@ -1,6 +1,10 @@
-"""Committed golden fixtures (tests/golden/*.npz, made by tools/make_golden.py): fixed-seed
-maps and 120-turn trajectories.  The CPU leg pins the oracle to them; the GPU leg runs the
-same rollouts through libgrlcuda.so and must reproduce every recorded plane bit for bit."""
+"""Committed REGRESSION fixtures (tests/golden/rollout_*.npz, made by tools/make_golden.py): fixed-seed maps and
+120-turn trajectories recorded from this repository's own oracle.  They are not reference data — the Go engine cannot
+run here — and pin nothing against the reference; they freeze behaviour, so that a later edit of the oracle OR of the
+kernels that moves any trajectory is noticed.  (Reference pins live elsewhere: tests/kats.py — the reference's own Go
+tests —, the seeded mapgen counts, and tests/golden/gym_ref/ — outputs of the reference's own Python client.)
+The CPU leg checks the oracle against the fixtures; the GPU leg runs the same rollouts through libgrlcuda.so and must
+reproduce every recorded plane bit for bit."""
 import glob
 import os
 
