@@ -15,7 +15,7 @@
 #include "grl_layout.h"
 
 #define FULL 0xffffffffu
-#define GRL_WARPS_PER_CTA 8
+#define GRL_WARPS_PER_CTA 8  // 4 measured equal or slower on every board (profiles/r2_variants.md)
 
 // ---------------------------------------------------------------------------------------
 // small helpers
