@@ -37,9 +37,9 @@ __device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, co
 // CURRENT state (client-side rejection, generals_env.py:226-229), then the opponent's index or the random
 // opponent's draw; decoded moves go to s_act.  Returns whether the agent's action is valid.
 template <int PT, int LG>
-__device__ __noinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK &gk, uint32_t *s, const uint32_t *st,
-                                           uint32_t *s_act, uint32_t alive, bool over, uint32_t turn_before, int game, Geo g,
-                                           int W, int H, int N, int NW);
+__device__ __forceinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK &gk, uint32_t *s, const uint32_t *st,
+                                              uint32_t *s_act, uint32_t alive, bool over, uint32_t turn_before, int game, Geo g,
+                                              int W, int H, int N, int NW, long long a0, long long a1);
 // Elimination orders: tile turnover over the eliminated player's cached list, then the stats
 // rebuild of engine.go:101-109.  Reads and writes own/list/changed/vchg words in the slab.
 template <int PT, int LG>
@@ -164,6 +164,11 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
       }
     }
     // decode this game's action slots while its slab lands
+    long long gym_a0 = 0, gym_a1 = 0;  // the fused gym step's Discrete(N*5) indices: fetched now, tested after the wait
+    if constexpr (GYM) {
+      gym_a0 = __ldg(gk.action + game);
+      if (gk.opponent_action) gym_a1 = __ldg(gk.opponent_action + game);
+    }
     bool skip = false;  // GRL_ACTION_FLAG_SKIP_ENV on slot 0: this env takes no turn in this call
     if (DO_STEP) {
       uint32_t slot0_hi = 0u;
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
       gym_army0 = (int)S.hdr[GRL_HDR_PLAYER0 + GRL_PL_ARMY_COUNT];
       gym_tiles0 = __reduce_add_sync(g.seg, __popc(lst[0]));
       gym_alive0 = alive;
-      skip = !gym_pre_phase<PT, LG>(prm, gk, s, st, s_act, alive, over, turn, game, g, W, H, N, NW);
+      skip = !gym_pre_phase<PT, LG>(prm, gk, s, st, s_act, alive, over, turn, game, g, W, H, N, NW, gym_a0, gym_a1);
     }
 
     if (DO_STEP) {
@@ -813,9 +818,9 @@ __device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, co
 }
 
 template <int PT, int LG>
-__device__ __noinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK &gk, uint32_t *s, const uint32_t *st,
-                                           uint32_t *s_act, uint32_t alive, bool over, uint32_t turn_before, int game, Geo g,
-                                           int W, int H, int N, int NW) {
+__device__ __forceinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK &gk, uint32_t *s, const uint32_t *st,
+                                              uint32_t *s_act, uint32_t alive, bool over, uint32_t turn_before, int game, Geo g,
+                                              int W, int H, int N, int NW, long long a0, long long a1) {
   const GrlLayout &L = prm.L;
   const int P = prm.P;
   SlabView S = make_view(s, st, L);
@@ -862,11 +867,9 @@ __device__ __noinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK 
       s_act[2 * slot + 1] = d.y;
     }
   };
-  const long long a0 = gk.action[game];
   const bool ok0 = gym_ok(a0, 0);
   if (ok0) put(a0, 0, 0);
   if (gk.opponent_action) {
-    const long long a1 = gk.opponent_action[game];
     if (gym_ok(a1, 1)) put(a1, 1, 1);
   } else if (!over) {
     // the reference's default opponent (generals_env.py:443-497): a uniformly random legal FULL move; the
