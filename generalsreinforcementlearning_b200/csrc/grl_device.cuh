@@ -448,4 +448,104 @@ __device__ __forceinline__ void stream_or_mask(uint32_t *strm, uint32_t word, in
   atomicOr(strm + (qs >> 5) + lane, ROT ? rotl4(c) : c);
 }
 
+// ---- the compile-time-scheduled sweep ----------------------------------------------------------------------------------
+// When a warp holds GPW whole games of a baked board and every player template slot is in use (P == PT), the games'
+// [P][CH][N] blocks form ONE run of GPW * TOTAL floats that starts 16-byte aligned (GPW * TOTAL * 4 bytes is a multiple
+// of 16 for GPW = 4), and every position in it is a compile-time constant: the plane and tile of every float, the round
+// (32 float4s = 128 floats, one STG.128 per lane) every float4 falls in, the float4s that straddle two planes or two
+// games.  A game's pass then is straight-line code: per round one stream word (LDS, immediate offset), a rotate, four
+// selects and the store (STG.128, immediate offset) — no loop control, no address arithmetic, no per-lane range tests
+// except in the rounds where a scaled plane begins or ends.  Game gi writes the rounds that END inside its block;
+// the floats of its last, incomplete round are carried (as stream bits, in registers) into the front of the next game's
+// stream, whose first round completes them: every store of the run except the very last covers 512 contiguous bytes.
+template <int TOTAL, int GPW>
+struct CtRun {
+  static_assert((GPW * TOTAL) % 4 == 0, "the run of a warp's games is a whole number of float4s");
+  __host__ __device__ static constexpr int q0(int gi) { return TOTAL * gi; }                     // run float of game gi's first float
+  __host__ __device__ static constexpr int r_lo(int gi) { return q0(gi) / 128; }                 // first round game gi's pass writes
+  __host__ __device__ static constexpr int r_hi(int gi) { return gi + 1 < GPW ? q0(gi + 1) / 128 : (q0(GPW) + 127) / 128; }
+  __host__ __device__ static constexpr int rounds(int gi) { return r_hi(gi) - r_lo(gi); }
+  __host__ __device__ static constexpr int pre(int gi) { return q0(gi) - 128 * r_lo(gi); }       // carried floats in front of the block
+  __host__ __device__ static constexpr int last_active() { return GPW * TOTAL / 4 - 32 * (r_hi(GPW - 1) - 1); }  // lanes of the run's last round
+  __host__ __device__ static constexpr int stream_words() { return (((TOTAL + 127 + 31) / 32 + 1) + 3) & ~3; }
+};
 
+struct CtLane {     // per-lane constants of a run
+  uint32_t sp;      // shared address of the stream word this lane reads in round 0 (round j: + 16 j)
+  uint32_t rot;     // rotate-right amount that leaves the lane's 4-bit field at bits 0-3
+  uint32_t F;       // shared address of the multiplier array + 16 * lane
+  float4 *op;       // the run's first float4 + lane
+  __device__ __forceinline__ void init(const uint32_t *strm, const float *Fp, float *run_base, int lane) {
+    sp = pinned_reg(smem_addr(strm) + 4u * (uint32_t)(lane >> 3));
+    rot = 4u * (uint32_t)(lane & 7);
+    F = pinned_reg(smem_addr(Fp) + 16u * (uint32_t)lane);
+    op = reinterpret_cast<float4 *>(run_base) + lane;
+  }
+};
+
+#define CT_PLAIN 0   // 0/1 floats
+#define CT_F 1       // float4s ka..kz of the stream take multipliers from F (F4[0] = float4 ka)
+#define CT_SCALAR 2  // floats at or after stream float qt are multiplied by tf
+// Local rounds [j0, j1) of a game's pass (global round = rlo + j).  Every argument but `c`, `lane` and `tf` is a constant at
+// the call site: after inlining and unrolling each round is LDS, SHF, the selects and STG.128 with immediate offsets.  Four
+// rounds are loaded before the first is stored, so the shared-memory latencies overlap.
+template <int MODE>
+__device__ __forceinline__ void ct_rounds(const CtLane &c, int lane, int j0, int j1, int rlo, int ka, int kz, int qt, float tf,
+                                          int last_active) {
+#pragma unroll
+  for (int jb = j0; jb < j1; jb += 4) {
+    uint32_t w[4];
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (jb + i < j1) w[i] = lds32(c.sp + 16u * (uint32_t)(jb + i));
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (jb + i < j1) {
+        // four selects instead of the table look-up of StreamSweep: these kernels wait on the shared-memory pipe, not on
+        // issue slots (15x15: main -0.5 %, gym step -1.5 %; the quad writers of 10x10 / 20x20 measured 1-2 % slower this way)
+        const uint32_t n = __funnelshift_r(w[i], w[i], c.rot);  // the lane's 4-bit field at bits 0-3
+        v[i] = make_float4((n & 1u) ? 1.f : 0.f, (n & 2u) ? 1.f : 0.f, (n & 4u) ? 1.f : 0.f, (n & 8u) ? 1.f : 0.f);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (jb + i < j1) {
+        const int j = jb + i;
+        if (MODE == CT_F) {
+          const int lo = ka - 32 * j, hi = kz - 32 * j;  // lanes lo..hi of this round hold float4s ka..kz
+          if (hi >= 0 && lo <= 31) {
+            if ((lo <= 0 || lane >= lo) && (hi >= 31 || lane <= hi)) {
+              const float4 m = lds128(c.F + (uint32_t)(16 * (32 * j - ka)));
+              v[i].x *= m.x;
+              v[i].y *= m.y;
+              v[i].z *= m.z;
+              v[i].w *= m.w;
+            }
+          }
+        } else if (MODE == CT_SCALAR) {
+          const int th = qt - 128 * j;  // floats th.. of this round take the multiplier
+          if (th <= 0) {
+            v[i].x *= tf, v[i].y *= tf, v[i].z *= tf, v[i].w *= tf;
+          } else if (th < 128) {
+            if (4 * lane + 0 >= th) v[i].x *= tf;
+            if (4 * lane + 1 >= th) v[i].y *= tf;
+            if (4 * lane + 2 >= th) v[i].z *= tf;
+            if (4 * lane + 3 >= th) v[i].w *= tf;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (jb + i < j1) {
+        const int j = jb + i;
+        if (last_active < 32 && j == j1 - 1) {
+          if (lane < last_active) __stcs(c.op + 32 * (rlo + j), v[i]);
+        } else {
+          __stcs(c.op + 32 * (rlo + j), v[i]);
+        }
+      }
+    }
+  }
+}

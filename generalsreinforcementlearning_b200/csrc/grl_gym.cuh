@@ -22,7 +22,7 @@ __host__ __device__ inline int grl_gym_smem_words(int P, int NW, int N, int mode
     m = PT * 4 * NW + 5 * ((N + 3) / 4);
   } else if (mode == GRL_GYM_EMIT_LINEAR) {  // gym_emit_linear: concatenated direction streams + (F + bit stream | staged mask words)
     const int dirs = 4 * (((PT * N + 31) / 32 + 1 + 3) & ~3);
-    const int lin_obs = ((2 * N + 8 + 3) & ~3) + ((((PT * GRL_GYM_CHANNELS * N + 7 + 31) / 32 + 1) + 3) & ~3);
+    const int lin_obs = ((2 * N + 8 + 3) & ~3) + ((((PT * GRL_GYM_CHANNELS * N + 127 + 31) / 32 + 1) + 3) & ~3);
     const int lin_mask = 5 * ((PT * N + 3) / 4) + 12;
     m = dirs + (lin_obs > lin_mask ? lin_obs : lin_mask);
   } else {  // gym_emit
@@ -389,7 +389,7 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
   constexpr int NWC = (N + 31) / 32, CH = GRL_GYM_CHANNELS;
   constexpr int DW = ((PT * N + 31) / 32 + 1 + 3) & ~3;                                        // words of one direction stream
   constexpr int FW = (2 * N + 8 + 3) & ~3;
-  constexpr int SW = (((PT * GRL_GYM_CHANNELS * N + 7 + 31) / 32 + 1) + 3) & ~3;
+  constexpr int SW = (((PT * GRL_GYM_CHANNELS * N + 127 + 31) / 32 + 1) + 3) & ~3;
   const GrlLayout &L = prm.L;
   const int P = prm.P, NW = NWC;
   const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
@@ -559,6 +559,90 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
     so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> lane) & 1u);
     so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_GENERAL_IDX];
   }
+  __syncwarp();
+}
+
+// ---- the observation half of gym_emit_linear with a compile-time schedule (a warp's four whole games, P == PT; CtRun /
+// ct_rounds in grl_device.cuh).  Planes 1-2 of a view take their multipliers (0.5 on own tiles, log-army) from F; plane 7
+// (turn fraction, the same on every tile) multiplies by a register, with the float4 that straddles planes 6 and 7 split
+// by compile-time lane tests; plane 8 is zeros, so the carried floats of a game's incomplete round are zero bits.
+// `sw` is the warp's scratch as gym_emit_linear lays it out; the mask half (gym_emit_linear with obs == nullptr) reuses
+// F and the stream as its staging area.
+template <int PT, int N, int GI>
+__device__ __forceinline__ void gym_run_game_obs(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+                                                 const uint32_t *s, const uint32_t *stt, const CtLane &c, uint32_t *sw,
+                                                 int lane, const Geo &g) {
+  constexpr int NWC = (N + 31) / 32, CH = GRL_GYM_CHANNELS, TOTAL = PT * CH * N, NW = NWC;
+  using R = CtRun<TOTAL, 4>;
+  constexpr int DW = ((PT * N + 31) / 32 + 1 + 3) & ~3;
+  constexpr int FW = (2 * N + 8 + 3) & ~3;
+  constexpr int SW = (((PT * GRL_GYM_CHANNELS * N + 127 + 31) / 32 + 1) + 3) & ~3;
+  static_assert(SW >= R::stream_words(), "the stream holds a carried round in front of the block");
+  constexpr int PRE = R::pre(GI), RLO = R::r_lo(GI), NR = R::rounds(GI);
+  const GrlLayout &L = prm.L;
+  const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+  float *F = reinterpret_cast<float *>(sw + 4 * DW);
+  uint32_t *strm = sw + 4 * DW + FW;
+  uint4 *strm4 = reinterpret_cast<uint4 *>(strm);
+  const bool w = lane < NWC;
+  const uint32_t valid = w ? g.valid : 0u;
+  const uint32_t M = w ? stt[lane] : 0u, C = w ? stt[NW + lane] : 0u, G = w ? stt[2 * NW + lane] : 0u;
+  uint32_t any_own = 0;
+#pragma unroll
+  for (int p = 0; p < PT; p++)
+    if (w) any_own |= s[L.off_own + p * NW + lane];
+  // the carried floats in front of the block are the previous game's plane 8: zero bits, like the rest of a fresh stream
+  static_assert(PRE <= N, "the carried round lies inside the previous game's last plane");
+  for (int k = lane; k < SW / 4; k += 32) strm4[k] = make_uint4(0u, 0u, 0u, 0u);
+  float lg[NWC];  // log(army + 1) / 10 of tiles lane, lane + 32, ...
+#pragma unroll
+  for (int j = 0; j < NWC; j++) {
+    const int t = lane + 32 * j;
+    lg[j] = t < N ? __ldg(logtab + army[t]) : 0.f;  // logtab[0] == 0
+  }
+  const float tf = fminf(__fdiv_rn((float)s[GRL_HDR_TURN], (float)max_turns), 1.0f);
+  __syncwarp();
+  if (lane <= NWC) {
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      const uint32_t v = w ? (prm.fog ? s[L.off_vis + p * NW + lane] : valid) : 0u;
+      const uint32_t ch[CH - 1] = {v, v & any_own, v, valid & ~(M | C | G), M, C, G, valid};  // plane 8 stays zero
+#pragma unroll
+      for (int k = 0; k < CH - 1; k++) stream_or_mask<NWC, false>(strm, ch[k], PRE + (p * CH + k) * N, lane);
+    }
+  }
+  __syncwarp();
+  int jdone = 0;
+#pragma unroll
+  for (int p = 0; p < PT; p++) {
+    const int qv = PRE + p * CH * N;  // this view's first stream float
+    // ---- planes 1 (ownership: 0.5 on own tiles in sight, 1 on enemy tiles) and 2 (log army in sight) ------------------
+    const int qa = qv + N, qz = qa + 2 * N - 1, sa = qa & 3, ka = qa >> 2, kz = qz >> 2, ja = ka >> 5, jz = kz >> 5;
+    ct_rounds<CT_PLAIN>(c, lane, jdone, ja, RLO, 0, 0, 0, 0.f, 32);
+    __syncwarp();  // F is free
+    {
+      const uint32_t mine = w ? ((prm.fog ? s[L.off_vis + p * NW + lane] : valid) & s[L.off_own + p * NW + lane]) : 0u;
+#pragma unroll
+      for (int j = 0; j < NWC; j++) {
+        const int t = lane + 32 * j;
+        const uint32_t mw = __shfl_sync(FULL, mine, j);
+        if (t < N) {
+          F[sa + t] = ((mw >> lane) & 1u) ? 0.5f : 1.f;
+          F[sa + N + t] = lg[j];
+        }
+      }
+      if (lane < sa) F[lane] = 1.f;
+      if (lane < 4) F[sa + 2 * N + lane] = 1.f;
+    }
+    __syncwarp();
+    ct_rounds<CT_F>(c, lane, ja, jz + 1, RLO, ka, kz, 0, 0.f, 32);
+    // ---- plane 7: min(turn / max_turns, 1) on every tile; the rounds that hold it end inside plane 8 (zeros) -----------
+    const int qt = qv + 7 * N, jt0 = qt >> 7, jt1 = (qt + N - 1) >> 7;
+    ct_rounds<CT_PLAIN>(c, lane, jz + 1, jt0, RLO, 0, 0, 0, 0.f, 32);
+    ct_rounds<CT_SCALAR>(c, lane, jt0, jt1 + 1, RLO, 0, 0, qt, tf, 32);
+    jdone = jt1 + 1;
+  }
+  ct_rounds<CT_PLAIN>(c, lane, jdone, NR, RLO, 0, 0, 0, 0.f, GI == 3 ? R::last_active() : 32);
   __syncwarp();
 }
 

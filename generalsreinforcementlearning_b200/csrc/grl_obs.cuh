@@ -4,10 +4,11 @@
 #include "grl_device.cuh"
 
 // per-warp shared-memory words of the bit-stream observation writer (only baked boards with N % 4 != 0): the
-// army-multiplier array F [2N + 8] and the block's bit stream (one bit per float, up to 7 lead bits, one spare word)
+// army-multiplier array F [2N + 8] and the block's bit stream (one bit per float, up to 127 carried lead bits — a whole
+// round, see CtRun in grl_device.cuh — and one spare word)
 __host__ __device__ constexpr int grl_obs_region_words(int N) { return (2 * N + 8 + 3) & ~3; }
 __host__ __device__ constexpr int grl_obs_stream_words(int N, int PT) {
-  return (((PT * GRL_OBS_CHANNELS * N + 7 + 31) / 32 + 1) + 3) & ~3;
+  return (((PT * GRL_OBS_CHANNELS * N + 127 + 31) / 32 + 1) + 3) & ~3;
 }
 __host__ __device__ constexpr int grl_obs_scratch_words(int TW, int TH, int PT, int NW) {
   return (TW > 0 && ((TW * TH) & 3) != 0) ? grl_obs_region_words(TW * TH) + grl_obs_stream_words(TW * TH, PT) : 0;
@@ -215,5 +216,75 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
     sw.scaled(qs, qs + 2 * N - 1, F_sa, lane);
   }
   sw.finish(lane);
+  __syncwarp();
+}
+
+// ---- the same writer with a compile-time schedule (a warp's four whole games, P == PT; CtRun / ct_rounds in
+// grl_device.cuh).  Game GI of the run: its stream starts with the `carry` words of the previous game's incomplete round,
+// every plane's bit offset, every round and the army rounds' float4 ranges are constants.  `carry` returns this game's
+// own incomplete round for the next game.
+template <int PT, int N, int GI>
+__device__ __forceinline__ void obs_run_game(const GrlKParams &prm, const SlabView &S, const CtLane &c, uint32_t *scratch,
+                                             int NW, int lane, uint4 &carry) {
+  constexpr int NWC = (N + 31) / 32, CH = GRL_OBS_CHANNELS, TOTAL = PT * CH * N;
+  using R = CtRun<TOTAL, 4>;
+  constexpr int SW = grl_obs_stream_words(N, PT);
+  static_assert(SW >= R::stream_words(), "the stream holds a carried round in front of the block");
+  constexpr int PRE = R::pre(GI), RLO = R::r_lo(GI), NR = R::rounds(GI);
+  float *F = reinterpret_cast<float *>(scratch);  // [2N + 8]
+  uint32_t *strm = scratch + grl_obs_region_words(N);
+  uint4 *strm4 = reinterpret_cast<uint4 *>(strm);
+  for (int w = lane; w < SW / 4; w += 32) strm4[w] = w == 0 ? carry : make_uint4(0u, 0u, 0u, 0u);
+  float fr[NWC];  // army / 1000 of tiles lane, lane + 32, ...
+#pragma unroll
+  for (int j = 0; j < NWC; j++) {
+    const int t = lane + 32 * j;
+    fr[j] = t < N ? army_frac((uint32_t)S.army[t]) : 0.f;
+  }
+  __syncwarp();
+  if (lane <= NWC) {
+    const bool w = lane < NWC;
+    const uint32_t valid = w ? prm.geom[lane] : 0u;
+    const uint32_t M = w ? S.M[lane] : 0u;
+    const uint32_t CG = w ? (S.C[lane] | S.G[lane]) : 0u;
+    uint32_t any_own = 0;
+#pragma unroll
+    for (int p = 0; p < PT; p++)
+      if (w) any_own |= S.own[p * NW + lane];
+#pragma unroll
+    for (int p = 0; p < PT; p++) {
+      const uint32_t own = w ? S.own[p * NW + lane] : 0u;
+      const uint32_t v = w ? (prm.fog ? S.vis[p * NW + lane] : valid) : 0u;
+      const uint32_t nm = v & ~M;
+      const uint32_t mine = nm & own, enemy = nm & any_own & ~own;   // serializer.go:75-90
+      const uint32_t ch[CH] = {mine, enemy, mine, enemy, nm & ~any_own, nm & CG, v & M, v, ~v & valid};
+#pragma unroll
+      for (int k = 0; k < CH; k++) stream_or_mask<NWC, false>(strm, ch[k], PRE + (p * CH + k) * N, lane);
+    }
+  }
+  __syncwarp();
+  int jdone = 0;
+#pragma unroll
+  for (int p = 0; p < PT; p++) {
+    // this view's two army planes: stream floats [qa, qa + 2N)
+    const int qa = PRE + p * CH * N, qz = qa + 2 * N - 1, s = qa & 3, ka = qa >> 2, kz = qz >> 2, ja = ka >> 5, jz = kz >> 5;
+    ct_rounds<CT_PLAIN>(c, lane, jdone, ja, RLO, 0, 0, 0, 0.f, 32);
+    __syncwarp();  // the previous view's army rounds are done with F
+#pragma unroll
+    for (int j = 0; j < NWC; j++) {
+      const int t = lane + 32 * j;
+      if (t < N) {
+        F[s + t] = fr[j];
+        F[s + N + t] = fr[j];
+      }
+    }
+    if (lane < s) F[lane] = 1.f;
+    if (lane < 4) F[s + 2 * N + lane] = 1.f;
+    __syncwarp();
+    ct_rounds<CT_F>(c, lane, ja, jz + 1, RLO, ka, kz, 0, 0.f, 32);
+    jdone = jz + 1;
+  }
+  ct_rounds<CT_PLAIN>(c, lane, jdone, NR, RLO, 0, 0, 0, 0.f, GI == 3 ? R::last_active() : 32);
+  if (GI < 3) carry = strm4[NR];
   __syncwarp();
 }

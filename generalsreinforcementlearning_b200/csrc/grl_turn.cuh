@@ -165,9 +165,14 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
     }
     // decode this game's action slots while its slab lands
     long long gym_a0 = 0, gym_a1 = 0;  // the fused gym step's Discrete(N*5) indices: fetched now, tested after the wait
+    int gym_tn = 0, gym_cl = 0;        // the env's turn / call counters: read-modify-write at the end, loaded now
     if constexpr (GYM) {
       gym_a0 = __ldg(gk.action + game);
       if (gk.opponent_action) gym_a1 = __ldg(gk.opponent_action + game);
+      if (l == 0) {
+        gym_tn = gk.turns[game];
+        gym_cl = gk.calls[game];
+      }
     }
     bool skip = false;  // GRL_ACTION_FLAG_SKIP_ENV on slot 0: this env takes no turn in this call
     if (DO_STEP) {
@@ -576,7 +581,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
       const int tiles1 = __reduce_add_sync(g.seg, act_lane ? __popc(S.list[l]) : 0);
       if (l == 0) {
         const int valid = skip ? 0 : 1;
-        const int tn = gk.turns[game] + valid, cl = gk.calls[game] + 1;
+        const int tn = gym_tn + valid, cl = gym_cl + 1;
         gk.turns[game] = tn;
         gk.calls[game] = cl;
         const bool term = over && valid;
@@ -608,6 +613,31 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
   if constexpr (GYM) {
     // the client's read-outs of the new state, one game of the warp after the other (obs, N*5 mask, PlayerState)
     const Geo g32 = make_geo(prm, W, lane, 32);
+    if constexpr (TW > 0 && ((TW * TH) & 3) != 0 && GPW == 4) {
+      // four whole games, every player slot in use: the observation blocks are one 16-byte aligned run with a
+      // compile-time schedule (gym_run_game_obs); the mask bytes and PlayerStates follow game by game
+      if (gk.obs && P == PT && (warp_game0 & 3) == 0 && warp_game0 + GPW <= game_end) {
+        constexpr int NT = TW > 0 ? TW * TH : 5;
+        constexpr int DW = ((PT * NT + 31) / 32 + 1 + 3) & ~3, FW = (2 * NT + 8 + 3) & ~3;
+        CtLane c;
+        c.init(s_obs + 4 * DW + FW, reinterpret_cast<const float *>(s_obs + 4 * DW),
+               gk.obs + (size_t)warp_game0 * (PT * GRL_GYM_CHANNELS * NT), lane);
+        {
+          const uint32_t *s0 = wbase, *s1 = wbase + per_game, *s2 = wbase + 2 * per_game, *s3 = wbase + 3 * per_game;
+          gym_run_game_obs<PT, NT, 0>(prm, gk.max_turns, gk.logtab, s0, s0 + L.slab_words, c, s_obs, lane, g32);
+          gym_run_game_obs<PT, NT, 1>(prm, gk.max_turns, gk.logtab, s1, s1 + L.slab_words, c, s_obs, lane, g32);
+          gym_run_game_obs<PT, NT, 2>(prm, gk.max_turns, gk.logtab, s2, s2 + L.slab_words, c, s_obs, lane, g32);
+          gym_run_game_obs<PT, NT, 3>(prm, gk.max_turns, gk.logtab, s3, s3 + L.slab_words, c, s_obs, lane, g32);
+        }
+#pragma unroll 1
+        for (int gi = 0; gi < GPW; gi++) {  // the mask bytes and PlayerStates (F and the stream are their staging area now)
+          const uint32_t *sg = wbase + gi * per_game;
+          gym_emit_linear<PT, NT>(prm, gk.max_turns, gk.logtab, nullptr, gk.mask, gk.stats, sg, sg + L.slab_words, s_lut, s_obs,
+                                  warp_game0 + gi, lane, g32, false, false);
+        }
+        return;
+      }
+    }
 #pragma unroll 1
     for (int gi = 0; gi < GPW; gi++) {
       const int game_g = warp_game0 + gi;
@@ -686,6 +716,21 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
   if (prm.obs) {
     if (TW > 0) {
       // baked boards: the whole warp writes one game's block after the other, from the slabs in shared memory
+      if constexpr (TW > 0 && ((TW * TH) & 3) != 0 && GPW == 4) {
+        // four whole games, every player slot in use: one 16-byte aligned run with a compile-time schedule
+        if (P == PT && (warp_game0 & 3) == 0 && warp_game0 + GPW <= game_end) {
+          constexpr int NT = TW > 0 ? TW * TH : 5;
+          CtLane c;
+          c.init(s_obs + grl_obs_region_words(NT), reinterpret_cast<const float *>(s_obs),
+                 prm.obs + (size_t)warp_game0 * (PT * GRL_OBS_CHANNELS * NT), lane);
+          uint4 carry = make_uint4(0u, 0u, 0u, 0u);
+          obs_run_game<PT, NT, 0>(prm, make_view(wbase + 0 * per_game, wbase + 0 * per_game + L.slab_words, L), c, s_obs, NW, lane, carry);
+          obs_run_game<PT, NT, 1>(prm, make_view(wbase + 1 * per_game, wbase + 1 * per_game + L.slab_words, L), c, s_obs, NW, lane, carry);
+          obs_run_game<PT, NT, 2>(prm, make_view(wbase + 2 * per_game, wbase + 2 * per_game + L.slab_words, L), c, s_obs, NW, lane, carry);
+          obs_run_game<PT, NT, 3>(prm, make_view(wbase + 3 * per_game, wbase + 3 * per_game + L.slab_words, L), c, s_obs, NW, lane, carry);
+          return;
+        }
+      }
 #pragma unroll 1
       for (int gi = 0; gi < GPW; gi++) {
         const int game_g = warp_game0 + gi;
