@@ -207,8 +207,13 @@ __device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, c
 // [P][9][N] block as one linear sweep of 128-bit stores with compile-time addressing.  The N*5 mask bytes of a
 // player (tile-major, {up,right,down,left,any} per tile) are 20 bytes per quad: a lane assembles its five words,
 // the warp stages them in shared memory and copies them out as a linear sweep.
+#ifdef GRL_GYM_EMIT_CALL
+#define GRL_GYM_EMIT_FN __noinline__
+#else
+#define GRL_GYM_EMIT_FN __forceinline__
+#endif
 template <int PT, int N>
-__device__ __forceinline__ void gym_emit_quads(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+__device__ GRL_GYM_EMIT_FN void gym_emit_quads(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
                                                float *__restrict__ obs, uint8_t *__restrict__ mask,
                                                int32_t *__restrict__ stats, const uint32_t *s, const uint32_t *stt,
                                                const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g) {
@@ -381,7 +386,7 @@ __device__ __forceinline__ void gym_emit_quads(const GrlKParams &prm, int max_tu
 // concatenated into P*N-bit streams, a lane expands a quad of four tiles into five words (as gym_emit_quads does), and the
 // staged words leave as an aligned 32-bit sweep shifted by the block's misalignment.
 template <int PT, int N>
-__device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+__device__ GRL_GYM_EMIT_FN void gym_emit_linear(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
                                                 float *__restrict__ obs, uint8_t *__restrict__ mask,
                                                 int32_t *__restrict__ stats, const uint32_t *s, const uint32_t *stt,
                                                 const float4 *lut, uint32_t *sw, int game, int lane, const Geo &g,
@@ -569,7 +574,7 @@ __device__ __forceinline__ void gym_emit_linear(const GrlKParams &prm, int max_t
 // `sw` is the warp's scratch as gym_emit_linear lays it out; the mask half (gym_emit_linear with obs == nullptr) reuses
 // F and the stream as its staging area.
 template <int PT, int N, int GI>
-__device__ __forceinline__ void gym_run_game_obs(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
+__device__ GRL_GYM_EMIT_FN void gym_run_game_obs(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
                                                  const uint32_t *s, const uint32_t *stt, const CtLane &c, uint32_t *sw,
                                                  int lane, const Geo &g) {
   constexpr int NWC = (N + 31) / 32, CH = GRL_GYM_CHANNELS, TOTAL = PT * CH * N, NW = NWC;
