@@ -207,11 +207,7 @@ __device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, c
 // [P][9][N] block as one linear sweep of 128-bit stores with compile-time addressing.  The N*5 mask bytes of a
 // player (tile-major, {up,right,down,left,any} per tile) are 20 bytes per quad: a lane assembles its five words,
 // the warp stages them in shared memory and copies them out as a linear sweep.
-#ifdef GRL_GYM_EMIT_CALL
-#define GRL_GYM_EMIT_FN __noinline__
-#else
-#define GRL_GYM_EMIT_FN __forceinline__
-#endif
+#define GRL_GYM_EMIT_FN __forceinline__  // as real calls (__noinline__) the emitters measured 6-13 % slower
 template <int PT, int N>
 __device__ GRL_GYM_EMIT_FN void gym_emit_quads(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
                                                float *__restrict__ obs, uint8_t *__restrict__ mask,
@@ -351,8 +347,11 @@ __device__ GRL_GYM_EMIT_FN void gym_emit_quads(const GrlKParams &prm, int max_tu
           o[4] = __byte_perm(__byte_perm(URh, DLh, 0x0763), Ab, 0x7210);
         }
       }
-      __syncwarp();
       uint8_t *base = mask + ((size_t)game * P + p) * (size_t)(N * 5);
+      __syncwarp();
+      // (one bulk copy per view, cp.async.bulk.global.shared::cta, instead of these stores: 20x20 2-4 % slower with either
+      // L2 policy and with the copy overlapped by the view's planes; 10x10, whole game as one run, equal.  The 15x15 writer
+      // below gains 4 % from it and keeps it.)
       if constexpr (MW % 4 == 0) {
         uint4 *dst = reinterpret_cast<uint4 *>(base);
         const uint4 *src = reinterpret_cast<const uint4 *>(s_stage);
@@ -409,6 +408,12 @@ __device__ GRL_GYM_EMIT_FN void gym_emit_linear(const GrlKParams &prm, int max_t
 #pragma unroll
   for (int p = 0; p < PT; p++)
     if (p < P && w) any_own |= s[L.off_own + p * NW + lane];
+  // the previous game's bulk copy of its mask bytes must have read the staging area before it is written again: here when
+  // the observation pass comes first (its stream and F share the area), else only before the mask words are staged
+  if (obs) {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+  }
 
   if (obs) {
     const int planes = P * CH, total = planes * N;
@@ -522,6 +527,52 @@ __device__ GRL_GYM_EMIT_FN void gym_emit_linear(const GrlKParams &prm, int max_t
     const size_t goff = (size_t)game * bytes;
     const int mis = (int)(goff & 3u), woff = (int)(((goff - mis) >> 2) & 3u);
     const uint8_t *bd = reinterpret_cast<const uint8_t *>(s_dir);
+    const int b0 = 4 * woff + mis, b1 = b0 + bytes;            // the block in line coordinates (below)
+    uint8_t *line0 = mask + goff - b0;                          // 16-byte aligned
+    if ((mis & 1) == 0) {
+      // The staging area becomes a byte image of the 16-byte lines the block touches: stage byte i <-> line0[i].  The whole
+      // lines leave as ONE bulk copy (cp.async.bulk.global.shared::cta, SASS UBLKCP) issued by lane 0, the ragged ends
+      // (at most 14 bytes each) as 16-bit stores.  A block that starts 2 bytes into a word is staged in halfwords.
+      uint16_t *img = reinterpret_cast<uint16_t *>(stage);
+      if (!obs) {  // (the direction streams above were built while the previous copy drained)
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+      for (int q = lane; q < quads; q += 32) {
+        const int b = q >> 1, bsh = 4 * (q & 1);
+        const uint32_t U = (bd[b] >> bsh) & 0xfu, R = (bd[4 * DW + b] >> bsh) & 0xfu;
+        const uint32_t D = (bd[8 * DW + b] >> bsh) & 0xfu, Lm = (bd[12 * DW + b] >> bsh) & 0xfu, A = U | R | D | Lm;
+        auto spread = [](uint32_t n) -> uint32_t { return (n * 0x00204081u) & 0x01010101u; };
+        const uint32_t Ub = spread(U), Rb = spread(R), Db = spread(D), Lb = spread(Lm), Ab = spread(A);
+        const uint32_t UR = __byte_perm(Ub, Rb, 0x5140), URh = __byte_perm(Ub, Rb, 0x7362);
+        const uint32_t DL = __byte_perm(Db, Lb, 0x5140), DLh = __byte_perm(Db, Lb, 0x7362);
+        const uint32_t o0 = __byte_perm(UR, DL, 0x5410);   // (byte layout: see the word-staged path below)
+        const uint32_t o1 = __byte_perm(__byte_perm(UR, DL, 0x6320), Ab, 0x3214);
+        const uint32_t o2 = __byte_perm(__byte_perm(DL, URh, 0x5403), Ab, 0x3250);
+        const uint32_t o3 = __byte_perm(__byte_perm(DLh, URh, 0x6010), Ab, 0x3610);
+        const uint32_t o4 = __byte_perm(__byte_perm(URh, DLh, 0x0763), Ab, 0x7210);
+        if (mis == 0) {
+          uint32_t *o = stage + woff + 5 * q;
+          o[0] = o0, o[1] = o1, o[2] = o2, o[3] = o3, o[4] = o4;
+        } else {
+          uint16_t *o = img + 2 * (woff + 5 * q) + 1;
+          o[0] = (uint16_t)o0, o[1] = (uint16_t)(o0 >> 16), o[2] = (uint16_t)o1, o[3] = (uint16_t)(o1 >> 16);
+          o[4] = (uint16_t)o2, o[5] = (uint16_t)(o2 >> 16), o[6] = (uint16_t)o3, o[7] = (uint16_t)(o3 >> 16);
+          o[8] = (uint16_t)o4, o[9] = (uint16_t)(o4 >> 16);
+        }
+      }
+      fence_proxy_async_smem();  // every lane's staged bytes become visible to the async proxy
+      __syncwarp();
+      const int l0 = (b0 + 15) >> 4, l1 = b1 >> 4;                // whole lines [l0, l1)
+      if (lane == 0 && l1 > l0) {
+        tma_store(line0 + 16 * l0, reinterpret_cast<const uint8_t *>(stage) + 16 * l0, (uint32_t)(16 * (l1 - l0)));
+        tma_store_commit();
+      }
+      for (int x = b0 + 2 * lane; x < 16 * l0 && x < b1; x += 64) *reinterpret_cast<uint16_t *>(line0 + x) = img[x >> 1];
+      for (int x = (l1 > l0 ? 16 * l1 : 16 * l0) + 2 * lane; x < b1; x += 64) *reinterpret_cast<uint16_t *>(line0 + x) = img[x >> 1];
+    } else {  // odd byte offsets (an odd number of views): staged as words, shifted on the way out
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
     if (lane < 4) stage[lane] = 0u;  // the words before the first quad's (read by the shifted copy, never stored)
     for (int q = lane; q < quads; q += 32) {
       const int b = q >> 1, bsh = 4 * (q & 1);
@@ -544,8 +595,6 @@ __device__ GRL_GYM_EMIT_FN void gym_emit_linear(const GrlKParams &prm, int max_t
     // word 4 + i holds the bytes of line word i shifted up by `mis` bytes: line word i = bytes [4i - mis, 4i - mis + 4)
     // of the staged run = funnel(staged[4 + i - 1], staged[4 + i]) >> 8 (4 - mis).  The block covers line bytes
     // [b0, b1): whole lines go out as 128-bit stores, the ragged ends as bytes.
-    const int b0 = 4 * woff + mis, b1 = b0 + bytes;
-    uint8_t *line0 = mask + goff - b0;                          // 16-byte aligned
     const int shb = (32 - 8 * mis) & 31, adj = mis ? 0 : 1;
     auto line_word = [&](int i) -> uint32_t { return __funnelshift_r(stage[3 + i + adj], stage[4 + i + adj], shb); };
     const int l0 = (b0 + 15) >> 4, l1 = b1 >> 4;                // whole lines [l0, l1)
@@ -554,6 +603,7 @@ __device__ GRL_GYM_EMIT_FN void gym_emit_linear(const GrlKParams &prm, int max_t
     // ragged ends: bytes [b0, 16 l0) and [16 l1, b1) (at most 15 each); byte x of the line space = byte x & 3 of line word x >> 2
     for (int x = b0 + lane; x < 16 * l0 && x < b1; x += 32) line0[x] = (uint8_t)(line_word(x >> 2) >> (8 * (x & 3)));
     for (int x = (l1 > l0 ? 16 * l1 : 16 * l0) + lane; x < b1; x += 32) line0[x] = (uint8_t)(line_word(x >> 2) >> (8 * (x & 3)));
+    }
   }
   if (stats && lane < P) {
     int tiles = 0;
