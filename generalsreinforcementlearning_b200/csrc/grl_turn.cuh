@@ -611,13 +611,6 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
   __syncwarp();  // every group's slab in shared memory is final: the plane read-outs below are warp-wide
 
   if constexpr (GYM) {
-#ifdef GRL_GYM_NO_MASK  // measurement only: the launch without its mask bytes and PlayerStates
-    uint8_t *const gk_mask = nullptr;
-    int32_t *const gk_stats = nullptr;
-#else
-    uint8_t *const gk_mask = gk.mask;
-    int32_t *const gk_stats = gk.stats;
-#endif
     // the client's read-outs of the new state, one game of the warp after the other (obs, N*5 mask, PlayerState)
     const Geo g32 = make_geo(prm, W, lane, 32);
     if constexpr (TW > 0 && ((TW * TH) & 3) != 0 && GPW == 4) {
@@ -639,7 +632,7 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
 #pragma unroll 1
         for (int gi = 0; gi < GPW; gi++) {  // the mask bytes and PlayerStates (F and the stream are their staging area now)
           const uint32_t *sg = wbase + gi * per_game;
-          gym_emit_linear<PT, NT>(prm, gk.max_turns, gk.logtab, nullptr, gk_mask, gk_stats, sg, sg + L.slab_words, s_lut, s_obs,
+          gym_emit_linear<PT, NT>(prm, gk.max_turns, gk.logtab, nullptr, gk.mask, gk.stats, sg, sg + L.slab_words, s_lut, s_obs,
                                   warp_game0 + gi, lane, g32, false, false);
         }
         return;
@@ -651,13 +644,13 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
       if (game_g >= game_end) break;
       const uint32_t *sg = wbase + gi * per_game;
       if constexpr (TW > 0 && ((TW * TH) & 3) == 0)
-        gym_emit_quads<PT, (TW > 0 && ((TW * TH) & 3) == 0 ? TW * TH : 4)>(prm, gk.max_turns, gk.logtab, gk.obs, gk_mask, gk_stats, sg,
+        gym_emit_quads<PT, (TW > 0 && ((TW * TH) & 3) == 0 ? TW * TH : 4)>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg,
                                                                           sg + L.slab_words, s_lut, s_obs, game_g, lane, g32);
       else if constexpr (TW > 0)
-        gym_emit_linear<PT, (TW > 0 ? TW * TH : 5)>(prm, gk.max_turns, gk.logtab, gk.obs, gk_mask, gk_stats, sg, sg + L.slab_words,
+        gym_emit_linear<PT, (TW > 0 ? TW * TH : 5)>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg, sg + L.slab_words,
                                                     s_lut, s_obs, game_g, lane, g32, gi > 0, gi + 1 < GPW && game_g + 1 < game_end);
       else
-        gym_emit<0>(prm, gk.max_turns, gk.logtab, gk.obs, gk_mask, gk_stats, sg, sg + L.slab_words, s_obs, game_g, lane, g32);
+        gym_emit<0>(prm, gk.max_turns, gk.logtab, gk.obs, gk.mask, gk.stats, sg, sg + L.slab_words, s_obs, game_g, lane, g32);
     }
     if (lane == 0) tma_store_wait_read();  // bulk stores of the mask bytes: the stage stays valid until they have read it
     return;

@@ -413,6 +413,25 @@ def test_pinned_host_results_are_written_in_place(cuda_lib, oracle_lib):
     assert np.array_equal(gc.state_hash(), oc.state_hash())
 
 
+@pytest.mark.parametrize("W,H,P,B", [(15, 15, 2, 8202), (15, 15, 4, 8197), (15, 15, 3, 8200)])
+def test_observation_run_writer_through_host_subranges(cuda_lib, oracle_lib, W, H, P, B):
+    """15x15 observation tensors in HOST memory for a ragged batch >= 8192: the call is pipelined as sub-ranges, whole
+    warps take the compile-time-scheduled run writer (four games per run, P == PT), the last, partial warp and P < PT the
+    run-time-scheduled one; every float must equal the oracle's, block edges between sub-ranges and writers included."""
+    gc, oc = new_engine(cuda_lib, W, H, P, B, host_threads=0), new_engine(oracle_lib, W, H, P, B, host_threads=0)
+    seeds = np.arange(B, dtype=np.int64) + 99
+    gc.reset_seeded(seeds)
+    oc.reset_seeded(seeds)
+    go, oo = gc.alloc_outputs_host(), oc.alloc_outputs_host()
+    for t in range(8):
+        go["obs"].fill(-3.0)
+        acts = oc.sample_actions(5)
+        gc.step_fused(acts, gc.outputs(**go))
+        oc.step_fused(acts, oc.outputs(**oo))
+        compare_outputs(go, oo, f"turn {t}")
+    assert np.array_equal(gc.state_hash(), oc.state_hash())
+
+
 @pytest.mark.parametrize("W,H,P,fog", [(20, 20, 2, 1), (15, 15, 2, 1), (10, 10, 2, 1), (20, 20, 4, 1), (7, 13, 3, 1), (15, 15, 2, 0)])
 def test_packed_observation_records(cuda_lib, oracle_lib, W, H, P, fog):
     """grl_step_outputs.obs_packed (the host-delivery read-out): the kernel's records equal the oracle's word for word,

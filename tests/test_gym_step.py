@@ -96,6 +96,8 @@ CASES = [  # W, H, P, B, steps, max_turns, self_play
     (15, 15, 2, 130, 40, 500, True),    # 8 lanes per game, self-play opponent indices
     (20, 20, 2, 96, 60, 500, False),    # one game per warp
     (20, 20, 4, 40, 50, 35, False),     # four players: players 2,3 keep the synthetic policy's half-move bit
+    (15, 15, 4, 38, 30, 40, False),     # four views per game on the run writer (P == PT = 4), partial last warp
+    (15, 15, 3, 37, 30, 40, False),     # P < PT: run-time-scheduled writer; odd byte offsets of the mask blocks
     (7, 13, 3, 33, 40, 500, True),      # generic geometry
     (5, 5, 2, 64, 80, 500, False),      # tiny boards finish: terminated, +-100, eliminated-opponent bonus
 ]
