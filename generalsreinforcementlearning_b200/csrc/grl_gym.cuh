@@ -274,6 +274,7 @@ __device__ GRL_GYM_EMIT_FN void gym_emit_quads(const GrlKParams &prm, int max_tu
     if (!prm.fog) nV[p] = livem;
     seen |= nV[p];
   }
+  auto emit_obs_block = [&]() {
   if (obs) {
     float f[NCH][4];  // log(army + 1) / 10 of the lane's quads
 #pragma unroll
@@ -321,6 +322,8 @@ __device__ GRL_GYM_EMIT_FN void gym_emit_quads(const GrlKParams &prm, int max_tu
       }
     }
   }
+  };
+  auto emit_mask_block = [&]() {
   if (mask) {
     constexpr int MW = 5 * NQ;  // words of one player's mask
     for (int p = 0; p < P; p++) {
@@ -363,6 +366,11 @@ __device__ GRL_GYM_EMIT_FN void gym_emit_quads(const GrlKParams &prm, int max_tu
       __syncwarp();
     }
   }
+  };
+  // the short mask runs first, then the long observation sweep (20x20: 0.4165 -> 0.4095 ms; the other order of the two
+  // output streams, and default-policy instead of streaming stores for the mask words, measured slower)
+  emit_mask_block();
+  emit_obs_block();
   if (stats && lane < P) {
     int tiles = 0;
     for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + lane * NW + k]);
