@@ -68,6 +68,11 @@ struct grl_env {
   cudaStream_t pipe[kPipe] = {};
   cudaEvent_t ev_start = nullptr, ev_done[kPipe] = {};
   int pipe_chunks = 6;  // GRL_PIPE_CHUNKS=1 disables the pipelining (e2e: 160 M env-steps/s at 1, 169 M at 4, 170 M at 6-8)
+  // launch overlap (grl_turn.cuh): per-warp epoch words, the sequence number of the last turn launch, and that number again
+  // while nothing else has been enqueued on the stream since (the next whole-batch turn launch may then overlap it)
+  uint32_t *d_epoch = nullptr;
+  uint32_t epoch_seq = 0, overlap_prev = 0;
+  int overlap = 1;      // GRL_LAUNCH_OVERLAP=0 serialises the launches as CUDA does by default
 };
 
 namespace {
@@ -295,7 +300,7 @@ int upload_and_reset(grl_env *env, const int32_t *env_ids, int n, const std::vec
   }
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_reset(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, n, env->stream));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   CUDA_TRY(cudaStreamSynchronize(env->stream));
   (void)L;
   return GRL_OK;
@@ -450,8 +455,18 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
   if (!do_step && !do_out) return GRL_OK;
 
   if (!any_staged) {  // device (or device-addressable) buffers only: one launch on the env's stream
+    // it may overlap the previous turn launch when that is still the last thing this library put on the stream (whatever
+    // else the caller enqueued in between is serialised by CUDA as always); never while the stream is being captured:
+    // a replayed graph would carry stale sequence numbers
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(env->stream, &cap) != cudaSuccess) cudaGetLastError(), cap = cudaStreamCaptureStatusActive;
+    const bool live = cap == cudaStreamCaptureStatusNone;
+    prm.epoch = live ? env->d_epoch : nullptr;
+    prm.epoch_seq = live ? ++env->epoch_seq : 0u;
+    prm.epoch_need = (live && env->overlap && !zero_copied) ? env->overlap_prev : 0u;
     CUDA_TRY(grl_launch_turn(prm, do_step, do_out, env->stream));
     env->launches++;
+    env->overlap_prev = live ? prm.epoch_seq : 0u;
     if (zero_copied) CUDA_TRY(cudaStreamSynchronize(env->stream));  // host buffers are valid / consumed on return
     return GRL_OK;
   }
@@ -483,7 +498,7 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
     pk.game0 = (int)g0;
     pk.game_end = (int)g1;
     CUDA_TRY(grl_launch_turn(pk, do_step, do_out, sq));
-    env->launches++;
+    env->launches++, env->overlap_prev = 0;
     for (int i = 0; i < n_planes; i++) {
       const OutBuf &ob = planes[i].ob;
       if (ob.staged)
@@ -570,6 +585,8 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   if (pc && atoi(pc) >= 1) env->pipe_chunks = atoi(pc);
   const char *pf = getenv("GRL_PREFETCH_DIST");
   env->prefetch_dist = pf ? atoi(pf) : 8192;  // ~1.7 waves of resident warps ahead (profiles/r1_variants.md)
+  const char *ov = getenv("GRL_LAUNCH_OVERLAP");
+  if (ov) env->overlap = atoi(ov) != 0;
   auto bail = [&](int code) {
     grl_destroy(env);
     return code;
@@ -583,6 +600,9 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   const size_t sbytes_al = (sbytes + 255) & ~(size_t)255, tbytes_al = (tbytes + 255) & ~(size_t)255;
   if (cudaMalloc((void **)&env->d_state, sbytes_al + tbytes_al + 96 * 4) != cudaSuccess)
     return bail(fail(GRL_ERR_NOMEM, "cudaMalloc of %zu state bytes: %s", sbytes + tbytes, cudaGetErrorString(cudaGetLastError())));
+  if (cudaMalloc((void **)&env->d_epoch, (size_t)cfg->num_envs * 4) != cudaSuccess ||
+      cudaMemsetAsync(env->d_epoch, 0, (size_t)cfg->num_envs * 4, env->stream) != cudaSuccess)
+    return bail(fail(GRL_ERR_NOMEM, "cudaMalloc of the epoch words: %s", cudaGetErrorString(cudaGetLastError())));
   env->d_static = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(env->d_state) + sbytes_al);
   env->d_geom = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(env->d_static) + tbytes_al);
   uint32_t geom[96];
@@ -594,7 +614,7 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   GrlKParams prm = base_params(env);
   if (grl_launch_mark_over(prm, env->stream) != cudaSuccess || cudaStreamSynchronize(env->stream) != cudaSuccess)
     return bail(fail(GRL_ERR_CUDA, "state init kernel: %s", cudaGetErrorString(cudaGetLastError())));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   *out = env;
   return GRL_OK;
 }
@@ -607,6 +627,7 @@ int grl_destroy(grl_env *env) {
     if (s.ptr) cudaFree(s.ptr);
   if (env->d_logtab) cudaFree(env->d_logtab);
   if (env->d_state) cudaFree(env->d_state);  // d_static and d_geom live in the same allocation
+  if (env->d_epoch) cudaFree(env->d_epoch);
   for (int k = 0; k < grl_env::kPipe; k++) {
     if (env->pipe[k]) cudaStreamDestroy(env->pipe[k]);
     if (env->ev_done[k]) cudaEventDestroy(env->ev_done[k]);
@@ -629,6 +650,7 @@ int grl_set_stream(grl_env *env, void *cuda_stream) {
   CUDA_TRY(cudaSetDevice(env->cfg.device));
   CUDA_TRY(cudaStreamSynchronize(env->stream));  // work already issued stays ordered
   env->stream = static_cast<cudaStream_t>(cuda_stream);  // NULL is CUDA's default stream
+  env->overlap_prev = 0;
   return GRL_OK;
 }
 
@@ -691,7 +713,7 @@ static int reset_seeded_device(grl_env *env, const int32_t *env_ids, int32_t n, 
                                d_failed, env->stream));
     GrlKParams prm = base_params(env);
     CUDA_TRY(grl_launch_reset(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, cn, env->stream));
-    env->launches += 2;
+    env->launches += 2, env->overlap_prev = 0;
     int failed = 0;
     CUDA_TRY(cudaMemcpyAsync(&failed, d_failed, 4, cudaMemcpyDeviceToHost, env->stream));
     CUDA_TRY(cudaStreamSynchronize(env->stream));
@@ -763,13 +785,13 @@ int grl_mask(grl_env *env, int variant, void *out) {
     case GRL_MASK_SERIALIZER_UDLR:
       if ((st = bind_out(env, SL_MISC, out, B * P * N * 4, ob))) return st;
       CUDA_TRY(grl_launch_mask_bytes(prm, variant == GRL_MASK_ENGINE_URDL ? 0 : 1, (uint8_t *)ob.dev, env->stream));
-      env->launches++;
+      env->launches++, env->overlap_prev = 0;
       break;
     case GRL_MASK_ENGINE_URDL_BITS:
       if ((st = bind_out(env, SL_MASK, out, B * P * words * 4, ob))) return st;
       prm.mask_bits = (uint32_t *)ob.dev;
       CUDA_TRY(grl_launch_turn(prm, false, true, env->stream));
-      env->launches++;
+      env->launches++, env->overlap_prev = 0;
       break;
     case GRL_MASK_ENGINE_HALF_BITS: {
       void *tmp = nullptr;
@@ -778,7 +800,7 @@ int grl_mask(grl_env *env, int variant, void *out) {
       prm.mask_bits = (uint32_t *)tmp;
       CUDA_TRY(grl_launch_turn(prm, false, true, env->stream));
       CUDA_TRY(grl_launch_mask_replicate((const uint32_t *)tmp, (uint32_t *)ob.dev, B * P, (int)words, 2, env->stream));
-      env->launches += 2;
+      env->launches += 2, env->overlap_prev = 0;
       break;
     }
     default:
@@ -800,7 +822,7 @@ int grl_visibility(grl_env *env, uint8_t *visible, uint8_t *fog) {
   if ((st = bind_out(env, SL_MISC2, fog, bytes, f))) return st;
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_visibility(prm, (uint8_t *)v.dev, (uint8_t *)f.dev, env->stream));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   bool need_sync = false;
   if ((st = flush_out(env, v, need_sync))) return st;
   if ((st = flush_out(env, f, need_sync))) return st;
@@ -833,7 +855,7 @@ int grl_gym_observe(grl_env *env, int32_t max_turns, const grl_gym_outputs *out)
   if ((st = bind_out(env, SL_MISC2, out->stats, B * P * 4 * 4, stats))) return st;
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_gym(prm, max_turns, env->d_logtab, (float *)obs.dev, (uint8_t *)mask.dev, (int32_t *)stats.dev, env->stream));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   bool need_sync = false;
   if ((st = flush_out(env, obs, need_sync))) return st;
   if ((st = flush_out(env, mask, need_sync))) return st;
@@ -859,7 +881,7 @@ int grl_gym_observe_envs(grl_env *env, int32_t max_turns, const int32_t *env_ids
   CUDA_TRY(cudaMemcpyAsync(d_ids, env_ids, (size_t)n * 4, cudaMemcpyHostToDevice, env->stream));
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_gym(prm, max_turns, env->d_logtab, out->obs, out->mask, out->stats, env->stream, (const int32_t *)d_ids, n));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   CUDA_TRY(cudaStreamSynchronize(env->stream));  // env_ids (pageable host memory) is consumed on return
   return GRL_OK;
 }
@@ -875,7 +897,7 @@ int grl_gym_encode(grl_env *env, const int64_t *action_idx, int32_t player, int3
     return fail(GRL_ERR_UNSUPPORTED, "grl_gym_encode takes device pointers (it is the device-side glue of the vector env)");
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_gym_encode(prm, (const long long *)action_idx, player, slot, mask, skip_invalid, actions, valid, env->stream));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   return GRL_OK;
 }
 
@@ -916,7 +938,7 @@ int grl_gym_autoreset(grl_env *env, int32_t max_turns, int64_t base_seed, const 
   CUDA_TRY(grl_launch_reset(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, B, sq, d_count));
   CUDA_TRY(grl_launch_gym(prm, max_turns, env->d_logtab, io->out.obs, io->out.mask, io->out.stats, sq, d_ids, B, d_count));
   if (io->n_reset) CUDA_TRY(cudaMemcpyAsync(io->n_reset, d_count, 4, cudaMemcpyDeviceToDevice, sq));
-  env->launches += io->final_obs ? 7 : 6;
+  env->launches += io->final_obs ? 7 : 6, env->overlap_prev = 0;
   return GRL_OK;
 }
 
@@ -927,7 +949,7 @@ int grl_gym_sample(grl_env *env, uint64_t seed, const uint8_t *mask, int32_t pla
   if (!is_device_ptr(mask) || !is_device_ptr(action)) return fail(GRL_ERR_UNSUPPORTED, "grl_gym_sample takes device pointers");
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_gym_sample(prm, seed, mask, player, (long long *)action, env->stream));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   return GRL_OK;
 }
 
@@ -971,7 +993,7 @@ int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const 
   pt.step_error = io->step_error;
   if (io->n_finished) CUDA_TRY(cudaMemsetAsync(io->n_finished, 0, 4, sq));
   CUDA_TRY(grl_launch_gym_step(pt, gk, sq));
-  env->launches += 1;
+  env->launches += 1, env->overlap_prev = 0;
   return GRL_OK;
 }
 
@@ -985,7 +1007,7 @@ int grl_sample_actions(grl_env *env, uint64_t policy_seed, grl_action *actions) 
   GrlKParams prm = base_params(env);
   prm.policy_seed = policy_seed;
   CUDA_TRY(grl_launch_sample(prm, ob.dev, env->stream));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   bool need_sync = false;
   if ((st = flush_out(env, ob, need_sync))) return st;
   if (need_sync) CUDA_TRY(cudaStreamSynchronize(env->stream));
@@ -1086,7 +1108,7 @@ int grl_state_hash(grl_env *env, uint64_t *out) {
   if ((st = bind_out(env, SL_MISC, out, (size_t)env->cfg.num_envs * 8, ob))) return st;
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_state_hash(prm, (uint64_t *)ob.dev, env->stream));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   bool need_sync = false;
   if ((st = flush_out(env, ob, need_sync))) return st;
   if (need_sync) CUDA_TRY(cudaStreamSynchronize(env->stream));
@@ -1107,7 +1129,7 @@ int grl_buffer_hash(grl_env *env, const void *buf, size_t row_words, int32_t row
   OutBuf ob;
   if ((st = bind_out(env, SL_MISC, out, (size_t)rows * 8, ob))) return st;
   CUDA_TRY(grl_launch_buffer_hash((const uint32_t *)dbuf, row_words, rows, (uint64_t *)ob.dev, env->stream));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   bool need_sync = dbuf != buf;
   if ((st = flush_out(env, ob, need_sync))) return st;
   if (need_sync) CUDA_TRY(cudaStreamSynchronize(env->stream));
@@ -1123,7 +1145,7 @@ int grl_stats(grl_env *env, uint64_t out[4]) {
   CUDA_TRY(cudaMemsetAsync(d, 0, 32, env->stream));
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_stats(prm, (unsigned long long *)d, env->stream));
-  env->launches++;
+  env->launches++, env->overlap_prev = 0;
   CUDA_TRY(cudaMemcpyAsync(out, d, 32, cudaMemcpyDeviceToHost, env->stream));
   CUDA_TRY(cudaStreamSynchronize(env->stream));
   return GRL_OK;

@@ -96,6 +96,11 @@ struct GrlKParams {
   int fog, pg, pc, pn, grow_interval;
   int env_id_base;
   int prefetch_dist;        // > 0: the warp of game g prefetches the slab of game g + dist into L2
+  // Overlapped launches (grl_turn.cuh, "launch overlap"): one word per warp of the grid.  A warp publishes epoch_seq when
+  // everything it wrote is visible; with epoch_need != 0 it first waits until the warp that held its games in the previous
+  // launch has published at least epoch_need.  nullptr: neither.
+  uint32_t *epoch;
+  uint32_t epoch_need, epoch_seq;
   float rw[11];
 };
 

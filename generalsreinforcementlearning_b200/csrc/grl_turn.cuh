@@ -83,8 +83,7 @@ struct TurnOccupancy {  // CTAs of 256 threads per SM the register budget is tun
 };
 
 template <int PT, int TW, int TH, int LG, bool DO_STEP, bool DO_OUT, bool GYM>
-__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>::kMinBlocks)
-    grl_turn_kernel(const __grid_constant__ GrlKParams prm, const __grid_constant__ GrlGymK gk) {
+__device__ __forceinline__ void grl_turn_body(const GrlKParams &prm, const GrlGymK &gk) {
   static_assert(!GYM || (DO_STEP && DO_OUT), "the fused gym step is a turn plus read-outs");
   constexpr int GPW = 32 / LG;  // games per warp
   static_assert(LG == 32 || LG == 16 || LG == 8 || LG == 4, "a group is 4, 8, 16 or 32 lanes");
@@ -838,6 +837,49 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>:
   }
 }
 
+// ---- launch overlap -------------------------------------------------------------------------------------------------
+// A launch costs 12-14 us beyond its per-game time whatever the board (the first wave loads and steps before any store
+// is issued, the last one drains alone; t(B) is linear in B with that intercept: profiles/r2_variants.md) — 4 % of the
+// headline launch, 12 % of a 10x10 one.  Consecutive turn launches of one env therefore OVERLAP: every CTA lets the next
+// launch in the stream start as soon as this grid is fully resident (griddepcontrol.launch_dependents, "programmatic
+// dependent launch"), so that its CTAs take the SM slots this grid's last wave leaves idle.  Games are independent, so
+// what the next launch must wait for is not this GRID but the WARP that holds the same games: a warp publishes the
+// launch's sequence number in its word of prm.epoch (st.release.gpu after a warp barrier: slab, planes and scalars of
+// its games are visible) and, when the host marked the launch as overlapping (epoch_need != 0), first waits until its
+// word has reached the previous launch's number (ld.acquire.gpu) — no griddepcontrol.wait, which would wait for the
+// whole previous grid.  The warp -> games map is the same in every turn launch of an env; any other work on the stream
+// (sampling, resets, copies, the caller's own kernels) does not trigger early and is serialised as always.
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int PT, int TW, int TH, int LG, bool DO_STEP, bool DO_OUT, bool GYM>
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>::kMinBlocks)
+    grl_turn_kernel(const __grid_constant__ GrlKParams prm, const __grid_constant__ GrlGymK gk) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  uint32_t *flag = nullptr;
+  if (prm.epoch) {
+    constexpr int GPW = 32 / LG;
+    flag = prm.epoch + prm.game0 / GPW + blockIdx.x * GRL_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (prm.epoch_need) {
+      if ((threadIdx.x & 31) == 0)
+        while ((int32_t)(ld_acquire_gpu(flag) - prm.epoch_need) < 0) __nanosleep(40);
+      __syncwarp();
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // the slab is read by the async proxy (cp.async.bulk)
+    }
+  }
+  grl_turn_body<PT, TW, TH, LG, DO_STEP, DO_OUT, GYM>(prm, gk);
+  if (flag) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) st_release_gpu(flag, prm.epoch_seq);
+  }
+}
+
 template <int PT, int LG>
 __device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t *s_act,
                                           uint32_t alive, uint32_t turn_before, int game, Geo g, int W, int H, int N, int NW) {
@@ -1026,6 +1068,20 @@ static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream, con
   // store phases out of step with each other, which keeps the observation store stream busy
   const int per_cta = GRL_WARPS_PER_CTA * (32 / LG);
   int grid = (prm.game_end - prm.game0 + per_cta - 1) / per_cta;
+  if (prm.epoch && prm.epoch_need) {  // may start while the previous turn launch of the stream drains (launch overlap)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid < 1 ? 1 : grid);
+    cfg.blockDim = dim3(GRL_WARPS_PER_CTA * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, prm, gk);
+  }
   kern<<<grid < 1 ? 1 : grid, GRL_WARPS_PER_CTA * 32, smem, stream>>>(prm, gk);
   return cudaGetLastError();
 }

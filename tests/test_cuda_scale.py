@@ -175,3 +175,52 @@ def test_step_is_cuda_graph_capturable(cuda_lib, oracle_lib):
         assert np.array_equal(reward[K - 1].cpu().numpy().view(np.uint32), oo["reward"].view(np.uint32))
         assert np.array_equal(obs[K - 1].cpu().numpy().view(np.uint32), oo["obs"].view(np.uint32))
     assert int(e.get_state(0, 1)["turn"][0]) == K * 4
+
+
+@pytest.mark.parametrize("W,H,P,B,T", [(10, 10, 2, 65536, 80), (15, 15, 2, 40002, 50), (20, 20, 2, 32768, 50), (20, 20, 4, 8192, 40)])
+def test_overlapped_launches_keep_parity(cuda_lib, oracle_lib, W, H, P, B, T, monkeypatch):
+    """Turn launches enqueued back to back overlap on the device (programmatic dependent launch + per-warp epoch words,
+    grl_turn.cuh): the next launch's warps start while the previous grid drains and wait only for the warp that held
+    their games.  T launches without a host synchronisation in between must leave exactly the state and the read-outs
+    of T oracle turns — and of the same launches serialised (GRL_LAUNCH_OVERLAP=0)."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    seeds = np.arange(B, dtype=np.int64) + 777
+
+    def run(overlap):
+        monkeypatch.setenv("GRL_LAUNCH_OVERLAP", "1" if overlap else "0")
+        e = new_engine(cuda_lib, W, H, P, B, host_threads=0)
+        e.reset_seeded(seeds)
+        obs = torch.empty((B, P, 9, H, W), dtype=torch.float32, device=dev)
+        mask = torch.empty((B, P, e.mask_words), dtype=torch.int32, device=dev)
+        reward = torch.empty((B, P), dtype=torch.float32, device=dev)
+        done = torch.empty(B, dtype=torch.uint8, device=dev)
+        outs = e.outputs(obs=obs, mask_bits=mask, reward=reward, done=done)
+        for t in range(T):          # no synchronisation: every launch may overlap the one before
+            if t % 7 == 3:
+                e.step(None, _abi.STEP_FLAG_RANDOM_POLICY, 4711)          # step-only launches in the same chain
+            else:
+                e.step_fused(None, outs, _abi.STEP_FLAG_RANDOM_POLICY, 4711)
+        torch.cuda.synchronize()
+        return e, obs, mask.cpu().numpy().view(np.uint32), reward.cpu().numpy().view(np.uint32), done.cpu().numpy()
+
+    oc = new_engine(oracle_lib, W, H, P, B, host_threads=0)
+    oc.reset_seeded(seeds)
+    oo = oc.alloc_outputs_host()
+    for t in range(T):
+        if t % 7 == 3:
+            oc.step(None, _abi.STEP_FLAG_RANDOM_POLICY, 4711)
+        else:
+            oc.step_fused(None, oc.outputs(**({k: oo[k] for k in ("mask_bits", "reward", "done")} if t < T - 1 else oo)),
+                          _abi.STEP_FLAG_RANDOM_POLICY, 4711)
+    rows, words = B * P, 9 * W * H
+    want_obs = oc.buffer_hash(oo["obs"], words, rows)
+    for overlap in (True, False):
+        e, obs, mask, reward, done = run(overlap)
+        assert np.array_equal(e.state_hash(), oc.state_hash()), f"overlap={overlap}"
+        assert np.array_equal(reward, oo["reward"].view(np.uint32)) and np.array_equal(done, oo["done"]), f"overlap={overlap}"
+        assert np.array_equal(mask, oo["mask_bits"]), f"overlap={overlap}"
+        assert np.array_equal(e.buffer_hash(obs, words, rows), want_obs), f"overlap={overlap}"
+        assert np.array_equal(e.stats(), oc.stats())
+        e.close()
