@@ -72,6 +72,7 @@ struct grl_env {
   // while nothing else has been enqueued on the stream since (the next whole-batch turn launch may then overlap it)
   uint32_t *d_epoch = nullptr;
   uint32_t epoch_seq = 0, overlap_prev = 0;
+  bool overlap_published = false;  // the launch overlap_prev names wrote its epoch words
   int overlap = 1;      // GRL_LAUNCH_OVERLAP=0 serialises the launches as CUDA does by default
 };
 
@@ -460,13 +461,23 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
     // a replayed graph would carry stale sequence numbers
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(env->stream, &cap) != cudaSuccess) cudaGetLastError(), cap = cudaStreamCaptureStatusActive;
-    const bool live = cap == cudaStreamCaptureStatusNone;
-    prm.epoch = live ? env->d_epoch : nullptr;
-    prm.epoch_seq = live ? ++env->epoch_seq : 0u;
-    prm.epoch_need = (live && env->overlap && !zero_copied) ? env->overlap_prev : 0u;
+    // A launch PUBLISHES its epoch words (a release fence at the end of every warp: 1-4 % of an isolated launch) only
+    // inside a chain: the stream still has work and the last thing this library enqueued was a turn launch.  The first
+    // launch of a chain runs as always, the second publishes, from the third on they overlap their predecessor.
+    bool chain = false;
+    if (cap == cudaStreamCaptureStatusNone && env->overlap && !zero_copied && env->overlap_prev != 0) {
+      const cudaError_t q = cudaStreamQuery(env->stream);
+      if (q == cudaErrorNotReady) cudaGetLastError(), chain = true;
+      else if (q != cudaSuccess) return fail(GRL_ERR_CUDA, "cudaStreamQuery: %s", cudaGetErrorString(q));
+    }
+    const uint32_t seq = ++env->epoch_seq ? env->epoch_seq : ++env->epoch_seq;  // never 0
+    prm.epoch = chain ? env->d_epoch : nullptr;
+    prm.epoch_seq = seq;
+    prm.epoch_need = (chain && env->overlap_published) ? env->overlap_prev : 0u;
     CUDA_TRY(grl_launch_turn(prm, do_step, do_out, env->stream));
     env->launches++;
-    env->overlap_prev = live ? prm.epoch_seq : 0u;
+    env->overlap_prev = (cap == cudaStreamCaptureStatusNone) ? seq : 0u;
+    env->overlap_published = chain;
     if (zero_copied) CUDA_TRY(cudaStreamSynchronize(env->stream));  // host buffers are valid / consumed on return
     return GRL_OK;
   }
