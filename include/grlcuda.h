@@ -26,7 +26,14 @@
  * device memory (detected with cudaPointerGetAttributes; host buffers are staged
  * through library scratch and copied on the env's stream, and the call returns
  * after the copy completes).  Calls with device buffers are asynchronous on the
- * env's stream; use grl_sync().
+ * env's stream; use grl_sync().  Turn launches (grl_step / grl_step_fused with
+ * device buffers) that follow each other on the stream with nothing in between
+ * OVERLAP on the device: the later launch starts while the earlier grid drains and
+ * its warps wait only for the warp that held their games (programmatic dependent
+ * launch + per-warp release/acquire words).  Stream order as the caller sees it is
+ * unchanged — anything enqueued after call k, on this stream or behind an event,
+ * finds call k complete, and a kernel or copy enqueued between two calls
+ * serialises them as always.  GRL_LAUNCH_OVERLAP=0 turns the overlap off.
  *
  * The same ABI, prefixed grlo_, is exported by the CPU oracle (oracle/) — test
  * infrastructure only.
