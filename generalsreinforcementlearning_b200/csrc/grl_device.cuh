@@ -455,23 +455,31 @@ __device__ __forceinline__ void stream_or_mask(uint32_t *strm, uint32_t word, in
 // ---- the compile-time-scheduled sweep ----------------------------------------------------------------------------------
 // When a warp holds GPW whole games of a baked board and every player template slot is in use (P == PT), the games'
 // [P][CH][N] blocks form ONE run of GPW * TOTAL floats that starts 16-byte aligned (GPW * TOTAL * 4 bytes is a multiple
-// of 16 for GPW = 4), and every position in it is a compile-time constant: the plane and tile of every float, the round
-// (32 float4s = 128 floats, one STG.128 per lane) every float4 falls in, the float4s that straddle two planes or two
-// games.  A game's pass then is straight-line code: per round one stream word (LDS, immediate offset), a rotate, four
-// selects and the store (STG.128, immediate offset) — no loop control, no address arithmetic, no per-lane range tests
-// except in the rounds where a scaled plane begins or ends.  Game gi writes the rounds that END inside its block;
-// the floats of its last, incomplete round are carried (as stream bits, in registers) into the front of the next game's
-// stream, whose first round completes them: every store of the run except the very last covers 512 contiguous bytes.
+// of 16 for GPW = 4).  The run is written in ROUNDS of 32 float4s (128 floats, one STG.128 per lane).  Game gi writes the
+// rounds that END inside its block; the floats of its last, incomplete round are carried (as stream bits, in registers)
+// into the front of the next game's stream, whose first round completes them: every store of the run except the very last
+// covers 512 contiguous bytes.  A game's pass is straight-line code: the round index of every load and store is a
+// compile-time constant (LDS / STG.128 with immediate offsets from one base each, no loop control, no address arithmetic);
+// what depends on the game — the number `pre` of carried floats in front of its block (0..127), hence where in the stream
+// a scaled plane begins and ends — enters as a handful of registers, and the rounds a scaled plane CAN touch for any `pre`
+// carry a per-lane range test.  One copy of the pass serves the four games of a warp: four specialised copies (every
+// range a constant) executed 5 % fewer instructions and ran 3-4 % slower — the kernels wait on instruction fetch
+// (`no_instruction` 1.9 -> 4.3 stall cycles per issue with the four copies).
 template <int TOTAL, int GPW>
 struct CtRun {
   static_assert((GPW * TOTAL) % 4 == 0, "the run of a warp's games is a whole number of float4s");
+  static constexpr int NR_MIN = TOTAL / 128;    // every game's pass writes at least this many rounds,
+  static constexpr int NR_MAX = NR_MIN + 2;     // at most this many (a carried round in front, the run's last round)
   __host__ __device__ static constexpr int q0(int gi) { return TOTAL * gi; }                     // run float of game gi's first float
   __host__ __device__ static constexpr int r_lo(int gi) { return q0(gi) / 128; }                 // first round game gi's pass writes
   __host__ __device__ static constexpr int r_hi(int gi) { return gi + 1 < GPW ? q0(gi + 1) / 128 : (q0(GPW) + 127) / 128; }
   __host__ __device__ static constexpr int rounds(int gi) { return r_hi(gi) - r_lo(gi); }
   __host__ __device__ static constexpr int pre(int gi) { return q0(gi) - 128 * r_lo(gi); }       // carried floats in front of the block
   __host__ __device__ static constexpr int last_active() { return GPW * TOTAL / 4 - 32 * (r_hi(GPW - 1) - 1); }  // lanes of the run's last round
-  __host__ __device__ static constexpr int stream_words() { return (((TOTAL + 127 + 31) / 32 + 1) + 3) & ~3; }
+  __host__ __device__ static constexpr int stream_words() { return 4 * NR_MAX; }
+  // rounds [win_lo(c), win_hi(c, len)] are the ones a plane range [pre + c, pre + c + len) can touch for some pre in 0..127
+  __host__ __device__ static constexpr int win_lo(int c) { return c / 128; }
+  __host__ __device__ static constexpr int win_hi(int c, int len) { return (c + 127 + len - 1) / 128; }
 };
 
 struct CtLane {     // per-lane constants of a run
@@ -489,13 +497,16 @@ struct CtLane {     // per-lane constants of a run
 
 #define CT_PLAIN 0   // 0/1 floats
 #define CT_F 1       // float4s ka..kz of the stream take multipliers from F (F4[0] = float4 ka)
-#define CT_SCALAR 2  // floats at or after stream float qt are multiplied by tf
-// Local rounds [j0, j1) of a game's pass (global round = rlo + j).  Every argument but `c`, `lane` and `tf` is a constant at
-// the call site: after inlining and unrolling each round is LDS, SHF, the selects and STG.128 with immediate offsets.  Four
-// rounds are loaded before the first is stored, so the shared-memory latencies overlap.
+#define CT_SCALAR 2  // stream floats qt .. qt + n - 1 are multiplied by tf
+#define CT_ALL_ROUNDS (1 << 20)
+// Rounds [j0, j1) of a game's pass; `op` is the lane's float4 of the pass's round 0.  j0 and j1 are constants at the call
+// site, so after inlining and unrolling each round is LDS, SHF, four selects and STG.128 with immediate offsets; four
+// rounds are loaded before the first is stored, so the shared-memory latencies overlap.  ka, kz, Fb (= c.F - 16 ka), qt
+// are the game's registers; `nr` = rounds the pass has (CT_ALL_ROUNDS when [j0, j1) certainly exist), `last_lanes` = lanes
+// of round nr - 1 that store.
 template <int MODE>
-__device__ __forceinline__ void ct_rounds(const CtLane &c, int lane, int j0, int j1, int rlo, int ka, int kz, int qt, float tf,
-                                          int last_active) {
+__device__ __forceinline__ void ct_rounds(const CtLane &c, float4 *op, int lane, int j0, int j1, int ka, int kz, uint32_t Fb,
+                                          int qt, int n, float tf, int nr, int last_lanes) {
 #pragma unroll
   for (int jb = j0; jb < j1; jb += 4) {
     uint32_t w[4];
@@ -508,8 +519,8 @@ __device__ __forceinline__ void ct_rounds(const CtLane &c, int lane, int j0, int
       if (jb + i < j1) {
         // four selects instead of the table look-up of StreamSweep: these kernels wait on the shared-memory pipe, not on
         // issue slots (15x15: main -0.5 %, gym step -1.5 %; the quad writers of 10x10 / 20x20 measured 1-2 % slower this way)
-        const uint32_t n = __funnelshift_r(w[i], w[i], c.rot);  // the lane's 4-bit field at bits 0-3
-        v[i] = make_float4((n & 1u) ? 1.f : 0.f, (n & 2u) ? 1.f : 0.f, (n & 4u) ? 1.f : 0.f, (n & 8u) ? 1.f : 0.f);
+        const uint32_t nib = __funnelshift_r(w[i], w[i], c.rot);  // the lane's 4-bit field at bits 0-3
+        v[i] = make_float4((nib & 1u) ? 1.f : 0.f, (nib & 2u) ? 1.f : 0.f, (nib & 4u) ? 1.f : 0.f, (nib & 8u) ? 1.f : 0.f);
       }
     }
 #pragma unroll
@@ -517,26 +528,19 @@ __device__ __forceinline__ void ct_rounds(const CtLane &c, int lane, int j0, int
       if (jb + i < j1) {
         const int j = jb + i;
         if (MODE == CT_F) {
-          const int lo = ka - 32 * j, hi = kz - 32 * j;  // lanes lo..hi of this round hold float4s ka..kz
-          if (hi >= 0 && lo <= 31) {
-            if ((lo <= 0 || lane >= lo) && (hi >= 31 || lane <= hi)) {
-              const float4 m = lds128(c.F + (uint32_t)(16 * (32 * j - ka)));
-              v[i].x *= m.x;
-              v[i].y *= m.y;
-              v[i].z *= m.z;
-              v[i].w *= m.w;
-            }
+          if ((uint32_t)(32 * j + lane - ka) <= (uint32_t)(kz - ka)) {  // this lane's float4 is one of ka..kz
+            const float4 m = lds128(Fb + (uint32_t)(512 * j));
+            v[i].x *= m.x;
+            v[i].y *= m.y;
+            v[i].z *= m.z;
+            v[i].w *= m.w;
           }
         } else if (MODE == CT_SCALAR) {
-          const int th = qt - 128 * j;  // floats th.. of this round take the multiplier
-          if (th <= 0) {
-            v[i].x *= tf, v[i].y *= tf, v[i].z *= tf, v[i].w *= tf;
-          } else if (th < 128) {
-            if (4 * lane + 0 >= th) v[i].x *= tf;
-            if (4 * lane + 1 >= th) v[i].y *= tf;
-            if (4 * lane + 2 >= th) v[i].z *= tf;
-            if (4 * lane + 3 >= th) v[i].w *= tf;
-          }
+          const uint32_t d = (uint32_t)(128 * j + 4 * lane - qt);  // float d + i of the range, if below n
+          if (d + 0u < (uint32_t)n) v[i].x *= tf;
+          if (d + 1u < (uint32_t)n) v[i].y *= tf;
+          if (d + 2u < (uint32_t)n) v[i].z *= tf;
+          if (d + 3u < (uint32_t)n) v[i].w *= tf;
         }
       }
     }
@@ -544,10 +548,10 @@ __device__ __forceinline__ void ct_rounds(const CtLane &c, int lane, int j0, int
     for (int i = 0; i < 4; i++) {
       if (jb + i < j1) {
         const int j = jb + i;
-        if (last_active < 32 && j == j1 - 1) {
-          if (lane < last_active) __stcs(c.op + 32 * (rlo + j), v[i]);
-        } else {
-          __stcs(c.op + 32 * (rlo + j), v[i]);
+        if (nr == CT_ALL_ROUNDS) {
+          __stcs(op + 32 * j, v[i]);
+        } else if (j < nr) {
+          if (j < nr - 1 || lane < last_lanes) __stcs(op + 32 * j, v[i]);
         }
       }
     }

@@ -627,21 +627,25 @@ __device__ GRL_GYM_EMIT_FN void gym_emit_linear(const GrlKParams &prm, int max_t
 
 // ---- the observation half of gym_emit_linear with a compile-time schedule (a warp's four whole games, P == PT; CtRun /
 // ct_rounds in grl_device.cuh).  Planes 1-2 of a view take their multipliers (0.5 on own tiles, log-army) from F; plane 7
-// (turn fraction, the same on every tile) multiplies by a register, with the float4 that straddles planes 6 and 7 split
-// by compile-time lane tests; plane 8 is zeros, so the carried floats of a game's incomplete round are zero bits.
-// `sw` is the warp's scratch as gym_emit_linear lays it out; the mask half (gym_emit_linear with obs == nullptr) reuses
-// F and the stream as its staging area.
-template <int PT, int N, int GI>
+// (turn fraction, the same on every tile) multiplies by a register, with per-float range tests in the rounds it can
+// touch; plane 8 is zeros, so the carried floats of a game's incomplete round are zero bits.  `sw` is the warp's scratch
+// as gym_emit_linear lays it out; the mask half (gym_emit_linear with obs == nullptr) reuses F and the stream as its
+// staging area.
+template <int PT, int N>
 __device__ GRL_GYM_EMIT_FN void gym_run_game_obs(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
                                                  const uint32_t *s, const uint32_t *stt, const CtLane &c, uint32_t *sw,
-                                                 int lane, const Geo &g) {
-  constexpr int NWC = (N + 31) / 32, CH = GRL_GYM_CHANNELS, TOTAL = PT * CH * N, NW = NWC;
-  using R = CtRun<TOTAL, 4>;
+                                                 int lane, const Geo &g, int gi) {
+  constexpr int NWC = (N + 31) / 32, CH = GRL_GYM_CHANNELS, TOTAL = PT * CH * N, NW = NWC, GPW = 4;
+  using R = CtRun<TOTAL, GPW>;
   constexpr int DW = ((PT * N + 31) / 32 + 1 + 3) & ~3;
   constexpr int FW = (2 * N + 8 + 3) & ~3;
   constexpr int SW = (((PT * GRL_GYM_CHANNELS * N + 127 + 31) / 32 + 1) + 3) & ~3;
   static_assert(SW >= R::stream_words(), "the stream holds a carried round in front of the block");
-  constexpr int PRE = R::pre(GI), RLO = R::r_lo(GI), NR = R::rounds(GI);
+  static_assert(R::win_hi((PT - 1) * CH * N + 7 * N, N) < R::NR_MIN, "plane 7 ends before the rounds only some games have");
+  static_assert(N >= 127, "the carried round lies inside the previous game's last plane (zeros)");
+  const int q0 = TOTAL * gi, rlo = q0 >> 7, pre = q0 & 127;
+  const int nr = (gi == GPW - 1 ? (GPW * TOTAL + 127) >> 7 : (q0 + TOTAL) >> 7) - rlo;  // rounds of this pass
+  float4 *op = c.op + 32 * rlo;
   const GrlLayout &L = prm.L;
   const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
   float *F = reinterpret_cast<float *>(sw + 4 * DW);
@@ -655,7 +659,6 @@ __device__ GRL_GYM_EMIT_FN void gym_run_game_obs(const GrlKParams &prm, int max_
   for (int p = 0; p < PT; p++)
     if (w) any_own |= s[L.off_own + p * NW + lane];
   // the carried floats in front of the block are the previous game's plane 8: zero bits, like the rest of a fresh stream
-  static_assert(PRE <= N, "the carried round lies inside the previous game's last plane");
   for (int k = lane; k < SW / 4; k += 32) strm4[k] = make_uint4(0u, 0u, 0u, 0u);
   float lg[NWC];  // log(army + 1) / 10 of tiles lane, lane + 32, ...
 #pragma unroll
@@ -671,17 +674,19 @@ __device__ GRL_GYM_EMIT_FN void gym_run_game_obs(const GrlKParams &prm, int max_
       const uint32_t v = w ? (prm.fog ? s[L.off_vis + p * NW + lane] : valid) : 0u;
       const uint32_t ch[CH - 1] = {v, v & any_own, v, valid & ~(M | C | G), M, C, G, valid};  // plane 8 stays zero
 #pragma unroll
-      for (int k = 0; k < CH - 1; k++) stream_or_mask<NWC, false>(strm, ch[k], PRE + (p * CH + k) * N, lane);
+      for (int k = 0; k < CH - 1; k++) stream_or_mask<NWC, false>(strm, ch[k], pre + (p * CH + k) * N, lane);
     }
   }
   __syncwarp();
+  constexpr int kAll = CT_ALL_ROUNDS;
   int jdone = 0;
 #pragma unroll
   for (int p = 0; p < PT; p++) {
-    const int qv = PRE + p * CH * N;  // this view's first stream float
-    // ---- planes 1 (ownership: 0.5 on own tiles in sight, 1 on enemy tiles) and 2 (log army in sight) ------------------
-    const int qa = qv + N, qz = qa + 2 * N - 1, sa = qa & 3, ka = qa >> 2, kz = qz >> 2, ja = ka >> 5, jz = kz >> 5;
-    ct_rounds<CT_PLAIN>(c, lane, jdone, ja, RLO, 0, 0, 0, 0.f, 32);
+    // ---- planes 1 (ownership: 0.5 on own tiles in sight, 1 on enemy tiles) and 2 (log army in sight): stream floats
+    //      [qa, qa + 2N), inside rounds ja_lo..ja_hi whatever `pre` is --------------------------------------------------
+    const int ja_lo = R::win_lo(p * CH * N + N), ja_hi = R::win_hi(p * CH * N + N, 2 * N);
+    const int qa = pre + p * CH * N + N, qz = qa + 2 * N - 1, sa = qa & 3, ka = qa >> 2, kz = qz >> 2;
+    ct_rounds<CT_PLAIN>(c, op, lane, jdone, ja_lo, 0, 0, 0u, 0, 0, 0.f, kAll, 32);
     __syncwarp();  // F is free
     {
       const uint32_t mine = w ? ((prm.fog ? s[L.off_vis + p * NW + lane] : valid) & s[L.off_own + p * NW + lane]) : 0u;
@@ -698,14 +703,15 @@ __device__ GRL_GYM_EMIT_FN void gym_run_game_obs(const GrlKParams &prm, int max_
       if (lane < 4) F[sa + 2 * N + lane] = 1.f;
     }
     __syncwarp();
-    ct_rounds<CT_F>(c, lane, ja, jz + 1, RLO, ka, kz, 0, 0.f, 32);
-    // ---- plane 7: min(turn / max_turns, 1) on every tile; the rounds that hold it end inside plane 8 (zeros) -----------
-    const int qt = qv + 7 * N, jt0 = qt >> 7, jt1 = (qt + N - 1) >> 7;
-    ct_rounds<CT_PLAIN>(c, lane, jz + 1, jt0, RLO, 0, 0, 0, 0.f, 32);
-    ct_rounds<CT_SCALAR>(c, lane, jt0, jt1 + 1, RLO, 0, 0, qt, tf, 32);
-    jdone = jt1 + 1;
+    ct_rounds<CT_F>(c, op, lane, ja_lo, ja_hi + 1, ka, kz, c.F - 16u * (uint32_t)ka, 0, 0, 0.f, kAll, 32);
+    // ---- plane 7: min(turn / max_turns, 1) on every tile: stream floats [qt, qt + N) ----------------------------------
+    const int jt_lo = R::win_lo(p * CH * N + 7 * N), jt_hi = R::win_hi(p * CH * N + 7 * N, N);
+    ct_rounds<CT_PLAIN>(c, op, lane, ja_hi + 1, jt_lo, 0, 0, 0u, 0, 0, 0.f, kAll, 32);
+    ct_rounds<CT_SCALAR>(c, op, lane, jt_lo, jt_hi + 1, 0, 0, 0u, pre + p * CH * N + 7 * N, N, tf, kAll, 32);
+    jdone = jt_hi + 1;
   }
-  ct_rounds<CT_PLAIN>(c, lane, jdone, NR, RLO, 0, 0, 0, 0.f, GI == 3 ? R::last_active() : 32);
+  ct_rounds<CT_PLAIN>(c, op, lane, jdone, R::NR_MIN, 0, 0, 0u, 0, 0, 0.f, kAll, 32);
+  ct_rounds<CT_PLAIN>(c, op, lane, R::NR_MIN, R::NR_MAX, 0, 0, 0u, 0, 0, 0.f, nr, gi == GPW - 1 ? R::last_active() : 32);
   __syncwarp();
 }
 

@@ -220,17 +220,20 @@ __device__ __forceinline__ void obs_linear(const GrlKParams &prm, const SlabView
 }
 
 // ---- the same writer with a compile-time schedule (a warp's four whole games, P == PT; CtRun / ct_rounds in
-// grl_device.cuh).  Game GI of the run: its stream starts with the `carry` words of the previous game's incomplete round,
-// every plane's bit offset, every round and the army rounds' float4 ranges are constants.  `carry` returns this game's
-// own incomplete round for the next game.
-template <int PT, int N, int GI>
+// grl_device.cuh).  Game gi of the run: its stream starts with the `carry` words of the previous game's incomplete round;
+// round indices are constants, the bit offsets of the planes and the float4 range of the army planes follow from the
+// game's `pre` in registers.  `carry` returns this game's own incomplete round for the next game.
+template <int PT, int N>
 __device__ __forceinline__ void obs_run_game(const GrlKParams &prm, const SlabView &S, const CtLane &c, uint32_t *scratch,
-                                             int NW, int lane, uint4 &carry) {
-  constexpr int NWC = (N + 31) / 32, CH = GRL_OBS_CHANNELS, TOTAL = PT * CH * N;
-  using R = CtRun<TOTAL, 4>;
+                                             int NW, int lane, int gi, uint4 &carry) {
+  constexpr int NWC = (N + 31) / 32, CH = GRL_OBS_CHANNELS, TOTAL = PT * CH * N, GPW = 4;
+  using R = CtRun<TOTAL, GPW>;
   constexpr int SW = grl_obs_stream_words(N, PT);
   static_assert(SW >= R::stream_words(), "the stream holds a carried round in front of the block");
-  constexpr int PRE = R::pre(GI), RLO = R::r_lo(GI), NR = R::rounds(GI);
+  static_assert(R::win_hi((PT - 1) * CH * N, 2 * N) < R::NR_MIN, "the army planes end before the rounds only some games have");
+  const int q0 = TOTAL * gi, rlo = q0 >> 7, pre = q0 & 127;
+  const int nr = (gi == GPW - 1 ? (GPW * TOTAL + 127) >> 7 : (q0 + TOTAL) >> 7) - rlo;  // rounds of this pass
+  float4 *op = c.op + 32 * rlo;
   float *F = reinterpret_cast<float *>(scratch);  // [2N + 8]
   uint32_t *strm = scratch + grl_obs_region_words(N);
   uint4 *strm4 = reinterpret_cast<uint4 *>(strm);
@@ -259,16 +262,18 @@ __device__ __forceinline__ void obs_run_game(const GrlKParams &prm, const SlabVi
       const uint32_t mine = nm & own, enemy = nm & any_own & ~own;   // serializer.go:75-90
       const uint32_t ch[CH] = {mine, enemy, mine, enemy, nm & ~any_own, nm & CG, v & M, v, ~v & valid};
 #pragma unroll
-      for (int k = 0; k < CH; k++) stream_or_mask<NWC, false>(strm, ch[k], PRE + (p * CH + k) * N, lane);
+      for (int k = 0; k < CH; k++) stream_or_mask<NWC, false>(strm, ch[k], pre + (p * CH + k) * N, lane);
     }
   }
   __syncwarp();
   int jdone = 0;
 #pragma unroll
   for (int p = 0; p < PT; p++) {
-    // this view's two army planes: stream floats [qa, qa + 2N)
-    const int qa = PRE + p * CH * N, qz = qa + 2 * N - 1, s = qa & 3, ka = qa >> 2, kz = qz >> 2, ja = ka >> 5, jz = kz >> 5;
-    ct_rounds<CT_PLAIN>(c, lane, jdone, ja, RLO, 0, 0, 0, 0.f, 32);
+    // this view's two army planes: stream floats [qa, qa + 2N), inside rounds j_lo..j_hi whatever `pre` is
+    constexpr int kAll = CT_ALL_ROUNDS;
+    const int j_lo = R::win_lo(p * CH * N), j_hi = R::win_hi(p * CH * N, 2 * N);
+    const int qa = pre + p * CH * N, qz = qa + 2 * N - 1, s = qa & 3, ka = qa >> 2, kz = qz >> 2;
+    ct_rounds<CT_PLAIN>(c, op, lane, jdone, j_lo, 0, 0, 0u, 0, 0, 0.f, kAll, 32);
     __syncwarp();  // the previous view's army rounds are done with F
 #pragma unroll
     for (int j = 0; j < NWC; j++) {
@@ -281,10 +286,11 @@ __device__ __forceinline__ void obs_run_game(const GrlKParams &prm, const SlabVi
     if (lane < s) F[lane] = 1.f;
     if (lane < 4) F[s + 2 * N + lane] = 1.f;
     __syncwarp();
-    ct_rounds<CT_F>(c, lane, ja, jz + 1, RLO, ka, kz, 0, 0.f, 32);
-    jdone = jz + 1;
+    ct_rounds<CT_F>(c, op, lane, j_lo, j_hi + 1, ka, kz, c.F - 16u * (uint32_t)ka, 0, 0, 0.f, kAll, 32);
+    jdone = j_hi + 1;
   }
-  ct_rounds<CT_PLAIN>(c, lane, jdone, NR, RLO, 0, 0, 0, 0.f, GI == 3 ? R::last_active() : 32);
-  if (GI < 3) carry = strm4[NR];
+  ct_rounds<CT_PLAIN>(c, op, lane, jdone, R::NR_MIN, 0, 0, 0u, 0, 0, 0.f, CT_ALL_ROUNDS, 32);
+  ct_rounds<CT_PLAIN>(c, op, lane, R::NR_MIN, R::NR_MAX, 0, 0, 0u, 0, 0, 0.f, nr, gi == GPW - 1 ? R::last_active() : 32);
+  if (gi < GPW - 1) carry = strm4[nr];
   __syncwarp();
 }

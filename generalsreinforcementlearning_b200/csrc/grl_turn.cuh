@@ -621,12 +621,10 @@ __device__ __forceinline__ void grl_turn_body(const GrlKParams &prm, const GrlGy
         CtLane c;
         c.init(s_obs + 4 * DW + FW, reinterpret_cast<const float *>(s_obs + 4 * DW),
                gk.obs + (size_t)warp_game0 * (PT * GRL_GYM_CHANNELS * NT), lane);
-        {
-          const uint32_t *s0 = wbase, *s1 = wbase + per_game, *s2 = wbase + 2 * per_game, *s3 = wbase + 3 * per_game;
-          gym_run_game_obs<PT, NT, 0>(prm, gk.max_turns, gk.logtab, s0, s0 + L.slab_words, c, s_obs, lane, g32);
-          gym_run_game_obs<PT, NT, 1>(prm, gk.max_turns, gk.logtab, s1, s1 + L.slab_words, c, s_obs, lane, g32);
-          gym_run_game_obs<PT, NT, 2>(prm, gk.max_turns, gk.logtab, s2, s2 + L.slab_words, c, s_obs, lane, g32);
-          gym_run_game_obs<PT, NT, 3>(prm, gk.max_turns, gk.logtab, s3, s3 + L.slab_words, c, s_obs, lane, g32);
+#pragma unroll 1
+        for (int gi = 0; gi < GPW; gi++) {  // one copy of the pass, four games
+          const uint32_t *sg = wbase + gi * per_game;
+          gym_run_game_obs<PT, NT>(prm, gk.max_turns, gk.logtab, sg, sg + L.slab_words, c, s_obs, lane, g32, gi);
         }
 #pragma unroll 1
         for (int gi = 0; gi < GPW; gi++) {  // the mask bytes and PlayerStates (F and the stream are their staging area now)
@@ -724,10 +722,10 @@ __device__ __forceinline__ void grl_turn_body(const GrlKParams &prm, const GrlGy
           c.init(s_obs + grl_obs_region_words(NT), reinterpret_cast<const float *>(s_obs),
                  prm.obs + (size_t)warp_game0 * (PT * GRL_OBS_CHANNELS * NT), lane);
           uint4 carry = make_uint4(0u, 0u, 0u, 0u);
-          obs_run_game<PT, NT, 0>(prm, make_view(wbase + 0 * per_game, wbase + 0 * per_game + L.slab_words, L), c, s_obs, NW, lane, carry);
-          obs_run_game<PT, NT, 1>(prm, make_view(wbase + 1 * per_game, wbase + 1 * per_game + L.slab_words, L), c, s_obs, NW, lane, carry);
-          obs_run_game<PT, NT, 2>(prm, make_view(wbase + 2 * per_game, wbase + 2 * per_game + L.slab_words, L), c, s_obs, NW, lane, carry);
-          obs_run_game<PT, NT, 3>(prm, make_view(wbase + 3 * per_game, wbase + 3 * per_game + L.slab_words, L), c, s_obs, NW, lane, carry);
+#pragma unroll 1
+          for (int gi = 0; gi < GPW; gi++)  // one copy of the pass, four games
+            obs_run_game<PT, NT>(prm, make_view(wbase + gi * per_game, wbase + gi * per_game + L.slab_words, L), c, s_obs, NW, lane,
+                                 gi, carry);
           return;
         }
       }
@@ -1069,8 +1067,7 @@ static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream, con
   const int per_cta = GRL_WARPS_PER_CTA * (32 / LG);
   int grid = (prm.game_end - prm.game0 + per_cta - 1) / per_cta;
   if (prm.epoch && prm.epoch_need) {  // may start while the previous turn launch of the stream drains (launch overlap)
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid < 1 ? 1 : grid);
     cfg.blockDim = dim3(GRL_WARPS_PER_CTA * 32);
     cfg.dynamicSmemBytes = smem;
