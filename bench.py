@@ -14,7 +14,10 @@ untimed rollout and replayed, so that the timed region is the turn engine itself
   python bench.py --impl reference ...                       CPU arm: the oracle restatement of
                                                              the Go engine on the host cores
 
-`value`  : device-resident run (recorded actions in HBM, outputs stay in HBM).
+`value`  : device-resident run (recorded actions in HBM, outputs stay in HBM).  The K timed launches are enqueued back
+           to back, so consecutive launches overlap on the device (a launch's warps wait for the warp that held their
+           games in the previous launch, not for the whole grid: csrc/grl_turn.cuh); `roofline.kernel_ms` is the timed
+           region / K, `roofline.kernel_ms_serialised_launches` the same K launches with the overlap switched off (N=1).
 `e2e`    : the same rollout replayed through the C ABI with HOST buffers every step: that
            step's actions copied host->device from pinned memory, reward/done/winner/error
            planes copied device->host (observations and masks stay in HBM for an on-GPU learner).
@@ -455,6 +458,25 @@ def run_cuda(args):
             extra = {"host_expand_env_steps_per_s": n_exp / (time.perf_counter() - t1), "host_expand_threads": os.cpu_count()}
         return sum_over_ranks(n) / dt_max, B * A * 8, d2h + small, steps_k, extra
 
+    # the same K launches with the launch overlap switched off (GRL_LAUNCH_OVERLAP is read when an env is created): what one
+    # launch costs when every launch waits for the whole grid before it, reported beside the headline, not instead of it
+    serial_ms = None
+    if world == 1:
+        prev = os.environ.get("GRL_LAUNCH_OVERLAP")
+        os.environ["GRL_LAUNCH_OVERLAP"] = "0"
+        try:
+            ro_s = Rollout(lib, torch, dev, stream, W, H, P, B, rank, args.start_turn, Wm + K)
+            ms_s0, _, _ = ro_s.timed(Wm, K, barrier)
+            serial_ms = ms_s0 / K
+            ro_s.e.close()
+            del ro_s
+            torch.cuda.empty_cache()
+        finally:
+            if prev is None:
+                del os.environ["GRL_LAUNCH_OVERLAP"]
+            else:
+                os.environ["GRL_LAUNCH_OVERLAP"] = prev
+
     e2e_val, h2d, d2h, _, _ = e2e_run("device")
     e2e_packed, h2d_p, d2h_p, _, exp_info = e2e_run("packed")
     e2e_full, h2d_f, d2h_f, k_full, _ = e2e_run("fp32")
@@ -531,7 +553,10 @@ def run_cuda(args):
                      "kernel": "grl_turn_kernel<2,20,20,32,true,true,false>", "kernel_ms": kernel_ms,
                      "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
                      "traffic_source": traffic.get("source") if traffic else "no ncu capture of this build under profiles/",
-                     "frac_of_nominal_8TBs": achieved / 8000.0},
+                     "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "launches": "the K timed launches are enqueued back to back and overlap on the device (csrc/grl_turn.cuh, "
+                                 "launch overlap): kernel_ms = timed region / K",
+                     "kernel_ms_serialised_launches": serial_ms},
         "clocks": clocks,
         "env_steps_per_launch": env_steps / K,
         "shapes": shapes,
