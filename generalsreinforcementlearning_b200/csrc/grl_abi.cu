@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/grlcuda.h"
@@ -77,6 +79,29 @@ struct grl_env {
 };
 
 namespace {
+
+// Launch overlap bookkeeping.  A turn launch may be marked as overlapping its predecessor only when that predecessor is
+// the SAME env's turn launch and nothing this library knows of was enqueued on the stream since — by any env: two envs
+// stepped alternately on one stream must not overlap, because the later env's grid does not wait for the earlier env's
+// warps and could finish first, and what follows it in the stream would then run before the earlier launch is complete.
+std::mutex g_overlap_mu;
+std::unordered_map<cudaStream_t, std::pair<const grl_env *, uint32_t>> g_last_turn_launch;  // per stream: env, sequence number
+
+void note_other_work(grl_env *env) {  // anything but a whole-batch turn launch was enqueued on the env's stream
+  env->overlap_prev = 0;
+  std::lock_guard<std::mutex> lk(g_overlap_mu);
+  g_last_turn_launch[env->stream] = {nullptr, 0u};
+}
+void note_turn_launch(grl_env *env, uint32_t seq) {
+  env->overlap_prev = seq;
+  std::lock_guard<std::mutex> lk(g_overlap_mu);
+  g_last_turn_launch[env->stream] = {seq ? env : nullptr, seq};
+}
+bool last_on_stream_is(const grl_env *env, uint32_t seq) {
+  std::lock_guard<std::mutex> lk(g_overlap_mu);
+  auto it = g_last_turn_launch.find(env->stream);
+  return it != g_last_turn_launch.end() && it->second.first == env && it->second.second == seq && seq != 0;
+}
 
 bool is_device_ptr(const void *p) {
   if (!p) return false;
@@ -301,7 +326,7 @@ int upload_and_reset(grl_env *env, const int32_t *env_ids, int n, const std::vec
   }
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_reset(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, n, env->stream));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   CUDA_TRY(cudaStreamSynchronize(env->stream));
   (void)L;
   return GRL_OK;
@@ -465,7 +490,7 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
     // inside a chain: the stream still has work and the last thing this library enqueued was a turn launch.  The first
     // launch of a chain runs as always, the second publishes, from the third on they overlap their predecessor.
     bool chain = false;
-    if (cap == cudaStreamCaptureStatusNone && env->overlap && !zero_copied && env->overlap_prev != 0) {
+    if (cap == cudaStreamCaptureStatusNone && env->overlap && !zero_copied && last_on_stream_is(env, env->overlap_prev)) {
       const cudaError_t q = cudaStreamQuery(env->stream);
       if (q == cudaErrorNotReady) cudaGetLastError(), chain = true;
       else if (q != cudaSuccess) return fail(GRL_ERR_CUDA, "cudaStreamQuery: %s", cudaGetErrorString(q));
@@ -476,7 +501,7 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
     prm.epoch_need = (chain && env->overlap_published) ? env->overlap_prev : 0u;
     CUDA_TRY(grl_launch_turn(prm, do_step, do_out, env->stream));
     env->launches++;
-    env->overlap_prev = (cap == cudaStreamCaptureStatusNone) ? seq : 0u;
+    note_turn_launch(env, cap == cudaStreamCaptureStatusNone ? seq : 0u);
     env->overlap_published = chain;
     if (zero_copied) CUDA_TRY(cudaStreamSynchronize(env->stream));  // host buffers are valid / consumed on return
     return GRL_OK;
@@ -509,7 +534,7 @@ int run_turn(grl_env *env, const grl_action *actions, uint32_t flags, uint64_t p
     pk.game0 = (int)g0;
     pk.game_end = (int)g1;
     CUDA_TRY(grl_launch_turn(pk, do_step, do_out, sq));
-    env->launches++, env->overlap_prev = 0;
+    env->launches++, note_other_work(env);
     for (int i = 0; i < n_planes; i++) {
       const OutBuf &ob = planes[i].ob;
       if (ob.staged)
@@ -625,7 +650,7 @@ int grl_create(const grl_config *cfg, grl_env **out) {
   GrlKParams prm = base_params(env);
   if (grl_launch_mark_over(prm, env->stream) != cudaSuccess || cudaStreamSynchronize(env->stream) != cudaSuccess)
     return bail(fail(GRL_ERR_CUDA, "state init kernel: %s", cudaGetErrorString(cudaGetLastError())));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   *out = env;
   return GRL_OK;
 }
@@ -639,6 +664,11 @@ int grl_destroy(grl_env *env) {
   if (env->d_logtab) cudaFree(env->d_logtab);
   if (env->d_state) cudaFree(env->d_state);  // d_static and d_geom live in the same allocation
   if (env->d_epoch) cudaFree(env->d_epoch);
+  {
+    std::lock_guard<std::mutex> lk(g_overlap_mu);
+    for (auto it = g_last_turn_launch.begin(); it != g_last_turn_launch.end();)
+      it = (it->second.first == env || it->first == env->own_stream) ? g_last_turn_launch.erase(it) : std::next(it);
+  }
   for (int k = 0; k < grl_env::kPipe; k++) {
     if (env->pipe[k]) cudaStreamDestroy(env->pipe[k]);
     if (env->ev_done[k]) cudaEventDestroy(env->ev_done[k]);
@@ -661,7 +691,7 @@ int grl_set_stream(grl_env *env, void *cuda_stream) {
   CUDA_TRY(cudaSetDevice(env->cfg.device));
   CUDA_TRY(cudaStreamSynchronize(env->stream));  // work already issued stays ordered
   env->stream = static_cast<cudaStream_t>(cuda_stream);  // NULL is CUDA's default stream
-  env->overlap_prev = 0;
+  note_other_work(env);
   return GRL_OK;
 }
 
@@ -724,7 +754,7 @@ static int reset_seeded_device(grl_env *env, const int32_t *env_ids, int32_t n, 
                                d_failed, env->stream));
     GrlKParams prm = base_params(env);
     CUDA_TRY(grl_launch_reset(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, cn, env->stream));
-    env->launches += 2, env->overlap_prev = 0;
+    env->launches += 2, note_other_work(env);
     int failed = 0;
     CUDA_TRY(cudaMemcpyAsync(&failed, d_failed, 4, cudaMemcpyDeviceToHost, env->stream));
     CUDA_TRY(cudaStreamSynchronize(env->stream));
@@ -796,13 +826,13 @@ int grl_mask(grl_env *env, int variant, void *out) {
     case GRL_MASK_SERIALIZER_UDLR:
       if ((st = bind_out(env, SL_MISC, out, B * P * N * 4, ob))) return st;
       CUDA_TRY(grl_launch_mask_bytes(prm, variant == GRL_MASK_ENGINE_URDL ? 0 : 1, (uint8_t *)ob.dev, env->stream));
-      env->launches++, env->overlap_prev = 0;
+      env->launches++, note_other_work(env);
       break;
     case GRL_MASK_ENGINE_URDL_BITS:
       if ((st = bind_out(env, SL_MASK, out, B * P * words * 4, ob))) return st;
       prm.mask_bits = (uint32_t *)ob.dev;
       CUDA_TRY(grl_launch_turn(prm, false, true, env->stream));
-      env->launches++, env->overlap_prev = 0;
+      env->launches++, note_other_work(env);
       break;
     case GRL_MASK_ENGINE_HALF_BITS: {
       void *tmp = nullptr;
@@ -811,7 +841,7 @@ int grl_mask(grl_env *env, int variant, void *out) {
       prm.mask_bits = (uint32_t *)tmp;
       CUDA_TRY(grl_launch_turn(prm, false, true, env->stream));
       CUDA_TRY(grl_launch_mask_replicate((const uint32_t *)tmp, (uint32_t *)ob.dev, B * P, (int)words, 2, env->stream));
-      env->launches += 2, env->overlap_prev = 0;
+      env->launches += 2, note_other_work(env);
       break;
     }
     default:
@@ -833,7 +863,7 @@ int grl_visibility(grl_env *env, uint8_t *visible, uint8_t *fog) {
   if ((st = bind_out(env, SL_MISC2, fog, bytes, f))) return st;
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_visibility(prm, (uint8_t *)v.dev, (uint8_t *)f.dev, env->stream));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   bool need_sync = false;
   if ((st = flush_out(env, v, need_sync))) return st;
   if ((st = flush_out(env, f, need_sync))) return st;
@@ -866,7 +896,7 @@ int grl_gym_observe(grl_env *env, int32_t max_turns, const grl_gym_outputs *out)
   if ((st = bind_out(env, SL_MISC2, out->stats, B * P * 4 * 4, stats))) return st;
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_gym(prm, max_turns, env->d_logtab, (float *)obs.dev, (uint8_t *)mask.dev, (int32_t *)stats.dev, env->stream));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   bool need_sync = false;
   if ((st = flush_out(env, obs, need_sync))) return st;
   if ((st = flush_out(env, mask, need_sync))) return st;
@@ -892,7 +922,7 @@ int grl_gym_observe_envs(grl_env *env, int32_t max_turns, const int32_t *env_ids
   CUDA_TRY(cudaMemcpyAsync(d_ids, env_ids, (size_t)n * 4, cudaMemcpyHostToDevice, env->stream));
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_gym(prm, max_turns, env->d_logtab, out->obs, out->mask, out->stats, env->stream, (const int32_t *)d_ids, n));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   CUDA_TRY(cudaStreamSynchronize(env->stream));  // env_ids (pageable host memory) is consumed on return
   return GRL_OK;
 }
@@ -908,7 +938,7 @@ int grl_gym_encode(grl_env *env, const int64_t *action_idx, int32_t player, int3
     return fail(GRL_ERR_UNSUPPORTED, "grl_gym_encode takes device pointers (it is the device-side glue of the vector env)");
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_gym_encode(prm, (const long long *)action_idx, player, slot, mask, skip_invalid, actions, valid, env->stream));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   return GRL_OK;
 }
 
@@ -949,7 +979,7 @@ int grl_gym_autoreset(grl_env *env, int32_t max_turns, int64_t base_seed, const 
   CUDA_TRY(grl_launch_reset(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, B, sq, d_count));
   CUDA_TRY(grl_launch_gym(prm, max_turns, env->d_logtab, io->out.obs, io->out.mask, io->out.stats, sq, d_ids, B, d_count));
   if (io->n_reset) CUDA_TRY(cudaMemcpyAsync(io->n_reset, d_count, 4, cudaMemcpyDeviceToDevice, sq));
-  env->launches += io->final_obs ? 7 : 6, env->overlap_prev = 0;
+  env->launches += io->final_obs ? 7 : 6, note_other_work(env);
   return GRL_OK;
 }
 
@@ -960,7 +990,7 @@ int grl_gym_sample(grl_env *env, uint64_t seed, const uint8_t *mask, int32_t pla
   if (!is_device_ptr(mask) || !is_device_ptr(action)) return fail(GRL_ERR_UNSUPPORTED, "grl_gym_sample takes device pointers");
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_gym_sample(prm, seed, mask, player, (long long *)action, env->stream));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   return GRL_OK;
 }
 
@@ -1004,7 +1034,7 @@ int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const 
   pt.step_error = io->step_error;
   if (io->n_finished) CUDA_TRY(cudaMemsetAsync(io->n_finished, 0, 4, sq));
   CUDA_TRY(grl_launch_gym_step(pt, gk, sq));
-  env->launches += 1, env->overlap_prev = 0;
+  env->launches += 1, note_other_work(env);
   return GRL_OK;
 }
 
@@ -1018,7 +1048,7 @@ int grl_sample_actions(grl_env *env, uint64_t policy_seed, grl_action *actions) 
   GrlKParams prm = base_params(env);
   prm.policy_seed = policy_seed;
   CUDA_TRY(grl_launch_sample(prm, ob.dev, env->stream));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   bool need_sync = false;
   if ((st = flush_out(env, ob, need_sync))) return st;
   if (need_sync) CUDA_TRY(cudaStreamSynchronize(env->stream));
@@ -1119,7 +1149,7 @@ int grl_state_hash(grl_env *env, uint64_t *out) {
   if ((st = bind_out(env, SL_MISC, out, (size_t)env->cfg.num_envs * 8, ob))) return st;
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_state_hash(prm, (uint64_t *)ob.dev, env->stream));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   bool need_sync = false;
   if ((st = flush_out(env, ob, need_sync))) return st;
   if (need_sync) CUDA_TRY(cudaStreamSynchronize(env->stream));
@@ -1140,7 +1170,7 @@ int grl_buffer_hash(grl_env *env, const void *buf, size_t row_words, int32_t row
   OutBuf ob;
   if ((st = bind_out(env, SL_MISC, out, (size_t)rows * 8, ob))) return st;
   CUDA_TRY(grl_launch_buffer_hash((const uint32_t *)dbuf, row_words, rows, (uint64_t *)ob.dev, env->stream));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   bool need_sync = dbuf != buf;
   if ((st = flush_out(env, ob, need_sync))) return st;
   if (need_sync) CUDA_TRY(cudaStreamSynchronize(env->stream));
@@ -1156,7 +1186,7 @@ int grl_stats(grl_env *env, uint64_t out[4]) {
   CUDA_TRY(cudaMemsetAsync(d, 0, 32, env->stream));
   GrlKParams prm = base_params(env);
   CUDA_TRY(grl_launch_stats(prm, (unsigned long long *)d, env->stream));
-  env->launches++, env->overlap_prev = 0;
+  env->launches++, note_other_work(env);
   CUDA_TRY(cudaMemcpyAsync(out, d, 32, cudaMemcpyDeviceToHost, env->stream));
   CUDA_TRY(cudaStreamSynchronize(env->stream));
   return GRL_OK;

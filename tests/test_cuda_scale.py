@@ -224,3 +224,42 @@ def test_overlapped_launches_keep_parity(cuda_lib, oracle_lib, W, H, P, B, T, mo
         assert np.array_equal(e.buffer_hash(obs, words, rows), want_obs), f"overlap={overlap}"
         assert np.array_equal(e.stats(), oc.stats())
         e.close()
+
+
+def test_two_envs_interleaved_on_one_stream(cuda_lib, oracle_lib):
+    """Two envs stepped alternately on ONE stream without host synchronisation: a launch overlaps only a predecessor of its
+    own env with nothing else enqueued in between (csrc/grl_abi.cu, launch overlap bookkeeping), so the interleaved
+    launches serialise; the chains of each env alone, enqueued afterwards, overlap again.  Both must match the oracle."""
+    import torch
+
+    stream = torch.cuda.Stream()
+    W, H, P, B, T = 10, 10, 2, 32768, 30
+    envs, outs, refs = [], [], []
+    for k in range(2):
+        e = new_engine(cuda_lib, W, H, P, B, host_threads=0)
+        e.set_stream(stream.cuda_stream)
+        seeds = np.arange(B, dtype=np.int64) + 1000 * (k + 1)
+        e.reset_seeded(seeds)
+        reward = torch.empty((B, P), dtype=torch.float32, device="cuda:0")
+        done = torch.empty(B, dtype=torch.uint8, device="cuda:0")
+        envs.append(e)
+        outs.append((reward, done, e.outputs(reward=reward, done=done)))
+        o = new_engine(oracle_lib, W, H, P, B, host_threads=0)
+        o.reset_seeded(seeds)
+        refs.append(o)
+    with torch.cuda.stream(stream):
+        for t in range(T):                      # A, B, A, B, ...
+            for k in range(2):
+                envs[k].step_fused(None, outs[k][2], _abi.STEP_FLAG_RANDOM_POLICY, 5 + k)
+        for k in range(2):                      # then a chain of each env alone
+            for t in range(T):
+                envs[k].step_fused(None, outs[k][2], _abi.STEP_FLAG_RANDOM_POLICY, 5 + k)
+    stream.synchronize()
+    for k in range(2):
+        oo = refs[k].alloc_outputs_host()
+        for t in range(2 * T):
+            refs[k].step_fused(None, refs[k].outputs(reward=oo["reward"], done=oo["done"]), _abi.STEP_FLAG_RANDOM_POLICY, 5 + k)
+        assert np.array_equal(envs[k].state_hash(), refs[k].state_hash()), f"env {k}"
+        assert np.array_equal(outs[k][0].cpu().numpy().view(np.uint32), oo["reward"].view(np.uint32)), f"env {k}"
+        assert np.array_equal(outs[k][1].cpu().numpy(), oo["done"]), f"env {k}"
+        envs[k].close()
