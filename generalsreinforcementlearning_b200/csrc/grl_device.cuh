@@ -463,7 +463,7 @@ __device__ __forceinline__ void stream_or_mask(uint32_t *strm, uint32_t word, in
 // what depends on the game — the number `pre` of carried floats in front of its block (0..127), hence where in the stream
 // a scaled plane begins and ends — enters as a handful of registers, and the rounds a scaled plane CAN touch for any `pre`
 // carry a per-lane range test.  One copy of the pass serves the four games of a warp: four specialised copies (every
-// range a constant) executed 5 % fewer instructions and ran 3-4 % slower — the kernels wait on instruction fetch
+// range a constant) executed 13-16 % fewer instructions and ran 3-4 % slower — the kernels wait on instruction fetch
 // (`no_instruction` 1.9 -> 4.3 stall cycles per issue with the four copies).
 template <int TOTAL, int GPW>
 struct CtRun {
