@@ -92,7 +92,7 @@ def _compare(ta, tb, what):
 
 
 CASES = [  # W, H, P, B, steps, max_turns, self_play
-    (10, 10, 2, 203, 45, 30, False),    # 8 lanes per game, partial last warp, truncation by turns and by calls
+    (10, 10, 2, 203, 45, 30, False),    # 4 lanes per game, partial last warp, truncation by turns and by calls
     (15, 15, 2, 130, 40, 500, True),    # 8 lanes per game, self-play opponent indices
     (20, 20, 2, 96, 60, 500, False),    # one game per warp
     (20, 20, 4, 40, 50, 35, False),     # four players: players 2,3 keep the synthetic policy's half-move bit
