@@ -734,8 +734,6 @@ static int reset_seeded_device(grl_env *env, const int32_t *env_ids, int32_t n, 
     if ((st = ensure(env, SL_MISC2, stat_bytes + (size_t)cn * 4 + 16, &d_statics))) return st;
     if ((st = ensure(env, SL_ACTIONS, (size_t)cn * 8 + 16, &d_seeds))) return st;
     int *d_failed = reinterpret_cast<int *>(reinterpret_cast<char *>(d_seeds) + (size_t)cn * 8);
-    CUDA_TRY(cudaMemsetAsync(d_slabs, 0, slab_bytes, env->stream));
-    CUDA_TRY(cudaMemsetAsync(d_statics, 0, stat_bytes, env->stream));
     CUDA_TRY(cudaMemsetAsync(d_failed, 0, 4, env->stream));
     CUDA_TRY(cudaMemcpyAsync(d_seeds, seeds + c0, (size_t)cn * 8, cudaMemcpyHostToDevice, env->stream));
     int32_t *d_ids = nullptr;
@@ -970,16 +968,19 @@ int grl_gym_autoreset(grl_env *env, int32_t max_turns, int64_t base_seed, const 
   CUDA_TRY(cudaMemsetAsync(d_count, 0, 8, sq));
   CUDA_TRY(grl_launch_gym_compact(prm, io->terminated, io->truncated, (long long)base_seed, (long long *)io->episode, io->turns, io->calls,
                                   d_ids, d_seeds, d_count, sq));
-  if (io->final_obs) CUDA_TRY(grl_launch_gym_final_obs(prm, io->out.obs, io->final_obs, d_ids, d_count, sq));
-  CUDA_TRY(grl_launch_zero_rows((uint32_t *)d_slabs, L.slab_words, B, d_count, sq));
-  CUDA_TRY(grl_launch_zero_rows((uint32_t *)d_statics, L.static_words, B, d_count, sq));
+  // three launches: the finished envs compacted into an id list; their last observations saved and their next maps
+  // generated (one warp per env); turn-0 set-up and gym read-outs of the re-seeded envs (one warp per env)
   grl::MapParams hp = grl::DefaultMapParams(c.width, c.height, c.num_players, c.city_ratio, c.city_start_army, c.min_general_spacing);
   GrlMapParams mp = {hp.players, hp.city_ratio, hp.city_start_army, hp.spacing, hp.veins, hp.min_vein, hp.max_vein};
-  CUDA_TRY(grl_launch_mapgen(L, c.width, c.height, mp, d_seeds, B, (uint32_t *)d_slabs, (uint32_t *)d_statics, d_count + 1, sq, d_count));
-  CUDA_TRY(grl_launch_reset(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, B, sq, d_count));
-  CUDA_TRY(grl_launch_gym(prm, max_turns, env->d_logtab, io->out.obs, io->out.mask, io->out.stats, sq, d_ids, B, d_count));
+  CUDA_TRY(grl_launch_mapgen(L, c.width, c.height, mp, d_seeds, B, (uint32_t *)d_slabs, (uint32_t *)d_statics, d_count + 1, sq, d_count,
+                             d_ids, io->out.obs, io->final_obs, GRL_GYM_CHANNELS * c.width * c.height));
+  if (io->out.obs || io->out.mask || io->out.stats)
+    CUDA_TRY(grl_launch_gym_reseed(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, B, d_count, max_turns, env->d_logtab,
+                                   io->out.obs, io->out.mask, io->out.stats, sq));
+  else
+    CUDA_TRY(grl_launch_reset(prm, (const uint32_t *)d_slabs, (const uint32_t *)d_statics, d_ids, B, sq, d_count));
   if (io->n_reset) CUDA_TRY(cudaMemcpyAsync(io->n_reset, d_count, 4, cudaMemcpyDeviceToDevice, sq));
-  env->launches += io->final_obs ? 7 : 6, note_other_work(env);
+  env->launches += 3, note_other_work(env);
   return GRL_OK;
 }
 

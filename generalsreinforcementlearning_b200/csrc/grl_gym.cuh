@@ -84,8 +84,10 @@ __device__ __forceinline__ float4 gym_value4(const GymPlanes &g, int p, int plan
 // One game's gym read-outs by a whole warp.  `s` / `stt` are the game's slab and terrain words (global
 // memory in grl_gym_warp_kernel, the shared-memory copy in the fused gym step); `sw` is the warp's
 // scratch of grl_gym_smem_words() words; `g` is the full-warp (LG = 32) geometry.  NT > 0 bakes the tile
-// count in (the element -> (plane, tile) divisions become multiplications).
-template <int NT>
+// count in (the element -> (plane, tile) divisions become multiplications).  CTA: the whole thread block works on ONE game
+// (every thread calls; warp 0 stages the masks, all threads share the sweeps; `sw` is then the block's scratch) — the
+// version for a handful of games whose read-outs are on somebody's critical path (grl_gym_autoreset).
+template <int NT, bool CTA = false>
 __device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, const float *__restrict__ logtab,
                                          float *__restrict__ obs, uint8_t *__restrict__ mask, int32_t *__restrict__ stats,
                                          const uint32_t *s, const uint32_t *stt, uint32_t *sw, int game, int lane,
@@ -96,8 +98,10 @@ __device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, c
   uint32_t *s_normal = s_enemy + P * NWP, *s_M = s_normal + NWP, *s_C = s_M + NWP, *s_G = s_C + NWP, *s_pad = s_G + NWP;
   uint32_t *s_dir = s_pad + NWP;  // [P][5][NWP]: up, right, down, left, any
   float *s_logv = reinterpret_cast<float *>(s_dir + 5 * P * NWP);
+  const int tid = CTA ? (int)threadIdx.x : lane, nthr = CTA ? (int)blockDim.x : 32;
   {
     const uint16_t *army = reinterpret_cast<const uint16_t *>(s + L.off_army);
+    if (!CTA || threadIdx.x < 32) {
     const bool w = lane < NW;
     const uint32_t M = w ? stt[lane] : 0u, C = w ? stt[NW + lane] : 0u, G = w ? stt[2 * NW + lane] : 0u;
     uint32_t any_own = 0;
@@ -127,8 +131,9 @@ __device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, c
         d[4 * NWP] = up | right | down | left;
       }
     }
-    for (int t = lane; t < N + 4; t += 32) s_logv[t] = t < N ? logtab[army[t]] : 0.f;  // logtab[0] == 0
-    __syncwarp();
+    }
+    for (int t = tid; t < N + 4; t += nthr) s_logv[t] = t < N ? logtab[army[t]] : 0.f;  // logtab[0] == 0
+    if (CTA) __syncthreads(); else __syncwarp();
 
     GymPlanes gp;
     gp.vis = s_vis;
@@ -149,10 +154,10 @@ __device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, c
         float *base = obs + off;
         const int head = (int)((4u - (uint32_t)(off & 3u)) & 3u);
         const int body4 = (block - head) / 4, tail0 = head + 4 * body4;
-        if (lane < head) __stcs(base + lane, gym_value(gp, p, lane / N, lane % N));
-        if (lane < block - tail0) __stcs(base + tail0 + lane, gym_value(gp, p, (tail0 + lane) / N, (tail0 + lane) % N));
+        if (tid < head) __stcs(base + tid, gym_value(gp, p, tid / N, tid % N));
+        if (tid < block - tail0) __stcs(base + tail0 + tid, gym_value(gp, p, (tail0 + tid) / N, (tail0 + tid) % N));
         float4 *body = reinterpret_cast<float4 *>(base + head);
-        for (int i = lane; i < body4; i += 32) {
+        for (int i = tid; i < body4; i += nthr) {
           const int e = head + 4 * i, plane = e / N, t = e - plane * N;
           float4 val;
           if (t + 3 < N) {
@@ -179,25 +184,25 @@ __device__ __forceinline__ void gym_emit(const GrlKParams &prm, int max_turns, c
         };
         const int head = (int)((4u - (uint32_t)(off & 3u)) & 3u);
         const int body4 = (bytes - head) / 4, tail0 = head + 4 * body4;
-        if (lane < head) base[lane] = (uint8_t)flag(lane);
-        if (lane < bytes - tail0) base[tail0 + lane] = (uint8_t)flag(tail0 + lane);
+        if (tid < head) base[tid] = (uint8_t)flag(tid);
+        if (tid < bytes - tail0) base[tail0 + tid] = (uint8_t)flag(tail0 + tid);
         uint32_t *body = reinterpret_cast<uint32_t *>(base + head);
-        for (int i = lane; i < body4; i += 32) {
+        for (int i = tid; i < body4; i += nthr) {
           const int j = head + 4 * i;
           body[i] = flag(j) | (flag(j + 1) << 8) | (flag(j + 2) << 16) | (flag(j + 3) << 24);
         }
       }
     }
-    if (stats && lane < P) {
+    if (stats && tid < P) {
       int tiles = 0;
-      for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + lane * NW + k]);
-      int32_t *so = stats + ((size_t)game * P + lane) * 4;
-      so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_ARMY_COUNT];
+      for (int k = 0; k < NW; k++) tiles += __popc(s[L.off_list + tid * NW + k]);
+      int32_t *so = stats + ((size_t)game * P + tid) * 4;
+      so[0] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * tid + GRL_PL_ARMY_COUNT];
       so[1] = tiles;
-      so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> lane) & 1u);
-      so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * lane + GRL_PL_GENERAL_IDX];
+      so[2] = (int32_t)((s[GRL_HDR_FLAGS] >> tid) & 1u);
+      so[3] = (int32_t)s[GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * tid + GRL_PL_GENERAL_IDX];
     }
-    __syncwarp();
+    if (CTA) __syncthreads(); else __syncwarp();
   }
 }
 

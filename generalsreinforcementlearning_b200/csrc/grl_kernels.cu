@@ -13,6 +13,56 @@
 // the turn-0 set-up of engine_initializer.go:113-143,218-225 (players alive, full stats,
 // full fog, game-over check), preserving the env's lifetime counters.
 // ---------------------------------------------------------------------------------------
+// One game's turn-0 set-up by a whole warp: staging slab `ss` / static slab `sst` -> the env's slab `ds` / static slab `dst`.
+template <int PT>
+__device__ __forceinline__ void reset_one(const GrlKParams &prm, const uint32_t *__restrict__ ss, const uint32_t *__restrict__ sst,
+                                          uint32_t *ds, uint32_t *dst, int lane, const Geo &g) {
+  const GrlLayout &L = prm.L;
+  const int P = prm.P, NW = prm.NW, N = prm.N;
+  for (int k = lane; k < L.static_words; k += 32) dst[k] = sst[k];
+  for (int k = L.off_army + lane; k < L.slab_words; k += 32) ds[k] = ss[k];
+  const bool act = lane < NW;
+  const uint32_t G = act ? sst[2 * NW + lane] : 0u;
+  const uint16_t *army = reinterpret_cast<const uint16_t *>(ss + L.off_army);
+  uint32_t alive = 0;
+#pragma unroll
+  for (int p = 0; p < PT; p++) {
+    if (p < P) {
+      uint32_t own = act ? ss[L.off_own + p * NW + lane] : 0u;
+      int total = sum_army_over<32>(own, army, NW, N, g);
+      uint32_t gen = own & G;
+      int gi = gen ? (32 * lane + 31 - __clz(gen)) : -1;
+      gi = __reduce_max_sync(FULL, gi);
+      if (gi >= 0) alive |= 1u << p;
+      uint32_t v = (gi >= 0 && prm.fog) ? dilate3<32>(own, g) : 0u;  // players start Alive; stats then sets Alive = has general
+      if (act) {
+        ds[L.off_own + p * NW + lane] = own;
+        ds[L.off_list + p * NW + lane] = own;
+        ds[L.off_vis + p * NW + lane] = v;
+      }
+      if (lane == 0) {
+        uint32_t *h = ds + GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p;
+        h[GRL_PL_ARMY_COUNT] = (uint32_t)total;
+        h[GRL_PL_GENERAL_IDX] = (uint32_t)gi;
+        h[GRL_PL_TRUE_ARMY] = (uint32_t)total;
+        h[GRL_PL_REWARD] = 0u;
+        h[GRL_PL_ACTION_INDEX] = 0xffffffffu;
+      }
+    }
+  }
+  if (act) {
+    ds[L.off_changed + lane] = 0u;
+    ds[L.off_vchg + lane] = 0u;
+  }
+  if (lane == 0) {
+    int n_alive = __popc(alive);
+    bool over = P > 1 ? (n_alive <= 1) : (n_alive == 0);
+    ds[GRL_HDR_TURN] = 0u;
+    ds[GRL_HDR_FLAGS] = alive | (over ? GRL_FLAG_OVER : 0u);
+    ds[GRL_HDR_OVERFLOW] = 0u;
+  }
+}
+
 template <int PT>
 __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
     grl_reset_kernel(const __grid_constant__ GrlKParams prm, const uint32_t *__restrict__ src_state,
@@ -21,57 +71,12 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (n_dev) n = min(n, *n_dev);  // device-side count (grl_gym_autoreset)
   const GrlLayout &L = prm.L;
-  const int P = prm.P, NW = prm.NW, N = prm.N;
   const Geo g = make_geo(prm, prm.W, lane, 32);
   for (int i = blockIdx.x * GRL_WARPS_PER_CTA + warp; i < n; i += gridDim.x * GRL_WARPS_PER_CTA) {
     const int game = env_ids ? env_ids[i] : i;
     if (game < 0 || game >= prm.B) continue;
-    const uint32_t *ss = src_state + (size_t)i * L.slab_words;
-    const uint32_t *sst = src_static + (size_t)i * L.static_words;
-    uint32_t *ds = prm.state + (size_t)game * L.slab_words;
-    uint32_t *dst = const_cast<uint32_t *>(prm.statics) + (size_t)game * L.static_words;
-    for (int k = lane; k < L.static_words; k += 32) dst[k] = sst[k];
-    for (int k = L.off_army + lane; k < L.slab_words; k += 32) ds[k] = ss[k];
-    const bool act = lane < NW;
-    const uint32_t G = act ? sst[2 * NW + lane] : 0u;
-    const uint16_t *army = reinterpret_cast<const uint16_t *>(ss + L.off_army);
-    uint32_t alive = 0;
-#pragma unroll
-    for (int p = 0; p < PT; p++) {
-      if (p < P) {
-        uint32_t own = act ? ss[L.off_own + p * NW + lane] : 0u;
-        int total = sum_army_over<32>(own, army, NW, N, g);
-        uint32_t gen = own & G;
-        int gi = gen ? (32 * lane + 31 - __clz(gen)) : -1;
-        gi = __reduce_max_sync(FULL, gi);
-        if (gi >= 0) alive |= 1u << p;
-        uint32_t v = (gi >= 0 && prm.fog) ? dilate3<32>(own, g) : 0u;  // players start Alive; stats then sets Alive = has general
-        if (act) {
-          ds[L.off_own + p * NW + lane] = own;
-          ds[L.off_list + p * NW + lane] = own;
-          ds[L.off_vis + p * NW + lane] = v;
-        }
-        if (lane == 0) {
-          uint32_t *h = ds + GRL_HDR_PLAYER0 + GRL_HDR_PER_PLAYER * p;
-          h[GRL_PL_ARMY_COUNT] = (uint32_t)total;
-          h[GRL_PL_GENERAL_IDX] = (uint32_t)gi;
-          h[GRL_PL_TRUE_ARMY] = (uint32_t)total;
-          h[GRL_PL_REWARD] = 0u;
-          h[GRL_PL_ACTION_INDEX] = 0xffffffffu;
-        }
-      }
-    }
-    if (act) {
-      ds[L.off_changed + lane] = 0u;
-      ds[L.off_vchg + lane] = 0u;
-    }
-    if (lane == 0) {
-      int n_alive = __popc(alive);
-      bool over = P > 1 ? (n_alive <= 1) : (n_alive == 0);
-      ds[GRL_HDR_TURN] = 0u;
-      ds[GRL_HDR_FLAGS] = alive | (over ? GRL_FLAG_OVER : 0u);
-      ds[GRL_HDR_OVERFLOW] = 0u;
-    }
+    reset_one<PT>(prm, src_state + (size_t)i * L.slab_words, src_static + (size_t)i * L.static_words,
+                  prm.state + (size_t)game * L.slab_words, const_cast<uint32_t *>(prm.statics) + (size_t)game * L.static_words, lane, g);
   }
 }
 
@@ -144,6 +149,34 @@ __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
   }
 }
 
+// grl_gym_autoreset, last step: the turn-0 set-up of every re-seeded env and its gym read-outs in ONE launch, one thread
+// BLOCK per env: warp 0 runs reset_one, then the block reads the slab it has just written back (block barrier) and shares
+// the read-out sweeps (gym_emit<0, true>).  A vector step re-seeds a hundred-odd envs and waits for their read-outs, so what
+// counts here is the latency of one env, not throughput: a single warp per env took 28 us, two launches 35 us.
+template <int PT>
+__global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32)
+    grl_gym_reseed_kernel(const __grid_constant__ GrlKParams prm, const uint32_t *__restrict__ src_state,
+                          const uint32_t *__restrict__ src_static, const int32_t *__restrict__ ids, int n,
+                          const int *__restrict__ n_dev, int max_turns, const float *__restrict__ logtab, float *__restrict__ obs,
+                          uint8_t *__restrict__ mask, int32_t *__restrict__ stats) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const GrlLayout &L = prm.L;
+  const Geo g = make_geo(prm, prm.W, lane, 32);
+  n = min(n, *n_dev);
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {  // uniform over the block
+    const int game = ids[i];
+    if (game < 0 || game >= prm.B) continue;
+    uint32_t *ds = prm.state + (size_t)game * L.slab_words;
+    uint32_t *dst = const_cast<uint32_t *>(prm.statics) + (size_t)game * L.static_words;
+    if (threadIdx.x < 32)
+      reset_one<PT>(prm, src_state + (size_t)i * L.slab_words, src_static + (size_t)i * L.static_words, ds, dst, lane, g);
+    __threadfence_block();
+    __syncthreads();
+    gym_emit<0, true>(prm, max_turns, logtab, obs, mask, stats, ds, dst, smem, game, lane, g);
+  }
+}
+
 // GeneralsEnv._action_index_to_game_action (generals_env.py:389-441), one thread per env
 __global__ void grl_gym_encode_kernel(const GrlKParams prm, const long long *__restrict__ action_idx, int player, int slot,
                                       const uint8_t *__restrict__ mask, int skip_invalid, uint2 *__restrict__ actions,
@@ -195,25 +228,6 @@ __global__ void grl_gym_compact_kernel(const GrlKParams prm, const uint8_t *__re
   }
 }
 
-// step 2: player 0's last observation of every finished env, before its row is overwritten (one warp per env)
-__global__ void __launch_bounds__(256) grl_gym_final_obs_kernel(const GrlKParams prm, const float *__restrict__ obs,
-                                                                float *__restrict__ final_obs, const int32_t *__restrict__ ids,
-                                                                const int *__restrict__ count) {
-  const int lane = threadIdx.x & 31, n = *count, block = GRL_GYM_CHANNELS * prm.N;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
-    const int b = ids[i];
-    const float *src = obs + (size_t)b * prm.P * block;
-    float *dst = final_obs + (size_t)b * block;
-    for (int k = lane; k < block; k += 32) dst[k] = src[k];
-  }
-}
-
-// step 3: the staging rows the map generator fills have to start zeroed
-__global__ void grl_zero_rows_kernel(uint32_t *__restrict__ p, int row_words, int capacity, const int *__restrict__ count) {
-  const size_t total = (size_t)min(capacity, *count) * row_words;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) p[k] = 0u;
-}
-
 // A uniformly random valid gym action per env: the k-th set byte of the env's N*5 mask bytes, one warp per env
 // (the draw is policy_draw(seed, global env, 0, player) mod the number of set bytes).  The row is read as aligned
 // 128-bit vectors (512 contiguous bytes per warp instruction, whatever the row's own alignment), each lane turning its
@@ -240,23 +254,36 @@ __global__ void __launch_bounds__(256) grl_gym_sample_kernel(const GrlKParams pr
     const bool last_row = b == prm.B - 1 && player == prm.P - 1;  // its last vector may reach past the plane,
     const bool first_row = b == 0 && player == 0 && mis != 0;      // the first row's first vector before it
     int mine = 0;
-    for (int r = 0; r < rounds; r++) {
-      const int v = 32 * r + lane;
-      uint32_t m16 = 0;
-      if (v < nvec) {
-        const int g0 = 16 * v - mis;  // row-relative index of this vector's first byte
-        if ((last_row && v == nvec - 1) || (first_row && v == 0)) {
-          for (int j = 0; j < 16; j++)
-            if (g0 + j >= 0 && g0 + j < M && row[g0 + j] != 0) m16 |= 1u << j;
-        } else {
-          const uint4 q = __ldg(base + v);
-          m16 = nonzero_bytes4(q.x) | (nonzero_bytes4(q.y) << 4) | (nonzero_bytes4(q.z) << 8) | (nonzero_bytes4(q.w) << 12);
-          if (g0 < 0) m16 &= 0xffffu << (-g0);                 // bytes before the row
-          if (g0 + 16 > M) m16 &= 0xffffu >> (g0 + 16 - M);    // bytes past its end
-        }
+    // the loads of four rounds are issued before the first is consumed: a row is then one or two trips to DRAM (15x15:
+    // three rounds, 20x20: four), not one per round — this kernel is bounded by that latency, not by the 74-131 MB it reads
+    for (int r0 = 0; r0 < rounds; r0 += 4) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int v = 32 * (r0 + u) + lane;
+        q[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (v < nvec && !((last_row && v == nvec - 1) || (first_row && v == 0))) q[u] = __ldg(base + v);
       }
-      sm[v] = (uint16_t)m16;
-      mine += __popc(m16);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int v = 32 * (r0 + u) + lane;
+        if (r0 + u >= rounds) break;
+        uint32_t m16 = 0;
+        if (v < nvec) {
+          const int g0 = 16 * v - mis;  // row-relative index of this vector's first byte
+          if ((last_row && v == nvec - 1) || (first_row && v == 0)) {
+            for (int j = 0; j < 16; j++)
+              if (g0 + j >= 0 && g0 + j < M && row[g0 + j] != 0) m16 |= 1u << j;
+          } else {
+            m16 = nonzero_bytes4(q[u].x) | (nonzero_bytes4(q[u].y) << 4) | (nonzero_bytes4(q[u].z) << 8) |
+                  (nonzero_bytes4(q[u].w) << 12);
+            if (g0 < 0) m16 &= 0xffffu << (-g0);                 // bytes before the row
+            if (g0 + 16 > M) m16 &= 0xffffu >> (g0 + 16 - M);    // bytes past its end
+          }
+        }
+        sm[v] = (uint16_t)m16;
+        mine += __popc(m16);
+      }
     }
     const int total = __reduce_add_sync(FULL, mine);
     __syncwarp();
@@ -264,17 +291,17 @@ __global__ void __launch_bounds__(256) grl_gym_sample_kernel(const GrlKParams pr
     if (total > 0) {
       const uint64_t rr = policy_draw(seed, (uint64_t)(prm.env_id_base + b), 0ull, (uint64_t)player);
       int k = (int)(rr % (uint64_t)total);
-      for (int r = 0; r < rounds; r++) {
+      for (int r = 0; r < rounds; r++) {  // the round the k-th set byte lies in, then one prefix sum inside it
         const uint32_t w = sm[32 * r + lane];
         const int c = __popc(w);
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(FULL, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const int stripe = __shfl_sync(FULL, incl, 31);
+        const int stripe = __reduce_add_sync(FULL, c);
         if (k < stripe) {
+          int incl = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+          }
           const uint32_t who = __ballot_sync(FULL, k >= incl - c && k < incl);
           const int src = __ffs(who) - 1;
           uint32_t ww = __shfl_sync(FULL, w, src);
@@ -497,22 +524,34 @@ cudaError_t grl_launch_gym_compact(const GrlKParams &prm, const uint8_t *termina
   return cudaGetLastError();
 }
 
-cudaError_t grl_launch_gym_final_obs(const GrlKParams &prm, const float *obs, float *final_obs, const int32_t *ids, const int *count,
-                                     cudaStream_t stream) {
-  grl_gym_final_obs_kernel<<<148 * 4, 256, 0, stream>>>(prm, obs, final_obs, ids, count);
-  return cudaGetLastError();
-}
-
-cudaError_t grl_launch_zero_rows(uint32_t *p, int row_words, int capacity, const int *count, cudaStream_t stream) {
-  grl_zero_rows_kernel<<<148 * 8, 256, 0, stream>>>(p, row_words, capacity, count);
+cudaError_t grl_launch_gym_reseed(const GrlKParams &prm, const uint32_t *src_state, const uint32_t *src_static, const int32_t *ids,
+                                  int n, const int *n_dev, int max_turns, const float *logtab, float *obs, uint8_t *mask,
+                                  int32_t *stats, cudaStream_t stream) {
+  const size_t smem = (size_t)grl_gym_smem_words(prm.P, prm.NW, prm.N, GRL_GYM_EMIT_GENERIC) * 4u;
+  const int grid = n < 148 * 8 ? (n < 1 ? 1 : n) : 148 * 8;  // one block per env, strided over the device-side count
+#define GRL_RESEED(PT)                                                                                                         \
+  {                                                                                                                            \
+    static size_t tuned = 0;                                                                                                   \
+    if (smem > 48 * 1024 && smem > tuned) {                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(grl_gym_reseed_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return e;                                                                                          \
+      tuned = smem;                                                                                                            \
+    }                                                                                                                          \
+    grl_gym_reseed_kernel<PT><<<grid, GRL_WARPS_PER_CTA * 32, smem, stream>>>(prm, src_state, src_static, ids, n, n_dev, max_turns, \
+                                                                              logtab, obs, mask, stats);                      \
+  }
+  switch (player_template(prm.P)) {
+    case 2: GRL_RESEED(2) break;
+    case 4: GRL_RESEED(4) break;
+    default: GRL_RESEED(8) break;
+  }
+#undef GRL_RESEED
   return cudaGetLastError();
 }
 
 cudaError_t grl_launch_gym_sample(const GrlKParams &prm, unsigned long long seed, const uint8_t *mask, int player, long long *action,
                                   cudaStream_t stream) {
-  int grid = grid_for(8, prm.B);
-  if (grid > 148 * 16) grid = 148 * 16;
-  grl_gym_sample_kernel<<<grid, 256, 0, stream>>>(prm, seed, mask, player, action);
+  grl_gym_sample_kernel<<<grid_for(8, prm.B), 256, 0, stream>>>(prm, seed, mask, player, action);
   return cudaGetLastError();
 }
 

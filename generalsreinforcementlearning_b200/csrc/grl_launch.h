@@ -19,9 +19,9 @@ cudaError_t grl_launch_reset(const GrlKParams &prm, const uint32_t *src_state, c
 cudaError_t grl_launch_gym_compact(const GrlKParams &prm, const uint8_t *terminated, const uint8_t *truncated, long long base_seed,
                                    long long *episode, int32_t *turns, int32_t *calls, int32_t *ids, long long *seeds, int *count,
                                    cudaStream_t stream);
-cudaError_t grl_launch_gym_final_obs(const GrlKParams &prm, const float *obs, float *final_obs, const int32_t *ids, const int *count,
-                                     cudaStream_t stream);
-cudaError_t grl_launch_zero_rows(uint32_t *p, int row_words, int capacity, const int *count, cudaStream_t stream);
+cudaError_t grl_launch_gym_reseed(const GrlKParams &prm, const uint32_t *src_state, const uint32_t *src_static, const int32_t *ids,
+                                  int n, const int *n_dev, int max_turns, const float *logtab, float *obs, uint8_t *mask,
+                                  int32_t *stats, cudaStream_t stream);
 cudaError_t grl_launch_sample(const GrlKParams &prm, void *out, cudaStream_t stream);
 cudaError_t grl_launch_mask_bytes(const GrlKParams &prm, int variant, uint8_t *out, cudaStream_t stream);
 cudaError_t grl_launch_visibility(const GrlKParams &prm, uint8_t *visible, uint8_t *fog, cudaStream_t stream);
@@ -45,4 +45,5 @@ struct GrlMapParams {
   int players, city_ratio, city_start_army, spacing, veins, min_vein, max_vein;
 };
 cudaError_t grl_launch_mapgen(const GrlLayout &L, int W, int H, const GrlMapParams &mp, const long long *seeds, int n,
-                              uint32_t *slabs, uint32_t *statics, int *failed, cudaStream_t stream, const int *n_dev = nullptr);
+                              uint32_t *slabs, uint32_t *statics, int *failed, cudaStream_t stream, const int *n_dev = nullptr,
+                              const int32_t *ids = nullptr, const float *obs = nullptr, float *final_obs = nullptr, int obs_block = 0);

@@ -24,12 +24,14 @@ constexpr int kLen = 607;
 constexpr int kTap = 273;
 constexpr int32_t kInt32Max = 2147483647;
 
-__constant__ int64_t c_cooked[kLen] = {
+// both tables are indexed per lane (word i, power 21+3i): from constant memory those reads would serialise 32 ways, so
+// they live in global memory and are fetched through the read-only path (coalesced, L1/L2 resident)
+__device__ const int64_t c_cooked[kLen] = {
 #include "go_rng_cooked.inc"
 };
 
 // 48271^k mod (2^31-1): x_k = 48271^k * x_0, so the 1,841 seeding steps become independent multiplications
-__constant__ int32_t c_lpow[1842] = {
+__device__ const int32_t c_lpow[1842] = {
 #include "go_rng_lehmer_pow.inc"
 };
 
@@ -47,11 +49,14 @@ struct GoRandDev {  // rng.go (*rngSource) + rand.go
     // rng.go seedrand runs 20 warm-up steps of x <- 48271 * x mod (2^31-1), then three per state word; the k-th
     // state is 48271^k * x_0, so word i takes the independent products for k = 21+3i .. 23+3i
     const uint64_t x0 = (uint64_t)s;
-    for (int i = lane; i < kLen; i += 32) {
+#pragma unroll  // 19 rounds, every table read independent of the others: one trip to L2, not nineteen
+    for (int j = 0; j < (kLen + 31) / 32; j++) {
+      const int i = lane + 32 * j;
+      if (i >= kLen) break;
       const int k = 21 + 3 * i;
-      const uint64_t u = ((uint64_t)mulmod31(c_lpow[k], x0) << 40) ^ ((uint64_t)mulmod31(c_lpow[k + 1], x0) << 20) ^
-                         (uint64_t)mulmod31(c_lpow[k + 2], x0);
-      vec[i] = u ^ (uint64_t)c_cooked[i];
+      const uint64_t u = ((uint64_t)mulmod31(__ldg(c_lpow + k), x0) << 40) ^ ((uint64_t)mulmod31(__ldg(c_lpow + k + 1), x0) << 20) ^
+                         (uint64_t)mulmod31(__ldg(c_lpow + k + 2), x0);
+      vec[i] = u ^ (uint64_t)__ldg(c_cooked + i);
     }
   }
   __device__ static uint32_t mulmod31(int32_t a, uint64_t x) {  // a * x mod (2^31 - 1), both in [1, 2^31 - 2]
@@ -74,6 +79,13 @@ struct GoRandDev {  // rng.go (*rngSource) + rand.go
     if ((n & (n - 1)) == 0) return int31() & (n - 1);
     const int32_t limit = (int32_t)((1u << 31) - 1 - (1u << 31) % (uint32_t)n);
     int32_t v = int31();
+    while (v > limit) v = int31();
+    return v % n;
+  }
+  __device__ static int32_t intn_limit(int n) { return (int32_t)((1u << 31) - 1 - (1u << 31) % (uint32_t)n); }
+  __device__ int intn(int n, int32_t limit) {  // Intn with the rejection limit of a non-power-of-two n precomputed
+    int32_t v = int31();
+    if ((n & (n - 1)) == 0) return v & (n - 1);
     while (v > limit) v = int31();
     return v % n;
   }
@@ -112,24 +124,55 @@ __device__ bool far_enough(int W, int idx, const int *seats, int n, int spacing)
 
 }  // namespace
 
-// staging buffers must be zero-filled; one warp writes map i into slab i / static slab i
+// One warp writes map i into staging slab i / static slab i: every word grl_reset_kernel reads (the ownership masks,
+// the army plane to the end of the slab, the whole static slab), so the staging rows need no zero fill.
+// With `final_obs` the CTA carries a second set of warps: warp kMapWarps + w saves player 0's observation block of env
+// ids[i] (grl_gym_autoreset: the episode's last view, before the re-seeded env's read-outs overwrite it) while warp w
+// generates that env's next map.
 constexpr int kMapWarps = 4;  // maps per CTA: 4 x (607 x 8 B state + 512 B masks + 2 KB armies) = 29.6 KB of shared memory
 
-__global__ void __launch_bounds__(kMapWarps * 32)
+__global__ void __launch_bounds__(2 * kMapWarps * 32)
     grl_mapgen_kernel(GrlLayout L, int W, int H, GrlMapParams mp, const long long *__restrict__ seeds, int n,
                       uint32_t *__restrict__ slabs, uint32_t *__restrict__ statics, int *__restrict__ failed,
-                      const int *__restrict__ n_dev) {
+                      const int *__restrict__ n_dev, const int32_t *__restrict__ ids, const float *__restrict__ obs,
+                      float *__restrict__ final_obs, int obs_block) {
   __shared__ uint64_t s_vec[kMapWarps][kLen];
   __shared__ uint32_t s_mask[kMapWarps][4][32];
   __shared__ __align__(16) uint16_t s_army[kMapWarps][1024];
   __shared__ int s_seat[kMapWarps][GRL_MAX_PLAYERS_DEV + 1];  // [players] = 1 when every general found a seat
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (threadIdx.x >> 5) % kMapWarps, lane = threadIdx.x & 31;
   const int i = blockIdx.x * kMapWarps + warp;
   if (n_dev) n = min(n, *n_dev);  // the launch covers the capacity; the number of maps lives on the device
   if (i >= n) return;             // uniform over the warp
   const int N = W * H, NW = L.NW;
   uint32_t *slab = slabs + (size_t)i * L.slab_words;
   uint32_t *stat = statics + (size_t)i * L.static_words;
+  if (threadIdx.x >= kMapWarps * 32) {  // a copy warp (launched only with final_obs): [P][obs_block] per env in `obs`, [obs_block] per env in `final_obs`; both 4-byte aligned only
+    const int b = ids[i];
+    const float *src = obs + (size_t)b * mp.players * obs_block;
+    float *dst = final_obs + (size_t)b * obs_block;
+    const int head = min(obs_block, (int)((4u - (uint32_t)(((size_t)b * obs_block) & 3u)) & 3u));  // dst to 16 bytes
+    if (lane < head) dst[lane] = src[lane];
+    const int n4 = (obs_block - head) >> 2;
+    float4 *d4 = reinterpret_cast<float4 *>(dst + head);
+    const float *s1 = src + head;
+    for (int k0 = 0; k0 < n4; k0 += 8 * 32) {  // eight independent rounds of loads in flight
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int k = k0 + 32 * u + lane;
+        if (k < n4) v[u] = make_float4(s1[4 * k], s1[4 * k + 1], s1[4 * k + 2], s1[4 * k + 3]);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int k = k0 + 32 * u + lane;
+        if (k < n4) d4[k] = v[u];
+      }
+    }
+    const int t0 = head + 4 * n4;
+    if (t0 + lane < obs_block) dst[t0 + lane] = src[t0 + lane];
+    return;
+  }
   for (int k = lane; k < 4 * 32; k += 32) (&s_mask[warp][0][0])[k] = 0u;
   for (int k = lane; k < 512; k += 32) reinterpret_cast<uint32_t *>(s_army[warp])[k] = 0u;
   GoRandDev rng;
@@ -145,13 +188,14 @@ __global__ void __launch_bounds__(kMapWarps * 32)
   b.army = s_army[warp];
   int *seats = s_seat[warp];
   seats[mp.players] = 0;
+  const int32_t limW = GoRandDev::intn_limit(W), limH = GoRandDev::intn_limit(H);  // two of three draws are Intn(W) / Intn(H)
 
   // generator.go:77-142 mountain veins
   for (int vein = 0; vein < mp.veins; ++vein) {
     int cx = -1, cy = -1;
     for (int attempt = 0; attempt < 100; ++attempt) {
-      const int sx = rng.intn(W);
-      const int sy = rng.intn(H);
+      const int sx = rng.intn(W, limW);
+      const int sy = rng.intn(H, limH);
       if (b.open(sy * W + sx)) {
         cx = sx;
         cy = sy;
@@ -195,8 +239,8 @@ __global__ void __launch_bounds__(kMapWarps * 32)
     const int want = N / mp.city_ratio;
     int placed = 0;
     for (int attempts = 0; placed < want && attempts < want * 20; ++attempts) {
-      const int x = rng.intn(W);
-      const int y = rng.intn(H);
+      const int x = rng.intn(W, limW);
+      const int y = rng.intn(H, limH);
       const int t = y * W + x;
       if (b.open(t)) {
         b.take(t);
@@ -211,8 +255,8 @@ __global__ void __launch_bounds__(kMapWarps * 32)
   for (int pid = 0; pid < mp.players && ok; ++pid) {
     int chosen = -1;
     for (int attempt = 0; attempt < N && chosen < 0; ++attempt) {
-      const int x = rng.intn(W);
-      const int y = rng.intn(H);
+      const int x = rng.intn(W, limW);
+      const int y = rng.intn(H, limH);
       const int t = y * W + x;
       if (b.open(t) && far_enough(W, t, seats, pid, mp.spacing)) chosen = t;
     }
@@ -233,23 +277,23 @@ __global__ void __launch_bounds__(kMapWarps * 32)
   __syncwarp();
 
   // ---- the finished map leaves shared memory with coalesced stores ---------------------------------------------
-  if (!s_seat[warp][mp.players]) return;
-  if (lane < NW) {
-    stat[lane] = s_mask[warp][1][lane];
-    stat[NW + lane] = s_mask[warp][2][lane];
-    stat[2 * NW + lane] = s_mask[warp][3][lane];
-  }
-  uint32_t *garmy = slab + L.off_army;
+  const bool placed = s_seat[warp][mp.players] != 0;  // a map without seats for every general leaves as an empty board (`failed` is set)
+  for (int k = lane; k < L.static_words; k += 32)
+    stat[k] = (placed && k < 3 * NW) ? (&s_mask[warp][1][0])[(k / NW) * 32 + k % NW] : 0u;
   const uint32_t *sarmy = reinterpret_cast<const uint32_t *>(s_army[warp]);
-  for (int k = lane; k < L.NA / 2; k += 32) garmy[k] = sarmy[k];
-  if (lane < mp.players) {
-    const int t = s_seat[warp][lane];
-    slab[L.off_own + lane * NW + (t >> 5)] = 1u << (t & 31);  // the staging slab is zero-filled: one general per player
+  for (int k = L.off_army + lane; k < L.slab_words; k += 32)
+    slab[k] = (placed && k - L.off_army < L.NA / 2) ? sarmy[k - L.off_army] : 0u;
+  for (int k = lane; k < L.P * NW; k += 32) {  // ownership: one general per player
+    const int p = k / NW, w = k - p * NW;
+    const int t = (placed && p < mp.players) ? s_seat[warp][p] : -1;
+    slab[L.off_own + k] = (t >= 0 && (t >> 5) == w) ? 1u << (t & 31) : 0u;
   }
 }
 
 cudaError_t grl_launch_mapgen(const GrlLayout &L, int W, int H, const GrlMapParams &mp, const long long *seeds, int n,
-                              uint32_t *slabs, uint32_t *statics, int *failed, cudaStream_t stream, const int *n_dev) {
-  grl_mapgen_kernel<<<(n + kMapWarps - 1) / kMapWarps, kMapWarps * 32, 0, stream>>>(L, W, H, mp, seeds, n, slabs, statics, failed, n_dev);
+                              uint32_t *slabs, uint32_t *statics, int *failed, cudaStream_t stream, const int *n_dev,
+                              const int32_t *ids, const float *obs, float *final_obs, int obs_block) {
+  grl_mapgen_kernel<<<(n + kMapWarps - 1) / kMapWarps, (final_obs ? 2 : 1) * kMapWarps * 32, 0, stream>>>(L, W, H, mp, seeds, n, slabs, statics, failed, n_dev,
+                                                                                   ids, obs, final_obs, obs_block);
   return cudaGetLastError();
 }
