@@ -360,6 +360,26 @@ def test_device_mapgen_matches_host_and_oracle(cuda_lib, oracle_lib, W, H, P, mo
     assert np.array_equal(dev.state_hash(), orc.state_hash())
 
 
+def test_device_mapgen_reports_unplaceable_generals(cuda_lib, oracle_lib, monkeypatch):
+    """mapgen/generator.go:166-253: when a general finds no tile far enough from the others the generator fails.  Eight
+    generals at Manhattan distance >= 2 do not fit a 3x3 board (five do), so every seed fails: the device generator, the
+    host generator and the oracle all report map generation failed; the device path leaves such envs as empty boards
+    without generals, i.e. finished games, never half-written ones."""
+    seeds = np.arange(16, dtype=np.int64) + 5
+    dev = new_engine(cuda_lib, 3, 3, 8, 16)
+    with pytest.raises(RuntimeError, match="map generation failed"):
+        dev.reset_seeded(seeds)
+    s = dev.get_state()
+    assert (s["owner"] == -1).all() and (s["army"] == 0).all() and (s["type"] == 0).all() and s["game_over"].all()
+    orc = new_engine(oracle_lib, 3, 3, 8, 16, host_threads=0)
+    with pytest.raises(RuntimeError, match="map generation failed"):
+        orc.reset_seeded(seeds)
+    monkeypatch.setenv("GRL_HOST_MAPGEN", "1")
+    host = new_engine(cuda_lib, 3, 3, 8, 16, host_threads=0)
+    with pytest.raises(RuntimeError, match="map generation failed"):
+        host.reset_seeded(seeds)
+
+
 @pytest.mark.parametrize("W,H,P", [(10, 10, 2), (15, 15, 2), (20, 20, 2), (20, 20, 4), (9, 9, 2)])
 def test_fog_disabled_parity(cuda_lib, oracle_lib, W, H, P):
     """GameState.FogOfWarEnabled == false (the reference's tests build such engines by hand): every tile is
