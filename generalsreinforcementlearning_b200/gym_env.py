@@ -17,7 +17,7 @@ engine's device — nothing crosses PCIe per step except one 4-byte "did any epi
 returns are the env's own (double-buffered) output planes: the observation, mask and turn are valid until the next
 step(), reward / terminated / truncated / the other info entries until the one after; clone what must live longer.
 Finished or truncated envs are re-seeded
-automatically (``info["final_observation"]`` keeps the pre-reset view), as Gymnasium vector
+automatically on the device (``info["final_observation"]`` keeps the pre-reset view), as Gymnasium vector
 envs do.
 
 This module needs neither ``gymnasium`` (absent from the image) nor gRPC.
@@ -66,13 +66,15 @@ class GeneralsVecEnv:
         self.num_envs, self.W, self.H, self.P = num_envs, board_width, board_height, max_players
         self.board_size = self.N = board_width * board_height
         self.max_turns, self.self_play = max_turns, self_play
-        # "host": the step reads one 4-byte flag and re-seeds finished envs from the host (compact
-        # info["final_observation"] / ["final_env_ids"]).  "device": grl_gym_autoreset re-seeds them on the device with
-        # NO host read — step() never synchronises, so a training loop can enqueue steps ahead; info["final_observation"]
-        # is then a dense [B, 9, H, W] plane whose rows are valid where info["final_env_mask"] is set, and info["turn"]
-        # already shows 0 for the re-seeded envs.
-        if auto_reset not in ("host", "device"):
-            raise ValueError("auto_reset is 'host' or 'device'")
+        # Finished envs are always re-seeded on the device (grl_gym_autoreset).  "device": NO host read — step() never
+        # synchronises, so a training loop can enqueue steps ahead; info["final_observation"] is a dense [B, 9, H, W]
+        # plane whose rows are valid where info["final_env_mask"] is set, and info["turn"] already shows 0 for the
+        # re-seeded envs.  "host": the step reads one 4-byte flag and, when episodes ended, hands out the compact
+        # info["final_observation"] / ["final_env_ids"] form with the finished envs' last turn counters in info["turn"].
+        # "host_reset": the same contract with the re-seeding driven from the host (grl_reset_seeded +
+        # grl_gym_observe_envs) — the independent path the tests check the device-side one against.
+        if auto_reset not in ("host", "device", "host_reset"):
+            raise ValueError("auto_reset is 'host', 'device' or 'host_reset'")
         self.auto_reset = auto_reset
         self.engine = BatchedEngine(lib, make_config(lib, num_envs=num_envs, width=board_width, height=board_height,
                                                      num_players=max_players, device=device, max_actions=max_players,
@@ -104,7 +106,7 @@ class GeneralsVecEnv:
         self._flip = 0
         self._nfin = torch.zeros(1, dtype=torch.int32, device=dev)
         self._opp_draws = 0
-        if auto_reset == "device":
+        if auto_reset != "host_reset":
             self._episode_dev = torch.zeros(B, dtype=torch.int64, device=dev)
             self._final_obs = torch.zeros((B, 9, self.H, self.W), dtype=torch.float32, device=dev)
         self._sample_draws = 0
@@ -131,7 +133,7 @@ class GeneralsVecEnv:
             self._base_seed = int(seed)
             self._gen.manual_seed(int(seed))
         self._episode[:] = 0
-        if self.auto_reset == "device":
+        if self.auto_reset != "host_reset":
             self._episode_dev.zero_()
         ids = np.arange(self.num_envs)
         self.engine.reset_seeded(self._seeds(ids))
@@ -169,25 +171,32 @@ class GeneralsVecEnv:
         turn = self._turns
         if self.auto_reset == "device":
             info["final_env_mask"] = terminated | truncated
-            self.engine.gym_autoreset(self.max_turns, self._base_seed, terminated=terminated, truncated=truncated,
-                                      episode=self._episode_dev, turns=self._turns, calls=self._calls, obs=self._obs,
-                                      mask=self._mask, stats=self._stats, final_obs=self._final_obs)
+            self._autoreset(terminated, truncated)
             info["final_observation"] = self._final_obs
         elif int(self._nfin.item()) > 0:   # the one host read of the step: does any env start a new episode?
             finished = terminated | truncated
             ids = finished.nonzero(as_tuple=True)[0]
-            info["final_observation"] = self._obs[ids, 0].clone()
             info["final_env_ids"] = ids
             turn = self._turns.clone()       # the finished envs' turn counters restart below
-            ids_np = ids.cpu().numpy()
-            self._episode[ids_np] += 1
-            self.engine.reset_seeded(self._seeds(ids_np), ids_np.astype(np.int32))
-            self._turns[ids] = 0
-            self._calls[ids] = 0
-            self._refresh(ids_np)
+            if self.auto_reset == "host":
+                self._autoreset(terminated, truncated)
+                info["final_observation"] = self._final_obs[ids]
+            else:
+                info["final_observation"] = self._obs[ids, 0].clone()
+                ids_np = ids.cpu().numpy()
+                self._episode[ids_np] += 1
+                self.engine.reset_seeded(self._seeds(ids_np), ids_np.astype(np.int32))
+                self._turns[ids] = 0
+                self._calls[ids] = 0
+                self._refresh(ids_np)
         info["turn"] = turn
         info["valid_actions_mask"] = self._mask[:, 0]
         return self._obs[:, 0], reward, terminated, truncated, info
+
+    def _autoreset(self, terminated, truncated):
+        self.engine.gym_autoreset(self.max_turns, self._base_seed, terminated=terminated, truncated=truncated,
+                                  episode=self._episode_dev, turns=self._turns, calls=self._calls, obs=self._obs,
+                                  mask=self._mask, stats=self._stats, final_obs=self._final_obs)
 
     def sample_actions(self, generator=None, player: int = 0):
         """A uniformly random VALID action per env (envs without one get action 0, which is rejected): the random

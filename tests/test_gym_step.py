@@ -251,7 +251,7 @@ def test_cuda_gym_sample_matches_oracle(cuda_lib, oracle_lib, W, H, P, B):
         assert np.array_equal(x, y)
 
 
-def _drive_pair(a, b, steps, compare_final=True):
+def _drive_pair(a, b, steps, compare_final=True, compact_info=False):
     """Two vector envs stepped with the same actions; every returned tensor compared each step."""
     import torch
 
@@ -279,17 +279,31 @@ def _drive_pair(a, b, steps, compare_final=True):
             fa = fa[fin] if fa.shape[0] == fin.shape[0] else fa
             fb = fb[fin] if fb.shape[0] == fin.shape[0] else fb
             assert torch.equal(fa, fb), f"final observation, step {t}"
+        if compact_info:   # both envs hand out the compact form: ids, final views and the pre-reset turn counters
+            assert ("final_env_ids" in ra[4]) == bool(fin.any()) and ("final_env_ids" in rb[4]) == bool(fin.any())
+            assert torch.equal(ra[4]["turn"].cpu(), rb[4]["turn"].cpu()), f"info turn, step {t}"
+            if fin.any():
+                assert torch.equal(ra[4]["final_env_ids"].cpu(), rb[4]["final_env_ids"].cpu()), f"final env ids, step {t}"
+                assert torch.equal(ra[4]["final_env_ids"].cpu(), fin.nonzero(as_tuple=True)[0])
+                assert torch.equal(ra[4]["final_observation"].cpu(), rb[4]["final_observation"].cpu())
     return resets
 
 
 def test_vector_env_device_autoreset_equals_host_autoreset(oracle_lib):
-    """auto_reset='device' (grl_gym_autoreset: no host read, dense final_observation) re-seeds the same envs with the
-    same seeds as the host path and hands out the same tensors."""
+    """auto_reset='device' (grl_gym_autoreset: no host read, dense final_observation) and 'host' (the same re-seeding,
+    compact final_observation / final_env_ids after one flag read) re-seed the same envs with the same seeds as the
+    host-driven path ('host_reset': grl_reset_seeded + grl_gym_observe_envs) and hand out the same tensors."""
     from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
 
-    a = GeneralsVecEnv(40, 8, 8, max_turns=9, seed=5, lib=oracle_lib, host_threads=1, auto_reset="host")
+    a = GeneralsVecEnv(40, 8, 8, max_turns=9, seed=5, lib=oracle_lib, host_threads=1, auto_reset="host_reset")
     b = GeneralsVecEnv(40, 8, 8, max_turns=9, seed=5, lib=oracle_lib, host_threads=1, auto_reset="device")
     assert _drive_pair(a, b, 40) >= 120
+    a.close()
+    b.close()
+    a = GeneralsVecEnv(40, 8, 8, max_turns=9, seed=5, lib=oracle_lib, host_threads=1, auto_reset="host_reset")
+    b = GeneralsVecEnv(40, 8, 8, max_turns=9, seed=5, lib=oracle_lib, host_threads=1)   # the default: "host"
+    assert b.auto_reset == "host"
+    assert _drive_pair(a, b, 40, compact_info=True) >= 120
     a.close()
     b.close()
 
@@ -307,8 +321,12 @@ def test_cuda_device_autoreset_matches_oracle(cuda_lib, oracle_lib, W, B, max_tu
     import numpy as np
     assert np.array_equal(g.engine.state_hash(), o.engine.state_hash())
     # and the device path equals the CUDA host path
-    h = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=31, lib=cuda_lib, auto_reset="host")
+    h = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=31, lib=cuda_lib, auto_reset="host_reset")
     g2 = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=31, lib=cuda_lib, auto_reset="device")
     _drive_pair(g2, h, 2 * max_turns + 2)
-    for e in (g, o, h, g2):
+    # and the compact-info mode over the device path equals the host-driven one, info entries included
+    h2 = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=31, lib=cuda_lib, auto_reset="host_reset")
+    g3 = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=31, lib=cuda_lib, auto_reset="host")
+    _drive_pair(g3, h2, 2 * max_turns + 2, compact_info=True)
+    for e in (g, o, h, g2, h2, g3):
         e.close()

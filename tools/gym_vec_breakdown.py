@@ -22,7 +22,7 @@ def timed(fn, steps):
 def main():
     B = int(os.environ.get("GRL_B", 65536))
     for W in (15, 20, 10):
-        for mode in ("device", "host"):
+        for mode in ("device", "host", "host_reset"):
             env = GeneralsVecEnv(B, W, W, max_turns=500, seed=3, auto_reset=mode)
             env.reset()
             env._calls.copy_(torch.randint(0, env.max_turns, (B,), device=env._calls.device, dtype=torch.int32))
