@@ -173,22 +173,28 @@ class GeneralsVecEnv:
             info["final_env_mask"] = terminated | truncated
             self._autoreset(terminated, truncated)
             info["final_observation"] = self._final_obs
-        elif int(self._nfin.item()) > 0:   # the one host read of the step: does any env start a new episode?
+        elif self.auto_reset == "host":
+            # the re-seeding is enqueued BEFORE the one host read of the step (how many episodes ended?), so the device
+            # works through it while the host waits; with the count known the id list needs no second synchronisation
+            turn = self._turns.clone()       # the finished envs' turn counters restart in the auto-reset
+            self._autoreset(terminated, truncated)
+            n = int(self._nfin.item())
+            if n > 0:
+                ids = t.nonzero_static(terminated | truncated, size=n).squeeze(1)
+                info["final_env_ids"] = ids
+                info["final_observation"] = self._final_obs[ids]
+        elif int(self._nfin.item()) > 0:     # "host_reset": the host drives the re-seeding
             finished = terminated | truncated
             ids = finished.nonzero(as_tuple=True)[0]
             info["final_env_ids"] = ids
-            turn = self._turns.clone()       # the finished envs' turn counters restart below
-            if self.auto_reset == "host":
-                self._autoreset(terminated, truncated)
-                info["final_observation"] = self._final_obs[ids]
-            else:
-                info["final_observation"] = self._obs[ids, 0].clone()
-                ids_np = ids.cpu().numpy()
-                self._episode[ids_np] += 1
-                self.engine.reset_seeded(self._seeds(ids_np), ids_np.astype(np.int32))
-                self._turns[ids] = 0
-                self._calls[ids] = 0
-                self._refresh(ids_np)
+            turn = self._turns.clone()
+            info["final_observation"] = self._obs[ids, 0].clone()
+            ids_np = ids.cpu().numpy()
+            self._episode[ids_np] += 1
+            self.engine.reset_seeded(self._seeds(ids_np), ids_np.astype(np.int32))
+            self._turns[ids] = 0
+            self._calls[ids] = 0
+            self._refresh(ids_np)
         info["turn"] = turn
         info["valid_actions_mask"] = self._mask[:, 0]
         return self._obs[:, 0], reward, terminated, truncated, info
