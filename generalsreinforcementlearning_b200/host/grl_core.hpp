@@ -5,7 +5,7 @@
 // meaning and error behaviour:
 //
 //   core::Tile, core::Board        internal/game/core/board.go:7-18, 20-26, 108-126
-//   core::Coordinate               internal/game/core/coordinate.go:5-56
+//   core::Coordinate, Direction    internal/game/core/coordinate.go:5-154
 //   core::MoveAction + Validate    internal/game/core/action.go:23-35, 56-105
 //   core::Err* sentinels, Wrap*    internal/game/core/errors.go:8-49
 //
@@ -88,6 +88,8 @@ inline Error WrapPlayerError(int playerID, const std::string &operation, const E
 }
 
 // ---- coordinate.go -----------------------------------------------------------------------
+enum Direction : int { North = 0, East = 1, South = 2, West = 3 };  // coordinate.go:106-113
+
 struct Coordinate {
   int X = 0, Y = 0;
   bool IsValid(int width, int height) const { return X >= 0 && X < width && Y >= 0 && Y < height; }
@@ -100,9 +102,42 @@ struct Coordinate {
     int dx = X - o.X, dy = Y - o.Y;
     return (dx == 0 && (dy == 1 || dy == -1)) || (dy == 0 && (dx == 1 || dx == -1));
   }
+  // coordinate.go:57-78: north, east, south, west — the order the gym client and the legal-move mask enumerate
+  std::vector<Coordinate> Neighbors() const { return {{X, Y - 1}, {X + 1, Y}, {X, Y + 1}, {X - 1, Y}}; }
+  std::vector<Coordinate> ValidNeighbors(int width, int height) const {
+    std::vector<Coordinate> valid;
+    valid.reserve(4);
+    for (const Coordinate &n : Neighbors())
+      if (n.IsValid(width, height)) valid.push_back(n);
+    return valid;
+  }
+  Coordinate Add(Coordinate o) const { return {X + o.X, Y + o.Y}; }
+  Coordinate Sub(Coordinate o) const { return {X - o.X, Y - o.Y}; }
+  bool Equal(Coordinate o) const { return X == o.X && Y == o.Y; }
+  std::string String() const { return "(" + std::to_string(X) + "," + std::to_string(Y) + ")"; }
+  // coordinate.go:123-129: one step in a direction; a value that is not a Direction leaves the coordinate unchanged
+  Coordinate Move(int direction) const;
+  // coordinate.go:131-154: the direction of an adjacent coordinate, -1 when `o` is not adjacent
+  int DirectionTo(Coordinate o) const {
+    if (!IsAdjacentTo(o)) return -1;
+    const int dx = o.X - X, dy = o.Y - Y;
+    if (dy == -1) return North;
+    if (dx == 1) return East;
+    if (dy == 1) return South;
+    if (dx == -1) return West;
+    return -1;
+  }
   bool operator==(Coordinate o) const { return X == o.X && Y == o.Y; }
+  bool operator!=(Coordinate o) const { return !(*this == o); }
+  bool operator<(Coordinate o) const { return Y != o.Y ? Y < o.Y : X < o.X; }  // Go structs are map keys; std::map needs an order
 };
+inline Coordinate NewCoordinate(int x, int y) { return Coordinate{x, y}; }
 inline Coordinate FromIndex(int idx, int width) { return Coordinate{idx % width, idx / width}; }
+// coordinate.go:115-121 (a map in Go; indexed by Direction here)
+inline const Coordinate DirectionVectors[4] = {{0, -1}, {1, 0}, {0, 1}, {-1, 0}};
+inline Coordinate Coordinate::Move(int direction) const {
+  return (direction >= North && direction <= West) ? Add(DirectionVectors[direction]) : *this;
+}
 
 // ---- board.go ----------------------------------------------------------------------------
 enum : int { TileNormal = 0, TileGeneral = 1, TileCity = 2, TileMountain = 3 };
@@ -135,6 +170,14 @@ struct Board {
   Tile *GetTile(int x, int y) { return InBounds(x, y) ? &T[Idx(x, y)] : nullptr; }
   const Tile *GetTile(int x, int y) const { return InBounds(x, y) ? &T[Idx(x, y)] : nullptr; }
   int Distance(int x1, int y1, int x2, int y2) const { return Coordinate{x1, y1}.DistanceTo({x2, y2}); }
+  // board.go:136-159, the coordinate-based forms
+  bool InBoundsCoord(Coordinate c) const { return InBounds(c.X, c.Y); }
+  Tile *GetTileCoord(Coordinate c) { return GetTile(c.X, c.Y); }
+  const Tile *GetTileCoord(Coordinate c) const { return GetTile(c.X, c.Y); }
+  void SetTile(Coordinate c, const Tile &tile) {
+    if (InBoundsCoord(c)) T[Idx(c.X, c.Y)] = tile;
+  }
+  int IdxCoord(Coordinate c) const { return Idx(c.X, c.Y); }
   std::shared_ptr<Board> Clone() const { return std::make_shared<Board>(*this); }
 };
 inline std::shared_ptr<Board> NewBoard(int w, int h) {
@@ -150,10 +193,15 @@ struct MoveAction {
   int PlayerID = 0;
   int FromX = 0, FromY = 0, ToX = 0, ToY = 0;
   bool MoveAll = false;  // true: leave one behind; false: move half (min 1)
+  // action.go:30-32: the coordinate fields.  As in the reference they only feed GetFrom/GetTo (and through them the
+  // adjacency test of Validate); bounds, ownership, armies and the move itself read FromX/FromY/ToX/ToY, and so does the
+  // device.  Declared after MoveAll so that the six-value aggregate form used throughout keeps its meaning.
+  Coordinate From{}, To{};
 
   int GetPlayerID() const { return PlayerID; }
-  Coordinate GetFrom() const { return {FromX, FromY}; }
-  Coordinate GetTo() const { return {ToX, ToY}; }
+  // action.go:40-54: the coordinate field when it is set (non-zero), the legacy pair otherwise
+  Coordinate GetFrom() const { return From != Coordinate{} ? From : Coordinate{FromX, FromY}; }
+  Coordinate GetTo() const { return To != Coordinate{} ? To : Coordinate{ToX, ToY}; }
 
   // action.go:56-105, checks in the reference's order.
   Error Validate(const Board &b, int playerID) const {
@@ -190,6 +238,16 @@ inline Error WrapActionError(const MoveAction &a, const Error &err) {
                          at(a.ToX, a.ToY),
                      err);
 }
+
+// utils.go:10-12: fmt.Sprintf("%*d", width, num) — left-padded with spaces, never truncated
+inline std::string IntToStringFixedWidth(int num, int width) {
+  std::string d = std::to_string(num);
+  const size_t w = width < 0 ? size_t(-(long long)width) : size_t(width);
+  if (d.size() >= w) return d;
+  return width < 0 ? d + std::string(w - d.size(), ' ') : std::string(w - d.size(), ' ') + d;  // a negative width left-justifies
+}
+// utils.go:14-19: fmt.Sprintf("%T", action); the only Action is *MoveAction
+inline std::string GetActionType(const MoveAction *action) { return action ? "*core.MoveAction" : "nil"; }
 
 }  // namespace core
 

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -859,6 +860,150 @@ TEST(TestBoardRendering) {
   EXPECT(engine->Board(0) == want, "Board(0):\n%s\nwant:\n%s", engine->Board(0).c_str(), want.c_str());
   std::string all = engine->Board(-1);  // spectator: no fog (rendering.go:96)
   EXPECT(all.find(Blue + "B+" + R) != std::string::npos, "spectator sees player 1's 150-army tile as B+");
+}
+
+// ---- core.Coordinate / Direction (coordinate_test.go), the coordinate forms of Board and MoveAction
+// (coordinate_integration_test.go:10-88), core/utils (utils_test.go) ---------------------------------
+using core::Coordinate;
+static Coordinate C(int x, int y) { return Coordinate{x, y}; }
+
+TEST(TestCoordinate_IndexRoundTrip) {  // coordinate_test.go:9-69
+  Coordinate c = core::NewCoordinate(3, 5);
+  EXPECT(c.X == 3 && c.Y == 5, "NewCoordinate");
+  struct { int index, width; Coordinate want; } cases[] = {{0, 10, {0, 0}}, {9, 10, {9, 0}}, {10, 10, {0, 1}}, {55, 10, {5, 5}},
+                                                          {99, 10, {9, 9}}, {7, 4, {3, 1}}};
+  for (auto &t : cases) {
+    EXPECT(core::FromIndex(t.index, t.width) == t.want, "FromIndex(%d, %d)", t.index, t.width);
+    EXPECT_EQ(t.index, t.want.ToIndex(t.width), "ToIndex of (%d,%d)", t.want.X, t.want.Y);
+  }
+  for (int i = 0; i < 100; i++) EXPECT_EQ(i, core::FromIndex(i, 10).ToIndex(10), "round trip of %d", i);
+}
+
+TEST(TestCoordinate_IsValid) {  // coordinate_test.go:71-96
+  struct { Coordinate c; bool valid; } cases[] = {{{0, 0}, true},  {{5, 5}, true},   {{9, 9}, true},   {{-1, 5}, false}, {{5, -1}, false},
+                                                  {{10, 5}, false}, {{5, 10}, false}, {{-1, -1}, false}, {{10, 10}, false}};
+  for (auto &t : cases) EXPECT_EQ(t.valid, t.c.IsValid(10, 10), "IsValid of (%d,%d)", t.c.X, t.c.Y);
+}
+
+TEST(TestCoordinate_DistanceAndAdjacency) {  // coordinate_test.go:98-153
+  struct { Coordinate a, b; int want; } dist[] = {{{5, 5}, {5, 5}, 0}, {{5, 5}, {6, 5}, 1},  {{5, 5}, {5, 6}, 1},
+                                                  {{0, 0}, {1, 1}, 2}, {{0, 0}, {5, 7}, 12}, {{-2, -3}, {2, 3}, 10}};
+  for (auto &t : dist) {
+    EXPECT_EQ(t.want, t.a.DistanceTo(t.b), "distance");
+    EXPECT_EQ(t.want, t.b.DistanceTo(t.a), "distance is symmetric");
+  }
+  const Coordinate center{5, 5};
+  struct { Coordinate o; bool adj; } adj[] = {{{5, 4}, true},  {{6, 5}, true},  {{5, 6}, true},  {{4, 5}, true},  {{6, 4}, false}, {{6, 6}, false},
+                                              {{4, 6}, false}, {{4, 4}, false}, {{5, 5}, false}, {{7, 5}, false}, {{0, 0}, false}};
+  for (auto &t : adj) {
+    EXPECT_EQ(t.adj, center.IsAdjacentTo(t.o), "adjacency of (%d,%d)", t.o.X, t.o.Y);
+    EXPECT_EQ(t.adj, t.o.IsAdjacentTo(center), "adjacency is symmetric");
+  }
+}
+
+TEST(TestCoordinate_Neighbors) {  // coordinate_test.go:155-197
+  auto has = [](const std::vector<Coordinate> &v, Coordinate c) {
+    for (const Coordinate &x : v)
+      if (x == c) return true;
+    return false;
+  };
+  auto nb = C(5, 5).Neighbors();
+  EXPECT_EQ(size_t(4), nb.size(), "four neighbours");
+  EXPECT(has(nb, {5, 4}) && has(nb, {6, 5}) && has(nb, {5, 6}) && has(nb, {4, 5}), "north, east, south, west");
+  EXPECT(nb[0] == C(5, 4) && nb[1] == C(6, 5) && nb[2] == C(5, 6) && nb[3] == C(4, 5),
+         "in the order of coordinate.go:59-64");
+  struct { Coordinate c; int w, h, count; } cases[] = {{{5, 5}, 10, 10, 4}, {{0, 0}, 10, 10, 2}, {{9, 0}, 10, 10, 2}, {{0, 9}, 10, 10, 2},
+                                                       {{9, 9}, 10, 10, 2}, {{5, 0}, 10, 10, 3}, {{5, 9}, 10, 10, 3}, {{0, 5}, 10, 10, 3},
+                                                       {{9, 5}, 10, 10, 3}, {{0, 0}, 1, 1, 0}};
+  for (auto &t : cases) {
+    auto valid = t.c.ValidNeighbors(t.w, t.h);
+    EXPECT_EQ(size_t(t.count), valid.size(), "valid neighbours of (%d,%d)", t.c.X, t.c.Y);
+    for (const Coordinate &n : valid) EXPECT(n.IsValid(t.w, t.h) && n.IsAdjacentTo(t.c), "a valid neighbour is in bounds and adjacent");
+  }
+}
+
+TEST(TestCoordinate_Arithmetic) {  // coordinate_test.go:199-258
+  Coordinate c1{3, 4}, c2{2, -1};
+  EXPECT(c1.Add(c2) == C(5, 3), "Add");
+  EXPECT(c1 == C(3, 4) && c2 == C(2, -1), "operands unchanged");
+  EXPECT(C(5, 3).Sub(c2) == C(3, 4), "Sub");
+  struct { Coordinate a, b; bool eq; } eq[] = {{{0, 0}, {0, 0}, true},  {{5, 7}, {5, 7}, true},  {{-1, -1}, {-1, -1}, true},
+                                               {{5, 7}, {7, 5}, false}, {{0, 0}, {0, 1}, false}, {{0, 0}, {1, 0}, false}};
+  for (auto &t : eq) EXPECT(t.a.Equal(t.b) == t.eq && t.b.Equal(t.a) == t.eq, "Equal, both ways");
+  EXPECT_EQ(std::string("(0,0)"), (C(0, 0).String()), "String");
+  EXPECT_EQ(std::string("(5,7)"), (C(5, 7).String()), "String");
+  EXPECT_EQ(std::string("(-1,-2)"), (C(-1, -2).String()), "String");
+  EXPECT_EQ(std::string("(100,200)"), (C(100, 200).String()), "String");
+}
+
+TEST(TestCoordinate_Directions) {  // coordinate_test.go:260-322
+  const Coordinate start{5, 5};
+  EXPECT(start.Move(core::North) == C(5, 4), "north");
+  EXPECT(start.Move(core::East) == C(6, 5), "east");
+  EXPECT(start.Move(core::South) == C(5, 6), "south");
+  EXPECT(start.Move(core::West) == C(4, 5), "west");
+  EXPECT(start.Move(7) == start, "an unknown direction moves nowhere (coordinate.go:124-128)");
+  EXPECT_EQ(int(core::North), start.DirectionTo({5, 4}), "direction north");
+  EXPECT_EQ(int(core::East), start.DirectionTo({6, 5}), "direction east");
+  EXPECT_EQ(int(core::South), start.DirectionTo({5, 6}), "direction south");
+  EXPECT_EQ(int(core::West), start.DirectionTo({4, 5}), "direction west");
+  EXPECT_EQ(-1, start.DirectionTo({6, 6}), "diagonal");
+  EXPECT_EQ(-1, start.DirectionTo({5, 5}), "same");
+  EXPECT_EQ(-1, start.DirectionTo({10, 10}), "far");
+  EXPECT(core::DirectionVectors[core::North] == C(0, -1) && core::DirectionVectors[core::East] == C(1, 0) &&
+             core::DirectionVectors[core::South] == C(0, 1) && core::DirectionVectors[core::West] == C(-1, 0),
+         "direction vectors");
+  for (const Coordinate &v : core::DirectionVectors) EXPECT_EQ(1, v.DistanceTo({0, 0}), "unit length");
+}
+
+TEST(TestCoordinate_ComparableAsMapKey) {  // coordinate_test.go:324-340
+  std::map<Coordinate, std::string> m;
+  m[C(5, 5)] = "first";
+  m[C(6, 5)] = "third";
+  EXPECT_EQ(std::string("first"), m[(C(5, 5))], "equal coordinates are one key");
+  EXPECT_EQ(std::string("third"), m[(C(6, 5))], "third");
+  EXPECT_EQ(size_t(2), m.size(), "two keys");
+}
+
+TEST(TestCoordinateIntegration_Board) {  // coordinate_integration_test.go:12-41
+  auto board = core::NewBoard(10, 10);
+  const Coordinate coord = core::NewCoordinate(5, 5);
+  EXPECT(board->InBoundsCoord(coord), "in bounds");
+  EXPECT(!board->InBoundsCoord(core::NewCoordinate(-1, 5)) && !board->InBoundsCoord(core::NewCoordinate(10, 5)), "out of bounds");
+  Tile *tile = board->GetTileCoord(coord);
+  REQUIRE(tile != nullptr, "tile");
+  EXPECT_EQ(core::NeutralID, tile->Owner, "a fresh tile is neutral");
+  Tile nt;
+  nt.Owner = 1, nt.Army = 10, nt.Type = core::TileNormal;
+  board->SetTile(coord, nt);
+  EXPECT(board->GetTileCoord(coord)->Owner == 1 && board->GetTileCoord(coord)->Army == 10, "SetTile");
+  EXPECT_EQ(55, board->IdxCoord(coord), "IdxCoord = 5 * 10 + 5");
+  board->SetTile(core::NewCoordinate(-1, -1), nt);  // out of bounds: ignored
+  EXPECT(board->GetTileCoord(core::NewCoordinate(-1, -1)) == nullptr, "no tile out of bounds");
+}
+
+TEST(TestCoordinateIntegration_MoveAction) {  // coordinate_integration_test.go:44-88
+  MoveAction a1{1, 3, 4, 3, 5, true};
+  EXPECT(a1.GetFrom() == C(3, 4) && a1.GetTo() == C(3, 5), "legacy fields");
+  MoveAction a2;
+  a2.PlayerID = 1, a2.From = core::NewCoordinate(5, 6), a2.To = core::NewCoordinate(5, 7);
+  EXPECT(a2.GetFrom() == C(5, 6) && a2.GetTo() == C(5, 7), "coordinate fields win when set");
+  MoveAction a3;
+  a3.PlayerID = 1, a3.From = core::NewCoordinate(2, 3), a3.ToX = 2, a3.ToY = 4, a3.MoveAll = true;
+  EXPECT(a3.GetFrom() == C(2, 3) && a3.GetTo() == C(2, 4), "mixed: To falls back to ToX, ToY");
+}
+
+TEST(TestIntToStringFixedWidth) {  // utils_test.go:10-93
+  struct { int num, width; const char *want; } cases[] = {{5, 3, "  5"},   {42, 3, " 42"}, {123, 3, "123"},           {1234, 3, "1234"}, {-5, 3, " -5"},
+                                                          {0, 3, "  0"},   {7, 1, "7"},    {99, 10, "        99"},   {123, 0, "123"},   {123, -5, "123  "},
+                                                          {999999999, 5, "999999999"}};
+  for (auto &t : cases) EXPECT_EQ(std::string(t.want), core::IntToStringFixedWidth(t.num, t.width), "%d in width %d", t.num, t.width);
+}
+
+TEST(TestGetActionType) {  // utils_test.go:95-141
+  EXPECT_EQ(std::string("nil"), core::GetActionType(nullptr), "nil action");
+  MoveAction mv{0, 0, 0, 1, 0, true};
+  EXPECT_EQ(std::string("*core.MoveAction"), core::GetActionType(&mv), "a move");
 }
 
 // ---- the product binding must not fall back to anything ---------------------------------------------
