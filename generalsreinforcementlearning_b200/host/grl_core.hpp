@@ -7,7 +7,7 @@
 //   core::Tile, core::Board        internal/game/core/board.go:7-18, 20-26, 108-126
 //   core::Coordinate, Direction    internal/game/core/coordinate.go:5-154
 //   core::MoveAction + Validate    internal/game/core/action.go:23-35, 56-105
-//   core::Err* sentinels, Wrap*    internal/game/core/errors.go:8-49
+//   core::Err* sentinels, Wrap*, GameError   internal/game/core/errors.go:8-79
 //
 // Nothing here steps a game: the turn runs on the GPU (grl_engine.hpp).  Validate is the
 // client-side pre-check the reference's server runs on a state copy before it queues an action
@@ -85,6 +85,23 @@ inline Error WrapGameStateError(int turn, const std::string &phase, const Error 
 // errors.go:43-49
 inline Error WrapPlayerError(int playerID, const std::string &operation, const Error &err) {
   return Error::Wrap("player " + std::to_string(playerID) + " " + operation, err);
+}
+
+// errors.go:51-79: a structured error with game context; Unwrap() is `Err`, so errors.Is reaches the sentinel
+struct GameError {
+  int Turn = 0, PlayerID = 0;
+  std::string Operation;
+  Error Err;
+  std::string String() const {  // Error() in Go
+    if (PlayerID != 0)
+      return "turn " + std::to_string(Turn) + ": player " + std::to_string(PlayerID) + " " + Operation + ": " + Err.String();
+    return "turn " + std::to_string(Turn) + ": " + Operation + ": " + Err.String();
+  }
+  const Error &Unwrap() const { return Err; }
+  bool Is(const Sentinel &s) const { return Err.Is(s); }
+};
+inline GameError NewGameError(int turn, int playerID, const std::string &operation, const Error &err) {
+  return GameError{turn, playerID, operation, err};
 }
 
 // ---- coordinate.go -----------------------------------------------------------------------
@@ -248,6 +265,11 @@ inline std::string IntToStringFixedWidth(int num, int width) {
 }
 // utils.go:14-19: fmt.Sprintf("%T", action); the only Action is *MoveAction
 inline std::string GetActionType(const MoveAction *action) { return action ? "*core.MoveAction" : "nil"; }
+
+// errors.go:20-33 with an action of unknown type (Go: a nil Action interface): the generic prefix
+inline Error WrapActionError(const MoveAction *a, const Error &err) {
+  return a ? WrapActionError(*a, err) : Error::Wrap("player action", err);
+}
 
 }  // namespace core
 

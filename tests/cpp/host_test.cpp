@@ -1006,6 +1006,64 @@ TEST(TestGetActionType) {  // utils_test.go:95-141
   EXPECT_EQ(std::string("*core.MoveAction"), core::GetActionType(&mv), "a move");
 }
 
+// ---- core/errors (errors_test.go) ---------------------------------------------------------------------
+TEST(TestWrapActionError) {  // errors_test.go:12-60
+  MoveAction a0{1, 0, 0, 1, 0, false};
+  EXPECT(core::WrapActionError(a0, core::Error()).IsNil(), "a nil error stays nil");
+  MoveAction a1{1, 5, 3, 5, 4, false};
+  core::Error w1 = core::WrapActionError(a1, core::ErrInvalidCoordinates);
+  EXPECT_EQ(std::string("player 1: move from (5,3) to (5,4): invalid coordinates"), w1.String(), "message");
+  EXPECT(errors::Is(w1, core::ErrInvalidCoordinates), "errors.Is through the wrap");
+  MoveAction a2{2, 10, 10, 11, 10, false};
+  core::Error w2 = core::WrapActionError(a2, core::ErrNotOwned);
+  EXPECT_EQ(std::string("player 2: move from (10,10) to (11,10): tile not owned by player"), w2.String(), "message");
+  EXPECT(errors::Is(w2, core::ErrNotOwned), "errors.Is through the wrap");
+  core::Error w3 = core::WrapActionError(static_cast<const MoveAction *>(nullptr), core::ErrGameOver);
+  EXPECT_EQ(std::string("player action: game is over"), w3.String(), "generic fallback");
+  EXPECT(errors::Is(w3, core::ErrGameOver), "errors.Is through the fallback");
+}
+
+TEST(TestWrapGameStateAndPlayerError) {  // errors_test.go:62-158
+  EXPECT(core::WrapGameStateError(50, "action", core::Error()).IsNil(), "a nil error stays nil");
+  core::Error g1 = core::WrapGameStateError(100, "action", core::ErrGameOver);
+  EXPECT_EQ(std::string("game turn 100 [action]: game is over"), g1.String(), "message");
+  EXPECT(errors::Is(g1, core::ErrGameOver), "errors.Is");
+  core::Error g2 = core::WrapGameStateError(25, "production", core::Error::New("failed to apply production"));
+  EXPECT_EQ(std::string("game turn 25 [production]: failed to apply production"), g2.String(), "a plain error wraps too");
+  EXPECT(!errors::Is(g2, core::ErrGameOver), "and carries no sentinel");
+  EXPECT(core::WrapPlayerError(1, "move validation", core::Error()).IsNil(), "a nil error stays nil");
+  core::Error p1 = core::WrapPlayerError(3, "move validation", core::ErrInsufficientArmy);
+  EXPECT_EQ(std::string("player 3 move validation: insufficient army to move"), p1.String(), "message");
+  EXPECT(errors::Is(p1, core::ErrInsufficientArmy), "errors.Is");
+  core::Error p2 = core::WrapPlayerError(0, "action processing", core::ErrInvalidPlayer);
+  EXPECT_EQ(std::string("player 0 action processing: invalid player ID"), p2.String(), "message");
+  EXPECT(errors::Is(p2, core::ErrInvalidPlayer), "errors.Is");
+}
+
+TEST(TestGameError) {  // errors_test.go:160-186
+  core::GameError e1 = core::NewGameError(150, 2, "capture general", core::ErrNotOwned);
+  EXPECT_EQ(std::string("turn 150: player 2 capture general: tile not owned by player"), e1.String(), "with a player");
+  EXPECT(e1.Is(core::ErrNotOwned), "unwraps to the sentinel");
+  core::GameError e2 = core::NewGameError(200, 0, "win condition check", core::ErrGameOver);
+  EXPECT_EQ(std::string("turn 200: win condition check: game is over"), e2.String(), "player 0 is left out (errors.go:61-66)");
+  EXPECT(e2.Is(core::ErrGameOver), "unwraps to the sentinel");
+  core::GameError e3 = core::NewGameError(50, 1, "network sync", core::Error::New("network timeout"));
+  EXPECT(e3.Turn == 50 && e3.PlayerID == 1 && e3.Operation == "network sync", "fields");
+  EXPECT_EQ(std::string("network timeout"), e3.Unwrap().String(), "Unwrap");
+}
+
+TEST(TestErrorUtilitiesUsageExample) {  // errors_test.go:188-216: a move from a neutral tile on an empty board
+  auto board = core::NewBoard(10, 10);
+  MoveAction move{1, 5, 3, 5, 4, false};
+  core::Error err = move.Validate(*board, 1);
+  REQUIRE(!err.IsNil(), "the tile is not the player's");
+  EXPECT(errors::Is(err, core::ErrNotOwned), "not owned");
+  core::Error wrapped = core::WrapActionError(move, err);
+  EXPECT(wrapped.String().rfind("player 1: move from (5,3) to (5,4): ", 0) == 0, "the action context comes first: %s", wrapped.String().c_str());
+  EXPECT(errors::Is(wrapped, core::ErrNotOwned), "the chain keeps the sentinel");
+  EXPECT(errors::Is(core::WrapPlayerError(1, "move", core::ErrInsufficientArmy), core::ErrInsufficientArmy), "example 4");
+}
+
 // ---- the product binding must not fall back to anything ---------------------------------------------
 TEST(TestLibraryMissingFailsLoudly) {
   bool threw = false;
