@@ -475,6 +475,34 @@ def test_more_games_than_env_slots_through_one_server(oracle_lib):
         gs.close()
 
 
+def test_reference_cleanup_kats(server):
+    """cleanup_test.go:14-103 (TestGameCleanup) and :105-149 (TestLastActivityUpdates): a lobby game without an engine is
+    kept while it shows activity and removed once it has been idle past the abandoned-game timeout (35 min > 30 min);
+    JoinGame refreshes lastActivity."""
+    import time as _t
+
+    gs, stub, _, _, _ = server
+    cfg = game.GameConfig(width=10, height=10, max_players=2)
+    gid = stub.CreateGame(game.CreateGameRequest(config=cfg)).game_id
+    g = gs.games[gid]
+    g.last_activity = _t.time()
+    gs.cleanup_games()
+    assert gid in gs.games, "Active game should not be cleaned up"
+    g.last_activity = _t.time() - 35 * 60
+    gs.cleanup_games()
+    assert gid not in gs.games, "Abandoned game without engine should be cleaned up"
+    gid2 = stub.CreateGame(game.CreateGameRequest(config=cfg)).game_id
+    gs.games[gid2].last_activity = _t.time()
+    gs.cleanup_games()
+    assert gid2 in gs.games, "Active game should not be cleaned up"
+    # TestLastActivityUpdates
+    gid3 = stub.CreateGame(game.CreateGameRequest(config=cfg)).game_id
+    initial = gs.games[gid3].last_activity
+    _t.sleep(0.01)
+    stub.JoinGame(game.JoinGameRequest(game_id=gid3, player_name="Player1"))
+    assert gs.games[gid3].last_activity > initial, "Join should update last activity"
+
+
 def test_reference_compat_emits_the_action_index_the_reference_server_emits(oracle_lib):
     """on the reference's gRPC path Experience.action is always 0 (turn_processor.go:194-199 reads
     MoveAction.From/To, converters.go:116-123 fills FromX/FromY/ToX/ToY).  Default: the real ActionToIndex."""
