@@ -1832,7 +1832,10 @@ int grlo_test_place_mountains(int W, int H, int veins, int min_len, int max_len,
 int grlo_test_place_cities(int W, int H, int city_ratio, int city_army, int64_t seed, int32_t *type, int32_t *army) {
   int N = W * H;
   tile_t *T = (tile_t *)calloc((size_t)N, sizeof(tile_t));
-  for (int i = 0; i < N; i++) T[i].owner = GRL_NEUTRAL;
+  for (int i = 0; i < N; i++) {
+    T[i].owner = GRL_NEUTRAL;
+    T[i].type = type[i]; /* in/out: a caller-prepared board (generator_test.go:196-244 pre-fills mountains) */
+  }
   go_rand *rng = (go_rand *)malloc(sizeof(go_rand));
   go_rand_seed(rng, seed);
   mapcfg_t m = {W, H, 0, city_ratio, city_army, 5, 0, 3, 3};

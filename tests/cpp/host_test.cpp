@@ -700,6 +700,75 @@ TEST(TestSimpleCollector) {
   EXPECT_EQ(0, collector.GetExperienceCount(), "GetExperiences drains the buffer");
 }
 
+// collector_test.go:98-123 BufferOverflow, :124-141 OnGameEnd, :142-174 GameEndingExperience, :175-196 Clear — the
+// transitions come from real turns here (the records' tensors are the device's), the asserted counts and values are the
+// reference's
+static bool firstLegalMove(game::Engine &engine, int p, int W, MoveAction *out) {
+  const int dxs[4] = {0, 1, 0, -1}, dys[4] = {-1, 0, 1, 0};
+  std::vector<bool> mask = engine.GetLegalActionMask(p);
+  for (int a = 0; a < int(mask.size()); a++)
+    if (mask[a]) {
+      const int t = a / 4, d = a % 4;
+      *out = mv(t % W, t / W, t % W + dxs[d], t / W + dys[d], false);
+      out->PlayerID = p;
+      return true;
+    }
+  return false;
+}
+
+TEST(TestSimpleCollector_BufferOverflowAndClear) {
+  experience::SimpleCollector collector(2, "test-game-123");  // a small buffer
+  auto engine = newEngine(5, 5, 2, &collector);
+  REQUIRE(engine != nullptr, "nil engine");
+  collector.Attach(engine.get());
+  for (int i = 0; i < 3; i++) {  // the general needs two armies before it can move
+    REQUIRE(!engine->Step(context::Background(), {}), "idle step");
+  }
+  for (int i = 0; i < 3; i++) {
+    MoveAction m;
+    REQUIRE(firstLegalMove(*engine, 0, 5, &m), "player 0 has a move on turn %d", i);
+    REQUIRE(!engine->Step(context::Background(), {m}), "move step");
+    EXPECT_EQ(i < 2 ? i + 1 : 2, collector.GetExperienceCount(), "the third record finds the buffer full: still 2");
+  }
+  collector.Clear();  // collector_test.go:175-196
+  EXPECT_EQ(0, collector.GetExperienceCount(), "Clear empties the buffer");
+  MoveAction m;
+  if (firstLegalMove(*engine, 0, 5, &m)) {
+    REQUIRE(!engine->Step(context::Background(), {m}), "move step");
+    EXPECT_EQ(1, collector.GetExperienceCount(), "and it fills again");
+  }
+}
+
+TEST(TestSimpleCollector_GameEndingExperience) {
+  experience::SimpleCollector collector(100, "test-game-123");
+  auto engine = newEngine(5, 5, 2, &collector);
+  REQUIRE(engine != nullptr, "nil engine");
+  collector.Attach(engine.get());
+  // the board of TestEngine_PlayerEliminationAndTileTurnover: player 0 takes player 1's general in one move
+  game::GameState *gs = engine->gs();
+  core::Board &board = *gs->Board;
+  board.T[board.Idx(0, 0)] = mk(0, 20, core::TileNormal);
+  const int old = gs->Players[1].GeneralIdx, gen = board.Idx(0, 1);
+  if (old != gen) board.T[old] = mk(core::NeutralID, 0, core::TileNormal);
+  board.T[gen] = mk(1, 1, core::TileGeneral);
+  gs->Players[1].GeneralIdx = gen;
+  REQUIRE(gs->Players[0].GeneralIdx != gen, "test setup conflict");
+  updatePlayerStats(*engine);
+  MoveAction action = mv(0, 0, 0, 1, true);
+  action.PlayerID = 0;
+  REQUIRE(!engine->Step(context::Background(), {action}), "capture step");
+  EXPECT(engine->IsGameOver(), "the game ends with the capture");
+  auto exps = collector.GetExperiences();
+  REQUIRE(exps.size() == 1, "one record, for the player that acted");
+  EXPECT(exps[0].Done, "Done");
+  EXPECT_EQ(1.0f, exps[0].Reward, "the winner gets +1.0 (rewards.go:48-52)");
+  EXPECT_EQ(0, exps[0].PlayerId, "player 0");
+  // collector_test.go:124-141: OnGameEnd with a finished state does not throw; the engine reports the end once
+  game::GameState fin = engine->GameState();
+  collector.OnGameEnd(&fin);
+  EXPECT(collector.GamesEnded() >= 1, "game end seen");
+}
+
 // ---- the pool: many games, one launch per turn --------------------------------------------------------
 TEST(TestEnginePool_SlotsAreIndependentGames) {
   const int B = 6, W = 10, H = 10, P = 2;
@@ -1004,6 +1073,62 @@ TEST(TestGetActionType) {  // utils_test.go:95-141
   EXPECT_EQ(std::string("nil"), core::GetActionType(nullptr), "nil action");
   MoveAction mv{0, 0, 0, 1, 0, true};
   EXPECT_EQ(std::string("*core.MoveAction"), core::GetActionType(&mv), "a move");
+}
+
+// ---- core.Board / core.Tile (board_test.go:10-281) -----------------------------------------------------
+TEST(TestBoard_Basics) {
+  struct { int w, h; } sizes[] = {{5, 5}, {10, 20}, {100, 100}, {1, 1}};  // TestNewBoard
+  for (auto &sz : sizes) {
+    auto b = core::NewBoard(sz.w, sz.h);
+    EXPECT(b->W == sz.w && b->H == sz.h && int(b->T.size()) == sz.w * sz.h, "%dx%d", sz.w, sz.h);
+    bool fresh = true;
+    for (const Tile &t : b->T) fresh = fresh && t.Owner == core::NeutralID && t.Type == core::TileNormal && t.Army == 0 && t.VisibleBitfield == 0;
+    EXPECT(fresh, "every tile neutral, normal, empty, unseen");
+  }
+  auto board = core::NewBoard(5, 5);
+  struct { int x, y, idx; } at[] = {{0, 0, 0}, {4, 0, 4}, {0, 1, 5}, {2, 2, 12}, {4, 4, 24}};  // TestBoard_Idx, TestBoard_XY
+  for (auto &t : at) {
+    EXPECT_EQ(t.idx, board->Idx(t.x, t.y), "Idx(%d,%d)", t.x, t.y);
+    EXPECT(board->XY(t.idx) == std::make_pair(t.x, t.y), "XY(%d)", t.idx);
+  }
+  struct { int x, y; bool in; } bounds[] = {{0, 0, true},  {4, 0, true},  {0, 4, true},  {4, 4, true},   {2, 2, true},  {-1, 2, false},
+                                            {2, -1, false}, {5, 2, false}, {2, 5, false}, {-1, -1, false}, {10, 10, false}};  // TestBoard_InBounds
+  for (auto &t : bounds) EXPECT_EQ(t.in, board->InBounds(t.x, t.y), "InBounds(%d,%d)", t.x, t.y);
+  board->T[0] = mk(0, 10, core::TileGeneral);  // TestBoard_GetTile
+  board->T[12] = mk(1, 5, core::TileCity);
+  Tile *g = board->GetTile(0, 0), *c = board->GetTile(2, 2);
+  REQUIRE(g && c, "tiles in bounds");
+  EXPECT(g->Owner == 0 && g->Army == 10 && g->Type == core::TileGeneral, "general tile");
+  EXPECT(c->Owner == 1 && c->Army == 5 && c->Type == core::TileCity, "city tile");
+  EXPECT(board->GetTile(-1, 0) == nullptr && board->GetTile(10, 10) == nullptr, "nil out of bounds");
+  auto b10 = core::NewBoard(10, 10);  // TestBoard_Distance
+  struct { int x1, y1, x2, y2, d; } dist[] = {{5, 5, 5, 5, 0}, {0, 0, 5, 0, 5}, {0, 0, 0, 5, 5}, {0, 0, 3, 4, 7}, {2, 2, -1, -1, 6}, {0, 0, 9, 9, 18}};
+  for (auto &t : dist) EXPECT(b10->Distance(t.x1, t.y1, t.x2, t.y2) == t.d && b10->Distance(t.x2, t.y2, t.x1, t.y1) == t.d, "distance %d", t.d);
+  auto one = core::NewBoard(1, 1);  // TestBoard_EdgeCases
+  EXPECT(one->T.size() == 1 && one->InBounds(0, 0) && !one->InBounds(1, 0) && !one->InBounds(0, 1), "1x1");
+  auto big = core::NewBoard(1000, 1000);
+  EXPECT(big->T.size() == 1000000 && big->InBounds(999, 999) && !big->InBounds(1000, 1000), "1000x1000");
+  auto m = core::NewBoard(5, 5);  // TestBoard_ModifyTile
+  Tile *t = m->GetTile(2, 2);
+  REQUIRE(t != nullptr, "tile");
+  t->Owner = 1, t->Army = 50, t->Type = core::TileCity;
+  Tile *same = m->GetTile(2, 2);
+  EXPECT(same->Owner == 1 && same->Army == 50 && same->Type == core::TileCity, "modifications persist");
+}
+
+TEST(TestTile_Predicates) {  // board_test.go:183-246
+  EXPECT(mk(core::NeutralID, 0, core::TileNormal).IsNeutral() && !mk(0, 0, core::TileNormal).IsNeutral() && !mk(1, 0, core::TileNormal).IsNeutral(), "IsNeutral");
+  struct { int type; bool city, general, mountain; } types[] = {{core::TileNormal, false, false, false}, {core::TileCity, true, false, false},
+                                                                {core::TileGeneral, false, true, false}, {core::TileMountain, false, false, true}};
+  for (auto &t : types) {
+    Tile tile = mk(core::NeutralID, 0, t.type);
+    EXPECT(tile.IsCity() == t.city && tile.IsGeneral() == t.general && tile.IsMountain() == t.mountain, "type %d", t.type);
+  }
+  EXPECT(mk(core::NeutralID, 0, core::TileNormal).IsEmpty(), "empty neutral tile");
+  EXPECT(!mk(core::NeutralID, 5, core::TileNormal).IsEmpty(), "neutral with army");
+  EXPECT(!mk(0, 0, core::TileNormal).IsEmpty(), "owned empty tile");
+  EXPECT(!mk(core::NeutralID, 0, core::TileCity).IsEmpty() && !mk(core::NeutralID, 0, core::TileGeneral).IsEmpty() &&
+             !mk(core::NeutralID, 0, core::TileMountain).IsEmpty(), "neutral city / general / mountain");
 }
 
 // ---- core/errors (errors_test.go) ---------------------------------------------------------------------

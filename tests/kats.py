@@ -57,6 +57,23 @@ def kat_apply_move_table(lib):
         assert s["turn"][0] == 1, name
 
 
+# ---- core/movement_test.go:275-332 TestApplyMoveAction_InvalidMoves ---------------------------
+def kat_apply_move_invalid(lib):
+    """5x5, player 0 holds (0,0) with 10 armies, a mountain at (1,0): moving into the mountain, moving from a tile
+    the player does not own, and moving with a single army are errors, and an error leaves the board as it was."""
+    W = H = 5
+    cases = [("move to mountain", [(0, 0, 0, 10, NORMAL), (1, 0, -1, 0, MOUNTAIN)], (0, 0, 0, 1, 0, True), _abi.STEP_TARGET_IS_MOUNTAIN),
+             ("move from unowned tile", [(0, 0, 0, 10, NORMAL), (1, 0, -1, 0, MOUNTAIN)], (0, 3, 3, 3, 4, True), _abi.STEP_NOT_OWNED),
+             ("move with insufficient army", [(0, 0, 0, 1, NORMAL)], (0, 0, 0, 1, 0, True), _abi.STEP_INSUFFICIENT_ARMY)]
+    for name, tiles, action, code in cases:
+        s, _ = _step_one_move(lib, tiles, action, W=W, H=H)
+        assert s["step_error"][0] == code, name
+        for (x, y, owner, army, type_) in tiles:
+            i = y * W + x
+            assert (s["owner"][0, i], s["army"][0, i], s["type"][0, i]) == (owner, army, type_), name
+        assert s["changed"][0].sum() == 0, name
+
+
 # ---- core/movement_test.go:237-273 capture details: city 50 vs 40 --------------------------
 def kat_capture_city(lib):
     s, _ = _step_one_move(lib, [(0, 0, 0, 50, NORMAL), (1, 0, 1, 40, CITY)], (0, 0, 0, 1, 0, True))
@@ -425,6 +442,18 @@ def kat_army_clip(lib):
     assert out["obs"][0, 0, 1, 1, 2] == np.float32(999.0) / np.float32(1000.0)
     assert out["obs"][0, 1, 0, 1, 2] == np.float32(999.0) / np.float32(1000.0)
     assert out["obs"][0, 1, 1, 0, 0] == 1.0
+    # serializer_test.go:222-243 TestNormalizeArmyValue: 0 -> 0, 100 -> 0.1, 500 -> 0.5, 1000 -> 1, 2000 -> 1 (capped)
+    e = new_engine(lib, 5, 5, 2, fog_of_war=0)
+    s = _detailed_state(5, 5)
+    table = [(0, np.float32(0.0)), (100, np.float32(0.1)), (500, np.float32(0.5)), (1000, np.float32(1.0)), (2000, np.float32(1.0))]
+    for k, (army, _) in enumerate(table):
+        put(s, 5, k, 3, 0, army, NORMAL)
+    e.set_state(s)
+    out = e.alloc_outputs_host()
+    e.observe(e.outputs(**out))
+    for k, (army, want) in enumerate(table):
+        assert out["obs"][0, 0, 0, 3, k] == want, f"NormalizeArmyValue({army})"
+        assert out["obs"][0, 1, 1, 3, k] == want, f"the enemy's view of {army}"
 
 
 # ---- fog of war semantics (visibility_optimized.go) ----------------------------------------------

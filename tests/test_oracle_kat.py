@@ -65,6 +65,34 @@ def test_mapgen_city_golden(oracle_lib):
     assert fn(20, 20, 20, 50, 12345, t.ctypes.data, a.ctypes.data) == 0
     assert (t == CITY).sum() == 20                                             # :175
     assert (a[t == CITY] == 50).all()
+    # generator_test.go:178-194 NoCitiesIfRatioIsTooHigh: 100 / 101 = 0 cities
+    t, a = np.zeros(100, np.int32), np.zeros(100, np.int32)
+    assert fn(10, 10, 101, 40, 12345, t.ctypes.data, a.ctypes.data) == 0 and (t == CITY).sum() == 0
+    # :196-218 CitiesNotOnPreExistingMountains: ratio 5 asks for 20 cities; (1,1) and (5,5) stay mountains
+    t, a = np.zeros(100, np.int32), np.zeros(100, np.int32)
+    t[1 * 10 + 1] = t[5 * 10 + 5] = MOUNTAIN
+    assert fn(10, 10, 5, 40, 12345, t.ctypes.data, a.ctypes.data) == 0
+    assert t[11] == MOUNTAIN and t[55] == MOUNTAIN and (t == CITY).sum() == 20 and (a[t == MOUNTAIN] == 0).all()
+    # :220-244 MaxAttemptsForCitiesWhenNoSpace: a board full of mountains takes no city and the loop ends
+    t, a = np.full(25, MOUNTAIN, np.int32), np.zeros(25, np.int32)
+    assert fn(5, 5, 1, 40, 12345, t.ctypes.data, a.ctypes.data) == 0 and (t == MOUNTAIN).all()
+
+
+def test_default_map_config(oracle_lib):
+    """generator_test.go:18-34 TestDefaultMapConfig: ratio 20, city army 40, spacing 5 (grl_default_config carries
+    them); veins (w*h)/50, vein length 3 .. w/4 are what both generators derive — checked through a 20x15 map made with
+    the explicit values against the default path, which must agree tile for tile."""
+    from generalsreinforcementlearning_b200.engine import make_config
+    cfg = make_config(oracle_lib, num_envs=1, width=20, height=15, num_players=2)
+    assert (cfg.city_ratio, cfg.city_start_army, cfg.min_general_spacing) == (20, 40, 5)
+    gen = ctypes_fn(oracle_lib, "test_generate_map", C.c_int, [C.c_int] * 9 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p])
+    W, H = 20, 15
+    o, a, t = (np.zeros(W * H, np.int32) for _ in range(3))
+    assert gen(W, H, 2, 20, 40, 5, (W * H) // 50, 3, W // 4, 4242, o.ctypes.data, a.ctypes.data, t.ctypes.data) == 0
+    e = new_engine(oracle_lib, W, H, 2, 1)
+    e.reset_seeded([4242])
+    s = e.get_state()
+    assert np.array_equal(s["owner"][0], o) and np.array_equal(s["army"][0], a) and np.array_equal(s["type"][0], t)
 
 
 def test_mapgen_full_25x25_golden(oracle_lib):
@@ -204,6 +232,33 @@ def test_reward_city_general_army(oracle_lib):
     e3.set_state(curr)
     r = _reward(oracle_lib, e3, 0, prev["owner"][0], prev["army"][0])
     assert abs(r - (5 * 0.001 + (5 / 25) * 0.05)) < 0.01              # :97-118
+
+
+def test_reward_city_changes(oracle_lib):
+    """rewards_test.go:144-171 (TestCountCityChanges): city (1,1) neutral -> player 0 and city (3,3) player 0 -> player 1
+    count as one gained and one lost; through CalculateRewardWithConfig that is 0.1 - 0.1 with no territory or army
+    change, plus the advantage term of the new position ((50 - 50) / 100 = 0), in the reference's order of additions."""
+    f32 = np.float32
+    e = new_engine(oracle_lib, 5, 5, 2, fog_of_war=0)
+    prev, curr = _test_state(5, 5), _test_state(5, 5)
+    put(prev, 5, 1, 1, -1, 40, CITY)
+    put(curr, 5, 1, 1, 0, 40, CITY)
+    put(prev, 5, 3, 3, 0, 40, CITY)
+    put(curr, 5, 3, 3, 1, 40, CITY)
+    e.set_state(curr)
+    r = _reward(oracle_lib, e, 0, prev["owner"][0], prev["army"][0])
+    acc = f32(0)
+    for term in (f32(0) * f32(0.01), f32(0) * f32(0.001), f32(1) * f32(0.1), f32(1) * f32(-0.1), f32(0) * f32(0.5),
+                 f32(0) * f32(-0.5), f32(0) * f32(0.05)):
+        acc = f32(acc + f32(term))
+    assert f32(r) == acc
+    # the other side of the same transition: player 1 gained a city, a tile and 40 armies, and lost nothing
+    r1 = _reward(oracle_lib, e, 1, prev["owner"][0], prev["army"][0])
+    acc = f32(0)
+    for term in (f32(1) * f32(0.01), f32(40) * f32(0.001), f32(1) * f32(0.1), f32(0) * f32(-0.1), f32(0) * f32(0.5),
+                 f32(0) * f32(-0.5), f32(f32(0) / f32(100)) * f32(0.05)):
+        acc = f32(acc + f32(term))
+    assert f32(r1) == acc
 
 
 def test_reward_army_advantage(oracle_lib):
