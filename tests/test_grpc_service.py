@@ -247,6 +247,62 @@ def test_stream_game_updates(server):
     it.cancel()
 
 
+def test_reference_stream_game_kats(server):
+    """stream_test.go:44-176 (TestStreamGame): a stream opened from the lobby gets the full state at once, a game-started
+    event when the second player joins, and a full state or delta after the turn both players passed on;
+    :178-195 invalid credentials and :197-209 an unknown game are errors."""
+    import threading
+
+    gs, stub, _, ch, _ = server
+    cfg = game.GameConfig(width=10, height=10, max_players=2, fog_of_war=True)
+    gid = stub.CreateGame(game.CreateGameRequest(config=cfg)).game_id
+    j1 = stub.JoinGame(game.JoinGameRequest(game_id=gid, player_name="Player1"))
+    it = stub.StreamGame(game.StreamGameRequest(game_id=gid, player_id=j1.player_id, player_token=j1.player_token))
+    updates, done = [], threading.Event()
+
+    def pump():
+        try:
+            for u in it:
+                updates.append(u)
+        except grpc.RpcError:
+            pass
+        done.set()
+
+    th = threading.Thread(target=pump, daemon=True)
+    th.start()
+
+    def wait_for(pred, what):
+        import time as _t
+        t0 = _t.time()
+        while _t.time() - t0 < 5.0:
+            if pred():
+                return
+            _t.sleep(0.01)
+        raise AssertionError(what)
+
+    wait_for(lambda: len(updates) >= 1, "initial state")
+    assert updates[0].WhichOneof("update") == "full_state"
+    j2 = stub.JoinGame(game.JoinGameRequest(game_id=gid, player_name="Player2"))
+    wait_for(lambda: any(u.WhichOneof("update") == "event" and u.event.WhichOneof("event") == "game_started" for u in updates[1:]),
+             "Expected to find game started event")
+    n_before = len(updates)
+    for j in (j1, j2):   # no action this turn, from both players
+        assert stub.SubmitAction(game.SubmitActionRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token)).success
+    wait_for(lambda: any(u.WhichOneof("update") in ("full_state", "delta") for u in updates[n_before:]),
+             "Expected to receive either full state or delta update after turn processing")
+    assert len(updates) > 2
+    it.cancel()
+    assert done.wait(1.0), "Stream did not finish within timeout"
+    # invalid credentials / unknown game
+    lobby = stub.CreateGame(game.CreateGameRequest()).game_id
+    with pytest.raises(grpc.RpcError) as e:
+        next(iter(stub.StreamGame(game.StreamGameRequest(game_id=lobby, player_id=999, player_token="invalid-token"))))
+    assert "invalid player credentials" in e.value.details()
+    with pytest.raises(grpc.RpcError) as e:
+        next(iter(stub.StreamGame(game.StreamGameRequest(game_id="non-existent-game", player_id=0, player_token="token"))))
+    assert "not found" in e.value.details()
+
+
 def test_validate_move_precedence():
     W = H = 3
     owner = [0, -1, -1, -1, -1, -1, -1, -1, 1]
@@ -473,6 +529,16 @@ def test_more_games_than_env_slots_through_one_server(oracle_lib):
         ch.close()
         srv.stop(0)
         gs.close()
+
+
+def test_max_games_zero_means_unlimited(server):
+    """max_games_test.go:48-68 (TestMaxGamesZeroMeansUnlimited): a server without a limit creates twenty lobby games."""
+    gs, stub, _, _, _ = server
+    assert gs.max_games == 0
+    before = len(gs.games)
+    cfg = game.GameConfig(width=10, height=10, max_players=2)
+    ids = [stub.CreateGame(game.CreateGameRequest(config=cfg)).game_id for _ in range(20)]
+    assert all(ids) and len(set(ids)) == 20 and len(gs.games) == before + 20
 
 
 def test_reference_cleanup_kats(server):
