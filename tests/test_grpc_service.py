@@ -491,6 +491,137 @@ def _play_duel(gs, stub):
     return gid, js
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/python/generals_gym"), reason="the reference's client is not on this box")
+def test_reference_gym_env_plays_against_this_server(server):
+    """The reference's UNMODIFIED GeneralsEnv (python/generals_gym/generals_env.py — its real gRPC client and its own
+    generated stubs) plays whole episodes against this server, as python/test_gym_minimal.py and test_gym_env.py do
+    against the Go server.  After reset() and after every step() the observation and the action mask the client derived
+    from the GameState messages must equal, bit for bit, the engine's own gym read-outs (grl_gym_observe_envs) of the
+    game's env slot — the path GeneralsVecEnv hands out.  (Plane 7 is the client's own step counter over max_turns,
+    generals_env.py:334-336, so it is compared with that.)  The opponent is an `opponent_agent` of the test that always
+    submits — a random legal move or an empty request — so every turn runs as soon as both players have submitted, not
+    on the turn timer the reference's 50 ms wait races with."""
+    import random
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import make_gym_fixtures as mk
+
+    generals_env, game_pb2, common_pb2 = mk.load_reference()
+    gs, stub, _, _, port = server
+    rnd = random.Random(11)
+    W = H = 6
+
+    class Opponent:
+        env = None
+
+        def select_action(self, _agent_view):
+            env = self.env
+            st = env.stub.GetGameState(game_pb2.GetGameStateRequest(game_id=env.game_id, player_id=env.opponent_id,
+                                                                    player_token=env.opponent_token)).state
+            moves = []
+            for t, tile in enumerate(st.board.tiles):
+                if tile.owner_id != env.opponent_id or tile.army_count <= 1:
+                    continue
+                x, y = t % W, t // W
+                for dx, dy in ((0, 1), (1, 0), (0, -1), (-1, 0)):
+                    nx, ny = x + dx, y + dy
+                    if 0 <= nx < W and 0 <= ny < H and st.board.tiles[ny * W + nx].type != common_pb2.TILE_TYPE_MOUNTAIN:
+                        a = game_pb2.Action(type=common_pb2.ACTION_TYPE_MOVE, half=False, turn_number=st.turn)
+                        getattr(a, "from").CopyFrom(common_pb2.Coordinate(x=x, y=y))
+                        a.to.CopyFrom(common_pb2.Coordinate(x=nx, y=ny))
+                        moves.append(a)
+            # submitted here, with the opponent's player id: the client's own submission for an opponent_agent leaves
+            # player_id at 0 (generals_env.py:247-251), which the server — the Go one too, action_validator.go:80-92 —
+            # refuses as invalid credentials
+            req = game_pb2.SubmitActionRequest(game_id=env.game_id, player_id=env.opponent_id, player_token=env.opponent_token)
+            if moves:
+                req.action.CopyFrom(rnd.choice(moves))   # else: no action this turn
+            env.stub.SubmitAction(req)   # (a turn in which a move fails in the engine answers "failed to process turn")
+            return None
+
+    class TurnStampingStub:
+        """The client never fills Action.turn_number (generals_env.py:430-441), so from turn 1 on every move it submits is
+        refused in-band as INVALID_TURN — by the Go server too (action_validator.go:102-108) — and it does not look at the
+        response.  This shim stamps the turn of the last state the client fetched, which is all a working client would
+        add; everything else on the wire is the reference client's own."""
+
+        def __init__(self, stub):
+            self._stub, self.turn, self.refused, self.failed_turn = stub, 0, 0, False
+
+        def __getattr__(self, name):
+            return getattr(self._stub, name)
+
+        def GetGameState(self, req, **kw):
+            r = self._stub.GetGameState(req, **kw)
+            self.turn = r.state.turn
+            return r
+
+        def SubmitAction(self, req, **kw):
+            if req.HasField("action"):
+                req.action.turn_number = self.turn
+            r = self._stub.SubmitAction(req, **kw)
+            self.refused += r.error_code in (common.ERROR_CODE_INVALID_TURN, common.ERROR_CODE_INVALID_PLAYER)
+            self.failed_turn |= "failed to process turn" in r.error_message
+            return r
+
+    opp = Opponent()
+    env = generals_env.GeneralsEnv(server_address=f"127.0.0.1:{port}", board_width=W, board_height=H, max_players=2,
+                                   fog_of_war=True, max_turns=40, turn_time_ms=600000, opponent_agent=opp)
+    opp.env = env
+    env.stub = TurnStampingStub(env.stub)
+    rng = np.random.default_rng(5)
+    steps = finished = 0
+    try:
+        for episode in range(3):
+            obs, info = env.reset()
+            g = gs.games[info["game_id"]]
+
+            def check(obs, mask, what):
+                pool = g.pool
+                S, P, N = pool.S, pool.P, pool.N
+                o = np.zeros((S, P, 9, H, W), np.float32)
+                m = np.zeros((S, P, N * 5), np.uint8)
+                st = np.zeros((S, P, 4), np.int32)
+                with pool.lock:
+                    pool.engine.gym_observe_envs(env.max_turns, [g.slot], o, m, st)
+                    turn = int(pool.engine.get_state(g.slot, 1)["turn"][0])
+                o, m = o[g.slot, env.player_id], m[g.slot, env.player_id].astype(bool)
+                assert obs.dtype == np.float32 and obs.shape == (9, H, W)
+                for plane in (0, 1, 2, 3, 4, 5, 6, 8):
+                    assert np.array_equal(obs[plane].view(np.uint32), o[plane].view(np.uint32)), f"plane {plane}, {what}"
+                assert (obs[7] == np.float32(min(env.turn_count / env.max_turns, 1.0))).all(), f"turn plane, {what}"
+                assert np.array_equal(np.asarray(mask, bool), m), f"mask, {what}"
+                return turn
+
+            assert check(obs, info["valid_actions_mask"], "after reset") == 0
+            for t in range(40):
+                valid = np.flatnonzero(info["valid_actions_mask"])
+                if len(valid) == 0:
+                    break
+                obs, reward, terminated, truncated, info = env.step(int(valid[rng.integers(len(valid))]))
+                steps += 1
+                assert np.isfinite(reward)
+                if g.slot < 0:        # the game ended and the server released the env slot
+                    assert terminated
+                    finished += 1
+                    break
+                turn = check(obs, info["valid_actions_mask"], f"episode {episode} step {t}")
+                assert info["turn"] == env.turn_count == t + 1 and turn == t + 1, "every step ran one turn"
+                if env.stub.failed_turn:
+                    # a move that was legal when submitted failed inside the turn (its source tile fell to the other
+                    # player's move first): Engine.Step errors, the server answers "failed to process turn" and — as in
+                    # the reference, game_manager.go:602-608 — keeps its own turn counter where it was, one behind the
+                    # engine's, so every later action stamped with the state's turn is refused.  The episode ends here.
+                    env.stub.failed_turn = False
+                    break
+                if terminated or truncated:
+                    break
+    finally:
+        env.close()
+    assert steps >= 60 and env.stub.refused == 0
+
+
 def test_more_games_than_env_slots_through_one_server(oracle_lib):
     """A gym client creates a new game on every reset() (generals_env.py:167-177): a server must outlive its pool size."""
     srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=3, seed=5, max_games=8, finished_game_ttl=600.0)
