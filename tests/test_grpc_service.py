@@ -622,6 +622,52 @@ def test_reference_gym_env_plays_against_this_server(server):
     assert steps >= 60 and env.stub.refused == 0
 
 
+@pytest.mark.skipif(not os.path.isfile("/root/reference/python/test_grpc_client.py"), reason="the reference's scripts are not on this box")
+def test_reference_client_scripts_run_unmodified(oracle_lib, tmp_path):
+    """python/test_grpc_client.py and python/test_gym_minimal.py — the reference's own smoke scripts, run as they are (they
+    dial localhost:50051) against this server: connection, lifecycle, a move from the general, and a GeneralsEnv reset and
+    steps.  The only thing added is a `gymnasium` package with the four names generals_env.py imports (absent from the
+    image)."""
+    import subprocess
+    import sys
+
+    try:
+        srv, gs, port = serve("localhost:50051", lib=oracle_lib, slots_per_pool=8, seed=7)
+    except Exception as exc:   # the port is taken on this machine
+        pytest.skip(f"cannot listen on localhost:50051: {exc}")
+    if port != 50051:
+        srv.stop(0)
+        gs.close()
+        pytest.skip("cannot listen on localhost:50051")
+    stub_pkg = tmp_path / "gymnasium"
+    stub_pkg.mkdir()
+    (stub_pkg / "__init__.py").write_text(
+        "from . import spaces\n"
+        "class Env:\n    def reset(self, seed=None, options=None):\n        return None\n"
+        "def register(**kw):\n    pass\n")
+    (stub_pkg / "spaces.py").write_text(
+        "class Box:\n    def __init__(self, low, high, shape, dtype):\n"
+        "        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype\n"
+        "class Discrete:\n    def __init__(self, n):\n        self.n = int(n)\n")
+    envv = dict(os.environ, PYTHONPATH=str(tmp_path), PYTHONDONTWRITEBYTECODE="1")
+    try:
+        for script, needles in (("test_grpc_client.py", ["Server is responsive. Created test game: game-1", "Player 1 joined: ID=0",
+                                                         "Player 2 joined: ID=1", "Status: GAME_STATUS_IN_PROGRESS", "Number of tiles: 100",
+                                                         "All tests completed successfully!"]),
+                                ("test_gym_minimal.py", ["Reset successful, game_id: game-", "Observation shape: (9, 5, 5)", "Step 1: Taking action",
+                                                         "Test complete!"])):
+            proc = subprocess.run([sys.executable, script], cwd="/root/reference/python", env=envv, stdout=subprocess.PIPE,
+                                  stderr=subprocess.STDOUT, text=True, timeout=120)
+            assert proc.returncode == 0, proc.stdout[-2000:]
+            for needle in needles:
+                assert needle in proc.stdout, f"{script}: {needle!r} missing from\n{proc.stdout[-2000:]}"
+            assert "✗" not in proc.stdout or "Move failed" in proc.stdout, proc.stdout[-2000:]
+            assert "Error during step" not in proc.stdout, proc.stdout[-2000:]
+    finally:
+        srv.stop(0)
+        gs.close()
+
+
 def test_more_games_than_env_slots_through_one_server(oracle_lib):
     """A gym client creates a new game on every reset() (generals_env.py:167-177): a server must outlive its pool size."""
     srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=3, seed=5, max_games=8, finished_game_ttl=600.0)
