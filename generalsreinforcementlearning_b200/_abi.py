@@ -124,6 +124,12 @@ class GymAutoresetIO(C.Structure):
                 ("calls", C.c_void_p), ("out", GymOutputs), ("final_obs", C.c_void_p), ("n_reset", C.c_void_p)]
 
 
+class ReplayRowsIO(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("final_obs", C.c_void_p), ("done", C.c_void_p), ("next_states", C.c_void_p),
+                ("states", C.c_void_p), ("capacity", C.c_int64), ("next_row0", C.c_int64), ("state_row0", C.c_int64),
+                ("views", C.c_int32), ("view", C.c_int32), ("obs_floats", C.c_int32), ("reserved", C.c_int32)]
+
+
 STATE_FIELDS = (
     ("owner", np.int32, "N"),
     ("army", np.int32, "N"),
@@ -170,6 +176,7 @@ ABI_FUNCTIONS = {
     "gym_observe_envs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(GymOutputs)]),
     "gym_autoreset": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(GymAutoresetIO)]),
     "gym_sample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "replay_push_rows": (C.c_int, [C.c_void_p, C.POINTER(ReplayRowsIO)]),
     "gym_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "gym_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(GymStepIO)]),
     "sample_actions": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),

@@ -984,6 +984,22 @@ int grl_gym_autoreset(grl_env *env, int32_t max_turns, int64_t base_seed, const 
   return GRL_OK;
 }
 
+int grl_replay_push_rows(grl_env *env, const grl_replay_rows_io *io) {
+  if (!env || !io || !io->obs) return fail(GRL_ERR_INVALID_ARG, "null argument");
+  if (io->capacity < 1 || io->obs_floats < 1 || io->views < 1 || io->view < 0 || io->view >= io->views || io->next_row0 < 0 ||
+      io->state_row0 < 0)
+    return fail(GRL_ERR_INVALID_ARG, "bad ring geometry");
+  CUDA_TRY(cudaSetDevice(env->cfg.device));
+  const void *ptrs[] = {io->obs, io->final_obs, io->done, io->next_states, io->states};
+  for (const void *p : ptrs)
+    if (p && !is_device_ptr(p)) return fail(GRL_ERR_UNSUPPORTED, "grl_replay_push_rows takes device pointers");
+  if (!io->next_states && !io->states) return GRL_OK;
+  CUDA_TRY(grl_launch_replay_rows(io->obs, io->final_obs, io->done, io->next_states, io->states, io->capacity, io->next_row0,
+                                  io->state_row0, io->views, io->view, io->obs_floats, env->cfg.num_envs, env->stream));
+  env->launches++, note_other_work(env);
+  return GRL_OK;
+}
+
 int grl_gym_sample(grl_env *env, uint64_t seed, const uint8_t *mask, int32_t player, int64_t *action) {
   if (!env || !mask || !action) return fail(GRL_ERR_INVALID_ARG, "null argument");
   if (player < 0 || player >= env->cfg.num_players) return fail(GRL_ERR_INVALID_ARG, "player %d out of range", player);

@@ -228,6 +228,42 @@ __global__ void grl_gym_compact_kernel(const GrlKParams prm, const uint8_t *__re
   }
 }
 
+// grl_replay_push_rows: one thread block per env copies the env's observation row (view `view` of [B][views][F]) into the
+// next_states ring row of the transition that just ended (final_obs[b] where done[b]) and into the states ring row of the
+// env's next transition — one read of the plane, two coalesced write streams.  Rows are F floats at 4-byte alignment
+// (F = 9 * 225 is odd), so accesses are 32-bit; a warp instruction still covers 128 contiguous bytes.
+__global__ void __launch_bounds__(256) grl_replay_rows_kernel(const float *__restrict__ obs, const float *__restrict__ final_obs,
+                                                              const uint8_t *__restrict__ done, float *__restrict__ next_states,
+                                                              float *__restrict__ states, long long capacity, long long next_row0,
+                                                              long long state_row0, int views, int view, int F, int B) {
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const float *row = obs + ((size_t)b * views + view) * (size_t)F;
+    const bool fin = next_states && done && final_obs && done[b] != 0;
+    const float *nsrc = fin ? final_obs + (size_t)b * F : row;
+    float *nd = next_states ? next_states + (size_t)((next_row0 + b) % capacity) * F : nullptr;
+    float *sd = states ? states + (size_t)((state_row0 + b) % capacity) * F : nullptr;
+    for (int k0 = threadIdx.x; k0 < F; k0 += 4 * 256) {  // four independent loads in flight per thread
+      float v[4], w[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int k = k0 + 256 * u;
+        if (k < F) {
+          v[u] = __ldcs(row + k);
+          w[u] = fin ? __ldcs(nsrc + k) : v[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int k = k0 + 256 * u;
+        if (k < F) {
+          if (nd) __stcs(nd + k, w[u]);
+          if (sd) __stcs(sd + k, v[u]);
+        }
+      }
+    }
+  }
+}
+
 // A uniformly random valid gym action per env: the k-th set byte of the env's N*5 mask bytes, one warp per env
 // (the draw is policy_draw(seed, global env, 0, player) mod the number of set bytes).  The row is read as aligned
 // 128-bit vectors (512 contiguous bytes per warp instruction, whatever the row's own alignment), each lane turning its
@@ -546,6 +582,15 @@ cudaError_t grl_launch_gym_reseed(const GrlKParams &prm, const uint32_t *src_sta
     default: GRL_RESEED(8) break;
   }
 #undef GRL_RESEED
+  return cudaGetLastError();
+}
+
+cudaError_t grl_launch_replay_rows(const float *obs, const float *final_obs, const uint8_t *done, float *next_states, float *states,
+                                   long long capacity, long long next_row0, long long state_row0, int views, int view, int F, int B,
+                                   cudaStream_t stream) {
+  const int grid = B < 148 * 64 ? B : 148 * 64;
+  grl_replay_rows_kernel<<<grid, 256, 0, stream>>>(obs, final_obs, done, next_states, states, capacity, next_row0, state_row0, views,
+                                                   view, F, B);
   return cudaGetLastError();
 }
 

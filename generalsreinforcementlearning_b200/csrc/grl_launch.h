@@ -30,6 +30,9 @@ cudaError_t grl_launch_gym(const GrlKParams &prm, int max_turns, const float *lo
 cudaError_t grl_launch_gym_step(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream);
 cudaError_t grl_launch_gym_encode(const GrlKParams &prm, const long long *action_idx, int player, int slot, const uint8_t *mask,
                                   int skip_invalid, void *actions, uint8_t *valid, cudaStream_t stream);
+cudaError_t grl_launch_replay_rows(const float *obs, const float *final_obs, const uint8_t *done, float *next_states, float *states,
+                                   long long capacity, long long next_row0, long long state_row0, int views, int view, int F, int B,
+                                   cudaStream_t stream);
 cudaError_t grl_launch_gym_sample(const GrlKParams &prm, unsigned long long seed, const uint8_t *mask, int player, long long *action,
                                   cudaStream_t stream);
 cudaError_t grl_launch_mask_replicate(const uint32_t *in, uint32_t *out, size_t rows, int words, int rep,

@@ -209,6 +209,17 @@ class BatchedEngine:
         self.lib.check(self.lib.gym_sample(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(mask), int(player), _ptr(action)),
                        "gym_sample")
 
+    def replay_push_rows(self, obs, views: int, view: int, obs_floats: int, capacity: int, next_states=None, next_row0: int = 0,
+                         states=None, state_row0: int = 0, done=None, final_obs=None) -> None:
+        """One vector step's observation rows into a replay ring (grl_replay_push_rows): ``next_states`` rows from
+        ``obs`` (``final_obs`` where ``done``), ``states`` rows of the next transition, in one pass."""
+        io = _abi.ReplayRowsIO()
+        io.obs, io.final_obs, io.done = _ptr(obs), _ptr(final_obs), _ptr(done)
+        io.next_states, io.states = _ptr(next_states), _ptr(states)
+        io.capacity, io.next_row0, io.state_row0 = int(capacity), int(next_row0), int(state_row0)
+        io.views, io.view, io.obs_floats = int(views), int(view), int(obs_floats)
+        self.lib.check(self.lib.replay_push_rows(self._h, C.byref(io)), "replay_push_rows")
+
     def gym_encode(self, action_idx, player: int, slot: int, mask, skip_invalid: bool, actions, valid) -> None:
         """Discrete(N*5) indices -> grl_action slots, rejecting indices the gym mask forbids."""
         self.lib.check(self.lib.gym_encode(self._h, _ptr(action_idx), int(player), int(slot), _ptr(mask),

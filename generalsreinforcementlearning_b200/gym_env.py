@@ -204,6 +204,26 @@ class GeneralsVecEnv:
                                   episode=self._episode_dev, turns=self._turns, calls=self._calls, obs=self._obs,
                                   mask=self._mask, stats=self._stats, final_obs=self._final_obs)
 
+    def reset_envs(self, env_mask) -> None:
+        """Start a new episode in the envs flagged in ``env_mask`` (bool [B]) — what a caller that caps episode length
+        itself does between steps (``ParallelEnvPool.max_steps_per_episode``).  Same re-seeding as the auto-reset: the
+        env's episode counter advances and its observation / mask rows are replaced; no host read unless the host
+        drives the re-seeding (``auto_reset="host_reset"``)."""
+        t = self.torch
+        env_mask = t.as_tensor(env_mask, device=self.device).to(t.bool)
+        if self.auto_reset != "host_reset":
+            self._autoreset(env_mask, t.zeros_like(env_mask))
+            return
+        ids = env_mask.nonzero(as_tuple=True)[0]
+        if ids.numel() == 0:
+            return
+        ids_np = ids.cpu().numpy()
+        self._episode[ids_np] += 1
+        self.engine.reset_seeded(self._seeds(ids_np), ids_np.astype(np.int32))
+        self._turns[ids] = 0
+        self._calls[ids] = 0
+        self._refresh(ids_np)
+
     def sample_actions(self, generator=None, player: int = 0):
         """A uniformly random VALID action per env (envs without one get action 0, which is rejected): the random
         agent of the reference (python/generals_agent/random_agent.py) for every env in one kernel launch.  With a

@@ -326,6 +326,24 @@ typedef struct grl_gym_autoreset_io {
 } grl_gym_autoreset_io;
 int grl_gym_autoreset(grl_env *env, int32_t max_turns, int64_t base_seed, const grl_gym_autoreset_io *io);
 
+/* The observation rows of one vector step for a replay ring — what python/generals_gym/vector_env.py:170-176 pushes env
+ * by env through replay_buffer.py:30-40, for every env at once.  `obs` is the gym observation plane
+ * [B][views][obs_floats] AFTER grl_gym_step (and grl_gym_autoreset); view `view` of env b is written to
+ *   next_states[(next_row0 + b) % capacity]   — final_obs[b] instead where done[b] != 0: the view the episode ended with,
+ *   states[(state_row0 + b) % capacity]       — the state of the env's NEXT transition (a re-seeded env's first view),
+ * in ONE pass over the plane (either destination may be NULL).  Rows of a ring are [obs_floats] floats, contiguous.
+ * libgrlcuda.so takes device pointers (one launch on the env's stream, no host read); the oracle takes host pointers. */
+typedef struct grl_replay_rows_io {
+  const float *obs;            /* [B][views][obs_floats]                                   */
+  const float *final_obs;      /* [B][obs_floats] or NULL                                   */
+  const uint8_t *done;         /* [B] or NULL: no row comes from final_obs                  */
+  float *next_states;          /* [capacity][obs_floats] or NULL                            */
+  float *states;               /* [capacity][obs_floats] or NULL                            */
+  int64_t capacity, next_row0, state_row0;
+  int32_t views, view, obs_floats, reserved;
+} grl_replay_rows_io;
+int grl_replay_push_rows(grl_env *env, const grl_replay_rows_io *io);
+
 /* Draw the synthetic policy's actions for the current state into `actions`
  * ([B][max_actions], slot p = player p's move, empty when it has none). */
 int grl_sample_actions(grl_env *env, uint64_t policy_seed, grl_action *actions);

@@ -1581,6 +1581,23 @@ int grlo_gym_encode(grlo_env *e, const int64_t *action_idx, int32_t player, int3
   return GRL_OK;
 }
 
+/* grl_replay_push_rows (include/grlcuda.h): what vector_env.py:170-176 pushes env by env, as plain loops */
+int grlo_replay_push_rows(grlo_env *e, const grl_replay_rows_io *io) {
+  if (!e || !io || !io->obs || io->capacity < 1 || io->obs_floats < 1 || io->views < 1 || io->view < 0 || io->view >= io->views)
+    return GRL_ERR_INVALID_ARG;
+  const int B = e->cfg.num_envs;
+  const size_t F = (size_t)io->obs_floats;
+  for (int b = 0; b < B; b++) {
+    const float *row = io->obs + ((size_t)b * (size_t)io->views + (size_t)io->view) * F;
+    if (io->next_states) {
+      const float *src = (io->done && io->final_obs && io->done[b]) ? io->final_obs + (size_t)b * F : row;
+      memcpy(io->next_states + (size_t)((io->next_row0 + b) % io->capacity) * F, src, F * sizeof(float));
+    }
+    if (io->states) memcpy(io->states + (size_t)((io->state_row0 + b) % io->capacity) * F, row, F * sizeof(float));
+  }
+  return GRL_OK;
+}
+
 /* a uniformly random valid gym action per env: the k-th set mask entry in index order (grlcuda.h) */
 int grlo_gym_sample(grlo_env *e, uint64_t seed, const uint8_t *mask, int32_t player, int64_t *action) {
   if (!e || !mask || !action) return GRL_ERR_INVALID_ARG;
