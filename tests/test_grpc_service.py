@@ -623,10 +623,10 @@ def test_reference_gym_env_plays_against_this_server(server):
 
 
 @pytest.mark.skipif(not os.path.isfile("/root/reference/python/test_grpc_client.py"), reason="the reference's scripts are not on this box")
-def test_reference_client_scripts_run_unmodified(oracle_lib, tmp_path):
-    """python/test_grpc_client.py and python/test_gym_minimal.py — the reference's own smoke scripts, run as they are (they
-    dial localhost:50051) against this server: connection, lifecycle, a move from the general, and a GeneralsEnv reset and
-    steps.  The only thing added is a `gymnasium` package with the four names generals_env.py imports (absent from the
+def test_reference_client_scripts_run_unmodified(oracle_lib, tmp_path):  # noqa: C901
+    """python/test_grpc_client.py, python/test_gym_minimal.py and python/test_parallel_env.py — the reference's own smoke
+    scripts, run as they are (they dial localhost:50051) against this server: connection, lifecycle, a move from the
+    general, a GeneralsEnv reset and steps, and the reference's ParallelEnvPool collecting four episodes.  The only thing added is a `gymnasium` package with the four names generals_env.py imports (absent from the
     image)."""
     import subprocess
     import sys
@@ -655,7 +655,11 @@ def test_reference_client_scripts_run_unmodified(oracle_lib, tmp_path):
                                                          "Player 2 joined: ID=1", "Status: GAME_STATUS_IN_PROGRESS", "Number of tiles: 100",
                                                          "All tests completed successfully!"]),
                                 ("test_gym_minimal.py", ["Reset successful, game_id: game-", "Observation shape: (9, 5, 5)", "Step 1: Taking action",
-                                                         "Test complete!"])):
+                                                         "Test complete!"]),
+                                # the reference's ParallelEnvPool (two worker threads, two gRPC envs) collecting into its
+                                # ReplayBuffer from this server: about 13 s of the client's own waits
+                                ("test_parallel_env.py", ["Game server is running", "4 episodes", "All workers stopped cleanly",
+                                                          "Sampled 32 transitions with valid shapes/types", "All tests passed"])):
             proc = subprocess.run([sys.executable, script], cwd="/root/reference/python", env=envv, stdout=subprocess.PIPE,
                                   stderr=subprocess.STDOUT, text=True, timeout=120)
             assert proc.returncode == 0, proc.stdout[-2000:]
