@@ -672,6 +672,52 @@ def test_reference_client_scripts_run_unmodified(oracle_lib, tmp_path):  # noqa:
         gs.close()
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/python/generals_agent"), reason="the reference's agent SDK is not on this box")
+def test_reference_agent_sdk_plays_a_match_against_this_server(server):
+    """BASELINE config 0's client side: two of the reference's RandomAgents (python/generals_agent: AgentRunner,
+    GameClient, GameSession, ExponentialBackoffPolling — unmodified, in their own threads) play a whole 5x5 match against
+    this server, as scripts/run_random_match.py does against the Go server (that script itself builds GameConfig with a
+    keyword the SDK does not have and cannot start).  Every move the agents submit carries the turn number of the state
+    they polled, so — unlike the gym client's — their moves are accepted turn after turn, until a general falls."""
+    import sys
+    import threading
+
+    sys.dont_write_bytecode = True
+    if "/root/reference/python" not in sys.path:
+        sys.path.insert(0, "/root/reference/python")
+    from generals_agent import AgentRunner, ExponentialBackoffPolling, GameClient, GameConfig, GameConnection, RandomAgent
+
+    gs, _, _, _, port = server
+    addr = f"127.0.0.1:{port}"
+    conn = GameConnection(addr)
+    gid = GameClient(conn).create_game(GameConfig(width=5, height=5))
+    res = {}
+
+    def play(name):
+        agent = RandomAgent(name=name)
+        runner = AgentRunner(agent, server_address=addr, polling_strategy=ExponentialBackoffPolling(base_interval=0.01), enable_logging=False)
+        try:
+            runner.join_game(gid)
+            runner.run(wait_for_players=2, timeout=60)
+            res[name] = agent.move_count
+        except Exception as exc:  # noqa: BLE001
+            res[name] = repr(exc)
+        finally:
+            runner.disconnect()
+
+    threads = [threading.Thread(target=play, args=(n,), daemon=True) for n in ("RandomAgent1", "RandomAgent2")]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(90)
+    conn.disconnect()
+    assert all(isinstance(v, int) and v >= 10 for v in res.values()) and len(res) == 2, res
+    g = gs.games[gid]
+    assert g.current_turn >= 10
+    if g.phase == common.GAME_PHASE_ENDED:   # random play on 5x5 ends within the minute almost always
+        assert g.slot == -1 and sorted(int(a) for a in g.final[0]["alive"][0]) == [0, 1], "one general fell"
+
+
 def test_more_games_than_env_slots_through_one_server(oracle_lib):
     """A gym client creates a new game on every reset() (generals_env.py:167-177): a server must outlive its pool size."""
     srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=3, seed=5, max_games=8, finished_game_ttl=600.0)
