@@ -675,7 +675,7 @@ def test_reference_client_scripts_run_unmodified(oracle_lib, tmp_path):  # noqa:
 @pytest.mark.skipif(not os.path.isdir("/root/reference/python/generals_agent"), reason="the reference's agent SDK is not on this box")
 def test_reference_agent_sdk_plays_a_match_against_this_server(server):
     """BASELINE config 0's client side: two of the reference's RandomAgents (python/generals_agent: AgentRunner,
-    GameClient, GameSession, ExponentialBackoffPolling — unmodified, in their own threads) play a whole 5x5 match against
+    GameClient, GameSession, ExponentialBackoffPolling — unmodified, in their own threads) play sixty turns of a 5x5 match (or all of it, when a general falls first) against
     this server, as scripts/run_random_match.py does against the Go server (that script itself builds GameConfig with a
     keyword the SDK does not have and cannot start).  Every move the agents submit carries the turn number of the state
     they polled, so — unlike the gym client's — their moves are accepted turn after turn, until a general falls."""
@@ -691,14 +691,15 @@ def test_reference_agent_sdk_plays_a_match_against_this_server(server):
     addr = f"127.0.0.1:{port}"
     conn = GameConnection(addr)
     gid = GameClient(conn).create_game(GameConfig(width=5, height=5))
-    res = {}
+    res, runners = {}, {}
 
     def play(name):
         agent = RandomAgent(name=name)
-        runner = AgentRunner(agent, server_address=addr, polling_strategy=ExponentialBackoffPolling(base_interval=0.01), enable_logging=False)
+        runner = runners[name] = AgentRunner(agent, server_address=addr, polling_strategy=ExponentialBackoffPolling(base_interval=0.01),
+                                             enable_logging=False)
         try:
             runner.join_game(gid)
-            runner.run(wait_for_players=2, timeout=60)
+            runner.run(wait_for_players=2, timeout=30)
             res[name] = agent.move_count
         except Exception as exc:  # noqa: BLE001
             res[name] = repr(exc)
@@ -708,13 +709,19 @@ def test_reference_agent_sdk_plays_a_match_against_this_server(server):
     threads = [threading.Thread(target=play, args=(n,), daemon=True) for n in ("RandomAgent1", "RandomAgent2")]
     for th in threads:
         th.start()
+    import time as _t
+    t0 = _t.time()
+    g = gs.games[gid]
+    while _t.time() - t0 < 12 and g.phase != common.GAME_PHASE_ENDED and g.current_turn < 60:
+        _t.sleep(0.05)
+    for r in list(runners.values()):   # sixty turns are enough: the match itself may take minutes of random play
+        r.stop()
     for th in threads:
-        th.join(90)
+        th.join(20)
     conn.disconnect()
     assert all(isinstance(v, int) and v >= 10 for v in res.values()) and len(res) == 2, res
-    g = gs.games[gid]
-    assert g.current_turn >= 10
-    if g.phase == common.GAME_PHASE_ENDED:   # random play on 5x5 ends within the minute almost always
+    assert g.current_turn >= 20
+    if g.phase == common.GAME_PHASE_ENDED:
         assert g.slot == -1 and sorted(int(a) for a in g.final[0]["alive"][0]) == [0, 1], "one general fell"
 
 
