@@ -91,7 +91,7 @@ def recorded_traffic():
 
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        return t if t.get("lib_source_hash") == grl_build.source_hash() else None
+        return t if t.get("turn_source_hash") == grl_build.turn_source_hash() else None
     except Exception:
         return None
 

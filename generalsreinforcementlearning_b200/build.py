@@ -48,6 +48,21 @@ def source_hash() -> str:
     return h.hexdigest()[:16]
 
 
+TURN_UNIT = ["grl_turn_20.cu", "grl_launch.h", "grl_turn.cuh", "grl_device.cuh", "grl_gym.cuh", "grl_obs.cuh", "grl_layout.h",
+             "../../include/grlcuda.h"]
+
+
+def turn_source_hash() -> str:
+    """sha256 over the translation unit of the headline turn kernel (grl_turn_20.cu and every header it includes):
+    profiles/traffic.json is keyed by it, so a change elsewhere in the library (ABI glue, off-path kernels) does not
+    void the capture while any change the kernel could see does."""
+    h = hashlib.sha256()
+    for f in sorted(TURN_UNIT):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
 def _run(cmd, verbose):
     proc = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:

@@ -989,6 +989,8 @@ int grl_replay_push_rows(grl_env *env, const grl_replay_rows_io *io) {
   if (io->capacity < 1 || io->obs_floats < 1 || io->views < 1 || io->view < 0 || io->view >= io->views || io->next_row0 < 0 ||
       io->state_row0 < 0)
     return fail(GRL_ERR_INVALID_ARG, "bad ring geometry");
+  if (io->capacity < env->cfg.num_envs)  // two envs of one step would write the same ring row
+    return fail(GRL_ERR_INVALID_ARG, "replay capacity %lld below the %d envs of a vector step", (long long)io->capacity, env->cfg.num_envs);
   CUDA_TRY(cudaSetDevice(env->cfg.device));
   const void *ptrs[] = {io->obs, io->final_obs, io->done, io->next_states, io->states};
   for (const void *p : ptrs)

@@ -1586,6 +1586,7 @@ int grlo_replay_push_rows(grlo_env *e, const grl_replay_rows_io *io) {
   if (!e || !io || !io->obs || io->capacity < 1 || io->obs_floats < 1 || io->views < 1 || io->view < 0 || io->view >= io->views)
     return GRL_ERR_INVALID_ARG;
   const int B = e->cfg.num_envs;
+  if (io->capacity < B || io->next_row0 < 0 || io->state_row0 < 0) return GRL_ERR_INVALID_ARG;
   const size_t F = (size_t)io->obs_floats;
   for (int b = 0; b < B; b++) {
     const float *row = io->obs + ((size_t)b * (size_t)io->views + (size_t)io->view) * F;

@@ -170,6 +170,8 @@ def test_replay_push_rows_matches_numpy(oracle_lib):
     assert np.array_equal(ns2[:B], obs[:, 0])
     with pytest.raises(RuntimeError):
         e.replay_push_rows(obs, P, 2, F, cap, next_states=ns2)                   # view out of range
+    with pytest.raises(RuntimeError):
+        e.replay_push_rows(obs, P, 0, F, B - 1, next_states=ns2)                 # a ring smaller than one vector step
 
 
 def test_pool_caps_episodes_at_max_steps(oracle_lib):

@@ -71,6 +71,7 @@ def main():
         t = sum(d['dram_bytes'] for d in out) / len(out)
         json.dump({"kernel": f"grl_turn_kernel<{P},{W},{H}>", "dram_bytes_per_launch": t, "algorithmic_bytes_per_launch": alg,
                    "traffic_over_algorithmic": t / alg, "lib_source_hash": grl_build.source_hash(),
+                   "turn_source_hash": grl_build.turn_source_hash(),
                    "source": f"profiles/{tag}_ncu_summary.json (ncu --set full, {games} games {W}x{H}x{P}p)"},
                   open(os.path.join(prof, "traffic.json"), "w"), indent=1)
     # per-region shares
