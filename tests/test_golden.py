@@ -1,4 +1,4 @@
-"""Committed REGRESSION fixtures (tests/golden/rollout_*.npz, made by tools/make_golden.py): fixed-seed maps and
+"""Committed REGRESSION fixtures (tests/golden/rollout_*.npz, made by tests/tools/make_golden.py): fixed-seed maps and
 120-turn trajectories recorded from this repository's own oracle.  They are not reference data — the Go engine cannot
 run here — and pin nothing against the reference; they freeze behaviour, so that a later edit of the oracle OR of the
 kernels that moves any trajectory is noticed.  (Reference pins live elsewhere: tests/kats.py — the reference's own Go

@@ -3,7 +3,7 @@
 tests/golden/gym_ref/*.npz hold outputs of the UNMODIFIED ``python/generals_gym/generals_env.py``
 (``_get_observation``, ``_get_valid_actions_mask``, ``_action_index_to_game_action``,
 ``_calculate_reward`` and whole ``reset()``/``step()`` episodes), produced in the build container by
-tools/make_gym_fixtures.py, which imports the reference client behind a ``gymnasium`` stub and serves
+tests/tools/make_gym_fixtures.py, which imports the reference client behind a ``gymnasium`` stub and serves
 it ``generals_pb`` ``GameState`` messages.  Nothing here reads /root/reference.
 
   readouts_*   given engine states (all planes, loaded with grl_set_state) -> for every player the

@@ -4,13 +4,13 @@ predecessor on the device: programmatic dependent launch + per-warp epoch words,
 stepping the same turns.  Compared at the end of every chain: every env's full-state digest, the counters, and the last
 launch's reward / done / mask planes and observation digests.  One JSON line per configuration.
 
-usage: python tools/chain_soak.py [W H P B chain_length chains] ..."""
+usage: python tests/tools/chain_soak.py [W H P B chain_length chains] ..."""
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

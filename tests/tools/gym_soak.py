@@ -5,13 +5,13 @@ episodes including truncation and automatic re-seeding; reward (float64 bits), t
 turn counters and full-state digests are compared EVERY step, observation and mask planes by digest every 20th step.
 One JSON line per configuration (profiles/r1h_gym_soak.jsonl).
 
-usage: python tools/gym_soak.py [W B max_turns steps] ..."""
+usage: python tests/tools/gym_soak.py [W B max_turns steps] ..."""
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

@@ -5,7 +5,7 @@ The reference is Go and cannot run in this image, so these vectors are produced 
 oracle (oracle/grl_oracle.c), which is itself pinned by the reference's own known-answer
 tests (tests/kats.py) and seeded mapgen golden counts.  They freeze the oracle's behaviour:
 a later edit of the oracle OR of the CUDA kernels that changes any trajectory fails
-tests/test_golden.py.  Usage: python tools/make_golden.py  (rewrites tests/golden/).
+tests/test_golden.py.  Usage: python tests/tools/make_golden.py  (rewrites tests/golden/).
 
 Per config (W,H,P): 16 games, seeds 12345+i, 120 turns of the counter-based random-legal-move
 policy (policy seed 2024):
@@ -21,7 +21,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -37,7 +37,7 @@ generals_env.py:421-428) is not buffered, the turn runs without it, and the clie
 Gymnasium's ``TimeLimit`` (``gym.register(max_episode_steps=500)``, generals_env.py:607-611) is not
 part of the class and is not emulated here; the fixtures record the class's own ``truncated``.
 
-Usage: python tools/make_gym_fixtures.py   (rewrites tests/golden/gym_ref/*.npz; this container only --
+Usage: python tests/tools/make_gym_fixtures.py   (rewrites tests/golden/gym_ref/*.npz; this container only --
 /root/reference does not exist on the GPU box).
 """
 from __future__ import annotations
@@ -48,7 +48,7 @@ import types
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 REF_PY = "/root/reference/python"

@@ -4,13 +4,13 @@ oracle with the same recorded actions, compared EVERY turn (full-state digest of
 bits, done, winner, step_error, packed masks; observation digests every 25th turn), then re-seeded
 and played on.  Prints one JSON line per configuration (profiles/r1_parity_soak.jsonl).
 
-usage: python tools/parity_soak.py [W H P B T] ...   (default: the four BASELINE shapes)"""
+usage: python tests/tools/parity_soak.py [W H P B T] ...   (default: the four BASELINE shapes)"""
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
