@@ -504,7 +504,7 @@ def test_reference_gym_env_plays_against_this_server(server):
     import random
     import sys
 
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
     import make_gym_fixtures as mk
 
     generals_env, game_pb2, common_pb2 = mk.load_reference()
