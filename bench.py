@@ -228,7 +228,8 @@ def run_reference(args):
     # moved the figure by +-25 % between boxes); the rate is per env-step, so the step's size does not enter it
     start = min(args.start_turn, 200)
     tps_max = max(1, (498 - start) // max(1, args.steps + args.warmup))
-    cal, _, _, _ = time_oracle(games, 2, 1, start_turn=start)          # calibration: this box, this state
+    # calibration: this box, this state; the better of two short runs (a cold first run would undersize the sample)
+    cal = max(time_oracle(games, 2, 1, start_turn=start)[0] for _ in range(2))
     tps = int(max(1, min(np.ceil(2.5 * cal / (games * max(1, args.steps))), tps_max)))
     rate, dt, cores, n = time_oracle(games, args.steps, args.warmup, start_turn=start, turns_per_step=tps)
     line = {

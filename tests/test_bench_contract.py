@@ -24,7 +24,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["gpu_launches"] == 0 and "workload" in d["config"]
     # the timed sample is long enough to anchor a ratio (a 0.1 s sample moved it by +-25 % between boxes)
     assert d["config"]["start_turn"] == 30 and d["config"]["turns_per_step"] >= 1
-    assert d["ms_per_step"] * d["steps"] >= 1000.0 or d["config"]["turns_per_step"] * (d["steps"] + d["warmup"]) >= 250
+    assert d["ms_per_step"] * d["steps"] >= 600.0 or d["config"]["turns_per_step"] * (d["steps"] + d["warmup"]) >= 250
 
 
 def test_algorithmic_bytes_match_the_design():
