@@ -255,7 +255,8 @@ def run_reference(args):
 
 def gym_contract_rate(envs=65536, board=15, steps=60):
     """Extra, informational: the generals_gym contract through GeneralsVecEnv at the reference's default
-    board (15x15) — one grl_gym_step launch per step, the reference's random agent (grl_gym_sample) as the policy, episode
+    board (15x15) — one grl_gym_step launch per step, the reference's random agent as the policy (drawn inside the step's
+    launch, and as a grl_gym_sample launch of its own for comparison), episode
     ends spread over time so that every step re-seeds envs on the device (grl_gym_autoreset).  Timed with CUDA events on
     torch's stream (the env's stream); never allowed to break the headline line."""
     try:
@@ -266,23 +267,31 @@ def gym_contract_rate(envs=65536, board=15, steps=60):
         env = GeneralsVecEnv(envs, board, board, max_turns=500, seed=12345, auto_reset="device")
         env.reset()
         env._calls.copy_(torch.randint(0, env.max_turns, (envs,), device=env._calls.device, dtype=torch.int32))
-        for _ in range(5):
-            env.step(env.sample_actions())
-        torch.cuda.synchronize()
-        l0 = env.engine.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            env.step(env.sample_actions())
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        launches = (env.engine.launch_count() - l0) / steps
+
+        def timed(one_step):
+            for _ in range(5):
+                one_step()
+            torch.cuda.synchronize()
+            l0 = env.engine.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                one_step()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps, (env.engine.launch_count() - l0) / steps
+
+        ms_sampler, launches_sampler = timed(lambda: env.step(env.sample_actions()))   # the agent as a launch of its own
+        ms, launches = timed(lambda: env.step(None))                                   # the agent drawn inside the step
         env.close()
         return {"value": envs / (ms * 1e-3), "unit": "env-steps/s", "envs": envs, "board": [board, board], "ms_per_vector_step": ms,
                 "launches_per_step": launches,
-                "what": "GeneralsVecEnv.step (one grl_gym_step launch) + random agent (grl_gym_sample) + device-side auto-reset of "
-                        "the ~130 envs whose episode ends each step (grl_gym_autoreset); reference gym path: 12 steps/s per env"}
+                "with_sampler_launch": {"value": envs / (ms_sampler * 1e-3), "ms_per_vector_step": ms_sampler,
+                                        "launches_per_step": launches_sampler},
+                "what": "GeneralsVecEnv.step(None): one grl_gym_step launch that also draws the reference's random agent from the "
+                        "direction masks in registers (the same indices grl_gym_sample returns) + device-side auto-reset of the "
+                        "~130 envs whose episode ends each step (grl_gym_autoreset); with_sampler_launch = step(sample_actions()), "
+                        "the agent as a separate grl_gym_sample launch over the mask bytes; reference gym path: 12 steps/s per env"}
     except Exception as exc:  # noqa: BLE001 - informational figure only
         return {"unavailable": repr(exc)[:200]}
 

@@ -116,7 +116,8 @@ class GymStepIO(C.Structure):
     _fields_ = [("action", C.c_void_p), ("opponent_action", C.c_void_p), ("out", GymOutputs), ("actions", C.c_void_p),
                 ("prev_stats", C.c_void_p), ("turns", C.c_void_p), ("calls", C.c_void_p), ("reward", C.c_void_p),
                 ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("valid", C.c_void_p), ("done", C.c_void_p),
-                ("winner", C.c_void_p), ("step_error", C.c_void_p), ("n_finished", C.c_void_p)]
+                ("winner", C.c_void_p), ("step_error", C.c_void_p), ("n_finished", C.c_void_p),
+                ("agent_seed", C.c_uint64), ("sampled_action", C.c_void_p)]
 
 
 class GymAutoresetIO(C.Structure):

@@ -1018,8 +1018,10 @@ int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const 
   const grl_config &c = env->cfg;
   if (c.num_players < 2 || c.max_actions < 2) return fail(GRL_ERR_INVALID_ARG, "the gym step drives 2 players / 2 action slots");
   // ONE launch: the turn kernel's gym instantiation (io->actions / io->prev_stats are scratch only the oracle uses).
-  const void *need[] = {io->action, io->out.mask, io->out.stats, io->turns, io->calls, io->reward,
-                        io->terminated, io->truncated, io->valid, io->done, io->winner, io->step_error};
+  // action == NULL: the random agent, drawn in the launch (its index goes to sampled_action)
+  const void *need[] = {io->action ? (const void *)io->action : (const void *)io->sampled_action, io->out.mask, io->out.stats,
+                        io->turns, io->calls, io->reward, io->terminated, io->truncated, io->valid, io->done, io->winner,
+                        io->step_error};
   CUDA_TRY(cudaSetDevice(c.device));
   for (const void *p : need)
     if (!p || !is_device_ptr(p)) return fail(GRL_ERR_UNSUPPORTED, "grl_gym_step takes device pointers for every plane");
@@ -1046,6 +1048,8 @@ int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const 
   gk.n_finished = io->n_finished;
   gk.opponent_seed = opponent_seed;
   gk.max_turns = max_turns;
+  gk.agent_seed = io->agent_seed;
+  gk.sampled_action = io->action ? nullptr : (long long *)io->sampled_action;
   GrlKParams pt = base_params(env);
   pt.actions = nullptr;
   pt.done = io->done;

@@ -107,7 +107,7 @@ struct GrlKParams {
 // Second parameter block of the turn kernel, read only by its fused gym-step instantiation
 // (grl_gym_step: one GeneralsEnv.step() for every env in a single launch).
 struct GrlGymK {
-  const long long *action;           // [B] Discrete(N*5) indices of player 0
+  const long long *action;           // [B] Discrete(N*5) indices of player 0, or nullptr: the random agent
   const long long *opponent_action;  // [B] or nullptr: the random opponent
   const float *logtab;               // log(a + 1) / 10 for every uint16 army
   float *obs;                        // [B][P][9][N]
@@ -119,4 +119,6 @@ struct GrlGymK {
   int32_t *n_finished;
   unsigned long long opponent_seed;
   int max_turns;
+  unsigned long long agent_seed;     // action == nullptr: player 0 draws grl_gym_sample(agent_seed, mask, 0) in the launch
+  long long *sampled_action;         // [B] the index it drew
 };

@@ -33,10 +33,61 @@ template <int PT, int LG>
 __device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, const uint32_t *st, uint32_t *s_act,
                                           uint32_t alive, uint32_t turn_before, int game, Geo g, int W, int H, int N, int NW);
 
+// The random agent of a fused gym step (GrlGymK.action == nullptr): the index grl_gym_sample(seed, mask, 0) returns for
+// this game's CURRENT mask — the k-th set entry of player 0's N*5 mask bytes in index order (tile-major; up, right, down,
+// left, half per tile), k = policy_draw(seed, env, 0, 0) mod the number of set entries; 0 (which the env rejects) when
+// none is set — from the view's direction masks in registers (word `lane` of the group) instead of the mask bytes in
+// HBM.  Only the GYM == 2 instantiations of the turn kernel contain it: the step that is handed its actions (GYM == 1) is
+// the same code as before.  Group-uniform result.
+template <int LG>
+__device__ __noinline__ long long gym_random_agent(unsigned long long seed, unsigned long long env_global, uint32_t U, uint32_t R,
+                                                   uint32_t D, uint32_t Lm, Geo g) {
+  const uint32_t Hf = U | R | D | Lm;  // the half move: valid wherever a full move is (generals_env.py:380-383)
+  const int cnt = __popc(U) + __popc(R) + __popc(D) + __popc(Lm) + __popc(Hf);
+  const int total = __reduce_add_sync(g.seg, cnt);
+  if (total == 0) return 0;
+  const uint64_t rr = policy_draw(seed, env_global, 0ull, 0ull);
+  const int k = (int)(rr % (uint64_t)total);
+  int incl = cnt;  // inclusive prefix sum over the group's lanes
+#pragma unroll
+  for (int o = 1; o < LG; o <<= 1) {
+    const int v = __shfl_up_sync(g.seg, incl, o, LG);
+    if (g.lane >= o) incl += v;
+  }
+  const int excl = incl - cnt;
+  const bool mine = k >= excl && k < incl;
+  const int kk = k - excl;
+  int b = 0;  // the tile bit of this word the kk-th entry belongs to: the largest b with count(bits < b) <= kk
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    const int cand = b + step;
+    const uint32_t m = (1u << cand) - 1u;  // cand in 1..31
+    const int c = __popc(U & m) + __popc(R & m) + __popc(D & m) + __popc(Lm & m) + __popc(Hf & m);
+    if (c <= kk) b = cand;
+  }
+  const uint32_t below = (1u << b) - 1u;
+  int rem = kk - (__popc(U & below) + __popc(R & below) + __popc(D & below) + __popc(Lm & below) + __popc(Hf & below));
+  const uint32_t five = ((U >> b) & 1u) | (((R >> b) & 1u) << 1) | (((D >> b) & 1u) << 2) | (((Lm >> b) & 1u) << 3) |
+                        (((Hf >> b) & 1u) << 4);
+  int dir = 0;
+#pragma unroll
+  for (int d = 0; d < 5; d++) {
+    if ((five >> d) & 1u) {
+      if (rem == 0) dir = d;
+      rem--;
+    }
+  }
+  int packed = mine ? (32 * g.lane + b) * 5 + dir : 0;
+  const uint32_t who = __ballot_sync(g.seg, mine) >> g.shift;
+  packed = __shfl_sync(g.seg, packed, __ffs(who) - 1, LG);
+  return (long long)packed;
+}
+
 // Fused gym step, before the turn: decode the agent's (player 0) Discrete(N*5) index against the gym mask of the
 // CURRENT state (client-side rejection, generals_env.py:226-229), then the opponent's index or the random
-// opponent's draw; decoded moves go to s_act.  Returns whether the agent's action is valid.
-template <int PT, int LG>
+// opponent's draw; decoded moves go to s_act.  AGENT: the agent's index is not given but drawn here
+// (gym_random_agent).  Returns whether the agent's action is valid.
+template <int PT, int LG, bool AGENT>
 __device__ __forceinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK &gk, uint32_t *s, const uint32_t *st,
                                               uint32_t *s_act, uint32_t alive, bool over, uint32_t turn_before, int game, Geo g,
                                               int W, int H, int N, int NW, long long a0, long long a1);
@@ -82,7 +133,7 @@ struct TurnOccupancy {  // CTAs of 256 threads per SM the register budget is tun
   static constexpr int kMinBlocks = PT <= 2 ? 4 : (PT <= 4 ? 3 : 2);
 };
 
-template <int PT, int TW, int TH, int LG, bool DO_STEP, bool DO_OUT, bool GYM>
+template <int PT, int TW, int TH, int LG, bool DO_STEP, bool DO_OUT, int GYM>
 __device__ __forceinline__ void grl_turn_body(const GrlKParams &prm, const GrlGymK &gk) {
   static_assert(!GYM || (DO_STEP && DO_OUT), "the fused gym step is a turn plus read-outs");
   constexpr int GPW = 32 / LG;  // games per warp
@@ -166,7 +217,7 @@ __device__ __forceinline__ void grl_turn_body(const GrlKParams &prm, const GrlGy
     long long gym_a0 = 0, gym_a1 = 0;  // the fused gym step's Discrete(N*5) indices: fetched now, tested after the wait
     int gym_tn = 0, gym_cl = 0;        // the env's turn / call counters: read-modify-write at the end, loaded now
     if constexpr (GYM) {
-      gym_a0 = __ldg(gk.action + game);
+      if constexpr (GYM == 1) gym_a0 = __ldg(gk.action + game);  // GYM == 2: the random agent, drawn in gym_pre_phase
       if (gk.opponent_action) gym_a1 = __ldg(gk.opponent_action + game);
       if (l == 0) {
         gym_tn = gk.turns[game];
@@ -224,7 +275,7 @@ __device__ __forceinline__ void grl_turn_body(const GrlKParams &prm, const GrlGy
       gym_army0 = (int)S.hdr[GRL_HDR_PLAYER0 + GRL_PL_ARMY_COUNT];
       gym_tiles0 = __reduce_add_sync(g.seg, __popc(lst[0]));
       gym_alive0 = alive;
-      skip = !gym_pre_phase<PT, LG>(prm, gk, s, st, s_act, alive, over, turn, game, g, W, H, N, NW, gym_a0, gym_a1);
+      skip = !gym_pre_phase<PT, LG, GYM == 2>(prm, gk, s, st, s_act, alive, over, turn, game, g, W, H, N, NW, gym_a0, gym_a1);
     }
 
     if (DO_STEP) {
@@ -856,7 +907,7 @@ __device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int PT, int TW, int TH, int LG, bool DO_STEP, bool DO_OUT, bool GYM>
+template <int PT, int TW, int TH, int LG, bool DO_STEP, bool DO_OUT, int GYM>
 __global__ void __launch_bounds__(GRL_WARPS_PER_CTA * 32, TurnOccupancy<PT, LG>::kMinBlocks)
     grl_turn_kernel(const __grid_constant__ GrlKParams prm, const __grid_constant__ GrlGymK gk) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -903,7 +954,7 @@ __device__ __noinline__ void policy_phase(const GrlKParams &prm, uint32_t *s, co
   __syncwarp(g.seg);
 }
 
-template <int PT, int LG>
+template <int PT, int LG, bool AGENT>
 __device__ __forceinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGymK &gk, uint32_t *s, const uint32_t *st,
                                               uint32_t *s_act, uint32_t alive, bool over, uint32_t turn_before, int game, Geo g,
                                               int W, int H, int N, int NW, long long a0, long long a1) {
@@ -953,6 +1004,14 @@ __device__ __forceinline__ bool gym_pre_phase(const GrlKParams &prm, const GrlGy
       s_act[2 * slot + 1] = d.y;
     }
   };
+  if constexpr (AGENT) {  // the random agent: one of the entries gym_ok accepts, or 0 when there is none
+    const uint32_t own0 = act_lane ? S.own[g.lane] : 0u;
+    const uint32_t v0 = act_lane ? (prm.fog ? S.vis[g.lane] : g.valid) : 0u;
+    const uint32_t src0 = v0 & own0 & gt1;
+    a0 = gym_random_agent<LG>(gk.agent_seed, (unsigned long long)(prm.env_id_base + game), src0 & dm.up, src0 & dm.right,
+                              src0 & dm.down, src0 & dm.left, g);
+    if (g.lane == 0) gk.sampled_action[game] = a0;
+  }
   const bool ok0 = gym_ok(a0, 0);
   if (ok0) put(a0, 0, 0);
   if (gk.opponent_action) {
@@ -1047,9 +1106,9 @@ static inline size_t grl_turn_smem_bytes(const GrlLayout &L, int TW, int TH, int
   return (size_t)GRL_WARPS_PER_CTA * (size_t)((32 / LG) * per_game + scratch) * 4u;
 }
 
-template <int PT, int TW, int TH, int LG, bool S, bool O, bool GYM = false>
+template <int PT, int TW, int TH, int LG, bool S, bool O, int GYM = 0>
 static cudaError_t launch_turn_t(const GrlKParams &prm, cudaStream_t stream, const GrlGymK *gym = nullptr) {
-  size_t smem = grl_turn_smem_bytes(prm.L, TW, TH, PT, LG, GYM);
+  size_t smem = grl_turn_smem_bytes(prm.L, TW, TH, PT, LG, GYM != 0);
   auto kern = grl_turn_kernel<PT, TW, TH, LG, S, O, GYM>;
   GrlGymK gk;
   memset(&gk, 0, sizeof gk);
@@ -1101,8 +1160,14 @@ static cudaError_t launch_turn_geo(const GrlKParams &prm, bool do_step, bool do_
 
 template <int TW, int TH, int LG>
 static cudaError_t launch_gym_geo(const GrlKParams &prm, const GrlGymK &gk, cudaStream_t stream) {
-  if (prm.P <= 2) return launch_turn_t<2, TW, TH, LG, true, true, true>(prm, stream, &gk);
-  if (prm.P <= 4) return launch_turn_t<4, TW, TH, LG, true, true, true>(prm, stream, &gk);
-  if constexpr (TW == 0) return launch_turn_t<8, TW, TH, LG, true, true, true>(prm, stream, &gk);
+  // GYM = 1: the agent's indices are given; 2: the random agent is drawn inside the launch (gk.action == nullptr).  The
+  // gym contract drives two players, so only the two-player template carries the second instantiation.
+  if (gk.action == nullptr) {
+    if (prm.P <= 2) return launch_turn_t<2, TW, TH, LG, true, true, 2>(prm, stream, &gk);
+    return cudaErrorInvalidValue;
+  }
+  if (prm.P <= 2) return launch_turn_t<2, TW, TH, LG, true, true, 1>(prm, stream, &gk);
+  if (prm.P <= 4) return launch_turn_t<4, TW, TH, LG, true, true, 1>(prm, stream, &gk);
+  if constexpr (TW == 0) return launch_turn_t<8, TW, TH, LG, true, true, 1>(prm, stream, &gk);
   return cudaErrorInvalidValue;
 }

@@ -228,8 +228,10 @@ class BatchedEngine:
     def gym_step(self, max_turns: int, opponent_seed: int, **planes) -> None:
         """One GeneralsEnv.step() for every env (grl_gym_step).  Keyword planes: action, opponent_action, obs, mask,
         stats, actions, prev_stats, turns, calls, reward, terminated, truncated, valid, done, winner, step_error,
-        n_finished."""
+        n_finished; with ``action`` absent (or None) player 0 is the random agent: ``agent_seed`` (int) keys its draw and
+        ``sampled_action`` (int64 [B]) receives the index it played."""
         io = GymStepIO()
+        io.agent_seed = int(planes.pop("agent_seed", 0)) & 0xFFFFFFFFFFFFFFFF
         for k, v in planes.items():
             if k in ("obs", "mask", "stats"):
                 setattr(io.out, k, _ptr(v))

@@ -143,7 +143,9 @@ class GeneralsVecEnv:
         return self._obs[:, 0], {"valid_actions_mask": self._mask[:, 0], "turn": self._turns.clone()}
 
     def step(self, action, opponent_action=None):
-        """action: int64 [B] indices into Discrete(N*5) for player 0 (and ``opponent_action`` for
+        """action: int64 [B] indices into Discrete(N*5) for player 0, or None for the reference's random agent
+        (python/generals_agent/random_agent.py) drawn inside the step's launch — ``step(None)`` plays exactly
+        ``step(sample_actions())`` and reports the indices in ``info["action"]`` (and ``opponent_action`` for
         player 1 under self-play; otherwise the reference's default random opponent, a uniformly
         random legal full move drawn on the device).  Returns (obs, reward, terminated, truncated, info).
 
@@ -151,9 +153,18 @@ class GeneralsVecEnv:
         rejection of masked-out indices (that env takes no turn, reward -0.1, generals_env.py:226-229),
         the turn, the gym read-outs, the client's reward (:499-561, float64) and the episode flags."""
         t = self.torch
-        action = t.as_tensor(action, device=self.device)
-        if action.dtype != t.int64 or not action.is_contiguous():
-            action = action.to(t.int64).contiguous()
+        agent = {}
+        if action is None:
+            # the random agent inside the step's own launch: the very index sample_actions() would have returned (same
+            # draw counter, same seed), without the sampler's launch and its pass over the N*5 mask bytes;
+            # info["action"] is what each env played
+            self._sample_draws += 1
+            agent = dict(agent_seed=self._base_seed * 7919 + self._sample_draws,
+                         sampled_action=self._sampled[self._sample_draws & 1])
+        else:
+            action = t.as_tensor(action, device=self.device)
+            if action.dtype != t.int64 or not action.is_contiguous():
+                action = action.to(t.int64).contiguous()
         oa = None
         if opponent_action is not None:
             oa = t.as_tensor(opponent_action, device=self.device).to(t.int64).contiguous()
@@ -164,10 +175,12 @@ class GeneralsVecEnv:
                              obs=self._obs, mask=self._mask, stats=self._stats, actions=self._actions,
                              prev_stats=self._prev_stats, turns=self._turns, calls=self._calls, reward=o["reward"],
                              terminated=o["terminated"], truncated=o["truncated"], valid=o["valid"], done=self._done,
-                             winner=o["winner"], step_error=o["step_error"], n_finished=self._nfin)
+                             winner=o["winner"], step_error=o["step_error"], n_finished=self._nfin, **agent)
         terminated, truncated, reward = o["terminated"], o["truncated"], o["reward"]
         # info tensors are the env's own planes: valid until the next step() (turn, mask) or the one after (the rest)
         info: Dict[str, Any] = {"invalid_action": ~o["valid"], "winner": o["winner"], "step_error": o["step_error"]}
+        if agent:
+            info["action"] = agent["sampled_action"]
         turn = self._turns
         if self.auto_reset == "device":
             info["final_env_mask"] = terminated | truncated

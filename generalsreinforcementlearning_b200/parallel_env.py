@@ -229,6 +229,11 @@ class ReplayBuffer:
             return self._size
 
 
+# batch_action_fn=RANDOM_AGENT: the reference's random agent (python/generals_agent/random_agent.py) drawn inside the vector
+# step's own launch — the indices vec.sample_actions() would return, without its launch
+RANDOM_AGENT = "random_agent"
+
+
 class ParallelEnvPool:
     """N environments stepped together (vector_env.py:27-192): one collector thread drives a ``GeneralsVecEnv``,
     pushes every env's transition of every step into the shared replay buffer and keeps the per-episode results."""
@@ -318,6 +323,8 @@ class ParallelEnvPool:
     # ------------------------------------------------------------------ one step of every env
     def _actions(self):
         t = self._t
+        if self.batch_action_fn == RANDOM_AGENT:   # drawn inside the vector step's launch (GeneralsVecEnv.step(None))
+            return None
         if self.batch_action_fn is not None:
             a = self.batch_action_fn(self._obs, self._mask)
             return t.as_tensor(a, device=self._vec.device).to(t.int64)
@@ -335,6 +342,8 @@ class ParallelEnvPool:
             return self._step_native(actions)
         ticket = self.replay_buffer.begin_step(self._obs)   # the env's observation plane is overwritten by the step
         next_obs, reward, terminated, truncated, info = vec.step(actions)
+        if actions is None:
+            actions = info["action"]
         done = terminated | truncated                       # vector_env.py:172: done = terminated or truncated
         final = None
         if self._dense_final:
@@ -356,6 +365,8 @@ class ParallelEnvPool:
     def _step_native(self, actions) -> None:
         t, vec, buf = self._t, self._vec, self.replay_buffer
         next_obs, reward, terminated, truncated, info = vec.step(actions)
+        if actions is None:
+            actions = info["action"]
         done = terminated | truncated
         self._ep_reward += reward
         self._ep_len += 1

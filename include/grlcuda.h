@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define GRL_ABI_VERSION 2 /* 2: grl_step_outputs.obs_packed, grl_obs_packed_words, grl_expand_obs */
+#define GRL_ABI_VERSION 3 /* 2: grl_step_outputs.obs_packed, grl_obs_packed_words, grl_expand_obs; 3: grl_gym_step_io.agent_seed / sampled_action */
 
 #define GRL_MAX_DIM 32      /* width, height <= 32: one 32-bit word spans a board row */
 #define GRL_MAX_PLAYERS 8   /* reference bitfield allows 32 (core/board.go:11); configs need <= 4 */
@@ -291,7 +291,7 @@ int grl_gym_sample(grl_env *env, uint64_t seed, const uint8_t *mask, int32_t pla
  * terminated (game left IN_PROGRESS) / truncated (turns or step() calls reached max_turns).
  * libgrlcuda.so requires device pointers for every plane; nothing is copied to the host. */
 typedef struct grl_gym_step_io {
-  const int64_t *action;          /* [B] in: Discrete(N*5) indices of player 0                              */
+  const int64_t *action;          /* [B] in: Discrete(N*5) indices of player 0, or NULL for the random agent */
   const int64_t *opponent_action; /* [B] in: indices of player 1, or NULL for the random opponent           */
   grl_gym_outputs out;            /* in/out: mask and stats of the CURRENT state are read, all three rewritten */
   grl_action *actions;            /* [B][max_actions] scratch                                                */
@@ -303,6 +303,13 @@ typedef struct grl_gym_step_io {
   int8_t *winner;                 /* [B] out                                                                  */
   uint8_t *step_error;            /* [B] out                                                                  */
   int32_t *n_finished;            /* [1] out: number of envs with terminated | truncated                      */
+  /* The random agent (python/generals_agent/random_agent.py; what the trainers' epsilon-greedy exploration draws with
+   * np.random.choice over valid_actions_mask): with action == NULL player 0 plays, in every env, exactly the index
+   * grl_gym_sample(agent_seed, out.mask, 0, .) returns for the CURRENT state — drawn inside the step's own launch, so
+   * a random-agent step costs no second launch and no read of the N*5 mask bytes.  The index played is written to
+   * sampled_action (required in that case; ignored when `action` is given). */
+  uint64_t agent_seed;
+  int64_t *sampled_action;        /* [B] out                                                                  */
 } grl_gym_step_io;
 int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const grl_gym_step_io *io);
 

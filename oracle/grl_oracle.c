@@ -1627,7 +1627,7 @@ int grlo_gym_observe(grlo_env *e, int32_t max_turns, const grl_gym_outputs *out)
 
 /* GeneralsEnv.step (generals_env.py:210-289) for every env; reward :499-561 in float64 like the client */
 int grlo_gym_step(grlo_env *e, int32_t max_turns, uint64_t opponent_seed, const grl_gym_step_io *io) {
-  if (!e || !io || !io->action || !io->out.mask || !io->out.stats || !io->actions || !io->prev_stats || !io->turns ||
+  if (!e || !io || (!io->action && !io->sampled_action) || !io->out.mask || !io->out.stats || !io->actions || !io->prev_stats || !io->turns ||
       !io->calls || !io->reward || !io->terminated || !io->truncated || !io->valid || !io->done || !io->winner ||
       !io->step_error || max_turns < 1)
     return GRL_ERR_INVALID_ARG;
@@ -1642,7 +1642,12 @@ int grlo_gym_step(grlo_env *e, int32_t max_turns, uint64_t opponent_seed, const 
     if ((st = grlo_sample_actions(e, opponent_seed, io->actions))) return st;
     for (int b = 0; b < B; b++) io->actions[(size_t)b * A + 1].move_all = 1;
   }
-  if ((st = grlo_gym_encode(e, io->action, 0, 0, io->out.mask, 1, io->actions, io->valid))) return st;
+  const int64_t *agent = io->action;
+  if (!agent) { /* the random agent (python/generals_agent/random_agent.py): a uniformly random entry of the CURRENT mask */
+    if ((st = grlo_gym_sample(e, io->agent_seed, io->out.mask, 0, io->sampled_action))) return st;
+    agent = io->sampled_action;
+  }
+  if ((st = grlo_gym_encode(e, agent, 0, 0, io->out.mask, 1, io->actions, io->valid))) return st;
   /* Server.SubmitAction -> ActionValidator.ValidateCoreAction (internal/grpc/gameserver/server.go:241,
    * action_validator.go:113-137): MoveAction.Validate against the board AT SUBMISSION; a refused action is never
    * buffered and the turn runs without it.  The client does not look at the response, so it still counts the

@@ -36,7 +36,7 @@ def test_header_and_binding_agree():
 def test_product_exports_every_declared_symbol(product_lib):
     for name in header_functions():
         assert hasattr(product_lib.cdll, name), name
-    assert product_lib.abi_version() == 2
+    assert product_lib.abi_version() == 3
 
 
 def test_oracle_exports_the_same_abi(oracle_lib):

@@ -166,7 +166,7 @@ def test_replay_and_state_codec_roundtrip(oracle_lib, tmp_path):
     w.save(path)
     meta, actions = replay.load_replay(path)
     assert meta["turns"] == 45 and actions.shape == (45, B, e.A, 8)
-    assert meta["abi"] == oracle_lib.abi_version() == 2 and meta["config"]["normal_growth_interval"] == 25
+    assert meta["abi"] == oracle_lib.abi_version() == 3 and meta["config"]["normal_growth_interval"] == 25
     e2 = new_engine(oracle_lib, 10, 10, 2, B)
     assert replay.replay(e2, path) == 45
     assert np.array_equal(e2.state_hash(), e.state_hash())

@@ -251,8 +251,10 @@ def test_cuda_gym_sample_matches_oracle(cuda_lib, oracle_lib, W, H, P, B):
         assert np.array_equal(x, y)
 
 
-def _drive_pair(a, b, steps, compare_final=True, compact_info=False):
-    """Two vector envs stepped with the same actions; every returned tensor compared each step."""
+def _drive_pair(a, b, steps, compare_final=True, compact_info=False, b_random_agent=False):
+    """Two vector envs stepped with the same actions; every returned tensor compared each step.  With b_random_agent env b
+    draws its agent's action inside the step (step(None), grl_gym_step_io.action == NULL) while env a plays what its
+    sampler (grl_gym_sample) returned: the two must be the same indices, step after step."""
     import torch
 
     oa, _ = a.reset()
@@ -261,11 +263,16 @@ def _drive_pair(a, b, steps, compare_final=True, compact_info=False):
     for t in range(steps):
         assert torch.equal(oa.cpu(), ob.cpu()), f"observation, step {t}"
         act = a.sample_actions().cpu()
-        assert torch.equal(act, b.sample_actions().cpu()), f"sampled actions, step {t}"
-        if t % 5 == 2:
-            act = act.clone()
-            act[::7] = 0
-        ra, rb = a.step(act.to(a.device)), b.step(act.to(b.device))
+        if b_random_agent:
+            ra, rb = a.step(act.to(a.device)), b.step(None)
+            assert torch.equal(act, rb[4]["action"].cpu()), f"the action drawn inside the step, step {t}"
+            assert torch.equal(ra[4]["invalid_action"].cpu(), rb[4]["invalid_action"].cpu()), f"valid flags, step {t}"
+        else:
+            assert torch.equal(act, b.sample_actions().cpu()), f"sampled actions, step {t}"
+            if t % 5 == 2:
+                act = act.clone()
+                act[::7] = 0
+            ra, rb = a.step(act.to(a.device)), b.step(act.to(b.device))
         oa, ob = ra[0], rb[0]
         for k, name in ((1, "reward"), (2, "terminated"), (3, "truncated")):
             assert torch.equal(ra[k].cpu(), rb[k].cpu()), f"{name}, step {t}"
@@ -306,6 +313,39 @@ def test_vector_env_device_autoreset_equals_host_autoreset(oracle_lib):
     assert _drive_pair(a, b, 40, compact_info=True) >= 120
     a.close()
     b.close()
+
+
+def test_vector_env_random_agent_step_equals_sampled_step(oracle_lib):
+    """step(None) — the random agent drawn by grl_gym_step itself (io.action == NULL, agent_seed, sampled_action) — plays
+    exactly step(sample_actions()): same indices, same transitions, through several generations of episodes."""
+    from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
+
+    for fog in (True, False):
+        a = GeneralsVecEnv(40, 8, 8, max_turns=9, seed=5, fog_of_war=fog, lib=oracle_lib, host_threads=1, auto_reset="device")
+        b = GeneralsVecEnv(40, 8, 8, max_turns=9, seed=5, fog_of_war=fog, lib=oracle_lib, host_threads=1, auto_reset="device")
+        assert _drive_pair(a, b, 40, b_random_agent=True) >= 120
+        a.close()
+        b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,B,max_turns,fog", [(15, 15, 300, 30, True), (20, 20, 96, 40, True), (10, 10, 1000, 25, True),
+                                                 (15, 15, 130, 30, False), (6, 9, 70, 20, True), (32, 32, 9, 30, True)])
+def test_cuda_random_agent_step_matches_sampler_and_oracle(cuda_lib, oracle_lib, W, H, B, max_turns, fog):
+    """The in-launch random agent of the CUDA gym step (gym_random_agent: the k-th valid entry from the direction masks
+    in registers) against the oracle stepping what ITS sampler drew from the mask bytes, and against the CUDA sampler
+    kernel: the same indices and the same transitions on every baked board, a generic one and the largest one."""
+    from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
+
+    mk = lambda lib, **kw: GeneralsVecEnv(B, W, H, max_turns=max_turns, seed=43, fog_of_war=fog, lib=lib, auto_reset="device", **kw)
+    o, g = mk(oracle_lib, host_threads=1), mk(cuda_lib)
+    assert _drive_pair(o, g, 2 * max_turns + 5, b_random_agent=True) >= B
+    import numpy as np
+    assert np.array_equal(g.engine.state_hash(), o.engine.state_hash())
+    g1, g2 = mk(cuda_lib), mk(cuda_lib)
+    _drive_pair(g1, g2, max_turns + 3, b_random_agent=True)     # CUDA sampler kernel + step == CUDA step(None)
+    for e in (o, g, g1, g2):
+        e.close()
 
 
 @pytest.mark.gpu

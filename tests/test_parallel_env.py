@@ -96,7 +96,7 @@ def test_parallel_env_pool_collects_like_the_reference(oracle_lib):
     pool.close()
 
 
-def _drive(lib, B, steps, auto_reset="device", cap=200, max_turns=12):
+def _drive(lib, B, steps, auto_reset="device", cap=200, max_turns=12, agent="first_valid"):
     """A pool stepped synchronously with a deterministic batch policy; returns everything it produced."""
     import torch
 
@@ -105,6 +105,11 @@ def _drive(lib, B, steps, auto_reset="device", cap=200, max_turns=12):
 
     def policy(states, masks):   # the first valid action of every env (0 when none): needs no generator
         return masks.to(torch.int8).argmax(dim=1)
+
+    if agent == "sampler":       # the random agent as a launch of its own
+        policy = lambda states, masks: vec.sample_actions()  # noqa: E731
+    elif agent == "in_step":     # the random agent drawn inside the vector step
+        from generalsreinforcementlearning_b200.parallel_env import RANDOM_AGENT as policy
 
     pool = ParallelEnvPool(B, vec_env=vec, batch_action_fn=policy, replay_buffer=buf, max_steps_per_episode=cap, seed=77)
     pool.run(steps)
@@ -146,6 +151,17 @@ def test_pool_transitions_are_consistent(oracle_lib):
     for x, y in zip(a["rows"], b2["rows"]):
         assert np.array_equal(x, y)
     assert a["results"] == b2["results"]
+
+
+def test_pool_random_agent_in_step_equals_sampler(oracle_lib):
+    """batch_action_fn=RANDOM_AGENT (the agent drawn inside grl_gym_step) collects the very rows — states, actions,
+    rewards, next states, done flags, episode results — that batch_action_fn=vec.sample_actions() does."""
+    a = _drive(oracle_lib, 9, 45, agent="sampler")
+    b = _drive(oracle_lib, 9, 45, agent="in_step")
+    for x, y in zip(a["rows"], b["rows"]):
+        assert np.array_equal(x, y)
+    assert a["rows"][4].any() and (a["rows"][1] > 0).any()
+    assert a["results"] == b["results"] and a["episodes"] == b["episodes"] > 0
 
 
 def test_replay_push_rows_matches_numpy(oracle_lib):
@@ -196,6 +212,12 @@ def test_cuda_pool_collects_what_the_oracle_pool_collects(cuda_lib, oracle_lib):
         for x, y in zip(g["rows"], o["rows"]):
             assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
         assert g["results"] == o["results"] and g["episodes"] == o["episodes"] and g["total"] == o["total"] == 9000
+    # the random agent drawn inside the CUDA gym step collects what the oracle pool collects with its sampler
+    g = _drive(cuda_lib, 300, 30, agent="in_step")
+    o = _drive(oracle_lib, 300, 30, agent="sampler")
+    for x, y in zip(g["rows"], o["rows"]):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    assert g["results"] == o["results"] and g["episodes"] == o["episodes"] > 0
     # and the tensor-copy path (compact final observations) on the GPU equals the kernel path
     h = _drive(cuda_lib, 300, 30, auto_reset="host")
     k = _drive(cuda_lib, 300, 30, auto_reset="device")

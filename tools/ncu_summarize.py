@@ -86,7 +86,7 @@ def main():
     m = re.search(r"grl_turn_kernel<([^>]*)>", out[0]['Kernel Name']) if out else None
     if m:
         a = [v.strip() for v in m.group(1).split(",")]
-        kernel = "grl_turn_kernelI" + "".join(f"Li{v}E" for v in a[:4]) + "".join(f"Lb{v}E" for v in a[4:]) + "E"
+        kernel = "grl_turn_kernelI" + "".join(f"Li{v}E" for v in a[:4]) + "".join(f"Lb{v}E" for v in a[4:6]) + "".join(f"Li{v}E" for v in a[6:]) + "E"   # <PT,TW,TH,LG, bool STEP, bool OUT, int GYM>
     for cub in sorted(glob.glob("/tmp/dis/*.cubin")):
         dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
         secs = [l for l in dis.split("\n") if l.startswith("\t.section\t.text.") and kernel in l]
