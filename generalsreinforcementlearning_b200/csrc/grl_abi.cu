@@ -1018,6 +1018,9 @@ int grl_gym_step(grl_env *env, int32_t max_turns, uint64_t opponent_seed, const 
   const grl_config &c = env->cfg;
   if (c.num_players < 2 || c.max_actions < 2) return fail(GRL_ERR_INVALID_ARG, "the gym step drives 2 players / 2 action slots");
   // ONE launch: the turn kernel's gym instantiation (io->actions / io->prev_stats are scratch only the oracle uses).
+  if (!io->action && c.num_players != 2)  // the turn kernel's in-launch agent is instantiated for the two-player template
+    return fail(GRL_ERR_UNSUPPORTED, "grl_gym_step: action == NULL (the in-launch random agent) needs a two-player env, got %d players; "
+                                     "use grl_gym_sample + action", c.num_players);
   // action == NULL: the random agent, drawn in the launch (its index goes to sampled_action)
   const void *need[] = {io->action ? (const void *)io->action : (const void *)io->sampled_action, io->out.mask, io->out.stats,
                         io->turns, io->calls, io->reward, io->terminated, io->truncated, io->valid, io->done, io->winner,

@@ -348,6 +348,41 @@ def test_cuda_random_agent_step_matches_sampler_and_oracle(cuda_lib, oracle_lib,
         e.close()
 
 
+def _random_agent_call(lib, P, sampled):
+    import torch
+
+    dev = torch.device("cuda", 0) if lib.prefix == "grl_" else torch.device("cpu")
+    e = BatchedEngine(lib, make_config(lib, num_envs=8, width=8, height=8, num_players=P, max_actions=P, host_threads=1))
+    if lib.prefix == "grl_":
+        e.use_torch_stream()
+    e.reset_seeded(np.arange(8, dtype=np.int64) + 3)
+    pl = _planes(torch, dev, 8, P, 64, 8, 8)
+    e.gym_observe(20, pl["obs"], pl["mask"], pl["stats"])
+    try:
+        e.gym_step(20, 1, agent_seed=5, sampled_action=torch.zeros(8, dtype=torch.int64, device=dev) if sampled else None, **pl)
+    finally:
+        e.close()
+
+
+def test_random_agent_step_needs_its_output_plane(oracle_lib):
+    """action == NULL without sampled_action is an argument error, not a draw that nobody can read."""
+    with pytest.raises(RuntimeError):
+        _random_agent_call(oracle_lib, 2, sampled=False)
+    _random_agent_call(oracle_lib, 2, sampled=True)
+    _random_agent_call(oracle_lib, 3, sampled=True)     # the oracle draws for any number of players
+
+
+@pytest.mark.gpu
+def test_cuda_random_agent_step_argument_errors(cuda_lib):
+    """libgrlcuda.so: the same argument error, and a clear GRL_ERR_UNSUPPORTED for envs of more than two players (the
+    in-launch agent is instantiated for the two-player template; grl_gym_sample + action serves the others)."""
+    with pytest.raises(RuntimeError):
+        _random_agent_call(cuda_lib, 2, sampled=False)
+    _random_agent_call(cuda_lib, 2, sampled=True)
+    with pytest.raises(RuntimeError, match="two-player"):
+        _random_agent_call(cuda_lib, 3, sampled=True)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("W,B,max_turns", [(15, 300, 7), (20, 96, 9), (10, 1000, 6)])
 def test_cuda_device_autoreset_matches_oracle(cuda_lib, oracle_lib, W, B, max_turns):
