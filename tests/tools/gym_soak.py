@@ -5,6 +5,9 @@ episodes including truncation and automatic re-seeding; reward (float64 bits), t
 turn counters and full-state digests are compared EVERY step, observation and mask planes by digest every 20th step.
 One JSON line per configuration (profiles/r1h_gym_soak.jsonl).
 
+GRL_SOAK_RESET=device: the device-side auto-reset; GRL_SOAK_AGENT=in_step: on eight steps of nine the CUDA env draws its
+random agent inside the gym step's own launch (step(None)) and must play what the oracle's sampler drew from its mask bytes.
+
 usage: python tests/tools/gym_soak.py [W B max_turns steps] ..."""
 import json
 import os
@@ -21,7 +24,7 @@ from generalsreinforcementlearning_b200._abi import BoundLibrary
 from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
 
 
-def soak(cuda, oracle, W, B, max_turns, steps, mode="host"):
+def soak(cuda, oracle, W, B, max_turns, steps, mode="host", in_step=False):
     g = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=777, lib=cuda, auto_reset=mode)
     o = GeneralsVecEnv(B, W, W, max_turns=max_turns, seed=777, lib=oracle, host_threads=0, auto_reset=mode)
     og, _ = g.reset()
@@ -32,11 +35,16 @@ def soak(cuda, oracle, W, B, max_turns, steps, mode="host"):
     for t in range(steps):
         ctx = f"{W}x{W} step {t}"
         a = o.sample_actions()
-        assert torch.equal(g.sample_actions().cpu(), a), f"{ctx}: sampled actions"
-        if t % 9 == 4:
-            a = a.clone()
-            a[::97] = (a[::97] + 1) % (N * 5)      # some arbitrary (often masked-out) indices
-        rg = g.step(a.to(g.device))
+        if in_step and t % 9 != 4:
+            # the CUDA env draws its random agent inside the step's launch: it must play what the oracle's sampler drew
+            rg = g.step(None)
+            assert torch.equal(rg[4]["action"].cpu(), a), f"{ctx}: the action drawn inside the step"
+        else:
+            assert torch.equal(g.sample_actions().cpu(), a), f"{ctx}: sampled actions"
+            if t % 9 == 4:
+                a = a.clone()
+                a[::97] = (a[::97] + 1) % (N * 5)      # some arbitrary (often masked-out) indices
+            rg = g.step(a.to(g.device))
         ro = o.step(a)
         for k, name in ((1, "reward"), (2, "terminated"), (3, "truncated")):
             x, y = rg[k].cpu(), ro[k]
@@ -62,7 +70,7 @@ def soak(cuda, oracle, W, B, max_turns, steps, mode="host"):
         rejected += int(ro[4]["invalid_action"].sum())
     g.close()
     o.close()
-    return dict(board=[W, W], envs=B, max_turns=max_turns, steps=steps, auto_reset=mode, env_steps_compared=B * steps, episodes_finished=finished,
+    return dict(board=[W, W], envs=B, max_turns=max_turns, steps=steps, auto_reset=mode, agent="in_step" if in_step else "sampler", env_steps_compared=B * steps, episodes_finished=finished,
                 rejected_actions=rejected, mismatches=0, seconds=round(time.time() - t0, 1))
 
 
@@ -73,7 +81,7 @@ def main():
     configs = [tuple(args[i:i + 4]) for i in range(0, len(args), 4)] or [(15, 65536, 120, 300), (20, 32768, 90, 200), (10, 65536, 60, 200)]
     mode = os.environ.get("GRL_SOAK_RESET", "host")
     for cfg in configs:
-        print(json.dumps(soak(cuda, oracle, *cfg, mode=mode)), flush=True)
+        print(json.dumps(soak(cuda, oracle, *cfg, mode=mode, in_step=os.environ.get("GRL_SOAK_AGENT") == "in_step")), flush=True)
 
 
 if __name__ == "__main__":
