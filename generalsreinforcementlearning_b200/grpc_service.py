@@ -667,10 +667,14 @@ class GameServer:
                     oldest = oldest or time.time()
             flush = len(pending) >= size or (pending and time.time() - oldest >= wait) or (pending and not req.follow and not items)
             while flush and pending:
+                batch_id += 1                                        # experience_service.go:342: atomic.AddInt32 -> ids from 1
                 b = experience.ExperienceBatch(batch_id=batch_id, stream_id=stream_id)
                 b.experiences.extend(pending[:size])
                 _now(b.created_at)
-                pending, batch_id = pending[size:], batch_id + 1
+                b.metadata["batch_size"] = str(len(b.experiences))    # :345-347
+                if req.enable_compression:                           # :350-353: requested, not implemented by the reference
+                    b.metadata["compression"] = "none"
+                pending = pending[size:]
                 oldest = time.time() if pending else None
                 yield b
                 flush = len(pending) >= size or (pending and not req.follow and not items)

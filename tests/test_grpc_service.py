@@ -728,6 +728,88 @@ def test_reference_agent_sdk_plays_a_match_against_this_server(server):
         assert g.current_turn >= 20
 
 
+def test_reference_experience_streaming_kats(server):
+    """experience_streaming_test.go transliterated over the wire (the Go tests drive the service object with a mock
+    stream; here the same requests go through gRPC and the experiences enter the way BufferManager buffers fill:
+    through the store the collectors write to).
+    :34-116 TestStreamExperienceBatches — a FOLLOWING stream started first, 100 experiences of one game added while it
+    runs, cancelled: batches arrive, each with a stream id, a creation time and batch_id > 0 (ids count from 1,
+    experience_service.go:342), at most batch_size experiences, metadata batch_size = its length (:345-347).
+    :184-239 TestBatchProcessor — 12 experiences, batch size 5: at least two batches, none above 5, all 12 delivered.
+    :241-343 TestStreamWithFilters — two games x three players x five turns; FilterByGame sees only game-A,
+    FilterByPlayer only players 1 and 2."""
+    import threading
+    import time as _t
+    import uuid as _uuid
+
+    gs, _, xstub, _, _ = server
+
+    def follow(req, seconds):
+        got = []
+        call = xstub.StreamExperienceBatches(req)
+
+        def pump():
+            try:
+                for b in call:
+                    got.append(b)
+            except grpc.RpcError as exc:            # the cancelled stream ends the iteration
+                assert exc.code() == grpc.StatusCode.CANCELLED
+        th = threading.Thread(target=pump, daemon=True)
+        th.start()
+        return got, call, th
+
+    def exp(game_id, player, turn, reward=0.0, done=False):
+        return experience.Experience(experience_id=str(_uuid.uuid4()), game_id=game_id, player_id=player, turn=turn,
+                                     reward=reward, done=done)
+
+    # TestStreamExperienceBatches
+    got, call, th = follow(experience.StreamExperiencesRequest(game_ids=["test-game-1"], batch_size=10, follow=True), 0)
+    _t.sleep(0.1)
+    for i in range(100):
+        gs.store.add([exp("test-game-1", i % 2, i, float(i), i == 99)])
+        if i % 10 == 0:
+            _t.sleep(0.01)
+    t0 = _t.time()
+    while sum(len(b.experiences) for b in got) < 100 and _t.time() - t0 < 5:
+        _t.sleep(0.02)
+    call.cancel()
+    th.join(3)
+    assert not th.is_alive() and len(got) > 0
+    assert len({b.stream_id for b in got}) == 1 and got[0].stream_id
+    assert [b.batch_id for b in got] == list(range(1, len(got) + 1))
+    for b in got:
+        assert b.HasField("created_at") and 0 < len(b.experiences) <= 10
+        assert b.metadata["batch_size"] == str(len(b.experiences)) and "compression" not in b.metadata
+    assert [x.turn for b in got for x in b.experiences] == list(range(100))   # every experience, in order
+    assert got[-1].experiences[-1].done
+
+    # TestBatchProcessor: 12 experiences through batch size 5 (100 ms flush)
+    gs.store.add([exp("test-game", i % 2, i) for i in range(12)])
+    batches = list(xstub.StreamExperienceBatches(experience.StreamExperiencesRequest(game_ids=["test-game"], batch_size=5,
+                                                                                     enable_compression=True)))
+    assert len(batches) >= 2 and all(len(b.experiences) <= 5 for b in batches)
+    assert sum(len(b.experiences) for b in batches) == 12
+    assert all(b.metadata["compression"] == "none" for b in batches)            # experience_service.go:350-353
+
+    # TestStreamWithFilters
+    for g_id in ("game-A", "game-B"):
+        for player in (1, 2, 3):
+            gs.store.add([exp(g_id, player, turn, float(turn) * player) for turn in range(5)])
+    got, call, th = follow(experience.StreamExperiencesRequest(game_ids=["game-A"], batch_size=5, follow=True), 0)
+    _t.sleep(0.5)
+    call.cancel()
+    th.join(3)
+    xs = [x for b in got for x in b.experiences]
+    assert len(xs) == 15 and all(x.game_id == "game-A" for x in xs)
+    got, call, th = follow(experience.StreamExperiencesRequest(player_ids=[1, 2], batch_size=5, follow=True), 0)
+    _t.sleep(0.5)
+    call.cancel()
+    th.join(3)
+    xs = [x for b in got for x in b.experiences]
+    assert xs and all(x.player_id in (1, 2) for x in xs)
+    assert sum(1 for x in xs if x.game_id in ("game-A", "game-B")) == 20
+
+
 def test_more_games_than_env_slots_through_one_server(oracle_lib):
     """A gym client creates a new game on every reset() (generals_env.py:167-177): a server must outlive its pool size."""
     srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=3, seed=5, max_games=8, finished_game_ttl=600.0)
