@@ -770,7 +770,7 @@ def test_reference_experience_streaming_kats(server):
         if i % 10 == 0:
             _t.sleep(0.01)
     t0 = _t.time()
-    while sum(len(b.experiences) for b in got) < 100 and _t.time() - t0 < 5:
+    while sum(len(b.experiences) for b in got) < 100 and _t.time() - t0 < 15:
         _t.sleep(0.02)
     call.cancel()
     th.join(3)
@@ -795,19 +795,24 @@ def test_reference_experience_streaming_kats(server):
     for g_id in ("game-A", "game-B"):
         for player in (1, 2, 3):
             gs.store.add([exp(g_id, player, turn, float(turn) * player) for turn in range(5)])
+    def until(got, n, seconds=15.0):   # the Go test sleeps 500 ms; a loaded host gets as long as it needs
+        t0 = _t.time()
+        while sum(len(b.experiences) for b in got) < n and _t.time() - t0 < seconds:
+            _t.sleep(0.02)
+        _t.sleep(0.2)                  # anything beyond the expected count would arrive now
+        return [x for b in got for x in b.experiences]
+
     got, call, th = follow(experience.StreamExperiencesRequest(game_ids=["game-A"], batch_size=5, follow=True), 0)
-    _t.sleep(0.5)
+    xs = until(got, 15)
     call.cancel()
     th.join(3)
-    xs = [x for b in got for x in b.experiences]
     assert len(xs) == 15 and all(x.game_id == "game-A" for x in xs)
     got, call, th = follow(experience.StreamExperiencesRequest(player_ids=[1, 2], batch_size=5, follow=True), 0)
-    _t.sleep(0.5)
+    xs = until(got, 76)                # 20 of games A/B + player 1's 50 of test-game-1 and 6 of test-game
     call.cancel()
     th.join(3)
-    xs = [x for b in got for x in b.experiences]
     assert xs and all(x.player_id in (1, 2) for x in xs)
-    assert sum(1 for x in xs if x.game_id in ("game-A", "game-B")) == 20
+    assert sum(1 for x in xs if x.game_id in ("game-A", "game-B")) == 20 and len(xs) == 76
 
 
 def test_more_games_than_env_slots_through_one_server(oracle_lib):
