@@ -675,7 +675,7 @@ def test_reference_client_scripts_run_unmodified(oracle_lib, tmp_path):  # noqa:
 @pytest.mark.skipif(not os.path.isdir("/root/reference/python/generals_agent"), reason="the reference's agent SDK is not on this box")
 def test_reference_agent_sdk_plays_a_match_against_this_server(server):
     """BASELINE config 0's client side: two of the reference's RandomAgents (python/generals_agent: AgentRunner,
-    GameClient, GameSession, ExponentialBackoffPolling — unmodified, in their own threads) play sixty turns of a 5x5 match (or all of it, when a general falls first) against
+    GameClient, GameSession, ExponentialBackoffPolling — unmodified, in their own threads) play some thirty turns of a 5x5 match (or all of it, when a general falls first) against
     this server, as scripts/run_random_match.py does against the Go server (that script itself builds GameConfig with a
     keyword the SDK does not have and cannot start).  Every move the agents submit carries the turn number of the state
     they polled, so — unlike the gym client's — their moves are accepted turn after turn, until a general falls."""
@@ -712,9 +712,9 @@ def test_reference_agent_sdk_plays_a_match_against_this_server(server):
     import time as _t
     t0 = _t.time()
     g = gs.games[gid]
-    while _t.time() - t0 < 30 and g.phase != common.GAME_PHASE_ENDED and g.current_turn < 60:
+    while _t.time() - t0 < 30 and g.phase != common.GAME_PHASE_ENDED and g.current_turn < 32:
         _t.sleep(0.05)
-    for r in list(runners.values()):   # sixty turns are enough: the match itself may take minutes of random play
+    for r in list(runners.values()):   # some thirty turns are enough: the match itself may take minutes of random play
         r.stop()
     for th in threads:
         th.join(20)
