@@ -815,6 +815,96 @@ def test_reference_experience_streaming_kats(server):
     assert sum(1 for x in xs if x.game_id in ("game-A", "game-B")) == 20 and len(xs) == 76
 
 
+def test_reference_mutex_kats(oracle_lib):
+    """mutex_test.go transliterated (threads for goroutines).
+    :13-87 TestNoDeadlock — a manager capped at ten games; ten concurrent creators whose games are then marked idle for
+    twice the abandoned-game timeout; five cleanup passes run while another thread keeps creating and reading games:
+    everything finishes within five seconds.
+    :90-143 TestConcurrentGameAccess — ten concurrent action submissions (empty requests: the player passes) and ten
+    concurrent state reads against one running game finish within two seconds."""
+    import threading
+    import time as _t
+
+    srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=4, seed=9, max_games=10)
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    stub = Stub(ch, GAME)
+    cfg = game.GameConfig(width=10, height=10, max_players=2)
+    try:
+        def create_idle():
+            try:
+                gid = stub.CreateGame(game.CreateGameRequest(config=cfg)).game_id
+            except grpc.RpcError:
+                return                                  # at capacity: skipped, as in the Go test
+            g = gs.games[gid]
+            with g.mu:
+                g.last_activity = _t.time() - 2 * gs.abandoned_game_timeout
+
+        ths = [threading.Thread(target=create_idle) for _ in range(10)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join(5)
+        assert len(gs.games) == 10
+        removed = []
+
+        def cleaner():
+            for _ in range(5):
+                removed.append(gs.cleanup_games())
+                _t.sleep(0.01)
+
+        def creator():
+            for _ in range(5):
+                try:
+                    gid = stub.CreateGame(game.CreateGameRequest(config=cfg)).game_id
+                    g = gs.games.get(gid)
+                    if g is not None:
+                        with g.mu:
+                            _ = g.phase
+                except grpc.RpcError:
+                    pass
+                _t.sleep(0.01)
+
+        a, b = threading.Thread(target=cleaner), threading.Thread(target=creator)
+        t0 = _t.time()
+        a.start(), b.start()
+        a.join(5), b.join(5)
+        assert not a.is_alive() and not b.is_alive() and _t.time() - t0 < 5, "deadlock: cleanup did not complete"
+        assert sum(removed) >= 10 and len(gs.games) <= 5         # the ten idle games went; the new ones are active
+
+        # TestConcurrentGameAccess
+        gid = stub.CreateGame(game.CreateGameRequest(config=cfg)).game_id
+        js = [stub.JoinGame(game.JoinGameRequest(game_id=gid, player_name=n)) for n in ("alice", "bob")]
+        errors = []
+
+        def submit(i):
+            j = js[i % 2]
+            try:
+                stub.SubmitAction(game.SubmitActionRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token))
+                stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token))
+            except Exception as exc:  # noqa: BLE001
+                errors.append(repr(exc))
+
+        def read(i):
+            g = gs.games[gid]
+            with g.mu:
+                _ = (g.current_turn, g.phase)
+
+        ths = [threading.Thread(target=submit, args=(i,)) for i in range(10)] + [threading.Thread(target=read, args=(i,)) for i in range(10)]
+        t0 = _t.time()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join(2)
+        assert not any(th.is_alive() for th in ths) and _t.time() - t0 < 2, "concurrent access took too long"
+        assert not errors, errors
+        g = gs.games[gid]
+        assert g.phase == common.GAME_PHASE_RUNNING and 1 <= g.current_turn <= 5   # ten passes, two per turn at most
+    finally:
+        ch.close()
+        srv.stop(0)
+        gs.close()
+
+
 def test_more_games_than_env_slots_through_one_server(oracle_lib):
     """A gym client creates a new game on every reset() (generals_env.py:167-177): a server must outlive its pool size."""
     srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=3, seed=5, max_games=8, finished_game_ttl=600.0)
