@@ -198,6 +198,11 @@ class GameServer:
         self.lib, self.slots_per_pool, self.device, self.max_games = lib, slots_per_pool, device, max_games
         self.games: Dict[str, GameInstance] = {}
         self.pools: Dict[tuple, EnginePool] = {}
+        # The reference gives every game its own Engine: the only bound on running games is max_games
+        # (game_manager.go:104-110).  A gym client creates a new game on every reset() and abandons the old one, which
+        # the server only forgets after abandoned_game_timeout (30 min) — so when every slot of a shape's pool is held,
+        # a further pool of the same shape is created instead of refusing the game.
+        self.more_pools: Dict[tuple, List[EnginePool]] = {}
         self.next_id = 0
         self.mu = threading.Lock()
         self.store = ExperienceStore()
@@ -235,31 +240,49 @@ class GameServer:
         return game.CreateGameResponse(game_id=gid, config=cfg)
 
     def _pool_for(self, cfg) -> EnginePool:
+        """A pool of the config's shape with a free slot: the shape's first pool, one of its further pools, or — after
+        finished and abandoned games have been swept — a new one."""
         key = (cfg.width, cfg.height, cfg.max_players)
-        with self.mu:
-            if key not in self.pools:
-                self.pools[key] = EnginePool(self.lib, cfg.width, cfg.height, cfg.max_players, self.slots_per_pool, self.device)
-            return self.pools[key]
+
+        def pick():
+            with self.mu:
+                if key not in self.pools:
+                    self.pools[key] = EnginePool(self.lib, cfg.width, cfg.height, cfg.max_players, self.slots_per_pool, self.device)
+                for p in [self.pools[key]] + self.more_pools.get(key, []):
+                    if p.free:
+                        return p
+            return None
+
+        pool = pick()
+        if pool is None:
+            self.cleanup_games()
+            pool = pick()
+        if pool is None:
+            with self.mu:
+                pool = EnginePool(self.lib, cfg.width, cfg.height, cfg.max_players, self.slots_per_pool, self.device)
+                self.more_pools.setdefault(key, []).append(pool)
+        return pool
 
     def _start_engine(self, g: GameInstance, ctx):
         cfg = g.config
         if not (1 <= cfg.width <= _abi.GRL_MAX_DIM and 1 <= cfg.height <= _abi.GRL_MAX_DIM
                 and 1 <= cfg.max_players <= _abi.GRL_MAX_PLAYERS):
             ctx.abort(grpc.StatusCode.INTERNAL, f"failed to start game engine for game {g.id}: unsupported board")
-        pool = self._pool_for(cfg)
-        if not pool.free:
-            self.cleanup_games()
-        with pool.lock:
-            if not pool.free:
-                ctx.abort(grpc.StatusCode.RESOURCE_EXHAUSTED, f"failed to start game engine for game {g.id}: no free env slot")
-            g.slot = pool.free.popleft()
-            seed = (int(time.time_ns()) if self.seed is None else self.seed + self.next_id) & 0x7FFFFFFFFFFFFFFF
-            try:
-                pool.engine.reset_seeded([seed], [g.slot])
-            except RuntimeError as exc:
-                pool.free.append(g.slot)
-                ctx.abort(grpc.StatusCode.INTERNAL, f"failed to start game engine for game {g.id}: {exc}")
-            pool.refresh()
+        while True:
+            pool = self._pool_for(cfg)
+            with pool.lock:
+                if not pool.free:     # another game took the last slot between the look-up and the lock
+                    continue
+                g.slot = pool.free.popleft()
+                seed = (int(time.time_ns()) if self.seed is None else self.seed + self.next_id) & 0x7FFFFFFFFFFFFFFF
+                try:
+                    pool.engine.reset_seeded([seed], [g.slot])
+                except RuntimeError as exc:
+                    pool.free.append(g.slot)
+                    g.slot = -1
+                    ctx.abort(grpc.StatusCode.INTERNAL, f"failed to start game engine for game {g.id}: {exc}")
+                pool.refresh()
+            break
         g.pool, g.phase, g.current_turn, g.actions = pool, common.GAME_PHASE_RUNNING, 0, {}
         g.started_at = g.last_activity = time.time()
         g.prev_alive = [True] * cfg.max_players
@@ -494,27 +517,40 @@ class GameServer:
         with self.mu:
             refs = list(self.games.items())
         drop = []
+        # A sweep can run on a request thread that already holds ITS game's lock (a JoinGame that found every slot
+        # taken): a game whose lock is busy is in use — it is left for the next sweep instead of being waited for, so two
+        # such threads cannot wait for each other.
         for gid, g in refs:
-            with g.mu:
+            if not g.mu.acquire(timeout=0.05):
+                continue
+            try:
                 idle = now - g.last_activity
                 if (g.phase == common.GAME_PHASE_ENDED and idle > self.finished_game_ttl) or \
                         (g.phase != common.GAME_PHASE_ENDED and idle > self.abandoned_game_timeout):
                     drop.append((gid, g))
+            finally:
+                g.mu.release()
+        dropped = []
         for gid, g in drop:
-            with g.mu:
+            if not g.mu.acquire(timeout=0.05):
+                continue
+            try:
                 if g.timer:
                     g.timer.cancel()
                 if g.phase != common.GAME_PHASE_ENDED:
                     g.phase = common.GAME_PHASE_ENDED     # an abandoned game stops accepting actions
                 self._release_slot(g)
                 g.idempotency.clear()
+                dropped.append((gid, g))
+            finally:
+                g.mu.release()
             with g.stream_cv:                              # StreamManager.CloseAll
                 g.streams.clear()
                 g.stream_cv.notify_all()
         with self.mu:
-            for gid, _ in drop:
+            for gid, _ in dropped:
                 self.games.pop(gid, None)
-        return len(drop)
+        return len(dropped)
 
     def _collect(self, g, prev_obs, prev_mask, over):
         """SimpleCollector.OnStateTransition (collector.go:30-98)."""
@@ -764,7 +800,7 @@ class GameServer:
         for g in self.games.values():
             if g.timer:
                 g.timer.cancel()
-        for p in self.pools.values():
+        for p in list(self.pools.values()) + [q for ps in self.more_pools.values() for q in ps]:
             p.engine.close()
 
 

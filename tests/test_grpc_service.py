@@ -672,6 +672,58 @@ def test_reference_client_scripts_run_unmodified(oracle_lib, tmp_path):  # noqa:
         gs.close()
 
 
+@pytest.mark.skipif(not os.path.isfile("/root/reference/python/test_gym_env.py"), reason="the reference's scripts are not on this box")
+def test_more_reference_scripts_run_unmodified(oracle_lib, tmp_path):
+    """python/test_gym_env.py (GeneralsEnv: reset, steps, action masks, observation channels), python/simple_game_client.py
+    (a demo match with board rendering) and python/examples/test_experience_collection.py (a game with
+    collect_experiences, ten turns of moves from both players, GetExperienceStats and StreamExperiences) — run as they
+    are against this server on localhost:50051.  The last one ends in the script's own `sys.exit` without `import sys`
+    after it has printed its verdict; python/simple_experience_test.py cannot run against any server (it reads
+    game_pb2.ActionType, which the reference's stubs do not have)."""
+    import subprocess
+    import sys
+
+    try:
+        srv, gs, port = serve("localhost:50051", lib=oracle_lib, slots_per_pool=4, seed=7)
+    except Exception as exc:   # the port is taken on this machine
+        pytest.skip(f"cannot listen on localhost:50051: {exc}")
+    if port != 50051:
+        srv.stop(0)
+        gs.close()
+        pytest.skip("cannot listen on localhost:50051")
+    stub_pkg = tmp_path / "gymnasium"
+    stub_pkg.mkdir()
+    (stub_pkg / "__init__.py").write_text(
+        "from . import spaces\n"
+        "class Env:\n    def reset(self, seed=None, options=None):\n        return None\n"
+        "def register(**kw):\n    pass\n")
+    (stub_pkg / "spaces.py").write_text(
+        "class Box:\n    def __init__(self, low, high, shape, dtype):\n"
+        "        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype\n"
+        "class Discrete:\n    def __init__(self, n):\n        self.n = int(n)\n")
+    envv = dict(os.environ, PYTHONPATH=f"{tmp_path}:/root/reference/python", PYTHONDONTWRITEBYTECODE="1")
+    try:
+        for script, rcs, needles in (
+                ("test_gym_env.py", (0,), ["Game server is running", "Environment created successfully", "Reset successful",
+                                           "All tests passed!", "Environment closed successfully", "Observation channels test complete"]),
+                ("simple_game_client.py", (0,), ["Demo complete!"]),
+                ("examples/test_experience_collection.py", (0, 1), ["Experiences collected: 20",
+                                                                    "SUCCESS: Experience collection is working!", "Experience 1: Player 0"])):
+            proc = subprocess.run([sys.executable, script], cwd="/root/reference/python", env=envv, stdout=subprocess.PIPE,
+                                  stderr=subprocess.STDOUT, text=True, timeout=120)
+            assert proc.returncode in rcs, proc.stdout[-2000:]
+            if proc.returncode == 1:
+                assert "NameError: name 'sys' is not defined" in proc.stdout, proc.stdout[-2000:]
+            for needle in needles:
+                assert needle in proc.stdout, f"{script}: {needle!r} missing from\n{proc.stdout[-2000:]}"
+            assert "✗" not in proc.stdout and "Error during step" not in proc.stdout, proc.stdout[-2000:]
+        # the scripts abandoned more running games than one pool has slots: the pools grew instead of refusing them
+        assert gs.more_pools
+    finally:
+        srv.stop(0)
+        gs.close()
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/python/generals_agent"), reason="the reference's agent SDK is not on this box")
 def test_reference_agent_sdk_plays_a_match_against_this_server(server):
     """BASELINE config 0's client side: two of the reference's RandomAgents (python/generals_agent: AgentRunner,
@@ -939,6 +991,37 @@ def test_more_games_than_env_slots_through_one_server(oracle_lib):
         assert gs.cleanup_games(_t.time() + 1801.0) == 4
         assert len(gs.pools[(5, 5, 2)].free) == 3 and not gs.games
         _play_duel(gs, stub)
+    finally:
+        ch.close()
+        srv.stop(0)
+        gs.close()
+
+
+def test_more_running_games_than_slots_grow_the_pool(oracle_lib):
+    """The reference gives every game its own Engine; only max_games bounds the running games (game_manager.go:104-110).
+    A gym client abandons its game at every reset() and the server forgets it only after 30 minutes, so a pool whose
+    slots are all held grows by another pool of the same shape instead of refusing the game: seven running games
+    through pools of three slots, every one of them playable, and their slots return when they are swept."""
+    import time as _t
+
+    srv, gs, port = serve("127.0.0.1:0", lib=oracle_lib, slots_per_pool=3, seed=5)
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    stub = Stub(ch, GAME)
+    try:
+        started = [_start(stub, 5, 5) for _ in range(7)]
+        assert len(gs.more_pools[(5, 5, 2)]) == 2 and not gs.pools[(5, 5, 2)].free
+        used = {(id(gs.games[gid].pool), gs.games[gid].slot) for gid, _ in started}
+        assert len(used) == 7, "every running game has a slot of its own"
+        for gid, js in started:                                   # both players pass: the turn runs in every game
+            for j in js:
+                r = stub.SubmitAction(game.SubmitActionRequest(game_id=gid, player_id=j.player_id, player_token=j.player_token))
+                assert r.success
+            st = stub.GetGameState(game.GetGameStateRequest(game_id=gid, player_id=0, player_token=js[0].player_token)).state
+            assert st.turn == 1 and st.status == common.GAME_STATUS_IN_PROGRESS and len(st.board.tiles) == 25
+        assert gs.cleanup_games(_t.time() + gs.abandoned_game_timeout + 1) == 7 and not gs.games
+        assert len(gs.pools[(5, 5, 2)].free) == 3 and all(len(p.free) == 3 for p in gs.more_pools[(5, 5, 2)])
+        _play_duel(gs, stub)                                      # and the first pool serves the next game
+        assert len(gs.more_pools[(5, 5, 2)]) == 2
     finally:
         ch.close()
         srv.stop(0)
