@@ -326,12 +326,18 @@ class GameServer:
         key = (req.player_id, req.idempotency_key)
 
         def done(resp):
-            if req.idempotency_key:
-                g.idempotency[key] = resp
+            if req.idempotency_key:                     # IdempotencyManager.Store (idempotency.go:62-85)
+                now = time.time()
+                g.idempotency[key] = (resp, now)
+                if len(g.idempotency) > 1000:           # :81-84: entries older than 24 h leave once the cache is large
+                    for k in [k for k, (_, t0) in g.idempotency.items() if now - t0 > 86400.0]:
+                        del g.idempotency[k]
             return resp
 
-        if req.idempotency_key and key in g.idempotency:
-            return g.idempotency[key]
+        if req.idempotency_key and key in g.idempotency:   # IdempotencyManager.Check (:36-60): valid for 24 hours
+            cached, t0 = g.idempotency[key]
+            if time.time() - t0 <= 86400.0:
+                return cached
         if g.phase != common.GAME_PHASE_RUNNING:
             code = common.ERROR_CODE_GAME_OVER if g.phase == common.GAME_PHASE_ENDED else common.ERROR_CODE_INVALID_PHASE
             return done(game.SubmitActionResponse(

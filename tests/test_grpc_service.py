@@ -997,6 +997,27 @@ def test_more_games_than_env_slots_through_one_server(oracle_lib):
         gs.close()
 
 
+def test_idempotency_entries_expire_after_a_day(server):
+    """IdempotencyManager.Check (idempotency.go:36-60): a cached response answers a repeated key for 24 hours; after that
+    the request is processed again."""
+    import time as _t
+
+    gs, stub, _, _, _ = server
+    gid, js = _start(stub, 5, 5)
+    req = game.SubmitActionRequest(game_id=gid, player_id=0, player_token=js[0].player_token, idempotency_key="k-1")
+    assert stub.SubmitAction(req).success
+    assert stub.SubmitAction(game.SubmitActionRequest(game_id=gid, player_id=1, player_token=js[1].player_token)).success
+    g = gs.games[gid]
+    assert g.current_turn == 1
+    req.action.type, req.action.turn_number = common.ACTION_TYPE_MOVE, 0      # a stale move under the same key
+    getattr(req.action, "from").x = 0
+    assert stub.SubmitAction(req).success, "within 24 h the cached response answers, whatever the request now says"
+    resp, t0 = g.idempotency[(0, "k-1")]
+    g.idempotency[(0, "k-1")] = (resp, t0 - 86401.0)
+    r = stub.SubmitAction(req)
+    assert not r.success and r.error_code == common.ERROR_CODE_INVALID_TURN, "an expired entry does not answer"
+
+
 def test_more_running_games_than_slots_grow_the_pool(oracle_lib):
     """The reference gives every game its own Engine; only max_games bounds the running games (game_manager.go:104-110).
     A gym client abandons its game at every reset() and the server forgets it only after 30 minutes, so a pool whose
