@@ -685,7 +685,14 @@ class GameServer:
             return False
         return x.turn >= req.min_turn
 
+    @staticmethod
+    def _validate_stream_request(req, ctx):
+        """validateStreamRequest (experience_service.go:510-520), reported as :161-163 / :292-294 do."""
+        if req.batch_size > 1000:
+            ctx.abort(grpc.StatusCode.INVALID_ARGUMENT, "invalid request: batch size too large (max 1000)")
+
     def StreamExperiences(self, req, ctx):
+        self._validate_stream_request(req, ctx)
         cursor = 0
         while ctx.is_active():
             items, cursor = self.store.read_from(cursor, 0.1)
@@ -696,6 +703,7 @@ class GameServer:
                 return
 
     def StreamExperienceBatches(self, req, ctx):
+        self._validate_stream_request(req, ctx)
         size = req.batch_size if req.batch_size > 0 else 32          # experience_service.go:510-514
         wait = (req.max_batch_wait_ms if req.max_batch_wait_ms > 0 else 100) / 1000.0
         stream_id, batch_id, cursor = str(uuid.uuid4()), 0, 0
@@ -724,9 +732,22 @@ class GameServer:
                 return
 
     def SubmitExperiences(self, req, ctx):
+        # experience_service.go:381-448: the request-level checks abort, an invalid experience (validateExperience,
+        # :522-540) is counted as rejected.  Beyond the reference, an experience_id already submitted is rejected as the
+        # duplicate the proto's `rejected` field names (experience.proto:103).
+        if len(req.experiences) == 0:
+            ctx.abort(grpc.StatusCode.INVALID_ARGUMENT, "no experiences provided")
+        if len(req.experiences) > 1000:
+            ctx.abort(grpc.StatusCode.INVALID_ARGUMENT, "too many experiences (max 1000)")
+        if not req.experiences[0].game_id:
+            ctx.abort(grpc.StatusCode.INVALID_ARGUMENT, "game ID required")
         accepted = rejected = 0
         fresh = []
         for x in req.experiences:
+            if not x.game_id or not x.HasField("state") or not x.HasField("next_state") or \
+                    len(x.state.data) == 0 or len(x.next_state.data) == 0:
+                rejected += 1
+                continue
             if x.experience_id and x.experience_id in self.submitted_ids:
                 rejected += 1
                 continue

@@ -226,6 +226,21 @@ def _experience_stream_records(server, oracle_lib):
     assert stats.total_experiences == 23 and stats.total_games == 1 and stats.experiences_per_player[0] == 12
     dup = xstub.SubmitExperiences(experience.SubmitExperiencesRequest(experiences=got[:3] + got[:1]))
     assert (dup.accepted, dup.rejected) == (3, 1)
+    # experience_service.go:381-448, 522-540: request-level checks abort, invalid experiences are counted as rejected
+    for bad, msg in ((experience.SubmitExperiencesRequest(), "no experiences provided"),
+                     (experience.SubmitExperiencesRequest(experiences=[experience.Experience(player_id=1)]), "game ID required"),
+                     (experience.SubmitExperiencesRequest(experiences=[experience.Experience(game_id="g")] * 1001), "too many experiences (max 1000)")):
+        with pytest.raises(grpc.RpcError) as e:
+            xstub.SubmitExperiences(bad)
+        assert e.value.code() == grpc.StatusCode.INVALID_ARGUMENT and e.value.details() == msg
+    stateless = experience.Experience(game_id=gid, player_id=0)
+    empty = experience.Experience(game_id=gid, player_id=0)
+    empty.state.shape.extend([9, 6, 6]), empty.next_state.shape.extend([9, 6, 6])
+    r = xstub.SubmitExperiences(experience.SubmitExperiencesRequest(experiences=[stateless, empty]))
+    assert (r.accepted, r.rejected) == (0, 2)
+    with pytest.raises(grpc.RpcError) as e:   # validateStreamRequest :510-520
+        list(xstub.StreamExperienceBatches(experience.StreamExperiencesRequest(batch_size=1001)))
+    assert e.value.code() == grpc.StatusCode.INVALID_ARGUMENT and e.value.details() == "invalid request: batch size too large (max 1000)"
 
 
 def test_stream_game_updates(server):
