@@ -198,9 +198,16 @@ class ReplayBuffer:
             if batch_size > self._size:
                 raise ValueError("Sample larger than population or is negative")   # what random.sample raises
             size, shift = self._size, 0
-            if self._pending is not None and self._size == self.capacity:
+            if self._pending is not None:
                 # the rows of a step in flight hold a new state but the old action/reward: sample the others
-                shift, size = (self._pending[0] + self._pending[1]) % self.capacity, self.capacity - self._pending[1]
+                end = self._pending[0] + self._pending[1]
+                if self._size == self.capacity:
+                    shift, size = end % self.capacity, self.capacity - self._pending[1]
+                elif end > self.capacity:
+                    # a ring that is not full yet whose step in flight already wraps (capacity not a multiple of the
+                    # vector step): its first rows, complete transitions of the oldest step, have new states too
+                    shift = end - self.capacity
+                    size = self._size - shift
                 if batch_size > size:
                     raise ValueError("Sample larger than population or is negative")
             if size <= (1 << 16) or 4 * batch_size > size:

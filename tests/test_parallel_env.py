@@ -153,6 +153,32 @@ def test_pool_transitions_are_consistent(oracle_lib):
     assert a["results"] == b2["results"]
 
 
+def test_sampling_skips_the_rows_of_a_step_in_flight_that_wraps_before_the_ring_is_full():
+    """A ring whose capacity is not a multiple of the vector step: the third step of four envs into ten rows writes its
+    states into rows 8, 9, 0, 1 while the ring holds only eight transitions — rows 0 and 1 then pair a new state with
+    the first step's action until the step is finished, and must not be sampled meanwhile."""
+    import torch
+
+    buf = ReplayBuffer(capacity=10)
+    mk = lambda step: (torch.full((4, 3), float(step)), torch.full((4,), step, dtype=torch.int64),
+                       torch.full((4,), float(step)), torch.full((4, 3), float(step)), torch.zeros(4, dtype=torch.bool))
+    for step in (1, 2):
+        s, a, r, ns, d = mk(step)
+        buf.finish_step(buf.begin_step(s), a, r, ns, d)
+    assert len(buf) == 8
+    s, a, r, ns, d = mk(3)
+    ticket = buf.begin_step(s)
+    for _ in range(20):
+        bs, ba, br, bns, bd = buf.sample_tensors(6)
+        assert torch.equal(bs[:, 0].to(torch.int64), ba), "a sampled row pairs its own state with its own action"
+    with pytest.raises(ValueError):
+        buf.sample_tensors(7)                       # six complete rows are readable while the step is in flight
+    buf.finish_step(ticket, a, r, ns, d)
+    assert len(buf) == 10
+    bs, ba, *_ = buf.sample_tensors(10)
+    assert torch.equal(bs[:, 0].to(torch.int64), ba) and sorted(ba.tolist()) == [1, 1, 2, 2, 2, 2, 3, 3, 3, 3]
+
+
 def test_pool_random_agent_in_step_equals_sampler(oracle_lib):
     """batch_action_fn=RANDOM_AGENT (the agent drawn inside grl_gym_step) collects the very rows — states, actions,
     rewards, next states, done flags, episode results — that batch_action_fn=vec.sample_actions() does."""
