@@ -138,3 +138,16 @@ def product_lib_expand(lib, W, H, P, packed):
     got = np.empty((packed.shape[0], P, 9, H, W), np.float32)
     assert lib.expand_obs(W, H, P, packed.ctypes.data, packed.shape[0], got.ctypes.data, 0) == 0
     return got
+
+
+def test_graft_entry_build_runs():
+    """The driver's "does it build" check: __graft_entry__.build() compiles whatever is stale (nothing, normally), loads
+    the library and compares its ABI version with the header's."""
+    import importlib
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    entry = importlib.import_module("__graft_entry__")
+    entry.build()
