@@ -129,9 +129,10 @@ class GeneralsVecEnv:
 
     # ------------------------------------------------------------------ gym API
     def reset(self, seed: Optional[int] = None, options=None) -> Tuple[Any, Dict[str, Any]]:
-        if seed is not None:
+        if seed is not None:   # a seeded reset restarts every random stream: maps, the opponent's and the agent's draws
             self._base_seed = int(seed)
             self._gen.manual_seed(int(seed))
+            self._opp_draws = self._sample_draws = 0
         self._episode[:] = 0
         if self.auto_reset != "host_reset":
             self._episode_dev.zero_()

@@ -348,6 +348,29 @@ def test_cuda_random_agent_step_matches_sampler_and_oracle(cuda_lib, oracle_lib,
         e.close()
 
 
+def test_seeded_reset_replays_the_same_episode(oracle_lib):
+    """reset(seed=s) restarts the maps and both random streams (the opponent's and the in-step agent's draws): the same
+    env replays the same trajectory; another seed does not."""
+    import torch
+
+    from generalsreinforcementlearning_b200.gym_env import GeneralsVecEnv
+
+    env = GeneralsVecEnv(24, 8, 8, max_turns=9, seed=1, lib=oracle_lib, host_threads=1, auto_reset="device")
+
+    def run(seed):
+        obs, _ = env.reset(seed=seed)
+        trace = [obs.clone()]
+        for _ in range(25):
+            obs, r, te, tr, info = env.step(None)
+            trace += [obs.clone(), r.clone(), te.clone(), tr.clone(), info["action"].clone()]
+        return trace
+
+    a, b, c = run(5), run(5), run(6)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert not all(torch.equal(x, y) for x, y in zip(a, c))
+    env.close()
+
+
 def _random_agent_call(lib, P, sampled):
     import torch
 
