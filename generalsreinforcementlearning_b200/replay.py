@@ -91,7 +91,9 @@ def replay(engine: BatchedEngine, path: str, until: Optional[int] = None) -> int
     meta, actions = load_replay(path)
     if meta.get("format") != FORMAT_VERSION:
         raise ValueError(f"replay format {meta.get('format')} (this codec reads format {FORMAT_VERSION})")
-    if meta["abi"] != int(engine.lib.abi_version()):
+    # ABI revisions only ADD entry points and trailing struct fields (include/grlcuda.h): a recording made with an older
+    # revision replays on a newer library — its digests catch any drift — but not the other way round
+    if meta["abi"] > int(engine.lib.abi_version()):
         raise ValueError(f"replay was recorded with ABI version {meta['abi']}, engine library has {int(engine.lib.abi_version())}")
     have = _config_of(engine)
     diff = {k: (meta["config"].get(k), have[k]) for k in _CONFIG_KEYS if meta["config"].get(k) != have[k]}

@@ -174,9 +174,23 @@ def test_replay_and_state_codec_roundtrip(oracle_lib, tmp_path):
     for other in (dict(fog_of_war=0), dict(normal_growth_interval=10), dict(env_id_base=5), dict(production_city=2)):
         with pytest.raises(ValueError, match="different configuration"):
             replay.replay(new_engine(oracle_lib, 10, 10, 2, B, **other), path)
+    # a recording of an OLDER ABI revision replays (revisions only add), one of a newer revision is refused
+    import io, json, zipfile
+
+    def rewrite(name, **changes):
+        out = str(tmp_path / name)
+        buf = io.BytesIO()
+        np.save(buf, actions)
+        with zipfile.ZipFile(out, "w") as z:
+            z.writestr("meta.json", json.dumps(dict(meta, **changes)))
+            z.writestr("actions.npy", buf.getvalue())
+        return out
+
+    assert replay.replay(new_engine(oracle_lib, 10, 10, 2, B), rewrite("older.grlreplay", abi=meta["abi"] - 1)) == 45
+    with pytest.raises(ValueError, match="ABI version"):
+        replay.replay(new_engine(oracle_lib, 10, 10, 2, B), rewrite("newer.grlreplay", abi=meta["abi"] + 1))
     # a tampered action stream is caught by the recorded digests
     actions[5, 0, 0, 3] ^= 1
-    import io, json, zipfile
     bad = str(tmp_path / "bad.grlreplay")
     buf = io.BytesIO()
     np.save(buf, actions)
