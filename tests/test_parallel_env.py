@@ -179,6 +179,35 @@ def test_sampling_skips_the_rows_of_a_step_in_flight_that_wraps_before_the_ring_
     assert torch.equal(bs[:, 0].to(torch.int64), ba) and sorted(ba.tolist()) == [1, 1, 2, 2, 2, 2, 3, 3, 3, 3]
 
 
+def test_sampled_rows_are_always_whole_transitions():
+    """Whatever the capacity / vector-step ratio and whenever sample() is called — between steps or while one is in
+    flight — a sampled row pairs the state, action, reward and next state of ONE transition, and the readable population
+    is exactly the finished transitions still in the ring."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        n = int(rng.integers(1, 7))
+        cap = int(rng.integers(n, 4 * n + 3))
+        buf = ReplayBuffer(capacity=cap, device="cpu")
+        buf.seed(int(rng.integers(1 << 30)))
+        for step in range(1, 14):
+            s = torch.full((n, 2), float(step))
+            ticket = buf.begin_step(s)
+            readable = min(len(buf), cap - n) if len(buf) + n > cap else len(buf)   # rows the step in flight does not touch
+            if readable:
+                bs, ba, br, bns, _ = buf.sample_tensors(readable)
+                assert torch.equal(bs[:, 0].to(torch.int64), ba) and torch.equal(bns[:, 0], br), (cap, n, step)
+                assert int(ba.max()) < step
+            with pytest.raises(ValueError):
+                buf.sample_tensors(readable + 1)
+            buf.finish_step(ticket, torch.full((n,), step, dtype=torch.int64), torch.full((n,), float(step)),
+                            torch.full((n, 2), float(step)), torch.zeros(n, dtype=torch.bool))
+            bs, ba, br, bns, _ = buf.sample_tensors(len(buf))
+            assert torch.equal(bs[:, 0].to(torch.int64), ba) and torch.equal(bns[:, 0], br), (cap, n, step)
+            assert len(buf) == min(cap, step * n)
+
+
 def test_pool_random_agent_in_step_equals_sampler(oracle_lib):
     """batch_action_fn=RANDOM_AGENT (the agent drawn inside grl_gym_step) collects the very rows — states, actions,
     rewards, next states, done flags, episode results — that batch_action_fn=vec.sample_actions() does."""
