@@ -208,6 +208,35 @@ def test_sampled_rows_are_always_whole_transitions():
             assert len(buf) == min(cap, step * n)
 
 
+def test_sampled_rows_are_whole_transitions_on_the_kernel_path():
+    """The same invariant for the pool's path over grl_replay_push_rows (its two row streams emulated with index
+    writes): a step's pass writes the next_states of the n rows at write_row and the states of the n rows after them;
+    commit_vector_step publishes the former and keeps the latter — new states under old actions — away from sample()."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    for _ in range(40):
+        n = int(rng.integers(1, 7))
+        cap = int(rng.integers(2 * n, 5 * n + 3))
+        buf = ReplayBuffer(capacity=cap, device="cpu")
+        buf.seed(int(rng.integers(1 << 30)))
+        buf.ensure_storage((2,), torch.device("cpu"))
+        rows = lambda r0: (r0 + torch.arange(n)) % cap   # noqa: E731
+        buf._states[rows(buf.write_row)] = 1.0                                   # the states of the first transitions
+        for step in range(1, 14):
+            w = buf.write_row
+            buf._next_states[rows(w)] = float(step)                              # one pass: next_states of this step ...
+            buf._states[rows(w + n)] = float(step + 1)                           # ... and states of the next one
+            buf.commit_vector_step(n, torch.full((n,), step, dtype=torch.int64), torch.full((n,), float(step)),
+                                   torch.zeros(n, dtype=torch.bool))
+            readable = min(step * n, cap - n)
+            assert len(buf) == min(cap, step * n)
+            bs, ba, br, bns, _ = buf.sample_tensors(readable)
+            assert torch.equal(bs[:, 0].to(torch.int64), ba) and torch.equal(bns[:, 0], br), (cap, n, step)
+            with pytest.raises(ValueError):
+                buf.sample_tensors(readable + 1)
+
+
 def test_pool_random_agent_in_step_equals_sampler(oracle_lib):
     """batch_action_fn=RANDOM_AGENT (the agent drawn inside grl_gym_step) collects the very rows — states, actions,
     rewards, next states, done flags, episode results — that batch_action_fn=vec.sample_actions() does."""
